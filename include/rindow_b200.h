@@ -1,0 +1,173 @@
+/*
+ * rindow_b200.h -- C ABI of librindow_b200.so, the B200 (sm_100a) compute driver for
+ * rindow-math-matrix.
+ *
+ * This is the drop-in boundary: the entry points below are what a
+ * PHP-FFI (`FFI::cdef`) shim class -- MatlibCuda\{CudaBlas,CudaMath,CudaBuffer} plugged
+ * into Rindow\Math\Matrix\Drivers\Service (reference src/Drivers/Service.php:4-26) via
+ * AbstractMatlibService's three factories (src/Drivers/AbstractMatlibService.php:43-75)
+ * -- binds, one per reference driver method on the hot path.  In this repository the
+ * same ABI is bound by ctypes (rindow_math_matrix_b200/_capi.py), because the image has
+ * no PHP; php/MatlibCuda holds the PHP side a maintainer would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and 64-bit sizes; no C++/torch types; no callbacks.
+ *  - every function returns 0 on success and a negative rb200 status on failure;
+ *    rb200_last_error() gives the message (thread-local).  No C++ exception crosses.
+ *  - device pointers are plain `void*` from rb200_buffer_alloc (or any cudaMalloc'd /
+ *    torch-owned allocation on the current device).  Offsets `off*`, leading dimensions
+ *    `ld*` and increments `inc*` are in ELEMENTS, exactly as in the reference driver
+ *    signatures; rb200_buffer_* offsets are in BYTES like the reference's DeviceBuffer
+ *    (src/NDArrayCL.php:261-270).
+ *  - all compute calls are asynchronous on the library stream (rb200_set_stream to
+ *    adopt the caller's); rb200_sync() before the host reads results.  Buffer h2d/d2h
+ *    are synchronous on return.
+ *  - argument VALIDATION with the reference's exact exception strings lives in the host
+ *    shim (Utils.php:30-65 semantics); the ABI re-checks only what would make the
+ *    device code fault (null pointers, non-positive sizes, unsupported dtype).
+ *  - not re-entrant: one host thread drives one device (PHP CLI is single-threaded,
+ *    PhpBlas.php:49-54 reports 1 thread).  One process per GPU for multi-GPU.
+ */
+#ifndef RINDOW_B200_H_
+#define RINDOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB200_ABI_VERSION 1
+
+/* status codes */
+#define RB200_OK              0
+#define RB200_E_INVALID      -1   /* bad argument (host shim should have thrown InvalidArgumentException) */
+#define RB200_E_CUDA         -2   /* CUDA runtime/driver error; message in rb200_last_error() */
+#define RB200_E_UNSUPPORTED  -3   /* dtype / mode not supported by this entry point */
+#define RB200_E_NOTINIT      -4   /* rb200_init not called or no device */
+#define RB200_E_NOMEM        -5
+
+/* dtype codes.  The ABI owns this enum; the host shim maps Interop\Polite\Math\Matrix\
+ * NDArray::float32 etc. to it symbolically in one table (the polite-math constant values
+ * are not vendored under the reference). */
+#define RB200_BOOL      0
+#define RB200_INT8      1
+#define RB200_INT16     2
+#define RB200_INT32     3
+#define RB200_INT64     4
+#define RB200_UINT8     5
+#define RB200_UINT16    6
+#define RB200_UINT32    7
+#define RB200_UINT64    8
+#define RB200_FLOAT32   12
+#define RB200_FLOAT64   13
+
+/* CBLAS-valued enums (reference: Interop\Polite\Math\Matrix\BLAS; LinearAlgebra.php:16-17) */
+#define RB200_ROW_MAJOR      101
+#define RB200_COL_MAJOR      102
+#define RB200_NO_TRANS       111
+#define RB200_TRANS          112
+#define RB200_CONJ_TRANS     113
+#define RB200_CONJ_NO_TRANS  114
+
+/* sgemm arithmetic modes (BASELINE.json north_star: "TF32 or 3xTF32 mode ... plus FFMA") */
+#define RB200_GEMM_AUTO      0    /* library default: see rb200_set_default_gemm_mode */
+#define RB200_GEMM_FP32_SIMT 1    /* FFMA, fp32 accumulate, any shape/stride */
+#define RB200_GEMM_TF32      2    /* tcgen05 kind::tf32, 1 pass  (max rel err ~1e-3 of max|C|) */
+#define RB200_GEMM_TF32X3    3    /* tcgen05 kind::tf32, 3 passes hi/lo split (~fp32 accuracy) */
+
+/* ---- library / device ------------------------------------------------------------- */
+int         rb200_abi_version(void);
+const char* rb200_last_error(void);
+int         rb200_device_count(int* count);
+/* Select `device`, create the library stream, query SM count.  Idempotent per device. */
+int         rb200_init(int device);
+int         rb200_shutdown(void);
+int         rb200_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor,
+                              int64_t* total_mem_bytes);
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the
+ * library-owned stream. */
+int         rb200_set_stream(void* cuda_stream);
+int         rb200_get_stream(void** cuda_stream);
+int         rb200_sync(void);
+int         rb200_set_default_gemm_mode(int mode);
+int         rb200_get_default_gemm_mode(int* mode);
+/* How many kernels this library has launched since init / since the last reset
+ * (bench.py's "gpu_launches"). */
+int         rb200_launch_count(int64_t* count, int reset);
+/* Name of the kernel family the last rb200_sgemm/dgemm dispatched to
+ * ("tcgen05_tf32", "tcgen05_tf32x3", "simt_f32", "simt_f64"). */
+const char* rb200_last_gemm_path(void);
+
+/* ---- buffers: replaces PhpBLASFactory::Buffer (PhpBLASFactory.php:35) storage and the
+ *      DeviceBuffer read/write/copy/fill calls of NDArrayCL (NDArrayCL.php:147-168,
+ *      252-272, 390-442) ------------------------------------------------------------- */
+int rb200_buffer_alloc(int64_t bytes, void** dptr);
+int rb200_buffer_free(void* dptr);
+int rb200_buffer_h2d(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes);
+int rb200_buffer_d2h(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes);
+int rb200_buffer_h2d_async(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes);
+int rb200_buffer_d2h_async(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes);
+int rb200_buffer_d2d(void* dst, int64_t dst_offset_bytes, const void* src, int64_t src_offset_bytes,
+                     int64_t bytes);
+/* fill n elements of `dtype` starting at element offset `off` with *value (value points to
+ * one element of that dtype on the host).  Replaces PhpMath::fill (PhpMath.php:2811) /
+ * zeros (:908) for the alloc+zeros every LinearAlgebra::gemm/im2col does. */
+int rb200_buffer_fill(int dtype, void* dptr, int64_t off, int64_t n, const void* value);
+/* pinned host staging memory for the host-indexable mirror of an LV_ADVANCED buffer */
+int rb200_host_alloc(int64_t bytes, void** hptr);
+int rb200_host_free(void* hptr);
+
+/* ---- BLAS: replaces PhpBlas::gemm (src/Drivers/MatlibPHP/PhpBlas.php:849-948) ------- */
+/* C[m,n] = alpha * op(A)[m,k] * op(B)[k,n] (+ beta * C iff beta != 0; C is not read when
+ * beta == 0, PhpBlas.php:940-944).  Row-major fast path; RB200_COL_MAJOR swaps m,n like
+ * PhpBlas.php:862-863.  ConjTrans == Trans, ConjNoTrans == NoTrans for real dtypes
+ * (PhpBlas.php:104-123). */
+int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                float alpha, const float* A, int64_t offA, int64_t ldA,
+                const float* B, int64_t offB, int64_t ldB,
+                float beta, float* C, int64_t offC, int64_t ldC, int mode);
+int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                double alpha, const double* A, int64_t offA, int64_t ldA,
+                const double* B, int64_t offB, int64_t ldB,
+                double beta, double* C, int64_t offC, int64_t ldC);
+
+/* ---- Math: replaces PhpMath::add / multiply (PhpMath.php:570-606 / 530-565) ---------- */
+/* trans==0: A[i,j] = alpha*X[j] + A[i,j]  (i<m, j<n, X has n elements)
+ * trans!=0: A[i,j] = alpha*X[i] + A[i,j]  (X has m elements); A is m x n with row stride ldA */
+int rb200_add(int dtype, int trans, int64_t m, int64_t n, double alpha,
+              const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,
+                   const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+
+/* ---- reductions over the middle axis of A[m,n,k] -> B[m,k]
+ *      replaces PhpMath::reduceSum/reduceMax/reduceArgMax (PhpMath.php:1552-1643) ------- */
+int rb200_reduce_sum(int dtype, int64_t m, int64_t n, int64_t k,
+                     const void* A, int64_t offA, void* B, int64_t offB);
+/* NaN-sticky (any NaN in the reduced run gives NaN): the rule the reference pins for its
+ * accelerated drivers (LinearAlgebraTest.php:7617-7643, OpenCLMath.php:142-157); equals
+ * PhpMath::math_max (:95-112) on NaN-free data and on rows whose only NaN is last. */
+int rb200_reduce_max(int dtype, int64_t m, int64_t n, int64_t k,
+                     const void* A, int64_t offA, void* B, int64_t offB);
+/* index of the first strict maximum (ties -> lowest index, NaN never wins, NaN at 0
+ * sticks): PhpMath::math_imax (:114-130).  index_dtype: RB200_INT32 or RB200_INT64. */
+int rb200_reduce_argmax(int dtype, int64_t m, int64_t n, int64_t k,
+                        const void* A, int64_t offA, int index_dtype, void* B, int64_t offB);
+
+/* ---- softmax: replaces PhpMath::softmax (PhpMath.php:1645-1670); in place, row stride ldA */
+int rb200_softmax(int dtype, int64_t m, int64_t n, void* A, int64_t offA, int64_t ldA);
+
+/* ---- im2col2d / col2im: replaces PhpMath::im2col2d (PhpMath.php:2158-2314), same 20
+ *      arguments in the same order (buffers become pointer + dtype) ---------------------- */
+int rb200_im2col2d(int dtype, int reverse,
+                   void* images, int64_t images_offset, int64_t images_size,
+                   int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                   int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                   int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
+                   int cols_channels_first,
+                   void* cols, int64_t cols_offset, int64_t cols_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RINDOW_B200_H_ */

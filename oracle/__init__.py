@@ -1,0 +1,170 @@
+"""CPU oracle -- TEST INFRASTRUCTURE ONLY (see oracle/rindow_oracle.c header).
+
+ctypes binding of oracle/liboracle.so, the C restatement of the reference's pure-PHP
+driver (PhpBlas / PhpMath).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package; the product package
+`rindow_math_matrix_b200` never does (tests/test_no_oracle_in_product.py enforces it).
+
+All functions follow the reference's *driver-level* signatures (flat buffer + offset +
+ld), operate on float64 buffers (a PhpBuffer holds PHP doubles -- PhpBuffer.php:19) and
+mutate their output argument in place, exactly like the PHP methods do.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+RowMajor, ColMajor = 101, 102
+NoTrans, Trans, ConjTrans, ConjNoTrans = 111, 112, 113, 114
+
+
+class OracleArgumentError(ValueError):
+    """Stands for the reference's InvalidArgumentException."""
+
+
+class OracleZeroDivide(RuntimeError):
+    """Stands for RuntimeException('Zero divide in softmax.') (PhpMath.php:1663)."""
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "rindow_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or (
+        os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)
+    ):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        i64, dbl, p, i32 = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
+        L.ro_gemm.argtypes = [i32, i32, i32, i64, i64, i64, dbl, p, i64, i64, i64,
+                              p, i64, i64, i64, dbl, p, i64, i64, i64]
+        L.ro_gemm_rows.argtypes = [i64, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64]
+        L.ro_gemm3.argtypes = [i64, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64]
+        L.ro_add.argtypes = [i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_multiply.argtypes = [i32, i64, i64, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_reduce_sum.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64]
+        L.ro_reduce_max.argtypes = [i32, i64, i64, i64, p, i64, i64, p, i64, i64]
+        L.ro_reduce_argmax.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64]
+        L.ro_softmax.argtypes = [i64, i64, p, i64, i64, i64]
+        L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
+                                  i32, i32, i64, i64, i32, p, i64, i64, i64]
+        for name in ("ro_gemm", "ro_gemm_rows", "ro_gemm3", "ro_add", "ro_multiply",
+                     "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
+                     "ro_im2col2d", "ro_abi_version"):
+            getattr(L, name).restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _buf(a: np.ndarray, dtype=np.float64) -> np.ndarray:
+    if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.ndim == 1):
+        raise TypeError("oracle buffers are flat C-contiguous %s arrays" % np.dtype(dtype).name)
+    return a
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check(rc: int) -> None:
+    if rc == -1:
+        raise OracleArgumentError("invalid argument (reference: InvalidArgumentException)")
+    if rc == -2:
+        raise OracleZeroDivide("Zero divide in softmax.")
+    if rc != 0:
+        raise RuntimeError("oracle rc=%d" % rc)
+
+
+def as_buffer(a) -> np.ndarray:
+    """Widen any array to the flat float64 buffer the PHP driver would hold."""
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float64).reshape(-1).copy()
+
+
+# PhpBlas::gemm, src/Drivers/MatlibPHP/PhpBlas.php:849-948
+def gemm(order, transA, transB, m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC):
+    _check(lib().ro_gemm(order, transA, transB, m, n, k, float(alpha),
+                         _ptr(_buf(A)), A.size, offA, ldA, _ptr(_buf(B)), B.size, offB, ldB,
+                         float(beta), _ptr(_buf(C)), C.size, offC, ldC))
+
+
+def gemm_rows(row0, rows, n, k, alpha, A, ldA, B, ldB, beta, C, ldC):
+    _check(lib().ro_gemm_rows(row0, rows, n, k, float(alpha), _ptr(_buf(A)), ldA,
+                              _ptr(_buf(B)), ldB, float(beta), _ptr(_buf(C)), ldC))
+
+
+# MatrixOperator::gemm3, src/MatrixOperator.php:510-529
+def gemm3(M, N, K, L, alpha, A, offA, B, offB, beta, C, offC):
+    _check(lib().ro_gemm3(M, N, K, L, float(alpha), _ptr(_buf(A)), offA, _ptr(_buf(B)), offB,
+                          float(beta), _ptr(_buf(C)), offC))
+
+
+# PhpMath::add, PhpMath.php:570-606
+def add(trans, m, n, alpha, X, offX, incX, A, offA, ldA):
+    _check(lib().ro_add(int(bool(trans)), m, n, float(alpha), _ptr(_buf(X)), X.size, offX, incX,
+                        _ptr(_buf(A)), A.size, offA, ldA))
+
+
+# PhpMath::multiply, PhpMath.php:530-565
+def multiply(trans, m, n, X, offX, incX, A, offA, ldA):
+    _check(lib().ro_multiply(int(bool(trans)), m, n, _ptr(_buf(X)), X.size, offX, incX,
+                             _ptr(_buf(A)), A.size, offA, ldA))
+
+
+# PhpMath::reduceSum, PhpMath.php:1552-1579
+def reduce_sum(m, n, k, A, offA, B, offB):
+    _check(lib().ro_reduce_sum(m, n, k, _ptr(_buf(A)), A.size, offA, _ptr(_buf(B)), B.size, offB))
+
+
+# PhpMath::reduceMax, PhpMath.php:1584-1611 (sticky=True: accelerated-path NaN rule)
+def reduce_max(m, n, k, A, offA, B, offB, sticky=False):
+    _check(lib().ro_reduce_max(int(bool(sticky)), m, n, k, _ptr(_buf(A)), A.size, offA,
+                               _ptr(_buf(B)), B.size, offB))
+
+
+# PhpMath::reduceArgMax, PhpMath.php:1616-1643 (B is an int64 buffer: PHP ints)
+def reduce_argmax(m, n, k, A, offA, B, offB):
+    _check(lib().ro_reduce_argmax(m, n, k, _ptr(_buf(A)), A.size, offA,
+                                  _ptr(_buf(B, np.int64)), B.size, offB))
+
+
+# PhpMath::softmax, PhpMath.php:1645-1670
+def softmax(m, n, A, offA, ldA):
+    _check(lib().ro_softmax(m, n, _ptr(_buf(A)), A.size, offA, ldA))
+
+
+# PhpMath::im2col2d, PhpMath.php:2158-2314
+def im2col2d(reverse, images, images_offset, images_size, batches, im_h, im_w, channels,
+             filter_h, filter_w, stride_h, stride_w, padding, channels_first,
+             dilation_h, dilation_w, cols_channels_first, cols, cols_offset, cols_size):
+    _check(lib().ro_im2col2d(int(bool(reverse)), _ptr(_buf(images)), images.size, images_offset,
+                             images_size, batches, im_h, im_w, channels, filter_h, filter_w,
+                             stride_h, stride_w, int(bool(padding)), int(bool(channels_first)),
+                             dilation_h, dilation_w, int(bool(cols_channels_first)),
+                             _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
+
+
+def im2col2d_out_shape(batches, im_h, im_w, channels, filter_h, filter_w, stride_h, stride_w,
+                       padding, dilation_h, dilation_w, cols_channels_first):
+    """Shape LinearAlgebra::im2col2d allocates for cols (src/LinearAlgebra.php:3645-3670)."""
+    if padding:
+        out_h, out_w = im_h, im_w
+    else:
+        out_h = (im_h - (filter_h - 1) * dilation_h - 1) // stride_h + 1
+        out_w = (im_w - (filter_w - 1) * dilation_w - 1) // stride_w + 1
+    if cols_channels_first:
+        return (batches, out_h, out_w, channels, filter_h, filter_w)
+    return (batches, out_h, out_w, filter_h, filter_w, channels)

@@ -1,0 +1,423 @@
+/*
+ * rindow_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the reference's pure-PHP compute driver (PhpBlas / PhpMath on
+ * PhpBuffer) for the hot path of SURVEY.md section 8.  It exists so that tests/, the
+ * smoke() check and bench.py's cpu_baseline / --impl reference legs have something to
+ * compare the CUDA path with.  Nothing under rindow_math_matrix_b200/ may include,
+ * link or call this file: the product path has no CPU fallback.
+ *
+ * Storage model (reference: src/Drivers/MatlibPHP/PhpBuffer.php:19,86-93,124-133):
+ * a PhpBuffer is an SplFixedArray of PHP scalars, so a "float32" buffer holds PHP
+ * doubles that are never rounded to binary32, and every PhpBlas/PhpMath loop runs in
+ * double precision, strictly sequentially in index order.  Hence every function here
+ * works on `double` arrays; callers widen float32 inputs to double first (exactly the
+ * values the PHP buffer would hold) and compare device float32 results against the
+ * double result with the tolerance the test states.
+ *
+ * Parity pinning: the PHP interpreter is absent from this image and from the GPU
+ * boxes, so the restatement cannot be diffed against a live run of the reference.  It
+ * is pinned instead against every known-answer vector the reference's own PHPUnit
+ * suite holds for this path (the JSON files in tests/golden, transcribed/extracted from
+ * the PHP files of tests/RindowTest/Math/Matrix by tools/extract_golden.py) -- see
+ * tests/test_oracle_golden.py.  Results on random data at BASELINE.json sizes are
+ * pinned by this restatement only ("parity pinned by restatement").
+ *
+ * Compile:  see oracle/Makefile  (gcc -O2 -fno-fast-math -ffp-contract=off: no
+ * reassociation, no FMA contraction -- PHP evaluates `$a * $b` and `+` separately).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define RO_OK            0
+#define RO_E_ARG        -1   /* InvalidArgumentException in the reference */
+#define RO_E_ZERODIV    -2   /* RuntimeException("Zero divide in softmax.") */
+
+/* ---- helpers: PhpMath.php:83-130 ------------------------------------------------ */
+
+/* math_sum, PhpMath.php:83-93: acc starts at 0.0, sequential += */
+static double ro_math_sum(int64_t n, const double *X, int64_t offX, int64_t incX)
+{
+    int64_t idx = offX;
+    double acc = 0.0;
+    for (int64_t i = 0; i < n; i++, idx += incX) {
+        acc += X[idx];
+    }
+    return acc;
+}
+
+/* math_max, PhpMath.php:95-112: `if(!($value<=$max)) $max=$value;` -- a NaN replaces
+ * the running max, and any later ordinary value replaces a NaN max again (quirk). */
+static double ro_math_max(int64_t n, const double *X, int64_t offX, int64_t incX)
+{
+    int64_t idx = offX;
+    double mx = X[idx];
+    idx += incX;
+    for (int64_t i = 1; i < n; i++, idx += incX) {
+        double v = X[idx];
+        if (!(v <= mx)) {
+            mx = v;
+        }
+    }
+    return mx;
+}
+
+/* NaN-sticky variant: the rule of the reference's accelerated path
+ * (src/Drivers/MatlibCL/OpenCLMath.php:142-157 'lrmax' / :88-98 'qmax') which
+ * LinearAlgebraTest.php:7617-7643 pins for NaN in the middle of a row.  Identical to
+ * ro_math_max on NaN-free rows and on rows whose only NaN is the last element. */
+static double ro_math_max_sticky(int64_t n, const double *X, int64_t offX, int64_t incX)
+{
+    int64_t idx = offX;
+    double mx = X[idx];
+    idx += incX;
+    for (int64_t i = 1; i < n; i++, idx += incX) {
+        double v = X[idx];
+        if (isnan(mx)) {
+            continue;
+        }
+        if (isnan(v) || v > mx) {
+            mx = v;
+        }
+    }
+    return mx;
+}
+
+/* math_imax, PhpMath.php:114-130: strict `>`; ties keep the lowest index; NaN never
+ * wins; NaN at position 0 is never displaced. */
+static int64_t ro_math_imax(int64_t n, const double *X, int64_t offX, int64_t incX)
+{
+    int64_t idx = offX;
+    double mx = X[idx];
+    int64_t imax = 0;
+    idx += incX;
+    for (int64_t i = 1; i < n; i++, idx += incX) {
+        double v = X[idx];
+        if (v > mx) {
+            mx = v;
+            imax = i;
+        }
+    }
+    return imax;
+}
+
+/* ---- BLAS: PhpBlas.php:849-948 (real path :927-947) ------------------------------- */
+
+/* order: 101 RowMajor / 102 ColMajor; trans: 111 NoTrans, 112 Trans, 113 ConjTrans,
+ * 114 ConjNoTrans (CBLAS values; polite-math BLAS constants).  countA/B/C are the
+ * buffer lengths (count($A)), used for the overflow checks of Utils.php:52-65. */
+int ro_gemm(int order, int transA, int transB,
+            int64_t m, int64_t n, int64_t k,
+            double alpha,
+            const double *A, int64_t countA, int64_t offA, int64_t ldA,
+            const double *B, int64_t countB, int64_t offB, int64_t ldB,
+            double beta,
+            double *C, int64_t countC, int64_t offC, int64_t ldC)
+{
+    if (order == 102) {                       /* PhpBlas.php:862-863 */
+        int64_t t = m; m = n; n = t;
+    } else if (order != 101) {
+        return RO_E_ARG;
+    }
+    int tA, tB;
+    switch (transA) { case 111: case 114: tA = 0; break; case 112: case 113: tA = 1; break; default: return RO_E_ARG; }
+    switch (transB) { case 111: case 114: tB = 0; break; case 112: case 113: tB = 1; break; default: return RO_E_ARG; }
+    if (m < 1 || n < 1 || k < 1) return RO_E_ARG;            /* Utils.php:30-36 */
+    int64_t rowsA = !tA ? m : k, colsA = !tA ? k : m;
+    int64_t rowsB = !tB ? k : n, colsB = !tB ? n : k;
+    if (offA < 0 || ldA < 1 || offA + (rowsA - 1) * ldA + (colsA - 1) >= countA) return RO_E_ARG;
+    if (offB < 0 || ldB < 1 || offB + (rowsB - 1) * ldB + (colsB - 1) >= countB) return RO_E_ARG;
+    if (offC < 0 || ldC < 1 || offC + (m - 1) * ldC + (n - 1) >= countC) return RO_E_ARG;
+
+    int64_t ldA_m = !tA ? ldA : 1, ldA_k = !tA ? 1 : ldA;    /* PhpBlas.php:883-886 */
+    int64_t ldB_k = !tB ? ldB : 1, ldB_n = !tB ? 1 : ldB;
+
+    int64_t idA_m = offA, idC_m = offC;
+    for (int64_t im = 0; im < m; im++, idA_m += ldA_m, idC_m += ldC) {
+        int64_t idB_n = offB, idC = idC_m;
+        for (int64_t in = 0; in < n; in++, idB_n += ldB_n, idC++) {
+            int64_t idA = idA_m, idB = idB_n;
+            double acc = 0.0;
+            for (int64_t ik = 0; ik < k; ik++, idA += ldA_k, idB += ldB_k) {
+                acc += A[idA] * B[idB];
+            }
+            if (beta == 0.0) {
+                C[idC] = alpha * acc;                        /* C is not read */
+            } else {
+                C[idC] = alpha * acc + beta * C[idC];
+            }
+        }
+    }
+    return RO_OK;
+}
+
+/* Bounded-sample variant for bench.py's CPU baseline: identical arithmetic, but only
+ * rows [row0, row0+rows) of C are produced.  Not a reference function. */
+int ro_gemm_rows(int64_t row0, int64_t rows,
+                 int64_t n, int64_t k, double alpha,
+                 const double *A, int64_t ldA, const double *B, int64_t ldB,
+                 double beta, double *C, int64_t ldC)
+{
+    for (int64_t im = row0; im < row0 + rows; im++) {
+        for (int64_t in = 0; in < n; in++) {
+            double acc = 0.0;
+            const double *a = A + im * ldA;
+            const double *b = B + in;
+            for (int64_t ik = 0; ik < k; ik++) {
+                acc += a[ik] * b[ik * ldB];
+            }
+            double *c = C + im * ldC + in;
+            if (beta == 0.0) *c = alpha * acc; else *c = alpha * acc + beta * *c;
+        }
+    }
+    return RO_OK;
+}
+
+/* MatrixOperator::gemm3, src/MatrixOperator.php:510-529 (cross() with rank(B) > 2). */
+int ro_gemm3(int64_t M, int64_t N, int64_t K, int64_t L, double alpha,
+             const double *A, int64_t offA, const double *B, int64_t offB,
+             double beta, double *C, int64_t offC)
+{
+    for (int64_t m = 0; m < M; m++) {
+        for (int64_t l = 0; l < L; l++) {
+            for (int64_t n = 0; n < N; n++) {
+                double acc = 0.0;
+                for (int64_t k = 0; k < K; k++) {
+                    acc += A[offA + m * K + k] * B[offB + N * K * l + k * N + n];
+                }
+                int64_t ic = offC + m * L * N + N * l + n;
+                C[ic] = alpha * acc + beta * C[ic];
+            }
+        }
+    }
+    return RO_OK;
+}
+
+/* ---- elementwise: PhpMath.php:530-606 --------------------------------------------- */
+
+int ro_add(int trans, int64_t m, int64_t n, double alpha,
+           const double *X, int64_t countX, int64_t offX, int64_t incX,
+           double *A, int64_t countA, int64_t offA, int64_t ldA)
+{
+    int64_t rows = !trans ? m : n, cols = !trans ? n : m;
+    if (offX + (cols - 1) * incX >= countX) return RO_E_ARG;      /* :590-591 */
+    if (offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG; /* :592-593 */
+    int64_t incAj = !trans ? ldA : 1, incAi = !trans ? 1 : ldA;
+    int64_t idAj = offA;
+    for (int64_t j = 0; j < rows; j++, idAj += incAj) {
+        int64_t idA = idAj, idX = offX;
+        for (int64_t i = 0; i < cols; i++, idA += incAi, idX += incX) {
+            A[idA] = alpha * X[idX] + A[idA];                     /* one mul, one add */
+        }
+    }
+    return RO_OK;
+}
+
+int ro_multiply(int trans, int64_t m, int64_t n,
+                const double *X, int64_t countX, int64_t offX, int64_t incX,
+                double *A, int64_t countA, int64_t offA, int64_t ldA)
+{
+    int64_t rows = !trans ? m : n, cols = !trans ? n : m;
+    if (offX + (cols - 1) * incX >= countX) return RO_E_ARG;
+    if (offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG;
+    int64_t incAj = !trans ? ldA : 1, incAi = !trans ? 1 : ldA;
+    int64_t idAj = offA;
+    for (int64_t j = 0; j < rows; j++, idAj += incAj) {
+        int64_t idA = idAj, idX = offX;
+        for (int64_t i = 0; i < cols; i++, idA += incAi, idX += incX) {
+            A[idA] = X[idX] * A[idA];
+        }
+    }
+    return RO_OK;
+}
+
+/* ---- reductions over the middle axis of A[m,n,k]: PhpMath.php:1552-1643 ----------- */
+
+int ro_reduce_sum(int64_t m, int64_t n, int64_t k,
+                  const double *A, int64_t countA, int64_t offA,
+                  double *B, int64_t countB, int64_t offB)
+{
+    if (offA + m * n * k > countA) return RO_E_ARG;
+    if (offB + m * k > countB) return RO_E_ARG;
+    int64_t idxA = offA, idxB = offB, ldA = n * k, ldB = k;
+    for (int64_t i = 0; i < m; i++, idxA += ldA, idxB += ldB) {
+        for (int64_t j = 0; j < k; j++) {
+            B[idxB + j] = ro_math_sum(n, A, idxA + j, k);
+        }
+    }
+    return RO_OK;
+}
+
+/* sticky=0: the PHP rule (math_max); sticky=1: the accelerated-path NaN-sticky rule. */
+int ro_reduce_max(int sticky, int64_t m, int64_t n, int64_t k,
+                  const double *A, int64_t countA, int64_t offA,
+                  double *B, int64_t countB, int64_t offB)
+{
+    if (offA + m * n * k > countA) return RO_E_ARG;
+    if (offB + m * k > countB) return RO_E_ARG;
+    int64_t idxA = offA, idxB = offB, ldA = n * k, ldB = k;
+    for (int64_t i = 0; i < m; i++, idxA += ldA, idxB += ldB) {
+        for (int64_t j = 0; j < k; j++) {
+            B[idxB + j] = sticky ? ro_math_max_sticky(n, A, idxA + j, k)
+                                 : ro_math_max(n, A, idxA + j, k);
+        }
+    }
+    return RO_OK;
+}
+
+int ro_reduce_argmax(int64_t m, int64_t n, int64_t k,
+                     const double *A, int64_t countA, int64_t offA,
+                     int64_t *B, int64_t countB, int64_t offB)
+{
+    if (offA + m * n * k > countA) return RO_E_ARG;
+    if (offB + m * k > countB) return RO_E_ARG;
+    int64_t idxA = offA, idxB = offB, ldA = n * k, ldB = k;
+    for (int64_t i = 0; i < m; i++, idxA += ldA, idxB += ldB) {
+        for (int64_t j = 0; j < k; j++) {
+            B[idxB + j] = ro_math_imax(n, A, idxA + j, k);
+        }
+    }
+    return RO_OK;
+}
+
+/* ---- softmax: PhpMath.php:1645-1670 ------------------------------------------------ */
+
+int ro_softmax(int64_t m, int64_t n, double *A, int64_t countA, int64_t offA, int64_t ldA)
+{
+    if (offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG;
+    int64_t idA = offA;
+    for (int64_t i = 0; i < m; i++, idA += ldA) {
+        double max_a = ro_math_max(n, A, idA, 1);
+        double sum_exp = 0;
+        for (int64_t j = 0; j < n; j++) {
+            double t = exp(A[idA + j] - max_a);
+            sum_exp += t;
+            A[idA + j] = t;
+        }
+        if (sum_exp == 0.0) {
+            return RO_E_ZERODIV;
+        }
+        for (int64_t j = 0; j < n; j++) {
+            A[idA + j] = A[idA + j] / sum_exp;
+        }
+    }
+    return RO_OK;
+}
+
+/* ---- im2col2d / col2im: PhpMath.php:2091-2148 (copyCell2d), :2158-2314 ------------- */
+
+static void ro_copy_cell2d(int reverse, double *images, int64_t images_pos,
+                           int64_t im_h, int64_t im_w, int64_t channels, int64_t channel_step,
+                           int64_t filter_h_step, int64_t filter_w_step,
+                           int64_t vim_y, int64_t vim_x, int64_t vfilter_h, int64_t vfilter_w,
+                           int64_t dilation_h, int64_t dilation_w,
+                           double *out, int64_t out_pos, int64_t out_filter_step,
+                           int64_t out_channel_step)
+{
+    int64_t filter_h_pos = images_pos;
+    int64_t out_filter_pos = out_pos;
+    for (int64_t vfy = 0; vfy < vfilter_h; vfy += dilation_h) {
+        int64_t filter_w_pos = filter_h_pos;
+        for (int64_t vfx = 0; vfx < vfilter_w; vfx += dilation_w) {
+            int64_t channel_pos = filter_w_pos;
+            int64_t out_channel_pos = out_filter_pos;
+            int64_t input_y = vim_y + vfy;
+            int64_t input_x = vim_x + vfx;
+            for (int64_t c = 0; c < channels; c++) {
+                if (input_y < 0 || input_y >= im_h || input_x < 0 || input_x >= im_w) {
+                    if (!reverse) {
+                        out[out_channel_pos] = 0;
+                    }
+                } else {
+                    if (!reverse) {
+                        out[out_channel_pos] = images[channel_pos];
+                    } else {
+                        images[channel_pos] += out[out_channel_pos];
+                    }
+                }
+                out_channel_pos += out_channel_step;
+                channel_pos += channel_step;
+            }
+            out_filter_pos += out_filter_step;
+            filter_w_pos += filter_w_step;
+        }
+        filter_h_pos += filter_h_step;
+    }
+}
+
+int ro_im2col2d(int reverse,
+                double *images, int64_t count_images, int64_t images_offset, int64_t images_size,
+                int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
+                int cols_channels_first,
+                double *cols, int64_t count_cols, int64_t cols_offset, int64_t cols_size)
+{
+    int64_t images_buf_size = batches * im_h * im_w * channels;
+    if (images_size != images_buf_size || count_images - images_offset < images_buf_size) {
+        return RO_E_ARG;                                  /* 'images buffer size is invalid' */
+    }
+    /* PHP intdiv truncates toward zero, like C integer division. */
+    int64_t out_h = (im_h - (filter_h - 1) * dilation_h - 1) / stride_h + 1;
+    int64_t out_w = (im_w - (filter_w - 1) * dilation_w - 1) / stride_w + 1;
+    if (out_h <= 0 || out_w <= 0) {
+        return RO_E_ARG;                                  /* 'Invalid shape or parameters.' */
+    }
+    int64_t out_buf_size, padding_h, padding_w;
+    if (padding) {
+        out_buf_size = batches * im_h * filter_h * im_w * filter_w * channels;
+        padding_h = ((im_h - 1) * stride_h - im_h + (filter_h - 1) * dilation_h + 1) / 2;
+        padding_w = ((im_w - 1) * stride_w - im_w + (filter_w - 1) * dilation_w + 1) / 2;
+        out_h = im_h;
+        out_w = im_w;
+    } else {
+        out_buf_size = batches * out_h * filter_h * out_w * filter_w * channels;
+        padding_h = 0;
+        padding_w = 0;
+    }
+    /* PhpMath.php:2243-2246: note the reference's `>` -- a cols buffer LARGER than the
+     * view is rejected; a smaller one would fault in SplFixedArray, so reject it too. */
+    if (cols_size != out_buf_size || count_cols - cols_offset > out_buf_size
+        || count_cols - cols_offset < out_buf_size) {
+        return RO_E_ARG;                                  /* 'output buffer size is invalid' */
+    }
+    int64_t im_w_step, im_h_step, channel_step, batch_step;
+    if (channels_first) {
+        im_w_step = 1; im_h_step = im_w; channel_step = im_w * im_h; batch_step = im_w * im_h * channels;
+    } else {
+        channel_step = 1; im_w_step = channels; im_h_step = channels * im_w; batch_step = channels * im_w * im_h;
+    }
+    int64_t stride_w_step = im_w_step * stride_w, stride_h_step = im_h_step * stride_h;
+    int64_t filter_w_step = im_w_step * dilation_w, filter_h_step = im_h_step * dilation_h;
+    int64_t out_filter_step, out_channel_step;
+    if (cols_channels_first) {
+        out_filter_step = 1; out_channel_step = filter_h * filter_w;
+    } else {
+        out_filter_step = channels; out_channel_step = 1;
+    }
+    int64_t out_cell_step = filter_h * filter_w * channels;
+    int64_t batch_pos = images_offset - im_h_step * padding_h - im_w_step * padding_w;
+    int64_t out_pos = cols_offset;
+    int64_t vim_h = out_h * stride_h, vim_w = out_w * stride_w;
+    int64_t vfilter_h = filter_h * dilation_h, vfilter_w = filter_w * dilation_w;
+    for (int64_t batch = 0; batch < batches; batch++) {
+        int64_t stride_h_pos = batch_pos;
+        for (int64_t vim_y = 0; vim_y < vim_h; vim_y += stride_h) {
+            int64_t stride_w_pos = stride_h_pos;
+            for (int64_t vim_x = 0; vim_x < vim_w; vim_x += stride_w) {
+                ro_copy_cell2d(reverse, images, stride_w_pos, im_h, im_w, channels, channel_step,
+                               filter_h_step, filter_w_step, vim_y - padding_h, vim_x - padding_w,
+                               vfilter_h, vfilter_w, dilation_h, dilation_w,
+                               cols, out_pos, out_filter_step, out_channel_step);
+                stride_w_pos += stride_w_step;
+                out_pos += out_cell_step;
+            }
+            stride_h_pos += stride_h_step;
+        }
+        batch_pos += batch_step;
+    }
+    return RO_OK;
+}
+
+int ro_abi_version(void) { return 1; }

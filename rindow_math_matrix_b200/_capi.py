@@ -1,0 +1,144 @@
+"""ctypes binding of librindow_b200.so -- the same C ABI (include/rindow_b200.h) a PHP-FFI
+shim would bind (php/MatlibCuda/CudaFFI.php).  There is deliberately NO fallback: if the
+shared library or a B200 is missing every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librindow_b200.so")
+
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOTINIT, E_NOMEM = 0, -1, -2, -3, -4, -5
+
+GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2, 3
+GEMM_MODE_NAMES = {GEMM_FP32_SIMT: "fp32_simt", GEMM_TF32: "tf32", GEMM_TF32X3: "tf32x3"}
+
+i32, i64, f32, f64, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/rindow_b200.h declares
+SIGNATURES = {
+    "rb200_abi_version": (i32, []),
+    "rb200_last_error": (ctypes.c_char_p, []),
+    "rb200_device_count": (i32, [ctypes.POINTER(i32)]),
+    "rb200_init": (i32, [i32]),
+    "rb200_shutdown": (i32, []),
+    "rb200_device_info": (i32, [ctypes.POINTER(i32)] * 4 + [ctypes.POINTER(i64)]),
+    "rb200_set_stream": (i32, [vp]),
+    "rb200_get_stream": (i32, [ctypes.POINTER(vp)]),
+    "rb200_sync": (i32, []),
+    "rb200_set_default_gemm_mode": (i32, [i32]),
+    "rb200_get_default_gemm_mode": (i32, [ctypes.POINTER(i32)]),
+    "rb200_launch_count": (i32, [ctypes.POINTER(i64), i32]),
+    "rb200_last_gemm_path": (ctypes.c_char_p, []),
+    "rb200_buffer_alloc": (i32, [i64, ctypes.POINTER(vp)]),
+    "rb200_buffer_free": (i32, [vp]),
+    "rb200_buffer_h2d": (i32, [vp, i64, vp, i64]),
+    "rb200_buffer_d2h": (i32, [vp, vp, i64, i64]),
+    "rb200_buffer_h2d_async": (i32, [vp, i64, vp, i64]),
+    "rb200_buffer_d2h_async": (i32, [vp, vp, i64, i64]),
+    "rb200_buffer_d2d": (i32, [vp, i64, vp, i64, i64]),
+    "rb200_buffer_fill": (i32, [i32, vp, i64, i64, vp]),
+    "rb200_host_alloc": (i32, [i64, ctypes.POINTER(vp)]),
+    "rb200_host_free": (i32, [vp]),
+    "rb200_sgemm": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32]),
+    "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
+    "rb200_add": (i32, [i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
+    "rb200_multiply": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_reduce_sum": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
+    "rb200_reduce_max": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
+    "rb200_reduce_argmax": (i32, [i32, i64, i64, i64, vp, i64, i32, vp, i64]),
+    "rb200_softmax": (i32, [i32, i64, i64, vp, i64, i64]),
+    "rb200_im2col2d": (i32, [i32, i32, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
+                             i32, i32, i64, i64, i32, vp, i64, i64]),
+}
+
+
+class B200Error(RuntimeError):
+    """A non-zero status from the C ABI (the PHP shim turns these into RuntimeException)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__("librindow_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and bind every declared symbol.  Works without a GPU (no CUDA call)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(E_NOTINIT, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                       "(make -C rindow_math_matrix_b200/csrc); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        msg = load().rb200_last_error()
+        raise B200Error(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+_initialised_device = None
+
+
+def init(device: int | None = None) -> int:
+    """rb200_init on `device` (default: LOCAL_RANK or 0).  Raises if there is no B200."""
+    global _initialised_device
+    L = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _initialised_device != device:
+        check(L.rb200_init(device))
+        _initialised_device = device
+    return device
+
+
+def is_initialised() -> bool:
+    return _initialised_device is not None
+
+
+def device_available() -> bool:
+    """True when a CUDA device is visible (used by the service-level diagnosis only)."""
+    try:
+        n = i32(0)
+        return load().rb200_device_count(ctypes.byref(n)) == OK and n.value > 0
+    except (OSError, B200Error):
+        return False
+
+
+def sync() -> None:
+    check(load().rb200_sync())
+
+
+def launch_count(reset: bool = False) -> int:
+    n = i64(0)
+    check(load().rb200_launch_count(ctypes.byref(n), 1 if reset else 0))
+    return n.value
+
+
+def set_stream(cuda_stream_ptr: int | None) -> None:
+    """Adopt a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None restores the
+    library-owned stream."""
+    ptr = vp(-1 & 0xFFFFFFFFFFFFFFFF) if cuda_stream_ptr is None else vp(cuda_stream_ptr)
+    check(load().rb200_set_stream(ptr))
+
+
+def last_gemm_path() -> str:
+    return load().rb200_last_gemm_path().decode()
+
+
+def device_info() -> dict:
+    d, sm, maj, mnr, mem = i32(), i32(), i32(), i32(), i64()
+    check(load().rb200_device_info(ctypes.byref(d), ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr),
+                                   ctypes.byref(mem)))
+    return {"device": d.value, "sm_count": sm.value, "cc": (maj.value, mnr.value), "total_mem": mem.value}

@@ -1,0 +1,260 @@
+// capi.cu -- library / device / buffer entry points of the C ABI (include/rindow_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace rb200 {
+
+static Context g_ctx;
+static thread_local char g_err[1024] = "";
+
+Context& ctx() { return g_ctx; }
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? RB200_E_NOMEM : RB200_E_CUDA;
+}
+
+int ensure_workspace(size_t bytes)
+{
+    Context& c = ctx();
+    if (bytes <= c.workspace_bytes) return RB200_OK;
+    if (c.workspace) {
+        RB_CUDA(cudaStreamSynchronize(c.stream));
+        RB_CUDA(cudaFree(c.workspace));
+        c.workspace = nullptr;
+        c.workspace_bytes = 0;
+    }
+    size_t want = bytes < (size_t)(8u << 20) ? (size_t)(8u << 20) : bytes;
+    RB_CUDA(cudaMalloc(&c.workspace, want));
+    c.workspace_bytes = want;
+    return RB200_OK;
+}
+
+}  // namespace rb200
+
+using rb200::ctx;
+
+extern "C" {
+
+int rb200_abi_version(void) { return RB200_ABI_VERSION; }
+
+const char* rb200_last_error(void) { return rb200::g_err; }
+
+int rb200_device_count(int* count)
+{
+    if (!count) RB_INVALID("count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return rb200::cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    *count = n;
+    return RB200_OK;
+}
+
+int rb200_init(int device)
+{
+    rb200::Context& c = ctx();
+    if (c.initialised && c.device == device) return RB200_OK;
+    if (c.initialised) {
+        int rc = rb200_shutdown();
+        if (rc != RB200_OK) return rc;
+    }
+    RB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        rb200::set_error("device %d is sm_%d%d; librindow_b200 contains sm_100a code only (no fallback)",
+                         device, prop.major, prop.minor);
+        return RB200_E_UNSUPPORTED;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.cc_major = prop.major;
+    c.cc_minor = prop.minor;
+    c.total_mem = prop.totalGlobalMem;
+    RB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    c.launches = 0;
+    c.initialised = true;
+    return RB200_OK;
+}
+
+int rb200_shutdown(void)
+{
+    rb200::Context& c = ctx();
+    if (!c.initialised) return RB200_OK;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    if (c.workspace) cudaFree(c.workspace);
+    c.workspace = nullptr;
+    c.workspace_bytes = 0;
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    c.own_stream = nullptr;
+    c.stream = nullptr;
+    c.initialised = false;
+    c.device = -1;
+    return RB200_OK;
+}
+
+int rb200_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes)
+{
+    RB_REQUIRE_INIT();
+    rb200::Context& c = ctx();
+    if (device) *device = c.device;
+    if (sm_count) *sm_count = c.sm_count;
+    if (cc_major) *cc_major = c.cc_major;
+    if (cc_minor) *cc_minor = c.cc_minor;
+    if (total_mem_bytes) *total_mem_bytes = (int64_t)c.total_mem;
+    return RB200_OK;
+}
+
+int rb200_set_stream(void* cuda_stream)
+{
+    RB_REQUIRE_INIT();
+    rb200::Context& c = ctx();
+    // cudaStream_t 0 (legacy default stream) is a valid caller stream; NULL restores ours
+    // only when the caller passes the sentinel (void*)-1.
+    if (cuda_stream == (void*)(intptr_t)-1) c.stream = c.own_stream;
+    else c.stream = (cudaStream_t)cuda_stream;
+    return RB200_OK;
+}
+
+int rb200_get_stream(void** cuda_stream)
+{
+    RB_REQUIRE_INIT();
+    if (!cuda_stream) RB_INVALID("cuda_stream is NULL");
+    *cuda_stream = (void*)ctx().stream;
+    return RB200_OK;
+}
+
+int rb200_sync(void)
+{
+    RB_REQUIRE_INIT();
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_set_default_gemm_mode(int mode)
+{
+    if (mode < RB200_GEMM_FP32_SIMT || mode > RB200_GEMM_TF32X3) RB_INVALID("unknown gemm mode %d", mode);
+    ctx().default_gemm_mode = mode;
+    return RB200_OK;
+}
+
+int rb200_get_default_gemm_mode(int* mode)
+{
+    if (!mode) RB_INVALID("mode is NULL");
+    *mode = ctx().default_gemm_mode;
+    return RB200_OK;
+}
+
+int rb200_launch_count(int64_t* count, int reset)
+{
+    if (count) *count = ctx().launches;
+    if (reset) ctx().launches = 0;
+    return RB200_OK;
+}
+
+const char* rb200_last_gemm_path(void) { return ctx().last_gemm_path; }
+
+/* ---- buffers ------------------------------------------------------------------------ */
+
+int rb200_buffer_alloc(int64_t bytes, void** dptr)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr) RB_INVALID("dptr is NULL");
+    if (bytes < 0) RB_INVALID("negative size");
+    *dptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    RB_CUDA(cudaMalloc(dptr, (size_t)bytes));
+    return RB200_OK;
+}
+
+int rb200_buffer_free(void* dptr)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr) return RB200_OK;
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    RB_CUDA(cudaFree(dptr));
+    return RB200_OK;
+}
+
+int rb200_buffer_h2d_async(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr || !host || bytes < 0 || dst_offset_bytes < 0) RB_INVALID("bad h2d arguments");
+    if (bytes == 0) return RB200_OK;
+    RB_CUDA(cudaMemcpyAsync((char*)dptr + dst_offset_bytes, host, (size_t)bytes,
+                            cudaMemcpyHostToDevice, ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_buffer_d2h_async(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr || !host || bytes < 0 || src_offset_bytes < 0) RB_INVALID("bad d2h arguments");
+    if (bytes == 0) return RB200_OK;
+    RB_CUDA(cudaMemcpyAsync(host, (const char*)dptr + src_offset_bytes, (size_t)bytes,
+                            cudaMemcpyDeviceToHost, ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_buffer_h2d(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes)
+{
+    int rc = rb200_buffer_h2d_async(dptr, dst_offset_bytes, host, bytes);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_buffer_d2h(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes)
+{
+    int rc = rb200_buffer_d2h_async(host, dptr, src_offset_bytes, bytes);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_buffer_d2d(void* dst, int64_t dst_offset_bytes, const void* src, int64_t src_offset_bytes,
+                     int64_t bytes)
+{
+    RB_REQUIRE_INIT();
+    if (!dst || !src || bytes < 0 || dst_offset_bytes < 0 || src_offset_bytes < 0) RB_INVALID("bad d2d arguments");
+    if (bytes == 0) return RB200_OK;
+    RB_CUDA(cudaMemcpyAsync((char*)dst + dst_offset_bytes, (const char*)src + src_offset_bytes,
+                            (size_t)bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_host_alloc(int64_t bytes, void** hptr)
+{
+    RB_REQUIRE_INIT();
+    if (!hptr || bytes < 0) RB_INVALID("bad host_alloc arguments");
+    if (bytes == 0) bytes = 16;
+    RB_CUDA(cudaHostAlloc(hptr, (size_t)bytes, cudaHostAllocDefault));
+    return RB200_OK;
+}
+
+int rb200_host_free(void* hptr)
+{
+    RB_REQUIRE_INIT();
+    if (!hptr) return RB200_OK;
+    RB_CUDA(cudaFreeHost(hptr));
+    return RB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,517 @@
+// gemm_tcgen05.cu -- float32 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+// accumulators in TMEM, operands staged in shared memory by TMA).  sm_100a only.
+//
+// Replaces the inner loop of PhpBlas::gemm (src/Drivers/MatlibPHP/PhpBlas.php:927-947) for
+// float32 when the operands are TMA-addressable (16-byte aligned bases, leading dimensions
+// that are multiples of 4 elements); everything else goes to gemm_simt.cu.
+//
+// Two arithmetic modes (include/rindow_b200.h):
+//   RB200_GEMM_TF32   : one tcgen05.mma per k-step on the raw float32 tiles (the tensor core
+//                       reads the top 19 bits).  Fastest; max error ~1e-3 of max|C|.
+//   RB200_GEMM_TF32X3 : A and B are first split into tf32 "hi" (cvt.rna) and "lo" (a - hi)
+//                       planes by a streaming pre-pass (split_tf32_kernel); the GEMM then
+//                       issues hi*lo + lo*hi + hi*hi into the same TMEM accumulator.
+//                       ~fp32 accuracy (meets the reference's isclose bound, rtol 1e-4).
+//
+// Kernel anatomy (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.3d into a STAGES-deep smem ring,
+//              mbarrier expect_tx / complete_tx
+//   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma (M=128, N=BN, K=8 per
+//              instruction, 4 per 32-float k-block), tcgen05.commit frees the smem slot and,
+//              after the last k-block, publishes the accumulator
+//   warp 2   : TMEM allocator (2 accumulators of BN columns: the epilogue of tile i overlaps
+//              the mainloop of tile i+1)
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> registers -> alpha/beta -> global
+// Tiles are visited in a grouped (L2-friendly) order: 16 row-blocks share each B column-block.
+//
+// Shared-memory operand layouts (128-byte swizzle everywhere, 1024-byte aligned tiles):
+//   K-major  (A NoTrans / B Trans): rows of 32 floats; TMA box {32, rows}; UMMA descriptor
+//            SBO = 1024 (8 rows); advancing K by 8 floats = +32 bytes on the start address.
+//   MN-major (A Trans / B NoTrans): boxes {32 mn, 32 k} of 4 KB, one per 32 columns; UMMA
+//            descriptor LBO = 4096 (next 32 columns), SBO = 1024 (next 8 k); advancing K by 8
+//            = +1024 bytes.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // floats per k-block = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;              // tf32: 32 bytes per instruction
+constexpr int TC_THREADS = 256;
+constexpr int TC_GROUP_M = 16;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SW128).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor for kind::tf32, fp32 accumulate (InstrDescriptor in the same header)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4)            // c_format = F32
+         | (2u << 7)            // a_format = TF32
+         | (2u << 10)           // b_format = TF32
+         | ((uint32_t)a_mn_major << 15)
+         | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17)
+         | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+    int64_t M, N, K;
+    float alpha, beta;
+    float* C;
+    int64_t ldC;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+};
+
+template <int BN, int PLANES, int STAGES>
+struct TcSmem {
+    static constexpr int A_PLANE = TC_BM * TC_BK * 4;         // 16 KB
+    static constexpr int B_PLANE = BN * TC_BK * 4;            // 16 / 32 KB
+    static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
+    static constexpr int BARRIER_OFF = STAGES * STAGE;
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;    // + barriers + alignment slack
+};
+
+// grouped tile order: TC_GROUP_M row-blocks share each column-block before moving on
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb)
+{
+    const int per_group = TC_GROUP_M * num_n;
+    const int group = tile / per_group;
+    const int first_m = group * TC_GROUP_M;
+    const int gsz = min(num_m - first_m, TC_GROUP_M);
+    const int in_group = tile - group * per_group;
+    mb = first_m + in_group % gsz;
+    nb = in_group / gsz;
+}
+
+template <int BN, bool A_MN, bool B_MN, int PLANES, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, TcParams p)
+{
+    using L = TcSmem<BN, PLANES, STAGES>;
+    constexpr int TMEM_COLS = 2 * BN;                         // two accumulators (256 or 512 columns)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + L::BARRIER_OFF;
+    // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+    auto full_bar  = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar= [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_ptr_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(tmem_ptr_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::BARRIER_OFF + 8 * (2 * STAGES + 4));
+
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mb, nb;
+                tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+                const int m0 = mb * TC_BM, n0 = nb * BN;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), (uint32_t)L::STAGE);
+                    const uint32_t sA = smem_base + stage * L::STAGE;
+                    const uint32_t sB = sA + PLANES * L::A_PLANE;
+                    const int k0 = kb * TC_BK;
+#pragma unroll
+                    for (int pl = 0; pl < PLANES; pl++) {
+                        if (!A_MN) {
+                            tma_load_3d(sA + pl * L::A_PLANE, &tmapA, full_bar(stage), k0, m0, pl);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TC_BM / 32; j++)
+                                tma_load_3d(sA + pl * L::A_PLANE + j * 4096, &tmapA, full_bar(stage), m0 + 32 * j, k0, pl);
+                        }
+                        if (!B_MN) {
+                            tma_load_3d(sB + pl * L::B_PLANE, &tmapB, full_bar(stage), k0, n0, pl);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; j++)
+                                tma_load_3d(sB + pl * L::B_PLANE + j * 4096, &tmapB, full_bar(stage), n0 + 32 * j, k0, pl);
+                        }
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + stage * L::STAGE;
+                    const uint32_t sB = sA + PLANES * L::A_PLANE;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / TC_UMMA_K; kk++) {
+                        // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +1024 (8 k-rows)
+                        const uint32_t aoff = A_MN ? kk * 1024 : kk * 32;
+                        const uint32_t boff = B_MN ? kk * 1024 : kk * 32;
+                        const uint64_t a_hi = make_smem_desc(sA + aoff, A_MN ? 4096 : 16, 1024);
+                        const uint64_t b_hi = make_smem_desc(sB + boff, B_MN ? 4096 : 16, 1024);
+                        const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                        if (PLANES == 1) {
+                            tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, first);
+                        } else {
+                            const uint64_t a_lo = make_smem_desc(sA + L::A_PLANE + aoff, A_MN ? 4096 : 16, 1024);
+                            const uint64_t b_lo = make_smem_desc(sB + L::B_PLANE + boff, B_MN ? 4096 : 16, 1024);
+                            tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, first);     // small terms first
+                            tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
+                            tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                    if (kb == p.num_k_blocks - 1) tc_commit(tfull_bar(acc));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int mb, nb;
+            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+            const int64_t row = (int64_t)mb * TC_BM + q * 32 + lane;
+            const int64_t col0 = (int64_t)nb * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            float* crow = p.C + row * p.ldC;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ch++) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32);
+                tc_ld_32x32b_x32(taddr, r);
+                tc_wait_ld();
+                const int64_t c0 = col0 + ch * 32;
+                if (row_ok && c0 < p.N) {
+                    if (c0 + 32 <= p.N) {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) {
+                            float4 o;
+                            o.x = p.alpha * __uint_as_float(r[4 * v + 0]);
+                            o.y = p.alpha * __uint_as_float(r[4 * v + 1]);
+                            o.z = p.alpha * __uint_as_float(r[4 * v + 2]);
+                            o.w = p.alpha * __uint_as_float(r[4 * v + 3]);
+                            float4* dst = reinterpret_cast<float4*>(crow + c0) + v;
+                            if (p.beta != 0.f) {
+                                const float4 old = *dst;
+                                o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
+                                o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+                            }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            if (c0 + e < p.N) {
+                                float o = p.alpha * __uint_as_float(r[e]);
+                                if (p.beta != 0.f) o = fmaf(p.beta, crow[c0 + e], o);
+                                crow[c0 + e] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---- hi/lo split pre-pass for the 3xTF32 mode ------------------------------------------------------
+// planes[0] = tf32(x) (round to nearest, low 13 bits zero), planes[1] = x - planes[0] (exact in fp32).
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
+                  float* __restrict__ dst, int64_t ld_dst, int64_t plane_stride)
+{
+    const int64_t cv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 column
+    if (cv * 4 >= cols) return;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(src + r * ld_src) + cv);
+        float4 hi, lo;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); hi.x = __uint_as_float(t); lo.x = v.x - hi.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); hi.y = __uint_as_float(t); lo.y = v.y - hi.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); hi.z = __uint_as_float(t); lo.z = v.z - hi.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); hi.w = __uint_as_float(t); lo.w = v.w - hi.w;
+        *(reinterpret_cast<float4*>(dst + r * ld_dst) + cv) = hi;
+        *(reinterpret_cast<float4*>(dst + plane_stride + r * ld_dst) + cv) = lo;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        }
+    }
+    return fn;
+}
+
+// 3-D map over a row-major [outer, inner] float matrix with `planes` copies `plane_stride` elements apart.
+int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int planes,
+             int64_t plane_stride, int box_inner, int box_outer)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { rb200::set_error("cuTensorMapEncodeTiled is not available from the driver"); return RB200_E_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(planes > 1 ? plane_stride * 4 : ld * 4 * outer)};
+    if (strides[1] % 16 != 0) strides[1] = (strides[1] + 15) / 16 * 16;
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rb200::set_error("cuTensorMapEncodeTiled failed (CUresult %d): inner=%lld outer=%lld ld=%lld planes=%d",
+                         (int)r, (long long)inner, (long long)outer, (long long)ld, planes);
+        return RB200_E_CUDA;
+    }
+    return RB200_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int PLANES, int STAGES>
+int launch_tf32(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
+{
+    rb200::Context& c = rb200::ctx();
+    using L = TcSmem<BN, PLANES, STAGES>;
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, PLANES, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int grid = tiles < c.sm_count ? tiles : c.sm_count;
+    kern<<<grid, TC_THREADS, L::TOTAL, c.stream>>>(mA, mB, p);
+    RB_LAUNCH_CHECK("gemm_tf32_kernel");
+    return RB200_OK;
+}
+
+template <int BN, int PLANES, int STAGES>
+int launch_by_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
+{
+    if (!a_mn && !b_mn) return launch_tf32<BN, false, false, PLANES, STAGES>(mA, mB, p);
+    if (!a_mn &&  b_mn) return launch_tf32<BN, false, true,  PLANES, STAGES>(mA, mB, p);
+    if ( a_mn && !b_mn) return launch_tf32<BN, true,  false, PLANES, STAGES>(mA, mB, p);
+    return launch_tf32<BN, true, true, PLANES, STAGES>(mA, mB, p);
+}
+
+}  // namespace
+
+namespace rb200 {
+
+// Whether the tensor-core path can take this problem (TMA alignment rules).
+bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
+                           const float* B, int64_t ldB, const float* C, int64_t ldC)
+{
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!al16(A) || !al16(B) || !al16(C)) return false;
+    if (ldA % 4 || ldB % 4 || ldC % 4) return false;
+    if (M < 1 || N < 1 || K < 1) return false;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return false;
+    if (rb_ceil_div(M, TC_BM) * rb_ceil_div(N, 128) > 0x3fffffffLL) return false;
+    return true;
+}
+
+// A is rowsA x colsA row-major with ldA (transA: stored [K,M]); B likewise (transB: stored [N,K]).
+int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
+                 const float* A, int64_t ldA, const float* B, int64_t ldB, float beta, float* C, int64_t ldC)
+{
+    Context& c = ctx();
+    const bool a_mn = transA;          // stored [K, M]: M contiguous
+    const bool b_mn = !transB;         // stored [K, N]: N contiguous
+    const int planes = (mode == RB200_GEMM_TF32X3) ? 2 : 1;
+    const int BN = planes == 1 ? 256 : 128;
+
+    const float* srcA = A; const float* srcB = B;
+    int64_t sldA = ldA, sldB = ldB, plsA = 0, plsB = 0;
+    const int64_t rowsA = transA ? K : M, colsA = transA ? M : K;
+    const int64_t rowsB = transB ? N : K, colsB = transB ? K : N;
+    if (planes == 2) {
+        // split pre-pass into the workspace: [2][rows][cols4] per operand
+        const int64_t cA = rb_ceil_div(colsA, 4) * 4, cB = rb_ceil_div(colsB, 4) * 4;
+        plsA = rowsA * cA; plsB = rowsB * cB;
+        const size_t need = (size_t)(2 * plsA + 2 * plsB) * sizeof(float);
+        int rc = ensure_workspace(need);
+        if (rc != RB200_OK) return rc;
+        float* wA = reinterpret_cast<float*>(c.workspace);
+        float* wB = wA + 2 * plsA;
+        {
+            dim3 grid((unsigned)rb_ceil_div(cA / 4, 256), (unsigned)(rowsA < 65535 ? rowsA : 65535));
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(A, rowsA, colsA, ldA, wA, cA, plsA);
+            RB_LAUNCH_CHECK("split_tf32_kernel");
+        }
+        {
+            dim3 grid((unsigned)rb_ceil_div(cB / 4, 256), (unsigned)(rowsB < 65535 ? rowsB : 65535));
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(B, rowsB, colsB, ldB, wB, cB, plsB);
+            RB_LAUNCH_CHECK("split_tf32_kernel");
+        }
+        srcA = wA; srcB = wB; sldA = cA; sldB = cB;
+    }
+
+    CUtensorMap mA, mB;
+    int rc;
+    // K-major: inner = K, outer = M|N, box {32, rows}.  MN-major: inner = M|N, outer = K, box {32, 32}.
+    if (!a_mn) rc = make_map(&mA, srcA, K, M, sldA, planes, plsA, TC_BK, TC_BM);
+    else       rc = make_map(&mA, srcA, M, K, sldA, planes, plsA, 32, TC_BK);
+    if (rc != RB200_OK) return rc;
+    if (!b_mn) rc = make_map(&mB, srcB, K, N, sldB, planes, plsB, TC_BK, BN);
+    else       rc = make_map(&mB, srcB, N, K, sldB, planes, plsB, 32, TC_BK);
+    if (rc != RB200_OK) return rc;
+
+    TcParams p;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
+    p.num_m_blocks = (int)rb_ceil_div(M, TC_BM);
+    p.num_n_blocks = (int)rb_ceil_div(N, BN);
+    p.num_k_blocks = (int)rb_ceil_div(K, TC_BK);
+    if (planes == 1) {
+        c.last_gemm_path = "tcgen05_tf32";
+        return launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
+    }
+    c.last_gemm_path = "tcgen05_tf32x3";
+    return launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
+}
+
+}  // namespace rb200

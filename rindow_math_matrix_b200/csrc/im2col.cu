@@ -1,0 +1,255 @@
+// im2col.cu -- im2col2d forward (gather) and reverse (col2im, gather-form) (HBM-bound,
+// write-dominated).
+//
+// Reference semantics (src/Drivers/MatlibPHP/PhpMath.php:2091-2148 copyCell2d, :2158-2314):
+//   forward : cols[b,oy,ox,ky,kx,c] = images[b, oy*sh + ky*dh - ph, ox*sw + kx*dw - pw, c]
+//             or 0 outside the image;  cols_channels_first -> cols[b,oy,ox,c,ky,kx];
+//             channels_first images are [b,c,h,w].
+//   reverse : images[...] += cols[...] for every in-bounds tap, accumulated in the
+//             reference's loop order (oy, ox ascending), on top of the existing image values.
+//   out = (in - (k-1)*d - 1) div s + 1;  padding => out = in,
+//   p = ((in-1)*s - in + (k-1)*d + 1) div 2                         (PhpMath.php:2217-2241)
+// A pure copy: results are bit-exact for every dtype (forward) and exact in the reference's
+// summation order (reverse).
+// Algorithmic bytes (forward): images read once + cols written once.
+//
+// Forward kernel: one thread per 16-byte group of consecutive cols elements (128-bit
+// stores, fully coalesced on the 340 MB side); the (ky,kx,c) -> source-delta map of one cell
+// is a shared-memory table, so each element costs one table read + one bounds test + one
+// (L1/L2-served, 9x reused) gather load.  Reverse kernel: one thread per image element,
+// summing its <= kh*kw taps -- no atomics, deterministic order.
+#include "common.cuh"
+
+namespace {
+
+struct Im2colParams {
+    int64_t batches, im_h, im_w, channels;
+    int64_t filter_h, filter_w, stride_h, stride_w, dilation_h, dilation_w;
+    int64_t out_h, out_w, padding_h, padding_w;
+    int64_t im_w_step, im_h_step, channel_step, batch_step;   // image strides in elements
+    int     cols_channels_first;
+    int64_t cell;            // filter_h*filter_w*channels
+    int64_t total_cols;      // batches*out_h*out_w*cell
+    int64_t total_images;
+};
+
+constexpr int IC_THREADS = 256;
+constexpr int IC_MAX_CELL = 4096;     // entries of the shared-memory tap table
+
+struct Tap { int delta; short dy, dx; };   // 8 bytes
+
+template <typename W> union IcPack { int4 raw; W v[16 / sizeof(W)]; };
+
+// VEC: cols + offset is 16-byte aligned -> 128-bit stores of 16/sizeof(W) elements.
+template <typename W, bool VEC, bool TABLE>
+__global__ void __launch_bounds__(IC_THREADS)
+im2col2d_forward(Im2colParams p, const W* __restrict__ images, W* __restrict__ cols)
+{
+    constexpr int V = VEC ? 16 / (int)sizeof(W) : 1;
+    __shared__ Tap taps[TABLE ? IC_MAX_CELL : 1];
+    const int cell = (int)p.cell;
+    const int khw = (int)(p.filter_h * p.filter_w);
+    auto make_tap = [&](int r) {
+        int ky, kx, c;
+        if (p.cols_channels_first) { c = r / khw; int q = r - c * khw; ky = q / (int)p.filter_w; kx = q - ky * (int)p.filter_w; }
+        else { int q = r / (int)p.channels; c = r - q * (int)p.channels; ky = q / (int)p.filter_w; kx = q - ky * (int)p.filter_w; }
+        Tap t;
+        t.dy = (short)(ky * p.dilation_h);
+        t.dx = (short)(kx * p.dilation_w);
+        t.delta = (int)(t.dy * p.im_h_step + t.dx * p.im_w_step + c * p.channel_step);
+        return t;
+    };
+    if (TABLE) {
+        for (int r = threadIdx.x; r < cell; r += IC_THREADS) taps[r] = make_tap(r);
+        __syncthreads();
+    }
+    const int64_t ngroups = (p.total_cols + V - 1) / V;
+    const int64_t cells_per_batch = p.out_h * p.out_w;
+    for (int64_t g = (int64_t)blockIdx.x * IC_THREADS + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * IC_THREADS) {
+        const int64_t o = g * V;
+        int64_t cell_id = o / cell;
+        int r = (int)(o - cell_id * cell);
+        int64_t b = cell_id / cells_per_batch;
+        int64_t q = cell_id - b * cells_per_batch;
+        int64_t oy = q / p.out_w;
+        int64_t ox = q - oy * p.out_w;
+        int64_t y0 = oy * p.stride_h - p.padding_h;
+        int64_t x0 = ox * p.stride_w - p.padding_w;
+        const W* src = images + b * p.batch_step + y0 * p.im_h_step + x0 * p.im_w_step;
+        IcPack<W> out;
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            W val = (W)0;
+            if (o + e < p.total_cols) {
+                const Tap t = TABLE ? taps[r] : make_tap(r);
+                const int64_t iy = y0 + t.dy, ix = x0 + t.dx;
+                if (iy >= 0 && iy < p.im_h && ix >= 0 && ix < p.im_w) val = __ldg(src + t.delta);
+            }
+            out.v[e] = val;
+            if (++r == cell) {           // next cell: advance (ox, oy, b) with carries
+                r = 0;
+                ox++; x0 += p.stride_w;
+                if (ox == p.out_w) {
+                    ox = 0; x0 = -p.padding_w;
+                    oy++; y0 += p.stride_h;
+                    if (oy == p.out_h) { oy = 0; y0 = -p.padding_h; b++; }
+                }
+                src = images + b * p.batch_step + y0 * p.im_h_step + x0 * p.im_w_step;
+            }
+        }
+        if (VEC) {
+            if (o + V <= p.total_cols) {
+                __stcs(reinterpret_cast<int4*>(cols + o), out.raw);
+            } else {
+                for (int e = 0; o + e < p.total_cols; e++) cols[o + e] = out.v[e];
+            }
+        } else {
+            cols[o] = out.v[0];
+        }
+    }
+}
+
+// reverse: one thread per image element; taps visited in the reference's accumulation order.
+template <typename T>
+__global__ void __launch_bounds__(IC_THREADS)
+col2im2d_reverse(Im2colParams p, T* __restrict__ images, const T* __restrict__ cols)
+{
+    for (int64_t idx = (int64_t)blockIdx.x * IC_THREADS + threadIdx.x; idx < p.total_images;
+         idx += (int64_t)gridDim.x * IC_THREADS) {
+        // decompose the image element index (memory order) into (b, iy, ix, c)
+        int64_t b = idx / p.batch_step;
+        int64_t rem = idx - b * p.batch_step;
+        int64_t c, iy, ix;
+        if (p.channel_step == 1) {          // channels last: [b, h, w, c]
+            iy = rem / p.im_h_step; rem -= iy * p.im_h_step;
+            ix = rem / p.im_w_step; c = rem - ix * p.im_w_step;
+        } else {                            // channels first: [b, c, h, w]
+            c = rem / p.channel_step; rem -= c * p.channel_step;
+            iy = rem / p.im_h_step; ix = rem - iy * p.im_h_step;
+        }
+        T acc = images[idx];
+        // increasing oy <=> decreasing ky; within one oy increasing ox <=> decreasing kx
+        for (int64_t ky = p.filter_h - 1; ky >= 0; ky--) {
+            const int64_t ny = iy + p.padding_h - ky * p.dilation_h;
+            if (ny < 0 || ny % p.stride_h != 0) continue;
+            const int64_t oy = ny / p.stride_h;
+            if (oy >= p.out_h) continue;
+            for (int64_t kx = p.filter_w - 1; kx >= 0; kx--) {
+                const int64_t nx = ix + p.padding_w - kx * p.dilation_w;
+                if (nx < 0 || nx % p.stride_w != 0) continue;
+                const int64_t ox = nx / p.stride_w;
+                if (ox >= p.out_w) continue;
+                const int64_t cellbase = ((b * p.out_h + oy) * p.out_w + ox) * p.cell;
+                const int64_t within = p.cols_channels_first
+                    ? (c * p.filter_h + ky) * p.filter_w + kx
+                    : (ky * p.filter_w + kx) * p.channels + c;
+                acc += __ldg(cols + cellbase + within);
+            }
+        }
+        images[idx] = acc;
+    }
+}
+
+template <typename W>
+int forward_launch(const Im2colParams& p, const void* images, void* cols)
+{
+    rb200::Context& c = rb200::ctx();
+    const W* im = reinterpret_cast<const W*>(images);
+    W* co = reinterpret_cast<W*>(cols);
+    const bool vec = (reinterpret_cast<uintptr_t>(co) & 15) == 0;
+    const bool table = p.cell <= IC_MAX_CELL;
+    const int V = vec ? 16 / (int)sizeof(W) : 1;
+    int64_t grid = rb_ceil_div(rb_ceil_div(p.total_cols, V), IC_THREADS);
+    const int64_t cap = (int64_t)c.sm_count * 32;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (vec && table)       im2col2d_forward<W, true, true><<<(unsigned)grid, IC_THREADS, 0, c.stream>>>(p, im, co);
+    else if (vec && !table) im2col2d_forward<W, true, false><<<(unsigned)grid, IC_THREADS, 0, c.stream>>>(p, im, co);
+    else if (table)         im2col2d_forward<W, false, true><<<(unsigned)grid, IC_THREADS, 0, c.stream>>>(p, im, co);
+    else                    im2col2d_forward<W, false, false><<<(unsigned)grid, IC_THREADS, 0, c.stream>>>(p, im, co);
+    RB_LAUNCH_CHECK("im2col2d_forward");
+    return RB200_OK;
+}
+
+template <typename T>
+int reverse_launch(const Im2colParams& p, void* images, const void* cols)
+{
+    rb200::Context& c = rb200::ctx();
+    int64_t grid = rb_ceil_div(p.total_images, IC_THREADS);
+    const int64_t cap = (int64_t)c.sm_count * 32;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    col2im2d_reverse<T><<<(unsigned)grid, IC_THREADS, 0, c.stream>>>(p, reinterpret_cast<T*>(images),
+                                                                    reinterpret_cast<const T*>(cols));
+    RB_LAUNCH_CHECK("col2im2d_reverse");
+    return RB200_OK;
+}
+
+}  // namespace
+
+extern "C" int rb200_im2col2d(int dtype, int reverse,
+                              void* images, int64_t images_offset, int64_t images_size,
+                              int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                              int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                              int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
+                              int cols_channels_first,
+                              void* cols, int64_t cols_offset, int64_t cols_size)
+{
+    RB_REQUIRE_INIT();
+    if (!images || !cols) RB_INVALID("NULL buffer");
+    if (batches < 1 || im_h < 1 || im_w < 1 || channels < 1 || filter_h < 1 || filter_w < 1 ||
+        stride_h < 1 || stride_w < 1 || dilation_h < 1 || dilation_w < 1) {
+        RB_INVALID("im2col2d: shape parameters must be greater than 0");
+    }
+    if (images_offset < 0 || cols_offset < 0) RB_INVALID("negative offset");
+    Im2colParams p;
+    p.batches = batches; p.im_h = im_h; p.im_w = im_w; p.channels = channels;
+    p.filter_h = filter_h; p.filter_w = filter_w; p.stride_h = stride_h; p.stride_w = stride_w;
+    p.dilation_h = dilation_h; p.dilation_w = dilation_w;
+    if (images_size != batches * im_h * im_w * channels) RB_INVALID("images buffer size is invalid");
+    int64_t out_h = (im_h - (filter_h - 1) * dilation_h - 1) / stride_h + 1;
+    int64_t out_w = (im_w - (filter_w - 1) * dilation_w - 1) / stride_w + 1;
+    if (out_h <= 0 || out_w <= 0) RB_INVALID("Invalid shape or parameters.");
+    if (padding) {
+        p.padding_h = ((im_h - 1) * stride_h - im_h + (filter_h - 1) * dilation_h + 1) / 2;
+        p.padding_w = ((im_w - 1) * stride_w - im_w + (filter_w - 1) * dilation_w + 1) / 2;
+        out_h = im_h;
+        out_w = im_w;
+    } else {
+        p.padding_h = 0;
+        p.padding_w = 0;
+    }
+    p.out_h = out_h; p.out_w = out_w;
+    p.cell = filter_h * filter_w * channels;
+    p.total_cols = batches * out_h * out_w * p.cell;
+    p.total_images = images_size;
+    if (cols_size != p.total_cols) RB_INVALID("output buffer size is invalid");
+    if (channels_first) {
+        p.im_w_step = 1; p.im_h_step = im_w; p.channel_step = im_w * im_h; p.batch_step = im_w * im_h * channels;
+    } else {
+        p.channel_step = 1; p.im_w_step = channels; p.im_h_step = channels * im_w; p.batch_step = channels * im_w * im_h;
+    }
+    p.cols_channels_first = cols_channels_first ? 1 : 0;
+    if (p.batch_step >= (1LL << 31)) RB_INVALID("im2col2d: one image exceeds 2^31 elements");
+    if (filter_h * dilation_h >= 32768 || filter_w * dilation_w >= 32768) RB_INVALID("im2col2d: filter extent too large");
+
+    const int es = rb_dtype_size(dtype);
+    if (es == 0) RB_UNSUPPORTED("im2col2d: unsupported dtype %d", dtype);
+    char* im = reinterpret_cast<char*>(images) + images_offset * es;
+    char* co = reinterpret_cast<char*>(cols) + cols_offset * es;
+    if (!reverse) {
+        switch (es) {
+            case 1: return forward_launch<uint8_t>(p, im, co);
+            case 2: return forward_launch<uint16_t>(p, im, co);
+            case 4: return forward_launch<uint32_t>(p, im, co);
+            default: return forward_launch<uint64_t>(p, im, co);
+        }
+    }
+    switch (dtype) {
+        case RB200_FLOAT32: return reverse_launch<float>(p, im, co);
+        case RB200_FLOAT64: return reverse_launch<double>(p, im, co);
+        case RB200_INT32:   return reverse_launch<int32_t>(p, im, co);
+        case RB200_INT64:   return reverse_launch<int64_t>(p, im, co);
+        default: RB_UNSUPPORTED("col2im: unsupported dtype %d", dtype);
+    }
+}

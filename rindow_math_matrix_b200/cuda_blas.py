@@ -1,0 +1,154 @@
+"""CudaBlas -- the `blas()` object of the B200 service.
+
+Same positional signatures, validation order and exception strings as PhpBlas
+(src/Drivers/MatlibPHP/PhpBlas.php) + the Utils trait (src/Drivers/MatlibPHP/Utils.php:30-65);
+the arithmetic runs in librindow_b200.so (rb200_sgemm / rb200_dgemm).  Only the hot-path
+method (gemm) is on the device in this round; the remaining BLAS methods raise -- the PHP shim
+delegates those to PhpBlas on the host mirror, this package has no CPU path.
+"""
+from __future__ import annotations
+
+from . import _capi, dtypes
+from .cuda_buffer import CudaBuffer
+from .exceptions import InvalidArgumentException, LogicException, RuntimeException
+
+
+class BLAS:
+    """Interop\\Polite\\Math\\Matrix\\BLAS constants (CBLAS values; LinearAlgebra.php:16-17)."""
+    RowMajor = 101
+    ColMajor = 102
+    NoTrans = 111
+    Trans = 112
+    ConjTrans = 113
+    ConjNoTrans = 114
+
+
+def assert_shape_parameter(name: str, n: int) -> None:                     # Utils.php:30-36
+    if n < 1:
+        raise InvalidArgumentException("Argument %s must be greater than 0." % name)
+
+
+def assert_vector_buffer_spec(name: str, buffer, n: int, offset: int, inc: int) -> None:   # Utils.php:38-50
+    if offset < 0:
+        raise InvalidArgumentException("Argument offset%s must be greater than equals 0." % name)
+    if inc < 1:
+        raise InvalidArgumentException("Argument inc%s must be greater than 0." % name)
+    if offset + (n - 1) * inc >= len(buffer):
+        raise InvalidArgumentException("Vector specification too large for buffer%s." % name)
+
+
+def assert_matrix_buffer_spec(name: str, buffer, m: int, n: int, offset: int, ld: int) -> None:  # Utils.php:52-65
+    if offset < 0:
+        raise InvalidArgumentException("Argument offset%s must be greater than equals 0." % name)
+    if ld < 1:
+        raise InvalidArgumentException("Argument ld%s must be greater than 0." % name)
+    if offset + (m - 1) * ld + (n - 1) >= len(buffer):
+        raise InvalidArgumentException("Matrix specification too large for buffer%s." % name)
+
+
+def code_to_trans(trans: int):                                             # PhpBlas.php:104-123
+    if trans == BLAS.NoTrans:
+        return False, False
+    if trans == BLAS.Trans:
+        return True, False
+    if trans == BLAS.ConjTrans:
+        return True, True
+    if trans == BLAS.ConjNoTrans:
+        return False, True
+    raise InvalidArgumentException("Unknown Tranpose Code: %s" % trans)
+
+
+class CudaBlas:
+    def __init__(self, gemm_mode: int = _capi.GEMM_AUTO):
+        self._lib = _capi.load()
+        self.gemm_mode = gemm_mode
+
+    # ---- meta (PhpBlas.php:49-90) -----------------------------------------------------------
+    def getNumThreads(self) -> int:
+        return 1
+
+    def getNumProcs(self) -> int:
+        return 1
+
+    def getConfig(self) -> str:
+        return "CudaBlas sm_100a"
+
+    def getCorename(self) -> str:
+        return "B200"
+
+    def getParallel(self) -> int:
+        return 0        # 0 = SEQUENTIAL from the host's point of view (AbstractMatlibService.php:225-244)
+
+    def hasIamin(self) -> bool:
+        return True
+
+    def hasOmatcopy(self) -> bool:
+        return True     # must be true so transposes never go through GEMM
+
+    def setGemmMode(self, mode: int) -> None:
+        self.gemm_mode = mode
+
+    # ---- gemm (PhpBlas.php:849-948) -------------------------------------------------------------
+    def gemm(self, order, transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB,
+             beta, C, offsetC, ldC) -> None:
+        if order == BLAS.ColMajor:
+            m, n = n, m
+        elif order != BLAS.RowMajor:
+            raise InvalidArgumentException("Invalid Order type")
+        tA, _ = code_to_trans(transA)
+        tB, _ = code_to_trans(transB)
+        assert_shape_parameter("m", m)
+        assert_shape_parameter("n", n)
+        assert_shape_parameter("k", k)
+        rowsA, colsA = (m, k) if not tA else (k, m)
+        rowsB, colsB = (k, n) if not tB else (n, k)
+        assert_matrix_buffer_spec("A", A, rowsA, colsA, offsetA, ldA)
+        assert_matrix_buffer_spec("B", B, rowsB, colsB, offsetB, ldB)
+        assert_matrix_buffer_spec("C", C, m, n, offsetC, ldC)
+        for name, buf in (("A", A), ("B", B), ("C", C)):
+            if not isinstance(buf, CudaBuffer):
+                raise InvalidArgumentException("buffer%s is not a CudaBuffer" % name)
+        if not (A.dtype() == B.dtype() == C.dtype()):
+            raise InvalidArgumentException("Unmatch data type for A, B and C")
+        try:
+            alpha = float(alpha)
+        except (TypeError, ValueError):
+            raise RuntimeException("alpha is not float")                   # PhpBlas.php:133-139
+        try:
+            beta = float(beta)
+        except (TypeError, ValueError):
+            raise RuntimeException("beta is not float")
+        # m,n were already swapped for ColMajor: the ABI is called RowMajor
+        a_ptr, b_ptr = A.device_ptr(), B.device_ptr()
+        c_ptr = C.device_ptr_rw()
+        if A.dtype() == dtypes.float32:
+            _capi.check(self._lib.rb200_sgemm(BLAS.RowMajor, transA, transB, m, n, k, alpha, a_ptr, offsetA, ldA,
+                                              b_ptr, offsetB, ldB, beta, c_ptr, offsetC, ldC, self.gemm_mode))
+        elif A.dtype() == dtypes.float64:
+            _capi.check(self._lib.rb200_dgemm(BLAS.RowMajor, transA, transB, m, n, k, alpha, a_ptr, offsetA, ldA,
+                                              b_ptr, offsetB, ldB, beta, c_ptr, offsetC, ldC))
+        else:
+            raise LogicException("CudaBlas::gemm supports float32/float64; the reference routes integer "
+                                 "dtypes to the LV_BASIC PHP driver (MatrixOperator.php:225-231)")
+
+    def __getattr__(self, name):
+        if name in ("scal", "axpy", "dot", "dotu", "dotc", "asum", "iamax", "iamin", "copy", "nrm2", "rotg", "rot",
+                    "rotm", "rotmg", "swap", "gemv", "symm", "syrk", "syr2k", "trmm", "trsm", "omatcopy"):
+            def _not_on_device(*a, **k):
+                raise LogicException("CudaBlas::%s is not on the B200 hot path (SURVEY.md section 8f); the PHP "
+                                     "shim delegates it to PhpBlas, this package has no CPU fallback" % name)
+            return _not_on_device
+        raise AttributeError(name)
+
+
+class CudaBlasFactory:
+    """`openblasFactory` slot of AbstractMatlibService (:43-75): isAvailable(), Blas(), Lapack()."""
+
+    def isAvailable(self) -> bool:
+        return _capi.device_available()
+
+    def Blas(self) -> CudaBlas:
+        return CudaBlas()
+
+    def Lapack(self):
+        raise LogicException("LAPACK is out of scope (SURVEY.md section 2); the PHP shim returns PhpLapack")

@@ -1,0 +1,236 @@
+"""LinearAlgebra -- host LA API over a driver service.
+
+Mirror of the hot-path callers of Rindow\\Math\\Matrix\\LinearAlgebra (src/LinearAlgebra.php):
+shape checks -> (m,n,k,ld,offset) -> one positional driver call, with the reference's exception
+strings.  gemm :925-995, add :1968-2016, multiply :1921-1963, softmax :3138-3156,
+reduceSum/Max/ArgMax :3161-3336, im2col :3369, col2im :3434, im2col2d :3597-3701, plus the
+array/alloc/zeros/ones/fill plumbing those need (:193-330, :4662).  It is driver-agnostic, exactly
+like the PHP class: everything numeric goes through service.blas() / service.math().
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import dtypes
+from .cuda_blas import BLAS
+from .exceptions import InvalidArgumentException
+from .ndarray import NDArray
+from .service import Service
+
+
+def _intdiv(a: int, b: int) -> int:
+    return int(a / b) if b else 0        # PHP intdiv truncates toward zero
+
+
+class LinearAlgebra:
+    def __init__(self, service, defaultFloatType: int | None = None):
+        self.service = service
+        self.blas = service.blas()
+        self.math = service.math()
+        self.defaultFloatType = dtypes.float32 if defaultFloatType is None else defaultFloatType
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def accelerated(self) -> bool:
+        return self.service.serviceLevel() >= Service.LV_ADVANCED and type(self.blas).__name__.startswith("Cuda")
+
+    def array(self, array, dtype: int | None = None) -> NDArray:
+        if isinstance(array, NDArray):
+            return array
+        if dtype is None:
+            a = np.asarray(array)
+            if a.dtype == np.bool_:
+                dtype = dtypes.bool_
+            else:
+                dtype = self.defaultFloatType
+        return NDArray(array, dtype=dtype, service=self.service)
+
+    def alloc(self, shape, dtype: int | None = None) -> NDArray:
+        return NDArray(None, dtype=self.defaultFloatType if dtype is None else dtype, shape=shape,
+                       service=self.service)
+
+    def toNDArray(self, x: NDArray) -> NDArray:
+        return x
+
+    def fill(self, value, X: NDArray) -> NDArray:                               # LinearAlgebra.php:4662
+        V = NDArray([value], dtype=X.dtype(), service=self.service)
+        self.math.fill(X.size(), V.buffer(), V.offset(), X.buffer(), X.offset(), 1)
+        return X
+
+    def zeros(self, X: NDArray) -> NDArray:
+        self.math.zeros(X.size(), X.buffer(), X.offset(), 1)
+        return X
+
+    def ones(self, X: NDArray) -> NDArray:
+        return self.fill(1.0, X)
+
+    def zerosLike(self, X: NDArray) -> NDArray:
+        return self.zeros(self.alloc(X.shape(), X.dtype()))
+
+    # ---- C := alpha * AB + beta * C   (LinearAlgebra.php:925-995) -----------------------------------
+    def gemm(self, A: NDArray, B: NDArray, alpha=None, beta=None, C: NDArray | None = None,
+             transA=None, transB=None) -> NDArray:
+        transA, transB = bool(transA), bool(transB)
+        if A.ndim() != 2 or B.ndim() != 2:
+            raise InvalidArgumentException("Dimensions must be 2D-NDArray")
+        shapeA = A.shape()
+        if transA:
+            shapeA = [shapeA[1], shapeA[0]]
+        shapeB = B.shape()
+        if transB:
+            shapeB = [shapeB[1], shapeB[0]]
+        if shapeA[1] != shapeB[0]:
+            raise InvalidArgumentException(
+                'The number of columns in "A" and the number of rows in "B" must be the same')
+        M, N, K = shapeA[0], shapeB[1], shapeA[1]
+        if alpha is None:
+            alpha = 1.0
+        if beta is None:
+            beta = 0.0
+        if C is not None:
+            shapeC = C.shape()
+            if M != shapeC[0] or N != shapeC[1]:
+                raise InvalidArgumentException(
+                    '"A" and "C" must have the same number of rows."B" and "C" must have the same number of columns')
+        else:
+            C = self.zeros(self.alloc([M, N], dtype=A.dtype()))
+            beta = 0.0
+        lda = M if transA else K
+        ldb = K if transB else N
+        ldc = N
+        self.blas.gemm(BLAS.RowMajor, BLAS.Trans if transA else BLAS.NoTrans,
+                       BLAS.Trans if transB else BLAS.NoTrans, M, N, K, alpha,
+                       A.buffer(), A.offset(), lda, B.buffer(), B.offset(), ldb, beta,
+                       C.buffer(), C.offset(), ldc)
+        return C
+
+    # ---- broadcast elementwise (LinearAlgebra.php:1921-2016) ------------------------------------------
+    def _broadcast_mn(self, X: NDArray, A: NDArray, trans: bool, reversed_in_message: bool):
+        shapeX = X.shape()
+        shapeA = A.shape()
+        if trans:
+            shapeA = shapeA[::-1]
+        while True:
+            if not shapeX:
+                break
+            xd = shapeX.pop()
+            ad = shapeA.pop() if shapeA else None
+            if xd != ad:
+                shown = A.shape()[::-1] if (trans and reversed_in_message) else A.shape()
+                raise InvalidArgumentException("Unmatch dimension size for broadcast.: [%s] => [%s]" % (
+                    ",".join(map(str, X.shape())), ",".join(map(str, shown))))
+        n = X.size()
+        m = A.size() // n
+        if trans:
+            m, n = n, m
+        return m, n
+
+    def multiply(self, X: NDArray, A: NDArray, trans=None) -> NDArray:
+        trans = bool(trans)
+        m, n = self._broadcast_mn(X, A, trans, True)
+        self.math.multiply(trans, m, n, X.buffer(), X.offset(), 1, A.buffer(), A.offset(), n)
+        return A
+
+    def add(self, X: NDArray, A: NDArray, alpha=None, trans=None) -> NDArray:
+        trans = bool(trans)
+        if alpha is None:
+            alpha = 1.0
+        m, n = self._broadcast_mn(X, A, trans, False)
+        self.math.add(trans, m, n, alpha, X.buffer(), X.offset(), 1, A.buffer(), A.offset(), n)
+        return A
+
+    # ---- softmax (LinearAlgebra.php:3138-3156) ---------------------------------------------------------
+    def softmax(self, X: NDArray) -> NDArray:
+        if X.ndim() != 2:
+            raise InvalidArgumentException('"X" must be 2-D dimension')
+        m, n = X.shape()
+        self.math.softmax(m, n, X.buffer(), X.offset(), n)
+        return X
+
+    # ---- reductions (LinearAlgebra.php:3161-3336) --------------------------------------------------------
+    def _reduce_args(self, input: NDArray, axis, keepdims, output, dtype, default_dtype):
+        ndim = input.ndim()
+        origAxis = axis
+        if axis is None:
+            axis = 0                                      # ** CAUTION ** null is 0
+        if axis < 0:
+            axis = ndim + axis
+        if axis < 0 or axis > ndim - 1:
+            raise InvalidArgumentException("Invalid axis: %s" % ("null" if origAxis is None else origAxis))
+        shape = input.shape()
+        prefix, n, postfix = shape[:axis], shape[axis], shape[axis + 1:]
+        m = int(np.prod(prefix, dtype=np.int64)) if prefix else 1
+        k = int(np.prod(postfix, dtype=np.int64)) if postfix else 1
+        outputShape = prefix + ([1] if keepdims else []) + postfix
+        if dtype is None:
+            dtype = default_dtype
+        if output is None:
+            output = self.alloc(outputShape, dtype=dtype)
+        elif output.shape() != outputShape:
+            raise InvalidArgumentException("Unmatch shape of dimension: (%s),(%s)" % (
+                ",".join(map(str, input.shape())), ",".join(map(str, output.shape()))))
+        return m, n, k, output
+
+    def reduceSum(self, input: NDArray, axis=None, keepdims=None, output=None, dtype=None) -> NDArray:
+        m, n, k, output = self._reduce_args(input, axis, keepdims, output, dtype, input.dtype())
+        self.math.reduceSum(m, n, k, input.buffer(), input.offset(), output.buffer(), output.offset())
+        return output
+
+    def reduceMax(self, input: NDArray, axis=None, keepdims=None, output=None, dtype=None) -> NDArray:
+        m, n, k, output = self._reduce_args(input, axis, keepdims, output, dtype, input.dtype())
+        self.math.reduceMax(m, n, k, input.buffer(), input.offset(), output.buffer(), output.offset())
+        return output
+
+    def reduceArgMax(self, input: NDArray, axis=None, keepdims=None, output=None, dtype=None) -> NDArray:
+        m, n, k, output = self._reduce_args(input, axis, keepdims, output, dtype, dtypes.int32)
+        self.math.reduceArgMax(m, n, k, input.buffer(), input.offset(), output.buffer(), output.offset())
+        return output
+
+    # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    def im2col(self, images: NDArray, filterSize=None, strides=None, padding=None, channels_first=None,
+               dilation_rate=None, cols_channels_first=None, cols: NDArray | None = None) -> NDArray:
+        if images.ndim() != 4:
+            raise InvalidArgumentException("unsuppoted images shape")       # 1d/3d are SURVEY 8(f) "next" rows
+        _cols = self.im2col2d(False, images, filterSize, strides, padding, channels_first, dilation_rate,
+                              cols_channels_first, cols)
+        return _cols if cols is None else cols
+
+    def col2im(self, cols: NDArray, images: NDArray, filterSize=None, strides=None, padding=None,
+               channels_first=None, dilation_rate=None, cols_channels_first=None) -> NDArray:
+        if images.ndim() != 4:
+            raise InvalidArgumentException("unsuppoted images shape")
+        self.im2col2d(True, images, filterSize, strides, padding, channels_first, dilation_rate,
+                      cols_channels_first, cols)
+        return images
+
+    def im2col2d(self, reverse, images: NDArray, filterSize=None, strides=None, padding=None,
+                 channels_first=None, dilation_rate=None, cols_channels_first=None,
+                 cols: NDArray | None = None) -> NDArray:
+        if images.ndim() != 4:
+            raise InvalidArgumentException("images must be 4D dimension")
+        if channels_first:
+            batches, channels, in_h, in_w = images.shape()
+        else:
+            batches, in_h, in_w, channels = images.shape()
+        filter_h, filter_w = filterSize if filterSize else (3, 3)
+        stride_h, stride_w = strides if strides else (1, 1)
+        padding = bool(padding)
+        channels_first = bool(channels_first)
+        dilation_h, dilation_w = dilation_rate if dilation_rate else (1, 1)
+        cols_channels_first = bool(cols_channels_first)
+        if cols is None:
+            if padding:
+                out_h, out_w = in_h, in_w
+            else:
+                out_h = _intdiv(in_h - (filter_h - 1) * dilation_h - 1, stride_h) + 1
+                out_w = _intdiv(in_w - (filter_w - 1) * dilation_w - 1, stride_w) + 1
+            if out_h <= 0 or out_w <= 0:
+                raise InvalidArgumentException("Invalid shape or paramaters.")
+            if cols_channels_first:
+                shape = [batches, out_h, out_w, channels, filter_h, filter_w]
+            else:
+                shape = [batches, out_h, out_w, filter_h, filter_w, channels]
+            cols = self.zeros(self.alloc(shape, dtype=images.dtype()))
+        self.math.im2col2d(reverse, images.buffer(), images.offset(), images.size(), batches, in_h, in_w,
+                           channels, filter_h, filter_w, stride_h, stride_w, padding, channels_first,
+                           dilation_h, dilation_w, cols_channels_first, cols.buffer(), cols.offset(), cols.size())
+        return cols
