@@ -1,0 +1,497 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 driver for rindow-math-matrix.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the reference's CPU algorithm
+  torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU
+
+Metric (BASELINE.json): "sgemm TFLOP/s; add/reduceSum HBM GB/s at 1/2/4/8 B200 vs PHP CPU path".
+The step is one float32 GEMM C = A*B (NoTrans/NoTrans, alpha=1, beta=0) of M=N=K=8192 per GPU
+(config C5; with N GPUs the matrix A/C is row-sharded: rank g owns rows [g*8192,(g+1)*8192) of an
+(8192*N) x 8192 problem, B replicated, no data-path collective -> weak scaling), issued through the
+reference-facing plugin interface (service.blas().gemm(...) with the PhpBlas signature) down the C
+ABI.  `value` times device-resident operands; `e2e` times the same call with HOST buffers (pinned
+host mirror -> h2d -> kernel -> d2h inside the timed region).  The HBM-bound configs (C2/C3/C4:
+add, multiply, reduceSum/Max/ArgMax, softmax, im2col2d) are reported in "hbm_ops" of the same JSON
+line with their own roofline fractions; other GEMM modes in "gemm_modes".
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sgemm TFLOP/s"
+UNIT = "TFLOP/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        # fallback stated by /opt/skills/guides/B200_PROFILING.md
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload_config(n, world, mode_name):
+    return {
+        "workload": "sgemm M=N=K=%d per GPU (BASELINE config C5), NoTrans/NoTrans, alpha=1, beta=0" % n,
+        "gemm_mode": mode_name,
+        "tolerance": {"tf32": "max|err| < 2e-3*max|C| (1xTF32; outside the reference isclose rtol 1e-4 by design)",
+                      "tf32x3": "max|err| < 1e-4*max|C| (reference isclose bound)",
+                      "fp32_simt": "max|err| < 1e-4*max|C| (reference isclose bound)"}[mode_name],
+        "global_shape": [n * world, n, n],
+        "parallelism": "row-sharded A/C over %d GPU(s), B replicated, no data-path collective" % world,
+        "l2": "inputs exceed L2: %d MiB working set per GPU vs 126 MB L2" % (3 * n * n * 4 >> 20),
+    }
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks: NVML sampler thread (nvidia-smi would give <1 sample in a 50 ms region)
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, local_rank):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        self.sm_max = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (C restatement of PhpBlas::gemm) on the host cores
+# -------------------------------------------------------------------------------------------------
+def reference_gemm_sample(n, rows_total, threads, A64=None, B64=None):
+    """Compute `rows_total` rows of C = A*B with the reference loop order (oracle.gemm_rows), spread
+    over `threads` host threads (ctypes releases the GIL).  Returns (seconds, rows, C_rows)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    if A64 is None:
+        lg = int(np.log2(n))
+        A64 = oracle.as_buffer(np.random.default_rng(5000 + lg).uniform(-1, 1, n * n).astype(np.float32))
+        B64 = oracle.as_buffer(np.random.default_rng(5100 + lg).uniform(-1, 1, n * n).astype(np.float32))
+    C = np.zeros(rows_total * n)
+    rows = list(range(rows_total))
+    chunks = [rows[i::threads] for i in range(threads)]
+
+    def work(chunk):
+        for r in chunk:
+            oracle.gemm_rows(r, 1, n, n, 1.0, A64, n, B64, n, 0.0, C, n)     # row r of A -> row r of the sample
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, chunks))
+    return time.perf_counter() - t0, rows_total, C.reshape(rows_total, n)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return 0
+    import oracle
+    n = args.n
+    cores = os.cpu_count() or 1
+    lg = int(np.log2(n))
+    A64 = oracle.as_buffer(np.random.default_rng(5000 + lg).uniform(-1, 1, n * n).astype(np.float32))
+    B64 = oracle.as_buffer(np.random.default_rng(5100 + lg).uniform(-1, 1, n * n).astype(np.float32))
+    # calibrate one row per thread, then size the per-step sample so the run stays within ~2.5 minutes
+    t_cal, _, _ = reference_gemm_sample(n, cores, cores, A64, B64)
+    budget = 150.0
+    total_steps = args.steps + args.warmup
+    rows_per_step = cores
+    if t_cal * total_steps > budget:
+        rows_per_step = max(1, int(cores * budget / (t_cal * total_steps)))
+    threads = min(cores, rows_per_step)
+    for _ in range(args.warmup):
+        reference_gemm_sample(n, rows_per_step, threads, A64, B64)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _, _ = reference_gemm_sample(n, rows_per_step, threads, A64, B64)
+        t += dt
+    flops = 2.0 * rows_per_step * n * n * args.steps
+    value = flops / t / 1e12
+    sample = ("%d of %d rows of C per step (N=K=%d), reference loop order m,n,k in double "
+              "(C restatement of PhpBlas::gemm; the PHP interpreter is not installable here and would be "
+              "much slower), %d thread(s)" % (rows_per_step, n, n, threads))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(n, world, "fp32_simt") | {"gemm_mode": "reference (double)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# this repo's arm
+# -------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        log("bench.py --gpus %d without torchrun: running rank 0 only; launch with torch.distributed.run" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 driver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import rindow_math_matrix_b200 as rb
+    from rindow_math_matrix_b200 import BLAS, CudaBuffer, _capi, dtypes
+
+    _capi.init(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    _capi.set_stream(stream.cuda_stream)              # kernels + events on the same stream
+    svc = rb.MatlibCuda()
+    assert svc.serviceLevel() >= rb.Service.LV_ADVANCED
+    blas, math = svc.blas(), svc.math()
+    peaks = measured_peaks()
+    mode = {"tf32": rb.GEMM_TF32, "tf32x3": rb.GEMM_TF32X3, "fp32_simt": rb.GEMM_FP32_SIMT}[args.mode]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, steps, warmup):
+        """W untimed calls, then exactly `steps` calls between two events on the launching stream,
+        barrier + synchronize on both sides, max over ranks.  Returns total ms."""
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                fn()
+            e1.record(stream)
+            barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- operands (resident in HBM before the timed region) ----------------------------------------
+    n = args.n
+    lg = int(np.log2(n))
+    Ah = np.random.default_rng(5000 + lg + 1000 * rank).uniform(-1, 1, n * n).astype(np.float32)
+    Bh = np.random.default_rng(5100 + lg).uniform(-1, 1, n * n).astype(np.float32)
+    A = CudaBuffer(n * n, dtypes.float32, zero=False).from_numpy(Ah)
+    B = CudaBuffer(n * n, dtypes.float32, zero=False).from_numpy(Bh)
+    C = CudaBuffer(n * n, dtypes.float32)
+    _capi.sync()
+
+    def gemm_step(m=mode):
+        blas.setGemmMode(m)
+        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A, 0, n, B, 0, n, 0.0, C, 0, n)
+
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        # keep the sampler running over a region long enough to see load clocks even for small K
+        _capi.launch_count(reset=True)
+        t_pre = time.perf_counter()
+        total_ms = timed(gemm_step, args.steps, args.warmup)
+        launches = _capi.launch_count() - 0
+        warm_launches = launches * args.warmup // (args.steps + args.warmup)
+        gpu_launches = launches - warm_launches
+        while time.perf_counter() - t_pre < 0.25:       # pad with the same kernel so NVML sees load
+            timed(gemm_step, 5, 0)
+    gemm_path = _capi.last_gemm_path()
+    ms_per_step = total_ms / args.steps
+    flops_per_step = 2.0 * n * n * n
+    value = world * flops_per_step / (ms_per_step * 1e-3) / 1e12
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    achieved = flops_per_step / (ms_per_step * 1e-3) / 1e12
+    if args.mode == "tf32x3":
+        achieved_note = "algorithmic flops 2*N^3 (the kernel issues 3x that on the tensor pipe)"
+    else:
+        achieved_note = "algorithmic flops 2*N^3"
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": None,
+                "kernel": gemm_path,
+                "peak_note": "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); %s"
+                             % (peaks["source"], achieved_note)}
+
+    # ---- e2e: the same call with HOST buffers (pinned mirror -> h2d, kernel, d2h) --------------------
+    A.host(); B.host(); C.host()                      # create the pinned mirrors outside the timed region
+    _capi.sync()
+
+    def e2e_step():
+        A.mark_host_written()                          # this step's inputs live in pinned host memory
+        B.mark_host_written()
+        gemm_step()                                    # flushes A,B (h2d) then launches
+        C.host()                                       # d2h read of the result (synchronises)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
+    e2e = {"value": world * flops_per_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
+           "h2d_bytes_per_step": 2 * n * n * 4, "d2h_bytes_per_step": n * n * 4, "ms_per_step": e2e_ms,
+           "steps": e2e_steps}
+
+    # ---- other GEMM modes + cuBLAS TF32 for context ---------------------------------------------------
+    gemm_modes = {}
+    if not args.quick:
+        for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3), ("fp32_simt", rb.GEMM_FP32_SIMT)):
+            if name == args.mode:
+                gemm_modes[name] = {"tflops_per_gpu": achieved, "ms": ms_per_step}
+                continue
+            k = 3 if name == "fp32_simt" else max(3, min(args.steps, 10))
+            ms = timed(lambda mm=mm: gemm_step(mm), k, 1) / k
+            gemm_modes[name] = {"tflops_per_gpu": flops_per_step / (ms * 1e-3) / 1e12, "ms": ms}
+        try:
+            ta = torch.as_tensor(A, device="cuda").view(n, n)
+            tb = torch.as_tensor(B, device="cuda").view(n, n)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            with torch.cuda.stream(stream):
+                tc = torch.empty(n, n, device="cuda")
+            ms = timed(lambda: torch.matmul(ta, tb, out=tc), max(3, min(args.steps, 10)), 2) / max(3, min(args.steps, 10))
+            gemm_modes["cublas_tf32_via_torch"] = {"tflops_per_gpu": flops_per_step / (ms * 1e-3) / 1e12, "ms": ms,
+                                                   "note": "library GEMM for context, not on the product path"}
+        except Exception as e:  # pragma: no cover
+            log("cuBLAS TF32 context measurement failed:", e)
+
+    # ---- HBM-bound configs (C2, C3, C4): rotating buffer sets defeat L2 --------------------------------
+    hbm_ops = {}
+    if not args.quick:
+        hbm_ops = run_hbm_ops(args, svc, timed, peaks, world, rank)
+
+    # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same GEMM with the oracle ---------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = 8
+        t, _, Cref = reference_gemm_sample(n, rows, 1, oracle_inputs(Ah), oracle_inputs(Bh))
+        gemm_step()
+        got = C.to_numpy().reshape(n, n)[:rows].astype(np.float64)
+        err = float(np.max(np.abs(got - Cref)) / np.max(np.abs(Cref)))
+        cpu_baseline = {
+            "value": 2.0 * rows * n * n / t / 1e12, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d of %d rows of C (N=K=%d), reference loop order m,n,k in double, 1 thread (the reference "
+                      "reports 1 thread, PhpBlas.php:49-54); C restatement of PhpBlas::gemm -- the PHP interpreter "
+                      "itself is not installable here and would be much slower" % (rows, n, n),
+            "seconds": t, "gpu_vs_oracle_max_rel_err_on_sample": err,
+        }
+        # numpy / OpenBLAS on all cores for context
+        try:
+            k = 4096
+            a = Ah[: k * k].reshape(k, k)
+            b = Bh[: k * k].reshape(k, k)
+            a @ b
+            t0 = time.perf_counter()
+            a @ b
+            t1 = time.perf_counter() - t0
+            cpu_baseline["numpy_openblas_sgemm"] = {"value": 2.0 * k ** 3 / t1 / 1e12, "unit": UNIT,
+                                                    "cores": os.cpu_count(), "n": k}
+        except Exception:
+            pass
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"tf32": "tf32 (f32 in/out, f32 accumulate)",
+                                           "tf32x3": "3xtf32 (f32 in/out, f32 accumulate)",
+                                           "fp32_simt": "f32"}[args.mode],
+            "data": "synthetic", "config": workload_config(n, world, args.mode),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
+            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "hbm_ops": hbm_ops,
+            "peaks": peaks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def oracle_inputs(a32):
+    import oracle
+    return oracle.as_buffer(a32)
+
+
+def run_hbm_ops(args, svc, timed, peaks, world, rank):
+    """C2/C3/C4 at BASELINE sizes; each op cycles through 3 operand sets (> L2) so every launch
+    streams from HBM.  GB/s uses the ALGORITHMIC bytes of SURVEY.md section 8(d)."""
+    from rindow_math_matrix_b200 import CudaBuffer, dtypes
+    math = svc.math()
+    out = {}
+    sets = 3
+    steps = max(6, min(args.steps, 30))
+    steps -= steps % sets
+    hbm = peaks["hbm_gbs"]
+
+    def report(name, fn, bytes_per_call, extra=None):
+        state = {"i": 0}
+
+        def step():
+            fn(state["i"] % sets)
+            state["i"] += 1
+        ms = timed(step, steps, sets) / steps
+        gbs = bytes_per_call / (ms * 1e-3) / 1e9
+        out[name] = {"GB/s_per_gpu": gbs, "GB/s": gbs * world, "frac_of_measured_hbm": gbs / hbm,
+                     "frac_of_nominal_8TBs": gbs / 8000.0, "ms": ms, "algorithmic_bytes": bytes_per_call}
+        if extra:
+            out[name].update(extra)
+
+    rng = np.random.default_rng(2001 + rank)
+    # C2: add / multiply f32 [8192,4096] (+|x) [4096]
+    m, n = 8192, 4096
+    a0 = rng.uniform(-1, 1, m * n).astype(np.float32)
+    As = [CudaBuffer(m * n, dtypes.float32, zero=False).from_numpy(a0) for _ in range(sets)]
+    X = CudaBuffer(n, dtypes.float32, zero=False).from_numpy(rng.uniform(0.9, 1.1, n).astype(np.float32))
+    ew_bytes = 2 * m * n * 4 + n * 4
+    report("add", lambda i: math.add(False, m, n, 1.0, X, 0, 1, As[i], 0, n), ew_bytes,
+           {"shape": "[8192,4096] + [4096]"})
+    report("multiply", lambda i: math.multiply(False, m, n, X, 0, 1, As[i], 0, n), ew_bytes,
+           {"shape": "[8192,4096] * [4096]"})
+    del As
+    # C3: reductions / softmax on f32 [65536,1024] axis=1
+    m, n = 65536, 1024
+    r0 = np.random.default_rng(3001 + rank).uniform(-1, 1, m * n).astype(np.float32)
+    Rs = [CudaBuffer(m * n, dtypes.float32, zero=False).from_numpy(r0) for _ in range(sets)]
+    Bf = CudaBuffer(m, dtypes.float32)
+    Bi = CudaBuffer(m, dtypes.int32)
+    rd_bytes = m * n * 4 + m * 4
+    report("reduceSum", lambda i: math.reduceSum(m, n, 1, Rs[i], 0, Bf, 0), rd_bytes, {"shape": "[65536,1024] axis=1"})
+    report("reduceMax", lambda i: math.reduceMax(m, n, 1, Rs[i], 0, Bf, 0), rd_bytes, {"shape": "[65536,1024] axis=1"})
+    report("reduceArgMax", lambda i: math.reduceArgMax(m, n, 1, Rs[i], 0, Bi, 0), rd_bytes,
+           {"shape": "[65536,1024] axis=1"})
+    report("reduceSum_axis0", lambda i: math.reduceSum(1, m, n, Rs[i], 0, Bf, 0), m * n * 4 + n * 4,
+           {"shape": "[65536,1024] axis=0 (split + merge path)"})
+    report("softmax", lambda i: math.softmax(m, n, Rs[i], 0, n), 2 * m * n * 4, {"shape": "[65536,1024] in place"})
+    del Rs
+    # C4: im2col2d 64x224x224x3, 3x3, stride 1, valid padding
+    b, h, w, c = 64, 224, 224, 3
+    img = np.random.default_rng(4001 + rank).uniform(0, 1, b * h * w * c).astype(np.float32)
+    images = CudaBuffer(img.size, dtypes.float32, zero=False).from_numpy(img)
+    ncols = b * 222 * 222 * 27
+    cols = [CudaBuffer(ncols, dtypes.float32, zero=False) for _ in range(2)]
+    ic_bytes = img.size * 4 + ncols * 4
+    sets_saved = sets
+    sets = 2
+    steps -= steps % sets
+    report("im2col2d", lambda i: math.im2col2d(False, images, 0, img.size, b, h, w, c, 3, 3, 1, 1, False, False, 1, 1,
+                                                False, cols[i], 0, ncols), ic_bytes,
+           {"shape": "64x224x224x3, 3x3 valid -> [64,222,222,3,3,3]"})
+    # conv gemm [3154176 x 27] x [27 x 64] (HBM-bound: report GB/s on the per-call bytes)
+    from rindow_math_matrix_b200 import BLAS
+    blas = svc.blas()
+    M = b * 222 * 222
+    Wt = CudaBuffer(27 * 64, dtypes.float32, zero=False).from_numpy(
+        (np.random.default_rng(4002).standard_normal(27 * 64) * 0.1).astype(np.float32))
+    outs = [CudaBuffer(M * 64, dtypes.float32, zero=False) for _ in range(2)]
+    from rindow_math_matrix_b200 import _capi
+    blas.setGemmMode(0)
+    conv_bytes = ncols * 4 + 27 * 64 * 4 + M * 64 * 4
+    report("conv_gemm", lambda i: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, 64, 27, 1.0, cols[i], 0, 27,
+                                            Wt, 0, 64, 0.0, outs[i], 0, 64), conv_bytes,
+           {"shape": "[3154176,27] x [27,64]", "flops": 2.0 * M * 27 * 64})
+    out["conv_gemm"]["path"] = _capi.last_gemm_path()
+    sets = sets_saved
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8192, help="sgemm size per GPU (M=N=K)")
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "tf32x3", "fp32_simt"])
+    ap.add_argument("--quick", action="store_true", help="headline workload only (no hbm_ops / other modes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("bench.py: raising --warmup to the required minimum of 3")
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

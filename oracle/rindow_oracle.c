@@ -174,6 +174,33 @@ int ro_gemm_rows(int64_t row0, int64_t rows,
     return RO_OK;
 }
 
+/* Same results as ro_gemm_rows, bit for bit, with the n and k loops interchanged: every
+ * C[im,in] still receives its products in k = 0..K-1 order (no reassociation inside an
+ * element, no FMA), only independent elements are interleaved.  Used by the tests to check
+ * sampled rows of large GEMMs in seconds; never timed as the baseline. */
+int ro_gemm_rows_interleaved(int64_t row0, int64_t rows,
+                             int64_t n, int64_t k, double alpha,
+                             const double *A, int64_t ldA, const double *B, int64_t ldB,
+                             double beta, double *C, int64_t ldC, double *acc /* n scratch */)
+{
+    for (int64_t im = row0; im < row0 + rows; im++) {
+        const double *a = A + im * ldA;
+        for (int64_t in = 0; in < n; in++) acc[in] = 0.0;
+        for (int64_t ik = 0; ik < k; ik++) {
+            const double av = a[ik];
+            const double *b = B + ik * ldB;
+            for (int64_t in = 0; in < n; in++) {
+                acc[in] += av * b[in];
+            }
+        }
+        double *c = C + im * ldC;
+        for (int64_t in = 0; in < n; in++) {
+            if (beta == 0.0) c[in] = alpha * acc[in]; else c[in] = alpha * acc[in] + beta * c[in];
+        }
+    }
+    return RO_OK;
+}
+
 /* MatrixOperator::gemm3, src/MatrixOperator.php:510-529 (cross() with rank(B) > 2). */
 int ro_gemm3(int64_t M, int64_t N, int64_t K, int64_t L, double alpha,
              const double *A, int64_t offA, const double *B, int64_t offB,

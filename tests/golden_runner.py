@@ -1,0 +1,172 @@
+"""Runs the golden known-answer cases (tests/golden/known_answers.json) through the host classes
+(LinearAlgebra / MatrixOperator / NDArray) over ANY driver service -- the oracle service on CPU,
+the CUDA service on the GPU.  The same thing the reference does when LinearAlgebraCLTest re-runs
+LinearAlgebraTest over another driver (tests/.../LinearAlgebraCLTest.php:722-758)."""
+import json
+import math
+import os
+
+import numpy as np
+
+from rindow_math_matrix_b200 import InvalidArgumentException, LinearAlgebra, MatrixOperator
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_known_answers():
+    with open(os.path.join(HERE, "golden", "known_answers.json")) as f:
+        return json.load(f)
+
+
+def _num(v):
+    if isinstance(v, str):
+        return {"inf": math.inf, "-inf": -math.inf, "nan": math.nan}[v]
+    return v
+
+
+def _arr(x):
+    if isinstance(x, list):
+        return [_arr(v) for v in x]
+    return _num(x)
+
+
+def _assert_equal(expect, got, tol=0.0):
+    e = np.array(_arr(expect), dtype=np.float64)
+    g = np.array(got, dtype=np.float64)
+    assert e.shape == g.shape, (e.shape, g.shape)
+    if tol:
+        assert np.allclose(e, g, rtol=0, atol=tol, equal_nan=True), (e, g)
+    else:
+        assert np.array_equal(e, g, equal_nan=True), (e, g)
+
+
+def run_case(case, service):
+    mo = MatrixOperator(service)
+    la = LinearAlgebra(service)
+    op = case["op"]
+    kw = dict(case.get("kwargs", {}))
+
+    def call():
+        if op == "gemm":
+            A, B = la.array(_arr(case["A"])), la.array(_arr(case["B"]))
+            C = la.array(_arr(case["C"])) if "C" in case else None
+            out = la.gemm(A, B, C=C, **kw)
+            if C is not None:
+                assert out is C
+            return out
+        if op == "cross":
+            A, B = mo.array(_arr(case["A"])), mo.array(_arr(case["B"]))
+            if "viewA" in case:
+                A = A[case["viewA"]]
+                assert A.offset() == case["offsetA"]
+            if "viewB" in case:
+                B = B[case["viewB"]]
+                assert B.offset() == case["offsetB"]
+            a0, b0 = A.toArray(), B.toArray()
+            out = mo.cross(A, B)
+            assert A.toArray() == a0 and B.toArray() == b0       # operands untouched
+            return out
+        if op in ("add", "multiply"):
+            X, A = la.array(_arr(case["X"])), la.array(_arr(case["A"]))
+            x0 = X.toArray()
+            out = getattr(la, op)(X, A, **kw)
+            assert out is A and X.toArray() == x0
+            return out
+        if op in ("reduceSum", "reduceMax", "reduceArgMax"):
+            if "x_ones" in case:
+                x = la.ones(la.alloc(case["x_ones"]))
+            else:
+                x = la.array(_arr(case["x"]))
+            if "view" in case:
+                x = x[case["view"]]
+            return getattr(la, op)(x, **kw)
+        if op == "softmax":
+            return la.softmax(la.array(_arr(case["x"])))
+        raise AssertionError("unknown op " + op)
+
+    if "error" in case:
+        try:
+            call()
+        except InvalidArgumentException as e:
+            assert case["error"] in str(e), str(e)
+        else:
+            raise AssertionError("expected InvalidArgumentException: " + case["error"])
+        return
+    out = call()
+    if "expect_shape" in case:
+        assert out.shape() == case["expect_shape"]
+    if "expect" in case:
+        _assert_equal(case["expect"], out.toArray(), case.get("tol", 0.0))
+    if "expect_row0" in case:
+        _assert_equal(case["expect_row0"], out.toArray()[0], case["tol"])
+        _assert_equal(case["expect_row0"], out.toArray()[-1], case["tol"])
+
+
+def im2col_reference_loops(params, images_np):
+    """The index loops the reference TEST uses to build its expectation
+    (LinearAlgebraTest.php:8962-9005 forward, :9190-9221 reverse) -- independent of PhpMath, so
+    it pins both the oracle and the CUDA path.  Returns (cols_expect, images_back_expect)."""
+    p = {k: (v if v is not None else 0) for k, v in params.items()}
+    b_, im_h, im_w, ch = p["batches"], p["im_h"], p["im_w"], p["channels"]
+    kh, kw, sh, sw = p["kernel_h"], p["kernel_w"], p["stride_h"], p["stride_w"]
+    dh, dw = p["dilation_h"], p["dilation_w"]
+    padding, cf, ccf = bool(params["padding"]), bool(params["channels_first"]), bool(params["cols_channels_first"])
+    out_h = int((im_h - (kh - 1) * dh - 1) / sh) + 1
+    out_w = int((im_w - (kw - 1) * dw - 1) / sw) + 1
+    if padding:
+        ph = int(((im_h - 1) * sh - im_h + (kh - 1) * dh + 1) / 2)
+        pw = int(((im_w - 1) * sw - im_w + (kw - 1) * dw + 1) / 2)
+        out_h, out_w = im_h, im_w
+    else:
+        ph = pw = 0
+    shape = (b_, out_h, out_w, ch, kh, kw) if ccf else (b_, out_h, out_w, kh, kw, ch)
+    flat_im = images_np.reshape(-1)
+    trues = np.zeros(int(np.prod(shape)))
+    back = np.zeros(flat_im.size)
+    for b in range(b_):
+        for c in range(ch):
+            for y in range(out_h):
+                for x in range(out_w):
+                    for ky in range(kh):
+                        for kx in range(kw):
+                            iy = y * sh + ky * dh - ph
+                            ix = x * sw + kx * dw - pw
+                            if cf:
+                                iid = ((b * ch + c) * im_h + iy) * im_w + ix
+                            else:
+                                iid = ((b * im_h + iy) * im_w + ix) * ch + c
+                            if ccf:
+                                cid = ((((b * out_h + y) * out_w + x) * ch + c) * kh + ky) * kw + kx
+                            else:
+                                cid = ((((b * out_h + y) * out_w + x) * kh + ky) * kw + kx) * ch + c
+                            if 0 <= iy < im_h and 0 <= ix < im_w:
+                                trues[cid] = flat_im[iid]
+                                back[iid] += flat_im[iid]
+    return trues.reshape(shape), back.reshape(images_np.shape)
+
+
+def run_im2col_case(params, service):
+    """testIm2col2dNormal (LinearAlgebraTest.php:8903-9221) for one provider row."""
+    la = LinearAlgebra(service)
+    p = params
+    n = p["batches"] * p["im_h"] * p["im_w"] * p["channels"]
+    arange = np.arange(n, dtype=np.float32)
+    if p["channels_first"]:
+        shape = [p["batches"], p["channels"], p["im_h"], p["im_w"]]
+    else:
+        shape = [p["batches"], p["im_h"], p["im_w"], p["channels"]]
+    images = la.array(arange.reshape(shape))
+    cols = la.im2col(images, filterSize=[p["kernel_h"], p["kernel_w"]], strides=[p["stride_h"], p["stride_w"]],
+                     padding=p["padding"], channels_first=p["channels_first"],
+                     dilation_rate=[p["dilation_h"], p["dilation_w"]],
+                     cols_channels_first=p["cols_channels_first"])
+    trues, back = im2col_reference_loops(p, arange.reshape(shape).astype(np.float64))
+    assert cols.shape() == list(trues.shape)
+    assert np.array_equal(np.asarray(cols.toArray(), dtype=np.float64), trues)
+    newImages = la.zerosLike(images)
+    la.col2im(cols, newImages, filterSize=[p["kernel_h"], p["kernel_w"]], strides=[p["stride_h"], p["stride_w"]],
+              padding=p["padding"], channels_first=p["channels_first"],
+              dilation_rate=[p["dilation_h"], p["dilation_w"]], cols_channels_first=p["cols_channels_first"])
+    assert np.array_equal(np.asarray(newImages.toArray(), dtype=np.float64), back)
+    # im2col left the images untouched
+    assert np.array_equal(np.asarray(images.toArray(), dtype=np.float64), arange.reshape(shape))

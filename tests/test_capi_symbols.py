@@ -1,0 +1,60 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/rindow_b200.h declares
+(no compute calls here).  CPU only."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from rindow_math_matrix_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "rindow_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb200_\w+)\s*\(", text)))
+
+
+def test_library_exists_and_loads():
+    assert os.path.exists(_capi.LIB_PATH), "run __graft_entry__.build()"
+    lib = _capi.load()
+    assert lib.rb200_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for name in syms:
+        assert hasattr(lib, name), "librindow_b200.so does not export " + name
+        assert name in _capi.SIGNATURES, "ctypes binding misses " + name
+    assert sorted(_capi.SIGNATURES) == syms          # and binds nothing the header does not declare
+
+
+def test_compute_without_init_fails_loudly():
+    """No device / no init -> a status + message, never a silent CPU path."""
+    lib = _capi.load()
+    if _capi.is_initialised():
+        pytest.skip("a GPU is present and initialised in this process")
+    rc = lib.rb200_add(12, 0, 1, 1, 1.0, None, 0, 1, None, 0, 1)
+    assert rc == _capi.E_NOTINIT
+    assert b"rb200_init" in lib.rb200_last_error()
+    with pytest.raises(_capi.B200Error):
+        _capi.check(rc)
+
+
+def test_library_is_sm100a_only_with_blackwell_instructions():
+    """cuobjdump shows sm_100a code with tcgen05 (UTCHMMA), TMA (UTMALDG) and TMEM loads (LDTM)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", elf))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic

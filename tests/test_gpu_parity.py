@@ -1,0 +1,664 @@
+"""Parity of the CUDA path (through the C ABI, via the host mirror classes) against the CPU oracle
+and the reference's golden vectors.  Every test needs a B200:  pytest -m gpu
+
+Tolerances (stated per test):
+  * integer / index / copy work (argmax, im2col2d, max): bit-exact;
+  * multiply, add with |alpha| == 1: bit-exact against the oracle's double result rounded once to
+    float32 (a float32 product is exact in double; double rounding of a sum of two float32 is
+    innocuous since 53 >= 2*24+2);
+  * everything else in float32: the reference's own isclose bound, max|d| < 1e-7 + 1e-4*max|ref|
+    (src/LinearAlgebra.php:5439-5464), with the much tighter measured bound asserted next to it;
+  * 1xTF32 GEMM: its own stated bound (2e-3 * max|C|), outside the reference bound by design.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_runner as gr
+import oracle
+import rindow_math_matrix_b200 as rb
+from rindow_math_matrix_b200 import BLAS, CudaBuffer, LinearAlgebra, MatrixOperator, NDArray, dtypes
+
+pytestmark = pytest.mark.gpu
+
+KA = gr.load_known_answers()
+with open(os.path.join(gr.HERE, "golden", "im2col2d_cases.json")) as f:
+    IM2COL = json.load(f)["cases"]
+
+
+def isclose_ref(got, ref, rtol=1e-4, atol=1e-7):
+    """LinearAlgebra::isclose (src/LinearAlgebra.php:5439-5464): max-norm test."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.max(np.abs(got - ref)) < atol + rtol * np.max(np.abs(ref))
+
+
+def buf(a, dtype=dtypes.float32):
+    a = np.asarray(a)
+    return CudaBuffer(a.size, dtype).from_numpy(a.reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors of the reference's PHPUnit suite, through the CUDA service
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", KA["cases"], ids=[c["id"] for c in KA["cases"]])
+def test_known_answer(case, cuda_service):
+    gr.run_case(case, cuda_service)
+
+
+@pytest.mark.parametrize("mode", [rb.GEMM_FP32_SIMT, rb.GEMM_TF32, rb.GEMM_TF32X3])
+def test_known_answer_gemm_all_modes(mode):
+    svc = rb.MatlibCuda(gemm_mode=mode)
+    for case in KA["cases"]:
+        if case["op"] in ("gemm", "cross"):
+            gr.run_case(case, svc)
+
+
+@pytest.mark.parametrize("case", IM2COL, ids=[c["name"].replace(" ", "_") for c in IM2COL])
+def test_im2col2d_provider(case, cuda_service):
+    gr.run_im2col_case(case["params"], cuda_service)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's "Large" tests (run only on accelerated drivers there)
+# ---------------------------------------------------------------------------------------------------
+def _large(cid):
+    return next(c for c in KA["large"]["cases"] if c["id"] == cid)
+
+
+@pytest.mark.parametrize("cid", ["multiply_large", "add_large"])
+def test_large_elementwise(cid, cuda_service):
+    c = _large(cid)
+    la = LinearAlgebra(cuda_service)
+    x = la.fill(c["x_fill"], la.alloc([c["rows"], c["cols"]]))
+    y = la.fill(c["a_fill"], la.alloc([c["rows"], c["cols"]]))
+    r = getattr(la, c["op"])(x, y)
+    assert np.max(np.abs(r.to_numpy() - c["expect_fill"])) < 1e-3
+
+
+@pytest.mark.parametrize("cid", ["reducesum_large_wide", "reducesum_large_tall", "reducemax_large",
+                                 "reduceargmax_large"])
+def test_large_reductions(cid, cuda_service):
+    c = _large(cid)
+    la = LinearAlgebra(cuda_service)
+    x = la.fill(c["fill"], la.alloc([c["rows"], c["cols"]]))
+    r = getattr(la, c["op"])(x, axis=1)
+    assert r.shape() == [c["rows"]]
+    assert np.max(np.abs(r.to_numpy().astype(np.float64) - c["expect_fill"])) < 1e-3
+
+
+def test_large_reducemax_nan_table(cuda_service):
+    c = _large("reducemax_large_nan_sticky")
+    la = LinearAlgebra(cuda_service)
+    for cols in c["cols_list"]:
+        x = np.zeros((6, cols), np.float32)
+        for r, head in enumerate(c["heads"]):
+            x[r, :2] = [gr._num(v) for v in head]
+        got = la.reduceMax(la.array(x), axis=1).to_numpy()
+        gr._assert_equal(c["expect"], got)
+
+
+@pytest.mark.parametrize("cid", ["softmax_large_wide", "softmax_large_tall"])
+def test_large_softmax(cid, cuda_service):
+    c = _large(cid)
+    la = LinearAlgebra(cuda_service)
+    x = la.ones(la.alloc([c["rows"], c["cols"]]))
+    r = la.softmax(x).to_numpy()
+    assert np.max(np.abs(r - 1.0 / c["cols"])) < 1e-3
+
+
+def test_large_im2col2d(cuda_service):
+    c = _large("im2col2d_large")
+    la = LinearAlgebra(cuda_service)
+    n = c["im_h"] * c["im_w"] * c["channels"]
+    img = np.arange(n, dtype=np.float32).reshape(1, c["im_h"], c["im_w"], c["channels"])
+    images = la.array(img)
+    cols = la.im2col(images, filterSize=[3, 3])
+    got = cols.to_numpy()
+    # index identity: cols[b,oy,ox,ky,kx,c] = images[b,oy+ky,ox+kx,c]  (values < 2^24: exact in f32)
+    win = np.lib.stride_tricks.sliding_window_view(img, (3, 3), axis=(1, 2))      # [b,oy,ox,c,ky,kx]
+    assert np.array_equal(got, win.transpose(0, 1, 2, 4, 5, 3))
+    back = la.col2im(cols, la.zerosLike(images), filterSize=[3, 3]).to_numpy()
+    counts = np.zeros_like(img, dtype=np.float64)
+    oh, ow = c["im_h"] - 2, c["im_w"] - 2
+    for ky in range(3):
+        for kx in range(3):
+            counts[:, ky:ky + oh, kx:kx + ow, :] += 1
+    # each pixel is summed `count` times; compare in the isclose bound (values up to 3e6 * 9)
+    assert isclose_ref(back, img.astype(np.float64) * counts)
+
+
+# ---------------------------------------------------------------------------------------------------
+# add / multiply vs oracle
+# ---------------------------------------------------------------------------------------------------
+EW_SHAPES = [  # (m, n, trans, ldA_extra, offX, offA, incX)
+    (64, 256, False, 0, 0, 0, 1), (64, 256, True, 0, 0, 0, 1), (1, 1, False, 0, 0, 0, 1),
+    (37, 129, False, 0, 0, 0, 1), (37, 129, True, 0, 0, 0, 1), (128, 64, False, 4, 8, 16, 1),
+    (33, 100, False, 3, 5, 7, 2), (33, 100, True, 3, 5, 7, 3), (1000, 16, False, 0, 0, 0, 1),
+    (512, 4096, False, 0, 0, 0, 1), (512, 4096, True, 0, 0, 0, 1),
+]
+
+
+@pytest.mark.parametrize("shape", EW_SHAPES, ids=[str(s) for s in EW_SHAPES])
+@pytest.mark.parametrize("op,alpha", [("add", 1.0), ("add", -1.0), ("add", 0.3), ("multiply", None)])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_elementwise_vs_oracle(shape, op, alpha, dt, cuda_service):
+    m, n, trans, ld_extra, offX, offA, incX = shape
+    rng = np.random.default_rng(2001 + m + n)
+    npdt = dtypes.NUMPY[dt]
+    ldA = n + ld_extra
+    xlen = m if trans else n
+    Xh = rng.uniform(-1, 1, offX + (xlen - 1) * incX + 1).astype(npdt)
+    Ah = rng.uniform(-1, 1, offA + m * ldA).astype(npdt)
+    math = cuda_service.math()
+    X, A = buf(Xh, dt), buf(Ah, dt)
+    xo, ao = oracle.as_buffer(Xh), oracle.as_buffer(Ah)
+    if op == "add":
+        math.add(trans, m, n, alpha, X, offX, incX, A, offA, ldA)
+        oracle.add(trans, m, n, alpha, xo, offX, incX, ao, offA, ldA)
+    else:
+        math.multiply(trans, m, n, X, offX, incX, A, offA, ldA)
+        oracle.multiply(trans, m, n, xo, offX, incX, ao, offA, ldA)
+    got = A.to_numpy()
+    assert np.array_equal(X.to_numpy(), Xh)                       # X untouched
+    if dt == dtypes.float64 and not (op == "add" and alpha == 0.3):
+        assert np.array_equal(got, ao)                            # same double arithmetic
+    elif dt == dtypes.float32 and (op == "multiply" or abs(alpha) == 1.0):
+        assert np.array_equal(got, ao.astype(np.float32))         # bit-exact vs oracle rounded once
+    else:
+        ulp = np.spacing(np.abs(ao).astype(npdt)).astype(np.float64)
+        assert np.all(np.abs(got.astype(np.float64) - ao) <= ulp)   # fused multiply-add: within 1 ulp
+    # elements outside the m x n view (ld padding, before offA) untouched
+    mask = np.ones(Ah.size, bool)
+    for i in range(m):
+        mask[offA + i * ldA: offA + i * ldA + n] = False
+    assert np.array_equal(got[mask], Ah[mask])
+
+
+def test_elementwise_int32(cuda_service):
+    math = cuda_service.math()
+    Xh = np.arange(8, dtype=np.int32)
+    Ah = np.arange(32, dtype=np.int32).reshape(4, 8) * 3
+    X, A = buf(Xh, dtypes.int32), buf(Ah, dtypes.int32)
+    math.add(False, 4, 8, 2, X, 0, 1, A, 0, 8)
+    assert np.array_equal(A.to_numpy().reshape(4, 8), Ah + 2 * Xh)
+    math.multiply(False, 4, 8, X, 0, 1, A, 0, 8)
+    assert np.array_equal(A.to_numpy().reshape(4, 8), (Ah + 2 * Xh) * Xh)
+
+
+def test_elementwise_errors(cuda_service):
+    math = cuda_service.math()
+    X, A = buf(np.zeros(3)), buf(np.zeros(6))
+    with pytest.raises(rb.InvalidArgumentException, match="Vector specification too large for buffer."):
+        math.add(False, 2, 4, 1.0, X, 0, 1, A, 0, 4)
+    with pytest.raises(rb.InvalidArgumentException, match="Vector specification too large for buffer."):
+        math.multiply(False, 3, 3, X, 0, 1, A, 0, 3)
+
+
+def test_add_full_config_size(cuda_service):
+    """BASELINE config C2: [8192,4096] (+|x) [4096], checked against the oracle on every element."""
+    m, n = 8192, 4096
+    Ah = np.random.default_rng(2001).uniform(-1, 1, m * n).astype(np.float32)
+    Xh = np.random.default_rng(2002).uniform(-1, 1, n).astype(np.float32)
+    math = cuda_service.math()
+    X, A = buf(Xh), buf(Ah)
+    math.add(False, m, n, 1.0, X, 0, 1, A, 0, n)
+    xo, ao = oracle.as_buffer(Xh), oracle.as_buffer(Ah)
+    oracle.add(False, m, n, 1.0, xo, 0, 1, ao, 0, n)
+    assert np.array_equal(A.to_numpy(), ao.astype(np.float32))
+    math.multiply(False, m, n, X, 0, 1, A, 0, n)
+    a2 = ao.astype(np.float32).astype(np.float64)
+    oracle.multiply(False, m, n, xo, 0, 1, a2, 0, n)
+    assert np.array_equal(A.to_numpy(), a2.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reductions vs oracle
+# ---------------------------------------------------------------------------------------------------
+RD_SHAPES = [  # (m, n, k)
+    (1, 1, 1), (7, 5, 1), (64, 1024, 1), (3000, 1024, 1), (5, 100000, 1), (64, 4097, 1), (2, 1 << 20, 1),
+    (4, 6, 3), (16, 33, 7), (1, 4096, 1024), (8, 512, 64), (3, 1000, 2), (2, 70000, 5), (300, 3, 1000),
+]
+
+
+def _rd_input(m, n, k, seed, quantise=False):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-1, 1, m * n * k).astype(np.float32)
+    if quantise:
+        a = (np.round(a * 64) / 64).astype(np.float32)       # many exact ties
+    return a
+
+
+@pytest.mark.parametrize("shape", RD_SHAPES, ids=[str(s) for s in RD_SHAPES])
+@pytest.mark.parametrize("off", [0, 3])
+def test_reduce_sum_vs_oracle(shape, off, cuda_service):
+    m, n, k = shape
+    a = np.concatenate([np.zeros(off, np.float32), _rd_input(m, n, k, 3001)])
+    A, B = buf(a), CudaBuffer(m * k + 2, dtypes.float32)
+    cuda_service.math().reduceSum(m, n, k, A, off, B, 2)
+    ao, bo = oracle.as_buffer(a), np.zeros(m * k + 2)
+    oracle.reduce_sum(m, n, k, ao, off, bo, 2)
+    got = B.to_numpy().astype(np.float64)
+    assert np.all(got[:2] == 0)
+    assert isclose_ref(got, bo)
+    # measured-tight bound: float32 tree sum vs sequential double sum
+    scale = np.abs(a.astype(np.float64)).reshape(-1)[off:].reshape(m, n, k).sum(axis=1).reshape(-1)
+    assert np.all(np.abs(got[2:] - bo[2:]) <= 2e-6 * scale + 1e-30)
+
+
+@pytest.mark.parametrize("shape", RD_SHAPES, ids=[str(s) for s in RD_SHAPES])
+def test_reduce_max_vs_oracle_bit_exact(shape, cuda_service):
+    m, n, k = shape
+    a = _rd_input(m, n, k, 3002)
+    A, B = buf(a), CudaBuffer(m * k, dtypes.float32)
+    cuda_service.math().reduceMax(m, n, k, A, 0, B, 0)
+    bo = np.zeros(m * k)
+    oracle.reduce_max(m, n, k, oracle.as_buffer(a), 0, bo, 0)          # PHP rule == sticky rule: no NaN
+    assert np.array_equal(B.to_numpy().astype(np.float64), bo)
+
+
+@pytest.mark.parametrize("shape", RD_SHAPES, ids=[str(s) for s in RD_SHAPES])
+@pytest.mark.parametrize("idx_dtype", [dtypes.int32, dtypes.int64])
+def test_reduce_argmax_vs_oracle_bit_exact(shape, idx_dtype, cuda_service):
+    m, n, k = shape
+    a = _rd_input(m, n, k, 3003, quantise=True)
+    A, B = buf(a), CudaBuffer(m * k, idx_dtype)
+    cuda_service.math().reduceArgMax(m, n, k, A, 0, B, 0)
+    bo = np.zeros(m * k, np.int64)
+    oracle.reduce_argmax(m, n, k, oracle.as_buffer(a), 0, bo, 0)
+    assert np.array_equal(B.to_numpy().astype(np.int64), bo)
+
+
+def test_reduce_nan_inf_semantics(cuda_service):
+    math = cuda_service.math()
+    rng = np.random.default_rng(5)
+    for (m, n, k) in [(6, 1024, 1), (6, 50000, 1), (2, 300, 8), (1, 9000, 16)]:
+        a = rng.uniform(-1, 1, (m, n, k)).astype(np.float32)
+        a[0, n // 3, 0] = np.nan             # NaN mid-run
+        a[m - 1, 0, k - 1] = np.nan          # NaN at position 0
+        a[0, n - 1, k - 1] = np.inf
+        if m > 2:
+            a[1, :, 0] = -np.inf
+            a[2, 5, 0] = np.inf
+            a[2, 7, 0] = np.inf              # +inf tie: lowest index wins
+        A = buf(a)
+        Bm, Bi = CudaBuffer(m * k, dtypes.float32), CudaBuffer(m * k, dtypes.int32)
+        math.reduceMax(m, n, k, A, 0, Bm, 0)
+        math.reduceArgMax(m, n, k, A, 0, Bi, 0)
+        ao = oracle.as_buffer(a)
+        bm, bi = np.zeros(m * k), np.zeros(m * k, np.int64)
+        oracle.reduce_max(m, n, k, ao, 0, bm, 0, sticky=True)
+        oracle.reduce_argmax(m, n, k, ao, 0, bi, 0)
+        assert np.array_equal(Bm.to_numpy().astype(np.float64), bm, equal_nan=True)
+        assert np.array_equal(Bi.to_numpy().astype(np.int64), bi)
+
+
+def test_reduce_float64(cuda_service):
+    m, n, k = 9, 777, 3
+    a = np.random.default_rng(11).standard_normal(m * n * k)
+    A = buf(a, dtypes.float64)
+    Bs, Bm = CudaBuffer(m * k, dtypes.float64), CudaBuffer(m * k, dtypes.float64)
+    cuda_service.math().reduceSum(m, n, k, A, 0, Bs, 0)
+    cuda_service.math().reduceMax(m, n, k, A, 0, Bm, 0)
+    bs, bm = np.zeros(m * k), np.zeros(m * k)
+    oracle.reduce_sum(m, n, k, a, 0, bs, 0)
+    oracle.reduce_max(m, n, k, a, 0, bm, 0)
+    assert np.allclose(Bs.to_numpy(), bs, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(Bm.to_numpy(), bm)
+
+
+def test_reduce_full_config_size(cuda_service):
+    """BASELINE config C3: [65536,1024] axis=1 -- all three reductions against the oracle."""
+    m, n = 65536, 1024
+    a = np.random.default_rng(3001).uniform(-1, 1, m * n).astype(np.float32)
+    aq = (np.round(a * 64) / 64).astype(np.float32)
+    math = cuda_service.math()
+    A, Aq = buf(a), buf(aq)
+    Bs, Bm, Bi = CudaBuffer(m, dtypes.float32), CudaBuffer(m, dtypes.float32), CudaBuffer(m, dtypes.int32)
+    math.reduceSum(m, n, 1, A, 0, Bs, 0)
+    math.reduceMax(m, n, 1, A, 0, Bm, 0)
+    math.reduceArgMax(m, n, 1, Aq, 0, Bi, 0)
+    ao = oracle.as_buffer(a)
+    bs, bm, bi = np.zeros(m), np.zeros(m), np.zeros(m, np.int64)
+    oracle.reduce_sum(m, n, 1, ao, 0, bs, 0)
+    oracle.reduce_max(m, n, 1, ao, 0, bm, 0)
+    oracle.reduce_argmax(m, n, 1, oracle.as_buffer(aq), 0, bi, 0)
+    assert isclose_ref(Bs.to_numpy(), bs)
+    assert np.max(np.abs(Bs.to_numpy() - bs)) < 2e-5             # measured-tight (|sum| <~ 100)
+    assert np.array_equal(Bm.to_numpy().astype(np.float64), bm)
+    assert np.array_equal(Bi.to_numpy().astype(np.int64), bi)
+    # axis = 0 of the same matrix (m=1, n=65536, k=1024): the split + merge path
+    B0 = CudaBuffer(n, dtypes.float32)
+    math.reduceSum(1, m, n, A, 0, B0, 0)
+    b0 = np.zeros(n)
+    oracle.reduce_sum(1, m, n, ao, 0, b0, 0)
+    assert isclose_ref(B0.to_numpy(), b0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# softmax vs oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,ld_extra,off", [(1, 1, 0, 0), (5, 5, 0, 0), (64, 1024, 0, 0), (33, 1000, 0, 0),
+                                              (17, 513, 3, 5), (128, 128, 4, 8), (9, 5000, 0, 0),
+                                              (3, 70001, 0, 1), (2000, 64, 0, 0)])
+def test_softmax_vs_oracle(m, n, ld_extra, off, cuda_service):
+    ld = n + ld_extra
+    a = np.random.default_rng(3001).uniform(-4, 4, off + m * ld).astype(np.float32)
+    A = buf(a)
+    cuda_service.math().softmax(m, n, A, off, ld)
+    ao = oracle.as_buffer(a)
+    oracle.softmax(m, n, ao, off, ld)
+    got = A.to_numpy().astype(np.float64)
+    assert isclose_ref(got, ao)
+    view = np.zeros(a.size, bool)
+    for i in range(m):
+        view[off + i * ld: off + i * ld + n] = True
+    assert np.array_equal(got[~view], ao[~view])                  # padding untouched
+    rel = np.abs(got[view] - ao[view]) / ao[view]
+    assert rel.max() < 5e-6                                       # measured-tight: expf + f32 tree sum
+    rows = np.array([got[off + i * ld: off + i * ld + n].sum() for i in range(m)])
+    assert np.allclose(rows, 1.0, atol=1e-5)
+
+
+def test_softmax_special_values(cuda_service):
+    x = np.array([[0.0, np.nan, 1.0, 2.0], [np.inf, 1.0, 2.0, 3.0], [-np.inf, 0.0, 0.0, -np.inf],
+                  [-np.inf] * 4, [1000.0, 999.0, -1000.0, 0.0]], np.float32)
+    A = buf(x)
+    cuda_service.math().softmax(5, 4, A, 0, 4)
+    ao = oracle.as_buffer(x)
+    oracle.softmax(5, 4, ao, 0, 4)
+    got = A.to_numpy().astype(np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(ao))
+    ok = ~np.isnan(ao)
+    assert np.allclose(got[ok], ao[ok], rtol=1e-6, atol=1e-30)
+
+
+def test_softmax_full_config_size(cuda_service):
+    m, n = 65536, 1024
+    a = np.random.default_rng(3001).uniform(-1, 1, m * n).astype(np.float32)
+    A = buf(a)
+    cuda_service.math().softmax(m, n, A, 0, n)
+    ao = oracle.as_buffer(a)
+    oracle.softmax(m, n, ao, 0, n)
+    got = A.to_numpy().astype(np.float64)
+    assert isclose_ref(got, ao)
+    assert np.max(np.abs(got - ao) / ao) < 5e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM vs oracle
+# ---------------------------------------------------------------------------------------------------
+GEMM_TOL = {rb.GEMM_FP32_SIMT: 2e-6, rb.GEMM_TF32X3: 2e-5, rb.GEMM_TF32: 2e-3}   # x max|C|
+
+
+def _gemm_case(svc, mode, m, n, k, tA, tB, alpha, beta, offA=0, offB=0, offC=0, ld_extra=0, seed=5000,
+               dt=dtypes.float32):
+    rng = np.random.default_rng(seed)
+    npdt = dtypes.NUMPY[dt]
+    rA, cA = (k, m) if tA else (m, k)
+    rB, cB = (n, k) if tB else (k, n)
+    ldA, ldB, ldC = cA + ld_extra, cB + ld_extra, n + ld_extra
+    Ah = rng.uniform(-1, 1, offA + rA * ldA).astype(npdt)
+    Bh = rng.uniform(-1, 1, offB + rB * ldB).astype(npdt)
+    Ch = rng.uniform(-1, 1, offC + m * ldC).astype(npdt)
+    A, B, C = buf(Ah, dt), buf(Bh, dt), buf(Ch, dt)
+    blas = svc.blas()
+    blas.setGemmMode(mode)
+    blas.gemm(BLAS.RowMajor, BLAS.Trans if tA else BLAS.NoTrans, BLAS.Trans if tB else BLAS.NoTrans,
+              m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC)
+    path = rb._capi.last_gemm_path()
+    co = oracle.as_buffer(Ch)
+    if m * n * k <= 1 << 18:
+        ao, bo = oracle.as_buffer(Ah), oracle.as_buffer(Bh)
+        oracle.gemm(oracle.RowMajor, oracle.Trans if tA else oracle.NoTrans, oracle.Trans if tB else oracle.NoTrans,
+                    m, n, k, alpha, ao, offA, ldA, bo, offB, ldB, beta, co, offC, ldC)
+    else:
+        # Larger cases: materialise op(A), op(B) (pure data movement) and use the interleaved-loop
+        # oracle, which is bit-identical to ro_gemm per element (tests/test_oracle_golden.py::
+        # test_gemm_rows_variants_bit_identical) but cache friendly.
+        Am = Ah[offA:offA + rA * ldA].reshape(rA, ldA)[:, :cA]
+        Bm = Bh[offB:offB + rB * ldB].reshape(rB, ldB)[:, :cB]
+        opA = oracle.as_buffer(Am.T if tA else Am)
+        opB = oracle.as_buffer(Bm.T if tB else Bm)
+        oracle.gemm_rows_fast(0, m, n, k, alpha, opA, k, opB, n, beta, co[offC:], ldC)
+    got = C.to_numpy().astype(np.float64)
+    view = np.zeros(Ch.size, bool)
+    for i in range(m):
+        view[offC + i * ldC: offC + i * ldC + n] = True
+    assert np.array_equal(got[~view], co[~view])                   # nothing outside C's m x n view
+    err = np.max(np.abs(got[view] - co[view])) / max(np.max(np.abs(co[view])), 1e-30)
+    return err, path
+
+
+SMALL_GEMMS = [(3, 3, 3), (1, 1, 1), (2, 3, 4), (17, 9, 33), (64, 64, 64), (65, 130, 31), (100, 257, 129)]
+
+
+@pytest.mark.parametrize("mnk", SMALL_GEMMS, ids=[str(s) for s in SMALL_GEMMS])
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_gemm_simt_small(mnk, tA, tB, dt, cuda_service):
+    m, n, k = mnk
+    for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (1.0, 1.0, 0, 0), (-0.5, 2.0, 9, 3)):
+        err, path = _gemm_case(cuda_service, rb.GEMM_FP32_SIMT, m, n, k, tA, tB, alpha, beta, off, off + 1, off + 2,
+                               ldx, dt=dt)
+        assert path == ("simt_f32" if dt == dtypes.float32 else "simt_f64")
+        assert err < (2e-6 if dt == dtypes.float32 else 1e-14), (err, path)
+
+
+TC_GEMMS = [(256, 256, 256), (128, 128, 32), (128, 256, 64), (384, 640, 160), (512, 384, 1024), (200, 300, 100),
+            (1000, 520, 36), (129, 257, 33), (2048, 128, 128), (128, 2048, 1024)]
+
+
+@pytest.mark.parametrize("mnk", TC_GEMMS, ids=[str(s) for s in TC_GEMMS])
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("mode", [rb.GEMM_TF32, rb.GEMM_TF32X3])
+def test_gemm_tcgen05(mnk, tA, tB, mode, cuda_service):
+    m, n, k = mnk
+    # TMA needs leading dimensions that are multiples of 4 floats: pad via ld_extra
+    rA_c = m if tA else k
+    rB_c = k if tB else n
+    ldx = 0
+    while (rA_c + ldx) % 4 or (rB_c + ldx) % 4 or (n + ldx) % 4:
+        ldx += 1
+    for alpha, beta, off in ((1.0, 0.0, 0), (1.0, 1.0, 0), (0.75, -1.5, 8)):
+        err, path = _gemm_case(cuda_service, mode, m, n, k, tA, tB, alpha, beta, off, off, off, ldx)
+        assert path == ("tcgen05_tf32" if mode == rb.GEMM_TF32 else "tcgen05_tf32x3"), path
+        assert err < GEMM_TOL[mode], (err, path, mnk, tA, tB, alpha, beta)
+        if mode == rb.GEMM_TF32X3:
+            assert err < 1e-4            # the reference's own isclose rtol
+
+
+def test_gemm_unaligned_falls_back_to_simt(cuda_service):
+    err, path = _gemm_case(cuda_service, rb.GEMM_TF32, 256, 256, 256, False, False, 1.0, 0.0, offA=1)
+    assert path == "simt_f32" and err < 2e-6
+    err, path = _gemm_case(cuda_service, rb.GEMM_TF32, 256, 255, 256, False, False, 1.0, 0.0)
+    assert path == "simt_f32" and err < 2e-6
+
+
+def test_gemm_errors(cuda_service):
+    blas = cuda_service.blas()
+    A, B, C = buf([1, 2, 3, 4, 5]), buf(np.eye(3)), buf(np.zeros(6))
+    with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for bufferA."):
+        blas.gemm(BLAS.RowMajor, BLAS.Trans, BLAS.NoTrans, 2, 3, 3, 1.0, A, 0, 2, B, 0, 3, 0.0, C, 0, 3)
+    A = buf([1, 2, 3, 4, 5, 6])
+    with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for bufferB."):
+        blas.gemm(BLAS.RowMajor, BLAS.Trans, BLAS.NoTrans, 2, 3, 3, 1.0, A, 0, 2, buf(np.zeros(8)), 0, 3, 0.0, C, 0, 3)
+    with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for bufferC."):
+        blas.gemm(BLAS.RowMajor, BLAS.Trans, BLAS.NoTrans, 2, 3, 3, 1.0, A, 0, 2, B, 0, 3, 0.0, buf(np.zeros(5)), 0, 3)
+    with pytest.raises(rb.InvalidArgumentException, match="Argument k must be greater than 0."):
+        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, 2, 3, 0, 1.0, A, 0, 3, B, 0, 3, 0.0, C, 0, 3)
+    with pytest.raises(rb.InvalidArgumentException, match="Unknown Tranpose Code"):
+        blas.gemm(BLAS.RowMajor, 7, BLAS.NoTrans, 2, 3, 3, 1.0, A, 0, 3, B, 0, 3, 0.0, C, 0, 3)
+
+
+def test_gemm_beta_zero_overwrites_nan(cuda_service):
+    blas = cuda_service.blas()
+    for mode, sz in ((rb.GEMM_FP32_SIMT, 8), (rb.GEMM_TF32, 256), (rb.GEMM_TF32X3, 256)):
+        blas.setGemmMode(mode)
+        A, B = buf(np.eye(sz)), buf(np.arange(sz * sz, dtype=np.float32) % 7)
+        C = buf(np.full(sz * sz, np.nan, np.float32))
+        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, sz, sz, sz, 1.0, A, 0, sz, B, 0, sz, 0.0, C, 0, sz)
+        assert np.array_equal(C.to_numpy(), np.arange(sz * sz, dtype=np.float32) % 7)     # PhpBlas.php:940-944
+
+
+@pytest.mark.parametrize("mode", [rb.GEMM_TF32, rb.GEMM_TF32X3, rb.GEMM_FP32_SIMT])
+def test_gemm_integer_valued_exact(mode, cuda_service):
+    """The reference's known-answer style: small integer inputs are exact in every mode."""
+    rng = np.random.default_rng(1)
+    m, n, k = 256, 384, 128
+    Ah = rng.integers(-8, 9, (m, k)).astype(np.float32)
+    Bh = rng.integers(-8, 9, (k, n)).astype(np.float32)
+    blas = cuda_service.blas()
+    blas.setGemmMode(mode)
+    A, B, C = buf(Ah), buf(Bh), CudaBuffer(m * n, dtypes.float32)
+    blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, m, n, k, 1.0, A, 0, k, B, 0, n, 0.0, C, 0, n)
+    assert np.array_equal(C.to_numpy().reshape(m, n), Ah.astype(np.float64) @ Bh.astype(np.float64))
+
+
+@pytest.mark.parametrize("N,mode", [(1024, rb.GEMM_TF32), (1024, rb.GEMM_TF32X3), (4096, rb.GEMM_TF32),
+                                    (4096, rb.GEMM_TF32X3)])
+def test_gemm_sweep_sizes_sampled(N, mode, cuda_service):
+    """BASELINE config C5 shapes: N <= 1024 checked in full against the oracle, larger N on a
+    sample of 64 full rows of C (oracle gemm_rows: same loop, bounded rows)."""
+    lg = int(np.log2(N))
+    Ah = np.random.default_rng(5000 + lg).uniform(-1, 1, N * N).astype(np.float32)
+    Bh = np.random.default_rng(5100 + lg).uniform(-1, 1, N * N).astype(np.float32)
+    blas = cuda_service.blas()
+    blas.setGemmMode(mode)
+    A, B, C = buf(Ah), buf(Bh), CudaBuffer(N * N, dtypes.float32)
+    blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, N, N, N, 1.0, A, 0, N, B, 0, N, 0.0, C, 0, N)
+    got = C.to_numpy().reshape(N, N).astype(np.float64)
+    ao, bo = oracle.as_buffer(Ah), oracle.as_buffer(Bh)
+    rows = range(N) if N <= 1024 else sorted(np.random.default_rng(9).choice(N, 64, replace=False).tolist())
+    co = np.zeros(N * N)
+    if N <= 1024:
+        oracle.gemm_rows_fast(0, N, N, N, 1.0, ao, N, bo, N, 0.0, co, N)
+    else:
+        for r in rows:
+            oracle.gemm_rows_fast(r, 1, N, N, 1.0, ao, N, bo, N, 0.0, co, N)
+    ref = co.reshape(N, N)[list(rows)]
+    err = np.max(np.abs(got[list(rows)] - ref)) / np.max(np.abs(ref))
+    assert err < GEMM_TOL[mode], err
+    # a wrong tile anywhere (not only in sampled rows) shows up in the column sums: 1^T C = (1^T A) B
+    colsum = Ah.reshape(N, N).astype(np.float64).sum(axis=0) @ Bh.reshape(N, N).astype(np.float64)
+    assert np.max(np.abs(got.sum(axis=0) - colsum)) < GEMM_TOL[mode] * N * np.max(np.abs(ref))
+
+
+def test_cross_256_config(cuda_service):
+    """BASELINE config C1: MatrixOperator::cross sgemm 256x256 (alpha=1, beta=1 on a zeroed C)."""
+    mo = MatrixOperator(cuda_service)
+    cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+    Ah = np.random.default_rng(1234).uniform(-1, 1, (256, 256)).astype(np.float32)
+    Bh = np.random.default_rng(1235).uniform(-1, 1, (256, 256)).astype(np.float32)
+    C = mo.cross(mo.array(Ah), mo.array(Bh))
+    co = np.zeros(256 * 256)
+    oracle.gemm(oracle.RowMajor, oracle.NoTrans, oracle.NoTrans, 256, 256, 256, 1.0, oracle.as_buffer(Ah), 0, 256,
+                oracle.as_buffer(Bh), 0, 256, 1.0, co, 0, 256)
+    assert isclose_ref(C.to_numpy().reshape(-1), co)
+
+
+# ---------------------------------------------------------------------------------------------------
+# im2col2d on random data and other dtypes; conv config
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32, dtypes.uint8, dtypes.int64])
+@pytest.mark.parametrize("padding,cf,ccf,k,s,d", [(False, False, False, (3, 3), (1, 1), (1, 1)),
+                                                 (True, False, False, (3, 3), (1, 1), (1, 1)),
+                                                 (True, True, True, (5, 3), (2, 1), (1, 2)),
+                                                 (False, True, False, (2, 4), (1, 3), (2, 1)),
+                                                 (True, False, True, (3, 3), (2, 2), (2, 2))])
+def test_im2col2d_random_bit_exact(dt, padding, cf, ccf, k, s, d, cuda_service):
+    b, h, w, c = 3, 19, 23, 5
+    rng = np.random.default_rng(4001)
+    npdt = dtypes.NUMPY[dt]
+    img = (rng.uniform(0, 1, b * h * w * c) * 100).astype(npdt)
+    off_i, off_c = 3, 4
+    shape = oracle.im2col2d_out_shape(b, h, w, c, k[0], k[1], s[0], s[1], padding, d[0], d[1], ccf)
+    ncols = int(np.prod(shape))
+    images = CudaBuffer(off_i + img.size, dt).from_numpy(img, off_i)
+    cols = CudaBuffer(off_c + ncols, dt)
+    math = cuda_service.math()
+    args = (b, h, w, c, k[0], k[1], s[0], s[1], padding, cf, d[0], d[1], ccf)
+    math.im2col2d(False, images, off_i, img.size, *args, cols, off_c, ncols)
+    io = np.concatenate([np.zeros(off_i), img.astype(np.float64)])
+    co = np.zeros(off_c + ncols)
+    oracle.im2col2d(False, io, off_i, img.size, *args, co, off_c, ncols)
+    assert np.array_equal(cols.to_numpy().astype(np.float64), co)              # bit-exact copy
+    if dt in (dtypes.float32, dtypes.float64, dtypes.int32, dtypes.int64):
+        # col2im accumulates on top of existing image values, in the reference's order
+        math.im2col2d(True, images, off_i, img.size, *args, cols, off_c, ncols)
+        oracle.im2col2d(True, io, off_i, img.size, *args, co, off_c, ncols)
+        assert np.array_equal(images.to_numpy().astype(np.float64), io)       # small integers: exact
+
+
+def test_im2col2d_errors(cuda_service):
+    math = cuda_service.math()
+    images, cols = CudaBuffer(2 * 8 * 8 * 3, dtypes.float32), CudaBuffer(2 * 6 * 6 * 27, dtypes.float32)
+    with pytest.raises(rb.InvalidArgumentException, match="images buffer size is invalid"):
+        math.im2col2d(False, images, 0, 100, 2, 8, 8, 3, 3, 3, 1, 1, False, False, 1, 1, False, cols, 0, 2 * 6 * 6 * 27)
+    with pytest.raises(rb.InvalidArgumentException, match="Invalid shape or parameters."):
+        math.im2col2d(False, images, 0, 384, 2, 8, 8, 3, 9, 9, 1, 1, False, False, 1, 1, False, cols, 0, 2 * 6 * 6 * 27)
+    with pytest.raises(rb.InvalidArgumentException, match="output buffer size is invalid"):
+        math.im2col2d(False, images, 0, 384, 2, 8, 8, 3, 3, 3, 1, 1, False, False, 1, 1, False, cols, 0, 100)
+
+
+def test_conv_config_im2col_gemm(cuda_service):
+    """BASELINE config C4 (reduced batch 4 of 64; the per-image work is identical): im2col2d + gemm
+    [B*222*222, 27] x [27, 64] against the oracle; cols bit-exact, conv output in the isclose bound."""
+    b, h, w, c, f = 4, 224, 224, 3, 64
+    la = LinearAlgebra(cuda_service)
+    cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+    img = np.random.default_rng(4001).uniform(0, 1, (b, h, w, c)).astype(np.float32)
+    W = (np.random.default_rng(4002).standard_normal((27, f)) * 0.1).astype(np.float32)
+    cols = la.im2col(la.array(img), filterSize=[3, 3])
+    assert cols.shape() == [b, 222, 222, 3, 3, 3]
+    win = np.lib.stride_tricks.sliding_window_view(img, (3, 3), axis=(1, 2)).transpose(0, 1, 2, 4, 5, 3)
+    assert np.array_equal(cols.to_numpy(), win)
+    out = la.gemm(cols.reshape([b * 222 * 222, 27]), la.array(W))
+    M = b * 222 * 222
+    co = np.zeros(M * f)
+    rows = np.random.default_rng(1).choice(M, 512, replace=False)
+    ao, bo = oracle.as_buffer(win.reshape(M, 27)), oracle.as_buffer(W)
+    for r in rows:
+        oracle.gemm_rows_fast(int(r), 1, f, 27, 1.0, ao, 27, bo, f, 0.0, co, f)
+    assert isclose_ref(out.to_numpy().reshape(M, f)[rows], co.reshape(M, f)[rows])
+
+
+# ---------------------------------------------------------------------------------------------------
+# buffer contract (PhpBufferTest.php)
+# ---------------------------------------------------------------------------------------------------
+def test_buffer_contract():
+    b = CudaBuffer(5, dtypes.float32)
+    assert len(b) == 5 and b.dtype() == dtypes.float32 and b.value_size() == 4
+    assert [b[i] for i in range(5)] == [0.0] * 5
+    b[2] = 1.5
+    assert b[2] == 1.5
+    with pytest.raises(rb.RuntimeException):
+        b[5]
+    with pytest.raises(rb.RuntimeException):
+        b[-1] = 1
+    with pytest.raises(rb.InvalidArgumentException, match="Invalid data type"):
+        CudaBuffer(3, 99)
+    raw = b.dump()
+    assert raw == np.array([0, 0, 1.5, 0, 0], "<f4").tobytes()
+    c = CudaBuffer(5, dtypes.float32)
+    c.load(raw)
+    assert c[2] == 1.5 and c.to_numpy().tolist() == [0, 0, 1.5, 0, 0]
+    for dt, sz in ((dtypes.int8, 1), (dtypes.uint16, 2), (dtypes.int64, 8), (dtypes.float64, 8), (dtypes.bool_, 1)):
+        assert CudaBuffer(2, dt).value_size() == sz
+
+
+def test_buffer_host_device_coherence(cuda_service):
+    """Host element writes are flushed before a kernel, kernel results fetched before a host read."""
+    la = LinearAlgebra(cuda_service)
+    A = la.array([[1, 2], [3, 4]])
+    X = la.array([10, 20])
+    A.buffer()[0] = 5.0                       # host write after upload
+    la.add(X, A)
+    assert A.toArray() == [[15, 22], [13, 24]]
+    A.buffer()[3] = 0.0                       # host write after kernel
+    la.add(X, A)
+    assert A.toArray() == [[25, 42], [23, 20]]
+    assert A[1][1] == 20.0 and A[0].toArray() == [25, 42]

@@ -1,0 +1,103 @@
+"""Host-side logic that needs no GPU: argument validation (exact reference strings), shape folding
+in LinearAlgebra / MatrixOperator, NDArray views, service-level diagnosis.  CPU only."""
+import numpy as np
+import pytest
+
+import rindow_math_matrix_b200 as rb
+from rindow_math_matrix_b200 import LinearAlgebra, MatrixOperator, NDArray, dtypes
+from rindow_math_matrix_b200.cuda_blas import (assert_matrix_buffer_spec, assert_shape_parameter,
+                                               assert_vector_buffer_spec, code_to_trans)
+
+
+def test_utils_messages():
+    """Utils.php:30-65 -- the strings PhpBlasTest.php:1988-2155 asserts."""
+    with pytest.raises(rb.InvalidArgumentException, match=r"Argument m must be greater than 0\."):
+        assert_shape_parameter("m", 0)
+    b = list(range(6))
+    with pytest.raises(rb.InvalidArgumentException, match=r"Matrix specification too large for bufferA\."):
+        assert_matrix_buffer_spec("A", b, 3, 3, 0, 3)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Argument offsetA must be greater than equals 0\."):
+        assert_matrix_buffer_spec("A", b, 2, 3, -1, 3)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Argument ldA must be greater than 0\."):
+        assert_matrix_buffer_spec("A", b, 2, 3, 0, 0)
+    assert_matrix_buffer_spec("A", b, 2, 3, 0, 3)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Vector specification too large for bufferX\."):
+        assert_vector_buffer_spec("X", b, 4, 0, 2)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Argument incX must be greater than 0\."):
+        assert_vector_buffer_spec("X", b, 4, 0, 0)
+    assert code_to_trans(111) == (False, False) and code_to_trans(113) == (True, True)
+    with pytest.raises(rb.InvalidArgumentException, match="Unknown Tranpose Code"):
+        code_to_trans(5)
+
+
+def test_ndarray_views_and_reshape(oracle_service):
+    a = NDArray(np.arange(24).reshape(2, 3, 4), dtype=dtypes.float32, service=oracle_service)
+    assert a.shape() == [2, 3, 4] and a.ndim() == 3 and a.size() == 24 and a.offset() == 0
+    v = a[1]
+    assert v.offset() == 12 and v.shape() == [3, 4] and v.buffer() is a.buffer()
+    assert v[2].offset() == 20 and v[2][3] == 23.0
+    assert a.reshape([6, 4])[5].toArray() == [20, 21, 22, 23]
+    with pytest.raises(rb.InvalidArgumentException, match="Unmatch size to reshape"):
+        a.reshape([5, 5])
+    with pytest.raises(rb.OutOfRangeException):
+        a[2]
+    v[0] = [9, 9, 9, 9]
+    assert a.toArray()[1][0] == [9, 9, 9, 9]
+    assert a[0:1].shape() == [1, 3, 4]
+
+
+def test_reduce_axis_errors(oracle_service):
+    la = LinearAlgebra(oracle_service)
+    x = la.array([[1, 2, 3], [4, 5, 6]])
+    with pytest.raises(rb.InvalidArgumentException, match="Invalid axis: 2"):
+        la.reduceSum(x, axis=2)
+    with pytest.raises(rb.InvalidArgumentException, match="Invalid axis: -3"):
+        la.reduceMax(x, axis=-3)
+    out = la.alloc([2])
+    with pytest.raises(rb.InvalidArgumentException, match=r"Unmatch shape of dimension: \(2,3\),\(2\)"):
+        la.reduceSum(x, axis=0, output=out)
+    assert la.reduceArgMax(x, axis=1).dtype() == dtypes.int32          # LinearAlgebra.php:3311-3313
+    assert la.reduceArgMax(x, axis=1, dtype=dtypes.int64).dtype() == dtypes.int64
+
+
+def test_broadcast_errors(oracle_service):
+    la = LinearAlgebra(oracle_service)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Unmatch dimension size for broadcast\.: \[2\] => \[2,3\]"):
+        la.add(la.array([1, 2]), la.array([[1, 2, 3], [4, 5, 6]]))
+    with pytest.raises(rb.InvalidArgumentException, match=r"Unmatch dimension size for broadcast\.: \[3\] => \[3,2\]"):
+        la.multiply(la.array([1, 2, 3]), la.array([[1, 2, 3], [4, 5, 6]]), trans=True)
+    with pytest.raises(rb.InvalidArgumentException, match='"X" must be 2-D dimension'):
+        la.softmax(la.array([1, 2, 3]))
+    with pytest.raises(rb.InvalidArgumentException, match="Dimensions must be 2D-NDArray"):
+        la.gemm(la.array([1, 2, 3]), la.array([[1], [2], [3]]))
+
+
+def test_cross_errors(oracle_service):
+    mo = MatrixOperator(oracle_service)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Unmatch shape of dimension to cross multiple: \(2,3\),\(2,3\)"):
+        mo.cross(mo.array([[1, 2, 3], [4, 5, 6]]), mo.array([[1, 2, 3], [4, 5, 6]]))
+    with pytest.raises(rb.InvalidArgumentException, match="unmatch value type"):
+        mo.cross(mo.array([[1.0]]), mo.array([[1.0]], dtype=dtypes.float64))
+
+
+def test_im2col_shape_errors(oracle_service):
+    la = LinearAlgebra(oracle_service)
+    with pytest.raises(rb.InvalidArgumentException, match="Invalid shape or paramaters."):
+        la.im2col(la.alloc([1, 2, 2, 1]), filterSize=[3, 3])
+    with pytest.raises(rb.InvalidArgumentException, match="unsuppoted images shape"):
+        la.im2col(la.alloc([2, 2]))
+
+
+def test_service_without_gpu_is_basic_and_refuses_to_compute():
+    from rindow_math_matrix_b200 import _capi
+    if _capi.device_available():
+        pytest.skip("a GPU is visible")
+    svc = rb.MatlibCuda()
+    assert svc.serviceLevel() == rb.Service.LV_BASIC
+    assert "Basic" in svc.info()
+    with pytest.raises(rb.LogicException, match="no CPU fallback"):
+        svc.blas()
+    with pytest.raises(rb.LogicException):
+        svc.math(rb.Service.LV_BASIC)
+    with pytest.raises(_capi.B200Error):
+        rb.CudaBuffer(4, dtypes.float32)
