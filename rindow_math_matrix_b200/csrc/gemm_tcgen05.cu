@@ -24,13 +24,16 @@
 //   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> registers -> alpha/beta -> global
 // Tiles are visited in a grouped (L2-friendly) order: 16 row-blocks share each B column-block.
 //
-// Shared-memory operand layouts (128-byte swizzle everywhere, 1024-byte aligned tiles):
+// Shared-memory operand layouts (128-byte swizzle, 1024-byte aligned tiles):
 //   K-major  (A NoTrans / B Trans): rows of 32 floats; TMA box {32, rows}; UMMA descriptor
 //            SBO = 1024 (8 rows); advancing K by 8 floats = +32 bytes on the start address.
-//   MN-major (A Trans / B NoTrans): boxes {32 mn, 32 k} of 4 KB, one per 32 columns; UMMA
-//            descriptor LBO = 4096 (next 32 columns), SBO = 1024 (next 8 k); advancing K by 8
-//            = +1024 bytes.
+//   MN-major (A Trans / B NoTrans): boxes {32 mn, 32 k} of 4 KB, one per 32 columns, in the
+//            128-byte swizzle with 32-BYTE atoms (TMA SWIZZLE_128B_ATOM_32B, UMMA layout
+//            SWIZZLE_128B_BASE32B -- the only layout the tensor core takes for MN-major 32-bit
+//            operands); descriptor LBO = 4096 (next 32 columns), SBO = 512 (next 4 k);
+//            advancing K by 8 = +1024 bytes.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -116,14 +119,18 @@ __device__ __forceinline__ bool elect_one()
 
 // UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SW128).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// layout: 2 = SWIZZLE_128B (16-byte atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte atoms:
+// the only layout the tensor core accepts for MN-major 32-bit operands, cf. CUTLASS
+// sm100_smem_selector "for mn-major tf32 operands, SW128_32B is the only available smem layout").
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(layout & 7) << 61;
     return d;
 }
 
@@ -145,6 +152,8 @@ struct TcParams {
     float* C;
     int64_t ldC;
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    // UMMA descriptor fields of an MN-major operand tile (boxes of 32 mn x 32 k floats):
+    uint32_t mn_lbo, mn_sbo, mn_layout;
 };
 
 template <int BN, int PLANES, int STAGES>
@@ -265,14 +274,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                         // K-major: +32 bytes per UMMA_K inside the swizzle row; MN-major: +1024 (8 k-rows)
                         const uint32_t aoff = A_MN ? kk * 1024 : kk * 32;
                         const uint32_t boff = B_MN ? kk * 1024 : kk * 32;
-                        const uint64_t a_hi = make_smem_desc(sA + aoff, A_MN ? 4096 : 16, 1024);
-                        const uint64_t b_hi = make_smem_desc(sB + boff, B_MN ? 4096 : 16, 1024);
+                        const uint64_t a_hi = A_MN ? make_smem_desc(sA + aoff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                   : make_smem_desc(sA + aoff, 16, 1024, 2);
+                        const uint64_t b_hi = B_MN ? make_smem_desc(sB + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                   : make_smem_desc(sB + boff, 16, 1024, 2);
                         const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
                         if (PLANES == 1) {
                             tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, first);
                         } else {
-                            const uint64_t a_lo = make_smem_desc(sA + L::A_PLANE + aoff, A_MN ? 4096 : 16, 1024);
-                            const uint64_t b_lo = make_smem_desc(sB + L::B_PLANE + boff, B_MN ? 4096 : 16, 1024);
+                            const uint64_t a_lo = A_MN ? make_smem_desc(sA + L::A_PLANE + aoff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : make_smem_desc(sA + L::A_PLANE + aoff, 16, 1024, 2);
+                            const uint64_t b_lo = B_MN ? make_smem_desc(sB + L::B_PLANE + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : make_smem_desc(sB + L::B_PLANE + boff, 16, 1024, 2);
                             tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, first);     // small terms first
                             tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
                             tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
@@ -391,7 +404,7 @@ EncodeTiledFn get_encode_fn()
 
 // 3-D map over a row-major [outer, inner] float matrix with `planes` copies `plane_stride` elements apart.
 int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int planes,
-             int64_t plane_stride, int box_inner, int box_outer)
+             int64_t plane_stride, int box_inner, int box_outer, CUtensorMapSwizzle swizzle)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { rb200::set_error("cuTensorMapEncodeTiled is not available from the driver"); return RB200_E_CUDA; }
@@ -401,7 +414,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, 
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         rb200::set_error("cuTensorMapEncodeTiled failed (CUresult %d): inner=%lld outer=%lld ld=%lld planes=%d",
@@ -494,11 +507,20 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
     CUtensorMap mA, mB;
     int rc;
     // K-major: inner = K, outer = M|N, box {32, rows}.  MN-major: inner = M|N, outer = K, box {32, 32}.
-    if (!a_mn) rc = make_map(&mA, srcA, K, M, sldA, planes, plsA, TC_BK, TC_BM);
-    else       rc = make_map(&mA, srcA, M, K, sldA, planes, plsA, 32, TC_BK);
+    // MN-major tiles use the 128-byte swizzle with 32-byte atoms on both sides (TMA and UMMA descriptor):
+    // k-rows of 128 bytes, 32-byte chunks XORed with (k mod 4); descriptor SBO = 512 (4 k-rows),
+    // LBO = 4096 (next box of 32 columns).  Debug overrides: RB200_DBG_MN_{SWIZZLE,LBO,SBO,LAYOUT}.
+    static const int dbg_sw = getenv("RB200_DBG_MN_SWIZZLE") ? atoi(getenv("RB200_DBG_MN_SWIZZLE")) : -1;
+    static const int dbg_lbo = getenv("RB200_DBG_MN_LBO") ? atoi(getenv("RB200_DBG_MN_LBO")) : -1;
+    static const int dbg_sbo = getenv("RB200_DBG_MN_SBO") ? atoi(getenv("RB200_DBG_MN_SBO")) : -1;
+    static const int dbg_layout = getenv("RB200_DBG_MN_LAYOUT") ? atoi(getenv("RB200_DBG_MN_LAYOUT")) : -1;
+    const CUtensorMapSwizzle k_sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle mn_sw = dbg_sw >= 0 ? (CUtensorMapSwizzle)dbg_sw : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!a_mn) rc = make_map(&mA, srcA, K, M, sldA, planes, plsA, TC_BK, TC_BM, k_sw);
+    else       rc = make_map(&mA, srcA, M, K, sldA, planes, plsA, 32, TC_BK, mn_sw);
     if (rc != RB200_OK) return rc;
-    if (!b_mn) rc = make_map(&mB, srcB, K, N, sldB, planes, plsB, TC_BK, BN);
-    else       rc = make_map(&mB, srcB, N, K, sldB, planes, plsB, 32, TC_BK);
+    if (!b_mn) rc = make_map(&mB, srcB, K, N, sldB, planes, plsB, TC_BK, BN, k_sw);
+    else       rc = make_map(&mB, srcB, N, K, sldB, planes, plsB, 32, TC_BK, mn_sw);
     if (rc != RB200_OK) return rc;
 
     TcParams p;
@@ -506,6 +528,9 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
     p.num_m_blocks = (int)rb_ceil_div(M, TC_BM);
     p.num_n_blocks = (int)rb_ceil_div(N, BN);
     p.num_k_blocks = (int)rb_ceil_div(K, TC_BK);
+    p.mn_lbo = dbg_lbo >= 0 ? (uint32_t)dbg_lbo : 4096u;
+    p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
+    p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
     if (planes == 1) {
         c.last_gemm_path = "tcgen05_tf32";
         return launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);

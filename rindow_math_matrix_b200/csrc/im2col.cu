@@ -13,10 +13,11 @@
 // summation order (reverse).
 // Algorithmic bytes (forward): images read once + cols written once.
 //
-// Forward kernel: one thread per 16-byte group of consecutive cols elements (128-bit
-// stores, fully coalesced on the 340 MB side); the (ky,kx,c) -> source-delta map of one cell
-// is a shared-memory table, so each element costs one table read + one bounds test + one
-// (L1/L2-served, 9x reused) gather load.  Reverse kernel: one thread per image element,
+// Forward kernels: (1) tiled -- one CTA per (batch, out row, block of out columns): the filter_h
+// source rows are staged in shared memory with coalesced loads, the block's contiguous run of cols
+// is produced with a tap table + shared-memory gather and coalesced stores (the common case);
+// (2) flat -- one thread per 16-byte group of cols with a global gather, for shapes whose working
+// set does not fit 48 KB of shared memory.  Reverse kernel: one thread per image element,
 // summing its <= kh*kw taps -- no atomics, deterministic order.
 #include "common.cuh"
 
@@ -109,6 +110,82 @@ im2col2d_forward(Im2colParams p, const W* __restrict__ images, W* __restrict__ c
     }
 }
 
+
+// ---- forward, tiled: one CTA per (batch, out row, block of TOX out columns) ------------------------
+// The filter_h source rows that feed this block of cells are staged in shared memory with coalesced
+// loads (zero-filled outside the image, so the inner loop has no bounds test), then the block's
+// TOX*cell output elements -- one contiguous run of cols -- are produced with one table lookup
+// (tap -> smem offset), one shared-memory read and one coalesced global store each.  All index
+// arithmetic is 32-bit; t / cell is a multiply-high by a precomputed reciprocal.
+struct Im2colTile {
+    int tox;            // out columns per CTA
+    int width_x;        // input columns staged per source row: (tox-1)*stride_w + (filter_w-1)*dilation_w + 1
+    int row_elems;      // elements per staged ky-slab: width_x * channels
+    unsigned cell_magic;   // floor(2^32 / cell) + 1
+    unsigned chan_magic;   // floor(2^32 / channels) + 1
+    unsigned wx_magic;     // floor(2^32 / width_x) + 1
+};
+
+// t / d for t*d < 2^32 with magic = floor(2^32/d) + 1 (d == 1 has no 32-bit magic)
+__device__ __forceinline__ int ic_fastdiv(int t, unsigned magic, int d)
+{
+    return d == 1 ? t : (int)__umulhi((unsigned)t, magic);
+}
+
+template <typename W>
+__global__ void __launch_bounds__(IC_THREADS)
+im2col2d_forward_tiled(Im2colParams p, Im2colTile tl, const W* __restrict__ images, W* __restrict__ cols)
+{
+    extern __shared__ __align__(16) unsigned char ic_smem_raw[];
+    int* lut = reinterpret_cast<int*>(ic_smem_raw);                       // [cell] tap -> smem offset
+    W* tile = reinterpret_cast<W*>(ic_smem_raw + ((p.cell * 4 + 15) & ~15LL));   // [filter_h][row_elems]
+
+    const int cell = (int)p.cell;
+    const int C = (int)p.channels, KW = (int)p.filter_w, KH = (int)p.filter_h;
+    const int ox0 = blockIdx.x * tl.tox;
+    const int oy = blockIdx.y;
+    const int b = blockIdx.z;
+    const int tox = min(tl.tox, (int)p.out_w - ox0);
+    const bool cf = p.channel_step != 1;                                 // channels_first images
+    // smem element (ky, x, c): channels-last ky*row_elems + x*C + c ; channels-first ky*row_elems + c*width_x + x
+    const int xs = cf ? 1 : C;
+    for (int r = threadIdx.x; r < cell; r += IC_THREADS) {
+        int ky, kx, c;
+        if (p.cols_channels_first) { c = r / (KH * KW); int q = r - c * KH * KW; ky = q / KW; kx = q - ky * KW; }
+        else { int q = r / C; c = r - q * C; ky = q / KW; kx = q - ky * KW; }
+        lut[r] = ky * tl.row_elems + kx * (int)p.dilation_w * xs + (cf ? c * tl.width_x : c);
+    }
+    // stage the source rows
+    const int x_start = ox0 * (int)p.stride_w - (int)p.padding_w;
+    const int y_start = oy * (int)p.stride_h - (int)p.padding_h;
+    const W* img_b = images + (int64_t)b * p.batch_step;
+    const int total = KH * tl.row_elems;
+    for (int e = threadIdx.x; e < total; e += IC_THREADS) {
+        const int ky = e / tl.row_elems;
+        const int rem = e - ky * tl.row_elems;
+        int x, c;
+        if (cf) { c = ic_fastdiv(rem, tl.wx_magic, tl.width_x); x = rem - c * tl.width_x; }
+        else    { x = ic_fastdiv(rem, tl.chan_magic, C); c = rem - x * C; }
+        const int iy = y_start + ky * (int)p.dilation_h;
+        const int ix = x_start + x;
+        W v = (W)0;
+        if (iy >= 0 && iy < (int)p.im_h && ix >= 0 && ix < (int)p.im_w) {
+            v = __ldg(img_b + (int64_t)iy * p.im_h_step + (int64_t)ix * p.im_w_step + (int64_t)c * p.channel_step);
+        }
+        tile[e] = v;
+    }
+    __syncthreads();
+    W* out = cols + (((int64_t)b * p.out_h + oy) * p.out_w + ox0) * cell;
+    const int n_out = tox * cell;
+    const int sx = (int)p.stride_w * xs;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < n_out; t += IC_THREADS) {
+        const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+        const int r = t - oxl * cell;
+        out[t] = tile[lut[r] + oxl * sx];
+    }
+}
+
 // reverse: one thread per image element; taps visited in the reference's accumulation order.
 template <typename T>
 __global__ void __launch_bounds__(IC_THREADS)
@@ -150,12 +227,51 @@ col2im2d_reverse(Im2colParams p, T* __restrict__ images, const T* __restrict__ c
     }
 }
 
+static unsigned magic_u32(int64_t d) { return (unsigned)((1ULL << 32) / (unsigned long long)d) + 1u; }
+
 template <typename W>
 int forward_launch(const Im2colParams& p, const void* images, void* cols)
 {
     rb200::Context& c = rb200::ctx();
     const W* im = reinterpret_cast<const W*>(images);
     W* co = reinterpret_cast<W*>(cols);
+    // tiled kernel: needs the per-CTA working set in 48 KB of shared memory and 32-bit in-tile indices
+    {
+        const int64_t smem_budget = 48 * 1024 - 16;
+        const int64_t lut_bytes = (p.cell * 4 + 15) & ~15LL;
+        const int64_t per_x = p.filter_h * p.channels * (int64_t)sizeof(W);      // bytes per staged input column
+        const int64_t base_x = (p.filter_w - 1) * p.dilation_w + 1;
+        int64_t max_wx = (smem_budget - lut_bytes) / (per_x > 0 ? per_x : 1);
+        int64_t tox = max_wx >= base_x ? (max_wx - base_x) / p.stride_w + 1 : 0;
+        if (tox > p.out_w) tox = p.out_w;
+        // keep >= ~4 CTAs per SM in flight for small images by splitting rows further
+        const int64_t ctas_full = p.batches * p.out_h;
+        if (tox > 64 && ctas_full * rb_ceil_div(p.out_w, tox) < (int64_t)c.sm_count * 4) {
+            const int64_t want = rb_ceil_div((int64_t)c.sm_count * 4, ctas_full);
+            int64_t t2 = rb_ceil_div(p.out_w, want);
+            if (t2 < 32) t2 = 32;
+            if (t2 < tox) tox = t2;
+        }
+        const bool small_idx = tox >= 1 && tox * p.cell * p.cell < (1LL << 32) && p.cell <= 65536 &&
+                               p.batches <= 65535 && p.out_h <= 65535 && p.im_h < (1LL << 30) && p.im_w < (1LL << 30) &&
+                               p.out_w * p.stride_w < (1LL << 30);
+        if (small_idx) {
+            Im2colTile tl;
+            tl.tox = (int)tox;
+            tl.width_x = (int)((tox - 1) * p.stride_w + base_x);
+            tl.row_elems = tl.width_x * (int)p.channels;
+            tl.cell_magic = magic_u32(p.cell);
+            tl.chan_magic = magic_u32(p.channels);
+            tl.wx_magic = magic_u32(tl.width_x);
+            const int64_t smem = lut_bytes + p.filter_h * (int64_t)tl.row_elems * (int64_t)sizeof(W);
+            if (smem <= smem_budget + 16 && (int64_t)tl.row_elems * p.channels < (1LL << 31)) {
+                dim3 grid((unsigned)rb_ceil_div(p.out_w, tox), (unsigned)p.out_h, (unsigned)p.batches);
+                im2col2d_forward_tiled<W><<<grid, IC_THREADS, (size_t)smem, c.stream>>>(p, tl, im, co);
+                RB_LAUNCH_CHECK("im2col2d_forward_tiled");
+                return RB200_OK;
+            }
+        }
+    }
     const bool vec = (reinterpret_cast<uintptr_t>(co) & 15) == 0;
     const bool table = p.cell <= IC_MAX_CELL;
     const int V = vec ? 16 / (int)sizeof(W) : 1;

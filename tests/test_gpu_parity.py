@@ -167,8 +167,16 @@ def test_elementwise_vs_oracle(shape, op, alpha, dt, cuda_service):
     elif dt == dtypes.float32 and (op == "multiply" or abs(alpha) == 1.0):
         assert np.array_equal(got, ao.astype(np.float32))         # bit-exact vs oracle rounded once
     else:
-        ulp = np.spacing(np.abs(ao).astype(npdt)).astype(np.float64)
-        assert np.all(np.abs(got.astype(np.float64) - ao) <= ulp)   # fused multiply-add: within 1 ulp
+        # general alpha: the device uses one fused multiply-add in the operand precision (alpha is cast
+        # to it), the oracle a separate double multiply and add: |d| <= 2 eps (|alpha x| + |a|)
+        eps = float(np.finfo(npdt).eps)
+        xs = Xh[offX::incX][: (m if trans else n)].astype(np.float64)
+        xb = np.repeat(xs, n).reshape(m, n) if trans else np.tile(xs, (m, 1))
+        a0 = np.stack([Ah[offA + i * ldA: offA + i * ldA + n] for i in range(m)]).astype(np.float64)
+        bound = 2 * eps * (np.abs(alpha * xb) + np.abs(a0)) + 1e-300
+        g = np.stack([got[offA + i * ldA: offA + i * ldA + n] for i in range(m)]).astype(np.float64)
+        r = np.stack([ao[offA + i * ldA: offA + i * ldA + n] for i in range(m)])
+        assert np.all(np.abs(g - r) <= bound)
     # elements outside the m x n view (ld padding, before offA) untouched
     mask = np.ones(Ah.size, bool)
     for i in range(m):
@@ -573,7 +581,7 @@ def test_im2col2d_random_bit_exact(dt, padding, cf, ccf, k, s, d, cuda_service):
     b, h, w, c = 3, 19, 23, 5
     rng = np.random.default_rng(4001)
     npdt = dtypes.NUMPY[dt]
-    img = (rng.uniform(0, 1, b * h * w * c) * 100).astype(npdt)
+    img = np.floor(rng.uniform(0, 1, b * h * w * c) * 100).astype(npdt)      # integer-valued: col2im sums are exact
     off_i, off_c = 3, 4
     shape = oracle.im2col2d_out_shape(b, h, w, c, k[0], k[1], s[0], s[1], padding, d[0], d[1], ccf)
     ncols = int(np.prod(shape))
@@ -591,6 +599,28 @@ def test_im2col2d_random_bit_exact(dt, padding, cf, ccf, k, s, d, cuda_service):
         math.im2col2d(True, images, off_i, img.size, *args, cols, off_c, ncols)
         oracle.im2col2d(True, io, off_i, img.size, *args, co, off_c, ncols)
         assert np.array_equal(images.to_numpy().astype(np.float64), io)       # small integers: exact
+
+
+@pytest.mark.parametrize("b,h,w,c,k,s,d,padding,cf,ccf", [
+    (2, 5, 7, 1, (1, 1), (1, 1), (1, 1), False, False, False),        # cell == 1, one channel
+    (1, 9, 9, 1, (3, 3), (1, 1), (1, 1), True, True, False),
+    (3, 6, 300, 2, (3, 5), (1, 2), (1, 3), True, False, True),        # wide rows
+    (1, 40, 3000, 16, (3, 3), (1, 1), (1, 1), False, False, False),   # row split into several column blocks
+    (2, 12, 12, 600, (3, 3), (1, 1), (1, 1), True, False, False),     # cell = 5400 > tap table of the flat kernel
+    (1, 4, 4, 20000, (2, 2), (1, 1), (1, 1), False, False, False),    # too wide for shared memory: flat kernel
+])
+def test_im2col2d_shapes_bit_exact(b, h, w, c, k, s, d, padding, cf, ccf, cuda_service):
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 1000, b * h * w * c).astype(np.float32)
+    shape = oracle.im2col2d_out_shape(b, h, w, c, k[0], k[1], s[0], s[1], padding, d[0], d[1], ccf)
+    ncols = int(np.prod(shape))
+    images = CudaBuffer(img.size, dtypes.float32).from_numpy(img)
+    cols = CudaBuffer(ncols, dtypes.float32)
+    args = (b, h, w, c, k[0], k[1], s[0], s[1], padding, cf, d[0], d[1], ccf)
+    cuda_service.math().im2col2d(False, images, 0, img.size, *args, cols, 0, ncols)
+    io, co = oracle.as_buffer(img), np.zeros(ncols)
+    oracle.im2col2d(False, io, 0, img.size, *args, co, 0, ncols)
+    assert np.array_equal(cols.to_numpy().astype(np.float64), co)
 
 
 def test_im2col2d_errors(cuda_service):

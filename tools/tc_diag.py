@@ -57,6 +57,12 @@ def main():
     _capi.init(0)
     print(_capi.device_info())
     shapes = [(128, 256, 32), (128, 256, 64), (256, 512, 256), (384, 384, 96), (1024, 1024, 1024)]
+    if os.environ.get("RB200_DIAG_QUICK"):
+        print("env:", {k: v for k, v in os.environ.items() if k.startswith("RB200_DBG")})
+        for tA, tB in ((False, False), (True, True), (True, False)):
+            for (m, n, k) in shapes[:3]:
+                run(rb.GEMM_TF32, m, n, k, tA, tB, integer=True)
+        return
     for mode in (rb.GEMM_TF32, rb.GEMM_TF32X3):
         for tA in (False, True):
             for tB in (False, True):
@@ -75,9 +81,14 @@ def main():
     rb.CudaBlas(rb.GEMM_TF32).gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, m, n, k, 1.0, A, 0, k, B, 0, n, 0.0,
                                    C, 0, n)
     v = float(C.to_numpy()[0])
-    print("tf32 input conversion probe: in=%.10f out=%.10f -> %s" % (
-        float(Ah[0, 0]), v, "truncation" if v == 1.0 + 2.0 ** -10 - 2.0 ** -10 + 0 * 1 or v == 1.0 else
-        ("round-to-nearest" if abs(v - (1.0 + 2.0 ** -10)) < 1e-9 else "other")))
+    kind = "truncation" if v == 1.0 else ("round-to-nearest" if abs(v - (1.0 + 2.0 ** -10)) < 1e-9 else "other")
+    print("tf32 input conversion probe (B NoTrans): in=%.10f out=%.10f -> %s" % (float(Ah[0, 0]), v, kind))
+    Bt = CudaBuffer(Bh.size, dtypes.float32).from_numpy(np.ascontiguousarray(Bh.T))
+    rb.CudaBlas(rb.GEMM_TF32).gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.Trans, m, n, k, 1.0, A, 0, k, Bt, 0, k, 0.0,
+                                   C, 0, n)
+    v = float(C.to_numpy()[0])
+    kind = "truncation" if v == 1.0 else ("round-to-nearest" if abs(v - (1.0 + 2.0 ** -10)) < 1e-9 else "other")
+    print("tf32 input conversion probe (B Trans): in=%.10f out=%.10f -> %s" % (float(Ah[0, 0]), v, kind))
 
 
 if __name__ == "__main__":
