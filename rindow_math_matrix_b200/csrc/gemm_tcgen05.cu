@@ -504,9 +504,6 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         srcA = wA; srcB = wB; sldA = cA; sldB = cB;
     }
 
-    CUtensorMap mA, mB;
-    int rc;
-    // K-major: inner = K, outer = M|N, box {32, rows}.  MN-major: inner = M|N, outer = K, box {32, 32}.
     // MN-major tiles use the 128-byte swizzle with 32-byte atoms on both sides (TMA and UMMA descriptor):
     // k-rows of 128 bytes, 32-byte chunks XORed with (k mod 4); descriptor SBO = 512 (4 k-rows),
     // LBO = 4096 (next box of 32 columns).  Debug overrides: RB200_DBG_MN_{SWIZZLE,LBO,SBO,LAYOUT}.
@@ -516,27 +513,42 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
     static const int dbg_layout = getenv("RB200_DBG_MN_LAYOUT") ? atoi(getenv("RB200_DBG_MN_LAYOUT")) : -1;
     const CUtensorMapSwizzle k_sw = CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapSwizzle mn_sw = dbg_sw >= 0 ? (CUtensorMapSwizzle)dbg_sw : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (!a_mn) rc = make_map(&mA, srcA, K, M, sldA, planes, plsA, TC_BK, TC_BM, k_sw);
-    else       rc = make_map(&mA, srcA, M, K, sldA, planes, plsA, 32, TC_BK, mn_sw);
-    if (rc != RB200_OK) return rc;
-    if (!b_mn) rc = make_map(&mB, srcB, K, N, sldB, planes, plsB, TC_BK, BN, k_sw);
-    else       rc = make_map(&mB, srcB, N, K, sldB, planes, plsB, 32, TC_BK, mn_sw);
-    if (rc != RB200_OK) return rc;
 
-    TcParams p;
-    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
-    p.num_m_blocks = (int)rb_ceil_div(M, TC_BM);
-    p.num_n_blocks = (int)rb_ceil_div(N, BN);
-    p.num_k_blocks = (int)rb_ceil_div(K, TC_BK);
-    p.mn_lbo = dbg_lbo >= 0 ? (uint32_t)dbg_lbo : 4096u;
-    p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
-    p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
-    if (planes == 1) {
-        c.last_gemm_path = "tcgen05_tf32";
-        return launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
+    // The TMEM fp32 accumulator TRUNCATES on every accumulation (measured: profiles/, accumulation
+    // probe -- all-positive inputs drift by -1.4e-5 at K=4096 and -9.3e-5 at K=16384, linearly in K).
+    // That is below the 1xTF32 tolerance, but the 3xTF32 parity mode promises the reference's 1e-4
+    // bound, so there K is processed in chunks of <= 2048 and the chunk results are added in the
+    // epilogue with round-to-nearest FMAs (C = alpha*acc + 1*C): drift <= ~5e-6 per chunk, and the
+    // chunk sums no longer accumulate it coherently.
+    const int64_t KC = (planes == 2) ? 2048 : K;
+    c.last_gemm_path = planes == 1 ? "tcgen05_tf32" : "tcgen05_tf32x3";
+    for (int64_t kc = 0; kc < K; kc += KC) {
+        const int64_t kl = (K - kc) < KC ? (K - kc) : KC;
+        // K-major: inner = K, outer = M|N, box {32, rows}.  MN-major: inner = M|N, outer = K, box {32, 32}.
+        const float* pa = a_mn ? srcA + kc * sldA : srcA + kc;
+        const float* pb = b_mn ? srcB + kc * sldB : srcB + kc;
+        CUtensorMap mA, mB;
+        int rc;
+        if (!a_mn) rc = make_map(&mA, pa, kl, M, sldA, planes, plsA, TC_BK, TC_BM, k_sw);
+        else       rc = make_map(&mA, pa, M, kl, sldA, planes, plsA, 32, TC_BK, mn_sw);
+        if (rc != RB200_OK) return rc;
+        if (!b_mn) rc = make_map(&mB, pb, kl, N, sldB, planes, plsB, TC_BK, BN, k_sw);
+        else       rc = make_map(&mB, pb, N, kl, sldB, planes, plsB, 32, TC_BK, mn_sw);
+        if (rc != RB200_OK) return rc;
+
+        TcParams p;
+        p.M = M; p.N = N; p.K = kl; p.alpha = alpha; p.beta = (kc == 0) ? beta : 1.0f; p.C = C; p.ldC = ldC;
+        p.num_m_blocks = (int)rb_ceil_div(M, TC_BM);
+        p.num_n_blocks = (int)rb_ceil_div(N, BN);
+        p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
+        p.mn_lbo = dbg_lbo >= 0 ? (uint32_t)dbg_lbo : 4096u;
+        p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
+        p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
+        if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
+        else             rc = launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
+        if (rc != RB200_OK) return rc;
     }
-    c.last_gemm_path = "tcgen05_tf32x3";
-    return launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
+    return RB200_OK;
 }
 
 }  // namespace rb200

@@ -178,11 +178,33 @@ im2col2d_forward_tiled(Im2colParams p, Im2colTile tl, const W* __restrict__ imag
     W* out = cols + (((int64_t)b * p.out_h + oy) * p.out_w + ox0) * cell;
     const int n_out = tox * cell;
     const int sx = (int)p.stride_w * xs;
-#pragma unroll 4
-    for (int t = threadIdx.x; t < n_out; t += IC_THREADS) {
+    // 128-bit stores: scalar head up to the next 16-byte boundary, vector body, scalar tail
+    constexpr int V = 16 / (int)sizeof(W);
+    const int mis = (int)((reinterpret_cast<uintptr_t>(out) / sizeof(W)) & (V - 1));
+    int head = (V - mis) & (V - 1);
+    if (head > n_out) head = n_out;
+    if ((int)threadIdx.x < head) {
+        const int t = threadIdx.x;
         const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
-        const int r = t - oxl * cell;
-        out[t] = tile[lut[r] + oxl * sx];
+        out[t] = tile[lut[t - oxl * cell] + oxl * sx];
+    }
+    const int nvec = (n_out - head) / V;
+    for (int g = threadIdx.x; g < nvec; g += IC_THREADS) {
+        const int t = head + g * V;
+        int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+        int r = t - oxl * cell;
+        int xoff = oxl * sx;
+        IcPack<W> pk;
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            pk.v[e] = tile[lut[r] + xoff];
+            if (++r == cell) { r = 0; xoff += sx; }
+        }
+        __stcs(reinterpret_cast<int4*>(out + t), pk.raw);
+    }
+    for (int t = head + nvec * V + threadIdx.x; t < n_out; t += IC_THREADS) {
+        const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+        out[t] = tile[lut[t - oxl * cell] + oxl * sx];
     }
 }
 

@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Run one hot-path op a few times at its BASELINE size -- the command ncu wraps
+(profiles/README.md lists the exact ncu invocations).  Usage: profile_ops.py OP [REPS]
+OP in: sgemm_tf32 sgemm_tf32x3 sgemm_simt add multiply reduce_sum reduce_sum_axis0 reduce_max
+       reduce_argmax softmax im2col2d conv_gemm"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import rindow_math_matrix_b200 as rb  # noqa: E402
+from rindow_math_matrix_b200 import BLAS, CudaBuffer, _capi, dtypes  # noqa: E402
+
+
+def main():
+    op = sys.argv[1]
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    svc = rb.MatlibCuda()
+    math, blas = svc.math(), svc.blas()
+    f32 = dtypes.float32
+    rng = np.random.default_rng(0)
+
+    def rnd(n):
+        return CudaBuffer(n, f32, zero=False).from_numpy(rng.uniform(-1, 1, n).astype(np.float32))
+
+    if op.startswith("sgemm"):
+        n = int(os.environ.get("N", "8192"))
+        mode = {"sgemm_tf32": rb.GEMM_TF32, "sgemm_tf32x3": rb.GEMM_TF32X3, "sgemm_simt": rb.GEMM_FP32_SIMT}[op]
+        A, B, C = rnd(n * n), rnd(n * n), CudaBuffer(n * n, f32)
+        blas.setGemmMode(mode)
+        fn = lambda: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A, 0, n, B, 0, n, 0.0, C, 0, n)
+    elif op in ("add", "multiply"):
+        m, n = 8192, 4096
+        A, X = rnd(m * n), rnd(n)
+        fn = (lambda: math.add(False, m, n, 1.0, X, 0, 1, A, 0, n)) if op == "add" else \
+             (lambda: math.multiply(False, m, n, X, 0, 1, A, 0, n))
+    elif op in ("reduce_sum", "reduce_max", "reduce_argmax", "reduce_sum_axis0", "softmax"):
+        m, n = 65536, 1024
+        A = rnd(m * n)
+        Bf, Bi = CudaBuffer(m, f32), CudaBuffer(m, dtypes.int32)
+        fn = {"reduce_sum": lambda: math.reduceSum(m, n, 1, A, 0, Bf, 0),
+              "reduce_max": lambda: math.reduceMax(m, n, 1, A, 0, Bf, 0),
+              "reduce_argmax": lambda: math.reduceArgMax(m, n, 1, A, 0, Bi, 0),
+              "reduce_sum_axis0": lambda: math.reduceSum(1, m, n, A, 0, Bf, 0),
+              "softmax": lambda: math.softmax(m, n, A, 0, n)}[op]
+    elif op in ("im2col2d", "conv_gemm"):
+        b, h, w, c = 64, 224, 224, 3
+        images = rnd(b * h * w * c)
+        ncols = b * 222 * 222 * 27
+        cols = CudaBuffer(ncols, f32, zero=False)
+        im2col = lambda: math.im2col2d(False, images, 0, b * h * w * c, b, h, w, c, 3, 3, 1, 1, False, False, 1, 1,
+                                       False, cols, 0, ncols)
+        if op == "im2col2d":
+            fn = im2col
+        else:
+            im2col()
+            M = b * 222 * 222
+            Wt, out = rnd(27 * 64), CudaBuffer(M * 64, f32, zero=False)
+            blas.setGemmMode(0)
+            fn = lambda: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, 64, 27, 1.0, cols, 0, 27, Wt, 0, 64,
+                                   0.0, out, 0, 64)
+    else:
+        raise SystemExit("unknown op " + op)
+    for _ in range(reps):
+        fn()
+    _capi.sync()
+    print(op, "ok", _capi.last_gemm_path() if "gemm" in op else "")
+
+
+if __name__ == "__main__":
+    main()

@@ -91,5 +91,33 @@ def main():
     print("tf32 input conversion probe (B Trans): in=%.10f out=%.10f -> %s" % (float(Ah[0, 0]), v, kind))
 
 
+def accumulation_probe():
+    """Accumulator rounding of tcgen05 kind::tf32: inputs with <= 8 mantissa bits (exact in tf32,
+    products exact in fp32), all positive, so every bit of error comes from the fp32 accumulation
+    in TMEM.  A round-to-nearest accumulator gives a mean relative error ~0 growing like sqrt(K);
+    a truncating one gives a negative mean growing like K."""
+    rng = np.random.default_rng(3)
+    m = n = 128
+    for mode in (rb.GEMM_TF32, rb.GEMM_TF32X3, rb.GEMM_FP32_SIMT):
+        for k in (256, 1024, 4096, 16384):
+            Ah = (np.round(rng.uniform(0.5, 1.0, (m, k)) * 256) / 256).astype(np.float32)
+            Bh = (np.round(rng.uniform(0.5, 1.0, (n, k)) * 256) / 256).astype(np.float32)
+            A = CudaBuffer(Ah.size, dtypes.float32).from_numpy(Ah)
+            B = CudaBuffer(Bh.size, dtypes.float32).from_numpy(Bh)
+            C = CudaBuffer(m * n, dtypes.float32)
+            rb.CudaBlas(mode).gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.Trans, m, n, k, 1.0, A, 0, k, B, 0, k, 0.0,
+                                   C, 0, n)
+            got = C.to_numpy().reshape(m, n).astype(np.float64)
+            ref = Ah.astype(np.float64) @ Bh.astype(np.float64).T
+            rel = (got - ref) / ref
+            print("accum probe mode=%-9s K=%6d path=%-14s mean_rel=%+.3e std_rel=%.3e max_abs_rel=%.3e" % (
+                _capi.GEMM_MODE_NAMES[mode], k, _capi.last_gemm_path(), rel.mean(), rel.std(), np.abs(rel).max()),
+                flush=True)
+
+
 if __name__ == "__main__":
+    if os.environ.get("RB200_DIAG_ACCUM"):
+        _capi.init(0)
+        accumulation_probe()
+        sys.exit(0)
     main()
