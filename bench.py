@@ -296,6 +296,25 @@ def run_b200(args):
                 "peak_note": "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); %s"
                              % (peaks["source"], achieved_note)}
 
+    # ---- multi-GPU: the same step followed by the NCCL all-gather of the C stripes (only when the caller
+    #      needs the full C on every rank; reported beside the collective-free number) --------------------
+    with_gather = None
+    if world > 1:
+        from rindow_math_matrix_b200 import sharding
+        tC = sharding.tensor_of(C, (n, n))
+        with torch.cuda.stream(stream):
+            full = torch.empty((n * world, n), dtype=torch.float32, device="cuda")
+
+        def gather_step():
+            gemm_step()
+            dist.all_gather_into_tensor(full, tC)
+
+        g_steps = max(3, min(args.steps, 10))
+        g_ms = timed(gather_step, g_steps, 3) / g_steps
+        with_gather = {"value": world * flops_per_step / (g_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": g_ms,
+                       "allgather_bytes_per_rank": (world - 1) * n * n * 4,
+                       "note": "gemm + ncclAllGather of the row stripes of C, same stream (not overlapped)"}
+
     # ---- e2e: the same call with HOST buffers (pinned mirror -> h2d, kernel, d2h) --------------------
     A.host(); B.host(); C.host()                      # create the pinned mirrors outside the timed region
     _capi.sync()
@@ -377,7 +396,7 @@ def run_b200(args):
                                            "fp32_simt": "f32"}[args.mode],
             "data": "synthetic", "config": workload_config(n, world, args.mode),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "hbm_ops": hbm_ops,
+            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "hbm_ops": hbm_ops, "with_gather": with_gather,
             "peaks": peaks,
         }
         print(json.dumps(line), flush=True)

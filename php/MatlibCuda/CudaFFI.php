@@ -1,0 +1,94 @@
+<?php
+namespace Rindow\Math\Matrix\Drivers\MatlibCuda;
+
+use FFI;
+use RuntimeException;
+
+/**
+ * Thin PHP-FFI binding of librindow_b200.so (C ABI: include/rindow_b200.h).
+ *
+ * NOTE: this file cannot be executed in the build environment of this repository (no PHP
+ * interpreter); it is the reference-side binding a maintainer adds, kept mechanical on purpose:
+ * every method is validation (the reference's own Utils trait) + one FFI call.  The same ABI is
+ * exercised by the ctypes binding rindow_math_matrix_b200/_capi.py, function for function.
+ */
+class CudaFFI
+{
+    private static ?FFI $ffi = null;
+
+    public const CDEF = <<<'CDEF'
+        int         rb200_abi_version(void);
+        const char* rb200_last_error(void);
+        int         rb200_device_count(int* count);
+        int         rb200_init(int device);
+        int         rb200_shutdown(void);
+        int         rb200_sync(void);
+        int         rb200_set_default_gemm_mode(int mode);
+        int         rb200_buffer_alloc(int64_t bytes, void** dptr);
+        int         rb200_buffer_free(void* dptr);
+        int         rb200_buffer_h2d(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes);
+        int         rb200_buffer_d2h(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes);
+        int         rb200_buffer_h2d_async(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes);
+        int         rb200_buffer_d2d(void* dst, int64_t dst_off, const void* src, int64_t src_off, int64_t bytes);
+        int         rb200_buffer_fill(int dtype, void* dptr, int64_t off, int64_t n, const void* value);
+        int         rb200_host_alloc(int64_t bytes, void** hptr);
+        int         rb200_host_free(void* hptr);
+        int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                        float alpha, const float* A, int64_t offA, int64_t ldA,
+                        const float* B, int64_t offB, int64_t ldB,
+                        float beta, float* C, int64_t offC, int64_t ldC, int mode);
+        int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                        double alpha, const double* A, int64_t offA, int64_t ldA,
+                        const double* B, int64_t offB, int64_t ldB,
+                        double beta, double* C, int64_t offC, int64_t ldC);
+        int rb200_add(int dtype, int trans, int64_t m, int64_t n, double alpha,
+                      const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+        int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,
+                           const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+        int rb200_reduce_sum(int dtype, int64_t m, int64_t n, int64_t k,
+                             const void* A, int64_t offA, void* B, int64_t offB);
+        int rb200_reduce_max(int dtype, int64_t m, int64_t n, int64_t k,
+                             const void* A, int64_t offA, void* B, int64_t offB);
+        int rb200_reduce_argmax(int dtype, int64_t m, int64_t n, int64_t k,
+                                const void* A, int64_t offA, int index_dtype, void* B, int64_t offB);
+        int rb200_softmax(int dtype, int64_t m, int64_t n, void* A, int64_t offA, int64_t ldA);
+        int rb200_im2col2d(int dtype, int reverse,
+                           void* images, int64_t images_offset, int64_t images_size,
+                           int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                           int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                           int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
+                           int cols_channels_first,
+                           void* cols, int64_t cols_offset, int64_t cols_size);
+        CDEF;
+
+    public static function lib() : FFI
+    {
+        if (self::$ffi === null) {
+            $path = getenv('RINDOW_B200_LIB') ?: 'librindow_b200.so';
+            self::$ffi = FFI::cdef(self::CDEF, $path);
+            self::check(self::$ffi->rb200_init((int)(getenv('RINDOW_B200_DEVICE') ?: 0)));
+        }
+        return self::$ffi;
+    }
+
+    public static function isAvailable() : bool
+    {
+        if (!extension_loaded('ffi')) {
+            return false;
+        }
+        try {
+            self::lib();
+            return true;
+        } catch (\Throwable $e) {
+            return false;
+        }
+    }
+
+    public static function check(int $status) : void
+    {
+        if ($status != 0) {
+            throw new RuntimeException(
+                'librindow_b200 status '.$status.': '.FFI::string(self::$ffi->rb200_last_error()));
+        }
+    }
+}

@@ -1,0 +1,20 @@
+<?php
+namespace RindowTest\Math\Matrix\MatrixOperatorCudaTest;
+
+use Rindow\Math\Matrix\MatrixOperator;
+use Rindow\Math\Matrix\Drivers\Service;
+use Rindow\Math\Matrix\Drivers\MatlibCuda\MatlibCuda;
+use RindowTest\Math\Matrix\MatrixOperatorTest\MatrixOperatorTest as ORGTest;
+
+/** MatrixOperatorTest over the B200 driver (cf. MatrixOperatorPhpModeTest.php:14-25). */
+class MatrixOperatorCudaTest extends ORGTest
+{
+    public function newMatrixOperator()
+    {
+        $service = new MatlibCuda();
+        if($service->serviceLevel()<Service::LV_ADVANCED) {
+            $this->markTestSkipped('librindow_b200.so / B200 not available');
+        }
+        return new MatrixOperator(service:$service);
+    }
+}

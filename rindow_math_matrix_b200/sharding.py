@@ -1,0 +1,120 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY.md section 8(e): the path shards by ROWS.
+  * sgemm            : rank g owns rows [start_g, start_g + rows_g) of A and C, B is replicated; each
+                       rank runs the single-GPU kernel on its stripe.  No data-path collective unless
+                       the caller wants the full C everywhere -> gather_rows() (NCCL all-gather).
+  * add / multiply / softmax / reductions along a non-sharded axis / im2col2d: independent units,
+                       no collective at all.
+  * reductions ALONG the sharded axis (axis 0 of row-sharded data): local partials [k] per rank, then
+                       one small exchange -- merge_sum / merge_max / merge_argmax below.  max and argmax
+                       gather the per-rank partials and merge them locally in rank order, so NaN
+                       stickiness and the lowest-global-index tie rule of the single-GPU kernels
+                       (PhpMath.php:95-130) are preserved exactly and deterministically.
+
+Everything here works on torch tensors of any device, so the same code runs under NCCL on B200s and
+under gloo on CPU (tests/test_sharding_gloo.py, world_size 2).  No compute happens in this module.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def row_range(total_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row stripe of `rank`: the first (total_rows % world) ranks get one extra row."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(total_rows, world)
+    rows = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, rows
+
+
+def all_row_ranges(total_rows: int, world: int) -> List[Tuple[int, int]]:
+    return [row_range(total_rows, world, r) for r in range(world)]
+
+
+def tensor_of(buffer, shape=None, offset: int = 0) -> torch.Tensor:
+    """Zero-copy torch view of a CudaBuffer (through __cuda_array_interface__), for NCCL."""
+    t = torch.as_tensor(buffer, device="cuda")
+    if offset:
+        t = t[offset:]
+    if shape is not None:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        t = t[:n].view(*shape)
+    return t
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def gather_rows(local: torch.Tensor, total_rows: int, group=None) -> torch.Tensor:
+    """All-gather row stripes [rows_g, ...] into the full [total_rows, ...] tensor on every rank."""
+    world = _world(group)
+    if world == 1:
+        return local
+    ranges = all_row_ranges(total_rows, world)
+    tail = tuple(local.shape[1:])
+    if len({r for _, r in ranges}) == 1:
+        out = torch.empty((total_rows,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # uneven stripes: pad to the largest, gather, trim
+    max_rows = max(r for _, r in ranges)
+    padded = torch.zeros((max_rows,) + tail, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:r] for p, (_, r) in zip(parts, ranges)], dim=0)
+
+
+def merge_sum(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of per-rank partial sums (all-reduce)."""
+    if _world(group) > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial
+
+
+def _gather_stack(t: torch.Tensor, group=None) -> torch.Tensor:
+    world = _world(group)
+    if world == 1:
+        return t.unsqueeze(0)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t.contiguous(), group=group)
+    return torch.stack(parts, dim=0)
+
+
+def merge_max(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """NaN-sticky maximum over ranks of per-rank partial maxima."""
+    stack = _gather_stack(partial, group)                  # [world, k]
+    has_nan = torch.isnan(stack).any(dim=0)
+    mx = torch.nan_to_num(stack, nan=float("-inf")).max(dim=0).values
+    return torch.where(has_nan, torch.full_like(mx, float("nan")), mx)
+
+
+def merge_argmax(values: torch.Tensor, indices: torch.Tensor, row_offset: int, group=None) -> torch.Tensor:
+    """Global arg-max along the sharded axis from per-rank (max value, local index) pairs.
+    `values` must be the value AT the local argmax (NaN if the local winner is a NaN in local
+    position 0).  Rule (math_imax, PhpMath.php:114-130): first strict maximum wins, ties -> lowest
+    global index; a NaN only wins when it sits at GLOBAL position 0."""
+    gidx = indices.to(torch.int64) + int(row_offset)
+    vals = _gather_stack(values, group)                    # [world, k]
+    idxs = _gather_stack(gidx, group)
+    world = vals.shape[0]
+    best_v, best_i = vals[0].clone(), idxs[0].clone()
+    # rank 0 holds global position 0: if its winner is NaN it is NaN-at-0 and is never displaced
+    locked = torch.isnan(best_v)
+    for r in range(1, world):
+        v, i = vals[r], idxs[r]
+        better = (v > best_v) & ~locked                   # NaN compares false: never wins later
+        # a later rank's NaN-at-local-0 is an ordinary (losing) NaN globally, but the values behind it
+        # on that rank were never compared: callers pass nan_free_values when that matters
+        best_v = torch.where(better, v, best_v)
+        best_i = torch.where(better, i, best_i)
+    return best_i
