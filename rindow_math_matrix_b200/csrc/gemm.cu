@@ -10,6 +10,9 @@ namespace rb200 {
 template <typename T>
 int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk,
               const T* B, int64_t sBk, int64_t sBn, T beta, T* C, int64_t ldC);
+bool gemm_shortk_eligible(int64_t M, int64_t N, int64_t K, int64_t sAk, int64_t sBn);
+int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
+                const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
 bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
                            const float* B, int64_t ldB, const float* C, int64_t ldC);
 int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
@@ -65,12 +68,22 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     // The tensor-core path pays off from one full 128 x 128 tile upwards; the known-answer
     // sized problems (3x3 ... 64x64) and anything TMA cannot address run on the FFMA path.
     const bool big = (m >= 128 && n >= 128 && k >= 32);
-    if (mode != RB200_GEMM_FP32_SIMT && big && rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC)) {
+    const bool shortk_first = (k <= 64) && !tA && !tB && (mode != RB200_GEMM_TF32) &&
+                              rb200::gemm_shortk_eligible(m, n, k, 1, 1);
+    if (!shortk_first && mode != RB200_GEMM_FP32_SIMT && big &&
+        rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC)) {
         return rb200::gemm_tcgen05(mode, tA, tB, m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
     }
-    c.last_gemm_path = "simt_f32";
     const int64_t sAm = tA ? 1 : ldA, sAk = tA ? ldA : 1;
     const int64_t sBk = tB ? 1 : ldB, sBn = tB ? ldB : 1;
+    // tall matrix with a short K (the conv-as-GEMM shape [B*oh*ow, kh*kw*C] x [kh*kw*C, filters]):
+    // HBM-bound, whole K in shared memory, FFMA in fp32 (exact-mode accuracy, any alignment)
+    if (rb200::gemm_shortk_eligible(m, n, k, sAk, sBn) && (mode != RB200_GEMM_TF32 || !big ||
+        !rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC))) {
+        c.last_gemm_path = "simt_f32_shortk";
+        return rb200::gemm_shortk(m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
+    }
+    c.last_gemm_path = "simt_f32";
     return rb200::gemm_simt<float>(m, n, k, alpha, a, sAm, sAk, b, sBk, sBn, beta, cc, ldC);
 }
 

@@ -82,9 +82,124 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, T alpha,
     }
 }
 
+// ---- short-K kernel (K <= 64, NoTrans/NoTrans, float32): the conv-as-GEMM shape of BASELINE config C4
+// ([B*oh*ow, kh*kw*C] x [kh*kw*C, filters], K = 27, N = 64).  HBM-bound: the whole K extent of a
+// 128-row A tile and of a 64-column B tile sits in shared memory, each thread owns a 4 x 16 register
+// tile (64 FFMA per 4 scalar + 4 vector shared loads), k ascending as in the reference loop.
+constexpr int SK_BM = 128, SK_BN = 64, SK_THREADS = 128, SK_MAXK = 64;
+
+__global__ void __launch_bounds__(SK_THREADS)
+gemm_shortk_kernel(int64_t M, int N, int K, float alpha,
+                   const float* __restrict__ A, int64_t ldA,
+                   const float* __restrict__ B, int64_t ldB,
+                   float beta, float* __restrict__ C, int64_t ldC, unsigned k_magic)
+{
+    extern __shared__ __align__(16) float sk_smem[];
+    const int KS = K | 1;                                  // odd row pitch: conflict-free column reads
+    float* As = sk_smem;                                   // [SK_BM][KS]
+    float* Bs = sk_smem + ((SK_BM * KS + 3) & ~3);         // [K][SK_BN], 16-byte aligned
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * SK_BM;
+    const int n0 = blockIdx.y * SK_BN;
+    const int rows = (int)min((int64_t)SK_BM, M - m0);
+
+    for (int e = tid; e < K * SK_BN; e += SK_THREADS) {
+        const int kk = e / SK_BN, j = e - kk * SK_BN;
+        Bs[e] = (n0 + j < N) ? __ldg(B + (int64_t)kk * ldB + n0 + j) : 0.f;
+    }
+    const float* Ablk = A + m0 * ldA;
+    for (int e = tid; e < SK_BM * K; e += SK_THREADS) {
+        const int r = K == 1 ? e : (int)__umulhi((unsigned)e, k_magic);
+        const int kk = e - r * K;
+        As[r * KS + kk] = (r < rows) ? __ldcs(Ablk + (int64_t)r * ldA + kk) : 0.f;
+    }
+    __syncthreads();
+
+    const int rg = tid >> 2, cg = tid & 3;                 // 32 row groups x 4 column groups
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[i][j] = 0.f;
+    const float* arow = As + (rg * 4) * KS;
+    const float4* brow = reinterpret_cast<const float4*>(Bs) + cg * 4;
+    for (int kk = 0; kk < K; kk++) {
+        float a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = arow[i * KS + kk];
+        float bv[16];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const float4 t = brow[kk * (SK_BN / 4) + v];
+            bv[4 * v] = t.x; bv[4 * v + 1] = t.y; bv[4 * v + 2] = t.z; bv[4 * v + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    const bool vec_ok = ((ldC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (n0 + SK_BN <= N);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = rg * 4 + i;
+        if (r >= rows) continue;
+        float* crow = C + (m0 + r) * ldC + n0 + cg * 16;
+        if (vec_ok) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                float4 o;
+                o.x = alpha * acc[i][4 * v]; o.y = alpha * acc[i][4 * v + 1];
+                o.z = alpha * acc[i][4 * v + 2]; o.w = alpha * acc[i][4 * v + 3];
+                float4* dst = reinterpret_cast<float4*>(crow) + v;
+                if (beta != 0.f) {
+                    const float4 old = *dst;
+                    o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
+                    o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+                }
+                __stcs(dst, o);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (n0 + cg * 16 + j < N) {
+                    float o = alpha * acc[i][j];
+                    if (beta != 0.f) o = fmaf(beta, crow[j], o);
+                    crow[j] = o;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 namespace rb200 {
+
+bool gemm_shortk_eligible(int64_t M, int64_t N, int64_t K, int64_t sAk, int64_t sBn)
+{
+    return K >= 1 && K <= SK_MAXK && sAk == 1 && sBn == 1 && M >= 4 * SK_BM && N <= 0x7fffffffLL &&
+           rb_ceil_div(M, SK_BM) <= 0x7fffffffLL && rb_ceil_div(N, SK_BN) <= 65535;
+}
+
+int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
+                const float* B, int64_t ldB, float beta, float* C, int64_t ldC)
+{
+    Context& c = ctx();
+    const int KS = (int)K | 1;
+    const size_t smem = (size_t)(((SK_BM * KS + 3) & ~3) + (int)K * SK_BN) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        RB_CUDA(cudaFuncSetAttribute(gemm_shortk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
+    dim3 grid((unsigned)rb_ceil_div(M, SK_BM), (unsigned)rb_ceil_div(N, SK_BN));
+    const unsigned k_magic = (unsigned)((1ULL << 32) / (unsigned long long)K) + 1u;
+    gemm_shortk_kernel<<<grid, SK_THREADS, smem, c.stream>>>(M, (int)N, (int)K, alpha, A, ldA, B, ldB, beta, C, ldC,
+                                                            k_magic);
+    RB_LAUNCH_CHECK("gemm_shortk_kernel");
+    return RB200_OK;
+}
+
 
 template <typename T>
 int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk,

@@ -10,7 +10,8 @@
 //                       reads the top 19 bits).  Fastest; max error ~1e-3 of max|C|.
 //   RB200_GEMM_TF32X3 : A and B are first split into tf32 "hi" (cvt.rna) and "lo" (a - hi)
 //                       planes by a streaming pre-pass (split_tf32_kernel); the GEMM then
-//                       issues hi*lo + lo*hi + hi*hi into the same TMEM accumulator.
+//                       issues hi*hi into one TMEM accumulator and hi*lo + lo*hi into a second one
+//                       (summed in the epilogue).
 //                       ~fp32 accuracy (meets the reference's isclose bound, rtol 1e-4).
 //
 // Kernel anatomy (one persistent CTA per SM, 256 threads, warp-specialised):
@@ -182,7 +183,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, TcParams p)
 {
     using L = TcSmem<BN, PLANES, STAGES>;
-    constexpr int TMEM_COLS = 2 * BN;                         // two accumulators (256 or 512 columns)
+    // two accumulator stages.  3xTF32: each stage holds a "big" accumulator (hi*hi) and a separate
+    // "small" one (hi*lo + lo*hi), summed in the epilogue -- the TMEM adder truncates, and adding the
+    // 2^-12-sized cross terms into the big accumulator would triple the number of truncating adds.
+    constexpr int ACC_COLS = PLANES * BN;                     // columns per accumulator stage (256)
+    constexpr int TMEM_COLS = 2 * ACC_COLS;                   // 512
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + L::BARRIER_OFF;
@@ -263,7 +268,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -286,9 +291,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                                                        : make_smem_desc(sA + L::A_PLANE + aoff, 16, 1024, 2);
                             const uint64_t b_lo = B_MN ? make_smem_desc(sB + L::B_PLANE + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                                        : make_smem_desc(sB + L::B_PLANE + boff, 16, 1024, 2);
-                            tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, first);     // small terms first
-                            tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
-                            tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+                            tc_mma_tf32(tmem_d + BN, a_hi, b_lo, idesc, first);   // cross terms -> small accumulator
+                            tc_mma_tf32(tmem_d + BN, a_lo, b_hi, idesc, 1u);
+                            tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, first);        // hi*hi -> big accumulator
                         }
                     }
                     tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
@@ -314,9 +319,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ch++) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 32);
                 tc_ld_32x32b_x32(taddr, r);
-                tc_wait_ld();
+                if (PLANES == 2) {
+                    uint32_t rs[32];
+                    tc_ld_32x32b_x32(taddr + BN, rs);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rs[e]));
+                } else {
+                    tc_wait_ld();
+                }
                 const int64_t c0 = col0 + ch * 32;
                 if (row_ok && c0 < p.N) {
                     if (c0 + 32 <= p.N) {

@@ -155,24 +155,31 @@ im2col2d_forward_tiled(Im2colParams p, Im2colTile tl, const W* __restrict__ imag
         else { int q = r / C; c = r - q * C; ky = q / KW; kx = q - ky * KW; }
         lut[r] = ky * tl.row_elems + kx * (int)p.dilation_w * xs + (cf ? c * tl.width_x : c);
     }
-    // stage the source rows
+    // stage the source rows: per ky one contiguous run (channels-last) or `channels` runs (channels-first)
+    // of the image; the in-image part of each run is an index interval, so no division is needed.
     const int x_start = ox0 * (int)p.stride_w - (int)p.padding_w;
     const int y_start = oy * (int)p.stride_h - (int)p.padding_h;
     const W* img_b = images + (int64_t)b * p.batch_step;
-    const int total = KH * tl.row_elems;
-    for (int e = threadIdx.x; e < total; e += IC_THREADS) {
-        const int ky = e / tl.row_elems;
-        const int rem = e - ky * tl.row_elems;
-        int x, c;
-        if (cf) { c = ic_fastdiv(rem, tl.wx_magic, tl.width_x); x = rem - c * tl.width_x; }
-        else    { x = ic_fastdiv(rem, tl.chan_magic, C); c = rem - x * C; }
+    const int x_lo = max(0, -x_start);                                   // first staged column inside the image
+    const int x_hi = max(x_lo, min(tl.width_x, (int)p.im_w - x_start));  // one past the last
+    for (int ky = 0; ky < KH; ky++) {
         const int iy = y_start + ky * (int)p.dilation_h;
-        const int ix = x_start + x;
-        W v = (W)0;
-        if (iy >= 0 && iy < (int)p.im_h && ix >= 0 && ix < (int)p.im_w) {
-            v = __ldg(img_b + (int64_t)iy * p.im_h_step + (int64_t)ix * p.im_w_step + (int64_t)c * p.channel_step);
+        const bool row_ok = iy >= 0 && iy < (int)p.im_h;
+        W* trow = tile + ky * tl.row_elems;
+        if (!cf) {
+            const W* src = img_b + (int64_t)iy * p.im_h_step + (int64_t)x_start * C;
+            const int lo = x_lo * C, hi = x_hi * C;
+            for (int idx = threadIdx.x; idx < tl.row_elems; idx += IC_THREADS) {
+                trow[idx] = (row_ok && idx >= lo && idx < hi) ? __ldg(src + idx) : (W)0;
+            }
+        } else {
+            for (int c = 0; c < C; c++) {
+                const W* src = img_b + (int64_t)c * p.channel_step + (int64_t)iy * p.im_h_step + x_start;
+                for (int x = threadIdx.x; x < tl.width_x; x += IC_THREADS) {
+                    trow[c * tl.width_x + x] = (row_ok && x >= x_lo && x < x_hi) ? __ldg(src + x) : (W)0;
+                }
+            }
         }
-        tile[e] = v;
     }
     __syncthreads();
     W* out = cols + (((int64_t)b * p.out_h + oy) * p.out_w + ox0) * cell;

@@ -509,6 +509,22 @@ def test_gemm_tf32x3_long_k_accumulator_drift(cuda_service):
         assert rel.max() < 2e-3
 
 
+SHORTK = [(4096, 64, 27), (1000, 100, 5), (513, 7, 64), (70000, 64, 27), (2048, 130, 1), (640, 64, 33)]
+
+
+@pytest.mark.parametrize("mnk", SHORTK, ids=[str(s) for s in SHORTK])
+def test_gemm_shortk_conv_shapes(mnk, cuda_service):
+    """Tall matrix x short K (conv-as-GEMM): dedicated FFMA kernel, fp32 accuracy, any ld/offset."""
+    m, n, k = mnk
+    for mode in (rb.GEMM_AUTO, rb.GEMM_FP32_SIMT, rb.GEMM_TF32X3):
+        for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (0.5, 1.5, 3, 1), (1.0, 1.0, 4, 4)):
+            err, path = _gemm_case(cuda_service, mode, m, n, k, False, False, alpha, beta, off, off, off, ldx)
+            assert path == "simt_f32_shortk", path
+            assert err < 2e-6, (err, mnk, mode)
+    err, path = _gemm_case(cuda_service, rb.GEMM_AUTO, m, n, k, True, False, 1.0, 0.0)
+    assert path != "simt_f32_shortk" and err < 5e-5
+
+
 def test_gemm_unaligned_falls_back_to_simt(cuda_service):
     err, path = _gemm_case(cuda_service, rb.GEMM_TF32, 256, 256, 256, False, False, 1.0, 0.0, offA=1)
     assert path == "simt_f32" and err < 2e-6
