@@ -86,7 +86,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, T alpha,
 // ([B*oh*ow, kh*kw*C] x [kh*kw*C, filters], K = 27, N = 64).  HBM-bound: the whole K extent of a
 // 128-row A tile and of a 64-column B tile sits in shared memory, each thread owns a 4 x 16 register
 // tile (64 FFMA per 4 scalar + 4 vector shared loads), k ascending as in the reference loop.
-constexpr int SK_BM = 128, SK_BN = 64, SK_THREADS = 128, SK_MAXK = 64;
+constexpr int SK_BM = 128, SK_BN = 64, SK_THREADS = 128, SK_MAXK = 64, SK_MLP = 9;
 
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_shortk_kernel(int64_t M, int N, int K, float alpha,
@@ -103,15 +103,43 @@ gemm_shortk_kernel(int64_t M, int N, int K, float alpha,
     const int n0 = blockIdx.y * SK_BN;
     const int rows = (int)min((int64_t)SK_BM, M - m0);
 
-    for (int e = tid; e < K * SK_BN; e += SK_THREADS) {
-        const int kk = e / SK_BN, j = e - kk * SK_BN;
-        Bs[e] = (n0 + j < N) ? __ldg(B + (int64_t)kk * ldB + n0 + j) : 0.f;
+    for (int e0 = 0; e0 < K * SK_BN; e0 += SK_MLP * SK_THREADS) {
+        float v[SK_MLP];
+#pragma unroll
+        for (int u = 0; u < SK_MLP; u++) {
+            const int e = e0 + u * SK_THREADS + tid;
+            const int kk = e / SK_BN, j = e - kk * SK_BN;
+            v[u] = (e < K * SK_BN && n0 + j < N) ? __ldg(B + (int64_t)kk * ldB + n0 + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < SK_MLP; u++) {
+            const int e = e0 + u * SK_THREADS + tid;
+            if (e < K * SK_BN) Bs[e] = v[u];
+        }
     }
+    // A tile: SK_MLP independent loads in flight per thread before the first shared-memory store
     const float* Ablk = A + m0 * ldA;
-    for (int e = tid; e < SK_BM * K; e += SK_THREADS) {
-        const int r = K == 1 ? e : (int)__umulhi((unsigned)e, k_magic);
-        const int kk = e - r * K;
-        As[r * KS + kk] = (r < rows) ? __ldcs(Ablk + (int64_t)r * ldA + kk) : 0.f;
+    const int total = SK_BM * K;
+    for (int e0 = 0; e0 < total; e0 += SK_MLP * SK_THREADS) {
+        float v[SK_MLP];
+#pragma unroll
+        for (int u = 0; u < SK_MLP; u++) {
+            const int e = e0 + u * SK_THREADS + tid;
+            v[u] = 0.f;
+            if (e < total) {
+                const int r = K == 1 ? e : (int)__umulhi((unsigned)e, k_magic);
+                const int kk = e - r * K;
+                if (r < rows) v[u] = __ldcs(Ablk + (int64_t)r * ldA + kk);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SK_MLP; u++) {
+            const int e = e0 + u * SK_THREADS + tid;
+            if (e < total) {
+                const int r = K == 1 ? e : (int)__umulhi((unsigned)e, k_magic);
+                As[r * KS + (e - r * K)] = v[u];
+            }
+        }
     }
     __syncthreads();
 

@@ -35,6 +35,7 @@ struct Im2colParams {
 };
 
 constexpr int IC_THREADS = 256;
+constexpr int IC_MLP = 8;             // independent global loads in flight per thread while staging
 constexpr int IC_MAX_CELL = 4096;     // entries of the shared-memory tap table
 
 struct Tap { int delta; short dy, dx; };   // 8 bytes
@@ -111,19 +112,21 @@ im2col2d_forward(Im2colParams p, const W* __restrict__ images, W* __restrict__ c
 }
 
 
-// ---- forward, tiled: one CTA per (batch, out row, block of TOX out columns) ------------------------
-// The filter_h source rows that feed this block of cells are staged in shared memory with coalesced
-// loads (zero-filled outside the image, so the inner loop has no bounds test), then the block's
-// TOX*cell output elements -- one contiguous run of cols -- are produced with one table lookup
-// (tap -> smem offset), one shared-memory read and one coalesced global store each.  All index
-// arithmetic is 32-bit; t / cell is a multiply-high by a precomputed reciprocal.
+// ---- forward, tiled: one CTA per (batch, block of ROWS out rows, block of TOX out columns) --------------
+// The source rows that feed this block of cells are staged ONCE in shared memory with coalesced loads
+// (zero-filled outside the image, so the inner loop has no bounds test; consecutive out rows share
+// filter_h - stride_h of their source rows), then every out row of the block -- one contiguous run of
+// cols -- is produced by shared-memory gathers and 128-bit stores.  All index arithmetic is 32-bit;
+// divisions are multiply-highs by precomputed reciprocals.
 struct Im2colTile {
     int tox;            // out columns per CTA
+    int rows;           // out rows per CTA
+    int slabs;          // staged source rows: (rows-1)*stride_h + (filter_h-1)*dilation_h + 1
     int width_x;        // input columns staged per source row: (tox-1)*stride_w + (filter_w-1)*dilation_w + 1
-    int row_elems;      // elements per staged ky-slab: width_x * channels
+    int row_elems;      // elements per staged source row: width_x * channels
     unsigned cell_magic;   // floor(2^32 / cell) + 1
-    unsigned chan_magic;   // floor(2^32 / channels) + 1
     unsigned wx_magic;     // floor(2^32 / width_x) + 1
+    unsigned row_magic;    // floor(2^32 / row_elems) + 1
 };
 
 // t / d for t*d < 2^32 with magic = floor(2^32/d) + 1 (d == 1 has no 32-bit magic)
@@ -138,80 +141,126 @@ im2col2d_forward_tiled(Im2colParams p, Im2colTile tl, const W* __restrict__ imag
 {
     extern __shared__ __align__(16) unsigned char ic_smem_raw[];
     int* lut = reinterpret_cast<int*>(ic_smem_raw);                       // [cell] tap -> smem offset
-    W* tile = reinterpret_cast<W*>(ic_smem_raw + ((p.cell * 4 + 15) & ~15LL));   // [filter_h][row_elems]
+    W* tile = reinterpret_cast<W*>(ic_smem_raw + ((p.cell * 4 + 15) & ~15LL));   // [slabs][row_elems]
 
     const int cell = (int)p.cell;
     const int C = (int)p.channels, KW = (int)p.filter_w, KH = (int)p.filter_h;
     const int ox0 = blockIdx.x * tl.tox;
-    const int oy = blockIdx.y;
+    const int oy0 = blockIdx.y * tl.rows;
     const int b = blockIdx.z;
     const int tox = min(tl.tox, (int)p.out_w - ox0);
+    const int nrows = min(tl.rows, (int)p.out_h - oy0);
     const bool cf = p.channel_step != 1;                                 // channels_first images
-    // smem element (ky, x, c): channels-last ky*row_elems + x*C + c ; channels-first ky*row_elems + c*width_x + x
+    // smem element (slab s, x, c): channels-last s*row_elems + x*C + c ; channels-first s*row_elems + c*width_x + x
     const int xs = cf ? 1 : C;
+    const int dil_h = (int)p.dilation_h;
     for (int r = threadIdx.x; r < cell; r += IC_THREADS) {
         int ky, kx, c;
         if (p.cols_channels_first) { c = r / (KH * KW); int q = r - c * KH * KW; ky = q / KW; kx = q - ky * KW; }
         else { int q = r / C; c = r - q * C; ky = q / KW; kx = q - ky * KW; }
-        lut[r] = ky * tl.row_elems + kx * (int)p.dilation_w * xs + (cf ? c * tl.width_x : c);
+        lut[r] = ky * dil_h * tl.row_elems + kx * (int)p.dilation_w * xs + (cf ? c * tl.width_x : c);
     }
-    // stage the source rows: per ky one contiguous run (channels-last) or `channels` runs (channels-first)
-    // of the image; the in-image part of each run is an index interval, so no division is needed.
+    // stage the source rows: one flat index space; each thread issues up to IC_MLP independent global
+    // loads before the first shared-memory store, so the HBM/L2 latency is paid once per CTA.
     const int x_start = ox0 * (int)p.stride_w - (int)p.padding_w;
-    const int y_start = oy * (int)p.stride_h - (int)p.padding_h;
+    const int y_start = oy0 * (int)p.stride_h - (int)p.padding_h;
     const W* img_b = images + (int64_t)b * p.batch_step;
     const int x_lo = max(0, -x_start);                                   // first staged column inside the image
     const int x_hi = max(x_lo, min(tl.width_x, (int)p.im_w - x_start));  // one past the last
-    for (int ky = 0; ky < KH; ky++) {
-        const int iy = y_start + ky * (int)p.dilation_h;
-        const bool row_ok = iy >= 0 && iy < (int)p.im_h;
-        W* trow = tile + ky * tl.row_elems;
-        if (!cf) {
-            const W* src = img_b + (int64_t)iy * p.im_h_step + (int64_t)x_start * C;
-            const int lo = x_lo * C, hi = x_hi * C;
-            for (int idx = threadIdx.x; idx < tl.row_elems; idx += IC_THREADS) {
-                trow[idx] = (row_ok && idx >= lo && idx < hi) ? __ldg(src + idx) : (W)0;
-            }
-        } else {
-            for (int c = 0; c < C; c++) {
-                const W* src = img_b + (int64_t)c * p.channel_step + (int64_t)iy * p.im_h_step + x_start;
-                for (int x = threadIdx.x; x < tl.width_x; x += IC_THREADS) {
-                    trow[c * tl.width_x + x] = (row_ok && x >= x_lo && x < x_hi) ? __ldg(src + x) : (W)0;
+    const int slabs = min(tl.slabs, (nrows - 1) * (int)p.stride_h + (KH - 1) * dil_h + 1);
+    const int total = slabs * tl.row_elems;
+    const int im_h_step = (int)p.im_h_step, chan_step = (int)p.channel_step;
+    for (int e0 = 0; e0 < total; e0 += IC_MLP * IC_THREADS) {
+        W v[IC_MLP];
+#pragma unroll
+        for (int u = 0; u < IC_MLP; u++) {
+            const int e = e0 + u * IC_THREADS + (int)threadIdx.x;
+            v[u] = (W)0;
+            if (e < total) {
+                const int sl = ic_fastdiv(e, tl.row_magic, tl.row_elems);
+                const int idx = e - sl * tl.row_elems;
+                const int iy = y_start + sl;
+                int off;
+                bool ok = iy >= 0 && iy < (int)p.im_h;
+                if (!cf) {
+                    ok = ok && idx >= x_lo * C && idx < x_hi * C;
+                    off = iy * im_h_step + x_start * C + idx;
+                } else {
+                    const int c = ic_fastdiv(idx, tl.wx_magic, tl.width_x);
+                    const int x = idx - c * tl.width_x;
+                    ok = ok && x >= x_lo && x < x_hi;
+                    off = c * chan_step + iy * im_h_step + x_start + x;
                 }
+                if (ok) v[u] = __ldg(img_b + off);
             }
+        }
+#pragma unroll
+        for (int u = 0; u < IC_MLP; u++) {
+            const int e = e0 + u * IC_THREADS + (int)threadIdx.x;
+            if (e < total) tile[e] = v[u];
         }
     }
     __syncthreads();
-    W* out = cols + (((int64_t)b * p.out_h + oy) * p.out_w + ox0) * cell;
+
     const int n_out = tox * cell;
     const int sx = (int)p.stride_w * xs;
-    // 128-bit stores: scalar head up to the next 16-byte boundary, vector body, scalar tail
     constexpr int V = 16 / (int)sizeof(W);
-    const int mis = (int)((reinterpret_cast<uintptr_t>(out) / sizeof(W)) & (V - 1));
-    int head = (V - mis) & (V - 1);
-    if (head > n_out) head = n_out;
-    if ((int)threadIdx.x < head) {
-        const int t = threadIdx.x;
-        const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
-        out[t] = tile[lut[t - oxl * cell] + oxl * sx];
-    }
-    const int nvec = (n_out - head) / V;
-    for (int g = threadIdx.x; g < nvec; g += IC_THREADS) {
-        const int t = head + g * V;
-        int oxl = ic_fastdiv(t, tl.cell_magic, cell);
-        int r = t - oxl * cell;
-        int xoff = oxl * sx;
-        IcPack<W> pk;
-#pragma unroll
-        for (int e = 0; e < V; e++) {
-            pk.v[e] = tile[lut[r] + xoff];
-            if (++r == cell) { r = 0; xoff += sx; }
+    const int gangs = cell <= IC_THREADS ? IC_THREADS / cell : 0;
+    const int gang = ic_fastdiv((int)threadIdx.x, tl.cell_magic, cell);
+    const int tx = (int)threadIdx.x - gang * cell;
+    for (int rr = 0; rr < nrows; rr++) {
+        W* out = cols + (((int64_t)b * p.out_h + oy0 + rr) * p.out_w + ox0) * cell;
+        const W* trow = tile + rr * (int)p.stride_h * tl.row_elems;
+        // 128-bit stores: scalar head up to the next 16-byte boundary, vector body, scalar tail
+        const int mis = (int)((reinterpret_cast<uintptr_t>(out) / sizeof(W)) & (V - 1));
+        int head = (V - mis) & (V - 1);
+        if (head > n_out) head = n_out;
+        if ((int)threadIdx.x < head) {
+            const int t = threadIdx.x;
+            const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+            out[t] = trow[lut[t - oxl * cell] + oxl * sx];
         }
-        __stcs(reinterpret_cast<int4*>(out + t), pk.raw);
-    }
-    for (int t = head + nvec * V + threadIdx.x; t < n_out; t += IC_THREADS) {
-        const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
-        out[t] = tile[lut[t - oxl * cell] + oxl * sx];
+        const int nvec = (n_out - head) / V;
+        if (gangs > 0) {
+            // "Gangs" of `cell` threads: thread tx of a gang always handles vector group tx of a run of
+            // V cells (V*cell elements = cell vector groups), so the tap of each of its V elements --
+            // and hence its shared-memory offset -- is loop invariant; successive runs add V*sx.
+            if (gang < gangs) {
+                int off[V];
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    const int u = head + V * tx + e;
+                    const int ce = ic_fastdiv(u, tl.cell_magic, cell);
+                    off[e] = lut[u - ce * cell] + ce * sx;
+                }
+                const int step = V * sx;
+                for (int j = gang, q = tx + cell * gang; q < nvec; j += gangs, q += cell * gangs) {
+                    const int base = j * step;
+                    IcPack<W> pk;
+#pragma unroll
+                    for (int e = 0; e < V; e++) pk.v[e] = trow[off[e] + base];
+                    __stcs(reinterpret_cast<int4*>(out + head + V * q), pk.raw);
+                }
+            }
+        } else {
+            for (int g = threadIdx.x; g < nvec; g += IC_THREADS) {
+                const int t = head + g * V;
+                int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+                int r = t - oxl * cell;
+                int xoff = oxl * sx;
+                IcPack<W> pk;
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    pk.v[e] = trow[lut[r] + xoff];
+                    if (++r == cell) { r = 0; xoff += sx; }
+                }
+                __stcs(reinterpret_cast<int4*>(out + t), pk.raw);
+            }
+        }
+        for (int t = head + nvec * V + threadIdx.x; t < n_out; t += IC_THREADS) {
+            const int oxl = ic_fastdiv(t, tl.cell_magic, cell);
+            out[t] = trow[lut[t - oxl * cell] + oxl * sx];
+        }
     }
 }
 
@@ -268,33 +317,53 @@ int forward_launch(const Im2colParams& p, const void* images, void* cols)
     {
         const int64_t smem_budget = 48 * 1024 - 16;
         const int64_t lut_bytes = (p.cell * 4 + 15) & ~15LL;
-        const int64_t per_x = p.filter_h * p.channels * (int64_t)sizeof(W);      // bytes per staged input column
+        const int64_t es = (int64_t)sizeof(W);
         const int64_t base_x = (p.filter_w - 1) * p.dilation_w + 1;
-        int64_t max_wx = (smem_budget - lut_bytes) / (per_x > 0 ? per_x : 1);
+        const int64_t base_y = (p.filter_h - 1) * p.dilation_h + 1;
+        // widest column block whose filter_h-row working set fits: slabs(rows=1) * width_x * C * es
+        int64_t max_wx = (smem_budget - lut_bytes) / (base_y * p.channels * es);
         int64_t tox = max_wx >= base_x ? (max_wx - base_x) / p.stride_w + 1 : 0;
         if (tox > p.out_w) tox = p.out_w;
-        // keep >= ~4 CTAs per SM in flight for small images by splitting rows further
-        const int64_t ctas_full = p.batches * p.out_h;
-        if (tox > 64 && ctas_full * rb_ceil_div(p.out_w, tox) < (int64_t)c.sm_count * 4) {
-            const int64_t want = rb_ceil_div((int64_t)c.sm_count * 4, ctas_full);
-            int64_t t2 = rb_ceil_div(p.out_w, want);
-            if (t2 < 32) t2 = 32;
-            if (t2 < tox) tox = t2;
-        }
-        const bool small_idx = tox >= 1 && tox * p.cell * p.cell < (1LL << 32) && p.cell <= 65536 &&
-                               p.batches <= 65535 && p.out_h <= 65535 && p.im_h < (1LL << 30) && p.im_w < (1LL << 30) &&
-                               p.out_w * p.stride_w < (1LL << 30);
-        if (small_idx) {
+        const bool dims_ok = tox >= 1 && p.cell <= 65536 && p.batches <= 65535 && p.out_h <= 65535 &&
+                             p.im_h < (1LL << 30) && p.im_w < (1LL << 30) && p.out_w * p.stride_w < (1LL << 30) &&
+                             p.batch_step < (1LL << 31);
+        if (dims_ok) {
+            const int64_t width_x = (tox - 1) * p.stride_w + base_x;
+            const int64_t row_elems = width_x * p.channels;
+            // as many out rows per CTA as fit in shared memory (they share source rows), but keep
+            // >= 4 CTAs per SM in flight
+            int64_t rows = 1;
+            const int64_t col_blocks = rb_ceil_div(p.out_w, tox);
+            while (rows < 8 && rows < p.out_h) {
+                const int64_t r2 = rows + 1;
+                const int64_t slabs2 = (r2 - 1) * p.stride_h + base_y;
+                if (lut_bytes + slabs2 * row_elems * es > smem_budget) break;
+                if (p.batches * rb_ceil_div(p.out_h, r2) * col_blocks < (int64_t)c.sm_count * 8) break;
+                rows = r2;
+            }
+            // few CTAs (small images): split the rows into narrower column blocks instead
+            if (rows == 1 && tox > 64 && p.batches * p.out_h * col_blocks < (int64_t)c.sm_count * 4) {
+                const int64_t want = rb_ceil_div((int64_t)c.sm_count * 4, p.batches * p.out_h);
+                int64_t t2 = rb_ceil_div(p.out_w, want);
+                if (t2 < 32) t2 = 32;
+                if (t2 < tox) tox = t2;
+            }
             Im2colTile tl;
             tl.tox = (int)tox;
+            tl.rows = (int)rows;
+            tl.slabs = (int)((rows - 1) * p.stride_h + base_y);
             tl.width_x = (int)((tox - 1) * p.stride_w + base_x);
             tl.row_elems = tl.width_x * (int)p.channels;
             tl.cell_magic = magic_u32(p.cell);
-            tl.chan_magic = magic_u32(p.channels);
             tl.wx_magic = magic_u32(tl.width_x);
-            const int64_t smem = lut_bytes + p.filter_h * (int64_t)tl.row_elems * (int64_t)sizeof(W);
-            if (smem <= smem_budget + 16 && (int64_t)tl.row_elems * p.channels < (1LL << 31)) {
-                dim3 grid((unsigned)rb_ceil_div(p.out_w, tox), (unsigned)p.out_h, (unsigned)p.batches);
+            tl.row_magic = magic_u32(tl.row_elems);
+            const int64_t smem = lut_bytes + (int64_t)tl.slabs * tl.row_elems * es;
+            const bool magic_ok = tox * p.cell * p.cell < (1LL << 32) &&                       // t / cell
+                                  (int64_t)tl.slabs * tl.row_elems * tl.row_elems < (1LL << 32) &&   // e / row_elems
+                                  (int64_t)tl.row_elems * tl.width_x < (1LL << 32) &&          // idx / width_x
+                                  256LL * p.cell < (1LL << 32);
+            if (smem <= smem_budget + 16 && magic_ok) {
+                dim3 grid((unsigned)rb_ceil_div(p.out_w, tox), (unsigned)rb_ceil_div(p.out_h, rows), (unsigned)p.batches);
                 im2col2d_forward_tiled<W><<<grid, IC_THREADS, (size_t)smem, c.stream>>>(p, tl, im, co);
                 RB_LAUNCH_CHECK("im2col2d_forward_tiled");
                 return RB200_OK;
