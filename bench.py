@@ -36,6 +36,18 @@ METRIC = "sgemm TFLOP/s"
 UNIT = "TFLOP/s"
 
 
+# Only the JSON line may reach stdout: NCCL / CUDA libraries print banners to fd 1 from C, so fd 1 is
+# pointed at stderr for the whole run and the line is written to a saved copy of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -52,6 +64,16 @@ def measured_peaks():
         # fallback stated by /opt/skills/guides/B200_PROFILING.md
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
                 "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/traffic.json: "<kernel>@<n>" -> bytes); None when no capture exists for this kernel/size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("%s@%d" % (kernel, n))
+    except Exception:
+        return None
 
 
 def workload_config(n, world, mode_name):
@@ -193,7 +215,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -291,7 +313,7 @@ def run_b200(args):
     else:
         achieved_note = "algorithmic flops 2*N^3"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": None,
+                "frac": achieved / tf32_peak, "traffic": ncu_traffic(gemm_path, n),
                 "kernel": gemm_path,
                 "peak_note": "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); %s"
                              % (peaks["source"], achieved_note)}
@@ -387,6 +409,7 @@ def run_b200(args):
         except Exception:
             pass
 
+    log("rank %d/%d: %.2f ms/step, %.1f TFLOP/s aggregate" % (rank, world, ms_per_step, value))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -399,7 +422,7 @@ def run_b200(args):
             "clocks": sampler.summary(), "gemm_modes": gemm_modes, "hbm_ops": hbm_ops, "with_gather": with_gather,
             "peaks": peaks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -499,7 +522,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8192, help="sgemm size per GPU (M=N=K)")
+    ap.add_argument("--size", dest="n", type=int, default=8192, help="sgemm size per GPU (M=N=K)")
     ap.add_argument("--mode", default="tf32", choices=["tf32", "tf32x3", "fp32_simt"])
     ap.add_argument("--quick", action="store_true", help="headline workload only (no hbm_ops / other modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
