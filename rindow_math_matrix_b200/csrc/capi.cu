@@ -41,6 +41,25 @@ int ensure_workspace(size_t bytes)
     return RB200_OK;
 }
 
+int ensure_counters(int64_t n, int** out)
+{
+    Context& c = ctx();
+    if ((size_t)n > c.counters_len) {
+        if (c.counters) {
+            RB_CUDA(cudaStreamSynchronize(c.stream));
+            RB_CUDA(cudaFree(c.counters));
+            c.counters = nullptr;
+            c.counters_len = 0;
+        }
+        size_t want = (size_t)n < 16384 ? 16384 : (size_t)n;
+        RB_CUDA(cudaMalloc(&c.counters, want * sizeof(int)));
+        RB_CUDA(cudaMemsetAsync(c.counters, 0, want * sizeof(int), c.stream));
+        c.counters_len = want;
+    }
+    *out = c.counters;
+    return RB200_OK;
+}
+
 }  // namespace rb200
 
 using rb200::ctx;
@@ -102,6 +121,9 @@ int rb200_shutdown(void)
     if (c.workspace) cudaFree(c.workspace);
     c.workspace = nullptr;
     c.workspace_bytes = 0;
+    if (c.counters) cudaFree(c.counters);
+    c.counters = nullptr;
+    c.counters_len = 0;
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     c.own_stream = nullptr;
     c.stream = nullptr;

@@ -24,12 +24,16 @@ struct Context {
     // scratch for two-pass reductions / split-K (grown on demand, stream ordered)
     void*       workspace = nullptr;
     size_t      workspace_bytes = 0;
+    // self-resetting arrival tickets of the split reductions (zero between launches)
+    int*        counters = nullptr;
+    size_t      counters_len = 0;
 };
 
 Context& ctx();
 void set_error(const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int  ensure_workspace(size_t bytes);
+int  ensure_counters(int64_t n, int** out);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
 

@@ -13,6 +13,9 @@ int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm,
 bool gemm_shortk_eligible(int64_t M, int64_t N, int64_t K, int64_t sAk, int64_t sBn);
 int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
                 const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
+bool gemm_tcgen05_skinny_eligible(int mode, int64_t M, int64_t N, int64_t K);
+int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
+                        const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
 bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
                            const float* B, int64_t ldB, const float* C, int64_t ldC);
 int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
@@ -65,21 +68,23 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     const float* a = A + offA;
     const float* b = B + offB;
     float* cc = C + offC;
-    // The tensor-core path pays off from one full 128 x 128 tile upwards; the known-answer
-    // sized problems (3x3 ... 64x64) and anything TMA cannot address run on the FFMA path.
-    const bool big = (m >= 128 && n >= 128 && k >= 32);
-    const bool shortk_first = (k <= 64) && !tA && !tB && (mode != RB200_GEMM_TF32) &&
-                              rb200::gemm_shortk_eligible(m, n, k, 1, 1);
-    if (!shortk_first && mode != RB200_GEMM_FP32_SIMT && big &&
-        rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC)) {
-        return rb200::gemm_tcgen05(mode, tA, tB, m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
-    }
     const int64_t sAm = tA ? 1 : ldA, sAk = tA ? ldA : 1;
     const int64_t sBk = tB ? 1 : ldB, sBn = tB ? ldB : 1;
-    // tall matrix with a short K (the conv-as-GEMM shape [B*oh*ow, kh*kw*C] x [kh*kw*C, filters]):
-    // HBM-bound, whole K in shared memory, FFMA in fp32 (exact-mode accuracy, any alignment)
-    if (rb200::gemm_shortk_eligible(m, n, k, sAk, sBn) && (mode != RB200_GEMM_TF32 || !big ||
-        !rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC))) {
+    if (mode != RB200_GEMM_FP32_SIMT) {
+        // The TMA-fed path pays off from one full 128 x 128 tile upwards; the known-answer sized
+        // problems (3x3 ... 64x64) and anything TMA cannot address run elsewhere.
+        const bool big = (m >= 128 && n >= 128 && k >= 32);
+        if (big && rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC)) {
+            return rb200::gemm_tcgen05(mode, tA, tB, m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
+        }
+        // tall-and-skinny NoTrans products (conv-as-GEMM: [B*oh*ow, kh*kw*C] x [kh*kw*C, filters]) of any
+        // alignment: tensor cores fed by software-swizzled staging
+        if (!tA && !tB && rb200::gemm_tcgen05_skinny_eligible(mode, m, n, k)) {
+            return rb200::gemm_tcgen05_skinny(mode, m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
+        }
+    }
+    // FFMA paths (exact fp32): short-K kernel for tall NoTrans shapes, generic tiled kernel otherwise
+    if (rb200::gemm_shortk_eligible(m, n, k, sAk, sBn)) {
         c.last_gemm_path = "simt_f32_shortk";
         return rb200::gemm_shortk(m, n, k, alpha, a, ldA, b, ldB, beta, cc, ldC);
     }

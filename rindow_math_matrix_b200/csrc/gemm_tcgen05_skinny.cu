@@ -1,0 +1,491 @@
+// gemm_tcgen05_skinny.cu -- tall-and-skinny float32 GEMM on tcgen05 for operands TMA cannot address:
+// C[M,N] = alpha * A[M,K] * B[K,N] (+ beta*C), NoTrans/NoTrans, M large, N <= 128, K <= 128, ANY leading
+// dimension / alignment.  This is the conv-as-GEMM shape of BASELINE config C4 -- cols [B*oh*ow, 27]
+// x W [27, 64] -- whose row pitch (27 floats) rules out TMA.  The op is HBM-bound (AI ~ 9.5 flop/B),
+// so the point of the tensor core here is to take the arithmetic off the FFMA pipe, not peak flops.
+//
+// Same reference semantics as gemm_tcgen05.cu (PhpBlas::gemm, PhpBlas.php:927-947), same two modes:
+//   1 plane : operands rounded to tf32 with cvt.rna while staging (unbiased, unlike the raw-fp32
+//             truncation of the TMA path)
+//   2 planes: hi = rna(x), lo = x - hi computed in registers while staging (no pre-pass); hi*hi goes to
+//             a "big" TMEM accumulator, hi*lo + lo*hi to a "small" one, summed in the epilogue.
+//
+// Persistent CTA per SM, 416 threads:
+//   warps 0-3 : producers -- coalesced global loads of the A tile (128 rows x 32 k), software 128-byte
+//               swizzle into the K-major UMMA layout, fence.proxy.async, mbarrier arrive (2 stages)
+//   warp  4   : MMA issuer (one lane): tcgen05.mma M=128, N=NP, K=8; commits free A stages / publish TMEM
+//   warps 5-12: epilogue, two groups of four (group g drains accumulator stage g, tiles alternate) --
+//               tcgen05.ld -> registers -> shared-memory transpose -> coalesced 128-bit stores
+// B (K x N, tiny) is staged once per CTA, transposed to K-major, all k-blocks resident.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SKT_BM = 128;
+constexpr int SKT_BK = 32;
+constexpr int SKT_THREADS = 416;                     // 4 producer + 1 MMA + 2 x 4 epilogue warps
+constexpr int SKT_PRODUCERS = 128;
+constexpr int SKT_A_TILE = SKT_BM * SKT_BK * 4;      // 16 KB per plane per stage
+constexpr int SKT_STAGES = 2;
+constexpr int SKT_PREFETCH = 3;                      // raw A tiles in flight ahead of the one being staged
+constexpr int SKT_RAW_SLOTS = SKT_PREFETCH + 1;
+constexpr int SKT_RAW_STAGE = SKT_BM * SKT_BK * 4;   // 16 KB
+constexpr int SKT_SMEM_LIMIT = 226 * 1024;
+
+__device__ __forceinline__ uint32_t sk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void sk_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sk_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sk_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sk_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void sk_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void sk_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzled tile: byte offset of element (row r, column kk < 32)
+__device__ __forceinline__ uint32_t sk_swz(int r, int kk)
+{
+    return (uint32_t)(r * 128 + ((((kk >> 2) ^ (r & 7)) << 4) | ((kk & 3) << 2)));
+}
+__device__ __forceinline__ uint64_t sk_desc(uint32_t smem_addr)          // K-major SW128: SBO = 1024
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ float sk_rna(float x)
+{
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+    return __uint_as_float(t);
+}
+
+struct SktParams {
+    int64_t M;
+    int N, K, NP, KB;              // NP = N rounded up to 32, KB = ceil(K / 32)
+    float alpha, beta;
+    const float* A; int64_t ldA;
+    const float* B; int64_t ldB;
+    float* C; int64_t ldC;
+    int num_tiles;
+    int a_contig;                  // ldA == K and A 16-byte aligned: the 128-row tile is one contiguous block
+    unsigned k_magic;              // floor(2^32 / K) + 1
+    uint32_t tmem_cols;
+    int epi_groups;                // 1 or 2 groups of four epilogue warps (2 when the staging fits)
+    int raw_slots;                 // slots of the raw cp.async ring (0 when the tile is not contiguous)
+};
+
+template <int PLANES>
+__global__ void __launch_bounds__(SKT_THREADS, 1)
+gemm_tf32_skinny_kernel(SktParams p)
+{
+    extern __shared__ uint8_t skt_raw[];
+    const uint32_t base = (sk_smem_u32(skt_raw) + 1023u) & ~1023u;
+    uint8_t* gen = skt_raw + (base - sk_smem_u32(skt_raw));
+    // layout: A stages | B planes | epilogue staging | barriers
+    const uint32_t a_stage_bytes = PLANES * SKT_A_TILE;
+    const uint32_t b_plane_bytes = (uint32_t)p.KB * p.NP * 128;
+    const uint32_t off_b = SKT_STAGES * a_stage_bytes;
+    const uint32_t off_epi = off_b + PLANES * b_plane_bytes;
+    const int epi_pitch = p.NP + 4;                                  // floats; keeps rows 16-byte aligned
+    const uint32_t off_raw = off_epi + (uint32_t)p.epi_groups * 4u * 32u * epi_pitch * 4u;   // 16-byte aligned
+    const uint32_t off_bar = off_raw + (uint32_t)p.raw_slots * SKT_RAW_STAGE;
+    const uint32_t bar = base + ((off_bar + 7u) & ~7u);
+    auto a_full  = [&](int s) { return bar + 8u * s; };
+    auto a_empty = [&](int s) { return bar + 8u * (SKT_STAGES + s); };
+    auto t_full  = [&](int a) { return bar + 8u * (2 * SKT_STAGES + a); };
+    auto t_empty = [&](int a) { return bar + 8u * (2 * SKT_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar + 8u * (2 * SKT_STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ACC_COLS = PLANES * p.NP;
+
+    if (warp == 4 && lane == 0) {
+        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), 4); sk_mbar_init(a_empty(s), 1); }
+        for (int a = 0; a < 2; a++) { sk_mbar_init(t_full(a), 1); sk_mbar_init(t_empty(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // zero the A stages once: columns K..32*KB-1 of the last k-block and rows past M stay zero forever
+    for (uint32_t o = threadIdx.x * 16u; o < SKT_STAGES * a_stage_bytes; o += SKT_THREADS * 16u) {
+        *reinterpret_cast<float4*>(gen + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // stage B once: global [K][N] (row pitch ldB) -> K-major [kb][n][32 k] swizzled, tf32 hi (and lo) planes
+    for (int e = threadIdx.x; e < p.KB * 32 * p.NP; e += SKT_THREADS) {
+        const int k = e / p.NP, n = e - k * p.NP;
+        float v = 0.f;
+        if (k < p.K && n < p.N) v = __ldg(p.B + (int64_t)k * p.ldB + n);
+        const float hi = sk_rna(v);
+        const uint32_t o = off_b + (uint32_t)(k >> 5) * (uint32_t)(p.NP * 128) + sk_swz(n, k & 31);
+        *reinterpret_cast<float*>(gen + o) = hi;
+        if (PLANES == 2) *reinterpret_cast<float*>(gen + o + b_plane_bytes) = v - hi;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    sk_fence_before();
+    __syncthreads();
+    sk_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp < 4) {
+        // ===== producers =====
+        const int t = threadIdx.x;                                    // 0..127
+        int stage = 0; uint32_t phase = 0;
+        if (p.a_contig && p.KB == 1) {
+            // Each 128-row tile is rows*K contiguous floats.  They are brought into a raw shared-memory
+            // ring with 16-byte cp.async copies issued SKT_PREFETCH tiles ahead (each thread later reads
+            // back exactly the chunks it copied, so cp.async.wait_group is the only synchronisation), then
+            // swizzled / split into the UMMA tiles.  Depth 3 keeps ~40 KB of reads in flight per SM.
+            constexpr int MAXV = (SKT_BM * SKT_BK / 4) / SKT_PRODUCERS;        // 8 chunks of 16 bytes per thread
+            uint8_t* raw = gen + off_raw;
+            auto issue = [&](int tile, int slot) {
+                if (tile < p.num_tiles) {
+                    const int64_t m0 = (int64_t)tile * SKT_BM;
+                    const int rows = (int)min((int64_t)SKT_BM, p.M - m0);
+                    const int nvec = (rows * p.K) >> 2;
+                    const float4* src = reinterpret_cast<const float4*>(p.A + m0 * p.ldA);
+#pragma unroll
+                    for (int i = 0; i < MAXV; i++) {
+                        const int q = t + i * SKT_PRODUCERS;
+                        if (q < nvec) {
+                            const uint32_t dst = base + off_raw + (uint32_t)slot * SKT_RAW_STAGE + (uint32_t)q * 16u;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + q) : "memory");
+                        }
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            const int step = gridDim.x;
+            int slot_in = 0;
+#pragma unroll
+            for (int d = 0; d < SKT_PREFETCH; d++) { issue(blockIdx.x + d * step, slot_in); slot_in = (slot_in + 1) % SKT_RAW_SLOTS; }
+            int slot_out = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += step) {
+                issue(tile + SKT_PREFETCH * step, slot_in);
+                slot_in = (slot_in + 1) % SKT_RAW_SLOTS;
+                asm volatile("cp.async.wait_group %0;" :: "n"(SKT_PREFETCH) : "memory");
+                const int64_t m0 = (int64_t)tile * SKT_BM;
+                const int rows = (int)min((int64_t)SKT_BM, p.M - m0);
+                const int nelem = rows * p.K, nvec = nelem >> 2;
+                sk_mbar_wait(a_empty(stage), phase ^ 1);
+                uint8_t* sa = gen + stage * a_stage_bytes;
+                const float4* rbuf = reinterpret_cast<const float4*>(raw + slot_out * SKT_RAW_STAGE);
+#pragma unroll
+                for (int i = 0; i < MAXV; i++) {
+                    const int q = t + i * SKT_PRODUCERS;
+                    if (q < nvec) {
+                        const float4 v4 = rbuf[q];
+                        const float vals[4] = {v4.x, v4.y, v4.z, v4.w};
+                        const int e = q * 4;
+                        int r = p.K == 1 ? e : (int)__umulhi((unsigned)e, p.k_magic);
+                        int kk = e - r * p.K;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float hi = sk_rna(vals[j]);
+                            const uint32_t o = sk_swz(r, kk);
+                            *reinterpret_cast<float*>(sa + o) = hi;
+                            if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = vals[j] - hi;
+                            if (++kk == p.K) { kk = 0; r++; }
+                        }
+                    }
+                }
+                for (int e = (nvec << 2) + t; e < nelem; e += SKT_PRODUCERS) {         // <= 3 leftover elements
+                    const int r = p.K == 1 ? e : (int)__umulhi((unsigned)e, p.k_magic);
+                    const int kk = e - r * p.K;
+                    const float x = __ldcs(p.A + m0 * p.ldA + e);
+                    const float hi = sk_rna(x);
+                    *reinterpret_cast<float*>(sa + sk_swz(r, kk)) = hi;
+                    if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + sk_swz(r, kk)) = x - hi;
+                }
+                // rows past M of a partial last tile: zero them (an earlier full tile left data there)
+                for (int e = rows * 32 + t; e < SKT_BM * 32; e += SKT_PRODUCERS) {
+                    const uint32_t o = sk_swz(e >> 5, e & 31);
+                    *reinterpret_cast<float*>(sa + o) = 0.f;
+                    if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = 0.f;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(a_full(stage));
+                if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
+                slot_out = (slot_out + 1) % SKT_RAW_SLOTS;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            // generic: a warp reads one row's 32 k (coalesced 128 bytes), 8 rows in flight per thread
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int64_t m0 = (int64_t)tile * SKT_BM;
+                const int rows = (int)min((int64_t)SKT_BM, p.M - m0);
+                for (int kb = 0; kb < p.KB; kb++) {
+                    sk_mbar_wait(a_empty(stage), phase ^ 1);
+                    uint8_t* sa = gen + stage * a_stage_bytes;
+                    const int kk = t & 31;
+                    const int k = kb * 32 + kk;
+                    const float* col = p.A + m0 * p.ldA + k;
+                    for (int r0 = t >> 5; r0 < SKT_BM; r0 += 32) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int r = r0 + 4 * i;
+                            v[i] = (r < rows && k < p.K) ? __ldcs(col + (int64_t)r * p.ldA) : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int r = r0 + 4 * i;
+                            const float hi = sk_rna(v[i]);
+                            const uint32_t o = sk_swz(r, kk);
+                            *reinterpret_cast<float*>(sa + o) = hi;
+                            if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v[i] - hi;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) sk_mbar_arrive(a_full(stage));
+                    if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                sk_mbar_wait(t_empty(acc), acc_phase ^ 1);
+                sk_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int kb = 0; kb < p.KB; kb++) {
+                    sk_mbar_wait(a_full(stage), phase);
+                    sk_fence_after();
+                    const uint32_t sA = base + stage * a_stage_bytes;
+                    const uint32_t sB = base + off_b + (uint32_t)kb * (uint32_t)(p.NP * 128);
+#pragma unroll
+                    for (int kk = 0; kk < SKT_BK / 8; kk++) {
+                        const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                        const uint64_t a_hi = sk_desc(sA + kk * 32), b_hi = sk_desc(sB + kk * 32);
+                        if (PLANES == 1) {
+                            sk_mma(tmem_d, a_hi, b_hi, idesc, first);
+                        } else {
+                            const uint64_t a_lo = sk_desc(sA + SKT_A_TILE + kk * 32);
+                            const uint64_t b_lo = sk_desc(sB + b_plane_bytes + kk * 32);
+                            sk_mma(tmem_d + p.NP, a_hi, b_lo, idesc, first);
+                            sk_mma(tmem_d + p.NP, a_lo, b_hi, idesc, 1u);
+                            sk_mma(tmem_d, a_hi, b_hi, idesc, first);
+                        }
+                    }
+                    sk_commit(a_empty(stage));
+                    if (kb == p.KB - 1) sk_commit(t_full(acc));
+                    if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles alternate) =====
+        const int g = (warp - 5) >> 2;
+        if (g < p.epi_groups) {
+            const int q = warp & 3;                                   // TMEM lane quarter of this warp
+            float* ebuf = reinterpret_cast<float*>(gen + off_epi) + (warp - 5) * 32 * epi_pitch;
+            const int nv = p.NP >> 2;                                 // float4 per row
+            const bool c_vec = ((p.ldC & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+            // lane -> (row, 16-byte piece) map of the transposed store; loop invariant when nv divides 32
+            const bool inv = (32 % nv) == 0;
+            const int rstep = inv ? 32 / nv : 0;
+            const int lr = inv ? lane / nv : 0, lc4 = inv ? lane - (lane / nv) * nv : 0;
+            uint32_t acc_phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                if (p.epi_groups == 2 && acc != g) continue;
+                const int64_t row0 = (int64_t)tile * SKT_BM + q * 32;
+                sk_mbar_wait(t_full(acc), acc_phase);
+                // with one group both stages are drained by it (phase flips every second tile); with two
+                // groups each group sees only its own stage (phase flips every visit)
+                if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
+                sk_fence_after();
+                for (int ch = 0; ch < p.NP / 16; ch++) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 16);
+                    sk_ld16(taddr, r);
+                    if (PLANES == 2) {
+                        uint32_t rs[16];
+                        sk_ld16(taddr + p.NP, rs);
+                        sk_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rs[e]));
+                    } else {
+                        sk_wait_ld();
+                    }
+                    float4* dst = reinterpret_cast<float4*>(ebuf + lane * epi_pitch + ch * 16);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        dst[v] = make_float4(p.alpha * __uint_as_float(r[4 * v]), p.alpha * __uint_as_float(r[4 * v + 1]),
+                                             p.alpha * __uint_as_float(r[4 * v + 2]), p.alpha * __uint_as_float(r[4 * v + 3]));
+                    }
+                }
+                // all TMEM reads of this accumulator are done: hand it back before the global stores
+                sk_fence_before();
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(t_empty(acc));
+                // transpose out of shared memory: consecutive lanes -> consecutive 16-byte pieces of a C row
+                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && row0 + 32 <= p.M) {
+                    // fast path: full tile, no beta -- 4 independent LDS.128 / STG.128 pairs per step
+                    float* cbase = p.C + (row0 + lr) * p.ldC + lc4 * 4;
+                    const float* sbase = ebuf + lr * epi_pitch + lc4 * 4;
+                    const int steps = nv;                             // 32 rows / rstep rows per step
+                    for (int s0 = 0; s0 < steps; s0 += 4) {
+                        float4 o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (s0 + u < steps) o[u] = *reinterpret_cast<const float4*>(sbase + (s0 + u) * rstep * epi_pitch);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (s0 + u < steps) __stcs(reinterpret_cast<float4*>(cbase + (int64_t)(s0 + u) * rstep * p.ldC), o[u]);
+                        }
+                    }
+                } else {
+                    for (int idx = lane; idx < 32 * nv; idx += 32) {
+                        const int rr = idx / nv, c4 = idx - rr * nv;
+                        const int64_t grow = row0 + rr;
+                        const int col = c4 * 4;
+                        if (grow < p.M && col < p.N) {
+                            float4 o = *reinterpret_cast<const float4*>(ebuf + rr * epi_pitch + col);
+                            float* cp = p.C + grow * p.ldC + col;
+                            if (c_vec && col + 4 <= p.N) {
+                                if (p.beta != 0.f) {
+                                    const float4 old = *reinterpret_cast<const float4*>(cp);
+                                    o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
+                                    o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+                                }
+                                __stcs(reinterpret_cast<float4*>(cp), o);
+                            } else {
+                                const float vals[4] = {o.x, o.y, o.z, o.w};
+                                for (int j = 0; j < 4 && col + j < p.N; j++) {
+                                    cp[j] = p.beta != 0.f ? fmaf(p.beta, cp[j], vals[j]) : vals[j];
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                         // ebuf is reused by the next tile
+            }
+        }
+    }
+
+    sk_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        sk_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+size_t skt_smem_bytes(int planes, int NP, int KB, int epi_groups, int raw_slots)
+{
+    size_t a = (size_t)SKT_STAGES * planes * SKT_A_TILE;
+    size_t b = (size_t)planes * KB * NP * 128;
+    size_t e = (size_t)epi_groups * 4 * 32 * (NP + 4) * 4;
+    return a + b + e + (size_t)raw_slots * SKT_RAW_STAGE + 256 + 1024;
+}
+
+}  // namespace
+
+namespace rb200 {
+
+bool gemm_tcgen05_skinny_eligible(int mode, int64_t M, int64_t N, int64_t K)
+{
+    if (mode != RB200_GEMM_TF32 && mode != RB200_GEMM_TF32X3) return false;
+    if (M < 2048 || N < 1 || N > 128 || K < 1 || K > 128) return false;
+    const int planes = mode == RB200_GEMM_TF32X3 ? 2 : 1;
+    const int NP = (int)((N + 31) / 32 * 32), KB = (int)((K + 31) / 32);
+    if (rb_ceil_div(M, SKT_BM) > 0x7fffffffLL) return false;
+    return skt_smem_bytes(planes, NP, KB, 1, 0) <= SKT_SMEM_LIMIT;
+}
+
+int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
+                        const float* B, int64_t ldB, float beta, float* C, int64_t ldC)
+{
+    Context& c = ctx();
+    const int planes = mode == RB200_GEMM_TF32X3 ? 2 : 1;
+    SktParams p;
+    p.M = M; p.N = (int)N; p.K = (int)K;
+    p.NP = (int)((N + 31) / 32 * 32);
+    p.KB = (int)((K + 31) / 32);
+    p.alpha = alpha; p.beta = beta;
+    p.A = A; p.ldA = ldA; p.B = B; p.ldB = ldB; p.C = C; p.ldC = ldC;
+    p.num_tiles = (int)rb_ceil_div(M, SKT_BM);
+    p.a_contig = (ldA == K) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((SKT_BM * K) % 4 == 0);
+    p.k_magic = (unsigned)((1ULL << 32) / (unsigned long long)K) + 1u;
+    uint32_t cols = (uint32_t)(2 * planes * p.NP), pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    p.tmem_cols = pow2;
+    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, 0) <= SKT_SMEM_LIMIT ? 2 : 1;
+    p.raw_slots = 0;
+    if (p.a_contig && p.KB == 1) {
+        // the contiguous-tile fast path needs the raw ring; give up the second epilogue group before it
+        if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) p.epi_groups = 1;
+        if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT) p.raw_slots = SKT_RAW_SLOTS;
+        else p.a_contig = 0;
+    }
+    const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, p.raw_slots);
+    static bool configured[3] = {false, false, false};
+    if (!configured[planes]) {
+        if (planes == 1) RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        else             RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        configured[planes] = true;
+    }
+    const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
+    if (planes == 1) gemm_tf32_skinny_kernel<1><<<grid, SKT_THREADS, smem, c.stream>>>(p);
+    else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p);
+    RB_LAUNCH_CHECK("gemm_tf32_skinny_kernel");
+    c.last_gemm_path = planes == 1 ? "tcgen05_tf32_skinny" : "tcgen05_tf32x3_skinny";
+    return RB200_OK;
+}
+
+}  // namespace rb200

@@ -11,11 +11,12 @@
 //
 // Kernel families (all warp-shuffle + shared-memory tree; 128-bit loads when aligned):
 //   k == 1, n <= 4096 : one warp per row            (reduce_rows_warp)
-//   k == 1, long rows : one CTA per (row, segment)  (reduce_rows_block) + partial merge
+//   k == 1, long rows : one CTA per (row, segment)  (reduce_rows_block)
 //   k  > 1            : threads along k, CTA tile TX x TY over (k, n), optional split of n
-//                       (reduce_cols) + partial merge
-// Two-pass splits keep every SM busy when m*k alone is too small to fill 148 SMs
-// (e.g. axis=0 of [65536,1024], or 64 rows of 1e6).
+//                       (reduce_cols)
+// Splitting the reduced axis keeps every SM busy when m*k alone is too small to fill 148 SMs
+// (e.g. axis=0 of [65536,1024], or 64 rows of 1e6); the last CTA of an output to finish (atomic
+// ticket) merges the partials in a fixed order inside the same launch.
 #include <float.h>
 #include <limits.h>
 
@@ -98,6 +99,16 @@ template <typename Op> __device__ __forceinline__ typename Op::Acc block_reduce(
     return a;
 }
 
+// partial accumulators written by other CTAs: read through L2 (volatile), never from a stale L1 line
+template <typename Op> __device__ __forceinline__ typename Op::Acc ld_acc(const typename Op::Acc* p)
+{
+    typename Op::Acc a;
+    if (sizeof(a) == 4)      { const int v  = __ldcg(reinterpret_cast<const int*>(p));  memcpy(&a, &v, 4); }
+    else if (sizeof(a) == 8) { const int2 v = __ldcg(reinterpret_cast<const int2*>(p)); memcpy(&a, &v, 8); }
+    else                     { const int4 v = __ldcg(reinterpret_cast<const int4*>(p)); memcpy(&a, &v, 16); }
+    return a;
+}
+
 template <typename T> struct RdVec { static constexpr int N = 16 / sizeof(T); };
 template <typename T> union RdPack { int4 raw; T v[16 / sizeof(T)]; };
 
@@ -156,11 +167,15 @@ reduce_rows_warp(int64_t m, int64_t n, const T* __restrict__ A, void* __restrict
 }
 
 // ---- k == 1: one CTA per (row, segment) --------------------------------------------------------
+// With S > 1 segments per row each CTA publishes its partial, and the LAST CTA of a row to finish
+// (atomic ticket; the counter resets itself) merges the S partials in a fixed order -- one launch,
+// deterministic result.
 template <typename T, typename Op, bool VEC>
 __global__ void __launch_bounds__(RD_THREADS)
 reduce_rows_block(int64_t m, int64_t n, int S, int64_t seglen, const T* __restrict__ A,
-                  void* __restrict__ B, int64_t offB, int idx64, typename Op::Acc* __restrict__ partial)
+                  void* __restrict__ B, int64_t offB, int idx64, typename Op::Acc* partial, int* counters)
 {
+    __shared__ int is_last;
     const int seg = blockIdx.x;
     for (int64_t row = blockIdx.y; row < m; row += gridDim.y) {
         const int64_t begin = (int64_t)seg * seglen;
@@ -169,26 +184,27 @@ reduce_rows_block(int64_t m, int64_t n, int S, int64_t seglen, const T* __restri
         typename Op::Acc acc = Op::identity();
         if (begin < end) accum_run<T, Op, VEC>(acc, A + row * n, begin, end, threadIdx.x, RD_THREADS);
         acc = block_reduce<Op>(acc);
-        if (threadIdx.x == 0) {
-            if (S == 1) Op::store(B, offB + row, acc, idx64);
-            else        partial[row * S + seg] = acc;
+        if (S == 1) {
+            if (threadIdx.x == 0) Op::store(B, offB + row, acc, idx64);
+        } else {
+            if (threadIdx.x == 0) {
+                partial[row * S + seg] = acc;
+                __threadfence();
+                const int ticket = atomicAdd(&counters[row], 1);
+                is_last = (ticket == S - 1);
+                if (is_last) counters[row] = 0;
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                typename Op::Acc a2 = Op::identity();
+                for (int s2 = threadIdx.x; s2 < S; s2 += RD_THREADS) a2 = Op::combine(a2, ld_acc<Op>(partial + row * S + s2));
+                __syncthreads();
+                a2 = block_reduce<Op>(a2);
+                if (threadIdx.x == 0) Op::store(B, offB + row, a2, idx64);
+            }
         }
-        __syncthreads();      // block_reduce's shared scratch is reused by the next row
-    }
-}
-
-// merge S partials per output; outputs laid out [rows, S, cols] (cols == 1 for the row kernels)
-template <typename Op>
-__global__ void __launch_bounds__(RD_THREADS)
-reduce_merge(int64_t rows, int S, int64_t cols, const typename Op::Acc* __restrict__ partial,
-             void* __restrict__ B, int64_t offB, int idx64)
-{
-    const int64_t total = rows * cols;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = o / cols, j = o - i * cols;
-        typename Op::Acc acc = Op::identity();
-        for (int s = 0; s < S; s++) acc = Op::combine(acc, partial[(i * S + s) * cols + j]);
-        Op::store(B, offB + o, acc, idx64);
+        __syncthreads();      // block_reduce's shared scratch and is_last are reused by the next row
     }
 }
 
@@ -198,10 +214,11 @@ reduce_merge(int64_t rows, int S, int64_t cols, const typename Op::Acc* __restri
 template <typename T, typename Op, bool VEC>
 __global__ void __launch_bounds__(RD_THREADS)
 reduce_cols(int64_t m, int64_t n, int64_t k, int S, int64_t tlen, const T* __restrict__ A,
-            void* __restrict__ B, int64_t offB, int idx64, typename Op::Acc* __restrict__ partial)
+            void* __restrict__ B, int64_t offB, int idx64, typename Op::Acc* partial, int* counters)
 {
     constexpr int V = VEC ? RdVec<T>::N : 1;
     __shared__ typename Op::Acc sm[RD_THREADS * V];
+    __shared__ int is_last;
     const int TX = blockDim.x, TY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t j0 = ((int64_t)blockIdx.x * TX + tx) * V;
@@ -273,6 +290,55 @@ reduce_cols(int64_t m, int64_t n, int64_t k, int S, int64_t tlen, const T* __res
                 }
             }
         }
+        if (S > 1) {
+            // the last CTA of this (i, column block) to finish merges the S partials (fixed order:
+            // ty-strided over s, then the same shared-memory tree) -- one launch, deterministic
+            __threadfence();
+            __syncthreads();
+            if (tx == 0 && ty == 0) {
+                int* ctr = counters + i * gridDim.x + blockIdx.x;
+                const int ticket = atomicAdd(ctr, 1);
+                is_last = (ticket == S - 1);
+                if (is_last) *ctr = 0;
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    typename Op::Acc a2 = Op::identity();
+                    if (j0 + e < k) {
+                        const typename Op::Acc* pp = partial + (i * S) * k + j0 + e;
+                        int s2 = ty;
+                        for (; s2 + 3 * TY < S; s2 += 4 * TY) {       // 4 independent L2 loads in flight
+                            const typename Op::Acc p0 = ld_acc<Op>(pp + (int64_t)s2 * k);
+                            const typename Op::Acc p1 = ld_acc<Op>(pp + (int64_t)(s2 + TY) * k);
+                            const typename Op::Acc p2 = ld_acc<Op>(pp + (int64_t)(s2 + 2 * TY) * k);
+                            const typename Op::Acc p3 = ld_acc<Op>(pp + (int64_t)(s2 + 3 * TY) * k);
+                            a2 = Op::combine(Op::combine(Op::combine(Op::combine(a2, p0), p1), p2), p3);
+                        }
+                        for (; s2 < S; s2 += TY) a2 = Op::combine(a2, ld_acc<Op>(pp + (int64_t)s2 * k));
+                    }
+                    sm[(ty * TX + tx) * V + e] = a2;
+                }
+                __syncthreads();
+                for (int half = TY >> 1; half > 0; half >>= 1) {
+                    if (ty < half) {
+#pragma unroll
+                        for (int e = 0; e < V; e++) {
+                            sm[(ty * TX + tx) * V + e] = Op::combine(sm[(ty * TX + tx) * V + e], sm[((ty + half) * TX + tx) * V + e]);
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (ty == 0 && j0 < k) {
+#pragma unroll
+                    for (int e = 0; e < V; e++) {
+                        if (j0 + e < k) Op::store(B, offB + i * k + j0 + e, sm[tx * V + e], idx64);
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
 }
@@ -286,6 +352,16 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
     using Acc = typename Op::Acc;
     const int64_t target_ctas = (int64_t)c.sm_count * 8;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    // CTAs per SM actually resident for the split kernels: splitting to exactly one full wave avoids
+    // a partially filled second wave (1184 CTAs on 888 slots cost 25% at axis-0 of [65536,1024])
+    static int occ_rows = 0, occ_cols = 0;
+    if (!occ_rows) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rows, reduce_rows_block<T, Op, true>, RD_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cols, reduce_cols<T, Op, true>, RD_THREADS, 0);
+        if (occ_rows < 1) occ_rows = 4;
+        if (occ_cols < 1) occ_cols = 4;
+    }
+    const int64_t wave_rows = (int64_t)c.sm_count * occ_rows, wave_cols = (int64_t)c.sm_count * occ_cols;
     if (n >= (int64_t)INT_MAX) RB_INVALID("reduced axis too long (n=%lld)", (long long)n);
 
     if (k == 1) {
@@ -304,7 +380,8 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
         int64_t S = 1;
         const int64_t min_seg = (int64_t)RD_THREADS * V * 4;          // >= 4 vectors per thread
         if (m < target_ctas) {
-            S = rb_ceil_div(target_ctas, m);
+            S = wave_rows / m;                       // floor: never more than one full wave
+            if (S < 1) S = 1;
             const int64_t smax = rb_ceil_div(n, min_seg);
             if (S > smax) S = smax;
             if (S < 1) S = 1;
@@ -314,20 +391,18 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
         seglen = rb_ceil_div(seglen, (int64_t)V) * V;                 // keep segments 16-byte aligned
         S = rb_ceil_div(n, seglen);
         Acc* partial = nullptr;
+        int* counters = nullptr;
         if (S > 1) {
             int rc = rb200::ensure_workspace((size_t)(m * S) * sizeof(Acc));
             if (rc != RB200_OK) return rc;
             partial = reinterpret_cast<Acc*>(c.workspace);
+            rc = rb200::ensure_counters(m, &counters);
+            if (rc != RB200_OK) return rc;
         }
         dim3 grid((unsigned)S, (unsigned)(m < 65535 ? m : 65535));
-        if (vec) reduce_rows_block<T, Op, true><<<grid, RD_THREADS, 0, c.stream>>>(m, n, (int)S, seglen, A, B, offB, idx64, partial);
-        else     reduce_rows_block<T, Op, false><<<grid, RD_THREADS, 0, c.stream>>>(m, n, (int)S, seglen, A, B, offB, idx64, partial);
+        if (vec) reduce_rows_block<T, Op, true><<<grid, RD_THREADS, 0, c.stream>>>(m, n, (int)S, seglen, A, B, offB, idx64, partial, counters);
+        else     reduce_rows_block<T, Op, false><<<grid, RD_THREADS, 0, c.stream>>>(m, n, (int)S, seglen, A, B, offB, idx64, partial, counters);
         RB_LAUNCH_CHECK("reduce_rows_block");
-        if (S > 1) {
-            int64_t g = rb_ceil_div(m, RD_THREADS);
-            reduce_merge<Op><<<(unsigned)(g < 1 ? 1 : g), RD_THREADS, 0, c.stream>>>(m, (int)S, 1, partial, B, offB, idx64);
-            RB_LAUNCH_CHECK("reduce_merge");
-        }
         return RB200_OK;
     }
 
@@ -340,7 +415,8 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
     const int64_t col_blocks = rb_ceil_div(kv, tx);
     int64_t S = 1;
     if (m * col_blocks < target_ctas) {
-        S = rb_ceil_div(target_ctas, m * col_blocks);
+        S = wave_cols / (m * col_blocks);            // floor: one full wave
+        if (S < 1) S = 1;
         const int64_t smax = rb_ceil_div(n, (int64_t)ty * 4);
         if (S > smax) S = smax;
         if (S < 1) S = 1;
@@ -349,25 +425,21 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
     int64_t tlen = rb_ceil_div(n, S);
     S = rb_ceil_div(n, tlen);
     Acc* partial = nullptr;
+    int* counters = nullptr;
     if (S > 1) {
         int rc = rb200::ensure_workspace((size_t)(m * S * k) * sizeof(Acc));
         if (rc != RB200_OK) return rc;
         partial = reinterpret_cast<Acc*>(c.workspace);
+        rc = rb200::ensure_counters(m * col_blocks, &counters);
+        if (rc != RB200_OK) return rc;
     }
     const int64_t units = m * S;
     dim3 block(tx, ty);
     dim3 grid((unsigned)col_blocks, (unsigned)(units < 65535 ? units : 65535));
     if (col_blocks > 0x7fffffffLL) RB_INVALID("k too large");
-    if (vec) reduce_cols<T, Op, true><<<grid, block, 0, c.stream>>>(m, n, k, (int)S, tlen, A, B, offB, idx64, partial);
-    else     reduce_cols<T, Op, false><<<grid, block, 0, c.stream>>>(m, n, k, (int)S, tlen, A, B, offB, idx64, partial);
+    if (vec) reduce_cols<T, Op, true><<<grid, block, 0, c.stream>>>(m, n, k, (int)S, tlen, A, B, offB, idx64, partial, counters);
+    else     reduce_cols<T, Op, false><<<grid, block, 0, c.stream>>>(m, n, k, (int)S, tlen, A, B, offB, idx64, partial, counters);
     RB_LAUNCH_CHECK("reduce_cols");
-    if (S > 1) {
-        int64_t g = rb_ceil_div(m * k, RD_THREADS);
-        const int64_t cap = (int64_t)c.sm_count * 16;
-        if (g > cap) g = cap;
-        reduce_merge<Op><<<(unsigned)g, RD_THREADS, 0, c.stream>>>(m, (int)S, k, partial, B, offB, idx64);
-        RB_LAUNCH_CHECK("reduce_merge");
-    }
     return RB200_OK;
 }
 

@@ -509,20 +509,32 @@ def test_gemm_tf32x3_long_k_accumulator_drift(cuda_service):
         assert rel.max() < 2e-3
 
 
-SHORTK = [(4096, 64, 27), (1000, 100, 5), (513, 7, 64), (70000, 64, 27), (2048, 130, 1), (640, 64, 33)]
+SHORTK = [(4096, 64, 27), (1000, 100, 5), (513, 7, 64), (70000, 64, 27), (2048, 130, 1), (640, 64, 33),
+          (5000, 128, 64), (3000, 33, 100), (2049, 96, 31), (2500, 1, 1)]
 
 
 @pytest.mark.parametrize("mnk", SHORTK, ids=[str(s) for s in SHORTK])
-def test_gemm_shortk_conv_shapes(mnk, cuda_service):
-    """Tall matrix x short K (conv-as-GEMM): dedicated FFMA kernel, fp32 accuracy, any ld/offset."""
+def test_gemm_tall_skinny_conv_shapes(mnk, cuda_service):
+    """Tall matrix x short K (conv-as-GEMM, e.g. cols [B*oh*ow, 27] x W [27, 64]) with arbitrary ld/offset:
+    FFMA short-K kernel in FP32 mode, software-staged tcgen05 kernel in the TF32 modes when M >= 2048,
+    N <= 128, K <= 128."""
     m, n, k = mnk
-    for mode in (rb.GEMM_AUTO, rb.GEMM_FP32_SIMT, rb.GEMM_TF32X3):
+    skinny = m >= 2048 and n <= 128 and k <= 128
+    for mode in (rb.GEMM_FP32_SIMT, rb.GEMM_AUTO, rb.GEMM_TF32X3, rb.GEMM_TF32):
         for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (0.5, 1.5, 3, 1), (1.0, 1.0, 4, 4)):
             err, path = _gemm_case(cuda_service, mode, m, n, k, False, False, alpha, beta, off, off, off, ldx)
-            assert path == "simt_f32_shortk", path
-            assert err < 2e-6, (err, mnk, mode)
+            if mode == rb.GEMM_FP32_SIMT:
+                assert path in ("simt_f32_shortk", "simt_f32") and err < 2e-6, (path, err)
+            elif mode == rb.GEMM_TF32:
+                if skinny:
+                    assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32"), path
+                assert err < 2e-3, (err, path)
+            else:
+                if skinny:      # aligned full-width shapes may take the TMA-fed kernel instead
+                    assert path in ("tcgen05_tf32x3_skinny", "tcgen05_tf32x3"), path
+                assert err < 5e-5, (err, path, mnk)
     err, path = _gemm_case(cuda_service, rb.GEMM_AUTO, m, n, k, True, False, 1.0, 0.0)
-    assert path != "simt_f32_shortk" and err < 5e-5
+    assert "skinny" not in path and "shortk" not in path and err < 5e-5
 
 
 def test_gemm_unaligned_falls_back_to_simt(cuda_service):
