@@ -375,6 +375,236 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     }
 }
 
+// =====================================================================================================
+// 2-CTA variant (1xTF32): a CTA pair (cluster of 2 on one TPC) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2 (M = 256).  CTA r stages only ITS 128 rows of A and ITS 128 columns of B; the
+// tensor cores of both SMs read both halves of B, so the L2 -> shared-memory traffic per MAC drops by a
+// third against the 1-CTA kernel (64 KB instead of 96 KB per 256x256x32 block) and the 32 KB stages
+// allow a 6-deep ring.  Each CTA keeps two 128 x 256 accumulators in its own TMEM and drains its own
+// 128 rows.  Synchronisation: both CTAs' TMA loads complete_tx on the LEADER's full barrier (the leader
+// posts the expect_tx for both), the leader's tcgen05.commit multicasts to the empty / tmem_full barriers
+// of both CTAs, and the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
+// =====================================================================================================
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB: this CTA's 128 rows of A
+constexpr int TC2_B_BYTES = 128 * TC_BK * 4;          // 16 KB: this CTA's 128 columns of B
+constexpr int TC2_STAGE = TC2_A_BYTES + TC2_B_BYTES;
+constexpr int TC2_BAR_OFF = TC2_STAGES * TC2_STAGE;
+constexpr int TC2_SMEM = TC2_BAR_OFF + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, TcParams p)
+{
+    constexpr int STAGES = TC2_STAGES;
+    constexpr int BN = 256;                                   // pair tile: 256 x 256
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TC2_BAR_OFF;
+    auto full_bar  = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar= [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_ptr_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                  // 0 = leader (issues the MMAs)
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(tmem_ptr_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                        // barriers of BOTH CTAs initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + TC2_BAR_OFF + 8 * (2 * STAGES + 4));
+
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;     // here: pair tiles (256 rows each)
+
+    if (warp == 0) {
+        // ===== TMA producer (one per CTA: its half of A and of B) =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                int mb, nb;
+                tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+                const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * 128;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t leader_full = mapa_rank(full_bar(stage), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * TC2_STAGE);     // both CTAs' bytes
+                    const uint32_t sA = smem_base + stage * TC2_STAGE;
+                    const uint32_t sB = sA + TC2_A_BYTES;
+                    const int k0 = kb * TC_BK;
+                    if (!A_MN) {
+                        tma_load_3d_2sm(sA, &tmapA, leader_full, k0, m0, 0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) tma_load_3d_2sm(sA + j * 4096, &tmapA, leader_full, m0 + 32 * j, k0, 0);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d_2sm(sB, &tmapB, leader_full, k0, n0, 0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) tma_load_3d_2sm(sB + j * 4096, &tmapB, leader_full, n0 + 32 * j, k0, 0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: leader CTA only =====
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);     // both CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);         // both halves of A and B have landed
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + stage * TC2_STAGE;
+                    const uint32_t sB = sA + TC2_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / TC_UMMA_K; kk++) {
+                        const uint32_t aoff = A_MN ? kk * 1024 : kk * 32;
+                        const uint32_t boff = B_MN ? kk * 1024 : kk * 32;
+                        const uint64_t ad = A_MN ? make_smem_desc(sA + aoff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                 : make_smem_desc(sA + aoff, 16, 1024, 2);
+                        const uint64_t bd = B_MN ? make_smem_desc(sB + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                 : make_smem_desc(sB + boff, 16, 1024, 2);
+                        tc_mma_tf32_2sm(tmem_d, ad, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    tc_commit_2sm(empty_bar(stage));           // frees this stage in BOTH CTAs
+                    if (kb == p.num_k_blocks - 1) tc_commit_2sm(tfull_bar(acc));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: this CTA's 128 rows of the pair tile =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            int mb, nb;
+            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+            const int64_t row = (int64_t)mb * 256 + (int64_t)rank * 128 + q * 32 + lane;
+            const int64_t col0 = (int64_t)nb * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            float* crow = p.C + row * p.ldC;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ch++) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32);
+                tc_ld_32x32b_x32(taddr, r);
+                tc_wait_ld();
+                const int64_t c0 = col0 + ch * 32;
+                if (row_ok && c0 < p.N) {
+                    if (c0 + 32 <= p.N) {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) {
+                            float4 o;
+                            o.x = p.alpha * __uint_as_float(r[4 * v + 0]);
+                            o.y = p.alpha * __uint_as_float(r[4 * v + 1]);
+                            o.z = p.alpha * __uint_as_float(r[4 * v + 2]);
+                            o.w = p.alpha * __uint_as_float(r[4 * v + 3]);
+                            float4* dst = reinterpret_cast<float4*>(crow + c0) + v;
+                            if (p.beta != 0.f) {
+                                const float4 old = *dst;
+                                o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
+                                o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+                            }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            if (c0 + e < p.N) {
+                                float o = p.alpha * __uint_as_float(r[e]);
+                                if (p.beta != 0.f) o = fmaf(p.beta, crow[c0 + e], o);
+                                crow[c0 + e] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));   // leader's barrier, 8 arrivals
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                        // nobody leaves while the peer still uses its smem / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- hi/lo split pre-pass for the 3xTF32 mode ------------------------------------------------------
 // planes[0] = tf32(x) (round to nearest, low 13 bits zero), planes[1] = x - planes[0] (exact in fp32).
 __global__ void __launch_bounds__(256)
@@ -462,6 +692,32 @@ int launch_by_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorM
     if (!a_mn &&  b_mn) return launch_tf32<BN, false, true,  PLANES, STAGES>(mA, mB, p);
     if ( a_mn && !b_mn) return launch_tf32<BN, true,  false, PLANES, STAGES>(mA, mB, p);
     return launch_tf32<BN, true, true, PLANES, STAGES>(mA, mB, p);
+}
+
+template <bool A_MN, bool B_MN>
+int launch_2cta_t(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
+{
+    rb200::Context& c = rb200::ctx();
+    auto kern = gemm_tf32_2cta_kernel<A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
+        configured = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int max_pairs = c.sm_count / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    kern<<<2 * pairs, TC_THREADS, TC2_SMEM, c.stream>>>(mA, mB, p);
+    RB_LAUNCH_CHECK("gemm_tf32_2cta_kernel");
+    return RB200_OK;
+}
+
+int launch_2cta(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
+{
+    if (!a_mn && !b_mn) return launch_2cta_t<false, false>(mA, mB, p);
+    if (!a_mn &&  b_mn) return launch_2cta_t<false, true>(mA, mB, p);
+    if ( a_mn && !b_mn) return launch_2cta_t<true, false>(mA, mB, p);
+    return launch_2cta_t<true, true>(mA, mB, p);
 }
 
 }  // namespace
@@ -557,8 +813,18 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_lbo = dbg_lbo >= 0 ? (uint32_t)dbg_lbo : 4096u;
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
-        if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
-        else             rc = launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
+        static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
+        if (planes == 1 && use_2cta && M >= 256 && c.sm_count >= 2) {
+            // CTA-pair kernel: 256-row pair tiles; B (and MN-major A) maps with 128-wide boxes
+            CUtensorMap mB2;
+            if (!b_mn) rc = make_map(&mB2, pb, kl, N, sldB, 1, 0, TC_BK, 128, k_sw);
+            else       rc = make_map(&mB2, pb, N, kl, sldB, 1, 0, 32, TC_BK, mn_sw);
+            if (rc != RB200_OK) return rc;
+            p.num_m_blocks = (int)rb_ceil_div(M, 256);
+            rc = launch_2cta(a_mn, b_mn, mA, mB2, p);
+            c.last_gemm_path = "tcgen05_tf32_2cta";
+        } else if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
+        else                    rc = launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
         if (rc != RB200_OK) return rc;
     }
     return RB200_OK;

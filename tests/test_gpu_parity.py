@@ -473,7 +473,7 @@ def test_gemm_tcgen05(mnk, tA, tB, mode, cuda_service):
         ldx += 1
     for alpha, beta, off in ((1.0, 0.0, 0), (1.0, 1.0, 0), (0.75, -1.5, 8)):
         err, path = _gemm_case(cuda_service, mode, m, n, k, tA, tB, alpha, beta, off, off, off, ldx)
-        assert path == ("tcgen05_tf32" if mode == rb.GEMM_TF32 else "tcgen05_tf32x3"), path
+        assert path in (("tcgen05_tf32", "tcgen05_tf32_2cta") if mode == rb.GEMM_TF32 else ("tcgen05_tf32x3",)), path
         assert err < GEMM_TOL[mode], (err, path, mnk, tA, tB, alpha, beta)
         if mode == rb.GEMM_TF32X3:
             assert err < 1e-4            # the reference's own isclose rtol
@@ -527,7 +527,7 @@ def test_gemm_tall_skinny_conv_shapes(mnk, cuda_service):
                 assert path in ("simt_f32_shortk", "simt_f32") and err < 2e-6, (path, err)
             elif mode == rb.GEMM_TF32:
                 if skinny:
-                    assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32"), path
+                    assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32", "tcgen05_tf32_2cta"), path
                 assert err < 2e-3, (err, path)
             else:
                 if skinny:      # aligned full-width shapes may take the TMA-fed kernel instead
