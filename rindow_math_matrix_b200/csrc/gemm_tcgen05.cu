@@ -155,6 +155,7 @@ struct TcParams {
     int num_m_blocks, num_n_blocks, num_k_blocks;
     // UMMA descriptor fields of an MN-major operand tile (boxes of 32 mn x 32 k floats):
     uint32_t mn_lbo, mn_sbo, mn_layout;
+    int group_m;                   // row-blocks per rasterisation group (CTA-pair kernel)
 };
 
 template <int BN, int PLANES, int STAGES>
@@ -167,12 +168,12 @@ struct TcSmem {
 };
 
 // grouped tile order: TC_GROUP_M row-blocks share each column-block before moving on
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb)
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb, int group_m = TC_GROUP_M)
 {
-    const int per_group = TC_GROUP_M * num_n;
+    const int per_group = group_m * num_n;
     const int group = tile / per_group;
-    const int first_m = group * TC_GROUP_M;
-    const int gsz = min(num_m - first_m, TC_GROUP_M);
+    const int first_m = group * group_m;
+    const int gsz = min(num_m - first_m, group_m);
     const int in_group = tile - group * per_group;
     mb = first_m + in_group % gsz;
     nb = in_group / gsz;
@@ -484,7 +485,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             int stage = 0; uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 int mb, nb;
-                tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+                tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
                 const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * 128;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -547,7 +548,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             int mb, nb;
-            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
             const int64_t row = (int64_t)mb * 256 + (int64_t)rank * 128 + q * 32 + lane;
             const int64_t col0 = (int64_t)nb * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -813,6 +814,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_lbo = dbg_lbo >= 0 ? (uint32_t)dbg_lbo : 4096u;
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
+        p.group_m = TC_GROUP_M;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         if (planes == 1 && use_2cta && M >= 256 && c.sm_count >= 2) {
             // CTA-pair kernel: 256-row pair tiles; B (and MN-major A) maps with 128-wide boxes
@@ -821,6 +823,10 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
             else       rc = make_map(&mB2, pb, N, kl, sldB, 1, 0, 32, TC_BK, mn_sw);
             if (rc != RB200_OK) return rc;
             p.num_m_blocks = (int)rb_ceil_div(M, 256);
+            // 74 pair tiles in flight as 8 pair-rows x ~9 column blocks: smallest A+B footprint per k-step,
+            // and an A panel (8 x 256 rows) that stays L2-resident across the waves of its group
+            static const int dbg_group = getenv("RB200_GEMM_GROUP") ? atoi(getenv("RB200_GEMM_GROUP")) : 8;
+            p.group_m = dbg_group > 0 ? dbg_group : 8;
             rc = launch_2cta(a_mn, b_mn, mA, mB2, p);
             c.last_gemm_path = "tcgen05_tf32_2cta";
         } else if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
