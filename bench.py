@@ -512,6 +512,18 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
                                             Wt, 0, 64, 0.0, outs[i], 0, 64), conv_bytes,
            {"shape": "[3154176,27] x [27,64]", "flops": 2.0 * M * 27 * 64})
     out["conv_gemm"]["path"] = _capi.last_gemm_path()
+    # fused conv2d forward (implicit GEMM): images + W + out only -- 846,011,136 B
+    fused_bytes = img.size * 4 + 27 * 64 * 4 + M * 64 * 4
+    ok = {"v": True}
+
+    def fused(i):
+        ok["v"] = math.conv2d_forward(images, 0, b, h, w, c, 3, 3, 1, 1, False, 1, 1, Wt, 0, 64, None, 0,
+                                      outs[i], 0) and ok["v"]
+    report("conv2d_fused", fused, fused_bytes,
+           {"shape": "64x224x224x3 * 3x3x3x64 -> [64,222,222,64] in one kernel (no cols)",
+            "flops": 2.0 * M * 27 * 64, "two_call_bytes": ic_bytes + conv_bytes})
+    out["conv2d_fused"]["path"] = _capi.last_gemm_path()
+    out["conv2d_fused"]["fused_kernel_used"] = bool(ok["v"])
     sets = sets_saved
     return out
 

@@ -85,8 +85,8 @@ int         rb200_init(int device);
 int         rb200_shutdown(void);
 int         rb200_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor,
                               int64_t* total_mem_bytes);
-/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the
- * library-owned stream. */
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream; 0 = the legacy default stream);
+ * (void*)-1 restores the library-owned stream. */
 int         rb200_set_stream(void* cuda_stream);
 int         rb200_get_stream(void** cuda_stream);
 int         rb200_sync(void);
@@ -95,8 +95,9 @@ int         rb200_get_default_gemm_mode(int* mode);
 /* How many kernels this library has launched since init / since the last reset
  * (bench.py's "gpu_launches"). */
 int         rb200_launch_count(int64_t* count, int reset);
-/* Name of the kernel family the last rb200_sgemm/dgemm dispatched to
- * ("tcgen05_tf32", "tcgen05_tf32x3", "simt_f32", "simt_f64"). */
+/* Name of the kernel family the last rb200_sgemm/dgemm/conv2d_forward dispatched to: "tcgen05_tf32_2cta",
+ * "tcgen05_tf32", "tcgen05_tf32x3", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
+ * "simt_f32", "simt_f64". */
 const char* rb200_last_gemm_path(void);
 
 /* ---- buffers: replaces PhpBLASFactory::Buffer (PhpBLASFactory.php:35) storage and the
@@ -166,6 +167,21 @@ int rb200_im2col2d(int dtype, int reverse,
                    int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
                    int cols_channels_first,
                    void* cols, int64_t cols_offset, int64_t cols_size);
+
+/* ---- fused conv2d forward (precedent for a fused entry in the reference:
+ *      LinearAlgebraCL::im2col2dclblast, src/LinearAlgebraCL.php:5001).  Computes exactly what
+ *      LinearAlgebra::im2col (src/LinearAlgebra.php:3369) + gemm (:925) (+ add, :1968) compute for the
+ *      reference's default layouts -- channels-last images [b,h,w,c], cols [b,oh,ow,kh,kw,c] viewed as
+ *      [b*oh*ow, kh*kw*c], kernel [kh*kw*c, filters] -- without materialising cols:
+ *        out[b,oy,ox,f] = sum_{ky,kx,c} images[b, oy*sh+ky*dh-ph, ox*sw+kx*dw-pw, c] * kernel[(ky,kx,c), f] (+ bias[f])
+ *      float32, TF32 / 3xTF32 modes, filters <= 128, kh*kw*c <= 128; anything else returns
+ *      RB200_E_UNSUPPORTED and the caller runs rb200_im2col2d + rb200_sgemm instead. ------------------ */
+int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset,
+                         int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                         int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                         int padding, int64_t dilation_h, int64_t dilation_w,
+                         const void* kernel, int64_t kernel_offset, int64_t filters,
+                         const void* bias, int64_t bias_offset, void* out, int64_t out_offset, int mode);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
     "rb200_reduce_max": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
     "rb200_reduce_argmax": (i32, [i32, i64, i64, i64, vp, i64, i32, vp, i64]),
     "rb200_softmax": (i32, [i32, i64, i64, vp, i64, i64]),
+    "rb200_conv2d_forward": (i32, [i32, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, i64, i64,
+                                   vp, i64, i64, vp, i64, vp, i64, i32]),
     "rb200_im2col2d": (i32, [i32, i32, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                              i32, i32, i64, i64, i32, vp, i64, i64]),
 }

@@ -16,6 +16,11 @@ int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, in
 bool gemm_tcgen05_skinny_eligible(int mode, int64_t M, int64_t N, int64_t K);
 int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
                         const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
+bool conv2d_tcgen05_eligible(int mode, int64_t M, int64_t N, int64_t K);
+int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                   int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                   int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
+                   const float* W, int64_t filters, const float* bias, float* out);
 bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
                            const float* B, int64_t ldB, const float* C, int64_t ldC);
 int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
@@ -90,6 +95,47 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     }
     c.last_gemm_path = "simt_f32";
     return rb200::gemm_simt<float>(m, n, k, alpha, a, sAm, sAk, b, sBk, sBn, beta, cc, ldC);
+}
+
+int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset,
+                         int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                         int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                         int padding, int64_t dilation_h, int64_t dilation_w,
+                         const void* kernel, int64_t kernel_offset, int64_t filters,
+                         const void* bias, int64_t bias_offset, void* out, int64_t out_offset, int mode)
+{
+    RB_REQUIRE_INIT();
+    rb200::Context& c = rb200::ctx();
+    if (dtype != RB200_FLOAT32) RB_UNSUPPORTED("conv2d_forward: float32 only (use im2col2d + gemm)");
+    if (!images || !kernel || !out) RB_INVALID("NULL buffer");
+    if (batches < 1 || im_h < 1 || im_w < 1 || channels < 1 || filter_h < 1 || filter_w < 1 || stride_h < 1 ||
+        stride_w < 1 || dilation_h < 1 || dilation_w < 1 || filters < 1) {
+        RB_INVALID("conv2d_forward: shape parameters must be greater than 0");
+    }
+    if (images_offset < 0 || kernel_offset < 0 || out_offset < 0 || bias_offset < 0) RB_INVALID("negative offset");
+    // same output-shape rule as PhpMath::im2col2d (PhpMath.php:2213-2241)
+    int64_t out_h = (im_h - (filter_h - 1) * dilation_h - 1) / stride_h + 1;
+    int64_t out_w = (im_w - (filter_w - 1) * dilation_w - 1) / stride_w + 1;
+    if (out_h <= 0 || out_w <= 0) RB_INVALID("Invalid shape or parameters.");
+    int64_t pad_h = 0, pad_w = 0;
+    if (padding) {
+        pad_h = ((im_h - 1) * stride_h - im_h + (filter_h - 1) * dilation_h + 1) / 2;
+        pad_w = ((im_w - 1) * stride_w - im_w + (filter_w - 1) * dilation_w + 1) / 2;
+        out_h = im_h;
+        out_w = im_w;
+    }
+    if (mode == RB200_GEMM_AUTO) mode = c.default_gemm_mode;
+    const int64_t M = batches * out_h * out_w, K = filter_h * filter_w * channels;
+    if (batches * im_h * im_w * channels >= (1LL << 31)) RB_UNSUPPORTED("conv2d_forward: images exceed 2^31 elements");
+    if (!rb200::conv2d_tcgen05_eligible(mode, M, filters, K)) {
+        RB_UNSUPPORTED("conv2d_forward: needs a TF32 mode, filters <= 128 and filter_h*filter_w*channels <= 128 "
+                       "(use im2col2d + gemm)");
+    }
+    return rb200::conv2d_tcgen05(mode, reinterpret_cast<const float*>(images) + images_offset, batches, im_h, im_w,
+                                 channels, filter_h, filter_w, stride_h, stride_w, dilation_h, dilation_w, pad_h, pad_w,
+                                 out_h, out_w, reinterpret_cast<const float*>(kernel) + kernel_offset, filters,
+                                 bias ? reinterpret_cast<const float*>(bias) + bias_offset : nullptr,
+                                 reinterpret_cast<float*>(out) + out_offset);
 }
 
 int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,

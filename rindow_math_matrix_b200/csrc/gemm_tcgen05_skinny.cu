@@ -114,6 +114,11 @@ struct SktParams {
     uint32_t tmem_cols;
     int epi_groups;                // 1 or 2 groups of four epilogue warps (2 when the staging fits)
     int raw_slots;                 // slots of the raw cp.async ring (0 when the tile is not contiguous)
+    // implicit-GEMM convolution (conv != 0): A is never materialised; row m = (b, oy, ox) and column
+    // k = (ky, kx, c) of the virtual cols matrix are gathered straight from the channels-last images
+    int conv;
+    int im_h, im_w, chan, filt_w, str_h, str_w, dil_h, dil_w, pad_h, pad_w, out_h, out_w;
+    const float* bias;             // optional [N] added in the epilogue (conv only)
 };
 
 template <int PLANES>
@@ -132,6 +137,7 @@ gemm_tf32_skinny_kernel(SktParams p)
     const uint32_t off_raw = off_epi + (uint32_t)p.epi_groups * 4u * 32u * epi_pitch * 4u;   // 16-byte aligned
     const uint32_t off_bar = off_raw + (uint32_t)p.raw_slots * SKT_RAW_STAGE;
     const uint32_t bar = base + ((off_bar + 7u) & ~7u);
+    const uint32_t off_rinfo = ((off_bar + 7u) & ~7u) + 128u;            // [128][3] ints, conv only
     auto a_full  = [&](int s) { return bar + 8u * s; };
     auto a_empty = [&](int s) { return bar + 8u * (SKT_STAGES + s); };
     auto t_full  = [&](int a) { return bar + 8u * (2 * SKT_STAGES + a); };
@@ -255,6 +261,67 @@ gemm_tf32_skinny_kernel(SktParams p)
                 slot_out = (slot_out + 1) % SKT_RAW_SLOTS;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (p.conv) {
+            // implicit GEMM: thread owns column k = (ky, kx, c) of the k-block (a fixed tap: fixed offset
+            // into the image) and walks the rows; the (b, oy, ox) decomposition of the 128 rows is done
+            // once per tile into shared memory.  Loads go through L1 (each input element is used by up
+            // to filter_h*filter_w neighbouring cells), 8 rows in flight per thread.
+            int* rinfo = reinterpret_cast<int*>(gen + off_rinfo);                  // [128][3]: base, y0, x0
+            const int cells = p.out_h * p.out_w;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int64_t m0 = (int64_t)tile * SKT_BM;
+                const int rows = (int)min((int64_t)SKT_BM, p.M - m0);
+                {
+                    const int64_t m = m0 + t;
+                    int bb = 0, y0 = 0, x0 = 0;
+                    if (t < rows) {
+                        bb = (int)(m / cells);
+                        const int q2 = (int)(m - (int64_t)bb * cells);
+                        const int oy = q2 / p.out_w, ox = q2 - oy * p.out_w;
+                        y0 = oy * p.str_h - p.pad_h;
+                        x0 = ox * p.str_w - p.pad_w;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                 // previous tile's readers are done
+                    rinfo[3 * t] = (bb * p.im_h + y0) * p.im_w * p.chan + x0 * p.chan;
+                    rinfo[3 * t + 1] = y0;
+                    rinfo[3 * t + 2] = x0;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                for (int kb = 0; kb < p.KB; kb++) {
+                    sk_mbar_wait(a_empty(stage), phase ^ 1);
+                    uint8_t* sa = gen + stage * a_stage_bytes;
+                    const int kk = t & 31;
+                    const int k = kb * 32 + kk;
+                    const int kwc = p.filt_w * p.chan;
+                    const int ky = k / kwc, rem = k - ky * kwc;
+                    const int kx = rem / p.chan, c = rem - kx * p.chan;
+                    const int dy = ky * p.dil_h, dx = kx * p.dil_w;
+                    const int delta = (dy * p.im_w + dx) * p.chan + c;
+                    const bool k_ok = k < p.K;
+                    for (int r0 = t >> 5; r0 < SKT_BM; r0 += 32) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int r = r0 + 4 * i;
+                            const int iy = rinfo[3 * r + 1] + dy, ix = rinfo[3 * r + 2] + dx;
+                            const bool ok = k_ok && r < rows && iy >= 0 && iy < p.im_h && ix >= 0 && ix < p.im_w;
+                            v[i] = ok ? __ldg(p.A + rinfo[3 * r] + delta) : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int r = r0 + 4 * i;
+                            const float hi = sk_rna(v[i]);
+                            const uint32_t o = sk_swz(r, kk);
+                            *reinterpret_cast<float*>(sa + o) = hi;
+                            if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v[i] - hi;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) sk_mbar_arrive(a_full(stage));
+                    if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
         } else {
             // generic: a warp reads one row's 32 k (coalesced 128 bytes), 8 rows in flight per thread
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -373,11 +440,14 @@ gemm_tf32_skinny_kernel(SktParams p)
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(t_empty(acc));
                 // transpose out of shared memory: consecutive lanes -> consecutive 16-byte pieces of a C row
-                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && row0 + 32 <= p.M) {
+                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && row0 + 32 <= p.M &&
+                    (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
                     // fast path: full tile, no beta -- 4 independent LDS.128 / STG.128 pairs per step
                     float* cbase = p.C + (row0 + lr) * p.ldC + lc4 * 4;
                     const float* sbase = ebuf + lr * epi_pitch + lc4 * 4;
                     const int steps = nv;                             // 32 rows / rstep rows per step
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias) + lc4);
                     for (int s0 = 0; s0 < steps; s0 += 4) {
                         float4 o[4];
 #pragma unroll
@@ -386,7 +456,10 @@ gemm_tf32_skinny_kernel(SktParams p)
                         }
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            if (s0 + u < steps) __stcs(reinterpret_cast<float4*>(cbase + (int64_t)(s0 + u) * rstep * p.ldC), o[u]);
+                            if (s0 + u < steps) {
+                                o[u].x += bv.x; o[u].y += bv.y; o[u].z += bv.z; o[u].w += bv.w;
+                                __stcs(reinterpret_cast<float4*>(cbase + (int64_t)(s0 + u) * rstep * p.ldC), o[u]);
+                            }
                         }
                     }
                 } else {
@@ -396,6 +469,12 @@ gemm_tf32_skinny_kernel(SktParams p)
                         const int col = c4 * 4;
                         if (grow < p.M && col < p.N) {
                             float4 o = *reinterpret_cast<const float4*>(ebuf + rr * epi_pitch + col);
+                            if (p.bias) {
+                                o.x += __ldg(p.bias + col);
+                                if (col + 1 < p.N) o.y += __ldg(p.bias + col + 1);
+                                if (col + 2 < p.N) o.z += __ldg(p.bias + col + 2);
+                                if (col + 3 < p.N) o.w += __ldg(p.bias + col + 3);
+                            }
                             float* cp = p.C + grow * p.ldC + col;
                             if (c_vec && col + 4 <= p.N) {
                                 if (p.beta != 0.f) {
@@ -431,7 +510,7 @@ size_t skt_smem_bytes(int planes, int NP, int KB, int epi_groups, int raw_slots)
     size_t a = (size_t)SKT_STAGES * planes * SKT_A_TILE;
     size_t b = (size_t)planes * KB * NP * 128;
     size_t e = (size_t)epi_groups * 4 * 32 * (NP + 4) * 4;
-    return a + b + e + (size_t)raw_slots * SKT_RAW_STAGE + 256 + 1024;
+    return a + b + e + (size_t)raw_slots * SKT_RAW_STAGE + 256 + 128 * 3 * 4 + 1024;
 }
 
 }  // namespace
@@ -459,6 +538,8 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
     p.KB = (int)((K + 31) / 32);
     p.alpha = alpha; p.beta = beta;
     p.A = A; p.ldA = ldA; p.B = B; p.ldB = ldB; p.C = C; p.ldC = ldC;
+    p.conv = 0; p.bias = nullptr;
+    p.im_h = p.im_w = p.chan = p.filt_w = p.str_h = p.str_w = p.dil_h = p.dil_w = p.pad_h = p.pad_w = p.out_h = p.out_w = 0;
     p.num_tiles = (int)rb_ceil_div(M, SKT_BM);
     p.a_contig = (ldA == K) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((SKT_BM * K) % 4 == 0);
     p.k_magic = (unsigned)((1ULL << 32) / (unsigned long long)K) + 1u;
@@ -485,6 +566,60 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
     else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p);
     RB_LAUNCH_CHECK("gemm_tf32_skinny_kernel");
     c.last_gemm_path = planes == 1 ? "tcgen05_tf32_skinny" : "tcgen05_tf32x3_skinny";
+    return RB200_OK;
+}
+
+// Fused conv2d forward: out[b,oy,ox,f] = sum_{ky,kx,c} images[b, oy*sh+ky*dh-ph,
+// ox*sw+kx*dw-pw, c] * W[(ky,kx,c), f] (+ bias[f]) == gemm(im2col2d(images) viewed [B*oh*ow, kh*kw*C], W) with
+// the reference's default layouts (channels-last images, cols-channels-last), without ever writing cols.
+bool conv2d_tcgen05_eligible(int mode, int64_t M, int64_t N, int64_t K)
+{
+    if (mode != RB200_GEMM_TF32 && mode != RB200_GEMM_TF32X3) return false;
+    if (M < 1 || N < 1 || N > 128 || K < 1 || K > 128) return false;
+    const int planes = mode == RB200_GEMM_TF32X3 ? 2 : 1;
+    const int NP = (int)((N + 31) / 32 * 32), KB = (int)((K + 31) / 32);
+    return skt_smem_bytes(planes, NP, KB, 1, 0) <= SKT_SMEM_LIMIT;
+}
+
+int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                   int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                   int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
+                   const float* W, int64_t filters, const float* bias, float* out)
+{
+    Context& c = ctx();
+    const int planes = mode == RB200_GEMM_TF32X3 ? 2 : 1;
+    SktParams p;
+    p.M = batches * out_h * out_w;
+    p.N = (int)filters; p.K = (int)(filter_h * filter_w * channels);
+    p.NP = (p.N + 31) / 32 * 32;
+    p.KB = (p.K + 31) / 32;
+    p.alpha = 1.f; p.beta = 0.f;
+    p.A = images; p.ldA = 0; p.B = W; p.ldB = filters; p.C = out; p.ldC = filters;
+    p.num_tiles = (int)rb_ceil_div(p.M, SKT_BM);
+    p.a_contig = 0;
+    p.k_magic = (unsigned)((1ULL << 32) / (unsigned long long)p.K) + 1u;
+    uint32_t cols = (uint32_t)(2 * planes * p.NP), pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    p.tmem_cols = pow2;
+    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, 0) <= SKT_SMEM_LIMIT ? 2 : 1;
+    p.raw_slots = 0;
+    p.conv = 1;
+    p.bias = bias;
+    p.im_h = (int)im_h; p.im_w = (int)im_w; p.chan = (int)channels; p.filt_w = (int)filter_w;
+    p.str_h = (int)stride_h; p.str_w = (int)stride_w; p.dil_h = (int)dilation_h; p.dil_w = (int)dilation_w;
+    p.pad_h = (int)pad_h; p.pad_w = (int)pad_w; p.out_h = (int)out_h; p.out_w = (int)out_w;
+    const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, 0);
+    static bool configured[3] = {false, false, false};
+    if (!configured[planes]) {
+        if (planes == 1) RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        else             RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        configured[planes] = true;
+    }
+    const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
+    if (planes == 1) gemm_tf32_skinny_kernel<1><<<grid, SKT_THREADS, smem, c.stream>>>(p);
+    else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p);
+    RB_LAUNCH_CHECK("gemm_tf32_skinny_kernel(conv)");
+    c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
     return RB200_OK;
 }
 

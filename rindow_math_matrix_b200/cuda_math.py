@@ -130,6 +130,33 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- fused conv2d forward (extension) ----------------------------------------
+    def conv2d_forward(self, images, images_offset, batches, im_h, im_w, channels, filter_h, filter_w,
+                       stride_h, stride_w, padding, dilation_h, dilation_w, kernel, kernel_offset, filters,
+                       bias, bias_offset, out, out_offset, gemm_mode=_capi.GEMM_AUTO) -> bool:
+        """out[b,oy,ox,f] = im2col2d(images) x kernel (+ bias) without materialising cols.  Returns False
+        (nothing launched) when the shape needs the two-call path (rb200 status UNSUPPORTED)."""
+        if len(images) - images_offset < batches * im_h * im_w * channels:
+            raise InvalidArgumentException("images buffer size is invalid")
+        if len(kernel) - kernel_offset < filter_h * filter_w * channels * filters:
+            raise InvalidArgumentException("kernel buffer size is invalid")
+        _cuda("images", images), _cuda("kernel", kernel), _cuda("out", out)
+        if images.dtype() != dtypes.float32:
+            return False
+        b_ptr = None
+        if bias is not None:
+            if len(bias) - bias_offset < filters:
+                raise InvalidArgumentException("bias buffer size is invalid")
+            b_ptr = _cuda("bias", bias).device_ptr()
+        rc = self._lib.rb200_conv2d_forward(images.dtype(), images.device_ptr(), images_offset, batches, im_h, im_w,
+                                            channels, filter_h, filter_w, stride_h, stride_w, 1 if padding else 0,
+                                            dilation_h, dilation_w, kernel.device_ptr(), kernel_offset, filters,
+                                            b_ptr, bias_offset, out.device_ptr_rw(), out_offset, gemm_mode)
+        if rc == _capi.E_UNSUPPORTED:
+            return False
+        _capi.check(rc)
+        return True
+
     # ---- zeros / fill (PhpMath.php:908-921, 2811-2827): unit-stride only on the device -------------------
     def zeros(self, n, X, offsetX, incX) -> None:
         if offsetX + (n - 1) * incX >= len(X):

@@ -202,6 +202,47 @@ class LinearAlgebra:
                       cols_channels_first, cols)
         return images
 
+    def conv2d(self, images: NDArray, kernel: NDArray, bias: NDArray | None = None, strides=None, padding=None,
+               dilation_rate=None) -> NDArray:
+        """Conv2D forward for channels-last images [b,h,w,c] and kernel [kh,kw,c,filters] -- the composition
+        the reference's users write by hand (im2col :3369 -> reshape -> gemm :925 -> add :1968; the Conv2D
+        layer itself lives in rindow-neuralnetworks).  Uses the driver's fused entry when it has one for
+        this shape, otherwise exactly those three driver calls."""
+        if images.ndim() != 4 or kernel.ndim() != 4:
+            raise InvalidArgumentException("images and kernel must be 4D dimension")
+        batches, in_h, in_w, channels = images.shape()
+        filter_h, filter_w, kc, filters = kernel.shape()
+        if kc != channels:
+            raise InvalidArgumentException("Unmatch channels of images and kernel")
+        stride_h, stride_w = strides if strides else (1, 1)
+        dilation_h, dilation_w = dilation_rate if dilation_rate else (1, 1)
+        padding = bool(padding)
+        if padding:
+            out_h, out_w = in_h, in_w
+        else:
+            out_h = _intdiv(in_h - (filter_h - 1) * dilation_h - 1, stride_h) + 1
+            out_w = _intdiv(in_w - (filter_w - 1) * dilation_w - 1, stride_w) + 1
+        if out_h <= 0 or out_w <= 0:
+            raise InvalidArgumentException("Invalid shape or paramaters.")
+        if bias is not None and bias.shape() != [filters]:
+            raise InvalidArgumentException("Unmatch shape of bias and kernel")
+        fused = getattr(self.math, "conv2d_forward", None) if type(self.math).__name__ == "CudaMath" else None
+        if fused is not None:
+            out = self.alloc([batches, out_h, out_w, filters], dtype=images.dtype())
+            if fused(images.buffer(), images.offset(), batches, in_h, in_w, channels, filter_h,
+                                           filter_w, stride_h, stride_w, padding, dilation_h, dilation_w,
+                                           kernel.buffer(), kernel.offset(), filters,
+                                           None if bias is None else bias.buffer(), 0 if bias is None else bias.offset(),
+                                           out.buffer(), out.offset()):
+                return out
+        cols = self.im2col(images, filterSize=[filter_h, filter_w], strides=[stride_h, stride_w], padding=padding,
+                           dilation_rate=[dilation_h, dilation_w])
+        out2d = self.gemm(cols.reshape([batches * out_h * out_w, filter_h * filter_w * channels]),
+                          kernel.reshape([filter_h * filter_w * channels, filters]))
+        if bias is not None:
+            self.add(bias, out2d)
+        return out2d.reshape([batches, out_h, out_w, filters])
+
     def im2col2d(self, reverse, images: NDArray, filterSize=None, strides=None, padding=None,
                  channels_first=None, dilation_rate=None, cols_channels_first=None,
                  cols: NDArray | None = None) -> NDArray:

@@ -714,6 +714,54 @@ def test_conv_config_im2col_gemm(cuda_service):
     assert isclose_ref(out.to_numpy().reshape(M, f)[rows], co.reshape(M, f)[rows])
 
 
+CONV_CASES = [  # (b, h, w, c, kh, kw, filters, strides, padding, dilation, bias)
+    (2, 16, 16, 3, 3, 3, 64, (1, 1), False, (1, 1), False),
+    (2, 16, 16, 3, 3, 3, 64, (1, 1), True, (1, 1), True),
+    (3, 17, 23, 3, 3, 3, 64, (2, 1), True, (1, 2), True),
+    (1, 30, 31, 8, 3, 3, 32, (1, 1), False, (1, 1), False),       # K = 72: three k-blocks
+    (2, 12, 12, 5, 2, 4, 100, (1, 2), True, (2, 1), True),         # N = 100 -> padded to 128
+    (4, 64, 64, 3, 3, 3, 64, (1, 1), False, (1, 1), True),
+    (1, 9, 9, 16, 3, 3, 16, (1, 1), False, (1, 1), False),         # K = 144 > 128: two-call path
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+@pytest.mark.parametrize("mode", [rb.GEMM_TF32X3, rb.GEMM_TF32, rb.GEMM_FP32_SIMT])
+def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
+    """Fused conv2d forward (implicit GEMM on tcgen05) == oracle im2col2d + oracle gemm (+ bias)."""
+    b, h, w, c, kh, kw, f, st, pad, dil, use_bias = case
+    rng = np.random.default_rng(4001)
+    img = rng.uniform(0, 1, (b, h, w, c)).astype(np.float32)
+    W = (rng.standard_normal((kh, kw, c, f)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(f).astype(np.float32) if use_bias else None
+    la = LinearAlgebra(cuda_service)
+    cuda_service.blas().setGemmMode(mode)
+    rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(mode))
+    try:
+        out = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st,
+                        padding=pad, dilation_rate=dil)
+    finally:
+        rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(rb.GEMM_TF32X3))
+        cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+    path = rb._capi.last_gemm_path()
+    K = kh * kw * c
+    if mode != rb.GEMM_FP32_SIMT and K <= 128 and f <= 128:
+        assert path.endswith("_conv"), path
+    shape = oracle.im2col2d_out_shape(b, h, w, c, kh, kw, st[0], st[1], pad, dil[0], dil[1], False)
+    M = shape[0] * shape[1] * shape[2]
+    cols = np.zeros(M * K)
+    oracle.im2col2d(False, oracle.as_buffer(img), 0, img.size, b, h, w, c, kh, kw, st[0], st[1], pad, False,
+                    dil[0], dil[1], False, cols, 0, cols.size)
+    ref = np.zeros(M * f)
+    oracle.gemm_rows_fast(0, M, f, K, 1.0, cols, K, oracle.as_buffer(W), f, 0.0, ref, f)
+    if bias is not None:
+        oracle.add(False, M, f, 1.0, oracle.as_buffer(bias), 0, 1, ref, 0, f)
+    assert out.shape() == [shape[0], shape[1], shape[2], f]
+    got = out.to_numpy().reshape(-1).astype(np.float64)
+    err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+    assert err < GEMM_TOL[mode], (err, path)
+
+
 # ---------------------------------------------------------------------------------------------------
 # buffer contract (PhpBufferTest.php)
 # ---------------------------------------------------------------------------------------------------

@@ -101,3 +101,23 @@ def test_service_without_gpu_is_basic_and_refuses_to_compute():
         svc.math(rb.Service.LV_BASIC)
     with pytest.raises(_capi.B200Error):
         rb.CudaBuffer(4, dtypes.float32)
+
+
+def test_conv2d_composition_over_any_driver(oracle_service):
+    """LinearAlgebra.conv2d without a fused driver entry = im2col -> gemm -> add (the reference calls)."""
+    la = LinearAlgebra(oracle_service)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 5, (2, 6, 7, 3)).astype(np.float32)
+    W = rng.integers(-2, 3, (3, 2, 3, 4)).astype(np.float32)
+    bias = np.arange(4, dtype=np.float32)
+    out = la.conv2d(la.array(img), la.array(W), la.array(bias), strides=(1, 2), padding=False)
+    ref = np.zeros((2, 4, 3, 4))
+    for b in range(2):
+        for oy in range(4):
+            for ox in range(3):
+                patch = img[b, oy:oy + 3, ox * 2:ox * 2 + 2, :]
+                ref[b, oy, ox] = np.tensordot(patch, W, axes=([0, 1, 2], [0, 1, 2])) + bias
+    assert out.shape() == [2, 4, 3, 4]
+    assert np.array_equal(out.to_numpy(), ref)
+    with pytest.raises(rb.InvalidArgumentException, match="Unmatch channels"):
+        la.conv2d(la.array(img), la.array(W[:, :, :2, :]))
