@@ -119,7 +119,35 @@ struct SktParams {
     int conv;
     int im_h, im_w, chan, filt_w, str_h, str_w, dil_h, dil_w, pad_h, pad_w, out_h, out_w;
     const float* bias;             // optional [N] added in the epilogue (conv only)
+    // conv tiling: an MMA tile = cv_rows out rows x cv_tw out columns of one image (cv_rows*cv_tw <= 128,
+    // always one contiguous run of rows of the [B*oh*ow, N] output); its input slab is staged in smem
+    int cv_tw, cv_rows, cv_col_blocks, cv_row_blocks;
+    int cv_slab_rows, cv_width_x, cv_row_elems, cv_slab_elems;
 };
+
+struct SktTile { int64_t m_start; int nvalid; int b, oy0, ox0; };
+
+__device__ __forceinline__ SktTile skt_tile(const SktParams& p, int tile)
+{
+    SktTile t;
+    if (!p.conv) {
+        t.m_start = (int64_t)tile * SKT_BM;
+        t.nvalid = (int)min((int64_t)SKT_BM, p.M - t.m_start);
+        t.b = t.oy0 = t.ox0 = 0;
+        return t;
+    }
+    const int per_img = p.cv_row_blocks * p.cv_col_blocks;
+    t.b = tile / per_img;
+    const int q = tile - t.b * per_img;
+    const int rb = q / p.cv_col_blocks, cb = q - rb * p.cv_col_blocks;
+    t.oy0 = rb * p.cv_rows;
+    t.ox0 = cb * p.cv_tw;
+    t.m_start = ((int64_t)t.b * p.out_h + t.oy0) * p.out_w + t.ox0;
+    const int rows = min(p.cv_rows, p.out_h - t.oy0);
+    // cv_rows > 1 only when cv_tw == out_w, so the valid cells are always one contiguous run
+    t.nvalid = p.cv_rows > 1 ? rows * p.out_w : min(p.cv_tw, p.out_w - t.ox0);
+    return t;
+}
 
 template <int PLANES>
 __global__ void __launch_bounds__(SKT_THREADS, 1)
@@ -262,66 +290,95 @@ gemm_tf32_skinny_kernel(SktParams p)
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else if (p.conv) {
-            // implicit GEMM: thread owns column k = (ky, kx, c) of the k-block (a fixed tap: fixed offset
-            // into the image) and walks the rows; the (b, oy, ox) decomposition of the 128 rows is done
-            // once per tile into shared memory.  Loads go through L1 (each input element is used by up
-            // to filter_h*filter_w neighbouring cells), 8 rows in flight per thread.
-            int* rinfo = reinterpret_cast<int*>(gen + off_rinfo);                  // [128][3]: base, y0, x0
-            const int cells = p.out_h * p.out_w;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int64_t m0 = (int64_t)tile * SKT_BM;
-                const int rows = (int)min((int64_t)SKT_BM, p.M - m0);
-                {
-                    const int64_t m = m0 + t;
-                    int bb = 0, y0 = 0, x0 = 0;
-                    if (t < rows) {
-                        bb = (int)(m / cells);
-                        const int q2 = (int)(m - (int64_t)bb * cells);
-                        const int oy = q2 / p.out_w, ox = q2 - oy * p.out_w;
-                        y0 = oy * p.str_h - p.pad_h;
-                        x0 = ox * p.str_w - p.pad_w;
+            // Implicit GEMM.  Per tile the input slab (the cv_slab_rows image rows x cv_width_x columns that
+            // feed its cells; zero outside the image) is brought into a shared-memory ring with 4-byte
+            // cp.async copies issued SKT_PREFETCH tiles ahead; the A stage is then built from the slab:
+            // thread = fixed k = (ky,kx,c) (fixed slab offset), walking the rows.  No global latency and no
+            // bounds test in the build loop.
+            int* roff = reinterpret_cast<int*>(gen + off_rinfo);                   // [128] slab offset of row r
+            {
+                const int rr = p.cv_rows > 1 ? t / p.cv_tw : 0;
+                const int cc = t - rr * p.cv_tw;
+                roff[t] = rr * p.str_h * p.cv_row_elems + cc * p.str_w * p.chan;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float* ring = reinterpret_cast<float*>(gen + off_raw);
+            auto issue_slab = [&](int tile, int slot) {
+                if (tile < p.num_tiles) {
+                    const SktTile ti = skt_tile(p, tile);
+                    const int x_start = ti.ox0 * p.str_w - p.pad_w, y_start = ti.oy0 * p.str_h - p.pad_h;
+                    const float* img_b = p.A + (int64_t)ti.b * p.im_h * p.im_w * p.chan;
+                    const uint32_t dst0 = base + off_raw + (uint32_t)slot * SKT_RAW_STAGE;
+                    float* dstg = ring + slot * (SKT_RAW_STAGE / 4);
+                    // per slab row the in-image part is one index interval [lo, hi): no per-element division
+                    const int x_lo = max(0, -x_start), x_hi = max(x_lo, min(p.cv_width_x, p.im_w - x_start));
+                    const int lo = x_lo * p.chan, hi = x_hi * p.chan;
+                    for (int sl = 0; sl < p.cv_slab_rows; sl++) {
+                        const int iy = y_start + sl;
+                        const bool row_ok = iy >= 0 && iy < p.im_h;
+                        const float* src = img_b + ((int64_t)iy * p.im_w + x_start) * p.chan;
+                        const uint32_t drow = dst0 + 4u * (uint32_t)(sl * p.cv_row_elems);
+                        float* grow = dstg + sl * p.cv_row_elems;
+                        for (int idx = t; idx < p.cv_row_elems; idx += SKT_PRODUCERS) {
+                            if (row_ok && idx >= lo && idx < hi) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(drow + 4u * idx), "l"(src + idx) : "memory");
+                            } else {
+                                grow[idx] = 0.f;
+                            }
+                        }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");                 // previous tile's readers are done
-                    rinfo[3 * t] = (bb * p.im_h + y0) * p.im_w * p.chan + x0 * p.chan;
-                    rinfo[3 * t + 1] = y0;
-                    rinfo[3 * t + 2] = x0;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            const int step = gridDim.x;
+            int slot_in = 0;
+#pragma unroll
+            for (int d = 0; d < SKT_PREFETCH; d++) { issue_slab(blockIdx.x + d * step, slot_in); slot_in = (slot_in + 1) % SKT_RAW_SLOTS; }
+            int slot_out = 0;
+            const int kwc = p.filt_w * p.chan;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += step) {
+                issue_slab(tile + SKT_PREFETCH * step, slot_in);
+                slot_in = (slot_in + 1) % SKT_RAW_SLOTS;
+                asm volatile("cp.async.wait_group %0;" :: "n"(SKT_PREFETCH) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");                     // every producer's copies of this slab landed
+                const SktTile ti = skt_tile(p, tile);
+                const float* slab = ring + slot_out * (SKT_RAW_STAGE / 4);
                 for (int kb = 0; kb < p.KB; kb++) {
                     sk_mbar_wait(a_empty(stage), phase ^ 1);
                     uint8_t* sa = gen + stage * a_stage_bytes;
                     const int kk = t & 31;
                     const int k = kb * 32 + kk;
-                    const int kwc = p.filt_w * p.chan;
                     const int ky = k / kwc, rem = k - ky * kwc;
                     const int kx = rem / p.chan, c = rem - kx * p.chan;
-                    const int dy = ky * p.dil_h, dx = kx * p.dil_w;
-                    const int delta = (dy * p.im_w + dx) * p.chan + c;
+                    const int koff = ky * p.dil_h * p.cv_row_elems + kx * p.dil_w * p.chan + c;
                     const bool k_ok = k < p.K;
-                    for (int r0 = t >> 5; r0 < SKT_BM; r0 += 32) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int r = r0 + 4 * i;
-                            const int iy = rinfo[3 * r + 1] + dy, ix = rinfo[3 * r + 2] + dx;
-                            const bool ok = k_ok && r < rows && iy >= 0 && iy < p.im_h && ix >= 0 && ix < p.im_w;
-                            v[i] = ok ? __ldg(p.A + rinfo[3 * r] + delta) : 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int r = r0 + 4 * i;
-                            const float hi = sk_rna(v[i]);
-                            const uint32_t o = sk_swz(r, kk);
-                            *reinterpret_cast<float*>(sa + o) = hi;
-                            if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v[i] - hi;
-                        }
+                    // rows r = r0 + 4i: (r & 7) alternates between two values, so the swizzled offset is
+                    // r*128 + one of two per-thread constants
+                    const int r0 = t >> 5;
+                    const uint32_t cw = (uint32_t)((kk & 3) << 2);
+                    const uint32_t sw_a = ((uint32_t)(((kk >> 2) ^ (r0 & 7)) << 4)) | cw;
+                    const uint32_t sw_b = ((uint32_t)(((kk >> 2) ^ ((r0 + 4) & 7)) << 4)) | cw;
+                    const int rstride = p.str_w * p.chan;
+                    const bool linear = p.cv_rows == 1;                            // roff[r] == r * rstride
+#pragma unroll 8
+                    for (int i = 0; i < SKT_BM / 4; i++) {
+                        const int r = r0 + 4 * i;
+                        const int ro = linear ? r * rstride : roff[r];
+                        const float v = (k_ok && r < ti.nvalid) ? slab[ro + koff] : 0.f;
+                        const float hi = sk_rna(v);
+                        const uint32_t o = (uint32_t)(r << 7) + ((i & 1) ? sw_b : sw_a);
+                        *reinterpret_cast<float*>(sa + o) = hi;
+                        if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v - hi;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) sk_mbar_arrive(a_full(stage));
                     if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");                     // slab slot may be refilled now
+                slot_out = (slot_out + 1) % SKT_RAW_SLOTS;
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
             // generic: a warp reads one row's 32 k (coalesced 128 bytes), 8 rows in flight per thread
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -409,7 +466,9 @@ gemm_tf32_skinny_kernel(SktParams p)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
                 const int acc = it & 1;
                 if (p.epi_groups == 2 && acc != g) continue;
-                const int64_t row0 = (int64_t)tile * SKT_BM + q * 32;
+                const SktTile ti = skt_tile(p, tile);
+                const int64_t row0 = ti.m_start + q * 32;
+                const int vrows = ti.nvalid - q * 32;                 // valid rows among this warp's 32
                 sk_mbar_wait(t_full(acc), acc_phase);
                 // with one group both stages are drained by it (phase flips every second tile); with two
                 // groups each group sees only its own stage (phase flips every visit)
@@ -440,7 +499,7 @@ gemm_tf32_skinny_kernel(SktParams p)
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(t_empty(acc));
                 // transpose out of shared memory: consecutive lanes -> consecutive 16-byte pieces of a C row
-                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && row0 + 32 <= p.M &&
+                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && vrows >= 32 &&
                     (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
                     // fast path: full tile, no beta -- 4 independent LDS.128 / STG.128 pairs per step
                     float* cbase = p.C + (row0 + lr) * p.ldC + lc4 * 4;
@@ -467,7 +526,7 @@ gemm_tf32_skinny_kernel(SktParams p)
                         const int rr = idx / nv, c4 = idx - rr * nv;
                         const int64_t grow = row0 + rr;
                         const int col = c4 * 4;
-                        if (grow < p.M && col < p.N) {
+                        if (rr < vrows && col < p.N) {
                             float4 o = *reinterpret_cast<const float4*>(ebuf + rr * epi_pitch + col);
                             if (p.bias) {
                                 o.x += __ldg(p.bias + col);
@@ -539,6 +598,7 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
     p.alpha = alpha; p.beta = beta;
     p.A = A; p.ldA = ldA; p.B = B; p.ldB = ldB; p.C = C; p.ldC = ldC;
     p.conv = 0; p.bias = nullptr;
+    p.cv_tw = p.cv_rows = p.cv_col_blocks = p.cv_row_blocks = p.cv_slab_rows = p.cv_width_x = p.cv_row_elems = p.cv_slab_elems = 0;
     p.im_h = p.im_w = p.chan = p.filt_w = p.str_h = p.str_w = p.dil_h = p.dil_w = p.pad_h = p.pad_w = p.out_h = p.out_w = 0;
     p.num_tiles = (int)rb_ceil_div(M, SKT_BM);
     p.a_contig = (ldA == K) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((SKT_BM * K) % 4 == 0);
@@ -601,14 +661,41 @@ int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h,
     uint32_t cols = (uint32_t)(2 * planes * p.NP), pow2 = 32;
     while (pow2 < cols) pow2 <<= 1;
     p.tmem_cols = pow2;
-    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, 0) <= SKT_SMEM_LIMIT ? 2 : 1;
-    p.raw_slots = 0;
     p.conv = 1;
     p.bias = bias;
     p.im_h = (int)im_h; p.im_w = (int)im_w; p.chan = (int)channels; p.filt_w = (int)filter_w;
     p.str_h = (int)stride_h; p.str_w = (int)stride_w; p.dil_h = (int)dilation_h; p.dil_w = (int)dilation_w;
     p.pad_h = (int)pad_h; p.pad_w = (int)pad_w; p.out_h = (int)out_h; p.out_w = (int)out_w;
-    const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, 0);
+    // tiling: <= 128 cells per MMA tile, as a block of out columns of one out row (wide images) or as
+    // several whole out rows (narrow feature maps); the slab of inputs must fit one 16 KB ring slot
+    if (out_w >= SKT_BM) { p.cv_tw = SKT_BM; p.cv_rows = 1; }
+    else { p.cv_tw = (int)out_w; p.cv_rows = (int)(SKT_BM / out_w); if (p.cv_rows > out_h) p.cv_rows = (int)out_h; }
+    for (;;) {
+        p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
+        p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
+        p.cv_row_elems = p.cv_width_x * p.chan;
+        p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
+        if ((int64_t)p.cv_slab_elems * 4 <= SKT_RAW_STAGE) break;
+        if (p.cv_rows > 1) { p.cv_rows--; continue; }
+        if (p.cv_tw > 16) { p.cv_tw /= 2; continue; }
+        set_error("conv2d_forward: the input slab of one tile exceeds the staging ring (use im2col2d + gemm)");
+        return RB200_E_UNSUPPORTED;
+    }
+    p.cv_col_blocks = (int)rb_ceil_div(out_w, p.cv_tw);
+    p.cv_row_blocks = (int)rb_ceil_div(out_h, p.cv_rows);
+    const int64_t tiles = batches * p.cv_row_blocks * p.cv_col_blocks;
+    if (tiles > 0x7fffffffLL) {
+        set_error("conv2d_forward: problem too large for 32-bit tile indices");
+        return RB200_E_UNSUPPORTED;
+    }
+    p.num_tiles = (int)tiles;
+    p.raw_slots = SKT_RAW_SLOTS;
+    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT ? 2 : 1;
+    if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) {
+        set_error("conv2d_forward: shared memory budget exceeded for filters=%d, K=%d (use im2col2d + gemm)", p.N, p.K);
+        return RB200_E_UNSUPPORTED;
+    }
+    const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, p.raw_slots);
     static bool configured[3] = {false, false, false};
     if (!configured[planes]) {
         if (planes == 1) RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
