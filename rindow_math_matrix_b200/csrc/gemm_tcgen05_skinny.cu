@@ -10,11 +10,11 @@
 //   2 planes: hi = rna(x), lo = x - hi computed in registers while staging (no pre-pass); hi*hi goes to
 //             a "big" TMEM accumulator, hi*lo + lo*hi to a "small" one, summed in the epilogue.
 //
-// Persistent CTA per SM, 416 threads:
-//   warps 0-3 : producers -- coalesced global loads of the A tile (128 rows x 32 k), software 128-byte
+// Persistent CTA per SM, 544 threads:
+//   warps 0-7 : producers -- coalesced global loads of the A tile (128 rows x 32 k), software 128-byte
 //               swizzle into the K-major UMMA layout, fence.proxy.async, mbarrier arrive (2 stages)
-//   warp  4   : MMA issuer (one lane): tcgen05.mma M=128, N=NP, K=8; commits free A stages / publish TMEM
-//   warps 5-12: epilogue, two groups of four (group g drains accumulator stage g, tiles alternate) --
+//   warp  8   : MMA issuer (one lane): tcgen05.mma M=128, N=NP, K=8; commits free A stages / publish TMEM
+//   warps 9-16: epilogue, two groups of four (group g drains accumulator stage g, tiles alternate) --
 //               tcgen05.ld -> registers -> shared-memory transpose -> coalesced 128-bit stores
 // B (K x N, tiny) is staged once per CTA, transposed to K-major, all k-blocks resident.
 #include <cuda.h>
@@ -25,8 +25,11 @@ namespace {
 
 constexpr int SKT_BM = 128;
 constexpr int SKT_BK = 32;
-constexpr int SKT_THREADS = 416;                     // 4 producer + 1 MMA + 2 x 4 epilogue warps
-constexpr int SKT_PRODUCERS = 128;
+constexpr int SKT_PROD_WARPS = 8;                    // two producer warps per scheduler: a lone warp issues at ~0.3 IPC
+constexpr int SKT_PRODUCERS = SKT_PROD_WARPS * 32;
+constexpr int SKT_MMA_WARP = SKT_PROD_WARPS;
+constexpr int SKT_EPI_WARP0 = SKT_PROD_WARPS + 1;    // first of 2 x 4 epilogue warps; (warp & 3) covers the 4 TMEM lane quarters
+constexpr int SKT_THREADS = (SKT_PROD_WARPS + 1 + 8) * 32;   // 544
 constexpr int SKT_A_TILE = SKT_BM * SKT_BK * 4;      // 16 KB per plane per stage
 constexpr int SKT_STAGES = 2;
 constexpr int SKT_PREFETCH = 3;                      // raw A tiles in flight ahead of the one being staged
@@ -176,12 +179,12 @@ gemm_tf32_skinny_kernel(SktParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ACC_COLS = PLANES * p.NP;
 
-    if (warp == 4 && lane == 0) {
-        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), 4); sk_mbar_init(a_empty(s), 1); }
+    if (warp == SKT_MMA_WARP && lane == 0) {
+        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), SKT_PROD_WARPS); sk_mbar_init(a_empty(s), 1); }
         for (int a = 0; a < 2; a++) { sk_mbar_init(t_full(a), 1); sk_mbar_init(t_empty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == SKT_EPI_WARP0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(tmem_slot), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -206,9 +209,9 @@ gemm_tf32_skinny_kernel(SktParams p)
     sk_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    if (warp < 4) {
+    if (warp < SKT_PROD_WARPS) {
         // ===== producers =====
-        const int t = threadIdx.x;                                    // 0..127
+        const int t = threadIdx.x;                                    // 0..SKT_PRODUCERS-1
         int stage = 0; uint32_t phase = 0;
         if (p.a_contig && p.KB == 1) {
             // Each 128-row tile is rows*K contiguous floats.  They are brought into a raw shared-memory
@@ -300,14 +303,34 @@ gemm_tf32_skinny_kernel(SktParams p)
                 const int rr = p.cv_rows > 1 ? t / p.cv_tw : 0;
                 const int cc = t - rr * p.cv_tw;
                 roff[t] = rr * p.str_h * p.cv_row_elems + cc * p.str_w * p.chan;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(SKT_PRODUCERS) : "memory");
             }
             float* ring = reinterpret_cast<float*>(gen + off_raw);
-            auto issue_slab = [&](int tile, int slot) {
+            // tile -> (image, row block, column block) without divisions: tiles advance by gridDim.x, so the
+            // mixed-radix digits advance by constant amounts with carries
+            struct TileIter { int b, rb, cb; };
+            const int step = gridDim.x;
+            const int per_img = p.cv_row_blocks * p.cv_col_blocks;
+            const int st_b = step / per_img, st_q = step - st_b * per_img;
+            const int st_rb = st_q / p.cv_col_blocks, st_cb = st_q - st_rb * p.cv_col_blocks;
+            auto iter_init = [&](int tile) {
+                TileIter it;
+                it.b = tile / per_img;
+                const int q = tile - it.b * per_img;
+                it.rb = q / p.cv_col_blocks;
+                it.cb = q - it.rb * p.cv_col_blocks;
+                return it;
+            };
+            auto iter_next = [&](TileIter& it) {
+                it.cb += st_cb; it.rb += st_rb; it.b += st_b;
+                if (it.cb >= p.cv_col_blocks) { it.cb -= p.cv_col_blocks; it.rb++; }
+                if (it.rb >= p.cv_row_blocks) { it.rb -= p.cv_row_blocks; it.b++; }
+            };
+            auto issue_slab = [&](int tile, const TileIter& it, int slot) {
                 if (tile < p.num_tiles) {
-                    const SktTile ti = skt_tile(p, tile);
-                    const int x_start = ti.ox0 * p.str_w - p.pad_w, y_start = ti.oy0 * p.str_h - p.pad_h;
-                    const float* img_b = p.A + (int64_t)ti.b * p.im_h * p.im_w * p.chan;
+                    const int oy0 = it.rb * p.cv_rows, ox0 = it.cb * p.cv_tw;
+                    const int x_start = ox0 * p.str_w - p.pad_w, y_start = oy0 * p.str_h - p.pad_h;
+                    const float* img_b = p.A + (int64_t)it.b * p.im_h * p.im_w * p.chan;
                     const uint32_t dst0 = base + off_raw + (uint32_t)slot * SKT_RAW_STAGE;
                     float* dstg = ring + slot * (SKT_RAW_STAGE / 4);
                     // per slab row the in-image part is one index interval [lo, hi): no per-element division
@@ -319,63 +342,83 @@ gemm_tf32_skinny_kernel(SktParams p)
                         const float* src = img_b + ((int64_t)iy * p.im_w + x_start) * p.chan;
                         const uint32_t drow = dst0 + 4u * (uint32_t)(sl * p.cv_row_elems);
                         float* grow = dstg + sl * p.cv_row_elems;
-                        for (int idx = t; idx < p.cv_row_elems; idx += SKT_PRODUCERS) {
-                            if (row_ok && idx >= lo && idx < hi) {
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(drow + 4u * idx), "l"(src + idx) : "memory");
-                            } else {
-                                grow[idx] = 0.f;
+                        const bool vec = row_ok && lo == 0 &&
+                                         ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((drow & 15u) == 0);
+                        if (vec) {
+                            // 16-byte copies for the aligned in-image part, 4-byte copies / zeros for the rest
+                            const int nv4 = hi >> 2;
+                            for (int q4 = t; q4 < nv4; q4 += SKT_PRODUCERS) {
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(drow + 16u * q4), "l"(src + 4 * q4) : "memory");
+                            }
+                            for (int idx = (nv4 << 2) + t; idx < p.cv_row_elems; idx += SKT_PRODUCERS) {
+                                if (idx < hi) {
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(drow + 4u * idx), "l"(src + idx) : "memory");
+                                } else {
+                                    grow[idx] = 0.f;
+                                }
+                            }
+                        } else {
+                            for (int idx = t; idx < p.cv_row_elems; idx += SKT_PRODUCERS) {
+                                if (row_ok && idx >= lo && idx < hi) {
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(drow + 4u * idx), "l"(src + idx) : "memory");
+                                } else {
+                                    grow[idx] = 0.f;
+                                }
                             }
                         }
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            const int step = gridDim.x;
             int slot_in = 0;
+            TileIter it_in = iter_init(blockIdx.x);
 #pragma unroll
-            for (int d = 0; d < SKT_PREFETCH; d++) { issue_slab(blockIdx.x + d * step, slot_in); slot_in = (slot_in + 1) % SKT_RAW_SLOTS; }
+            for (int d = 0; d < SKT_PREFETCH; d++) {
+                issue_slab(blockIdx.x + d * step, it_in, slot_in);
+                iter_next(it_in);
+                slot_in = (slot_in + 1) % SKT_RAW_SLOTS;
+            }
             int slot_out = 0;
             const int kwc = p.filt_w * p.chan;
+            // this thread's column k = (ky,kx,c) of each k-block: fixed slab offset
+            const int kk = t & 31;
+            const int r0 = t >> 5;
+            const uint32_t swc = ((uint32_t)(((kk >> 2) ^ (r0 & 7)) << 4)) | (uint32_t)((kk & 3) << 2);
+            const int rstride = p.str_w * p.chan;
+            const bool linear = p.cv_rows == 1;                                    // roff[r] == r * rstride
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += step) {
-                issue_slab(tile + SKT_PREFETCH * step, slot_in);
+                issue_slab(tile + SKT_PREFETCH * step, it_in, slot_in);
+                iter_next(it_in);
                 slot_in = (slot_in + 1) % SKT_RAW_SLOTS;
                 asm volatile("cp.async.wait_group %0;" :: "n"(SKT_PREFETCH) : "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");                     // every producer's copies of this slab landed
-                const SktTile ti = skt_tile(p, tile);
+                asm volatile("bar.sync 1, %0;" :: "n"(SKT_PRODUCERS) : "memory");  // every producer's copies of this slab landed
                 const float* slab = ring + slot_out * (SKT_RAW_STAGE / 4);
                 for (int kb = 0; kb < p.KB; kb++) {
                     sk_mbar_wait(a_empty(stage), phase ^ 1);
                     uint8_t* sa = gen + stage * a_stage_bytes;
-                    const int kk = t & 31;
                     const int k = kb * 32 + kk;
-                    const int ky = k / kwc, rem = k - ky * kwc;
-                    const int kx = rem / p.chan, c = rem - kx * p.chan;
-                    const int koff = ky * p.dil_h * p.cv_row_elems + kx * p.dil_w * p.chan + c;
-                    const bool k_ok = k < p.K;
-                    // rows r = r0 + 4i: (r & 7) alternates between two values, so the swizzled offset is
-                    // r*128 + one of two per-thread constants
-                    const int r0 = t >> 5;
-                    const uint32_t cw = (uint32_t)((kk & 3) << 2);
-                    const uint32_t sw_a = ((uint32_t)(((kk >> 2) ^ (r0 & 7)) << 4)) | cw;
-                    const uint32_t sw_b = ((uint32_t)(((kk >> 2) ^ ((r0 + 4) & 7)) << 4)) | cw;
-                    const int rstride = p.str_w * p.chan;
-                    const bool linear = p.cv_rows == 1;                            // roff[r] == r * rstride
+                    if (k < p.K) {
+                        // columns k >= K keep the zeros of the one-time fill; rows past the tile's valid cells
+                        // get whatever the slab holds -- their accumulator rows are never stored
+                        const int ky = k / kwc, rem = k - ky * kwc;
+                        const int kx = rem / p.chan, c = rem - kx * p.chan;
+                        const float* sk = slab + ky * p.dil_h * p.cv_row_elems + kx * p.dil_w * p.chan + c;
 #pragma unroll 8
-                    for (int i = 0; i < SKT_BM / 4; i++) {
-                        const int r = r0 + 4 * i;
-                        const int ro = linear ? r * rstride : roff[r];
-                        const float v = (k_ok && r < ti.nvalid) ? slab[ro + koff] : 0.f;
-                        const float hi = sk_rna(v);
-                        const uint32_t o = (uint32_t)(r << 7) + ((i & 1) ? sw_b : sw_a);
-                        *reinterpret_cast<float*>(sa + o) = hi;
-                        if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v - hi;
+                        for (int i = 0; i < SKT_BM / SKT_PROD_WARPS; i++) {
+                            const int r = r0 + SKT_PROD_WARPS * i;
+                            const float v = sk[linear ? r * rstride : roff[r]];
+                            const float hi = sk_rna(v);
+                            const uint32_t o = (uint32_t)(r << 7) + swc;
+                            *reinterpret_cast<float*>(sa + o) = hi;
+                            if (PLANES == 2) *reinterpret_cast<float*>(sa + SKT_A_TILE + o) = v - hi;
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) sk_mbar_arrive(a_full(stage));
                     if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");                     // slab slot may be refilled now
+                asm volatile("bar.sync 1, %0;" :: "n"(SKT_PRODUCERS) : "memory");  // slab slot may be refilled now
                 slot_out = (slot_out + 1) % SKT_RAW_SLOTS;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -390,16 +433,16 @@ gemm_tf32_skinny_kernel(SktParams p)
                     const int kk = t & 31;
                     const int k = kb * 32 + kk;
                     const float* col = p.A + m0 * p.ldA + k;
-                    for (int r0 = t >> 5; r0 < SKT_BM; r0 += 32) {
+                    for (int r0 = t >> 5; r0 < SKT_BM; r0 += 8 * SKT_PROD_WARPS) {
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            const int r = r0 + 4 * i;
+                            const int r = r0 + SKT_PROD_WARPS * i;
                             v[i] = (r < rows && k < p.K) ? __ldcs(col + (int64_t)r * p.ldA) : 0.f;
                         }
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            const int r = r0 + 4 * i;
+                            const int r = r0 + SKT_PROD_WARPS * i;
                             const float hi = sk_rna(v[i]);
                             const uint32_t o = sk_swz(r, kk);
                             *reinterpret_cast<float*>(sa + o) = hi;
@@ -413,7 +456,7 @@ gemm_tf32_skinny_kernel(SktParams p)
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == SKT_MMA_WARP) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
@@ -451,10 +494,10 @@ gemm_tf32_skinny_kernel(SktParams p)
         }
     } else {
         // ===== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles alternate) =====
-        const int g = (warp - 5) >> 2;
+        const int g = (warp - SKT_EPI_WARP0) >> 2;
         if (g < p.epi_groups) {
             const int q = warp & 3;                                   // TMEM lane quarter of this warp
-            float* ebuf = reinterpret_cast<float*>(gen + off_epi) + (warp - 5) * 32 * epi_pitch;
+            float* ebuf = reinterpret_cast<float*>(gen + off_epi) + (warp - SKT_EPI_WARP0) * 32 * epi_pitch;
             const int nv = p.NP >> 2;                                 // float4 per row
             const bool c_vec = ((p.ldC & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
             // lane -> (row, 16-byte piece) map of the transposed store; loop invariant when nv divides 32
@@ -499,7 +542,9 @@ gemm_tf32_skinny_kernel(SktParams p)
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(t_empty(acc));
                 // transpose out of shared memory: consecutive lanes -> consecutive 16-byte pieces of a C row
-                if (inv && c_vec && p.NP == p.N && p.beta == 0.f && vrows >= 32 &&
+                if (vrows <= 0) {
+                    // this warp's 32 rows are all past the tile's valid cells
+                } else if (inv && c_vec && p.NP == p.N && p.beta == 0.f &&
                     (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
                     // fast path: full tile, no beta -- 4 independent LDS.128 / STG.128 pairs per step
                     float* cbase = p.C + (row0 + lr) * p.ldC + lc4 * 4;
@@ -515,7 +560,7 @@ gemm_tf32_skinny_kernel(SktParams p)
                         }
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            if (s0 + u < steps) {
+                            if (s0 + u < steps && lr + (s0 + u) * rstep < vrows) {
                                 o[u].x += bv.x; o[u].y += bv.y; o[u].z += bv.z; o[u].w += bv.w;
                                 __stcs(reinterpret_cast<float4*>(cbase + (int64_t)(s0 + u) * rstep * p.ldC), o[u]);
                             }
@@ -558,7 +603,7 @@ gemm_tf32_skinny_kernel(SktParams p)
 
     sk_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == SKT_EPI_WARP0) {
         sk_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }

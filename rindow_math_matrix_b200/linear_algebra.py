@@ -203,11 +203,14 @@ class LinearAlgebra:
         return images
 
     def conv2d(self, images: NDArray, kernel: NDArray, bias: NDArray | None = None, strides=None, padding=None,
-               dilation_rate=None) -> NDArray:
+               dilation_rate=None, fused: bool = False) -> NDArray:
         """Conv2D forward for channels-last images [b,h,w,c] and kernel [kh,kw,c,filters] -- the composition
         the reference's users write by hand (im2col :3369 -> reshape -> gemm :925 -> add :1968; the Conv2D
-        layer itself lives in rindow-neuralnetworks).  Uses the driver's fused entry when it has one for
-        this shape, otherwise exactly those three driver calls."""
+        layer itself lives in rindow-neuralnetworks).  Default: exactly those three driver calls (on the
+        B200 driver: tiled im2col2d + software-staged tcgen05 GEMM, 0.27 ms for BASELINE config C4).
+        fused=True asks for the driver's single-kernel implicit-GEMM entry (rb200_conv2d_forward: no cols
+        round trip; correct and tested, but in round 1 its producer is still issue-bound -- 0.41 ms -- so
+        it is opt-in) and falls back to the three calls when the driver has none for this shape."""
         if images.ndim() != 4 or kernel.ndim() != 4:
             raise InvalidArgumentException("images and kernel must be 4D dimension")
         batches, in_h, in_w, channels = images.shape()
@@ -226,8 +229,9 @@ class LinearAlgebra:
             raise InvalidArgumentException("Invalid shape or paramaters.")
         if bias is not None and bias.shape() != [filters]:
             raise InvalidArgumentException("Unmatch shape of bias and kernel")
-        fused = getattr(self.math, "conv2d_forward", None) if type(self.math).__name__ == "CudaMath" else None
-        if fused is not None:
+        fused_fn = getattr(self.math, "conv2d_forward", None) if (fused and type(self.math).__name__ == "CudaMath") else None
+        if fused_fn is not None:
+            fused = fused_fn
             out = self.alloc([batches, out_h, out_w, filters], dtype=images.dtype())
             if fused(images.buffer(), images.offset(), batches, in_h, in_w, channels, filter_h,
                                            filter_w, stride_h, stride_w, padding, dilation_h, dilation_w,

@@ -739,11 +739,13 @@ def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
     rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(mode))
     try:
         out = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st,
-                        padding=pad, dilation_rate=dil)
+                        padding=pad, dilation_rate=dil, fused=True)
+        path = rb._capi.last_gemm_path()
+        out2 = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st,
+                         padding=pad, dilation_rate=dil)                        # default: im2col -> gemm -> add
     finally:
         rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(rb.GEMM_TF32X3))
         cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
-    path = rb._capi.last_gemm_path()
     K = kh * kw * c
     if mode != rb.GEMM_FP32_SIMT and K <= 128 and f <= 64:
         assert path.endswith("_conv"), path          # wider filter banks may not fit the shared-memory budget
@@ -760,6 +762,9 @@ def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
     got = out.to_numpy().reshape(-1).astype(np.float64)
     err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
     assert err < GEMM_TOL[mode], (err, path)
+    got2 = out2.to_numpy().reshape(-1).astype(np.float64)
+    assert out2.shape() == out.shape()
+    assert np.max(np.abs(got2 - ref)) / np.max(np.abs(ref)) < GEMM_TOL[mode]
 
 
 # ---------------------------------------------------------------------------------------------------

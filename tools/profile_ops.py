@@ -44,14 +44,18 @@ def main():
               "reduce_argmax": lambda: math.reduceArgMax(m, n, 1, A, 0, Bi, 0),
               "reduce_sum_axis0": lambda: math.reduceSum(1, m, n, A, 0, Bf, 0),
               "softmax": lambda: math.softmax(m, n, A, 0, n)}[op]
-    elif op in ("im2col2d", "conv_gemm"):
+    elif op in ("im2col2d", "conv_gemm", "conv2d_fused"):
         b, h, w, c = 64, 224, 224, 3
         images = rnd(b * h * w * c)
         ncols = b * 222 * 222 * 27
         cols = CudaBuffer(ncols, f32, zero=False)
         im2col = lambda: math.im2col2d(False, images, 0, b * h * w * c, b, h, w, c, 3, 3, 1, 1, False, False, 1, 1,
                                        False, cols, 0, ncols)
-        if op == "im2col2d":
+        if op == "conv2d_fused":
+            M = b * 222 * 222
+            Wt, out = rnd(27 * 64), CudaBuffer(M * 64, f32, zero=False)
+            fn = lambda: math.conv2d_forward(images, 0, b, h, w, c, 3, 3, 1, 1, False, 1, 1, Wt, 0, 64, None, 0, out, 0)
+        elif op == "im2col2d":
             fn = im2col
         else:
             im2col()
