@@ -375,6 +375,32 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             log("cuBLAS TF32 context measurement failed:", e)
 
+    # ---- config C5: the sgemm sweep M=N=K in {1024 ... 16384} (tf32 and tf32x3), per GPU ------------------
+    sweep = {}
+    if not args.quick and not args.no_sweep:
+        for sz in (1024, 2048, 4096, 8192, 16384):
+            if sz == n:
+                sweep[str(sz)] = {"tf32_tflops": gemm_modes.get("tf32", {}).get("tflops_per_gpu"),
+                                  "tf32x3_tflops": gemm_modes.get("tf32x3", {}).get("tflops_per_gpu")}
+                continue
+            sa = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+            sb = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+            sc = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+            sa.fill(0.5); sb.fill(0.25)
+            row = {}
+            for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3)):
+                blas.setGemmMode(mm)
+                k = 20 if sz <= 4096 else 5
+
+                def sweep_step():
+                    blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, sz, sz, sz, 1.0, sa, 0, sz, sb, 0, sz, 0.0,
+                              sc, 0, sz)
+                ms = timed(sweep_step, k, 3) / k
+                row[name + "_tflops"] = 2.0 * sz ** 3 / (ms * 1e-3) / 1e12
+                row[name + "_ms"] = ms
+            sweep[str(sz)] = row
+            del sa, sb, sc
+
     # ---- HBM-bound configs (C2, C3, C4): rotating buffer sets defeat L2 --------------------------------
     hbm_ops = {}
     if not args.quick:
@@ -419,7 +445,8 @@ def run_b200(args):
                                            "fp32_simt": "f32"}[args.mode],
             "data": "synthetic", "config": workload_config(n, world, args.mode),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "hbm_ops": hbm_ops, "with_gather": with_gather,
+            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "sgemm_sweep": sweep, "hbm_ops": hbm_ops,
+            "with_gather": with_gather,
             "peaks": peaks,
         }
         emit(line)
@@ -469,7 +496,22 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
            {"shape": "[8192,4096] + [4096]"})
     report("multiply", lambda i: math.multiply(False, m, n, X, 0, 1, As[i], 0, n), ew_bytes,
            {"shape": "[8192,4096] * [4096]"})
-    del As
+    # section 8(f) widening on the same [8192,4096] operands: axpy / copy / gemv / transpose (omatcopy)
+    from rindow_math_matrix_b200 import BLAS as _B
+    blas1 = svc.blas()
+    Y2 = CudaBuffer(m * n, dtypes.float32, zero=False).from_numpy(a0)
+    report("axpy", lambda i: blas1.axpy(m * n, 0.5, As[i], 0, 1, Y2, 0, 1), 3 * m * n * 4, {"shape": "n=33554432"})
+    report("copy", lambda i: blas1.copy(m * n, As[i], 0, 1, Y2, 0, 1), 2 * m * n * 4, {"shape": "n=33554432"})
+    report("transpose", lambda i: blas1.omatcopy(_B.RowMajor, _B.Trans, m, n, 1.0, As[i], 0, n, Y2, 0, m),
+           2 * m * n * 4, {"shape": "[8192,4096] -> [4096,8192] (omatcopy)"})
+    Yv = CudaBuffer(m, dtypes.float32)
+    report("gemv", lambda i: blas1.gemv(_B.RowMajor, _B.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Yv, 0, 1),
+           m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096] x [4096]"})
+    Yt = CudaBuffer(n, dtypes.float32)
+    Xt = CudaBuffer(m, dtypes.float32, zero=False).from_numpy(rng.uniform(-1, 1, m).astype(np.float32))
+    report("gemv_trans", lambda i: blas1.gemv(_B.RowMajor, _B.Trans, m, n, 1.0, As[i], 0, n, Xt, 0, 1, 0.0, Yt, 0, 1),
+           m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096]^T x [8192]"})
+    del As, Y2
     # C3: reductions / softmax on f32 [65536,1024] axis=1
     m, n = 65536, 1024
     r0 = np.random.default_rng(3001 + rank).uniform(-1, 1, m * n).astype(np.float32)
@@ -538,6 +580,7 @@ def main():
     ap.add_argument("--mode", default="tf32", choices=["tf32", "tf32x3", "fp32_simt"])
     ap.add_argument("--quick", action="store_true", help="headline workload only (no hbm_ops / other modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the C5 size sweep")
     args = ap.parse_args()
     if args.warmup < 3:
         log("bench.py: raising --warmup to the required minimum of 3")

@@ -133,6 +133,22 @@ int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
                 const double* B, int64_t offB, int64_t ldB,
                 double beta, double* C, int64_t offC, int64_t ldC);
 
+/* ---- BLAS level 1 / 2: replace PhpBlas::scal (PhpBlas.php:141-161),
+ *      axpy (:165-194), copy (:350-364), gemv (:762-844).  float32 / float64. ------------------------------ */
+int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX);
+int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
+               void* Y, int64_t offY, int64_t incY);
+int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY);
+/* Y[rows] = alpha * op(A)[rows,cols] * X[cols] (+ beta*Y iff beta != 0); A is m x n row-major with ldA;
+ * trans: rows = n, cols = m. */
+int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+               const void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX,
+               double beta, void* Y, int64_t offY, int64_t incY);
+/* B[rows,cols] = alpha * op(A), A is m x n; replaces PhpBlas::omatcopy (PhpBlas.php:1550-1612), the transpose
+ * LinearAlgebra::transpose2D issues (LinearAlgebra.php:4520-4565). */
+int rb200_omatcopy(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+                   const void* A, int64_t offA, int64_t ldA, void* B, int64_t offB, int64_t ldB);
+
 /* ---- Math: replaces PhpMath::add / multiply (PhpMath.php:570-606 / 530-565) ---------- */
 /* trans==0: A[i,j] = alpha*X[j] + A[i,j]  (i<m, j<n, X has n elements)
  * trans!=0: A[i,j] = alpha*X[i] + A[i,j]  (X has m elements); A is m x n with row stride ldA */

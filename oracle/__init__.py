@@ -55,6 +55,11 @@ def lib() -> ctypes.CDLL:
         L.ro_gemm_rows.argtypes = [i64, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64]
         L.ro_gemm_rows_interleaved.argtypes = [i64, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64, p]
         L.ro_gemm3.argtypes = [i64, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64]
+        L.ro_scal.argtypes = [i64, dbl, p, i64, i64, i64]
+        L.ro_axpy.argtypes = [i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_copy.argtypes = [i64, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_gemv.argtypes = [i32, i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64, dbl, p, i64, i64, i64]
+        L.ro_omatcopy.argtypes = [i32, i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_add.argtypes = [i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_multiply.argtypes = [i32, i64, i64, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_reduce_sum.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64]
@@ -64,6 +69,7 @@ def lib() -> ctypes.CDLL:
         L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
         for name in ("ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+                     "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
             getattr(L, name).restype = ctypes.c_int
@@ -118,6 +124,29 @@ def gemm_rows_fast(row0, rows, n, k, alpha, A, ldA, B, ldB, beta, C, ldC):
 def gemm3(M, N, K, L, alpha, A, offA, B, offB, beta, C, offC):
     _check(lib().ro_gemm3(M, N, K, L, float(alpha), _ptr(_buf(A)), offA, _ptr(_buf(B)), offB,
                           float(beta), _ptr(_buf(C)), offC))
+
+
+# PhpBlas::scal / axpy / copy / gemv / omatcopy, PhpBlas.php:141-194, :350-364, :762-844, :1550-1612
+def scal(n, alpha, X, offX, incX):
+    _check(lib().ro_scal(n, float(alpha), _ptr(_buf(X)), X.size, offX, incX))
+
+
+def axpy(n, alpha, X, offX, incX, Y, offY, incY):
+    _check(lib().ro_axpy(n, float(alpha), _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+def copy(n, X, offX, incX, Y, offY, incY):
+    _check(lib().ro_copy(n, _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+def gemv(order, trans, m, n, alpha, A, offA, ldA, X, offX, incX, beta, Y, offY, incY):
+    _check(lib().ro_gemv(order, trans, m, n, float(alpha), _ptr(_buf(A)), A.size, offA, ldA,
+                         _ptr(_buf(X)), X.size, offX, incX, float(beta), _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+def omatcopy(order, trans, m, n, alpha, A, offA, ldA, B, offB, ldB):
+    _check(lib().ro_omatcopy(order, trans, m, n, float(alpha), _ptr(_buf(A)), A.size, offA, ldA,
+                             _ptr(_buf(B)), B.size, offB, ldB))
 
 
 # PhpMath::add, PhpMath.php:570-606

@@ -447,4 +447,83 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* ---- BLAS level 1 / 2 and omatcopy (SURVEY.md section 8f widening) ------------------------------- */
+
+/* PhpBlas::scal, PhpBlas.php:141-161 (real path :156-159): X[i] = X[i] * alpha */
+int ro_scal(int64_t n, double alpha, double *X, int64_t countX, int64_t offX, int64_t incX)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    for (int64_t i = 0, id = offX; i < n; i++, id += incX) X[id] = X[id] * alpha;
+    return RO_OK;
+}
+
+/* PhpBlas::axpy, PhpBlas.php:165-194: alpha == 1 adds, otherwise one mul + one add */
+int ro_axpy(int64_t n, double alpha, const double *X, int64_t countX, int64_t offX, int64_t incX,
+            double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    if (offY < 0 || incY < 1 || offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    int64_t ix = offX, iy = offY;
+    if (alpha == 1.0) { for (int64_t i = 0; i < n; i++, ix += incX, iy += incY) Y[iy] = X[ix] + Y[iy]; }
+    else { for (int64_t i = 0; i < n; i++, ix += incX, iy += incY) Y[iy] = alpha * X[ix] + Y[iy]; }
+    return RO_OK;
+}
+
+/* PhpBlas::copy, PhpBlas.php:350-364 */
+int ro_copy(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX,
+            double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    if (offY < 0 || incY < 1 || offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    for (int64_t i = 0, ix = offX, iy = offY; i < n; i++, ix += incX, iy += incY) Y[iy] = X[ix];
+    return RO_OK;
+}
+
+/* PhpBlas::gemv, PhpBlas.php:762-844 (real path :826-842): acc += (alpha*A)*X in index order, then
+ * Y = acc + beta*Y iff beta != 0.  order/trans are the CBLAS codes. */
+int ro_gemv(int order, int trans, int64_t m, int64_t n, double alpha,
+            const double *A, int64_t countA, int64_t offA, int64_t ldA,
+            const double *X, int64_t countX, int64_t offX, int64_t incX,
+            double beta, double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (order == 102) { int64_t t = m; m = n; n = t; } else if (order != 101) return RO_E_ARG;
+    int t;
+    if (trans == 111 || trans == 114) t = 0; else if (trans == 112 || trans == 113) t = 1; else return RO_E_ARG;
+    int64_t rows = !t ? m : n, cols = !t ? n : m;
+    if (m < 1 || n < 1) return RO_E_ARG;
+    if (offA < 0 || ldA < 1 || offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG;
+    if (offX < 0 || incX < 1 || offX + (cols - 1) * incX >= countX) return RO_E_ARG;
+    if (offY < 0 || incY < 1 || offY + (rows - 1) * incY >= countY) return RO_E_ARG;
+    int64_t ldA_i = !t ? ldA : 1, ldA_j = !t ? 1 : ldA;
+    int64_t idA_i = offA, idY = offY;
+    for (int64_t i = 0; i < rows; i++, idA_i += ldA_i, idY += incY) {
+        int64_t idA = idA_i, idX = offX;
+        double acc = 0.0;
+        for (int64_t j = 0; j < cols; j++, idA += ldA_j, idX += incX) acc += alpha * A[idA] * X[idX];
+        Y[idY] = (beta != 0.0) ? acc + beta * Y[idY] : acc;
+    }
+    return RO_OK;
+}
+
+/* PhpBlas::omatcopy, PhpBlas.php:1550-1612 (real path :1603-1610): B[i,j] = alpha * op(A)[i,j] */
+int ro_omatcopy(int order, int trans, int64_t m, int64_t n, double alpha,
+                const double *A, int64_t countA, int64_t offA, int64_t ldA,
+                double *B, int64_t countB, int64_t offB, int64_t ldB)
+{
+    if (order == 102) { int64_t t = m; m = n; n = t; } else if (order != 101) return RO_E_ARG;
+    int t;
+    if (trans == 111 || trans == 114) t = 0; else if (trans == 112 || trans == 113) t = 1; else return RO_E_ARG;
+    if (m < 1 || n < 1) return RO_E_ARG;
+    int64_t rows = !t ? m : n, cols = !t ? n : m;
+    if (offA < 0 || ldA < 1 || offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG;
+    if (offB < 0 || ldB < 1 || offB + (rows - 1) * ldB + (cols - 1) >= countB) return RO_E_ARG;
+    int64_t ldA_i = !t ? ldA : 1, ldA_j = !t ? 1 : ldA;
+    int64_t idA_i = offA, idB_i = offB;
+    for (int64_t i = 0; i < rows; i++, idA_i += ldA_i, idB_i += ldB) {
+        int64_t idA = idA_i, idB = idB_i;
+        for (int64_t j = 0; j < cols; j++, idA += ldA_j, idB++) B[idB] = alpha * A[idA];
+    }
+    return RO_OK;
+}
+
 int ro_abi_version(void) { return 1; }

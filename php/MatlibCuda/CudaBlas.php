@@ -10,9 +10,10 @@ use Rindow\Math\Matrix\Drivers\MatlibPHP\PhpBlas;
 use Rindow\Math\Matrix\Drivers\MatlibPHP\Utils;
 
 /**
- * blas() object of the B200 service.  gemm runs on the device; every other BLAS method is
- * inherited from PhpBlas and therefore runs on the host mirror of the CudaBuffer (ArrayAccess),
- * exactly as SURVEY.md section 8(b) prescribes for the rows marked "next".
+ * blas() object of the B200 service.  gemm, scal, axpy, copy, gemv and omatcopy run on the device for
+ * float32/float64 CudaBuffers; every other BLAS method (and every other dtype) is inherited from PhpBlas
+ * and therefore runs on the host mirror of the CudaBuffer (ArrayAccess), exactly as SURVEY.md section
+ * 8(b) prescribes for the rows marked "next".
  */
 class CudaBlas extends PhpBlas
 {
@@ -66,5 +67,101 @@ class CudaBlas extends PhpBlas
                 $ffi->cast('double*',$a),$offsetA,$ldA,$ffi->cast('double*',$b),$offsetB,$ldB,
                 $beta,$ffi->cast('double*',$c),$offsetC,$ldC));
         }
+    }
+
+    /** true when every buffer is a float32/float64 CudaBuffer, i.e. the call can stay on the device */
+    protected function onDevice(Buffer ...$buffers) : bool
+    {
+        foreach ($buffers as $b) {
+            if (!($b instanceof CudaBuffer)) return false;
+            if ($b->dtype() != NDArray::float32 && $b->dtype() != NDArray::float64) return false;
+        }
+        return true;
+    }
+
+    public function scal(int $n, float|object $alpha, Buffer $X, int $offsetX, int $incX) : void
+    {
+        if (!$this->onDevice($X)) { parent::scal($n,$alpha,$X,$offsetX,$incX); return; }
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $alpha = $this->cleanFloatNumber($alpha,'alpha');
+        CudaFFI::check(CudaFFI::lib()->rb200_scal($X->dtype(),$n,$alpha,$X->devicePtrRW(),$offsetX,$incX));
+    }
+
+    public function axpy(int $n, float|object $alpha,
+        Buffer $X, int $offsetX, int $incX, Buffer $Y, int $offsetY, int $incY) : void
+    {
+        if (!$this->onDevice($X,$Y) || $X->dtype()!=$Y->dtype()) {
+            parent::axpy($n,$alpha,$X,$offsetX,$incX,$Y,$offsetY,$incY); return;
+        }
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
+        $alpha = $this->cleanFloatNumber($alpha,'alpha');
+        CudaFFI::check(CudaFFI::lib()->rb200_axpy($X->dtype(),$n,$alpha,
+            $X->devicePtr(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    public function copy(int $n, Buffer $X, int $offsetX, int $incX, Buffer $Y, int $offsetY, int $incY) : void
+    {
+        if (!$this->onDevice($X,$Y) || $X->dtype()!=$Y->dtype()) {
+            parent::copy($n,$X,$offsetX,$incX,$Y,$offsetY,$incY); return;
+        }
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
+        CudaFFI::check(CudaFFI::lib()->rb200_copy($X->dtype(),$n,
+            $X->devicePtr(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    public function gemv(int $order, int $trans, int $m, int $n, float|object $alpha,
+        Buffer $A, int $offsetA, int $ldA, Buffer $X, int $offsetX, int $incX,
+        float|object $beta, Buffer $Y, int $offsetY, int $incY ) : void
+    {
+        if (!$this->onDevice($A,$X,$Y) || $A->dtype()!=$X->dtype() || $A->dtype()!=$Y->dtype()) {
+            parent::gemv($order,$trans,$m,$n,$alpha,$A,$offsetA,$ldA,$X,$offsetX,$incX,$beta,$Y,$offsetY,$incY);
+            return;
+        }
+        // same validation order as PhpBlas::gemv (PhpBlas.php:773-788)
+        if ($order == BLAS::ColMajor) {
+            [$m,$n] = [$n,$m];
+        } elseif ($order != BLAS::RowMajor) {
+            throw new InvalidArgumentException('Invalid Order type');
+        }
+        [$t,$conj] = $this->codeToTrans($trans);
+        $this->assertShapeParameter('m',$m);
+        $this->assertShapeParameter('n',$n);
+        $this->assertMatrixBufferSpec("A", $A, $m, $n, $offsetA, $ldA);
+        $this->assertVectorBufferSpec('X', $X, (!$t) ? $n : $m, $offsetX, $incX);
+        $this->assertVectorBufferSpec('Y', $Y, (!$t) ? $m : $n, $offsetY, $incY);
+        $alpha = $this->cleanFloatNumber($alpha,'alpha');
+        $beta = $this->cleanFloatNumber($beta,'beta');
+        CudaFFI::check(CudaFFI::lib()->rb200_gemv($A->dtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
+            $A->devicePtr(),$offsetA,$ldA,$X->devicePtr(),$offsetX,$incX,$beta,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    public function omatcopy(int $order, int $trans, int $m, int $n, float|object $alpha,
+        Buffer $A, int $offsetA, int $ldA, Buffer $B, int $offsetB, int $ldB) : void
+    {
+        if (!$this->onDevice($A,$B)) {
+            parent::omatcopy($order,$trans,$m,$n,$alpha,$A,$offsetA,$ldA,$B,$offsetB,$ldB); return;
+        }
+        // same validation order as PhpBlas::omatcopy (PhpBlas.php:1560-1577)
+        if ($order == BLAS::ColMajor) {
+            [$m,$n] = [$n,$m];
+        } elseif ($order != BLAS::RowMajor) {
+            throw new InvalidArgumentException('Invalid Order type');
+        }
+        [$t,$conj] = $this->codeToTrans($trans);
+        $this->assertShapeParameter('m',$m);
+        $this->assertShapeParameter('n',$n);
+        $this->assertMatrixBufferSpec("A", $A, $m, $n, $offsetA, $ldA);
+        $this->assertMatrixBufferSpec("B", $B, (!$t) ? $m : $n, (!$t) ? $n : $m, $offsetB, $ldB);
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException("Unmatch data type for A and B");
+        }
+        $alpha = $this->cleanFloatNumber($alpha,'alpha');
+        CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->dtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
+            $A->devicePtr(),$offsetA,$ldA,$B->devicePtrRW(),$offsetB,$ldB));
     }
 }

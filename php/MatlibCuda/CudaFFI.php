@@ -41,6 +41,16 @@ class CudaFFI
                         double alpha, const double* A, int64_t offA, int64_t ldA,
                         const double* B, int64_t offB, int64_t ldB,
                         double beta, double* C, int64_t offC, int64_t ldC);
+        int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX);
+        int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
+                       void* Y, int64_t offY, int64_t incY);
+        int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
+                       void* Y, int64_t offY, int64_t incY);
+        int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+                       const void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX,
+                       double beta, void* Y, int64_t offY, int64_t incY);
+        int rb200_omatcopy(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+                           const void* A, int64_t offA, int64_t ldA, void* B, int64_t offB, int64_t ldB);
         int rb200_add(int dtype, int trans, int64_t m, int64_t n, double alpha,
                       const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
         int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,

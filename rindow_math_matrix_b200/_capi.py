@@ -44,6 +44,11 @@ SIGNATURES = {
     "rb200_host_free": (i32, [vp]),
     "rb200_sgemm": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32]),
     "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
+    "rb200_scal": (i32, [i32, i64, f64, vp, i64, i64]),
+    "rb200_axpy": (i32, [i32, i64, f64, vp, i64, i64, vp, i64, i64]),
+    "rb200_copy": (i32, [i32, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_gemv": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
+    "rb200_omatcopy": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_add": (i32, [i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_multiply": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),
     "rb200_reduce_sum": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),

@@ -1,0 +1,327 @@
+// blas1.cu -- scal / axpy / copy (BLAS level 1) and gemv on the device (SURVEY.md section 8f, ranks 2-3:
+// the callers either side of the hot path -- MatrixOperator::op / the tests' equalTest use scal/axpy/copy,
+// MatrixOperator::cross with a rank-1 right operand uses gemv).
+//
+// Reference semantics (src/Drivers/MatlibPHP/PhpBlas.php): scal :141-161  X[i] = X[i]*alpha;
+// axpy :165-194  Y[i] = alpha*X[i] + Y[i];  copy :350-364  Y[i] = X[i];
+// gemv :762-844  Y[i] = sum_j (alpha*opA[i,j])*X[j] (+ beta*Y[i] iff beta != 0).  All HBM-bound:
+// 128-bit accesses when the increments are 1 and the operands 16-byte aligned, strided scalar otherwise.
+#include "common.cuh"
+
+namespace {
+
+constexpr int B1_THREADS = 256;
+enum { B1_SCAL = 0, B1_AXPY = 1, B1_COPY = 2 };
+
+template <typename T> union B1Pack { int4 raw; T v[16 / sizeof(T)]; };
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(B1_THREADS)
+blas1_vec_kernel(int64_t nvec, T alpha, const T* __restrict__ X, T* __restrict__ Y)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t stride = (int64_t)gridDim.x * B1_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x; i < nvec; i += stride) {
+        B1Pack<T> x, y;
+        if (OP != B1_SCAL) x.raw = __ldcs(reinterpret_cast<const int4*>(X) + i);
+        if (OP != B1_COPY) y.raw = __ldcs(reinterpret_cast<const int4*>(Y) + i);
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+            if (OP == B1_SCAL) y.v[e] = y.v[e] * alpha;
+            else if (OP == B1_AXPY) y.v[e] = fma(alpha, x.v[e], y.v[e]);
+            else y.v[e] = x.v[e];
+        }
+        __stcs(reinterpret_cast<int4*>(Y) + i, y.raw);
+    }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(B1_THREADS)
+blas1_strided_kernel(int64_t n, T alpha, const T* __restrict__ X, int64_t incX, T* __restrict__ Y, int64_t incY)
+{
+    const int64_t stride = (int64_t)gridDim.x * B1_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x; i < n; i += stride) {
+        T* y = Y + i * incY;
+        if (OP == B1_SCAL) *y = *y * alpha;
+        else if (OP == B1_AXPY) *y = fma(alpha, X[i * incX], *y);
+        else *y = X[i * incX];
+    }
+}
+
+template <typename T, int OP>
+int blas1_launch(int64_t n, double alpha_d, const void* Xv, int64_t offX, int64_t incX, void* Yv, int64_t offY, int64_t incY)
+{
+    rb200::Context& c = rb200::ctx();
+    const T* X = Xv ? reinterpret_cast<const T*>(Xv) + offX : nullptr;
+    T* Y = reinterpret_cast<T*>(Yv) + offY;
+    const T alpha = (T)alpha_d;
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) && (OP == B1_SCAL || (reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    const int64_t cap = (int64_t)c.sm_count * 16;
+    if (incY == 1 && (OP == B1_SCAL || incX == 1) && aligned && n >= V) {
+        const int64_t nvec = n / V;
+        int64_t grid = rb_ceil_div(nvec, B1_THREADS);
+        if (grid > cap) grid = cap;
+        blas1_vec_kernel<T, OP><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(nvec, alpha, X, Y);
+        RB_LAUNCH_CHECK("blas1_vec_kernel");
+        const int64_t done = nvec * V;
+        if (done < n) {
+            blas1_strided_kernel<T, OP><<<1, B1_THREADS, 0, c.stream>>>(n - done, alpha, X ? X + done : nullptr, 1, Y + done, 1);
+            RB_LAUNCH_CHECK("blas1_strided_kernel");
+        }
+        return RB200_OK;
+    }
+    int64_t grid = rb_ceil_div(n, B1_THREADS);
+    if (grid > cap) grid = cap;
+    blas1_strided_kernel<T, OP><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(n, alpha, X, incX, Y, incY);
+    RB_LAUNCH_CHECK("blas1_strided_kernel");
+    return RB200_OK;
+}
+
+template <int OP>
+int blas1_dispatch(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
+                   void* Y, int64_t offY, int64_t incY)
+{
+    RB_REQUIRE_INIT();
+    if (!Y || (OP != B1_SCAL && !X)) RB_INVALID("NULL buffer");
+    if (n < 1) RB_INVALID("Argument n must be greater than 0.");
+    if (incY < 1 || (OP != B1_SCAL && incX < 1) || offX < 0 || offY < 0) RB_INVALID("bad increment / offset");
+    switch (dtype) {
+        case RB200_FLOAT32: return blas1_launch<float, OP>(n, alpha, X, offX, incX, Y, offY, incY);
+        case RB200_FLOAT64: return blas1_launch<double, OP>(n, alpha, X, offX, incX, Y, offY, incY);
+        default: RB_UNSUPPORTED("blas level 1: unsupported dtype %d", dtype);
+    }
+}
+
+// ---- gemv -------------------------------------------------------------------------------------------
+// NoTrans: one warp per row of A (coalesced along the row, shuffle reduction).
+template <typename T>
+__global__ void __launch_bounds__(B1_THREADS)
+gemv_n_kernel(int64_t m, int64_t n, T alpha, const T* __restrict__ A, int64_t ldA,
+              const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (B1_THREADS / 32);
+    for (int64_t i = (int64_t)blockIdx.x * (B1_THREADS / 32) + (threadIdx.x >> 5); i < m; i += warps) {
+        const T* row = A + i * ldA;
+        T acc = (T)0;
+#pragma unroll 8
+        for (int64_t j = lane; j < n; j += 32) acc = fma(alpha * __ldcs(row + j), __ldg(X + j * incX), acc);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+            T* y = Y + i * incY;
+            *y = (beta == (T)0) ? acc : fma(beta, *y, acc);
+        }
+    }
+}
+
+// Trans: Y[j] = sum_i (alpha*A[i,j])*X[i]; thread (tx,ty): column j = blockIdx.x*32+tx, rows ty, ty+8, ... of
+// the row segment blockIdx.y (coalesced along j); shared-memory tree over ty.  With one segment the CTA
+// finishes Y itself, otherwise it writes a partial row into the workspace and gemv_t_merge_kernel adds the
+// segments in index order (deterministic, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(B1_THREADS)
+gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restrict__ A, int64_t ldA,
+              const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY, T* __restrict__ partial)
+{
+    __shared__ T sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    const int64_t i0 = (int64_t)blockIdx.y * seg_rows;
+    const int64_t i1 = (i0 + seg_rows < m) ? i0 + seg_rows : m;
+    T acc = (T)0;
+    if (j < n) {
+        const T* a = A + j;
+#pragma unroll 4
+        for (int64_t i = i0 + ty; i < i1; i += 8) acc = fma(alpha * __ldcs(a + i * ldA), __ldg(X + i * incX), acc);
+    }
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+        T s = sm[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; r++) s += sm[r][tx];
+        if (partial) partial[(int64_t)blockIdx.y * n + j] = s;
+        else {
+            T* y = Y + j * incY;
+            *y = (beta == (T)0) ? s : fma(beta, *y, s);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B1_THREADS)
+gemv_t_merge_kernel(int64_t n, int segs, const T* __restrict__ partial, T beta, T* __restrict__ Y, int64_t incY)
+{
+    const int64_t j = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x;
+    if (j >= n) return;
+    T s = partial[j];
+    for (int g = 1; g < segs; g++) s += partial[(int64_t)g * n + j];
+    T* y = Y + j * incY;
+    *y = (beta == (T)0) ? s : fma(beta, *y, s);
+}
+
+template <typename T>
+int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, int64_t offA, int64_t ldA,
+                const void* Xv, int64_t offX, int64_t incX, double beta, void* Yv, int64_t offY, int64_t incY)
+{
+    rb200::Context& c = rb200::ctx();
+    const T* A = reinterpret_cast<const T*>(Av) + offA;
+    const T* X = reinterpret_cast<const T*>(Xv) + offX;
+    T* Y = reinterpret_cast<T*>(Yv) + offY;
+    if (!trans) {
+        int64_t grid = rb_ceil_div(m, B1_THREADS / 32);
+        const int64_t cap = (int64_t)c.sm_count * 32;
+        if (grid > cap) grid = cap;
+        gemv_n_kernel<T><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
+        RB_LAUNCH_CHECK("gemv_n_kernel");
+    } else {
+        const int64_t gx = rb_ceil_div(n, 32);
+        if (gx > 0x7fffffffLL) RB_INVALID("gemv: n too large");
+        // row segments: enough CTAs for ~8 per SM, at least 64 rows each
+        int64_t segs = rb_ceil_div((int64_t)c.sm_count * 8, gx);
+        if (segs > m / 64) segs = m / 64;
+        if (segs < 1) segs = 1;
+        if (segs > 1024) segs = 1024;
+        const int64_t seg_rows = rb_ceil_div(m, segs);
+        segs = rb_ceil_div(m, seg_rows);
+        T* partial = nullptr;
+        if (segs > 1) {
+            int rc = rb200::ensure_workspace((size_t)segs * (size_t)n * sizeof(T));
+            if (rc != RB200_OK) return rc;
+            partial = reinterpret_cast<T*>(c.workspace);
+        }
+        gemv_t_kernel<T><<<dim3((unsigned)gx, (unsigned)segs), B1_THREADS, 0, c.stream>>>(
+            m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
+        RB_LAUNCH_CHECK("gemv_t_kernel");
+        if (segs > 1) {
+            gemv_t_merge_kernel<T><<<(unsigned)rb_ceil_div(n, B1_THREADS), B1_THREADS, 0, c.stream>>>(
+                n, (int)segs, partial, (T)beta, Y, incY);
+            RB_LAUNCH_CHECK("gemv_t_merge_kernel");
+        }
+    }
+    return RB200_OK;
+}
+
+// ---- omatcopy ---------------------------------------------------------------------------------------
+// B[rows,cols] = alpha * op(A); Trans goes through a 32x33 shared tile so both sides stay coalesced; each CTA
+// (32x8 threads) walks tiles in a grid-stride loop.
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(B1_THREADS)
+omatcopy_kernel(int64_t rows, int64_t cols, T alpha, const T* __restrict__ A, int64_t ldA, T* __restrict__ B, int64_t ldB)
+{
+    __shared__ T tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    for (int64_t t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+        const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+        if (TRANS) {
+            // A is cols x rows (row-major, ldA): read A[c0+.., r0+tx] coalesced along r
+#pragma unroll
+            for (int y = ty; y < 32; y += 8) {
+                const int64_t ar = c0 + y, ac = r0 + tx;
+                if (ar < cols && ac < rows) tile[y][tx] = __ldcs(A + ar * ldA + ac);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int y = ty; y < 32; y += 8) {
+                const int64_t br = r0 + y, bc = c0 + tx;
+                if (br < rows && bc < cols) __stcs(B + br * ldB + bc, alpha * tile[tx][y]);
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int y = ty; y < 32; y += 8) {
+                const int64_t br = r0 + y, bc = c0 + tx;
+                if (br < rows && bc < cols) __stcs(B + br * ldB + bc, alpha * __ldcs(A + br * ldA + bc));
+            }
+        }
+    }
+}
+
+template <typename T>
+int omatcopy_launch(bool trans, int64_t rows, int64_t cols, double alpha, const void* Av, int64_t offA, int64_t ldA,
+                    void* Bv, int64_t offB, int64_t ldB)
+{
+    rb200::Context& c = rb200::ctx();
+    const T* A = reinterpret_cast<const T*>(Av) + offA;
+    T* B = reinterpret_cast<T*>(Bv) + offB;
+    int64_t grid = rb_ceil_div(rows, 32) * rb_ceil_div(cols, 32);
+    const int64_t cap = (int64_t)c.sm_count * 32;
+    if (grid > cap) grid = cap;
+    if (trans) omatcopy_kernel<T, true><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(rows, cols, (T)alpha, A, ldA, B, ldB);
+    else omatcopy_kernel<T, false><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(rows, cols, (T)alpha, A, ldA, B, ldB);
+    RB_LAUNCH_CHECK("omatcopy_kernel");
+    return RB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX)
+{
+    return blas1_dispatch<B1_SCAL>(dtype, n, alpha, nullptr, 0, 1, X, offX, incX);
+}
+
+int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
+               void* Y, int64_t offY, int64_t incY)
+{
+    return blas1_dispatch<B1_AXPY>(dtype, n, alpha, X, offX, incX, Y, offY, incY);
+}
+
+int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY)
+{
+    return blas1_dispatch<B1_COPY>(dtype, n, 1.0, X, offX, incX, Y, offY, incY);
+}
+
+int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+               const void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX,
+               double beta, void* Y, int64_t offY, int64_t incY)
+{
+    RB_REQUIRE_INIT();
+    if (!A || !X || !Y) RB_INVALID("NULL buffer");
+    if (order == RB200_COL_MAJOR) { int64_t t = m; m = n; n = t; }
+    else if (order != RB200_ROW_MAJOR) RB_INVALID("Invalid Order type");
+    bool t;
+    switch (trans) {
+        case RB200_NO_TRANS: case RB200_CONJ_NO_TRANS: t = false; break;
+        case RB200_TRANS: case RB200_CONJ_TRANS: t = true; break;
+        default: RB_INVALID("Unknown Tranpose Code: %d", trans);
+    }
+    if (m < 1) RB_INVALID("Argument m must be greater than 0.");
+    if (n < 1) RB_INVALID("Argument n must be greater than 0.");
+    if (ldA < 1 || incX < 1 || incY < 1 || offA < 0 || offX < 0 || offY < 0) RB_INVALID("bad ld / increment / offset");
+    switch (dtype) {
+        case RB200_FLOAT32: return gemv_launch<float>(t, m, n, alpha, A, offA, ldA, X, offX, incX, beta, Y, offY, incY);
+        case RB200_FLOAT64: return gemv_launch<double>(t, m, n, alpha, A, offA, ldA, X, offX, incX, beta, Y, offY, incY);
+        default: RB_UNSUPPORTED("gemv: unsupported dtype %d", dtype);
+    }
+}
+
+int rb200_omatcopy(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
+                   const void* A, int64_t offA, int64_t ldA, void* B, int64_t offB, int64_t ldB)
+{
+    RB_REQUIRE_INIT();
+    if (!A || !B) RB_INVALID("NULL buffer");
+    if (order == RB200_COL_MAJOR) { int64_t t = m; m = n; n = t; }
+    else if (order != RB200_ROW_MAJOR) RB_INVALID("Invalid Order type");
+    bool t;
+    switch (trans) {
+        case RB200_NO_TRANS: case RB200_CONJ_NO_TRANS: t = false; break;
+        case RB200_TRANS: case RB200_CONJ_TRANS: t = true; break;
+        default: RB_INVALID("Unknown Tranpose Code: %d", trans);
+    }
+    if (m < 1) RB_INVALID("Argument m must be greater than 0.");
+    if (n < 1) RB_INVALID("Argument n must be greater than 0.");
+    if (ldA < 1 || ldB < 1 || offA < 0 || offB < 0) RB_INVALID("bad ld / offset");
+    const int64_t rows = t ? n : m, cols = t ? m : n;
+    switch (dtype) {
+        case RB200_FLOAT32: return omatcopy_launch<float>(t, rows, cols, alpha, A, offA, ldA, B, offB, ldB);
+        case RB200_FLOAT64: return omatcopy_launch<double>(t, rows, cols, alpha, A, offA, ldA, B, offB, ldB);
+        default: RB_UNSUPPORTED("omatcopy: unsupported dtype %d", dtype);
+    }
+}
+
+}  // extern "C"

@@ -2,9 +2,9 @@
 
 Same positional signatures, validation order and exception strings as PhpBlas
 (src/Drivers/MatlibPHP/PhpBlas.php) + the Utils trait (src/Drivers/MatlibPHP/Utils.php:30-65);
-the arithmetic runs in librindow_b200.so (rb200_sgemm / rb200_dgemm).  Only the hot-path
-method (gemm) is on the device in this round; the remaining BLAS methods raise -- the PHP shim
-delegates those to PhpBlas on the host mirror, this package has no CPU path.
+the arithmetic runs in librindow_b200.so.  On the device: gemm (the hot path, rb200_sgemm / rb200_dgemm)
+and the section 8(f) widening -- scal, axpy, copy, gemv, omatcopy.  The remaining BLAS methods raise: the
+PHP shim delegates those to PhpBlas on the host mirror, this package has no CPU path.
 """
 from __future__ import annotations
 
@@ -131,9 +131,102 @@ class CudaBlas:
             raise LogicException("CudaBlas::gemm supports float32/float64; the reference routes integer "
                                  "dtypes to the LV_BASIC PHP driver (MatrixOperator.php:225-231)")
 
+    # ---- helpers ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _clean_float(value, name):                                           # PhpBlas.php:133-139
+        try:
+            return float(value)
+        except (TypeError, ValueError):
+            raise RuntimeException("%s is not float" % name)
+
+    @staticmethod
+    def _device_buffers(**bufs):
+        for name, buf in bufs.items():
+            if not isinstance(buf, CudaBuffer):
+                raise InvalidArgumentException("buffer%s is not a CudaBuffer" % name)
+
+    @staticmethod
+    def _float_dtype(buf, op):
+        if buf.dtype() not in (dtypes.float32, dtypes.float64):
+            raise LogicException("CudaBlas::%s supports float32/float64; the reference routes integer "
+                                 "dtypes to the LV_BASIC PHP driver (MatrixOperator.php:225-231)" % op)
+        return buf.dtype()
+
+    # ---- scal (PhpBlas.php:141-161) ---------------------------------------------------------------------
+    def scal(self, n, alpha, X, offsetX, incX) -> None:
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        self._device_buffers(X=X)
+        alpha = self._clean_float(alpha, "alpha")
+        _capi.check(self._lib.rb200_scal(self._float_dtype(X, "scal"), n, alpha, X.device_ptr_rw(), offsetX, incX))
+
+    # ---- axpy (PhpBlas.php:165-194) ---------------------------------------------------------------------
+    def axpy(self, n, alpha, X, offsetX, incX, Y, offsetY, incY) -> None:
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        assert_vector_buffer_spec("Y", Y, n, offsetY, incY)
+        self._device_buffers(X=X, Y=Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        alpha = self._clean_float(alpha, "alpha")
+        _capi.check(self._lib.rb200_axpy(self._float_dtype(X, "axpy"), n, alpha, X.device_ptr(), offsetX, incX,
+                                         Y.device_ptr_rw(), offsetY, incY))
+
+    # ---- copy (PhpBlas.php:350-364) ---------------------------------------------------------------------
+    def copy(self, n, X, offsetX, incX, Y, offsetY, incY) -> None:
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        assert_vector_buffer_spec("Y", Y, n, offsetY, incY)
+        self._device_buffers(X=X, Y=Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        _capi.check(self._lib.rb200_copy(self._float_dtype(X, "copy"), n, X.device_ptr(), offsetX, incX,
+                                         Y.device_ptr_rw(), offsetY, incY))
+
+    # ---- gemv (PhpBlas.php:762-844) ---------------------------------------------------------------------
+    def gemv(self, order, trans, m, n, alpha, A, offsetA, ldA, X, offsetX, incX, beta, Y, offsetY, incY) -> None:
+        if order == BLAS.ColMajor:
+            m, n = n, m
+        elif order != BLAS.RowMajor:
+            raise InvalidArgumentException("Invalid Order type")
+        t, _ = code_to_trans(trans)
+        rows, cols = (m, n) if not t else (n, m)
+        assert_shape_parameter("m", m)
+        assert_shape_parameter("n", n)
+        assert_matrix_buffer_spec("A", A, m, n, offsetA, ldA)
+        assert_vector_buffer_spec("X", X, cols, offsetX, incX)
+        assert_vector_buffer_spec("Y", Y, rows, offsetY, incY)
+        self._device_buffers(A=A, X=X, Y=Y)
+        if not (A.dtype() == X.dtype() == Y.dtype()):
+            raise InvalidArgumentException("Unmatch data type for A, X and Y")
+        alpha = self._clean_float(alpha, "alpha")
+        beta = self._clean_float(beta, "beta")
+        _capi.check(self._lib.rb200_gemv(self._float_dtype(A, "gemv"), BLAS.RowMajor, trans, m, n, alpha,
+                                         A.device_ptr(), offsetA, ldA, X.device_ptr(), offsetX, incX, beta,
+                                         Y.device_ptr_rw(), offsetY, incY))
+
+    # ---- omatcopy (PhpBlas.php:1550-1612) ---------------------------------------------------------------
+    def omatcopy(self, order, trans, m, n, alpha, A, offsetA, ldA, B, offsetB, ldB) -> None:
+        if order == BLAS.ColMajor:
+            m, n = n, m
+        elif order != BLAS.RowMajor:
+            raise InvalidArgumentException("Invalid Order type")
+        t, _ = code_to_trans(trans)
+        assert_shape_parameter("m", m)
+        assert_shape_parameter("n", n)
+        rows, cols = (m, n) if not t else (n, m)
+        assert_matrix_buffer_spec("A", A, m, n, offsetA, ldA)
+        assert_matrix_buffer_spec("B", B, rows, cols, offsetB, ldB)
+        self._device_buffers(A=A, B=B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        alpha = self._clean_float(alpha, "alpha")
+        _capi.check(self._lib.rb200_omatcopy(self._float_dtype(A, "omatcopy"), BLAS.RowMajor, trans, m, n, alpha,
+                                             A.device_ptr(), offsetA, ldA, B.device_ptr_rw(), offsetB, ldB))
+
     def __getattr__(self, name):
-        if name in ("scal", "axpy", "dot", "dotu", "dotc", "asum", "iamax", "iamin", "copy", "nrm2", "rotg", "rot",
-                    "rotm", "rotmg", "swap", "gemv", "symm", "syrk", "syr2k", "trmm", "trsm", "omatcopy"):
+        if name in ("dot", "dotu", "dotc", "asum", "iamax", "iamin", "nrm2", "rotg", "rot",
+                    "rotm", "rotmg", "swap", "symm", "syrk", "syr2k", "trmm", "trsm"):
             def _not_on_device(*a, **k):
                 raise LogicException("CudaBlas::%s is not on the B200 hot path (SURVEY.md section 8f); the PHP "
                                      "shim delegates it to PhpBlas, this package has no CPU fallback" % name)

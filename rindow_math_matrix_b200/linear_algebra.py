@@ -3,7 +3,9 @@
 Mirror of the hot-path callers of Rindow\\Math\\Matrix\\LinearAlgebra (src/LinearAlgebra.php):
 shape checks -> (m,n,k,ld,offset) -> one positional driver call, with the reference's exception
 strings.  gemm :925-995, add :1968-2016, multiply :1921-1963, softmax :3138-3156,
-reduceSum/Max/ArgMax :3161-3336, im2col :3369, col2im :3434, im2col2d :3597-3701, plus the
+reduceSum/Max/ArgMax :3161-3336, im2col :3369, col2im :3434, im2col2d :3597-3701, the section 8(f)
+widening (copy/scal/axpy :312-371, gemv :861-923, matmul :1000-1110, omatcopy :1443-1500, 2-D transpose
+:4438-4565), plus the
 array/alloc/zeros/ones/fill plumbing those need (:193-330, :4662).  It is driver-agnostic, exactly
 like the PHP class: everything numeric goes through service.blas() / service.math().
 """
@@ -13,7 +15,7 @@ import numpy as np
 
 from . import dtypes
 from .cuda_blas import BLAS
-from .exceptions import InvalidArgumentException
+from .exceptions import InvalidArgumentException, LogicException
 from .ndarray import NDArray
 from .service import Service
 
@@ -65,6 +67,157 @@ class LinearAlgebra:
 
     def zerosLike(self, X: NDArray) -> NDArray:
         return self.zeros(self.alloc(X.shape(), X.dtype()))
+
+    # ---- BLAS level 1 mirrors (LinearAlgebra.php:312-371) ----------------------------------------------
+    @staticmethod
+    def _shape_error(X: NDArray, Y: NDArray) -> str:
+        return "Unmatch shape of dimension: (%s),(%s)" % (",".join(map(str, X.shape())), ",".join(map(str, Y.shape())))
+
+    def copy(self, X: NDArray, Y: NDArray | None = None) -> NDArray:            # LinearAlgebra.php:312-331
+        if Y is None:
+            Y = self.alloc(X.shape(), dtype=X.dtype())
+        elif X.shape() != Y.shape():
+            raise InvalidArgumentException(self._shape_error(X, Y))
+        self.blas.copy(X.size(), X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    def scal(self, alpha, X: NDArray) -> NDArray:                               # LinearAlgebra.php:336-345
+        self.blas.scal(X.size(), alpha, X.buffer(), X.offset(), 1)
+        return X
+
+    def axpy(self, X: NDArray, Y: NDArray, alpha=None) -> NDArray:              # LinearAlgebra.php:350-371
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException(self._shape_error(X, Y))
+        if alpha is None:
+            alpha = 1.0
+        self.blas.axpy(X.size(), alpha, X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    # ---- y := alpha * Ax + beta * y   (LinearAlgebra.php:861-923) -------------------------------------
+    def gemv(self, A: NDArray, X: NDArray, alpha=None, beta=None, Y: NDArray | None = None,
+             trans=None, conj=None) -> NDArray:
+        trans = bool(trans)
+        if A.ndim() != 2 or X.ndim() != 1:
+            raise InvalidArgumentException('"A" must be 2D-NDArray and "X" must 1D-NDArray.')
+        shapeA = A.shape()
+        rows, cols = (shapeA[0], shapeA[1]) if not trans else (shapeA[1], shapeA[0])
+        if cols != X.shape()[0]:
+            raise InvalidArgumentException(
+                'The number of columns in "A" and The number of item in "X" must be the same')
+        m, n = shapeA
+        if alpha is None:
+            alpha = 1.0
+        if beta is None:
+            beta = 0.0
+        if Y is not None:
+            if Y.ndim() != 1:
+                raise InvalidArgumentException('"Y" must 1D-NDArray.')
+            if rows != Y.shape()[0]:
+                raise InvalidArgumentException(
+                    'The number of rows in "A" and The number of item in "Y" must be the same')
+        else:
+            Y = self.zeros(self.alloc([rows], dtype=X.dtype()))
+        self.blas.gemv(BLAS.RowMajor, BLAS.Trans if trans else BLAS.NoTrans, m, n, alpha,
+                       A.buffer(), A.offset(), n, X.buffer(), X.offset(), 1, beta, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    # ---- batched C := alpha * AB + beta * C with batch broadcast (LinearAlgebra.php:1000-1110) ----------
+    def matmul(self, A: NDArray, B: NDArray, transA=None, transB=None, C: NDArray | None = None,
+               alpha=None, beta=None) -> NDArray:
+        transA, transB = bool(transA), bool(transB)
+        shapes = "[%s]<=>[%s]" % (",".join(map(str, A.shape())), ",".join(map(str, B.shape())))
+        if A.ndim() < 2 or B.ndim() < 2:
+            raise InvalidArgumentException("Dimensions rank must be greater then 2D or equal:" + shapes)
+        shapeA, shapeB = A.shape(), B.shape()
+        shapeEA, shapeA = shapeA[-2:], shapeA[:-2]
+        shapeEB, shapeB = shapeB[-2:], shapeB[:-2]
+        batchA = int(np.prod(shapeA, dtype=np.int64)) if shapeA else 1
+        batchB = int(np.prod(shapeB, dtype=np.int64)) if shapeB else 1
+        if transA:
+            shapeEA = shapeEA[::-1]
+        if transB:
+            shapeEB = shapeEB[::-1]
+        if shapeEA[1] != shapeEB[0]:
+            raise InvalidArgumentException(
+                'The number of columns in "A" and the number of rows in "B" must be the same:' + shapes)
+        M, N, K = shapeEA[0], shapeEB[1], shapeEA[1]
+        if alpha is None:
+            alpha = 1.0
+        if beta is None:
+            beta = 0.0
+        lda = M if transA else K
+        ldb = K if transB else N
+        ldc = N
+        shapeEC = [M, N]
+        if batchA > batchB:
+            dest, base, orgShapeC = batchA, batchB, shapeA + shapeEC
+        else:
+            dest, base, orgShapeC = batchB, batchA, shapeB + shapeEC
+        if dest % base != 0:
+            raise InvalidArgumentException("Matrix size-incompatible for broadcast:" + shapes)
+        if C is not None:
+            if C.shape() != orgShapeC:
+                raise InvalidArgumentException(
+                    '"A" and "C" must have the same number of rows."B" and "C" must have the same number of '
+                    'columns:[%s] , [%s] => [%s]' % (",".join(map(str, A.shape())), ",".join(map(str, B.shape())),
+                                                     ",".join(map(str, C.shape()))))
+        else:
+            C = self.zeros(self.alloc(orgShapeC, dtype=A.dtype()))
+        tA = BLAS.Trans if transA else BLAS.NoTrans
+        tB = BLAS.Trans if transB else BLAS.NoTrans
+        offA, offB, offC = A.offset(), B.offset(), C.offset()
+        for _ in range(dest // base):
+            if batchA > batchB:
+                offB = B.offset()
+            else:
+                offA = A.offset()
+            for _ in range(base):
+                self.blas.gemm(BLAS.RowMajor, tA, tB, M, N, K, alpha, A.buffer(), offA, lda,
+                               B.buffer(), offB, ldb, beta, C.buffer(), offC, ldc)
+                offA += M * K
+                offB += N * K
+                offC += M * N
+        return C
+
+    # ---- B := alpha * op(A)   (LinearAlgebra.php:1443-1500) ----------------------------------------------
+    def omatcopy(self, A: NDArray, trans=None, conj=None, alpha=None, B: NDArray | None = None) -> NDArray:
+        trans = bool(trans)
+        if A.ndim() != 2:
+            raise InvalidArgumentException("Dimensions must be 2D-NDArray")
+        rows, cols = A.shape()
+        if trans:
+            rows, cols = cols, rows
+        if B is None:
+            B = self.zeros(self.alloc([rows, cols], dtype=A.dtype()))
+        elif B.shape() != [rows, cols]:
+            raise InvalidArgumentException(self._shape_error(A, B))
+        M, N = A.shape()
+        if alpha is None:
+            alpha = 1.0
+        self.blas.omatcopy(BLAS.RowMajor, BLAS.Trans if trans else BLAS.NoTrans, M, N, alpha,
+                           A.buffer(), A.offset(), N, B.buffer(), B.offset(), cols)
+        return B
+
+    # ---- 2-D float transpose (LinearAlgebra.php:4438-4465 -> transpose2D :4520-4565) -----------------------
+    def transpose(self, A: NDArray, perm=None, B: NDArray | None = None) -> NDArray:
+        if A.ndim() < 1:
+            raise InvalidArgumentException("input array must be grator than or equal 1D.")
+        if not (A.ndim() == 2 and A.dtype() in (dtypes.float32, dtypes.float64)):
+            raise LogicException("transposeND (math->transpose) is outside the B200 path (SURVEY.md section 8f)")
+        if perm is not None and len(perm) and len(perm) != 2:
+            raise InvalidArgumentException("unmatch sourceshape and perm")
+        shape = A.shape()[::-1]
+        if B is None:
+            B = self.alloc(shape, dtype=A.dtype())
+        else:
+            if B.shape() != shape:
+                raise InvalidArgumentException("output shape must be transpose matrix of input.")
+            if B.dtype() != A.dtype():
+                raise InvalidArgumentException("output data type must be same with matrix of input.")
+        m, n = shape[1], shape[0]
+        self.blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A.buffer(), A.offset(), n,
+                           B.buffer(), B.offset(), m)
+        return B
 
     # ---- C := alpha * AB + beta * C   (LinearAlgebra.php:925-995) -----------------------------------
     def gemm(self, A: NDArray, B: NDArray, alpha=None, beta=None, C: NDArray | None = None,

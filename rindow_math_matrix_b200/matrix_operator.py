@@ -68,7 +68,32 @@ class MatrixOperator:
     def cross(self, A: NDArray, B: NDArray) -> NDArray:                   # MatrixOperator.php:429-440
         if A.ndim() >= 2 and B.ndim() >= 2:
             return self.matrixMultiply(A, B)
-        raise InvalidArgumentException("unmatch shape of dimension")      # vectorTransform: SURVEY 8(f) rank 3
+        if A.ndim() >= 2 and B.ndim() == 1:
+            return self.vectorTransform(A, B)
+        raise InvalidArgumentException("unmatch shape of dimension")
+
+    def vectorTransform(self, A: NDArray, B: NDArray) -> NDArray:         # MatrixOperator.php:531-582
+        shapeA = A.shape()
+        batchSize = 1
+        while len(shapeA) > 2:
+            batchSize *= shapeA.pop(0)
+        shapeC = A.shape()[:-1]
+        C = self.zeros(shapeC, A.dtype())
+        sizeA = A.size() // batchSize
+        sizeC = C.size() // batchSize
+        aM, aN = shapeA
+        if aN != B.shape()[0]:
+            raise InvalidArgumentException("unmatch shape of dimension")
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("unmatch value type: %s and %s" % (A.dtype(), B.dtype()))
+        offA, offC = A.offset(), C.offset()
+        blas = self.getBlas(A.dtype())
+        for _ in range(batchSize):
+            blas.gemv(BLAS.RowMajor, BLAS.NoTrans, aM, aN, 1.0, A.buffer(), offA, aN,
+                      B.buffer(), B.offset(), 1, 1.0, C.buffer(), offC, 1)
+            offA += sizeA
+            offC += sizeC
+        return C
 
     def matrixMultiply(self, A: NDArray, B: NDArray) -> NDArray:          # MatrixOperator.php:442-508
         multiA = multiB = 1

@@ -82,6 +82,36 @@ def run_case(case, service):
             return getattr(la, op)(x, **kw)
         if op == "softmax":
             return la.softmax(la.array(_arr(case["x"])))
+        if op == "scal":
+            x = la.array(_arr(case["x"]))
+            out = la.scal(case["alpha"], x)
+            assert out is x
+            return out
+        if op == "axpy":
+            x, y = la.array(_arr(case["x"])), la.array(_arr(case["y"]))
+            x0 = x.toArray()
+            out = la.axpy(x, y, case.get("alpha"))
+            assert out is y and x.toArray() == x0
+            return out
+        if op == "copy":
+            x = la.array(_arr(case["x"]))
+            if case.get("into"):
+                y = la.zerosLike(x)
+                out = la.copy(x, y)
+                assert out is y
+            else:
+                out = la.copy(x)
+            assert out.shape() == x.shape() and out.dtype() == x.dtype()
+            return out
+        if op == "gemv":
+            A, X = la.array(_arr(case["A"])), la.array(_arr(case["X"]))
+            return la.gemv(A, X, **kw)
+        if op == "matmul":
+            A, B = la.array(_arr(case["A"])), la.array(_arr(case["B"]))
+            C = la.zeros(la.alloc(case["C_zeros"])) if "C_zeros" in case else None
+            return la.matmul(A, B, C=C, **kw)
+        if op == "transpose":
+            return la.transpose(la.array(_arr(case["x"])))
         raise AssertionError("unknown op " + op)
 
     if "error" in case:

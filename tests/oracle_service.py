@@ -74,6 +74,23 @@ class OracleBlas:
               beta, C.f64(), offC, ldC)
 
 
+    def scal(self, n, alpha, X, offX, incX):
+        _wrap(oracle.scal, n, alpha, X.f64(), offX, incX)
+
+    def axpy(self, n, alpha, X, offX, incX, Y, offY, incY):
+        _wrap(oracle.axpy, n, alpha, X.f64(), offX, incX, Y.f64(), offY, incY)
+
+    def copy(self, n, X, offX, incX, Y, offY, incY):
+        _wrap(oracle.copy, n, X.f64(), offX, incX, Y.f64(), offY, incY)
+
+    def gemv(self, order, trans, m, n, alpha, A, offA, ldA, X, offX, incX, beta, Y, offY, incY):
+        _wrap(oracle.gemv, order, trans, m, n, alpha, A.f64(), offA, ldA, X.f64(), offX, incX,
+              beta, Y.f64(), offY, incY)
+
+    def omatcopy(self, order, trans, m, n, alpha, A, offA, ldA, B, offB, ldB):
+        _wrap(oracle.omatcopy, order, trans, m, n, alpha, A.f64(), offA, ldA, B.f64(), offB, ldB)
+
+
 class OracleMath:
     sticky_max = False      # False: PhpMath::math_max rule; True: the accelerated-path rule
 

@@ -1,0 +1,187 @@
+"""Parity of the section 8(f) widening -- scal / axpy / copy / gemv / omatcopy / matmul / vectorTransform --
+through the C ABI against the CPU oracle.  pytest -m gpu
+
+Tolerances: copy and omatcopy with alpha == 1 are bit-exact (pure data movement); scal, omatcopy with
+alpha != 1 and axpy with |alpha| == 1 are one correctly-rounded float op, bit-exact against the oracle's
+double result rounded once; axpy with another alpha: 2*eps*(|alpha*x| + |y|) (the device fuses mul+add);
+gemv: the reference isclose bound 1e-7 + 1e-4*max|ref| with the measured-tight bound asserted next to it.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import rindow_math_matrix_b200 as rb
+from rindow_math_matrix_b200 import BLAS, CudaBuffer, InvalidArgumentException, LinearAlgebra, MatrixOperator, dtypes
+
+pytestmark = pytest.mark.gpu
+
+NP = {dtypes.float32: np.float32, dtypes.float64: np.float64}
+VEC = [(1, 1, 1, 0, 0), (7, 1, 1, 0, 0), (1000, 1, 1, 0, 0), (1000, 1, 1, 3, 5), (4096, 1, 1, 4, 8),
+       (333, 2, 3, 1, 2), (100003, 1, 1, 0, 0), (1 << 20, 1, 1, 0, 0), (65537, 3, 1, 2, 0)]
+
+
+def buf(a, dt):
+    a = np.asarray(a)
+    return CudaBuffer(a.size, dt).from_numpy(a.reshape(-1))
+
+
+def _vec(rng, n, inc, off, npdt):
+    return rng.standard_normal(off + (n - 1) * inc + 1 + 3).astype(npdt)
+
+
+@pytest.mark.parametrize("n,incX,incY,offX,offY", VEC, ids=[str(v) for v in VEC])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_copy_scal_axpy_vs_oracle(n, incX, incY, offX, offY, dt, cuda_service):
+    rng = np.random.default_rng(n + incX)
+    npdt = NP[dt]
+    blas = cuda_service.blas()
+    eps = np.finfo(npdt).eps
+    x, y = _vec(rng, n, incX, offX, npdt), _vec(rng, n, incY, offY, npdt)
+    # copy: bit-exact, untouched elements stay
+    X, Y = buf(x, dt), buf(y, dt)
+    blas.copy(n, X, offX, incX, Y, offY, incY)
+    ref = oracle.as_buffer(y)
+    oracle.copy(n, oracle.as_buffer(x), offX, incX, ref, offY, incY)
+    assert np.array_equal(Y.to_numpy(), ref.astype(npdt))
+    assert np.array_equal(X.to_numpy(), x)
+    # scal: one rounded multiply
+    X = buf(x, dt)
+    blas.scal(n, 0.37, X, offX, incX)
+    ref = oracle.as_buffer(x)
+    oracle.scal(n, float(npdt(0.37)), ref, offX, incX)
+    assert np.array_equal(X.to_numpy(), ref.astype(npdt))
+    # axpy
+    for alpha in (1.0, -1.0, 0.3):
+        X, Y = buf(x, dt), buf(y, dt)
+        blas.axpy(n, alpha, X, offX, incX, Y, offY, incY)
+        ref = oracle.as_buffer(y)
+        oracle.axpy(n, float(npdt(alpha)), oracle.as_buffer(x), offX, incX, ref, offY, incY)
+        got = Y.to_numpy().astype(np.float64)
+        if abs(alpha) == 1.0 and dt == dtypes.float32:
+            assert np.array_equal(got, ref.astype(npdt).astype(np.float64))
+        else:
+            xs = np.zeros_like(ref)
+            xs[offY:offY + (n - 1) * incY + 1:incY] = np.abs(alpha * x[offX:offX + (n - 1) * incX + 1:incX])
+            assert np.all(np.abs(got - ref) <= 2 * eps * (xs + np.abs(y.astype(np.float64))) + 1e-300)
+
+
+GEMV = [(1, 1, 0, 0), (2, 3, 0, 0), (64, 64, 0, 0), (257, 1023, 5, 3), (1000, 33, 0, 2), (33, 5000, 7, 0),
+        (4096, 4096, 0, 0), (3, 100000, 0, 0), (100000, 3, 1, 0)]
+
+
+@pytest.mark.parametrize("m,n,ld_extra,off", GEMV, ids=[str(v) for v in GEMV])
+@pytest.mark.parametrize("trans", [BLAS.NoTrans, BLAS.Trans])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_gemv_vs_oracle(m, n, ld_extra, off, trans, dt, cuda_service):
+    rng = np.random.default_rng(m * 31 + n)
+    npdt = NP[dt]
+    blas = cuda_service.blas()
+    ld = n + ld_extra
+    a = rng.standard_normal(off + m * ld).astype(npdt)
+    rows, cols = (m, n) if trans == BLAS.NoTrans else (n, m)
+    incX, incY = (1, 1) if m * n > 10000 else (2, 3)
+    x = rng.standard_normal(1 + (cols - 1) * incX + 1).astype(npdt)
+    y = rng.standard_normal(2 + (rows - 1) * incY + 1).astype(npdt)
+    for alpha, beta in ((1.0, 0.0), (0.5, 1.0), (-1.25, 0.75)):
+        A, X, Y = buf(a, dt), buf(x, dt), buf(y, dt)
+        blas.gemv(BLAS.RowMajor, trans, m, n, alpha, A, off, ld, X, 1, incX, beta, Y, 2, incY)
+        ref = oracle.as_buffer(y)
+        oracle.gemv(BLAS.RowMajor, trans, m, n, alpha, oracle.as_buffer(a), off, ld, oracle.as_buffer(x), 1, incX,
+                    beta, ref, 2, incY)
+        got = Y.to_numpy().astype(np.float64)
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) < 1e-7 + 1e-4 * scale                  # reference isclose
+        tight = (4e-6 if dt == dtypes.float32 else 1e-13) * max(scale, 1.0)
+        assert np.max(np.abs(got - ref)) < tight
+        # elements between the strides are untouched
+        mask = np.ones(y.size, bool)
+        mask[2:2 + (rows - 1) * incY + 1:incY] = False
+        assert np.array_equal(Y.to_numpy()[mask], y[mask])
+
+
+def test_gemv_beta_zero_ignores_nan_and_colmajor(cuda_service):
+    blas = cuda_service.blas()
+    a = np.arange(6, dtype=np.float32) + 1                                        # [[1,2,3],[4,5,6]]
+    A, X = buf(a, dtypes.float32), buf(np.array([100, 10, 1], np.float32), dtypes.float32)
+    Y = buf(np.full(2, np.nan, np.float32), dtypes.float32)
+    blas.gemv(BLAS.RowMajor, BLAS.NoTrans, 2, 3, 1.0, A, 0, 3, X, 0, 1, 0.0, Y, 0, 1)
+    assert Y.to_numpy().tolist() == [123.0, 456.0]
+    # ColMajor swaps m,n before anything else (PhpBlas.php:773-775): the 2x3 row-major A is a 3x2 col-major one
+    Y = buf(np.zeros(2, np.float32), dtypes.float32)
+    blas.gemv(BLAS.ColMajor, BLAS.NoTrans, 3, 2, 1.0, A, 0, 3, X, 0, 1, 0.0, Y, 0, 1)
+    ref = np.zeros(2)
+    oracle.gemv(BLAS.ColMajor, BLAS.NoTrans, 3, 2, 1.0, oracle.as_buffer(a), 0, 3,
+                oracle.as_buffer([100, 10, 1]), 0, 1, 0.0, ref, 0, 1)
+    assert Y.to_numpy().tolist() == ref.tolist() == [123.0, 456.0]
+
+
+OMAT = [(1, 1, 0, 0), (2, 3, 0, 0), (32, 32, 0, 0), (33, 65, 3, 2), (1000, 7, 0, 0), (7, 1000, 1, 5),
+        (2048, 2048, 0, 0), (4097, 1025, 0, 0)]
+
+
+@pytest.mark.parametrize("m,n,ld_extra,off", OMAT, ids=[str(v) for v in OMAT])
+@pytest.mark.parametrize("trans", [BLAS.NoTrans, BLAS.Trans])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_omatcopy_vs_oracle_bit_exact(m, n, ld_extra, off, trans, dt, cuda_service):
+    rng = np.random.default_rng(m * 7 + n)
+    npdt = NP[dt]
+    blas = cuda_service.blas()
+    ldA = n + ld_extra
+    rows, cols = (m, n) if trans == BLAS.NoTrans else (n, m)
+    ldB = cols + ld_extra
+    a = rng.standard_normal(off + m * ldA).astype(npdt)
+    b = rng.standard_normal(off + rows * ldB).astype(npdt)
+    for alpha in (1.0, -2.5):
+        A, B = buf(a, dt), buf(b, dt)
+        blas.omatcopy(BLAS.RowMajor, trans, m, n, alpha, A, off, ldA, B, off, ldB)
+        ref = oracle.as_buffer(b)
+        oracle.omatcopy(BLAS.RowMajor, trans, m, n, alpha, oracle.as_buffer(a), off, ldA, ref, off, ldB)
+        assert np.array_equal(B.to_numpy(), ref.astype(npdt))
+        assert np.array_equal(A.to_numpy(), a)
+
+
+def test_transpose_and_matmul_random(cuda_service, oracle_service):
+    rng = np.random.default_rng(5)
+    la, lo = LinearAlgebra(cuda_service), LinearAlgebra(oracle_service)
+    a = rng.standard_normal((300, 517)).astype(np.float32)
+    assert np.array_equal(la.transpose(la.array(a)).to_numpy(), a.T)
+    A = rng.standard_normal((3, 2, 40, 24)).astype(np.float32)
+    B = rng.standard_normal((2, 24, 56)).astype(np.float32)
+    got = la.matmul(la.array(A), la.array(B))
+    ref = lo.matmul(lo.array(A), lo.array(B))
+    assert got.shape() == ref.shape() == [3, 2, 40, 56]
+    r = np.asarray(ref.toArray(), np.float64)
+    assert np.max(np.abs(got.to_numpy() - r)) < 5e-5 * np.max(np.abs(r))
+
+
+def test_vector_transform_random(cuda_service, oracle_service):
+    rng = np.random.default_rng(6)
+    mo, mr = MatrixOperator(cuda_service), MatrixOperator(oracle_service)
+    A = rng.standard_normal((4, 5, 300, 129)).astype(np.float32)
+    B = rng.standard_normal(129).astype(np.float32)
+    got = mo.cross(mo.array(A), mo.array(B))
+    ref = mr.cross(mr.array(A), mr.array(B))
+    assert got.shape() == [4, 5, 300]
+    r = np.asarray(ref.toArray(), np.float64)
+    assert np.max(np.abs(got.to_numpy() - r)) < 4e-6 * np.max(np.abs(r))
+    with pytest.raises(InvalidArgumentException, match="unmatch shape of dimension"):
+        mo.cross(mo.array(A), mo.array(np.ones(128, np.float32)))
+
+
+def test_blas_widen_errors(cuda_service):
+    blas = cuda_service.blas()
+    X, Y = buf(np.zeros(4, np.float32), dtypes.float32), buf(np.zeros(4, np.float32), dtypes.float32)
+    with pytest.raises(InvalidArgumentException, match="Argument n must be greater than 0."):
+        blas.scal(0, 1.0, X, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Vector specification too large for bufferX."):
+        blas.axpy(5, 1.0, X, 0, 1, Y, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Vector specification too large for bufferY."):
+        blas.copy(3, X, 0, 1, Y, 0, 2)
+    with pytest.raises(InvalidArgumentException, match="Matrix specification too large for bufferA."):
+        blas.gemv(BLAS.RowMajor, BLAS.NoTrans, 2, 3, 1.0, X, 0, 3, Y, 0, 1, 0.0, Y, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Invalid Order type"):
+        blas.gemv(0, BLAS.NoTrans, 2, 2, 1.0, X, 0, 2, Y, 0, 1, 0.0, Y, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Unknown Tranpose Code"):
+        blas.omatcopy(BLAS.RowMajor, 0, 2, 2, 1.0, X, 0, 2, Y, 0, 2)
+    with pytest.raises(InvalidArgumentException, match="Matrix specification too large for bufferB."):
+        blas.omatcopy(BLAS.RowMajor, BLAS.Trans, 1, 4, 1.0, X, 0, 4, Y, 1, 1)
