@@ -386,7 +386,11 @@ def run_b200(args):
             sa = CudaBuffer(sz * sz, dtypes.float32, zero=False)
             sb = CudaBuffer(sz * sz, dtypes.float32, zero=False)
             sc = CudaBuffer(sz * sz, dtypes.float32, zero=False)
-            sa.fill(0.5); sb.fill(0.25)
+            # uniform(-1,1) operands like the headline run: constant operands toggle fewer bits, draw less
+            # power and clock ~35 % higher on this part -- such a number would not be comparable
+            reps = max(1, (sz * sz) // Ah.size)
+            sa.from_numpy(np.tile(Ah, reps)[:sz * sz] if reps > 1 else Ah[:sz * sz])
+            sb.from_numpy(np.tile(Bh, reps)[:sz * sz] if reps > 1 else Bh[:sz * sz])
             row = {}
             for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3)):
                 blas.setGemmMode(mm)

@@ -15,23 +15,37 @@ enum { B1_SCAL = 0, B1_AXPY = 1, B1_COPY = 2 };
 
 template <typename T> union B1Pack { int4 raw; T v[16 / sizeof(T)]; };
 
+constexpr int B1_UNROLL = 4;     // 16-byte packs in flight per thread and operand
+
 template <typename T, int OP>
 __global__ void __launch_bounds__(B1_THREADS)
 blas1_vec_kernel(int64_t nvec, T alpha, const T* __restrict__ X, T* __restrict__ Y)
 {
     constexpr int V = 16 / (int)sizeof(T);
-    const int64_t stride = (int64_t)gridDim.x * B1_THREADS;
-    for (int64_t i = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x; i < nvec; i += stride) {
-        B1Pack<T> x, y;
-        if (OP != B1_SCAL) x.raw = __ldcs(reinterpret_cast<const int4*>(X) + i);
-        if (OP != B1_COPY) y.raw = __ldcs(reinterpret_cast<const int4*>(Y) + i);
+    const int64_t chunk = (int64_t)B1_THREADS * B1_UNROLL;
+    for (int64_t base = (int64_t)blockIdx.x * chunk; base < nvec; base += (int64_t)gridDim.x * chunk) {
+        B1Pack<T> x[B1_UNROLL], y[B1_UNROLL];
 #pragma unroll
-        for (int e = 0; e < V; e++) {
-            if (OP == B1_SCAL) y.v[e] = y.v[e] * alpha;
-            else if (OP == B1_AXPY) y.v[e] = fma(alpha, x.v[e], y.v[e]);
-            else y.v[e] = x.v[e];
+        for (int u = 0; u < B1_UNROLL; u++) {
+            const int64_t i = base + u * B1_THREADS + threadIdx.x;
+            if (i < nvec) {
+                if (OP != B1_SCAL) x[u].raw = __ldcs(reinterpret_cast<const int4*>(X) + i);
+                if (OP != B1_COPY) y[u].raw = __ldcs(reinterpret_cast<const int4*>(Y) + i);
+            }
         }
-        __stcs(reinterpret_cast<int4*>(Y) + i, y.raw);
+#pragma unroll
+        for (int u = 0; u < B1_UNROLL; u++) {
+            const int64_t i = base + u * B1_THREADS + threadIdx.x;
+            if (i < nvec) {
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    if (OP == B1_SCAL) y[u].v[e] = y[u].v[e] * alpha;
+                    else if (OP == B1_AXPY) y[u].v[e] = fma(alpha, x[u].v[e], y[u].v[e]);
+                    else y[u].v[e] = x[u].v[e];
+                }
+                __stcs(reinterpret_cast<int4*>(Y) + i, y[u].raw);
+            }
+        }
     }
 }
 
@@ -60,7 +74,7 @@ int blas1_launch(int64_t n, double alpha_d, const void* Xv, int64_t offX, int64_
     const int64_t cap = (int64_t)c.sm_count * 16;
     if (incY == 1 && (OP == B1_SCAL || incX == 1) && aligned && n >= V) {
         const int64_t nvec = n / V;
-        int64_t grid = rb_ceil_div(nvec, B1_THREADS);
+        int64_t grid = rb_ceil_div(nvec, (int64_t)B1_THREADS * B1_UNROLL);
         if (grid > cap) grid = cap;
         blas1_vec_kernel<T, OP><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(nvec, alpha, X, Y);
         RB_LAUNCH_CHECK("blas1_vec_kernel");
@@ -94,19 +108,44 @@ int blas1_dispatch(int dtype, int64_t n, double alpha, const void* X, int64_t of
 }
 
 // ---- gemv -------------------------------------------------------------------------------------------
-// NoTrans: one warp per row of A (coalesced along the row, shuffle reduction).
-template <typename T>
+// NoTrans: one warp per row of A (coalesced along the row, shuffle reduction).  VEC: 16-byte loads of A and X
+// (ldA, the offsets and the base pointers 16-byte aligned, incX == 1), four packs in flight per lane.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(B1_THREADS)
 gemv_n_kernel(int64_t m, int64_t n, T alpha, const T* __restrict__ A, int64_t ldA,
               const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY)
 {
+    constexpr int V = 16 / (int)sizeof(T);
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (B1_THREADS / 32);
     for (int64_t i = (int64_t)blockIdx.x * (B1_THREADS / 32) + (threadIdx.x >> 5); i < m; i += warps) {
         const T* row = A + i * ldA;
         T acc = (T)0;
-#pragma unroll 8
-        for (int64_t j = lane; j < n; j += 32) acc = fma(alpha * __ldcs(row + j), __ldg(X + j * incX), acc);
+        int64_t j0 = 0;
+        if (VEC) {
+            const int64_t nv = n / V;
+            const int4* rv = reinterpret_cast<const int4*>(row);
+            const int4* xv = reinterpret_cast<const int4*>(X);
+            for (int64_t jb = 0; jb < nv; jb += 32 * 4) {
+                B1Pack<T> a[4], x[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t jv = jb + u * 32 + lane;
+                    if (jv < nv) { a[u].raw = __ldcs(rv + jv); x[u].raw = __ldg(xv + jv); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t jv = jb + u * 32 + lane;
+                    if (jv < nv) {
+#pragma unroll
+                        for (int e = 0; e < V; e++) acc = fma(alpha * a[u].v[e], x[u].v[e], acc);
+                    }
+                }
+            }
+            j0 = nv * V;
+        }
+#pragma unroll 4
+        for (int64_t j = j0 + lane; j < n; j += 32) acc = fma(alpha * __ldcs(row + j), __ldg(X + j * incX), acc);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
         if (lane == 0) {
@@ -116,36 +155,64 @@ gemv_n_kernel(int64_t m, int64_t n, T alpha, const T* __restrict__ A, int64_t ld
     }
 }
 
-// Trans: Y[j] = sum_i (alpha*A[i,j])*X[i]; thread (tx,ty): column j = blockIdx.x*32+tx, rows ty, ty+8, ... of
-// the row segment blockIdx.y (coalesced along j); shared-memory tree over ty.  With one segment the CTA
-// finishes Y itself, otherwise it writes a partial row into the workspace and gemv_t_merge_kernel adds the
-// segments in index order (deterministic, no atomics).
-template <typename T>
+// Trans: Y[j] = sum_i (alpha*A[i,j])*X[i]; thread (tx,ty) owns CPT adjacent columns (CPT = 16 bytes worth when
+// A's rows are 16-byte aligned, else 1) of column block blockIdx.x and rows ty, ty+8, ... of the row segment
+// blockIdx.y (coalesced along j); shared-memory tree over ty.  With one segment the CTA finishes Y itself,
+// otherwise it writes a partial row into the workspace and gemv_t_merge_kernel adds the segments in index
+// order (deterministic, no atomics).
+template <typename T, int CPT>
 __global__ void __launch_bounds__(B1_THREADS)
 gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restrict__ A, int64_t ldA,
               const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY, T* __restrict__ partial)
 {
-    __shared__ T sm[8][33];
+    __shared__ T sm[8][32 * CPT + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    const int64_t j = ((int64_t)blockIdx.x * 32 + tx) * CPT;
     const int64_t i0 = (int64_t)blockIdx.y * seg_rows;
     const int64_t i1 = (i0 + seg_rows < m) ? i0 + seg_rows : m;
-    T acc = (T)0;
-    if (j < n) {
-        const T* a = A + j;
-#pragma unroll 4
-        for (int64_t i = i0 + ty; i < i1; i += 8) acc = fma(alpha * __ldcs(a + i * ldA), __ldg(X + i * incX), acc);
-    }
-    sm[ty][tx] = acc;
-    __syncthreads();
-    if (ty == 0 && j < n) {
-        T s = sm[0][tx];
+    T acc[CPT];
 #pragma unroll
-        for (int r = 1; r < 8; r++) s += sm[r][tx];
-        if (partial) partial[(int64_t)blockIdx.y * n + j] = s;
-        else {
-            T* y = Y + j * incY;
-            *y = (beta == (T)0) ? s : fma(beta, *y, s);
+    for (int e = 0; e < CPT; e++) acc[e] = (T)0;
+    if (CPT == 1) {
+        if (j < n) {
+            const T* a = A + j;
+#pragma unroll 4
+            for (int64_t i = i0 + ty; i < i1; i += 8) acc[0] = fma(alpha * __ldcs(a + i * ldA), __ldg(X + i * incX), acc[0]);
+        }
+    } else if (j < n) {                    // n % CPT == 0 on this path: a pack never straddles the edge
+        const T* a = A + j;
+        for (int64_t ib = i0 + ty; ib < i1; ib += 8 * 4) {
+            B1Pack<T> v[4];
+            T x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t i = ib + u * 8;
+                if (i < i1) { v[u].raw = __ldcs(reinterpret_cast<const int4*>(a + i * ldA)); x[u] = __ldg(X + i * incX); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (ib + u * 8 < i1) {
+#pragma unroll
+                    for (int e = 0; e < CPT; e++) acc[e] = fma(alpha * v[u].v[e], x[u], acc[e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < CPT; e++) sm[ty][tx * CPT + e] = acc[e];
+    __syncthreads();
+    // 32*CPT columns finished by the first 32*CPT threads
+    for (int c = threadIdx.x; c < 32 * CPT; c += B1_THREADS) {
+        const int64_t jc = (int64_t)blockIdx.x * 32 * CPT + c;
+        if (jc < n) {
+            T s = sm[0][c];
+#pragma unroll
+            for (int r = 1; r < 8; r++) s += sm[r][c];
+            if (partial) partial[(int64_t)blockIdx.y * n + jc] = s;
+            else {
+                T* y = Y + jc * incY;
+                *y = (beta == (T)0) ? s : fma(beta, *y, s);
+            }
         }
     }
 }
@@ -167,17 +234,22 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
                 const void* Xv, int64_t offX, int64_t incX, double beta, void* Yv, int64_t offY, int64_t incY)
 {
     rb200::Context& c = rb200::ctx();
+    constexpr int V = 16 / (int)sizeof(T);
     const T* A = reinterpret_cast<const T*>(Av) + offA;
     const T* X = reinterpret_cast<const T*>(Xv) + offX;
     T* Y = reinterpret_cast<T*>(Yv) + offY;
+    const bool a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (ldA % V == 0);
     if (!trans) {
         int64_t grid = rb_ceil_div(m, B1_THREADS / 32);
         const int64_t cap = (int64_t)c.sm_count * 32;
         if (grid > cap) grid = cap;
-        gemv_n_kernel<T><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
+        const bool vec = a_vec && incX == 1 && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && n >= V;
+        if (vec) gemv_n_kernel<T, true><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
+        else gemv_n_kernel<T, false><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
         RB_LAUNCH_CHECK("gemv_n_kernel");
     } else {
-        const int64_t gx = rb_ceil_div(n, 32);
+        const bool vec = a_vec && (n % V == 0);
+        const int64_t gx = rb_ceil_div(n, vec ? 32 * V : 32);
         if (gx > 0x7fffffffLL) RB_INVALID("gemv: n too large");
         // row segments: enough CTAs for ~8 per SM, at least 64 rows each
         int64_t segs = rb_ceil_div((int64_t)c.sm_count * 8, gx);
@@ -192,8 +264,9 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
             if (rc != RB200_OK) return rc;
             partial = reinterpret_cast<T*>(c.workspace);
         }
-        gemv_t_kernel<T><<<dim3((unsigned)gx, (unsigned)segs), B1_THREADS, 0, c.stream>>>(
-            m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
+        const dim3 grid((unsigned)gx, (unsigned)segs);
+        if (vec) gemv_t_kernel<T, V><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
+        else gemv_t_kernel<T, 1><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
         RB_LAUNCH_CHECK("gemv_t_kernel");
         if (segs > 1) {
             gemv_t_merge_kernel<T><<<(unsigned)rb_ceil_div(n, B1_THREADS), B1_THREADS, 0, c.stream>>>(
@@ -240,6 +313,51 @@ omatcopy_kernel(int64_t rows, int64_t cols, T alpha, const T* __restrict__ A, in
     }
 }
 
+// Transposing copy with 16-byte global accesses on both sides: 64x64 tile, 256 threads, all of a thread's
+// loads issued before its first shared store.  Needs 16-byte aligned A/B rows and rows, cols multiples of the
+// pack width; everything else takes omatcopy_kernel.
+template <typename T>
+__global__ void __launch_bounds__(B1_THREADS)
+omatcopy_t_vec_kernel(int64_t rows, int64_t cols, T alpha, const T* __restrict__ A, int64_t ldA,
+                      T* __restrict__ B, int64_t ldB)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int TS = 64;                       // tile edge in elements
+    constexpr int VPR = TS / V;                  // packs per tile row
+    constexpr int RPP = B1_THREADS / VPR;        // tile rows per pass
+    constexpr int PASSES = TS / RPP;
+    __shared__ T tile[TS][TS + 1];
+    const int xv = threadIdx.x % VPR, y0 = threadIdx.x / VPR;
+    const int64_t tiles_c = (cols + TS - 1) / TS, tiles_r = (rows + TS - 1) / TS;
+    for (int64_t t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+        const int64_t r0 = (t / tiles_c) * TS, c0 = (t % tiles_c) * TS;
+        B1Pack<T> v[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; p++) {
+            const int64_t ar = c0 + y0 + p * RPP, ac = r0 + xv * V;      // A is cols x rows
+            if (ar < cols && ac < rows) v[p].raw = __ldcs(reinterpret_cast<const int4*>(A + ar * ldA + ac));
+        }
+#pragma unroll
+        for (int p = 0; p < PASSES; p++) {
+#pragma unroll
+            for (int e = 0; e < V; e++) tile[y0 + p * RPP][xv * V + e] = v[p].v[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < PASSES; p++) {
+            const int y = y0 + p * RPP;
+            const int64_t br = r0 + y, bc = c0 + xv * V;
+            if (br < rows && bc < cols) {
+                B1Pack<T> o;
+#pragma unroll
+                for (int e = 0; e < V; e++) o.v[e] = alpha * tile[xv * V + e][y];
+                __stcs(reinterpret_cast<int4*>(B + br * ldB + bc), o.raw);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 int omatcopy_launch(bool trans, int64_t rows, int64_t cols, double alpha, const void* Av, int64_t offA, int64_t ldA,
                     void* Bv, int64_t offB, int64_t ldB)
@@ -247,8 +365,17 @@ int omatcopy_launch(bool trans, int64_t rows, int64_t cols, double alpha, const 
     rb200::Context& c = rb200::ctx();
     const T* A = reinterpret_cast<const T*>(Av) + offA;
     T* B = reinterpret_cast<T*>(Bv) + offB;
-    int64_t grid = rb_ceil_div(rows, 32) * rb_ceil_div(cols, 32);
+    constexpr int V = 16 / (int)sizeof(T);
     const int64_t cap = (int64_t)c.sm_count * 32;
+    if (trans && rows % V == 0 && cols % V == 0 && ldA % V == 0 && ldB % V == 0 &&
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0) {
+        int64_t grid = rb_ceil_div(rows, 64) * rb_ceil_div(cols, 64);
+        if (grid > cap) grid = cap;
+        omatcopy_t_vec_kernel<T><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(rows, cols, (T)alpha, A, ldA, B, ldB);
+        RB_LAUNCH_CHECK("omatcopy_t_vec_kernel");
+        return RB200_OK;
+    }
+    int64_t grid = rb_ceil_div(rows, 32) * rb_ceil_div(cols, 32);
     if (grid > cap) grid = cap;
     if (trans) omatcopy_kernel<T, true><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(rows, cols, (T)alpha, A, ldA, B, ldB);
     else omatcopy_kernel<T, false><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(rows, cols, (T)alpha, A, ldA, B, ldB);

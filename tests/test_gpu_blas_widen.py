@@ -66,7 +66,8 @@ def test_copy_scal_axpy_vs_oracle(n, incX, incY, offX, offY, dt, cuda_service):
 
 
 GEMV = [(1, 1, 0, 0), (2, 3, 0, 0), (64, 64, 0, 0), (257, 1023, 5, 3), (1000, 33, 0, 2), (33, 5000, 7, 0),
-        (4096, 4096, 0, 0), (3, 100000, 0, 0), (100000, 3, 1, 0)]
+        (4096, 4096, 0, 0), (3, 100000, 0, 0), (100000, 3, 1, 0), (1000, 1028, 4, 4), (517, 2052, 0, 8),
+        (2048, 136, 0, 0)]
 
 
 @pytest.mark.parametrize("m,n,ld_extra,off", GEMV, ids=[str(v) for v in GEMV])
@@ -80,13 +81,14 @@ def test_gemv_vs_oracle(m, n, ld_extra, off, trans, dt, cuda_service):
     a = rng.standard_normal(off + m * ld).astype(npdt)
     rows, cols = (m, n) if trans == BLAS.NoTrans else (n, m)
     incX, incY = (1, 1) if m * n > 10000 else (2, 3)
-    x = rng.standard_normal(1 + (cols - 1) * incX + 1).astype(npdt)
+    offX = 4 if m * n > 10000 else 1            # 16-byte aligned X takes the 128-bit kernels
+    x = rng.standard_normal(offX + (cols - 1) * incX + 1).astype(npdt)
     y = rng.standard_normal(2 + (rows - 1) * incY + 1).astype(npdt)
     for alpha, beta in ((1.0, 0.0), (0.5, 1.0), (-1.25, 0.75)):
         A, X, Y = buf(a, dt), buf(x, dt), buf(y, dt)
-        blas.gemv(BLAS.RowMajor, trans, m, n, alpha, A, off, ld, X, 1, incX, beta, Y, 2, incY)
+        blas.gemv(BLAS.RowMajor, trans, m, n, alpha, A, off, ld, X, offX, incX, beta, Y, 2, incY)
         ref = oracle.as_buffer(y)
-        oracle.gemv(BLAS.RowMajor, trans, m, n, alpha, oracle.as_buffer(a), off, ld, oracle.as_buffer(x), 1, incX,
+        oracle.gemv(BLAS.RowMajor, trans, m, n, alpha, oracle.as_buffer(a), off, ld, oracle.as_buffer(x), offX, incX,
                     beta, ref, 2, incY)
         got = Y.to_numpy().astype(np.float64)
         scale = np.max(np.abs(ref))
@@ -116,7 +118,7 @@ def test_gemv_beta_zero_ignores_nan_and_colmajor(cuda_service):
 
 
 OMAT = [(1, 1, 0, 0), (2, 3, 0, 0), (32, 32, 0, 0), (33, 65, 3, 2), (1000, 7, 0, 0), (7, 1000, 1, 5),
-        (2048, 2048, 0, 0), (4097, 1025, 0, 0)]
+        (2048, 2048, 0, 0), (4097, 1025, 0, 0), (100, 260, 4, 8), (4096, 1028, 0, 0), (64, 64, 0, 0), (68, 4, 0, 4)]
 
 
 @pytest.mark.parametrize("m,n,ld_extra,off", OMAT, ids=[str(v) for v in OMAT])
