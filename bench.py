@@ -318,6 +318,17 @@ def run_b200(args):
                 "peak_note": "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); %s"
                              % (peaks["source"], achieved_note)}
 
+    # the same kernel back to back for ~2 s: the power-capped figure, against the sustained cuBLAS bf16 peak / 2
+    if not args.quick:
+        reps = max(args.steps, int(2000.0 / max(ms_per_step, 1e-3)))
+        sus_ms = timed(gemm_step, reps, 0) / reps
+        sus = flops_per_step / (sus_ms * 1e-3) / 1e12
+        roofline["sustained"] = {"achieved": sus, "peak": peaks["bf16_tflops_sustained"] / 2.0,
+                                 "frac": sus / (peaks["bf16_tflops_sustained"] / 2.0), "launches": reps,
+                                 "ms_per_launch": sus_ms,
+                                 "note": "same launch repeated for ~2 s (sw_power_cap engaged); peak = 1/2 of the "
+                                         "sustained cuBLAS bf16 figure"}
+
     # ---- multi-GPU: the same step followed by the NCCL all-gather of the C stripes (only when the caller
     #      needs the full C on every rank; reported beside the collective-free number) --------------------
     with_gather = None

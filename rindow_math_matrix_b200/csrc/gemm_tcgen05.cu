@@ -386,12 +386,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 // posts the expect_tx for both), the leader's tcgen05.commit multicasts to the empty / tmem_full barriers
 // of both CTAs, and the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
 // =====================================================================================================
-constexpr int TC2_STAGES = 6;
-constexpr int TC2_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB: this CTA's 128 rows of A
-constexpr int TC2_B_BYTES = 128 * TC_BK * 4;          // 16 KB: this CTA's 128 columns of B
-constexpr int TC2_STAGE = TC2_A_BYTES + TC2_B_BYTES;
-constexpr int TC2_BAR_OFF = TC2_STAGES * TC2_STAGE;
-constexpr int TC2_SMEM = TC2_BAR_OFF + 256 + 1024;
+// PLANES = 1 (TF32): pair tile 256 x 256, 32 KB stages, 6-deep ring, two 128 x 256 accumulators per CTA.
+// PLANES = 2 (3xTF32): pair tile 256 x 128 of hi/lo planes, 48 KB stages, 4-deep ring; each accumulator
+// stage holds a big (hi*hi) and a small (hi*lo + lo*hi) 128 x 128 accumulator, summed in the epilogue.
+template <int PLANES>
+struct Tc2Cfg {
+    static constexpr int BN = PLANES == 1 ? 256 : 128;        // pair-tile columns (instruction N)
+    static constexpr int HALF_N = BN / 2;                      // columns of B this CTA stages
+    static constexpr int A_PLANE = TC_BM * TC_BK * 4;          // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_PLANE = HALF_N * TC_BK * 4;         // 16 / 8 KB
+    static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
+    static constexpr int STAGES = PLANES == 1 ? 6 : 4;
+    static constexpr int BAR_OFF = STAGES * STAGE;
+    static constexpr int SMEM = BAR_OFF + 256 + 1024;
+    static constexpr int ACC_COLS = PLANES * BN;               // 256 TMEM columns per accumulator stage
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -435,15 +444,17 @@ __device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc,
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int PLANES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, TcParams p)
 {
-    constexpr int STAGES = TC2_STAGES;
-    constexpr int BN = 256;                                   // pair tile: 256 x 256
+    using L = Tc2Cfg<PLANES>;
+    constexpr int STAGES = L::STAGES;
+    constexpr int BN = L::BN;                                 // pair tile: 256 x BN
+    constexpr int ACC_COLS = L::ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + TC2_BAR_OFF;
+    const uint32_t bar_base = smem_base + L::BAR_OFF;
     auto full_bar  = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -475,7 +486,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     tc_fence_before();
     cluster_sync_all();                                        // barriers of BOTH CTAs initialised, TMEM allocated
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + TC2_BAR_OFF + 8 * (2 * STAGES + 4));
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFF + 8 * (2 * STAGES + 4));
 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;     // here: pair tiles (256 rows each)
 
@@ -486,25 +497,30 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 int mb, nb;
                 tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
-                const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * 128;
+                const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * L::HALF_N;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t leader_full = mapa_rank(full_bar(stage), 0);
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * TC2_STAGE);     // both CTAs' bytes
-                    const uint32_t sA = smem_base + stage * TC2_STAGE;
-                    const uint32_t sB = sA + TC2_A_BYTES;
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * L::STAGE);     // both CTAs' bytes
+                    const uint32_t sA = smem_base + stage * L::STAGE;
+                    const uint32_t sB = sA + PLANES * L::A_PLANE;
                     const int k0 = kb * TC_BK;
-                    if (!A_MN) {
-                        tma_load_3d_2sm(sA, &tmapA, leader_full, k0, m0, 0);
-                    } else {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) tma_load_3d_2sm(sA + j * 4096, &tmapA, leader_full, m0 + 32 * j, k0, 0);
-                    }
-                    if (!B_MN) {
-                        tma_load_3d_2sm(sB, &tmapB, leader_full, k0, n0, 0);
-                    } else {
+                    for (int pl = 0; pl < PLANES; pl++) {
+                        if (!A_MN) {
+                            tma_load_3d_2sm(sA + pl * L::A_PLANE, &tmapA, leader_full, k0, m0, pl);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) tma_load_3d_2sm(sB + j * 4096, &tmapB, leader_full, n0 + 32 * j, k0, 0);
+                            for (int j = 0; j < 4; j++)
+                                tma_load_3d_2sm(sA + pl * L::A_PLANE + j * 4096, &tmapA, leader_full, m0 + 32 * j, k0, pl);
+                        }
+                        if (!B_MN) {
+                            tma_load_3d_2sm(sB + pl * L::B_PLANE, &tmapB, leader_full, k0, n0, pl);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < L::HALF_N / 32; j++)
+                                tma_load_3d_2sm(sB + pl * L::B_PLANE + j * 4096, &tmapB, leader_full, n0 + 32 * j, k0, pl);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -519,12 +535,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);     // both CTAs' epilogues drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(full_bar(stage), phase);         // both halves of A and B have landed
                     tc_fence_after();
-                    const uint32_t sA = smem_base + stage * TC2_STAGE;
-                    const uint32_t sB = sA + TC2_A_BYTES;
+                    const uint32_t sA = smem_base + stage * L::STAGE;
+                    const uint32_t sB = sA + PLANES * L::A_PLANE;
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / TC_UMMA_K; kk++) {
                         const uint32_t aoff = A_MN ? kk * 1024 : kk * 32;
@@ -533,7 +549,18 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                                                  : make_smem_desc(sA + aoff, 16, 1024, 2);
                         const uint64_t bd = B_MN ? make_smem_desc(sB + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                                  : make_smem_desc(sB + boff, 16, 1024, 2);
-                        tc_mma_tf32_2sm(tmem_d, ad, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                        const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                        if (PLANES == 1) {
+                            tc_mma_tf32_2sm(tmem_d, ad, bd, idesc, first);
+                        } else {
+                            const uint64_t a_lo = A_MN ? make_smem_desc(sA + L::A_PLANE + aoff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : make_smem_desc(sA + L::A_PLANE + aoff, 16, 1024, 2);
+                            const uint64_t b_lo = B_MN ? make_smem_desc(sB + L::B_PLANE + boff, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : make_smem_desc(sB + L::B_PLANE + boff, 16, 1024, 2);
+                            tc_mma_tf32_2sm(tmem_d + BN, ad, b_lo, idesc, first);  // cross terms -> small accumulator
+                            tc_mma_tf32_2sm(tmem_d + BN, a_lo, bd, idesc, 1u);
+                            tc_mma_tf32_2sm(tmem_d, ad, bd, idesc, first);         // hi*hi -> big accumulator
+                        }
                     }
                     tc_commit_2sm(empty_bar(stage));           // frees this stage in BOTH CTAs
                     if (kb == p.num_k_blocks - 1) tc_commit_2sm(tfull_bar(acc));
@@ -558,9 +585,17 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ch++) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 32);
                 tc_ld_32x32b_x32(taddr, r);
-                tc_wait_ld();
+                if (PLANES == 2) {
+                    uint32_t rs[32];
+                    tc_ld_32x32b_x32(taddr + BN, rs);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rs[e]));
+                } else {
+                    tc_wait_ld();
+                }
                 const int64_t c0 = col0 + ch * 32;
                 if (row_ok && c0 < p.N) {
                     if (c0 + 32 <= p.N) {
@@ -695,30 +730,32 @@ int launch_by_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorM
     return launch_tf32<BN, true, true, PLANES, STAGES>(mA, mB, p);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int PLANES>
 int launch_2cta_t(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
 {
     rb200::Context& c = rb200::ctx();
-    auto kern = gemm_tf32_2cta_kernel<A_MN, B_MN>;
+    auto kern = gemm_tf32_2cta_kernel<A_MN, B_MN, PLANES>;
+    constexpr int SMEM = Tc2Cfg<PLANES>::SMEM;
     static bool configured = false;
     if (!configured) {
-        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int max_pairs = c.sm_count / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    kern<<<2 * pairs, TC_THREADS, TC2_SMEM, c.stream>>>(mA, mB, p);
+    kern<<<2 * pairs, TC_THREADS, SMEM, c.stream>>>(mA, mB, p);
     RB_LAUNCH_CHECK("gemm_tf32_2cta_kernel");
     return RB200_OK;
 }
 
+template <int PLANES>
 int launch_2cta(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
 {
-    if (!a_mn && !b_mn) return launch_2cta_t<false, false>(mA, mB, p);
-    if (!a_mn &&  b_mn) return launch_2cta_t<false, true>(mA, mB, p);
-    if ( a_mn && !b_mn) return launch_2cta_t<true, false>(mA, mB, p);
-    return launch_2cta_t<true, true>(mA, mB, p);
+    if (!a_mn && !b_mn) return launch_2cta_t<false, false, PLANES>(mA, mB, p);
+    if (!a_mn &&  b_mn) return launch_2cta_t<false, true, PLANES>(mA, mB, p);
+    if ( a_mn && !b_mn) return launch_2cta_t<true, false, PLANES>(mA, mB, p);
+    return launch_2cta_t<true, true, PLANES>(mA, mB, p);
 }
 
 }  // namespace
@@ -816,19 +853,20 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
-        if (planes == 1 && use_2cta && M >= 256 && c.sm_count >= 2) {
-            // CTA-pair kernel: 256-row pair tiles; B (and MN-major A) maps with 128-wide boxes
+        static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
+        if ((planes == 1 || use_2cta_x3) && use_2cta && M >= 256 && c.sm_count >= 2) {
+            // CTA-pair kernel: 256-row pair tiles; each CTA stages half of the pair tile's B columns
             CUtensorMap mB2;
-            if (!b_mn) rc = make_map(&mB2, pb, kl, N, sldB, 1, 0, TC_BK, 128, k_sw);
-            else       rc = make_map(&mB2, pb, N, kl, sldB, 1, 0, 32, TC_BK, mn_sw);
+            if (!b_mn) rc = make_map(&mB2, pb, kl, N, sldB, planes, plsB, TC_BK, BN / 2, k_sw);
+            else       rc = make_map(&mB2, pb, N, kl, sldB, planes, plsB, 32, TC_BK, mn_sw);
             if (rc != RB200_OK) return rc;
             p.num_m_blocks = (int)rb_ceil_div(M, 256);
             // 74 pair tiles in flight as 8 pair-rows x ~9 column blocks: smallest A+B footprint per k-step,
             // and an A panel (8 x 256 rows) that stays L2-resident across the waves of its group
             static const int dbg_group = getenv("RB200_GEMM_GROUP") ? atoi(getenv("RB200_GEMM_GROUP")) : 8;
             p.group_m = dbg_group > 0 ? dbg_group : 8;
-            rc = launch_2cta(a_mn, b_mn, mA, mB2, p);
-            c.last_gemm_path = "tcgen05_tf32_2cta";
+            rc = planes == 1 ? launch_2cta<1>(a_mn, b_mn, mA, mB2, p) : launch_2cta<2>(a_mn, b_mn, mA, mB2, p);
+            c.last_gemm_path = planes == 1 ? "tcgen05_tf32_2cta" : "tcgen05_tf32x3_2cta";
         } else if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);
         else                    rc = launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
         if (rc != RB200_OK) return rc;

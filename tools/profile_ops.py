@@ -2,7 +2,7 @@
 """Run one hot-path op a few times at its BASELINE size -- the command ncu wraps
 (profiles/README.md lists the exact ncu invocations).  Usage: profile_ops.py OP [REPS]
 OP in: sgemm_tf32 sgemm_tf32x3 sgemm_simt add multiply reduce_sum reduce_sum_axis0 reduce_max
-       reduce_argmax softmax im2col2d conv_gemm"""
+       reduce_argmax softmax im2col2d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans"""
 import os
 import sys
 
@@ -64,6 +64,16 @@ def main():
             blas.setGemmMode(0)
             fn = lambda: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, 64, 27, 1.0, cols, 0, 27, Wt, 0, 64,
                                    0.0, out, 0, 64)
+    elif op in ("axpy", "copy", "transpose", "gemv", "gemv_trans"):
+        m, n = 8192, 4096
+        A, Y = rnd(m * n), rnd(m * n)
+        Xn, Xm, Yn, Ym = rnd(n), rnd(m), CudaBuffer(n, f32), CudaBuffer(m, f32)
+        fn = {"axpy": lambda: blas.axpy(m * n, 0.5, A, 0, 1, Y, 0, 1),
+              "copy": lambda: blas.copy(m * n, A, 0, 1, Y, 0, 1),
+              "transpose": lambda: blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A, 0, n, Y, 0, m),
+              "gemv": lambda: blas.gemv(BLAS.RowMajor, BLAS.NoTrans, m, n, 1.0, A, 0, n, Xn, 0, 1, 0.0, Ym, 0, 1),
+              "gemv_trans": lambda: blas.gemv(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A, 0, n, Xm, 0, 1, 0.0, Yn, 0, 1),
+              }[op]
     else:
         raise SystemExit("unknown op " + op)
     for _ in range(reps):
