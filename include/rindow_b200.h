@@ -133,6 +133,19 @@ int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
                 const double* B, int64_t offB, int64_t ldB,
                 double beta, double* C, int64_t offC, int64_t ldC);
 
+/* sgemm for operands whose current copy is in (pinned) HOST memory -- the e2e form of PhpBlas::gemm for a
+ * caller that fills buffers from PHP and reads the product back (MatrixOperator::cross followed by
+ * toArray(), MatrixOperator.php:429-508).  dX is the device allocation, hX the host mirror with the same
+ * element indexing; hA / hB NULL = the device copy is current, hC NULL = leave C on the device.  The call
+ * pipelines the transfers with the multiply: B first, then A (and C when beta != 0 and hC_is_current) in
+ * row stripes on a copy-in stream, one sgemm per landed stripe on the library stream, finished C stripes
+ * back on a copy-out stream (both PCIe directions busy).  Returns after hC is complete.  Same arithmetic,
+ * modes and argument rules as rb200_sgemm. */
+int rb200_sgemm_streamed(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                         float alpha, float* dA, const float* hA, int64_t offA, int64_t ldA,
+                         float* dB, const float* hB, int64_t offB, int64_t ldB,
+                         float beta, float* dC, float* hC, int hC_is_current, int64_t offC, int64_t ldC, int mode);
+
 /* ---- BLAS level 1 / 2: replace PhpBlas::scal (PhpBlas.php:141-161),
  *      axpy (:165-194), copy (:350-364), gemv (:762-844).  float32 / float64. ------------------------------ */
 int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX);

@@ -57,6 +57,10 @@ class CudaBlas extends PhpBlas
         $alpha = $this->cleanFloatNumber($alpha,'alpha');
         $beta = $this->cleanFloatNumber($beta,'beta');
         $ffi = CudaFFI::lib();
+        if ($dtype == NDArray::float32 && $this->gemmStreamed($transA,$transB,$m,$n,$k,$alpha,
+                $A,$offsetA,$ldA,$B,$offsetB,$ldB,$beta,$C,$offsetC,$ldC,$tA,$tB)) {
+            return;
+        }
         $a = $A->devicePtr(); $b = $B->devicePtr(); $c = $C->devicePtrRW();
         if ($dtype == NDArray::float32) {
             CudaFFI::check($ffi->rb200_sgemm(BLAS::RowMajor,$transA,$transB,$m,$n,$k,$alpha,
@@ -67,6 +71,47 @@ class CudaBlas extends PhpBlas
                 $ffi->cast('double*',$a),$offsetA,$ldA,$ffi->cast('double*',$b),$offsetB,$ldB,
                 $beta,$ffi->cast('double*',$c),$offsetC,$ldC));
         }
+    }
+
+    /** null: bring C back eagerly iff the caller already indexes C from PHP (its mirror exists); true/false: always/never */
+    protected ?bool $hostResultPrefetch = null;
+    public function setHostResultPrefetch(?bool $flag) : void { $this->hostResultPrefetch = $flag; }
+
+    /**
+     * Host-operand form (rb200_sgemm_streamed): when an operand's current copy is in its pinned mirror and/or
+     * the caller reads C from PHP, the transfers are pipelined with the multiply instead of
+     * flush -> kernel -> fetch.  Returns false when the plain path should run.
+     */
+    protected function gemmStreamed(int $transA, int $transB, int $m, int $n, int $k, float $alpha,
+        CudaBuffer $A, int $offsetA, int $ldA, CudaBuffer $B, int $offsetB, int $ldB, float $beta,
+        CudaBuffer $C, int $offsetC, int $ldC, bool $tA, bool $tB) : bool
+    {
+        if ($m < 2048 || $A === $C || $B === $C || $A === $B) return false;
+        $whole = fn(CudaBuffer $buf, int $off, int $rows, int $cols, int $ld) : bool =>
+            $off == 0 && $ld == $cols && count($buf) == $rows * $cols;
+        $upA = $A->hostPending() && $whole($A,$offsetA,(!$tA)?$m:$k,(!$tA)?$k:$m,$ldA);
+        $upB = $B->hostPending() && $whole($B,$offsetB,(!$tB)?$k:$n,(!$tB)?$n:$k,$ldB);
+        $wantC = $this->hostResultPrefetch ?? $C->hasMirror();
+        $downC = $wantC && ($whole($C,$offsetC,$m,$n,$ldC) || $C->mirrorCurrent());
+        if (!($upA || $upB || $downC)) return false;
+        if ($A->hostPending() && !$upA) $A->devicePtr();           // plain flush
+        if ($B->hostPending() && !$upB) $B->devicePtr();
+        $cHostCurrent = 0;
+        if ($C->hostPending()) {
+            if ($whole($C,$offsetC,$m,$n,$ldC) && $downC) { $cHostCurrent = 1; $C->streamedUploaded(); }
+            else $C->devicePtr();
+        }
+        if ($downC) $C->ensureMirror();
+        [$dA,$hA] = $A->rawPointers(); [$dB,$hB] = $B->rawPointers(); [$dC,$hC] = $C->rawPointers();
+        $ffi = CudaFFI::lib();
+        $f = fn($p) => $p === null ? null : $ffi->cast('float*',$p);
+        CudaFFI::check($ffi->rb200_sgemm_streamed(BLAS::RowMajor,$transA,$transB,$m,$n,$k,$alpha,
+            $f($dA), $upA ? $f($hA) : null, $offsetA,$ldA, $f($dB), $upB ? $f($hB) : null, $offsetB,$ldB,
+            $beta, $f($dC), $downC ? $f($hC) : null, $cHostCurrent, $offsetC,$ldC,$this->gemmMode));
+        if ($upA) $A->streamedUploaded();
+        if ($upB) $B->streamedUploaded();
+        $C->streamedResult($downC);
+        return true;
     }
 
     /** true when every buffer is a float32/float64 CudaBuffer, i.e. the call can stay on the device */

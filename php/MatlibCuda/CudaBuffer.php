@@ -99,6 +99,26 @@ class CudaBuffer implements LinearBuffer
         return $this->dptr;
     }
 
+    // ---- state the streamed (host-operand) gemm needs: it moves the data itself (CudaBlas::gemmStreamed) ----
+    public function hostPending() : bool { return $this->hostDirty; }
+    public function hasMirror() : bool { return $this->host !== null; }
+    public function mirrorCurrent() : bool { return $this->host !== null && !$this->devDirty; }
+    /** [device pointer, pinned host pointer|null] without any implied transfer */
+    public function rawPointers() : array { return [$this->dptr, $this->hptr]; }
+    public function streamedUploaded() : void { $this->hostDirty = false; }
+    public function streamedResult(bool $downloaded) : void { $this->devDirty = !$downloaded; }
+    public function ensureMirror() : void
+    {
+        if ($this->host === null) {
+            $ffi = CudaFFI::lib();
+            $p = $ffi->new('void*');
+            CudaFFI::check($ffi->rb200_host_alloc(max(16, $this->size * $this->valueSize), FFI::addr($p)));
+            $this->hptr = $p;
+            $this->host = $ffi->cast($this->ctype.'['.max(1, $this->size).']', $p);
+            $this->devDirty = true;
+        }
+    }
+
     /** device pointer for a kernel that writes the buffer */
     public function devicePtrRW()
     {

@@ -41,6 +41,10 @@ class CudaFFI
                         double alpha, const double* A, int64_t offA, int64_t ldA,
                         const double* B, int64_t offB, int64_t ldB,
                         double beta, double* C, int64_t offC, int64_t ldC);
+        int rb200_sgemm_streamed(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                        float alpha, float* dA, const float* hA, int64_t offA, int64_t ldA,
+                        float* dB, const float* hB, int64_t offB, int64_t ldB,
+                        float beta, float* dC, float* hC, int hC_is_current, int64_t offC, int64_t ldC, int mode);
         int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX);
         int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
                        void* Y, int64_t offY, int64_t incY);

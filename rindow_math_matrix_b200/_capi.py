@@ -44,6 +44,8 @@ SIGNATURES = {
     "rb200_host_free": (i32, [vp]),
     "rb200_sgemm": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32]),
     "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
+    "rb200_sgemm_streamed": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, vp, i64, i64, vp, vp, i64, i64,
+                                   f32, vp, vp, i32, i64, i64, i32]),
     "rb200_scal": (i32, [i32, i64, f64, vp, i64, i64]),
     "rb200_axpy": (i32, [i32, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_copy": (i32, [i32, i64, vp, i64, i64, vp, i64, i64]),

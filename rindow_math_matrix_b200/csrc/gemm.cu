@@ -97,6 +97,121 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     return rb200::gemm_simt<float>(m, n, k, alpha, a, sAm, sAk, b, sBk, sBn, beta, cc, ldC);
 }
 
+}  // extern "C"
+
+// ---- rb200_sgemm_streamed: the host-operand form of sgemm -------------------------------------------
+// For callers whose operands live in (pinned) host memory -- the PHP side's host-indexable buffers.  The
+// copies are part of the call, so they are pipelined instead of serialised: B goes up first, then A (and C
+// when beta != 0) in row stripes on a copy-in stream while the compute stream multiplies the stripes that
+// have landed and a copy-out stream brings finished C stripes back over the other PCIe direction.
+namespace {
+
+struct StreamedState {
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_start = nullptr;
+    cudaEvent_t ev_in[16] = {}, ev_done[16] = {};
+    bool ready = false;
+};
+StreamedState g_streamed;
+
+int streamed_init()
+{
+    StreamedState& st = g_streamed;
+    if (st.ready) return RB200_OK;
+    RB_CUDA(cudaStreamCreateWithFlags(&st.in, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&st.out, cudaStreamNonBlocking));
+    RB_CUDA(cudaEventCreateWithFlags(&st.ev_b, cudaEventDisableTiming));
+    RB_CUDA(cudaEventCreateWithFlags(&st.ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < 16; i++) {
+        RB_CUDA(cudaEventCreateWithFlags(&st.ev_in[i], cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&st.ev_done[i], cudaEventDisableTiming));
+    }
+    st.ready = true;
+    return RB200_OK;
+}
+
+// copy the [rows x cols] view at element offset `off` with leading dimension ld (host <-> device mirrors share
+// the element indexing): one contiguous copy when the rows are dense, a pitched copy otherwise
+int copy_view(float* dst, const float* src, int64_t off, int64_t rows, int64_t cols, int64_t ld,
+              cudaMemcpyKind kind, cudaStream_t stream)
+{
+    if (rows < 1 || cols < 1) return RB200_OK;
+    if (ld == cols || rows == 1) {
+        RB_CUDA(cudaMemcpyAsync(dst + off, src + off, (size_t)((rows - 1) * ld + cols) * sizeof(float), kind, stream));
+    } else {
+        RB_CUDA(cudaMemcpy2DAsync(dst + off, (size_t)ld * sizeof(float), src + off, (size_t)ld * sizeof(float),
+                                  (size_t)cols * sizeof(float), (size_t)rows, kind, stream));
+    }
+    return RB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb200_sgemm_streamed(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                         float alpha, float* dA, const float* hA, int64_t offA, int64_t ldA,
+                         float* dB, const float* hB, int64_t offB, int64_t ldB,
+                         float beta, float* dC, float* hC, int hC_is_current, int64_t offC, int64_t ldC, int mode)
+{
+    bool tA, tB;
+    int rc = decode(order, transA, transB, m, n, k, tA, tB, dA, dB, dC, offA, ldA, offB, ldB, offC, ldC);
+    if (rc != RB200_OK) return rc;
+    rb200::Context& c = rb200::ctx();
+    rc = streamed_init();
+    if (rc != RB200_OK) return rc;
+    StreamedState& st = g_streamed;
+    // decode() swapped m,n for ColMajor: from here on the problem is row-major m x n
+    // everything queued so far on the compute stream (earlier kernels that wrote dA/dB/dC, or read the regions
+    // about to be overwritten) happens-before the first copy
+    RB_CUDA(cudaEventRecord(st.ev_start, c.stream));
+    RB_CUDA(cudaStreamWaitEvent(st.in, st.ev_start, 0));
+    RB_CUDA(cudaStreamWaitEvent(st.out, st.ev_start, 0));
+
+    const int64_t rowsB = tB ? n : k, colsB = tB ? k : n;
+    if (hB) {
+        rc = copy_view(dB, hB, offB, rowsB, colsB, ldB, cudaMemcpyHostToDevice, st.in);
+        if (rc != RB200_OK) return rc;
+    }
+    RB_CUDA(cudaEventRecord(st.ev_b, st.in));
+    RB_CUDA(cudaStreamWaitEvent(c.stream, st.ev_b, 0));
+
+    // row stripes of C (and of op(A)): multiples of 256 rows (the CTA-pair tile), at most 16, at least ~1024 rows
+    int64_t stripes = m / 1024;
+    if (stripes > 16) stripes = 16;
+    if (stripes < 1 || (!hA && !hC)) stripes = 1;
+    int64_t stripe_rows = rb_ceil_div(rb_ceil_div(m, stripes), 256) * 256;
+    stripes = rb_ceil_div(m, stripe_rows);
+    const bool upload_c = (beta != 0.0f) && hC && hC_is_current;
+    for (int64_t s = 0; s < stripes; s++) {
+        const int64_t r0 = s * stripe_rows;
+        const int64_t mr = (m - r0 < stripe_rows) ? m - r0 : stripe_rows;
+        if (hA) {
+            // NoTrans: rows r0.. of the m x k matrix; Trans: columns r0.. of the stored k x m matrix
+            rc = tA ? copy_view(dA, hA, offA + r0, k, mr, ldA, cudaMemcpyHostToDevice, st.in)
+                    : copy_view(dA, hA, offA + r0 * ldA, mr, k, ldA, cudaMemcpyHostToDevice, st.in);
+            if (rc != RB200_OK) return rc;
+        }
+        if (upload_c) {
+            rc = copy_view(dC, hC, offC + r0 * ldC, mr, n, ldC, cudaMemcpyHostToDevice, st.in);
+            if (rc != RB200_OK) return rc;
+        }
+        RB_CUDA(cudaEventRecord(st.ev_in[s], st.in));
+        RB_CUDA(cudaStreamWaitEvent(c.stream, st.ev_in[s], 0));
+        rc = rb200_sgemm(RB200_ROW_MAJOR, transA, transB, mr, n, k, alpha, dA, tA ? offA + r0 : offA + r0 * ldA, ldA,
+                         dB, offB, ldB, beta, dC, offC + r0 * ldC, ldC, mode);
+        if (rc != RB200_OK) return rc;
+        if (hC) {
+            RB_CUDA(cudaEventRecord(st.ev_done[s], c.stream));
+            RB_CUDA(cudaStreamWaitEvent(st.out, st.ev_done[s], 0));
+            rc = copy_view(hC, dC, offC + r0 * ldC, mr, n, ldC, cudaMemcpyDeviceToHost, st.out);
+            if (rc != RB200_OK) return rc;
+        }
+    }
+    if (hC) RB_CUDA(cudaStreamSynchronize(st.out));      // the host may read hC as soon as the call returns
+    return RB200_OK;
+}
+
 int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset,
                          int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
                          int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,

@@ -59,9 +59,15 @@ def code_to_trans(trans: int):                                             # Php
 
 
 class CudaBlas:
+    # rows from which the host-operand GEMM pipelines its transfers (below that one copy + one launch wins)
+    STREAMED_MIN_ROWS = 2048
+
     def __init__(self, gemm_mode: int = _capi.GEMM_AUTO):
         self._lib = _capi.load()
         self.gemm_mode = gemm_mode
+        # None: bring C back eagerly iff the caller already indexes C from the host (its mirror exists);
+        # True / False: always / never.  Only matters for buffers filled or read from the host side.
+        self.host_result_prefetch = None
 
     # ---- meta (PhpBlas.php:49-90) -----------------------------------------------------------
     def getNumThreads(self) -> int:
@@ -87,6 +93,59 @@ class CudaBlas:
 
     def setGemmMode(self, mode: int) -> None:
         self.gemm_mode = mode
+
+    def setHostResultPrefetch(self, flag) -> None:
+        self.host_result_prefetch = flag
+
+    def _gemm_streamed(self, transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB, beta,
+                       C, offsetC, ldC, rowsA, colsA, rowsB, colsB) -> bool:
+        """Host-operand form (rb200_sgemm_streamed): when an operand's current copy is in its pinned mirror
+        and/or the caller reads C from the host, the transfers are pipelined with the multiply instead of
+        flush -> kernel -> fetch.  Returns False when the plain path should run."""
+        if m < self.STREAMED_MIN_ROWS or A is C or B is C:
+            return False
+
+        def whole(buf, off, rows, cols, ld):        # the view is the entire buffer, rows dense
+            return off == 0 and ld == cols and len(buf) == rows * cols
+
+        upA = A.host_pending() and whole(A, offsetA, rowsA, colsA, ldA)
+        upB = B.host_pending() and whole(B, offsetB, rowsB, colsB, ldB) and B is not A
+        if B is A and upA:
+            upB = False                      # one buffer: uploaded once, whole, as "B"
+            upA = False
+            A.flush()
+        want_c = self.host_result_prefetch
+        if want_c is None:
+            want_c = C.has_mirror()
+        downC = bool(want_c) and (whole(C, offsetC, m, n, ldC) or C.mirror_current())
+        if not (upA or upB or downC):
+            return False
+        if A.host_pending() and not upA:
+            A.flush()
+        if B.host_pending() and not upB:
+            B.flush()
+        c_host_current = 0
+        if C.host_pending():
+            if whole(C, offsetC, m, n, ldC) and downC:
+                c_host_current = 1           # uploaded stripe by stripe (only read when beta != 0)
+                C.streamed_uploaded()
+            else:
+                C.flush()
+        if downC:
+            C._ensure_mirror()               # allocate only: the call itself fills it
+        dA, hA = A.raw_pointers()
+        dB, hB = B.raw_pointers()
+        dC, hC = C.raw_pointers()
+        _capi.check(self._lib.rb200_sgemm_streamed(
+            BLAS.RowMajor, transA, transB, m, n, k, alpha, dA, hA if upA else None, offsetA, ldA,
+            dB, hB if upB else None, offsetB, ldB, beta, dC, hC if downC else None, c_host_current,
+            offsetC, ldC, self.gemm_mode))
+        if upA:
+            A.streamed_uploaded()
+        if upB:
+            B.streamed_uploaded()
+        C.streamed_result(downC)
+        return True
 
     # ---- gemm (PhpBlas.php:849-948) -------------------------------------------------------------
     def gemm(self, order, transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB,
@@ -119,12 +178,17 @@ class CudaBlas:
         except (TypeError, ValueError):
             raise RuntimeException("beta is not float")
         # m,n were already swapped for ColMajor: the ABI is called RowMajor
-        a_ptr, b_ptr = A.device_ptr(), B.device_ptr()
-        c_ptr = C.device_ptr_rw()
         if A.dtype() == dtypes.float32:
+            if self._gemm_streamed(transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB, beta,
+                                   C, offsetC, ldC, rowsA, colsA, rowsB, colsB):
+                return
+            a_ptr, b_ptr = A.device_ptr(), B.device_ptr()
+            c_ptr = C.device_ptr_rw()
             _capi.check(self._lib.rb200_sgemm(BLAS.RowMajor, transA, transB, m, n, k, alpha, a_ptr, offsetA, ldA,
                                               b_ptr, offsetB, ldB, beta, c_ptr, offsetC, ldC, self.gemm_mode))
         elif A.dtype() == dtypes.float64:
+            a_ptr, b_ptr = A.device_ptr(), B.device_ptr()
+            c_ptr = C.device_ptr_rw()
             _capi.check(self._lib.rb200_dgemm(BLAS.RowMajor, transA, transB, m, n, k, alpha, a_ptr, offsetA, ldA,
                                               b_ptr, offsetB, ldB, beta, c_ptr, offsetC, ldC))
         else:

@@ -161,6 +161,27 @@ class CudaBuffer:
     def mark_host_written(self) -> None:
         self._host_dirty = True
 
+    # state the streamed (host-operand) GEMM needs: it moves the data itself, pipelined with the multiply
+    def host_pending(self) -> bool:
+        """The host mirror holds writes the device has not seen yet."""
+        return self._host_dirty
+
+    def has_mirror(self) -> bool:
+        return self._host is not None
+
+    def mirror_current(self) -> bool:
+        return self._host is not None and not self._dev_dirty
+
+    def raw_pointers(self):
+        """(device pointer, pinned host pointer or None) WITHOUT any implied transfer."""
+        return self._dptr, self._hptr
+
+    def streamed_uploaded(self) -> None:
+        self._host_dirty = False
+
+    def streamed_result(self, downloaded: bool) -> None:
+        self._dev_dirty = not downloaded
+
     def flush(self) -> None:
         """Make the device copy current (h2d of the mirror if the host wrote to it).  The copy is
         asynchronous on the library stream, i.e. ordered before the next kernel."""
