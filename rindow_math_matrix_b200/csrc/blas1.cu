@@ -108,49 +108,78 @@ int blas1_dispatch(int dtype, int64_t n, double alpha, const void* X, int64_t of
 }
 
 // ---- gemv -------------------------------------------------------------------------------------------
-// NoTrans: one warp per row of A (coalesced along the row, shuffle reduction).  VEC: 16-byte loads of A and X
-// (ldA, the offsets and the base pointers 16-byte aligned, incX == 1), four packs in flight per lane.
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(B1_THREADS)
-gemv_n_kernel(int64_t m, int64_t n, T alpha, const T* __restrict__ A, int64_t ldA,
+// NoTrans: SPLIT warps per row of A (coalesced along the row, shuffle reduction, shared-memory add of the SPLIT
+// parts in index order; SPLIT > 1 only for matrices with too few rows to occupy the SMs).  Compiled for 8
+// CTAs per SM (<= 32 registers) so that the 8192 rows of the bench shape are all resident in ONE wave: with 4
+// CTAs per SM the same launch is 1.73 waves and pays the tail.  VEC: 16-byte loads of A and X (ldA, the
+// offsets and the base pointers 16-byte aligned, incX == 1), four packs in flight per lane.
+constexpr int GEMV_PACKS = 2;     // 16-byte packs of A in flight per lane: <= 32 registers, 64 warps resident per SM
+
+template <typename T, bool VEC, int SPLIT>
+__global__ void __launch_bounds__(B1_THREADS, SPLIT == 1 ? 8 : 6)
+gemv_n_kernel(int64_t m, int64_t n, int64_t part_cols, T alpha, const T* __restrict__ A, int64_t ldA,
               const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY)
 {
     constexpr int V = 16 / (int)sizeof(T);
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (B1_THREADS / 32);
-    for (int64_t i = (int64_t)blockIdx.x * (B1_THREADS / 32) + (threadIdx.x >> 5); i < m; i += warps) {
-        const T* row = A + i * ldA;
+    constexpr int WARPS = B1_THREADS / 32;
+    constexpr int RPC = WARPS / SPLIT;              // rows per CTA-unit
+    __shared__ T parts[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_local = warp / SPLIT, part = warp % SPLIT;
+    const int64_t c_begin = (int64_t)part * part_cols;
+    const int64_t c_end = (c_begin + part_cols < n) ? c_begin + part_cols : n;
+    const int64_t units = (m + RPC - 1) / RPC;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int64_t i = u * RPC + row_local;
         T acc = (T)0;
-        int64_t j0 = 0;
-        if (VEC) {
-            const int64_t nv = n / V;
-            const int4* rv = reinterpret_cast<const int4*>(row);
-            const int4* xv = reinterpret_cast<const int4*>(X);
-            for (int64_t jb = 0; jb < nv; jb += 32 * 4) {
-                B1Pack<T> a[4], x[4];
+        if (i < m && c_begin < c_end) {
+            const T* row = A + i * ldA;
+            int64_t j0 = c_begin;
+            if (VEC) {                               // part_cols is a multiple of V on this path
+                const int64_t v0 = c_begin / V, v1 = c_end / V;
+                const int4* rv = reinterpret_cast<const int4*>(row);
+                const int4* xv = reinterpret_cast<const int4*>(X);
+                for (int64_t jb = v0; jb < v1; jb += 32 * GEMV_PACKS) {
+                    B1Pack<T> a[GEMV_PACKS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int64_t jv = jb + u * 32 + lane;
-                    if (jv < nv) { a[u].raw = __ldcs(rv + jv); x[u].raw = __ldg(xv + jv); }
-                }
+                    for (int q = 0; q < GEMV_PACKS; q++) {
+                        const int64_t jv = jb + q * 32 + lane;
+                        if (jv < v1) a[q].raw = __ldcs(rv + jv);
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int64_t jv = jb + u * 32 + lane;
-                    if (jv < nv) {
+                    for (int q = 0; q < GEMV_PACKS; q++) {
+                        const int64_t jv = jb + q * 32 + lane;
+                        if (jv < v1) {
+                            B1Pack<T> x;
+                            x.raw = __ldg(xv + jv);
 #pragma unroll
-                        for (int e = 0; e < V; e++) acc = fma(alpha * a[u].v[e], x[u].v[e], acc);
+                            for (int e = 0; e < V; e++) acc = fma(alpha * a[q].v[e], x.v[e], acc);
+                        }
                     }
                 }
+                j0 = v1 * V;
             }
-            j0 = nv * V;
-        }
 #pragma unroll 4
-        for (int64_t j = j0 + lane; j < n; j += 32) acc = fma(alpha * __ldcs(row + j), __ldg(X + j * incX), acc);
+            for (int64_t j = j0 + lane; j < c_end; j += 32) acc = fma(alpha * __ldcs(row + j), __ldg(X + j * incX), acc);
+        }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        if (lane == 0) {
-            T* y = Y + i * incY;
-            *y = (beta == (T)0) ? acc : fma(beta, *y, acc);
+        for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+        if (SPLIT == 1) {
+            if (lane == 0 && i < m) {
+                T* y = Y + i * incY;
+                *y = (beta == (T)0) ? acc : fma(beta, *y, acc);
+            }
+        } else {
+            if (lane == 0) parts[warp] = acc;
+            __syncthreads();
+            if (part == 0 && lane == 0 && i < m) {
+                T sum = parts[warp];
+#pragma unroll
+                for (int q = 1; q < SPLIT; q++) sum += parts[warp + q];
+                T* y = Y + i * incY;
+                *y = (beta == (T)0) ? sum : fma(beta, *y, sum);
+            }
+            __syncthreads();
         }
     }
 }
@@ -158,12 +187,15 @@ gemv_n_kernel(int64_t m, int64_t n, T alpha, const T* __restrict__ A, int64_t ld
 // Trans: Y[j] = sum_i (alpha*A[i,j])*X[i]; thread (tx,ty) owns CPT adjacent columns (CPT = 16 bytes worth when
 // A's rows are 16-byte aligned, else 1) of column block blockIdx.x and rows ty, ty+8, ... of the row segment
 // blockIdx.y (coalesced along j); shared-memory tree over ty.  With one segment the CTA finishes Y itself,
-// otherwise it writes a partial row into the workspace and gemv_t_merge_kernel adds the segments in index
-// order (deterministic, no atomics).
+// otherwise it writes a partial row into the workspace and the last CTA of the column block to finish (ticket)
+// adds the segments in a fixed order -- one launch, deterministic.
+constexpr int GEMV_T_PACKS = 4;
+
 template <typename T, int CPT>
 __global__ void __launch_bounds__(B1_THREADS)
 gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restrict__ A, int64_t ldA,
-              const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY, T* __restrict__ partial)
+              const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY, T* __restrict__ partial,
+              int* __restrict__ counters)
 {
     __shared__ T sm[8][32 * CPT + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -181,19 +213,20 @@ gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restri
         }
     } else if (j < n) {                    // n % CPT == 0 on this path: a pack never straddles the edge
         const T* a = A + j;
-        for (int64_t ib = i0 + ty; ib < i1; ib += 8 * 4) {
-            B1Pack<T> v[4];
-            T x[4];
+        for (int64_t ib = i0 + ty; ib < i1; ib += 8 * GEMV_T_PACKS) {
+            B1Pack<T> v[GEMV_T_PACKS];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < GEMV_T_PACKS; u++) {
                 const int64_t i = ib + u * 8;
-                if (i < i1) { v[u].raw = __ldcs(reinterpret_cast<const int4*>(a + i * ldA)); x[u] = __ldg(X + i * incX); }
+                if (i < i1) v[u].raw = __ldcs(reinterpret_cast<const int4*>(a + i * ldA));
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (ib + u * 8 < i1) {
+            for (int u = 0; u < GEMV_T_PACKS; u++) {
+                const int64_t i = ib + u * 8;
+                if (i < i1) {
+                    const T x = __ldg(X + i * incX);
 #pragma unroll
-                    for (int e = 0; e < CPT; e++) acc[e] = fma(alpha * v[u].v[e], x[u], acc[e]);
+                    for (int e = 0; e < CPT; e++) acc[e] = fma(alpha * v[u].v[e], x, acc[e]);
                 }
             }
         }
@@ -215,18 +248,42 @@ gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restri
             }
         }
     }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(B1_THREADS)
-gemv_t_merge_kernel(int64_t n, int segs, const T* __restrict__ partial, T beta, T* __restrict__ Y, int64_t incY)
-{
-    const int64_t j = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x;
-    if (j >= n) return;
-    T s = partial[j];
-    for (int g = 1; g < segs; g++) s += partial[(int64_t)g * n + j];
-    T* y = Y + j * incY;
-    *y = (beta == (T)0) ? s : fma(beta, *y, s);
+    if (!partial) return;
+    // the last CTA of this column block to finish adds the segment partials in a fixed order (one launch,
+    // deterministic): thread (c, r) sums segments r, r+8, ...; shared-memory tree over r
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* ctr = counters + blockIdx.x;
+        const int ticket = atomicAdd(ctr, 1);
+        is_last = (ticket == (int)gridDim.y - 1);
+        if (is_last) *ctr = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int segs = (int)gridDim.y;
+    for (int c0 = 0; c0 < 32 * CPT; c0 += 32) {
+        const int c = c0 + tx;
+        const int64_t jc = (int64_t)blockIdx.x * 32 * CPT + c;
+        T a = (T)0;
+        if (jc < n) {
+            for (int g = ty; g < segs; g += 8) a += __ldcg(partial + (int64_t)g * n + jc);
+        }
+        sm[ty][c] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * CPT; c += B1_THREADS) {
+        const int64_t jc = (int64_t)blockIdx.x * 32 * CPT + c;
+        if (jc < n) {
+            T s2 = sm[0][c];
+#pragma unroll
+            for (int r = 1; r < 8; r++) s2 += sm[r][c];
+            T* y = Y + jc * incY;
+            *y = (beta == (T)0) ? s2 : fma(beta, *y, s2);
+        }
+    }
 }
 
 template <typename T>
@@ -240,39 +297,57 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
     T* Y = reinterpret_cast<T*>(Yv) + offY;
     const bool a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (ldA % V == 0);
     if (!trans) {
-        int64_t grid = rb_ceil_div(m, B1_THREADS / 32);
-        const int64_t cap = (int64_t)c.sm_count * 32;
-        if (grid > cap) grid = cap;
         const bool vec = a_vec && incX == 1 && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && n >= V;
-        if (vec) gemv_n_kernel<T, true><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
-        else gemv_n_kernel<T, false><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>(m, n, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY);
+        static int resident = 0;
+        if (!resident) {
+            int per_sm = 0;
+            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_n_kernel<T, true, 1>, B1_THREADS, 0));
+            resident = (per_sm > 0 ? per_sm : 1) * c.sm_count;
+        }
+        // one warp per row; rows are split over 2/4/8 warps only when there are too few of them to occupy the SMs
+        int split = 1;
+        while (split < 8 && n / (split * 2) >= 512 && rb_ceil_div(m * split, B1_THREADS / 32) * 2 <= resident) split *= 2;
+        const int64_t units = rb_ceil_div(m * split, B1_THREADS / 32);
+        int64_t grid = units < resident ? units : resident;
+        int64_t part_cols = rb_ceil_div(rb_ceil_div(n, split), 128) * 128;
+#define RB_GEMV_N(VEC_, SP_) gemv_n_kernel<T, VEC_, SP_><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>( \
+            m, n, part_cols, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY)
+        if (vec) { if (split == 1) RB_GEMV_N(true, 1); else if (split == 2) RB_GEMV_N(true, 2);
+                   else if (split == 4) RB_GEMV_N(true, 4); else RB_GEMV_N(true, 8); }
+        else     { if (split == 1) RB_GEMV_N(false, 1); else if (split == 2) RB_GEMV_N(false, 2);
+                   else if (split == 4) RB_GEMV_N(false, 4); else RB_GEMV_N(false, 8); }
+#undef RB_GEMV_N
         RB_LAUNCH_CHECK("gemv_n_kernel");
     } else {
         const bool vec = a_vec && (n % V == 0);
         const int64_t gx = rb_ceil_div(n, vec ? 32 * V : 32);
         if (gx > 0x7fffffffLL) RB_INVALID("gemv: n too large");
-        // row segments: enough CTAs for ~8 per SM, at least 64 rows each
-        int64_t segs = rb_ceil_div((int64_t)c.sm_count * 8, gx);
+        // row segments: one full wave of resident CTAs, at least 64 rows each
+        static int t_resident = 0;
+        if (!t_resident) {
+            int per_sm = 0;
+            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_t_kernel<T, V>, B1_THREADS, 0));
+            t_resident = (per_sm > 0 ? per_sm : 1) * c.sm_count;
+        }
+        int64_t segs = t_resident / gx;
         if (segs > m / 64) segs = m / 64;
         if (segs < 1) segs = 1;
         if (segs > 1024) segs = 1024;
         const int64_t seg_rows = rb_ceil_div(m, segs);
         segs = rb_ceil_div(m, seg_rows);
         T* partial = nullptr;
+        int* counters = nullptr;
         if (segs > 1) {
             int rc = rb200::ensure_workspace((size_t)segs * (size_t)n * sizeof(T));
             if (rc != RB200_OK) return rc;
             partial = reinterpret_cast<T*>(c.workspace);
+            rc = rb200::ensure_counters(gx, &counters);
+            if (rc != RB200_OK) return rc;
         }
         const dim3 grid((unsigned)gx, (unsigned)segs);
-        if (vec) gemv_t_kernel<T, V><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
-        else gemv_t_kernel<T, 1><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial);
+        if (vec) gemv_t_kernel<T, V><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
+        else gemv_t_kernel<T, 1><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
         RB_LAUNCH_CHECK("gemv_t_kernel");
-        if (segs > 1) {
-            gemv_t_merge_kernel<T><<<(unsigned)rb_ceil_div(n, B1_THREADS), B1_THREADS, 0, c.stream>>>(
-                n, (int)segs, partial, (T)beta, Y, incY);
-            RB_LAUNCH_CHECK("gemv_t_merge_kernel");
-        }
     }
     return RB200_OK;
 }

@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Time the HBM-bound ops at BASELINE sizes with CUDA events (rotating operand sets) -- a quick loop for
+kernel work; bench.py's hbm_ops is the reported number.  Usage: hbm_quick.py [op ...]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch  # noqa: E402
+import rindow_math_matrix_b200 as rb  # noqa: E402
+from rindow_math_matrix_b200 import BLAS, CudaBuffer, _capi, dtypes  # noqa: E402
+
+
+def main():
+    want = set(sys.argv[1:])
+    svc = rb.MatlibCuda()
+    math, blas = svc.math(), svc.blas()
+    f32 = dtypes.float32
+    rng = np.random.default_rng(0)
+    stream = torch.cuda.Stream()
+    _capi.set_stream(stream.cuda_stream)              # kernels + events on the same stream
+
+    def rnd(n):
+        return CudaBuffer(n, f32, zero=False).from_numpy(rng.uniform(-1, 1, n).astype(np.float32))
+
+    def timed(name, fn, nbytes, sets=3, reps=30):
+        if want and name not in want:
+            return
+        for i in range(6):
+            fn(i % sets)
+        _capi.sync()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(reps):
+                fn(i % sets)
+            e1.record(stream)
+            _capi.sync()
+            best = min(best, e0.elapsed_time(e1) / reps)
+        print("%-16s %.4f ms  %7.0f GB/s  frac %.3f" % (name, best, nbytes / best / 1e6, nbytes / best / 1e6 / 6543.4), flush=True)
+
+    m, n = 8192, 4096
+    As = [rnd(m * n) for _ in range(3)]
+    Y2 = rnd(m * n)
+    X, Xm, Yn, Ym = rnd(n), rnd(m), CudaBuffer(n, f32), CudaBuffer(m, f32)
+    timed("copy", lambda i: blas.copy(m * n, As[i], 0, 1, Y2, 0, 1), 2 * m * n * 4)
+    timed("axpy", lambda i: blas.axpy(m * n, 0.5, As[i], 0, 1, Y2, 0, 1), 3 * m * n * 4)
+    timed("transpose", lambda i: blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, As[i], 0, n, Y2, 0, m), 2 * m * n * 4)
+    timed("gemv", lambda i: blas.gemv(BLAS.RowMajor, BLAS.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Ym, 0, 1), m * n * 4)
+    timed("gemv_trans", lambda i: blas.gemv(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, As[i], 0, n, Xm, 0, 1, 0.0, Yn, 0, 1), m * n * 4)
+    timed("add", lambda i: math.add(False, m, n, 1.0, X, 0, 1, As[i], 0, n), 2 * m * n * 4)
+    del As, Y2
+    m, n = 65536, 1024
+    Rs = [rnd(m * n) for _ in range(3)]
+    Bf = CudaBuffer(m, f32)
+    timed("reduce_sum", lambda i: math.reduceSum(m, n, 1, Rs[i], 0, Bf, 0), m * n * 4)
+    timed("reduce_sum_axis0", lambda i: math.reduceSum(1, m, n, Rs[i], 0, Bf, 0), m * n * 4)
+    timed("softmax", lambda i: math.softmax(m, n, Rs[i], 0, n), 2 * m * n * 4)
+
+
+if __name__ == "__main__":
+    main()
