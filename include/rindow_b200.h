@@ -170,6 +170,71 @@ int rb200_add(int dtype, int trans, int64_t m, int64_t n, double alpha,
 int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,
                    const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
 
+/* ---- the rest of the broadcast family: replaces PhpMath::maximum (:274),
+ *      minimum (:318), greater (:362), greaterEqual (:404), less (:446), lessEqual (:488), pow (:687),
+ *      duplicate (:860).  Same A[m,n] / X broadcast rule as rb200_add (trans: X has m elements, one per row;
+ *      the PHP methods without a $trans argument pass 0).  In place on A; float32/float64/int32/int64.
+ *        MAXIMUM/MINIMUM: a NaN in X is written, a NaN already in A stays (:300-309).
+ *        GREATER..LESS_EQUAL: A := (A op X) ? 1 : 0 in A's dtype; every NaN operand compares false.
+ *        POW: A := A ** X.   DUPLICATE: A := X (A is not read). ------------------------------------------ */
+#define RB200_BC_MAXIMUM        0
+#define RB200_BC_MINIMUM        1
+#define RB200_BC_GREATER        2
+#define RB200_BC_GREATER_EQUAL  3
+#define RB200_BC_LESS           4
+#define RB200_BC_LESS_EQUAL     5
+#define RB200_BC_POW            6
+#define RB200_BC_DUPLICATE      7
+int rb200_broadcast(int dtype, int op, int trans, int64_t m, int64_t n,
+                    void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX);
+
+/* ---- unary family, in place on X (n elements, stride incX): replaces PhpMath::increment (:221, X := alpha*X +
+ *      beta), reciprocal (:244, 1/(alpha*X+beta), INF when the denominator is 0), square (:611), sqrt (:634),
+ *      rsqrt (:657, 1/(alpha*sqrt(X)+beta), INF at 0), exp (:727), log (:749), tanh (:772), sin (:794), cos (:816),
+ *      tan (:838), not (:1528, X := (X == 0) ? 1 : 0), nan2num (:2830, NaN -> alpha), isnan (:2853, 1.0 / 0.0).
+ *      alpha / beta are ignored by the ops that have none.  float32/float64; NOT also int32/int64/bool/uint8. -- */
+#define RB200_UN_INCREMENT   0
+#define RB200_UN_RECIPROCAL  1
+#define RB200_UN_SQUARE      2
+#define RB200_UN_SQRT        3
+#define RB200_UN_RSQRT       4
+#define RB200_UN_EXP         5
+#define RB200_UN_LOG         6
+#define RB200_UN_TANH        7
+#define RB200_UN_SIN         8
+#define RB200_UN_COS         9
+#define RB200_UN_TAN         10
+#define RB200_UN_NOT         11
+#define RB200_UN_NAN2NUM     12
+#define RB200_UN_ISNAN       13
+int rb200_unary(int dtype, int op, int64_t n, double alpha, void* X, int64_t offX, int64_t incX, double beta);
+
+/* Y := (Y == X) ? 1 : 0  /  (Y != X) ? 1 : 0  -- PhpMath::equal (:1470) / notEqual (:1499); any dtype. */
+#define RB200_CMP_EQUAL      0
+#define RB200_CMP_NOT_EQUAL  1
+int rb200_compare(int dtype, int op, int64_t n, const void* X, int64_t offX, int64_t incX,
+                  void* Y, int64_t offY, int64_t incY);
+
+/* Y[to_dtype] := cast(X[from_dtype]) -- PhpMath::astype (:1710-1778): to bool = (x != 0); to float = (float)x;
+ * to int = truncation toward zero (PHP (int)), unsigned targets keep the low 8/16/32 bits (the $mask). */
+int rb200_astype(int64_t n, int from_dtype, const void* X, int64_t offX, int64_t incX,
+                 int to_dtype, void* Y, int64_t offY, int64_t incY);
+
+/* ---- scalar results (the call returns after the value is on the host): PhpMath::sum (:150), imax (:171: first
+ *      maximum, a NaN running value is replaced by the next element), imin (:196: first minimum, NaN at 0 stays).
+ *      These are what MatrixOperator::sum/max/argMax/min/argMin call (MatrixOperator.php:820-931). --------- */
+int rb200_sum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+int rb200_imax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+int rb200_imin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+
+/* Y[i, (int)X[i]] += a for i < m -- PhpMath::updateAddOnehot (:1438-1464), what LinearAlgebra::onehot (:3095)
+ * calls.  X holds the labels (any real dtype), Y is float32/float64 with row stride ldY.  A label outside
+ * [0,n) returns RB200_E_RANGE (the reference throws RuntimeException 'Label number is out of bounds.'); the
+ * call synchronises to report it. */
+#define RB200_E_RANGE        -6
+int rb200_onehot(int dtype_x, int dtype_y, int64_t m, int64_t n, double a,
+                 const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t ldY);
+
 /* ---- reductions over the middle axis of A[m,n,k] -> B[m,k]
  *      replaces PhpMath::reduceSum/reduceMax/reduceArgMax (PhpMath.php:1552-1643) ------- */
 int rb200_reduce_sum(int dtype, int64_t m, int64_t n, int64_t k,

@@ -32,6 +32,10 @@ class OracleZeroDivide(RuntimeError):
     """Stands for RuntimeException('Zero divide in softmax.') (PhpMath.php:1663)."""
 
 
+class OracleLabelRange(RuntimeError):
+    """Stands for RuntimeException('Label number is out of bounds.') (PhpMath.php:1461)."""
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "rindow_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or (
@@ -68,7 +72,14 @@ def lib() -> ctypes.CDLL:
         L.ro_softmax.argtypes = [i64, i64, p, i64, i64, i64]
         L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
-        for name in ("ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        L.ro_broadcast.argtypes = [i32, i32, i64, i64, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_unary.argtypes = [i32, i64, dbl, p, i64, i64, i64, dbl]
+        L.ro_compare.argtypes = [i32, i64, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_sum.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_imax.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_imin.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_onehot.argtypes = [i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
+        for name in ("ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -92,6 +103,8 @@ def _check(rc: int) -> None:
         raise OracleArgumentError("invalid argument (reference: InvalidArgumentException)")
     if rc == -2:
         raise OracleZeroDivide("Zero divide in softmax.")
+    if rc == -3:
+        raise OracleLabelRange("Label number is out of bounds.")
     if rc != 0:
         raise RuntimeError("oracle rc=%d" % rc)
 
@@ -159,6 +172,68 @@ def add(trans, m, n, alpha, X, offX, incX, A, offA, ldA):
 def multiply(trans, m, n, X, offX, incX, A, offA, ldA):
     _check(lib().ro_multiply(int(bool(trans)), m, n, _ptr(_buf(X)), X.size, offX, incX,
                              _ptr(_buf(A)), A.size, offA, ldA))
+
+
+# broadcast family: PhpMath::maximum :274, minimum :318, greater :362, greaterEqual :404, less :446, lessEqual :488
+# (A[m,n] against X[n]; no trans), pow :687 and duplicate :860 (trans like add).  op = BC_* below.
+BC_MAXIMUM, BC_MINIMUM, BC_GREATER, BC_GREATER_EQUAL, BC_LESS, BC_LESS_EQUAL, BC_POW, BC_DUPLICATE = range(8)
+
+
+def broadcast(op, trans, m, n, A, offA, ldA, X, offX, incX):
+    _check(lib().ro_broadcast(op, int(bool(trans)), m, n, _ptr(_buf(A)), A.size, offA, ldA,
+                              _ptr(_buf(X)), X.size, offX, incX))
+
+
+# unary family: PhpMath::increment :221, reciprocal :244, square :611, sqrt :634, rsqrt :657, exp :727, log :749,
+# tanh :772, sin :794, cos :816, tan :838, not :1528, nan2num :2830, isnan :2853.  op = UN_* below.
+(UN_INCREMENT, UN_RECIPROCAL, UN_SQUARE, UN_SQRT, UN_RSQRT, UN_EXP, UN_LOG, UN_TANH, UN_SIN, UN_COS, UN_TAN,
+ UN_NOT, UN_NAN2NUM, UN_ISNAN) = range(14)
+
+
+def unary(op, n, X, offX, incX, alpha=1.0, beta=0.0):
+    _check(lib().ro_unary(op, n, float(alpha), _ptr(_buf(X)), X.size, offX, incX, float(beta)))
+
+
+# PhpMath::equal :1470 / notEqual :1499
+def compare(not_equal, n, X, offX, incX, Y, offY, incY):
+    _check(lib().ro_compare(int(bool(not_equal)), n, _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+# PhpMath::sum :150, imax :171, imin :196
+def sum(n, X, offX, incX):
+    out = ctypes.c_double(0.0)
+    _check(lib().ro_sum(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def imax(n, X, offX, incX):
+    out = ctypes.c_int64(0)
+    _check(lib().ro_imax(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def imin(n, X, offX, incX):
+    out = ctypes.c_int64(0)
+    _check(lib().ro_imin(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+# PhpMath::updateAddOnehot :1438
+def onehot(m, n, a, X, offX, incX, Y, offY, ldY):
+    _check(lib().ro_onehot(m, n, float(a), _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, ldY))
+
+
+# PhpMath::astype :1710-1778 on the PHP value model (numpy restatement: integer / byte work).  X is the float64 or
+# int64 flat buffer; returns what the PHP loop stores: bool -> 1/0, float target -> (float)x, integer target ->
+# (int)x truncated toward zero, unsigned 8/16/32 targets masked to their low bits.
+def astype(n, to_kind, mask, X, offX, incX):
+    x = X[offX:offX + (n - 1) * incX + 1:incX]
+    if to_kind == "bool":
+        return (x != 0).astype(np.int64)
+    if to_kind == "float":
+        return x.astype(np.float64)
+    v = np.trunc(x).astype(np.int64) if x.dtype.kind == "f" else x.astype(np.int64)
+    return (v & mask) if mask else v
 
 
 # PhpMath::reduceSum, PhpMath.php:1552-1579

@@ -526,4 +526,147 @@ int ro_omatcopy(int order, int trans, int64_t m, int64_t n, double alpha,
     return RO_OK;
 }
 
+/* ---- the rest of the broadcast family: PhpMath.php:274-528 (maximum, minimum,
+ *      greater, greaterEqual, less, lessEqual: A[m,n] against X[n], no $trans), :687-722 (pow) and :860-891
+ *      (duplicate), which take $trans like add.  op codes = RB200_BC_* of include/rindow_b200.h. ------------ */
+int ro_broadcast(int op, int trans, int64_t m, int64_t n,
+                 double *A, int64_t countA, int64_t offA, int64_t ldA,
+                 const double *X, int64_t countX, int64_t offX, int64_t incX)
+{
+    if (op <= 5) {                                               /* maximum .. lessEqual */
+        if (trans) return RO_E_ARG;                              /* these methods have no $trans */
+        if (m <= 0 || n <= 0) return RO_E_ARG;                   /* :285-287 */
+        if ((m - 1) * ldA + (n - 1) + offA >= countA) return RO_E_ARG;   /* "Matrix A is too small" */
+        if ((n - 1) * incX + offX >= countX) return RO_E_ARG;            /* "Buffer X is too small" */
+        int64_t lna = offA;
+        for (int64_t i = 0; i < m; i++, lna += ldA) {
+            int64_t idx = offX, ida = lna;
+            for (int64_t j = 0; j < n; j++, idx += incX, ida++) {
+                double v = X[idx];
+                switch (op) {
+                    case 0: if (isnan(v)) A[ida] = v; else if (A[ida] < v) A[ida] = v; break;   /* :300-309 */
+                    case 1: if (isnan(v)) A[ida] = v; else if (A[ida] > v) A[ida] = v; break;   /* :344-353 */
+                    case 2: A[ida] = (A[ida] >  v) ? 1.0 : 0.0; break;                          /* :390-395 */
+                    case 3: A[ida] = (A[ida] >= v) ? 1.0 : 0.0; break;
+                    case 4: A[ida] = (A[ida] <  v) ? 1.0 : 0.0; break;
+                    default: A[ida] = (A[ida] <= v) ? 1.0 : 0.0; break;
+                }
+            }
+        }
+        return RO_OK;
+    }
+    if (op != 6 && op != 7) return RO_E_ARG;
+    int64_t rows = !trans ? m : n, cols = !trans ? n : m;       /* :700-712 / :873-885 */
+    if (offX + (cols - 1) * incX >= countX) return RO_E_ARG;
+    if (offA + (m - 1) * ldA + (n - 1) >= countA) return RO_E_ARG;
+    int64_t incAj = !trans ? ldA : 1, incAi = !trans ? 1 : ldA;
+    int64_t idAj = offA;
+    for (int64_t j = 0; j < rows; j++, idAj += incAj) {
+        int64_t idA = idAj, idX = offX;
+        for (int64_t i = 0; i < cols; i++, idA += incAi, idX += incX) {
+            A[idA] = (op == 6) ? pow(A[idA], X[idX]) : X[idX];
+        }
+    }
+    return RO_OK;
+}
+
+/* ---- unary family, in place: PhpMath.php:221-268 (increment, reciprocal), :611-682 (square, sqrt, rsqrt),
+ *      :727-855 (exp, log, tanh, sin, cos, tan), :1528-1547 (not), :2830-2875 (nan2num, isnan).
+ *      op codes = RB200_UN_*. ------------------------------------------------------------------------------- */
+int ro_unary(int op, int64_t n, double alpha, double *X, int64_t countX, int64_t offX, int64_t incX, double beta)
+{
+    if (offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    int64_t idx = offX;
+    for (int64_t i = 0; i < n; i++, idx += incX) {
+        double t = X[idx], r;
+        switch (op) {
+            case 0: r = alpha * t + beta; break;
+            case 1: t = alpha * t + beta; r = (t == 0.0) ? INFINITY : 1 / t; break;
+            case 2: r = t * t; break;
+            case 3: r = sqrt(t); break;
+            case 4: t = alpha * sqrt(t) + beta; r = (t != 0.0) ? 1 / t : INFINITY; break;
+            case 5: r = exp(t); break;
+            case 6: r = log(t); break;
+            case 7: r = tanh(t); break;
+            case 8: r = sin(t); break;
+            case 9: r = cos(t); break;
+            case 10: r = tan(t); break;
+            case 11: r = (t == 0.0) ? 1.0 : 0.0; break;
+            case 12: r = isnan(t) ? alpha : t; break;
+            case 13: r = isnan(t) ? 1.0 : 0.0; break;
+            default: return RO_E_ARG;
+        }
+        X[idx] = r;
+    }
+    return RO_OK;
+}
+
+/* equal / notEqual: PhpMath.php:1470-1522.  ne = 0: Y := (Y == X) ? 1 : 0;  ne = 1: Y := (Y != X) ? 1 : 0 */
+int ro_compare(int ne, int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX,
+               double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    if (offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    int64_t idX = offX, idY = offY;
+    for (int64_t i = 0; i < n; i++, idX += incX, idY += incY) {
+        if (!ne) Y[idY] = (Y[idY] == X[idX]) ? 1.0 : 0.0;
+        else     Y[idY] = (Y[idY] != X[idX]) ? 1.0 : 0.0;
+    }
+    return RO_OK;
+}
+
+/* sum / imax / imin: PhpMath.php:150-216 */
+int ro_sum(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, double *result)
+{
+    if (offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    *result = ro_math_sum(n, X, offX, incX);
+    return RO_OK;
+}
+
+int ro_imax(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, int64_t *result)
+{
+    if (offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    int64_t idx = offX + incX, best = 0;
+    double acc = X[offX];
+    for (int64_t i = 1; i < n; i++, idx += incX) {
+        if (acc < X[idx] || isnan(acc)) {                        /* :185 */
+            acc = X[idx];
+            best = i;
+        }
+    }
+    *result = best;
+    return RO_OK;
+}
+
+int ro_imin(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, int64_t *result)
+{
+    if (offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    int64_t idx = offX + incX, best = 0;
+    double acc = X[offX];
+    for (int64_t i = 1; i < n; i++, idx += incX) {
+        if (acc > X[idx]) {                                      /* :210 */
+            acc = X[idx];
+            best = i;
+        }
+    }
+    *result = best;
+    return RO_OK;
+}
+
+#define RO_E_RANGE -3   /* RuntimeException('Label number is out of bounds.') */
+/* updateAddOnehot: PhpMath.php:1438-1464 (rows before a bad label are already updated, as in the PHP loop) */
+int ro_onehot(int64_t m, int64_t n, double a, const double *X, int64_t countX, int64_t offX, int64_t incX,
+              double *Y, int64_t countY, int64_t offY, int64_t ldY)
+{
+    if (offX + (m - 1) * incX >= countX) return RO_E_ARG;
+    if (offY + (m - 1) * ldY + (n - 1) >= countY) return RO_E_ARG;
+    int64_t idx = offX, idy = offY;
+    for (int64_t i = 0; i < m; i++, idy += ldY, idx += incX) {
+        int64_t label = (int64_t)X[idx];
+        if (label >= n || label < 0) return RO_E_RANGE;
+        Y[idy + label] = Y[idy + label] + a;
+    }
+    return RO_OK;
+}
+
 int ro_abi_version(void) { return 1; }

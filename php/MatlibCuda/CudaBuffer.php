@@ -68,6 +68,15 @@ class CudaBuffer implements LinearBuffer
 
     public function dtype() : int { return $this->dtype; }
     public function abiDtype() : int { return $this->abiDtype; }
+    /** polite-math dtype constant -> C ABI dtype code (the one mapping table, see table()) */
+    public static function abiDtypeOf(int $dtype) : int
+    {
+        $t = self::table();
+        if (!isset($t[$dtype])) {
+            throw new InvalidArgumentException('dtype must be type of integer or float: '.$dtype);
+        }
+        return $t[$dtype][0];
+    }
     public function value_size() : int { return $this->valueSize; }
     public function count() : int { return $this->size; }
 

@@ -59,6 +59,18 @@ class CudaFFI
                       const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
         int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,
                            const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+        int rb200_broadcast(int dtype, int op, int trans, int64_t m, int64_t n,
+                            void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX);
+        int rb200_unary(int dtype, int op, int64_t n, double alpha, void* X, int64_t offX, int64_t incX, double beta);
+        int rb200_compare(int dtype, int op, int64_t n, const void* X, int64_t offX, int64_t incX,
+                          void* Y, int64_t offY, int64_t incY);
+        int rb200_astype(int64_t n, int from_dtype, const void* X, int64_t offX, int64_t incX,
+                         int to_dtype, void* Y, int64_t offY, int64_t incY);
+        int rb200_sum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+        int rb200_imax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+        int rb200_imin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+        int rb200_onehot(int dtype_x, int dtype_y, int64_t m, int64_t n, double a,
+                         const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t ldY);
         int rb200_reduce_sum(int dtype, int64_t m, int64_t n, int64_t k,
                              const void* A, int64_t offA, void* B, int64_t offB);
         int rb200_reduce_max(int dtype, int64_t m, int64_t n, int64_t k,

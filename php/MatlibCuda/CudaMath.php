@@ -119,4 +119,169 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    // ---- SURVEY.md section 8(f) widening: the rest of the broadcast family, the unary family, equal / notEqual /
+    //      not, astype, sum / imax / imin, updateAddOnehot.  Op codes: RB200_BC_* / RB200_UN_* / RB200_CMP_*
+    //      of include/rindow_b200.h.  Validation and messages are PhpMath's own (PhpMath.php:274-528, 687-722,
+    //      860-891, 221-268, 611-682, 727-855, 1470-1547, 1710-1778, 150-216, 1438-1464).
+    protected function anyOnDevice(Buffer ...$buffers) : bool
+    {
+        foreach ($buffers as $b) {
+            if (!($b instanceof CudaBuffer)) { return false; }
+        }
+        return true;
+    }
+
+    protected function broadcastMN(string $name,int $op,int $m,int $n,
+        Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    {
+        if (!$this->onDevice($A,$X) || $A->dtype()!=$X->dtype()) {
+            parent::$name($m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); return;
+        }
+        if ($m<=0 || $n<=0) throw new InvalidArgumentException("m and n must be greater than 0");
+        if (($m-1)*$ldA+($n-1)+$offsetA>=count($A)) throw new InvalidArgumentException("Matrix A is too small");
+        if (($n-1)*$incX+$offsetX>=count($X)) throw new InvalidArgumentException("Buffer X is too small");
+        CudaFFI::check(CudaFFI::lib()->rb200_broadcast($A->abiDtype(),$op,0,$m,$n,
+            $A->devicePtrRW(),$offsetA,$ldA,$X->devicePtr(),$offsetX,$incX));
+    }
+    public function maximum(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('maximum',0,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+    public function minimum(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('minimum',1,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+    public function greater(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('greater',2,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+    public function greaterEqual(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('greaterEqual',3,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+    public function less(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('less',4,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+    public function lessEqual(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    { $this->broadcastMN('lessEqual',5,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); }
+
+    protected function broadcastTrans(int $op,bool $trans,int $m,int $n,
+        Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    {
+        $cols = (!$trans) ? $n : $m;
+        if ($offsetX+($cols-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        if ($offsetA+($m-1)*$ldA+($n-1)>=count($A))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        CudaFFI::check(CudaFFI::lib()->rb200_broadcast($A->abiDtype(),$op,$trans?1:0,$m,$n,
+            $A->devicePtrRW(),$offsetA,$ldA,$X->devicePtr(),$offsetX,$incX));
+    }
+    public function pow(bool $trans,int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX) : void
+    {
+        if (!$this->onDevice($A,$X) || $A->dtype()!=$X->dtype()) { parent::pow($trans,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX); return; }
+        $this->broadcastTrans(6,$trans,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX);
+    }
+    public function duplicate(bool $trans,int $m,int $n,Buffer $X,int $offsetX,int $incX,Buffer $A,int $offsetA,int $ldA) : void
+    {
+        if (!$this->onDevice($A,$X) || $A->dtype()!=$X->dtype()) { parent::duplicate($trans,$m,$n,$X,$offsetX,$incX,$A,$offsetA,$ldA); return; }
+        $this->broadcastTrans(7,$trans,$m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX);
+    }
+
+    /** @return bool true when the device ran it */
+    protected function unaryOnDevice(int $op,int $n,Buffer $X,int $offsetX,int $incX,float $alpha=1.0,float $beta=0.0) : bool
+    {
+        if (!$this->onDevice($X)) { return false; }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        CudaFFI::check(CudaFFI::lib()->rb200_unary($X->abiDtype(),$op,$n,$alpha,$X->devicePtrRW(),$offsetX,$incX,$beta));
+        return true;
+    }
+    public function increment(int $n,float $alpha,Buffer $X,int $offsetX,int $incX,float $beta) : void
+    { if (!$this->unaryOnDevice(0,$n,$X,$offsetX,$incX,$alpha,$beta)) parent::increment($n,$alpha,$X,$offsetX,$incX,$beta); }
+    public function reciprocal(int $n,float $alpha,Buffer $X,int $offsetX,int $incX,float $beta) : void
+    { if (!$this->unaryOnDevice(1,$n,$X,$offsetX,$incX,$alpha,$beta)) parent::reciprocal($n,$alpha,$X,$offsetX,$incX,$beta); }
+    public function square(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(2,$n,$X,$offsetX,$incX)) parent::square($n,$X,$offsetX,$incX); }
+    public function sqrt(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(3,$n,$X,$offsetX,$incX)) parent::sqrt($n,$X,$offsetX,$incX); }
+    public function rsqrt(int $n,float $alpha,Buffer $X,int $offsetX,int $incX,float $beta) : void
+    { if (!$this->unaryOnDevice(4,$n,$X,$offsetX,$incX,$alpha,$beta)) parent::rsqrt($n,$alpha,$X,$offsetX,$incX,$beta); }
+    public function exp(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(5,$n,$X,$offsetX,$incX)) parent::exp($n,$X,$offsetX,$incX); }
+    public function log(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(6,$n,$X,$offsetX,$incX)) parent::log($n,$X,$offsetX,$incX); }
+    public function tanh(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(7,$n,$X,$offsetX,$incX)) parent::tanh($n,$X,$offsetX,$incX); }
+    public function sin(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(8,$n,$X,$offsetX,$incX)) parent::sin($n,$X,$offsetX,$incX); }
+    public function cos(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(9,$n,$X,$offsetX,$incX)) parent::cos($n,$X,$offsetX,$incX); }
+    public function tan(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(10,$n,$X,$offsetX,$incX)) parent::tan($n,$X,$offsetX,$incX); }
+    public function nan2num(int $n,Buffer $X,int $offsetX,int $incX,float $alpha) : void
+    { if (!$this->unaryOnDevice(12,$n,$X,$offsetX,$incX,$alpha)) parent::nan2num($n,$X,$offsetX,$incX,$alpha); }
+    public function isnan(int $n,Buffer $X,int $offsetX,int $incX) : void
+    { if (!$this->unaryOnDevice(13,$n,$X,$offsetX,$incX)) parent::isnan($n,$X,$offsetX,$incX); }
+    public function not(int $n,Buffer $X,int $offsetX,int $incX) : void
+    {
+        if (!($X instanceof CudaBuffer)) { parent::not($n,$X,$offsetX,$incX); return; }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        CudaFFI::check(CudaFFI::lib()->rb200_unary($X->abiDtype(),11,$n,1.0,$X->devicePtrRW(),$offsetX,$incX,0.0));
+    }
+
+    protected function compareOnDevice(int $op,int $n,Buffer $X,int $offsetX,int $incX,Buffer $Y,int $offsetY,int $incY) : bool
+    {
+        if (!$this->anyOnDevice($X,$Y) || $X->dtype()!=$Y->dtype()) { return false; }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        if ($offsetY+($n-1)*$incY>=count($Y))
+            throw new InvalidArgumentException('Vector specification too large for buffer.');
+        CudaFFI::check(CudaFFI::lib()->rb200_compare($Y->abiDtype(),$op,$n,$X->devicePtr(),$offsetX,$incX,
+            $Y->devicePtrRW(),$offsetY,$incY));
+        return true;
+    }
+    public function equal(int $n,Buffer $X,int $offsetX,int $incX,Buffer $Y,int $offsetY,int $incY) : void
+    { if (!$this->compareOnDevice(0,$n,$X,$offsetX,$incX,$Y,$offsetY,$incY)) parent::equal($n,$X,$offsetX,$incX,$Y,$offsetY,$incY); }
+    public function notEqual(int $n,Buffer $X,int $offsetX,int $incX,Buffer $Y,int $offsetY,int $incY) : void
+    { if (!$this->compareOnDevice(1,$n,$X,$offsetX,$incX,$Y,$offsetY,$incY)) parent::notEqual($n,$X,$offsetX,$incX,$Y,$offsetY,$incY); }
+
+    public function astype(int $n,int $dtype,Buffer $X,int $offsetX,int $incX,Buffer $Y,int $offsetY,int $incY) : void
+    {
+        if (!$this->anyOnDevice($X,$Y)) { parent::astype($n,$dtype,$X,$offsetX,$incX,$Y,$offsetY,$incY); return; }
+        CudaFFI::check(CudaFFI::lib()->rb200_astype($n,$X->abiDtype(),$X->devicePtr(),$offsetX,$incX,
+            CudaBuffer::abiDtypeOf($dtype),$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    public function sum(int $n,Buffer $X,int $offsetX,int $incX) : float
+    {
+        if (!($X instanceof CudaBuffer)) { return parent::sum($n,$X,$offsetX,$incX); }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector X specification too large for buffer.');
+        $out = CudaFFI::lib()->new('double');
+        CudaFFI::check(CudaFFI::lib()->rb200_sum($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,\FFI::addr($out)));
+        return $out->cdata;
+    }
+    public function imax(int $n,Buffer $X,int $offsetX,int $incX) : int
+    {
+        if (!($X instanceof CudaBuffer)) { return parent::imax($n,$X,$offsetX,$incX); }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector X specification too large for buffer.');
+        $out = CudaFFI::lib()->new('int64_t');
+        CudaFFI::check(CudaFFI::lib()->rb200_imax($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,\FFI::addr($out)));
+        return $out->cdata;
+    }
+    public function imin(int $n,Buffer $X,int $offsetX,int $incX) : int
+    {
+        if (!($X instanceof CudaBuffer)) { return parent::imin($n,$X,$offsetX,$incX); }
+        if ($offsetX+($n-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector X specification too large for buffer.');
+        $out = CudaFFI::lib()->new('int64_t');
+        CudaFFI::check(CudaFFI::lib()->rb200_imin($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,\FFI::addr($out)));
+        return $out->cdata;
+    }
+
+    public function updateAddOnehot(int $m,int $n,float $a,Buffer $X,int $offsetX,int $incX,Buffer $Y,int $offsetY,int $ldY) : void
+    {
+        if (!$this->anyOnDevice($X) || !$this->onDevice($Y)) { parent::updateAddOnehot($m,$n,$a,$X,$offsetX,$incX,$Y,$offsetY,$ldY); return; }
+        if ($offsetX+($m-1)*$incX>=count($X))
+            throw new InvalidArgumentException('Vector specification too large for bufferX.');
+        if ($offsetY+($m-1)*$ldY+($n-1)>=count($Y))
+            throw new InvalidArgumentException('Vector specification too large for bufferY.');
+        $rc = CudaFFI::lib()->rb200_onehot($X->abiDtype(),$Y->abiDtype(),$m,$n,$a,
+            $X->devicePtr(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$ldY);
+        if ($rc == -6) throw new \RuntimeException('Label number is out of bounds.');   // RB200_E_RANGE
+        CudaFFI::check($rc);
+    }
 }

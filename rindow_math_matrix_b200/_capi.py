@@ -10,7 +10,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librindow_b200.so")
 
-OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOTINIT, E_NOMEM = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOTINIT, E_NOMEM, E_RANGE = 0, -1, -2, -3, -4, -5, -6
+
+# rb200_broadcast / rb200_unary / rb200_compare op codes (include/rindow_b200.h)
+BC_MAXIMUM, BC_MINIMUM, BC_GREATER, BC_GREATER_EQUAL, BC_LESS, BC_LESS_EQUAL, BC_POW, BC_DUPLICATE = range(8)
+(UN_INCREMENT, UN_RECIPROCAL, UN_SQUARE, UN_SQRT, UN_RSQRT, UN_EXP, UN_LOG, UN_TANH, UN_SIN, UN_COS, UN_TAN,
+ UN_NOT, UN_NAN2NUM, UN_ISNAN) = range(14)
+CMP_EQUAL, CMP_NOT_EQUAL = 0, 1
 
 GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2, 3
 GEMM_MODE_NAMES = {GEMM_FP32_SIMT: "fp32_simt", GEMM_TF32: "tf32", GEMM_TF32X3: "tf32x3"}
@@ -53,6 +59,14 @@ SIGNATURES = {
     "rb200_omatcopy": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_add": (i32, [i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_multiply": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_broadcast": (i32, [i32, i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_unary": (i32, [i32, i32, i64, f64, vp, i64, i64, f64]),
+    "rb200_compare": (i32, [i32, i32, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_astype": (i32, [i64, i32, vp, i64, i64, i32, vp, i64, i64]),
+    "rb200_sum": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(f64)]),
+    "rb200_imax": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(i64)]),
+    "rb200_imin": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(i64)]),
+    "rb200_onehot": (i32, [i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_reduce_sum": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
     "rb200_reduce_max": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
     "rb200_reduce_argmax": (i32, [i32, i64, i64, i64, vp, i64, i32, vp, i64]),

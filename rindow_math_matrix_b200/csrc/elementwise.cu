@@ -1,4 +1,6 @@
-// elementwise.cu -- broadcast add / multiply and fill (HBM-bound).
+// elementwise.cu -- broadcast add / multiply, the rest of the broadcast
+// family (section 8f rank 2: maximum, minimum, greater, greaterEqual, less, lessEqual, pow, duplicate --
+// PhpMath.php:274-528, 687-722, 860-891) and fill.  All HBM-bound.
 //
 // Reference semantics (src/Drivers/MatlibPHP/PhpMath.php:530-606):
 //   trans == false:  A[i*ldA + j] = alpha*X[j*incX] + A[i*ldA + j]     i<m, j<n
@@ -15,7 +17,20 @@
 
 namespace {
 
-enum { OP_ADD = 0, OP_MUL = 1 };
+// OP_ADD / OP_MUL are rb200_add / rb200_multiply; the others follow the RB200_BC_* codes + 2
+enum { OP_ADD = 0, OP_MUL = 1, OP_MAXIMUM = 2, OP_MINIMUM = 3, OP_GREATER = 4, OP_GREATER_EQUAL = 5, OP_LESS = 6,
+       OP_LESS_EQUAL = 7, OP_POW = 8, OP_DUPLICATE = 9 };
+
+template <typename T> __device__ __forceinline__ bool ew_isnan(T) { return false; }
+template <> __device__ __forceinline__ bool ew_isnan<float>(float v) { return v != v; }
+template <> __device__ __forceinline__ bool ew_isnan<double>(double v) { return v != v; }
+template <typename T> __device__ __forceinline__ T ew_pow(T a, T x)
+{
+    // integer dtypes: PHP pow() on ints -- computed in double, stored back truncated
+    return (T)pow((double)a, (double)x);
+}
+template <> __device__ __forceinline__ float ew_pow<float>(float a, float x) { return powf(a, x); }
+template <> __device__ __forceinline__ double ew_pow<double>(double a, double x) { return pow(a, x); }
 
 template <typename T> struct VecOf { static constexpr int N = 16 / sizeof(T); };
 
@@ -27,7 +42,17 @@ template <typename T, int OP>
 __device__ __forceinline__ T ew_apply(T alpha, T x, T a)
 {
     if (OP == OP_ADD) return ew_apply_add<T>(alpha, x, a);
-    return x * a;
+    if (OP == OP_MUL) return x * a;
+    // maximum / minimum (PhpMath.php:274-357): a NaN in X is written; a NaN already in A stays
+    if (OP == OP_MAXIMUM) return ew_isnan(x) ? x : ((a < x) ? x : a);
+    if (OP == OP_MINIMUM) return ew_isnan(x) ? x : ((a > x) ? x : a);
+    // comparisons (:362-528): 1 / 0 in the buffer's dtype, false for every NaN operand
+    if (OP == OP_GREATER) return (a > x) ? (T)1 : (T)0;
+    if (OP == OP_GREATER_EQUAL) return (a >= x) ? (T)1 : (T)0;
+    if (OP == OP_LESS) return (a < x) ? (T)1 : (T)0;
+    if (OP == OP_LESS_EQUAL) return (a <= x) ? (T)1 : (T)0;
+    if (OP == OP_POW) return ew_pow<T>(a, x);          // :687-722
+    return x;                                          // OP_DUPLICATE (:860-891)
 }
 
 template <typename T> union Pack16 {
@@ -63,7 +88,7 @@ ew_vec_kernel(int64_t m, int64_t nvec, T alpha,
         for (int i = 0; i < EW_ROWS; i++) {
             const int64_t r = row0 + (int64_t)i * TY;
             if (r < m) {
-                a[i].raw = __ldcs(reinterpret_cast<const int4*>(A + r * ldA) + cv);
+                if (OP != OP_DUPLICATE) a[i].raw = __ldcs(reinterpret_cast<const int4*>(A + r * ldA) + cv);
                 if (TRANS) xs[i] = __ldg(X + r * incX);
             }
         }
@@ -94,7 +119,7 @@ ew_scalar_kernel(int64_t m, int64_t n, T alpha,
     for (int64_t i = blockIdx.y; i < m; i += gridDim.y) {
         const T x = TRANS ? X[i * incX] : X[j * incX];
         T* p = A + i * ldA + j;
-        *p = ew_apply<T, OP>(alpha, x, *p);
+        *p = ew_apply<T, OP>(alpha, x, (OP == OP_DUPLICATE) ? x : *p);
     }
 }
 
@@ -107,6 +132,16 @@ int ew_launch(int trans, int64_t m, int64_t n, double alpha_d,
     T* A = reinterpret_cast<T*>(Av) + offA;
     const T alpha = (T)alpha_d;
     constexpr int V = VecOf<T>::N;
+
+    // a single X element broadcast over a dense column (LinearAlgebra::calcBroadcastFormat's scalar case:
+    // m = size, n = 1, ldA = 1; or trans with one row): view A as [m/w, w] rows of X[0]
+    if ((!trans && n == 1 && ldA == 1) || (trans && m == 1)) {
+        const int64_t total = trans ? n : m;
+        int64_t w = 1;
+        while (w < 2048 && total % (w * 2) == 0) w *= 2;
+        if (w < V) w = total;                 // odd lengths: one long row (scalar kernel when unaligned)
+        trans = 1; m = total / w; n = w; ldA = w; incX = 0;
+    }
 
     const bool a_vec_ok = (n % V == 0) && (ldA % V == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool x_vec_ok = trans ? true : (incX == 1 && (reinterpret_cast<uintptr_t>(X) & 15) == 0);
@@ -191,9 +226,44 @@ int fill_launch(void* dptr, int64_t off, int64_t n, const void* value)
     return RB200_OK;
 }
 
+
+template <typename T>
+int bc_launch(int op, int trans, int64_t m, int64_t n, const void* X, int64_t offX, int64_t incX,
+              void* A, int64_t offA, int64_t ldA)
+{
+    switch (op) {
+        case RB200_BC_MAXIMUM:       return ew_launch<T, OP_MAXIMUM>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_MINIMUM:       return ew_launch<T, OP_MINIMUM>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_GREATER:       return ew_launch<T, OP_GREATER>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_GREATER_EQUAL: return ew_launch<T, OP_GREATER_EQUAL>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_LESS:          return ew_launch<T, OP_LESS>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_LESS_EQUAL:    return ew_launch<T, OP_LESS_EQUAL>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_POW:           return ew_launch<T, OP_POW>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        case RB200_BC_DUPLICATE:     return ew_launch<T, OP_DUPLICATE>(trans, m, n, 1.0, X, offX, incX, A, offA, ldA);
+        default: RB_INVALID("unknown broadcast op %d", op);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int rb200_broadcast(int dtype, int op, int trans, int64_t m, int64_t n,
+                    void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX)
+{
+    RB_REQUIRE_INIT();
+    if (!X || !A) RB_INVALID("NULL buffer");
+    if (m < 1 || n < 1) RB_INVALID("m and n must be greater than 0");
+    if (incX < 1 || ldA < 1 || offX < 0 || offA < 0) RB_INVALID("bad increment / leading dimension / offset");
+    if (ldA < n) RB_INVALID("ldA (%lld) is smaller than n (%lld)", (long long)ldA, (long long)n);
+    switch (dtype) {
+        case RB200_FLOAT32: return bc_launch<float>(op, trans, m, n, X, offX, incX, A, offA, ldA);
+        case RB200_FLOAT64: return bc_launch<double>(op, trans, m, n, X, offX, incX, A, offA, ldA);
+        case RB200_INT32:   return bc_launch<int32_t>(op, trans, m, n, X, offX, incX, A, offA, ldA);
+        case RB200_INT64:   return bc_launch<int64_t>(op, trans, m, n, X, offX, incX, A, offA, ldA);
+        default: RB_UNSUPPORTED("broadcast op: unsupported dtype %d", dtype);
+    }
+}
 
 int rb200_add(int dtype, int trans, int64_t m, int64_t n, double alpha,
               const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA)

@@ -45,6 +45,7 @@ class CudaBuffer:
         self._host = None            # numpy view of the mirror
         self._host_dirty = False     # host mirror newer than device
         self._dev_dirty = False      # device newer than host mirror
+        self._single_reads = 0       # element reads served by one-element d2h since the last device write
         if zero and self._size:
             z = np.zeros(1, self._np)
             _capi.check(self._lib.rb200_buffer_fill(self._dtype, self._dptr, 0, self._size, z.ctypes.data))
@@ -82,6 +83,13 @@ class CudaBuffer:
 
     def __getitem__(self, i):
         i = self._index(i)
+        # a few scattered reads of a device-current buffer (LinearAlgebra::max reads $XX[$offX+$i] once,
+        # LinearAlgebra.php:1644-1645) fetch single elements; a loop over the buffer gets the whole mirror
+        if (self._host is None or self._dev_dirty) and not self._host_dirty and self._single_reads < 8:
+            self._single_reads += 1
+            one = np.empty(1, self._np)
+            _capi.check(self._lib.rb200_buffer_d2h(one.ctypes.data, self._dptr, i * self._np.itemsize, self._np.itemsize))
+            return bool(one[0]) if self._dtype == dtypes.bool_ else one[0].item()
         v = self.host()[i]
         return bool(v) if self._dtype == dtypes.bool_ else v.item()
 
@@ -199,6 +207,7 @@ class CudaBuffer:
         """Device pointer for a kernel that WRITES the buffer (marks the mirror stale)."""
         self.flush()
         self._dev_dirty = True
+        self._single_reads = 0
         return self._dptr
 
     # bulk host transfer helpers for tests / benches (typed, element offsets)

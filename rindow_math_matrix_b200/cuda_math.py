@@ -3,15 +3,20 @@
 Same positional signatures, checks and exception strings as PhpMath
 (src/Drivers/MatlibPHP/PhpMath.php); arithmetic in librindow_b200.so.  Hot-path methods:
 add :570, multiply :530, reduceSum :1552, reduceMax :1584, reduceArgMax :1616, softmax :1645,
-im2col2d :2158, plus zeros :908 / fill :2811 (every alloc+zeros on the path).
+im2col2d :2158, plus zeros :908 / fill :2811 (every alloc+zeros on the path), and the section 8(f) widening:
+the broadcast family (maximum ... lessEqual :274-528, pow :687, duplicate :860), the unary family (:221-268,
+:611-682, :727-855, not :1528, nan2num :2830, isnan :2853), equal/notEqual :1470-1522, astype :1710,
+sum/imax/imin :150-216 and updateAddOnehot :1438.
 """
 from __future__ import annotations
+
+import ctypes
 
 import numpy as np
 
 from . import _capi, dtypes
 from .cuda_buffer import CudaBuffer
-from .exceptions import InvalidArgumentException, LogicException
+from .exceptions import InvalidArgumentException, LogicException, RuntimeException
 
 
 def _cuda(name: str, buf) -> CudaBuffer:
@@ -63,6 +68,175 @@ class CudaMath:
             raise InvalidArgumentException("Unmatch data type for X and A")
         _capi.check(self._lib.rb200_multiply(A.dtype(), 1 if trans else 0, m, n,
                                              X.device_ptr(), offsetX, incX, A.device_ptr_rw(), offsetA, ldA))
+
+    # ---- the rest of the broadcast family ------------------------------------
+    # maximum :274, minimum :318, greater :362, greaterEqual :404, less :446, lessEqual :488 share one signature,
+    # one set of checks and messages; A[m,n] against X[n] in place.
+    def _broadcast_mn(self, op, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        if m <= 0 or n <= 0:
+            raise InvalidArgumentException("m and n must be greater than 0")
+        if (m - 1) * ldA + (n - 1) + offsetA >= len(A):
+            raise InvalidArgumentException("Matrix A is too small")
+        if (n - 1) * incX + offsetX >= len(X):
+            raise InvalidArgumentException("Buffer X is too small")
+        _cuda("X", X), _cuda("A", A)
+        if X.dtype() != A.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and X")
+        _capi.check(self._lib.rb200_broadcast(A.dtype(), op, 0, m, n, A.device_ptr_rw(), offsetA, ldA,
+                                              X.device_ptr(), offsetX, incX))
+
+    def maximum(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_MAXIMUM, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def minimum(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_MINIMUM, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def greater(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_GREATER, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def greaterEqual(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_GREATER_EQUAL, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def less(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_LESS, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def lessEqual(self, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_mn(_capi.BC_LESS_EQUAL, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    # pow :687-722 and duplicate :860-891 take $trans like add
+    def _broadcast_trans(self, op, trans, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        trans = bool(trans)
+        rows, cols = (m, n) if not trans else (n, m)
+        if offsetX + (cols - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        if offsetA + (m - 1) * ldA + (n - 1) >= len(A):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        _cuda("X", X), _cuda("A", A)
+        if X.dtype() != A.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and X")
+        _capi.check(self._lib.rb200_broadcast(A.dtype(), op, 1 if trans else 0, m, n, A.device_ptr_rw(), offsetA, ldA,
+                                              X.device_ptr(), offsetX, incX))
+
+    def pow(self, trans, m, n, A, offsetA, ldA, X, offsetX, incX) -> None:
+        self._broadcast_trans(_capi.BC_POW, trans, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    def duplicate(self, trans, m, n, X, offsetX, incX, A, offsetA, ldA) -> None:
+        self._broadcast_trans(_capi.BC_DUPLICATE, trans, m, n, A, offsetA, ldA, X, offsetX, incX)
+
+    # ---- unary family, in place (PhpMath.php:221-268, 611-682, 727-855, 1528-1547, 2830-2875) ----------------
+    def _unary(self, op, n, X, offsetX, incX, alpha=1.0, beta=0.0) -> None:
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        _cuda("X", X)
+        _capi.check(self._lib.rb200_unary(X.dtype(), op, n, float(alpha), X.device_ptr_rw(), offsetX, incX, float(beta)))
+
+    def increment(self, n, alpha, X, offsetX, incX, beta) -> None:
+        self._unary(_capi.UN_INCREMENT, n, X, offsetX, incX, alpha, beta)
+
+    def reciprocal(self, n, alpha, X, offsetX, incX, beta) -> None:
+        self._unary(_capi.UN_RECIPROCAL, n, X, offsetX, incX, alpha, beta)
+
+    def square(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_SQUARE, n, X, offsetX, incX)
+
+    def sqrt(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_SQRT, n, X, offsetX, incX)
+
+    def rsqrt(self, n, alpha, X, offsetX, incX, beta) -> None:
+        self._unary(_capi.UN_RSQRT, n, X, offsetX, incX, alpha, beta)
+
+    def exp(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_EXP, n, X, offsetX, incX)
+
+    def log(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_LOG, n, X, offsetX, incX)
+
+    def tanh(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_TANH, n, X, offsetX, incX)
+
+    def sin(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_SIN, n, X, offsetX, incX)
+
+    def cos(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_COS, n, X, offsetX, incX)
+
+    def tan(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_TAN, n, X, offsetX, incX)
+
+    def nan2num(self, n, X, offsetX, incX, alpha) -> None:
+        self._unary(_capi.UN_NAN2NUM, n, X, offsetX, incX, alpha)
+
+    def isnan(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_ISNAN, n, X, offsetX, incX)
+
+    # `not` is a Python keyword: the mirror of PhpMath::not (:1528) is not_, also reachable as getattr(m, "not")
+    def not_(self, n, X, offsetX, incX) -> None:
+        self._unary(_capi.UN_NOT, n, X, offsetX, incX)
+
+    # ---- equal / notEqual (PhpMath.php:1470-1522): Y := (Y == X) / (Y != X) as 1 / 0 ------------------------
+    def _compare(self, op, n, X, offsetX, incX, Y, offsetY, incY) -> None:
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        if offsetY + (n - 1) * incY >= len(Y):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        _cuda("X", X), _cuda("Y", Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        _capi.check(self._lib.rb200_compare(Y.dtype(), op, n, X.device_ptr(), offsetX, incX,
+                                            Y.device_ptr_rw(), offsetY, incY))
+
+    def equal(self, n, X, offsetX, incX, Y, offsetY, incY) -> None:
+        self._compare(_capi.CMP_EQUAL, n, X, offsetX, incX, Y, offsetY, incY)
+
+    def notEqual(self, n, X, offsetX, incX, Y, offsetY, incY) -> None:
+        self._compare(_capi.CMP_NOT_EQUAL, n, X, offsetX, incX, Y, offsetY, incY)
+
+    # ---- astype (PhpMath.php:1710-1778) ----------------------------------------------------------------------
+    def astype(self, n, dtype, X, offsetX, incX, Y, offsetY, incY) -> None:
+        if dtype not in dtypes.NUMPY:
+            raise InvalidArgumentException("dtype must be type of integer or float: %s" % dtype)
+        if offsetX + (n - 1) * incX >= len(X) or offsetY + (n - 1) * incY >= len(Y):
+            raise InvalidArgumentException("Vector specification too large for buffer.")
+        _cuda("X", X), _cuda("Y", Y)
+        if Y.dtype() != dtype:
+            raise InvalidArgumentException("Unmatch data type for Y")
+        _capi.check(self._lib.rb200_astype(n, X.dtype(), X.device_ptr(), offsetX, incX,
+                                           dtype, Y.device_ptr_rw(), offsetY, incY))
+
+    # ---- scalar results (PhpMath.php:150-216): the value is on the host when the call returns ---------------
+    def sum(self, n, X, offsetX, incX) -> float:
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector X specification too large for buffer.")
+        out = ctypes.c_double(0.0)
+        _capi.check(self._lib.rb200_sum(_cuda("X", X).dtype(), n, X.device_ptr(), offsetX, incX, ctypes.byref(out)))
+        return out.value
+
+    def imax(self, n, X, offsetX, incX) -> int:
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector X specification too large for buffer.")
+        out = ctypes.c_int64(0)
+        _capi.check(self._lib.rb200_imax(_cuda("X", X).dtype(), n, X.device_ptr(), offsetX, incX, ctypes.byref(out)))
+        return out.value
+
+    def imin(self, n, X, offsetX, incX) -> int:
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector X specification too large for buffer.")
+        out = ctypes.c_int64(0)
+        _capi.check(self._lib.rb200_imin(_cuda("X", X).dtype(), n, X.device_ptr(), offsetX, incX, ctypes.byref(out)))
+        return out.value
+
+    # ---- updateAddOnehot (PhpMath.php:1438-1464) -------------------------------------------------------------
+    def updateAddOnehot(self, m, n, a, X, offsetX, incX, Y, offsetY, ldY) -> None:
+        if offsetX + (m - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for bufferX.")
+        if offsetY + (m - 1) * ldY + (n - 1) >= len(Y):
+            raise InvalidArgumentException("Vector specification too large for bufferY.")
+        _cuda("X", X), _cuda("Y", Y)
+        rc = self._lib.rb200_onehot(X.dtype(), Y.dtype(), m, n, float(a), X.device_ptr(), offsetX, incX,
+                                    Y.device_ptr_rw(), offsetY, ldY)
+        if rc == _capi.E_RANGE:
+            raise RuntimeException("Label number is out of bounds.")
+        _capi.check(rc)
 
     # ---- reductions over the middle axis of A[m,n,k] (PhpMath.php:1552-1643) ----------------------
     def _reduce_check(self, m, n, k, A, offsetA, B, offsetB) -> None:
@@ -176,6 +350,8 @@ class CudaMath:
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
+        if name == "not":
+            return self.not_
 
         def _not_on_device(*a, **k):
             raise LogicException("CudaMath::%s is not on the B200 hot path (SURVEY.md section 8f); the PHP shim "

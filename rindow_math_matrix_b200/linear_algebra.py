@@ -291,6 +291,219 @@ class LinearAlgebra:
         self.math.add(trans, m, n, alpha, X.buffer(), X.offset(), 1, A.buffer(), A.offset(), n)
         return A
 
+    # ---- scalar reductions (LinearAlgebra.php:1602-1659) ---------------------------------------------------
+    def sum(self, X: NDArray) -> float:
+        return self.math.sum(X.size(), X.buffer(), X.offset(), 1)
+
+    def imax(self, X: NDArray) -> int:
+        return self.math.imax(X.size(), X.buffer(), X.offset(), 1)
+
+    def imin(self, X: NDArray) -> int:
+        return self.math.imin(X.size(), X.buffer(), X.offset(), 1)
+
+    def max(self, X: NDArray):
+        i = self.math.imax(X.size(), X.buffer(), X.offset(), 1)
+        return X.buffer()[X.offset() + i]
+
+    def min(self, X: NDArray):
+        i = self.math.imin(X.size(), X.buffer(), X.offset(), 1)
+        return X.buffer()[X.offset() + i]
+
+    # ---- unary family, in place (LinearAlgebra.php:1664-1715, 2021-2080, 2143-2246, 2296-2304, 4817-4853) ----
+    def increment(self, X: NDArray, beta=None, alpha=None) -> NDArray:
+        self.math.increment(X.size(), 1.0 if alpha is None else alpha, X.buffer(), X.offset(), 1,
+                            0.0 if beta is None else beta)
+        return X
+
+    def reciprocal(self, X: NDArray, beta=None, alpha=None) -> NDArray:
+        self.math.reciprocal(X.size(), 1.0 if alpha is None else alpha, X.buffer(), X.offset(), 1,
+                             0.0 if beta is None else beta)
+        return X
+
+    def rsqrt(self, X: NDArray, beta=None, alpha=None) -> NDArray:
+        self.math.rsqrt(X.size(), 1.0 if alpha is None else alpha, X.buffer(), X.offset(), 1,
+                        0.0 if beta is None else beta)
+        return X
+
+    def _unary(self, name: str, X: NDArray) -> NDArray:
+        getattr(self.math, name)(X.size(), X.buffer(), X.offset(), 1)
+        return X
+
+    def square(self, X: NDArray) -> NDArray:
+        return self._unary("square", X)
+
+    def sqrt(self, X: NDArray) -> NDArray:
+        return self._unary("sqrt", X)
+
+    def exp(self, X: NDArray) -> NDArray:
+        return self._unary("exp", X)
+
+    def log(self, X: NDArray) -> NDArray:
+        return self._unary("log", X)
+
+    def tanh(self, X: NDArray) -> NDArray:
+        return self._unary("tanh", X)
+
+    def sin(self, X: NDArray) -> NDArray:
+        return self._unary("sin", X)
+
+    def cos(self, X: NDArray) -> NDArray:
+        return self._unary("cos", X)
+
+    def tan(self, X: NDArray) -> NDArray:
+        return self._unary("tan", X)
+
+    def not_(self, X: NDArray) -> NDArray:                                      # LinearAlgebra::not :2296
+        return self._unary("not", X)
+
+    def isnan(self, X: NDArray) -> NDArray:                                     # :4840
+        return self._unary("isnan", X)
+
+    def nan2num(self, X: NDArray, alpha=None) -> NDArray:                       # :4817
+        self.math.nan2num(X.size(), X.buffer(), X.offset(), 1, 0.0 if alpha is None else alpha)
+        return X
+
+    # ---- A[m,n] against X[n] (LinearAlgebra.php:1720-1916) ---------------------------------------------------
+    def _calc_broadcast_format(self, A: NDArray, X):
+        if isinstance(X, (int, float, np.integer, np.floating)) and not isinstance(X, bool):
+            X = self.array(X, dtype=A.dtype())
+        if not isinstance(X, NDArray):
+            raise InvalidArgumentException("X must be NDArray or float")
+        if X.ndim() == 0:
+            X = X.reshape([X.size()])
+            m, n = A.size(), 1
+        else:
+            shapeA, shapeX = A.shape(), X.shape()
+            if shapeA == shapeX:
+                m, n = 1, A.size()
+            else:
+                n = 1
+                while shapeX:
+                    tmpX = shapeX.pop()
+                    tmpA = shapeA.pop() if shapeA else None
+                    if tmpA != tmpX:
+                        raise InvalidArgumentException("A and X is unmatched for broadcast")
+                    n *= tmpX
+                m = int(np.prod(shapeA, dtype=np.int64)) if shapeA else 1
+        if A.dtype() != X.dtype():
+            raise InvalidArgumentException("A and X must be same data type")
+        return int(m), int(n), X
+
+    def _broadcast_op(self, name: str, A: NDArray, X) -> NDArray:
+        m, n, X = self._calc_broadcast_format(A, X)
+        getattr(self.math, name)(m, n, A.buffer(), A.offset(), n, X.buffer(), X.offset(), 1)
+        return A
+
+    def maximum(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("maximum", A, X)
+
+    def minimum(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("minimum", A, X)
+
+    def greater(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("greater", A, X)
+
+    def greaterEqual(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("greaterEqual", A, X)
+
+    def less(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("less", A, X)
+
+    def lessEqual(self, A: NDArray, X) -> NDArray:
+        return self._broadcast_op("lessEqual", A, X)
+
+    # ---- A(m,n) := A(m,n) ** alpha(n)   (LinearAlgebra.php:2085-2138) ----------------------------------------
+    def pow(self, A: NDArray, alpha, trans=None) -> NDArray:
+        trans = bool(trans)
+        shapeA = A.shape()
+        if isinstance(alpha, (int, float, np.integer, np.floating)):
+            alpha = self.array(alpha, dtype=A.dtype())
+        shapeX = alpha.shape()
+        if len(shapeX) == 0:
+            trans = False
+            shapeA = [int(np.prod(shapeA, dtype=np.int64)) if shapeA else 1, 1]
+            shapeX = [1]
+        if trans:
+            shapeA = shapeA[::-1]
+        while shapeX:
+            xd = shapeX.pop()
+            ad = shapeA.pop() if shapeA else None
+            if xd != ad:
+                shown = A.shape()[::-1] if trans else A.shape()
+                raise InvalidArgumentException("Unmatch dimension size for broadcast.: [%s] => [%s]" % (
+                    ",".join(map(str, shapeX)), ",".join(map(str, shown))))
+        n = alpha.size()
+        m = A.size() // n
+        if trans:
+            m, n = n, m
+        self.math.pow(trans, m, n, A.buffer(), A.offset(), n, alpha.buffer(), alpha.offset(), 1)
+        return A
+
+    # ---- Y := (X == Y) / (X != Y) as 1 / 0   (LinearAlgebra.php:2252-2290) -----------------------------------
+    def _xy_shape_check(self, X: NDArray, Y: NDArray) -> None:
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException('Unmatch shape of dimension "X" and "Y" and "numClass": (%s),(%s)' % (
+                ",".join(map(str, X.shape())), ",".join(map(str, Y.shape()))))
+
+    def equal(self, X: NDArray, Y: NDArray) -> NDArray:
+        self._xy_shape_check(X, Y)
+        self.math.equal(X.size(), X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    def notEqual(self, X: NDArray, Y: NDArray) -> NDArray:
+        self._xy_shape_check(X, Y)
+        self.math.notEqual(X.size(), X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    # ---- A(m,n) := X(n)   (LinearAlgebra.php:2311-2361) ------------------------------------------------------
+    def duplicate(self, input: NDArray, repeats=None, trans=None, output: NDArray | None = None) -> NDArray:
+        trans = bool(trans)
+        if output is None:
+            if repeats is None:
+                repeats = 1
+            shape = ([repeats] + input.shape()) if not trans else (input.shape() + [repeats])
+            output = self.alloc(shape, dtype=input.dtype())
+        else:
+            shapeX, shapeA = input.shape(), output.shape()
+            if trans:
+                shapeA = shapeA[::-1]
+            while shapeX:
+                xd = shapeX.pop()
+                ad = shapeA.pop() if shapeA else None
+                if xd != ad:
+                    raise InvalidArgumentException("Unmatch dimension size for broadcast.: [%s] => [%s]" % (
+                        ",".join(map(str, input.shape())), ",".join(map(str, output.shape()))))
+        n = input.size()
+        m = output.size() // n
+        if trans:
+            m, n = n, m
+        self.math.duplicate(trans, m, n, input.buffer(), input.offset(), 1, output.buffer(), output.offset(), n)
+        return output
+
+    # ---- astype (LinearAlgebra.php:291-307) ------------------------------------------------------------------
+    def astype(self, X: NDArray, dtype: int) -> NDArray:
+        Y = self.alloc(X.shape(), dtype=dtype)
+        self.math.astype(X.size(), dtype, X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+        return Y
+
+    # ---- onehot (LinearAlgebra.php:3095-3133) ----------------------------------------------------------------
+    def onehot(self, X: NDArray, numClass: int, alpha=None, output: NDArray | None = None) -> NDArray:
+        if X.ndim() != 1:
+            raise InvalidArgumentException('"X" must be 1D-NDArray.')
+        sizeX = X.size()
+        if output is None:
+            output = self.zeros(self.alloc([sizeX, numClass], dtype=self.defaultFloatType))
+        if output.ndim() != 2:
+            raise InvalidArgumentException('"Y" must be 2D-NDArray.')
+        m, n = output.shape()
+        if m != sizeX or n != numClass:
+            raise InvalidArgumentException('Unmatch shape of dimension "X" and "Y" and "numClass": (%s),(%s)' % (
+                ",".join(map(str, X.shape())), ",".join(map(str, output.shape()))))
+        if alpha is None:
+            alpha = 1.0
+        self.math.updateAddOnehot(m, n, alpha, X.buffer(), X.offset(), 1, output.buffer(), output.offset(), n)
+        return output
+
     # ---- softmax (LinearAlgebra.php:3138-3156) ---------------------------------------------------------
     def softmax(self, X: NDArray) -> NDArray:
         if X.ndim() != 2:
@@ -336,6 +549,19 @@ class LinearAlgebra:
     def reduceArgMax(self, input: NDArray, axis=None, keepdims=None, output=None, dtype=None) -> NDArray:
         m, n, k, output = self._reduce_args(input, axis, keepdims, output, dtype, dtypes.int32)
         self.math.reduceArgMax(m, n, k, input.buffer(), input.offset(), output.buffer(), output.offset())
+        return output
+
+    def reduceMean(self, input: NDArray, axis=None, keepdims=None, output=None, dtype=None) -> NDArray:
+        if axis is None:                                                         # LinearAlgebra.php:3338-3362
+            axis = 0
+        output = self.reduceSum(input, axis=axis, keepdims=keepdims, output=output, dtype=dtype)
+        ndim = input.ndim()
+        if axis < 0:
+            axis = ndim + axis
+        if ndim <= axis:
+            raise InvalidArgumentException("axis must be less then num of dimension")
+        rows = input.shape()[axis]
+        self.scal(1 / rows, output)
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------

@@ -40,6 +40,38 @@ def _assert_equal(expect, got, tol=0.0):
         assert np.array_equal(e, g, equal_nan=True), (e, g)
 
 
+_DTYPES = {"bool": 0, "int8": 1, "int16": 2, "int32": 3, "int64": 4, "uint8": 5, "uint16": 6, "uint32": 7,
+           "uint64": 8, "float32": 12, "float64": 13}
+
+
+def _la_arg(la, a):
+    if isinstance(a, str) and a.startswith("@dtype:"):
+        return _DTYPES[a[7:]]
+    if isinstance(a, str) and a.startswith("@ones"):
+        return la.ones(la.alloc(json.loads(a[5:])))
+    if not isinstance(a, dict):
+        return _num(a)
+    dtype = _DTYPES[a["dtype"]] if "dtype" in a else None
+    if "ones" in a:
+        x = la.ones(la.alloc(a["ones"], dtype=dtype))
+    elif "fill" in a:
+        x = la.fill(a["fill"], la.alloc(a["shape"], dtype=dtype))
+    elif "arange" in a:
+        v = np.arange(a["arange"]) + a.get("start", 0)
+        for i, val in a.get("set", {}).items():
+            v[int(i)] = val
+        x = la.array(v, dtype=dtype)
+    else:
+        v = np.array(_arr(a["a"]))
+        if dtype is not None and a["dtype"].startswith("uint"):
+            v = v.astype(np.int64).astype({"uint8": np.uint8, "uint16": np.uint16, "uint32": np.uint32,
+                                           "uint64": np.uint64}[a["dtype"]])      # PHP ints wrap into the C buffer
+        x = la.array(v, dtype=dtype)
+    if "view" in a:
+        x = x[a["view"]]
+    return x
+
+
 def run_case(case, service):
     mo = MatrixOperator(service)
     la = LinearAlgebra(service)
@@ -112,6 +144,20 @@ def run_case(case, service):
             return la.matmul(A, B, C=C, **kw)
         if op == "transpose":
             return la.transpose(la.array(_arr(case["x"])))
+        if op == "la":
+            # generic: method of LinearAlgebra called on NDArray / scalar arguments; "steps" = further in-place calls
+            # on the first argument (the reference tests chain them); the result is the last call's return value
+            args = [_la_arg(la, a) for a in case["args"]]
+            kwa = {k: _la_arg(la, v) for k, v in kw.items()}
+            out = getattr(la, case["method"])(*args, **kwa)
+            if case.get("returns_arg") is not None:
+                assert out is args[case["returns_arg"]]
+            for step in case.get("steps", []):
+                out = getattr(la, step["method"])(args[0], *[_la_arg(la, a) for a in step.get("args", [])],
+                                                  **step.get("kwargs", {}))
+            for i, want in case.get("untouched", {}).items():
+                _assert_equal(want, args[int(i)].toArray())
+            return out
         raise AssertionError("unknown op " + op)
 
     if "error" in case:
@@ -125,8 +171,13 @@ def run_case(case, service):
     out = call()
     if "expect_shape" in case:
         assert out.shape() == case["expect_shape"]
+    if "expect_dtype" in case:
+        assert out.dtype() == _DTYPES[case["expect_dtype"]]
     if "expect" in case:
-        _assert_equal(case["expect"], out.toArray(), case.get("tol", 0.0))
+        _assert_equal(case["expect"], out.toArray() if hasattr(out, "toArray") else out, case.get("tol", 0.0))
+    if "expect_fill" in case:
+        got = np.asarray(out.toArray(), dtype=np.float64)
+        assert np.all(got == case["expect_fill"])
     if "expect_row0" in case:
         _assert_equal(case["expect_row0"], out.toArray()[0], case["tol"])
         _assert_equal(case["expect_row0"], out.toArray()[-1], case["tol"])

@@ -58,7 +58,7 @@ def _wrap(fn, *args, **kw):
         return fn(*args, **kw)
     except oracle.OracleArgumentError as e:
         raise InvalidArgumentException(str(e))
-    except oracle.OracleZeroDivide as e:
+    except (oracle.OracleZeroDivide, oracle.OracleLabelRange) as e:
         raise RuntimeException(str(e))
 
 
@@ -121,6 +121,130 @@ class OracleMath:
         _wrap(oracle.im2col2d, reverse, images.f64(), images_offset, images_size, batches, im_h, im_w, channels,
               filter_h, filter_w, stride_h, stride_w, padding, channels_first, dilation_h, dilation_w,
               cols_channels_first, cols.f64(), cols_offset, cols_size)
+
+    # ---- SURVEY.md section 8(f) widening: broadcast / unary / compare families, astype, scalar reductions, onehot
+    def _bc(self, op, trans, m, n, A, offA, ldA, X, offX, incX):
+        a, x = self._f(A), self._f(X)
+        _wrap(oracle.broadcast, op, trans, m, n, a, offA, ldA, x, offX, incX)
+        self._back(A, a)
+
+    @staticmethod
+    def _f(buf):
+        """float64 working copy of any buffer (PHP ints and floats share one arithmetic)."""
+        return buf.data if buf.data.dtype == np.float64 else buf.data.astype(np.float64)
+
+    @staticmethod
+    def _back(buf, work):
+        if work is not buf.data:
+            buf.data[:] = work.astype(np.int64)
+
+    def maximum(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_MAXIMUM, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def minimum(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_MINIMUM, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def greater(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_GREATER, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def greaterEqual(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_GREATER_EQUAL, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def less(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_LESS, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def lessEqual(self, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_LESS_EQUAL, False, m, n, A, offA, ldA, X, offX, incX)
+
+    def pow(self, trans, m, n, A, offA, ldA, X, offX, incX):
+        self._bc(oracle.BC_POW, trans, m, n, A, offA, ldA, X, offX, incX)
+
+    def duplicate(self, trans, m, n, X, offX, incX, A, offA, ldA):
+        self._bc(oracle.BC_DUPLICATE, trans, m, n, A, offA, ldA, X, offX, incX)
+
+    def _un(self, op, n, X, offX, incX, alpha=1.0, beta=0.0):
+        x = self._f(X)
+        _wrap(oracle.unary, op, n, x, offX, incX, alpha, beta)
+        self._back(X, x)
+
+    def increment(self, n, alpha, X, offX, incX, beta):
+        self._un(oracle.UN_INCREMENT, n, X, offX, incX, alpha, beta)
+
+    def reciprocal(self, n, alpha, X, offX, incX, beta):
+        self._un(oracle.UN_RECIPROCAL, n, X, offX, incX, alpha, beta)
+
+    def rsqrt(self, n, alpha, X, offX, incX, beta):
+        self._un(oracle.UN_RSQRT, n, X, offX, incX, alpha, beta)
+
+    def square(self, n, X, offX, incX):
+        self._un(oracle.UN_SQUARE, n, X, offX, incX)
+
+    def sqrt(self, n, X, offX, incX):
+        self._un(oracle.UN_SQRT, n, X, offX, incX)
+
+    def exp(self, n, X, offX, incX):
+        self._un(oracle.UN_EXP, n, X, offX, incX)
+
+    def log(self, n, X, offX, incX):
+        self._un(oracle.UN_LOG, n, X, offX, incX)
+
+    def tanh(self, n, X, offX, incX):
+        self._un(oracle.UN_TANH, n, X, offX, incX)
+
+    def sin(self, n, X, offX, incX):
+        self._un(oracle.UN_SIN, n, X, offX, incX)
+
+    def cos(self, n, X, offX, incX):
+        self._un(oracle.UN_COS, n, X, offX, incX)
+
+    def tan(self, n, X, offX, incX):
+        self._un(oracle.UN_TAN, n, X, offX, incX)
+
+    def not_(self, n, X, offX, incX):
+        self._un(oracle.UN_NOT, n, X, offX, incX)
+
+    def __getattr__(self, name):
+        if name == "not":
+            return self.not_
+        raise AttributeError(name)
+
+    def nan2num(self, n, X, offX, incX, alpha):
+        self._un(oracle.UN_NAN2NUM, n, X, offX, incX, alpha)
+
+    def isnan(self, n, X, offX, incX):
+        self._un(oracle.UN_ISNAN, n, X, offX, incX)
+
+    def equal(self, n, X, offX, incX, Y, offY, incY):
+        y = self._f(Y)
+        _wrap(oracle.compare, False, n, self._f(X), offX, incX, y, offY, incY)
+        self._back(Y, y)
+
+    def notEqual(self, n, X, offX, incX, Y, offY, incY):
+        y = self._f(Y)
+        _wrap(oracle.compare, True, n, self._f(X), offX, incX, y, offY, incY)
+        self._back(Y, y)
+
+    def astype(self, n, dtype, X, offX, incX, Y, offY, incY):
+        if dtype == dtypes.bool_:
+            kind, mask = "bool", 0
+        elif dtype in dtypes.FLOAT_TYPES:
+            kind, mask = "float", 0
+        else:
+            kind = "int"
+            mask = {dtypes.uint8: 0xff, dtypes.uint16: 0xffff, dtypes.uint32: 0xffffffff}.get(dtype, 0)
+        Y.data[offY:offY + (n - 1) * incY + 1:incY] = oracle.astype(n, kind, mask, X.data, offX, incX)
+
+    def sum(self, n, X, offX, incX):
+        return _wrap(oracle.sum, n, self._f(X), offX, incX)
+
+    def imax(self, n, X, offX, incX):
+        return _wrap(oracle.imax, n, self._f(X), offX, incX)
+
+    def imin(self, n, X, offX, incX):
+        return _wrap(oracle.imin, n, self._f(X), offX, incX)
+
+    def updateAddOnehot(self, m, n, a, X, offX, incX, Y, offY, ldY):
+        _wrap(oracle.onehot, m, n, a, self._f(X), offX, incX, Y.f64(), offY, ldY)
 
     def zeros(self, n, X, offX, incX):
         X.data[offX:offX + n * incX:incX] = 0

@@ -51,7 +51,18 @@ def main():
     timed("gemv", lambda i: blas.gemv(BLAS.RowMajor, BLAS.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Ym, 0, 1), m * n * 4)
     timed("gemv_trans", lambda i: blas.gemv(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, As[i], 0, n, Xm, 0, 1, 0.0, Yn, 0, 1), m * n * 4)
     timed("add", lambda i: math.add(False, m, n, 1.0, X, 0, 1, As[i], 0, n), 2 * m * n * 4)
-    del As, Y2
+    timed("maximum", lambda i: math.maximum(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
+    timed("greater", lambda i: math.greater(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
+    timed("duplicate", lambda i: math.duplicate(False, m, n, X, 0, 1, As[i], 0, n), m * n * 4)
+    timed("exp", lambda i: math.exp(m * n, As[i], 0, 1), 2 * m * n * 4)
+    timed("tanh", lambda i: math.tanh(m * n, As[i], 0, 1), 2 * m * n * 4)
+    timed("increment", lambda i: math.increment(m * n, 1.0001, As[i], 0, 1, 0.001), 2 * m * n * 4)
+    timed("equal", lambda i: math.equal(m * n, As[i], 0, 1, Y2, 0, 1), 3 * m * n * 4)
+    I32 = CudaBuffer(m * n, dtypes.int32)
+    timed("astype_f32_i32", lambda i: math.astype(m * n, dtypes.int32, As[i], 0, 1, I32, 0, 1), 2 * m * n * 4)
+    timed("sum", lambda i: math.sum(m * n, As[i], 0, 1), m * n * 4)
+    timed("imax", lambda i: math.imax(m * n, As[i], 0, 1), m * n * 4)
+    del As, Y2, I32
     m, n = 65536, 1024
     Rs = [rnd(m * n) for _ in range(3)]
     Bf = CudaBuffer(m, f32)
