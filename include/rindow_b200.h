@@ -146,6 +146,26 @@ int rb200_sgemm_streamed(int order, int transA, int transB, int64_t m, int64_t n
                          float* dB, const float* hB, int64_t offB, int64_t ldB,
                          float beta, float* dC, float* hC, int hC_is_current, int64_t offC, int64_t ldC, int mode);
 
+/* ---- multi-GPU: row-sharded sgemm whose C stripe is ALSO written into the peers' copies of
+ *      the full C from the GEMM epilogue (peer stores over NVLink / NVSwitch), i.e. the all-gather of C overlaps
+ *      the multiply tile by tile instead of following it as an NCCL call.  One process per GPU: a rank exports its
+ *      full-C allocation with rb200_ipc_export (64-byte CUDA IPC handle, exchanged by the host -- e.g.
+ *      torch.distributed all_gather_object), opens the other ranks' handles with rb200_ipc_open and passes the
+ *      mapped base pointers as peer_C.  C / offC / ldC address this rank's stripe inside its own full C; every
+ *      peer_C[j] is indexed with the same offC / ldC.  The caller orders the ranks afterwards (a barrier) before
+ *      any rank reads rows it did not compute.  Same arithmetic, modes and argument rules as rb200_sgemm; shapes
+ *      that do not take the CTA-pair tensor-core kernel are multiplied first and pushed with peer copies. ------ */
+#define RB200_MAX_PEERS        15
+#define RB200_IPC_HANDLE_BYTES 64
+int rb200_ipc_export(void* dptr, void* handle64);
+int rb200_ipc_open(const void* handle64, void** dptr);
+int rb200_ipc_close(void* dptr);
+int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                          float alpha, const float* A, int64_t offA, int64_t ldA,
+                          const float* B, int64_t offB, int64_t ldB,
+                          float beta, float* C, int64_t offC, int64_t ldC, int mode,
+                          int n_peers, void* const* peer_C);
+
 /* ---- BLAS level 1 / 2: replace PhpBlas::scal (PhpBlas.php:141-161),
  *      axpy (:165-194), copy (:350-364), gemv (:762-844).  float32 / float64. ------------------------------ */
 int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_t incX);

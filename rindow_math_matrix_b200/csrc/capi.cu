@@ -107,6 +107,7 @@ int rb200_init(int device)
     c.total_mem = prop.totalGlobalMem;
     RB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
+    RB_CUDA(cudaHostAlloc(&c.pinned_scalar, 64, cudaHostAllocDefault));
     c.launches = 0;
     c.initialised = true;
     return RB200_OK;
@@ -124,6 +125,8 @@ int rb200_shutdown(void)
     if (c.counters) cudaFree(c.counters);
     c.counters = nullptr;
     c.counters_len = 0;
+    if (c.pinned_scalar) cudaFreeHost(c.pinned_scalar);
+    c.pinned_scalar = nullptr;
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     c.own_stream = nullptr;
     c.stream = nullptr;
@@ -259,6 +262,39 @@ int rb200_buffer_d2d(void* dst, int64_t dst_offset_bytes, const void* src, int64
     if (bytes == 0) return RB200_OK;
     RB_CUDA(cudaMemcpyAsync((char*)dst + dst_offset_bytes, (const char*)src + src_offset_bytes,
                             (size_t)bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return RB200_OK;
+}
+
+/* ---- peer memory (one process per GPU; NVLink / NVSwitch peer access through CUDA IPC) -------------- */
+
+int rb200_ipc_export(void* dptr, void* handle64)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr || !handle64) RB_INVALID("bad ipc_export arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RB200_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    RB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, sizeof(h));
+    return RB200_OK;
+}
+
+int rb200_ipc_open(const void* handle64, void** dptr)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr || !handle64) RB_INVALID("bad ipc_open arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *dptr = nullptr;
+    RB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RB200_OK;
+}
+
+int rb200_ipc_close(void* dptr)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr) return RB200_OK;
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    RB_CUDA(cudaIpcCloseMemHandle(dptr));
     return RB200_OK;
 }
 

@@ -27,6 +27,12 @@ struct Context {
     // self-resetting arrival tickets of the split reductions (zero between launches)
     int*        counters = nullptr;
     size_t      counters_len = 0;
+    // pinned 64-byte slot the scalar-result calls (sum / imax / imin / onehot's error flag) copy into
+    void*       pinned_scalar = nullptr;
+    // peer copies of C the next tensor-core GEMM also writes from its epilogue (rb200_sgemm_allgather)
+    float*      gemm_peers[RB200_MAX_PEERS] = {};
+    int         n_gemm_peers = 0;
+    bool        gemm_peers_written = false;
 };
 
 Context& ctx();

@@ -97,6 +97,40 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     return rb200::gemm_simt<float>(m, n, k, alpha, a, sAm, sAk, b, sBk, sBn, beta, cc, ldC);
 }
 
+// Row-sharded sgemm + all-gather of C through peer stores (include/rindow_b200.h).  The CTA-pair tensor-core kernel
+// writes every finished value to the peers from its epilogue; any other kernel family multiplies first and the
+// stripe is pushed with peer-to-peer copies on the same stream.
+int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                          float alpha, const float* A, int64_t offA, int64_t ldA,
+                          const float* B, int64_t offB, int64_t ldB,
+                          float beta, float* C, int64_t offC, int64_t ldC, int mode,
+                          int n_peers, void* const* peer_C)
+{
+    RB_REQUIRE_INIT();
+    if (n_peers < 0 || n_peers > RB200_MAX_PEERS || (n_peers > 0 && !peer_C)) RB_INVALID("bad peer list");
+    if (order != RB200_ROW_MAJOR) RB_UNSUPPORTED("rb200_sgemm_allgather: row-major only (the stripes are rows)");
+    rb200::Context& c = rb200::ctx();
+    for (int j = 0; j < n_peers; j++) {
+        if (!peer_C[j]) RB_INVALID("peer_C[%d] is NULL", j);
+        c.gemm_peers[j] = reinterpret_cast<float*>(peer_C[j]) + offC;
+    }
+    c.n_gemm_peers = n_peers;
+    c.gemm_peers_written = false;
+    const int rc = rb200_sgemm(order, transA, transB, m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC, mode);
+    c.n_gemm_peers = 0;
+    if (rc != RB200_OK || n_peers == 0 || c.gemm_peers_written) return rc;
+    for (int j = 0; j < n_peers; j++) {
+        float* dst = reinterpret_cast<float*>(peer_C[j]) + offC;
+        if (ldC == n) {
+            RB_CUDA(cudaMemcpyAsync(dst, C + offC, (size_t)(m * n) * sizeof(float), cudaMemcpyDefault, c.stream));
+        } else {
+            RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldC * sizeof(float), C + offC, (size_t)ldC * sizeof(float),
+                                      (size_t)n * sizeof(float), (size_t)m, cudaMemcpyDefault, c.stream));
+        }
+    }
+    return RB200_OK;
+}
+
 }  // extern "C"
 
 // ---- rb200_sgemm_streamed: the host-operand form of sgemm -------------------------------------------

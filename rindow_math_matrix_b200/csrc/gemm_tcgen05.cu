@@ -156,6 +156,10 @@ struct TcParams {
     // UMMA descriptor fields of an MN-major operand tile (boxes of 32 mn x 32 k floats):
     uint32_t mn_lbo, mn_sbo, mn_layout;
     int group_m;                   // row-blocks per rasterisation group (CTA-pair kernel)
+    // rb200_sgemm_allgather: peer copies of C (same row / column indexing, same ldC) that the CTA-pair kernel's
+    // epilogue also stores every finished value to -- NVLink peer stores overlapping the remaining tiles
+    int n_peers;
+    float* peers[RB200_MAX_PEERS];
 };
 
 template <int BN, int PLANES, int STAGES>
@@ -398,7 +402,9 @@ struct Tc2Cfg {
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int STAGES = PLANES == 1 ? 6 : 4;
     static constexpr int BAR_OFF = STAGES * STAGE;
-    static constexpr int SMEM = BAR_OFF + 256 + 1024;
+    static constexpr int STG_LD = 36;                          // floats per staged row (32 + 4: conflict-free float4 rows)
+    static constexpr int STG_OFF = BAR_OFF + 256;              // 4 epilogue warps x [32][STG_LD] floats (peer stores)
+    static constexpr int SMEM = STG_OFF + 4 * 32 * STG_LD * 4 + 1024;
     static constexpr int ACC_COLS = PLANES * BN;               // 256 TMEM columns per accumulator stage
 };
 
@@ -597,30 +603,69 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                     tc_wait_ld();
                 }
                 const int64_t c0 = col0 + ch * 32;
-                if (row_ok && c0 < p.N) {
-                    if (c0 + 32 <= p.N) {
+                if (c0 < p.N) {                                   // warp-uniform
+                    if (row_ok) {
+                        if (c0 + 32 <= p.N) {
+#pragma unroll
+                            for (int v = 0; v < 8; v++) {
+                                float4 o;
+                                o.x = p.alpha * __uint_as_float(r[4 * v + 0]);
+                                o.y = p.alpha * __uint_as_float(r[4 * v + 1]);
+                                o.z = p.alpha * __uint_as_float(r[4 * v + 2]);
+                                o.w = p.alpha * __uint_as_float(r[4 * v + 3]);
+                                float4* dst = reinterpret_cast<float4*>(crow + c0) + v;
+                                if (p.beta != 0.f) {
+                                    const float4 old = *dst;
+                                    o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
+                                    o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+                                }
+                                *dst = o;
+                                r[4 * v + 0] = __float_as_uint(o.x); r[4 * v + 1] = __float_as_uint(o.y);
+                                r[4 * v + 2] = __float_as_uint(o.z); r[4 * v + 3] = __float_as_uint(o.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; e++) {
+                                if (c0 + e < p.N) {
+                                    float o = p.alpha * __uint_as_float(r[e]);
+                                    if (p.beta != 0.f) o = fmaf(p.beta, crow[c0 + e], o);
+                                    crow[c0 + e] = o;
+                                    r[e] = __float_as_uint(o);
+                                }
+                            }
+                        }
+                    }
+                    if (p.n_peers > 0) {
+                        // all-gather leg: the warp's 32 x 32 block of final values goes through a padded smem tile so
+                        // that every peer store instruction writes whole 128-byte row segments (NVLink-friendly),
+                        // instead of 32 scattered 16-byte pieces
+                        float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + (warp - 4) * (32 * L::STG_LD);
+                        __syncwarp();
 #pragma unroll
                         for (int v = 0; v < 8; v++) {
-                            float4 o;
-                            o.x = p.alpha * __uint_as_float(r[4 * v + 0]);
-                            o.y = p.alpha * __uint_as_float(r[4 * v + 1]);
-                            o.z = p.alpha * __uint_as_float(r[4 * v + 2]);
-                            o.w = p.alpha * __uint_as_float(r[4 * v + 3]);
-                            float4* dst = reinterpret_cast<float4*>(crow + c0) + v;
-                            if (p.beta != 0.f) {
-                                const float4 old = *dst;
-                                o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
-                                o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
-                            }
-                            *dst = o;
+                            *reinterpret_cast<float4*>(stg + lane * L::STG_LD + 4 * v) =
+                                make_float4(__uint_as_float(r[4 * v + 0]), __uint_as_float(r[4 * v + 1]),
+                                            __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                         }
-                    } else {
+                        __syncwarp();
+                        const int64_t row_base = (int64_t)mb * 256 + (int64_t)rank * 128 + q * 32;
+                        const int cc = (lane & 7) * 4;
 #pragma unroll
-                        for (int e = 0; e < 32; e++) {
-                            if (c0 + e < p.N) {
-                                float o = p.alpha * __uint_as_float(r[e]);
-                                if (p.beta != 0.f) o = fmaf(p.beta, crow[c0 + e], o);
-                                crow[c0 + e] = o;
+                        for (int pass = 0; pass < 8; pass++) {
+                            const int rr = pass * 4 + (lane >> 3);
+                            const int64_t grow = row_base + rr;
+                            if (grow < p.M && c0 + cc < p.N) {
+                                const float4 val = *reinterpret_cast<const float4*>(stg + rr * L::STG_LD + cc);
+                                const int64_t at = grow * p.ldC + c0 + cc;
+                                if (c0 + cc + 4 <= p.N) {
+                                    for (int pj = 0; pj < p.n_peers; pj++)
+                                        st_stream_f4(reinterpret_cast<float4*>(p.peers[pj] + at), val);
+                                } else {
+                                    const float ve[4] = {val.x, val.y, val.z, val.w};
+                                    for (int pj = 0; pj < p.n_peers; pj++)
+                                        for (int e = 0; e < 4; e++)
+                                            if (c0 + cc + e < p.N) p.peers[pj][at + e] = ve[e];
+                                }
                             }
                         }
                     }
@@ -852,6 +897,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
+        p.n_peers = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
         if ((planes == 1 || use_2cta_x3) && use_2cta && M >= 256 && c.sm_count >= 2) {
@@ -865,6 +911,11 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
             // and an A panel (8 x 256 rows) that stays L2-resident across the waves of its group
             static const int dbg_group = getenv("RB200_GEMM_GROUP") ? atoi(getenv("RB200_GEMM_GROUP")) : 8;
             p.group_m = dbg_group > 0 ? dbg_group : 8;
+            if (c.n_gemm_peers > 0 && kc + KC >= K) {            // the chunk that produces the final values
+                p.n_peers = c.n_gemm_peers;
+                for (int pj = 0; pj < c.n_gemm_peers; pj++) p.peers[pj] = c.gemm_peers[pj];
+                c.gemm_peers_written = true;
+            }
             rc = planes == 1 ? launch_2cta<1>(a_mn, b_mn, mA, mB2, p) : launch_2cta<2>(a_mn, b_mn, mA, mB2, p);
             c.last_gemm_path = planes == 1 ? "tcgen05_tf32_2cta" : "tcgen05_tf32x3_2cta";
         } else if (planes == 1) rc = launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p);

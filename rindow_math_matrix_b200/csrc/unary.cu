@@ -276,17 +276,62 @@ astype_kernel(int64_t n, const S* __restrict__ X, int64_t incX, D* __restrict__ 
     }
 }
 
+// unit-stride form: a thread moves groups of four consecutive elements (4..32-byte accesses on either side),
+// four groups in flight
+template <typename T> struct alignas(sizeof(T) * 4) AsVec4 { T v[4]; };
+constexpr int AS_UNROLL = 4;
+
+template <typename D, typename S, bool TO_BOOL>
+__global__ void __launch_bounds__(UN_THREADS)
+astype_vec_kernel(int64_t ngroups, const S* __restrict__ X, D* __restrict__ Y)
+{
+    const AsVec4<S>* xv = reinterpret_cast<const AsVec4<S>*>(X);
+    AsVec4<D>* yv = reinterpret_cast<AsVec4<D>*>(Y);
+    const int64_t chunk = (int64_t)UN_THREADS * AS_UNROLL;
+    for (int64_t base = (int64_t)blockIdx.x * chunk; base < ngroups; base += (int64_t)gridDim.x * chunk) {
+        AsVec4<S> x[AS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            const int64_t i = base + u * UN_THREADS + threadIdx.x;
+            if (i < ngroups) x[u] = xv[i];
+        }
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            const int64_t i = base + u * UN_THREADS + threadIdx.x;
+            if (i < ngroups) {
+                AsVec4<D> y;
+#pragma unroll
+                for (int e = 0; e < 4; e++) y.v[e] = TO_BOOL ? (D)(as_truthy<S>(x[u].v[e]) ? 1 : 0) : AsCast<D, S>::run(x[u].v[e]);
+                yv[i] = y;
+            }
+        }
+    }
+}
+
 template <typename D, typename S>
 int astype_launch(bool to_bool, int64_t n, const void* Xv, int64_t offX, int64_t incX, void* Yv, int64_t offY, int64_t incY)
 {
     rb200::Context& c = rb200::ctx();
     const S* X = reinterpret_cast<const S*>(Xv) + offX;
     D* Y = reinterpret_cast<D*>(Yv) + offY;
-    int64_t grid = rb_ceil_div(n, (int64_t)UN_THREADS * UN_UNROLL);
     const int64_t cap = (int64_t)c.sm_count * 16;
+    int64_t done = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(X) % (sizeof(S) * 4) == 0) && (reinterpret_cast<uintptr_t>(Y) % (sizeof(D) * 4) == 0);
+    if (incX == 1 && incY == 1 && aligned && n >= 4) {
+        const int64_t ngroups = n / 4;
+        int64_t grid = rb_ceil_div(ngroups, (int64_t)UN_THREADS * AS_UNROLL);
+        if (grid > cap) grid = cap;
+        if (to_bool) astype_vec_kernel<D, S, true><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(ngroups, X, Y);
+        else         astype_vec_kernel<D, S, false><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(ngroups, X, Y);
+        RB_LAUNCH_CHECK("astype_vec_kernel");
+        done = ngroups * 4;
+        if (done == n) return RB200_OK;
+    }
+    const int64_t rest = n - done;
+    int64_t grid = rb_ceil_div(rest, (int64_t)UN_THREADS * UN_UNROLL);
     if (grid > cap) grid = cap;
-    if (to_bool) astype_kernel<D, S, true><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(n, X, incX, Y, incY);
-    else         astype_kernel<D, S, false><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(n, X, incX, Y, incY);
+    if (to_bool) astype_kernel<D, S, true><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(rest, X + done * incX, incX, Y + done * incY, incY);
+    else         astype_kernel<D, S, false><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(rest, X + done * incX, incX, Y + done * incY, incY);
     RB_LAUNCH_CHECK("astype_kernel");
     return RB200_OK;
 }
@@ -409,16 +454,27 @@ scalar_reduce_kernel(int64_t n, const T* __restrict__ X, int64_t incX, int64_t s
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // the last CTA merges the partials: thread-strided loads (L2, bypassing L1), shuffle tree, one writer
+    static_assert(sizeof(Acc) % 8 == 0, "partials are moved as 8-byte words");
+    acc = Pol::init();
+    bool have = false;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += SR_THREADS) {
+        Acc pb;
+        const long long* src = reinterpret_cast<const long long*>(partials + b);
+        long long* dst = reinterpret_cast<long long*>(&pb);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(Acc) / 8); k++) dst[k] = __ldcg(src + k);
+        acc = have ? Pol::merge(acc, pb) : pb;
+        have = true;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = Pol::merge(acc, Pol::shfl(acc, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) warp_acc[threadIdx.x >> 5] = acc;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const volatile Acc* vp = partials;
-        Acc a = Pol::init();
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            Acc pb;
-            const volatile char* src = reinterpret_cast<const volatile char*>(vp + b);
-            char* dst = reinterpret_cast<char*>(&pb);
-            for (int k = 0; k < (int)sizeof(Acc); k++) dst[k] = src[k];
-            a = (b == 0) ? pb : Pol::merge(a, pb);
-        }
+        Acc a = warp_acc[0];
+        for (int w = 1; w < SR_THREADS / 32; w++) a = Pol::merge(a, warp_acc[w]);
         out[0] = Pol::finish(a, n, X);
         *counter = 0;                                                          // self-resetting ticket
     }
@@ -450,8 +506,9 @@ int scalar_reduce_launch(int64_t n, const void* Xv, int64_t offX, int64_t incX, 
     if (vec) scalar_reduce_kernel<T, Pol, true><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, 1, seg, partials, counter, out);
     else     scalar_reduce_kernel<T, Pol, false><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, incX, seg, partials, counter, out);
     RB_LAUNCH_CHECK("scalar_reduce_kernel");
-    RB_CUDA(cudaMemcpyAsync(host_out, out, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaMemcpyAsync(c.pinned_scalar, out, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
     RB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(host_out, c.pinned_scalar, sizeof(int64_t));
     return RB200_OK;
 }
 
@@ -513,9 +570,10 @@ int onehot_launch(int64_t m, int64_t n, double a, const void* Xv, int64_t offX, 
     onehot_kernel<TX, TY><<<(unsigned)grid, UN_THREADS, 0, c.stream>>>(
         m, n, (TY)a, reinterpret_cast<const TX*>(Xv) + offX, incX, reinterpret_cast<TY*>(Yv) + offY, ldY, bad);
     RB_LAUNCH_CHECK("onehot_kernel");
-    int host_bad = 0;
-    RB_CUDA(cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaMemcpyAsync(c.pinned_scalar, bad, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     RB_CUDA(cudaStreamSynchronize(c.stream));
+    int host_bad = 0;
+    memcpy(&host_bad, c.pinned_scalar, sizeof(int));
     if (host_bad) {
         rb200::set_error("Label number is out of bounds.");
         return RB200_E_RANGE;

@@ -8,6 +8,8 @@ PHP shim delegates those to PhpBlas on the host mirror, this pa
 """
 from __future__ import annotations
 
+import ctypes
+
 from . import _capi, dtypes
 from .cuda_buffer import CudaBuffer
 from .exceptions import InvalidArgumentException, LogicException, RuntimeException
@@ -194,6 +196,31 @@ class CudaBlas:
         else:
             raise LogicException("CudaBlas::gemm supports float32/float64; the reference routes integer "
                                  "dtypes to the LV_BASIC PHP driver (MatrixOperator.php:225-231)")
+
+    # ---- multi-GPU: row-sharded gemm whose C stripe also lands in the peers' full C ----
+    def gemmAllgather(self, transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB,
+                      beta, C, offsetC, ldC, peer_ptrs) -> None:
+        """PhpBlas::gemm semantics (row-major) for this rank's stripe: C[offsetC ...] is the stripe inside this
+        rank's full C; peer_ptrs are the other ranks' full-C allocations mapped here (sharding.PeerRows).  The
+        tensor-core kernel stores every finished tile to the peers from its epilogue (rb200_sgemm_allgather);
+        the caller orders the ranks afterwards (PeerRows.arrive)."""
+        tA, _ = code_to_trans(transA)
+        tB, _ = code_to_trans(transB)
+        assert_shape_parameter("m", m)
+        assert_shape_parameter("n", n)
+        assert_shape_parameter("k", k)
+        rowsA, colsA = (m, k) if not tA else (k, m)
+        rowsB, colsB = (k, n) if not tB else (n, k)
+        assert_matrix_buffer_spec("A", A, rowsA, colsA, offsetA, ldA)
+        assert_matrix_buffer_spec("B", B, rowsB, colsB, offsetB, ldB)
+        assert_matrix_buffer_spec("C", C, m, n, offsetC, ldC)
+        if not (A.dtype() == B.dtype() == C.dtype() == dtypes.float32):
+            raise LogicException("CudaBlas::gemmAllgather supports float32")
+        peers = (ctypes.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
+        _capi.check(self._lib.rb200_sgemm_allgather(
+            BLAS.RowMajor, transA, transB, m, n, k, float(alpha), A.device_ptr(), offsetA, ldA,
+            B.device_ptr(), offsetB, ldB, float(beta), C.device_ptr_rw(), offsetC, ldC, self.gemm_mode,
+            len(peer_ptrs), peers))
 
     # ---- helpers ----------------------------------------------------------------------------------------
     @staticmethod

@@ -74,6 +74,67 @@ def gather_rows(local: torch.Tensor, total_rows: int, group=None) -> torch.Tenso
     return torch.cat([p[:r] for p, (_, r) in zip(parts, ranges)], dim=0)
 
 
+class PeerRows:
+    """A full [total_rows, cols] float32 matrix replicated on every rank whose row stripes are produced by their
+    owners and pushed to all peers over NVLink from inside the producing kernel (rb200_sgemm_allgather) -- the
+    fused form of `gemm` + `gather_rows`.  One process per GPU: the full-C allocations are exchanged as CUDA IPC
+    handles through the process group (host plumbing only) and mapped with rb200_ipc_open.
+
+    exchange() is injectable so the handle plumbing runs under gloo on CPU (tests/test_sharding_gloo.py)."""
+
+    def __init__(self, full_buffer, total_rows: int, cols: int, group=None, export=None, open_handle=None):
+        from . import _capi
+        import ctypes
+        self.buffer, self.total_rows, self.cols, self.group = full_buffer, int(total_rows), int(cols), group
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.start, self.rows = row_range(self.total_rows, self.world, self.rank)
+        self._opened = []
+        self._flag = None
+        self.peer_ptrs: List[int] = []
+        if self.world == 1:
+            return
+        lib = _capi.load() if export is None else None
+
+        def _export():
+            h = (ctypes.c_uint8 * 64)()
+            _capi.check(lib.rb200_ipc_export(full_buffer.raw_pointers()[0], h))
+            return bytes(h)
+
+        def _open(handle: bytes) -> int:
+            p = ctypes.c_void_p()
+            hb = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+            _capi.check(lib.rb200_ipc_open(hb, ctypes.byref(p)))
+            self._opened.append(p.value)
+            return p.value
+
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (export or _export)(), group=group)
+        self.handles = handles
+        self.peer_ptrs = [(open_handle or _open)(h) for r, h in enumerate(handles) if r != self.rank]
+
+    def stripe_offset(self) -> int:
+        """element offset of this rank's stripe inside the full matrix"""
+        return self.start * self.cols
+
+    def arrive(self) -> None:
+        """Order the ranks after a step: every stripe has landed everywhere once this returns on the stream
+        (a process-group barrier; under NCCL a tiny all-reduce on the current stream)."""
+        if self.world > 1:
+            if self._flag is None:
+                on_gpu = dist.get_backend(self.group) == "nccl"
+                self._flag = torch.zeros(1, dtype=torch.int32, device="cuda" if on_gpu else "cpu")
+            dist.all_reduce(self._flag, group=self.group)         # stream-ordered under NCCL: no host sync
+
+    def close(self) -> None:
+        if self._opened:
+            from . import _capi
+            lib = _capi.load()
+            for p in self._opened:
+                lib.rb200_ipc_close(p)
+            self._opened = []
+
+
 def merge_sum(partial: torch.Tensor, group=None) -> torch.Tensor:
     """Sum of per-rank partial sums (all-reduce)."""
     if _world(group) > 1:

@@ -80,6 +80,15 @@ def _worker(rank, world, port, q):
             col_ok &= ~np.isnan(X[s1])
         assert np.array_equal(got_i[col_ok], gi[col_ok]), ("merge_argmax", got_i, gi)
         assert got_i[7] == 0                                      # NaN at global 0 sticks
+        # --- PeerRows (fused gemm + gather): handle exchange and stripe addressing, with fake handles
+        pr = sharding.PeerRows(None, M, N, export=lambda: bytes([rank + 1]) * 64, open_handle=lambda h: 1000 + h[0])
+        assert pr.world == world and pr.rank == rank
+        assert (pr.start, pr.rows) == sharding.row_range(M, world, rank)
+        assert pr.stripe_offset() == start * N
+        assert pr.peer_ptrs == [1000 + r + 1 for r in range(world) if r != rank]     # rank order, self excluded
+        assert pr.handles == [bytes([r + 1]) * 64 for r in range(world)]
+        pr.arrive()
+        pr.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
