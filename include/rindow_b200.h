@@ -96,7 +96,7 @@ int         rb200_get_default_gemm_mode(int* mode);
  * (bench.py's "gpu_launches"). */
 int         rb200_launch_count(int64_t* count, int reset);
 /* Name of the kernel family the last rb200_sgemm/dgemm/conv2d_forward dispatched to: "tcgen05_tf32_2cta",
- * "tcgen05_tf32", "tcgen05_tf32x3", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
+ * "tcgen05_tf32", "tcgen05_tf32_128", "tcgen05_tf32x3", "tcgen05_tf32x3_64", "tcgen05_tf32x3_2cta", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
  * "simt_f32", "simt_f64". */
 const char* rb200_last_gemm_path(void);
 

@@ -900,7 +900,40 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.n_peers = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
-        if ((planes == 1 || use_2cta_x3) && use_2cta && M >= 256 && c.sm_count >= 2) {
+        static const int use_small = getenv("RB200_GEMM_SMALL_TILES") ? atoi(getenv("RB200_GEMM_SMALL_TILES")) : 1;
+        // Tile shape by estimated makespan (tiles are strided over the persistent CTAs, so a launch takes
+        // ceil(tiles / units) tile times): the CTA pair wins whenever it fills the machine; problems with fewer
+        // pair tiles than half the pairs (1024^3: 16 of 74) run 128 x 128 tiles on single CTAs instead -- four
+        // times the tiles, a quarter of the work each.
+        const bool pair_ok = (planes == 1 || use_2cta_x3) && use_2cta && M >= 256 && c.sm_count >= 2;
+        const int64_t pairs = c.sm_count / 2;
+        const int64_t tiles_pair = rb_ceil_div(M, 256) * rb_ceil_div(N, BN);
+        const int64_t tiles_small = rb_ceil_div(M, 128) * rb_ceil_div(N, 128);
+        const double t_pair = (double)rb_ceil_div(tiles_pair, pairs) * (256.0 * BN / 2.0);
+        const double t_small = (double)rb_ceil_div(tiles_small, (int64_t)c.sm_count) * (128.0 * 128.0) * 1.15;
+        const bool small_tiles = planes == 1 && use_small && c.n_gemm_peers == 0 && (!pair_ok || t_small < t_pair);
+        // 3xTF32: the pair tile is 256 x 128 and the single-CTA tile 128 x 128 (the same work per SM); small
+        // problems take 128 x 64 tiles
+        const int64_t tiles_x3s = rb_ceil_div(M, 128) * rb_ceil_div(N, 64);
+        const double t_x3s = (double)rb_ceil_div(tiles_x3s, (int64_t)c.sm_count) * (128.0 * 64.0) * 1.15;
+        const bool small_x3 = planes == 2 && use_small && c.n_gemm_peers == 0 && t_x3s < t_pair;
+        if (small_x3) {
+            CUtensorMap mBs;
+            if (!b_mn) rc = make_map(&mBs, pb, kl, N, sldB, planes, plsB, TC_BK, 64, k_sw);
+            else       rc = make_map(&mBs, pb, N, kl, sldB, planes, plsB, 32, TC_BK, mn_sw);
+            if (rc != RB200_OK) return rc;
+            p.num_n_blocks = (int)rb_ceil_div(N, 64);
+            rc = launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mBs, p);
+            c.last_gemm_path = "tcgen05_tf32x3_64";
+        } else if (small_tiles) {
+            CUtensorMap mBs;
+            if (!b_mn) rc = make_map(&mBs, pb, kl, N, sldB, planes, plsB, TC_BK, 128, k_sw);
+            else       rc = make_map(&mBs, pb, N, kl, sldB, planes, plsB, 32, TC_BK, mn_sw);
+            if (rc != RB200_OK) return rc;
+            p.num_n_blocks = (int)rb_ceil_div(N, 128);
+            rc = launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mBs, p);
+            c.last_gemm_path = "tcgen05_tf32_128";
+        } else if (pair_ok) {
             // CTA-pair kernel: 256-row pair tiles; each CTA stages half of the pair tile's B columns
             CUtensorMap mB2;
             if (!b_mn) rc = make_map(&mB2, pb, kl, N, sldB, planes, plsB, TC_BK, BN / 2, k_sw);

@@ -35,7 +35,9 @@ def test_sgemm_allgather_local_peers(total, start, rows, n, k, mode, path, n_pee
     blas = rb.MatlibCuda(gemm_mode=mode).blas()
     blas.gemmAllgather(BLAS.NoTrans, BLAS.NoTrans, rows, n, k, 1.0, A, 0, k, B, 0, n, 0.0, C, start * n, n,
                        [p.raw_pointers()[0] for p in peers])
-    assert _capi.last_gemm_path() == path
+    # without peers, problems that leave most CTA pairs idle take the 128 x 128 single-CTA tiles instead
+    small = {rb.GEMM_TF32: "tcgen05_tf32_128", rb.GEMM_TF32X3: "tcgen05_tf32x3_64"}.get(mode)
+    assert _capi.last_gemm_path() in ((path, small) if n_peers == 0 else (path,))
     got = C.to_numpy().reshape(total, n)
     # the plain call on the same operands is the reference for "same arithmetic": bit-identical
     C2 = CudaBuffer(total * n, f32).from_numpy(sentinel.reshape(-1))

@@ -473,7 +473,7 @@ def test_gemm_tcgen05(mnk, tA, tB, mode, cuda_service):
         ldx += 1
     for alpha, beta, off in ((1.0, 0.0, 0), (1.0, 1.0, 0), (0.75, -1.5, 8)):
         err, path = _gemm_case(cuda_service, mode, m, n, k, tA, tB, alpha, beta, off, off, off, ldx)
-        assert path in (("tcgen05_tf32", "tcgen05_tf32_2cta") if mode == rb.GEMM_TF32 else ("tcgen05_tf32x3", "tcgen05_tf32x3_2cta")), path
+        assert path in (("tcgen05_tf32", "tcgen05_tf32_2cta", "tcgen05_tf32_128") if mode == rb.GEMM_TF32 else ("tcgen05_tf32x3", "tcgen05_tf32x3_2cta", "tcgen05_tf32x3_64")), path
         assert err < GEMM_TOL[mode], (err, path, mnk, tA, tB, alpha, beta)
         if mode == rb.GEMM_TF32X3:
             assert err < 1e-4            # the reference's own isclose rtol
@@ -492,7 +492,7 @@ def test_gemm_tf32x3_long_k_accumulator_drift(cuda_service):
         A, B, C = buf(Ah), buf(Bh), CudaBuffer(m * n, dtypes.float32)
         blas.setGemmMode(rb.GEMM_TF32X3)
         blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, m, n, k, 1.0, A, 0, k, B, 0, n, 0.0, C, 0, n)
-        assert rb._capi.last_gemm_path() in ("tcgen05_tf32x3", "tcgen05_tf32x3_2cta")
+        assert rb._capi.last_gemm_path() in ("tcgen05_tf32x3", "tcgen05_tf32x3_2cta", "tcgen05_tf32x3_64")
         rel = np.abs(C.to_numpy().reshape(m, n) - ref) / ref
         assert rel.max() < 3e-5, (k, rel.max())          # ~7e-9 * min(K, 2048) drift, see DESIGN.md 4.1
         # beta / alpha survive the chunking: C = 0.5*A*B + 2*C0
@@ -527,7 +527,7 @@ def test_gemm_tall_skinny_conv_shapes(mnk, cuda_service):
                 assert path in ("simt_f32_shortk", "simt_f32") and err < 2e-6, (path, err)
             elif mode == rb.GEMM_TF32:
                 if skinny:
-                    assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32", "tcgen05_tf32_2cta"), path
+                    assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32", "tcgen05_tf32_2cta", "tcgen05_tf32_128"), path
                 assert err < 2e-3, (err, path)
             else:
                 if skinny:      # aligned full-width shapes may take the TMA-fed kernel instead

@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""Time rb200_sgemm over sizes / modes with CUDA events (random operands).  Usage: gemm_sweep.py [mode] [sizes...]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch  # noqa: E402
+import rindow_math_matrix_b200 as rb  # noqa: E402
+from rindow_math_matrix_b200 import BLAS, CudaBuffer, _capi, dtypes  # noqa: E402
+
+
+def main():
+    mode_name = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+    sizes = [int(x) for x in sys.argv[2:]] or [512, 768, 1024, 1536, 2048, 3072, 4096]
+    mode = {"tf32": rb.GEMM_TF32, "tf32x3": rb.GEMM_TF32X3}[mode_name]
+    blas = rb.MatlibCuda(gemm_mode=mode).blas()
+    stream = torch.cuda.Stream()
+    _capi.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(0)
+    for n in sizes:
+        A = [CudaBuffer(n * n, dtypes.float32).from_numpy(rng.uniform(-1, 1, n * n).astype(np.float32)) for _ in range(3)]
+        B = CudaBuffer(n * n, dtypes.float32).from_numpy(rng.uniform(-1, 1, n * n).astype(np.float32))
+        C = CudaBuffer(n * n, dtypes.float32)
+
+        def step(i):
+            blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A[i % 3], 0, n, B, 0, n, 0.0, C, 0, n)
+
+        for i in range(5):
+            step(i)
+        _capi.sync()
+        reps = max(10, min(200, int(2e12 / (2.0 * n ** 3)) + 1))
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(reps):
+                step(i)
+            e1.record(stream)
+            _capi.sync()
+            best = min(best, e0.elapsed_time(e1) / reps)
+        print("%-7s n=%5d  %.4f ms  %7.1f TFLOP/s  path=%s" % (mode_name, n, best, 2.0 * n ** 3 / best / 1e9, _capi.last_gemm_path()), flush=True)
+
+
+if __name__ == "__main__":
+    main()
