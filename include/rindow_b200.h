@@ -133,6 +133,16 @@ int rb200_dgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
                 const double* B, int64_t offB, int64_t ldB,
                 double beta, double* C, int64_t offC, int64_t ldC);
 
+/* `batch` row-major products C_i = alpha * op(A_i) * op(B_i) (+ beta * C_i) with A_i = A + offA + i*strideA etc.
+ * (strides in elements; strideA or strideB == 0 shares that operand across the batch) -- the inner loop of
+ * LinearAlgebra::matmul (src/LinearAlgebra.php:1091-1106; the reference's accelerated driver has the same entry:
+ * LinearAlgebraCL::matmul -> gemmStridedBatched, src/LinearAlgebraCL.php:2001).  dtype float32 (mode as in
+ * rb200_sgemm) or float64. */
+int rb200_gemm_strided_batched(int dtype, int transA, int transB, int64_t m, int64_t n, int64_t k, double alpha,
+                               const void* A, int64_t offA, int64_t ldA, int64_t strideA,
+                               const void* B, int64_t offB, int64_t ldB, int64_t strideB, double beta,
+                               void* C, int64_t offC, int64_t ldC, int64_t strideC, int64_t batch, int mode);
+
 /* sgemm for operands whose current copy is in (pinned) HOST memory -- the e2e form of PhpBlas::gemm for a
  * caller that fills buffers from PHP and reads the product back (MatrixOperator::cross followed by
  * toArray(), MatrixOperator.php:429-508).  dX is the device allocation, hX the host mirror with the same

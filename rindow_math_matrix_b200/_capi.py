@@ -52,6 +52,8 @@ SIGNATURES = {
     "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
     "rb200_sgemm_streamed": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, vp, i64, i64, vp, vp, i64, i64,
                                    f32, vp, vp, i32, i64, i64, i32]),
+    "rb200_gemm_strided_batched": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, i64, vp, i64, i64, i64, f64,
+                                         vp, i64, i64, i64, i64, i32]),
     "rb200_ipc_export": (i32, [vp, vp]),
     "rb200_ipc_open": (i32, [vp, ctypes.POINTER(vp)]),
     "rb200_ipc_close": (i32, [vp]),

@@ -10,6 +10,10 @@ namespace rb200 {
 template <typename T>
 int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk,
               const T* B, int64_t sBk, int64_t sBn, T beta, T* C, int64_t ldC);
+template <typename T>
+int gemm_simt_batched(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk, int64_t strideA,
+                      const T* B, int64_t sBk, int64_t sBn, int64_t strideB, T beta, T* C, int64_t ldC, int64_t strideC,
+                      int64_t batch);
 bool gemm_shortk_eligible(int64_t M, int64_t N, int64_t K, int64_t sAk, int64_t sBn);
 int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t ldA,
                 const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
@@ -95,6 +99,52 @@ int rb200_sgemm(int order, int transA, int transB, int64_t m, int64_t n, int64_t
     }
     c.last_gemm_path = "simt_f32";
     return rb200::gemm_simt<float>(m, n, k, alpha, a, sAm, sAk, b, sBk, sBn, beta, cc, ldC);
+}
+
+// `batch` products at fixed element strides (0 shares an operand): what LinearAlgebra::matmul issues as a loop of
+// gemm calls (LinearAlgebra.php:1091-1106).  Matrices of at least one tensor-core tile each go through rb200_sgemm
+// one after the other (every launch already fills the machine); smaller / unaligned / float64 ones run as ONE
+// launch of the FFMA / DFMA kernel with the batch on blockIdx.z.
+int rb200_gemm_strided_batched(int dtype, int transA, int transB, int64_t m, int64_t n, int64_t k, double alpha,
+                               const void* A, int64_t offA, int64_t ldA, int64_t strideA,
+                               const void* B, int64_t offB, int64_t ldB, int64_t strideB, double beta,
+                               void* C, int64_t offC, int64_t ldC, int64_t strideC, int64_t batch, int mode)
+{
+    bool tA, tB;
+    int rc = decode(RB200_ROW_MAJOR, transA, transB, m, n, k, tA, tB, A, B, C, offA, ldA, offB, ldB, offC, ldC);
+    if (rc != RB200_OK) return rc;
+    if (batch < 1) RB_INVALID("Argument batch must be greater than 0.");
+    if (strideA < 0 || strideB < 0 || strideC < 0) RB_INVALID("Argument stride must be greater than equals 0.");
+    if (strideC == 0 && batch > 1) RB_INVALID("strideC must not be 0: the products would overwrite each other");
+    rb200::Context& c = rb200::ctx();
+    const int64_t sAm = tA ? 1 : ldA, sAk = tA ? ldA : 1;
+    const int64_t sBk = tB ? 1 : ldB, sBn = tB ? ldB : 1;
+    if (dtype == RB200_FLOAT64) {
+        c.last_gemm_path = "simt_f64_batched";
+        return rb200::gemm_simt_batched<double>(m, n, k, alpha, reinterpret_cast<const double*>(A) + offA, sAm, sAk, strideA,
+                                                reinterpret_cast<const double*>(B) + offB, sBk, sBn, strideB, beta,
+                                                reinterpret_cast<double*>(C) + offC, ldC, strideC, batch);
+    }
+    if (dtype != RB200_FLOAT32) RB_UNSUPPORTED("gemm_strided_batched: unsupported dtype %d", dtype);
+    if (mode == RB200_GEMM_AUTO) mode = c.default_gemm_mode;
+    if (mode < RB200_GEMM_FP32_SIMT || mode > RB200_GEMM_TF32X3) RB_INVALID("unknown gemm mode %d", mode);
+    const float* a = reinterpret_cast<const float*>(A) + offA;
+    const float* b = reinterpret_cast<const float*>(B) + offB;
+    float* cc = reinterpret_cast<float*>(C) + offC;
+    const bool tensor = mode != RB200_GEMM_FP32_SIMT && m >= 128 && n >= 128 && k >= 32 &&
+                        strideA % 4 == 0 && strideB % 4 == 0 && strideC % 4 == 0 &&
+                        rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC);
+    if (tensor) {
+        for (int64_t i = 0; i < batch; i++) {
+            rc = rb200::gemm_tcgen05(mode, tA, tB, m, n, k, (float)alpha, a + i * strideA, ldA, b + i * strideB, ldB,
+                                     (float)beta, cc + i * strideC, ldC);
+            if (rc != RB200_OK) return rc;
+        }
+        return RB200_OK;
+    }
+    c.last_gemm_path = "simt_f32_batched";
+    return rb200::gemm_simt_batched<float>(m, n, k, (float)alpha, a, sAm, sAk, strideA, b, sBk, sBn, strideB, (float)beta,
+                                           cc, ldC, strideC, batch);
 }
 
 // Row-sharded sgemm + all-gather of C through peer stores (include/rindow_b200.h).  The CTA-pair tensor-core kernel

@@ -20,8 +20,13 @@ __global__ void __launch_bounds__(GS_THREADS)
 gemm_simt_kernel(int64_t M, int64_t N, int64_t K, T alpha,
                  const T* __restrict__ A, int64_t sAm, int64_t sAk,
                  const T* __restrict__ B, int64_t sBk, int64_t sBn,
-                 T beta, T* __restrict__ C, int64_t ldC)
+                 T beta, T* __restrict__ C, int64_t ldC,
+                 int64_t strideA, int64_t strideB, int64_t strideC)
 {
+    // blockIdx.z = matrix of a strided batch (strides in elements; 0 broadcasts an operand)
+    A += (int64_t)blockIdx.z * strideA;
+    B += (int64_t)blockIdx.z * strideB;
+    C += (int64_t)blockIdx.z * strideC;
     __shared__ T As[GS_BK][GS_BM + 1];
     __shared__ T Bs[GS_BK][GS_BN + 1];
     const int tid = threadIdx.x;
@@ -230,8 +235,22 @@ int gemm_shortk(int64_t M, int64_t N, int64_t K, float alpha, const float* A, in
 
 
 template <typename T>
+int gemm_simt_batched(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk, int64_t strideA,
+                      const T* B, int64_t sBk, int64_t sBn, int64_t strideB, T beta, T* C, int64_t ldC, int64_t strideC,
+                      int64_t batch);
+
+template <typename T>
 int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk,
               const T* B, int64_t sBk, int64_t sBn, T beta, T* C, int64_t ldC)
+{
+    return gemm_simt_batched<T>(M, N, K, alpha, A, sAm, sAk, 0, B, sBk, sBn, 0, beta, C, ldC, 0, 1);
+}
+
+// `batch` matrices at element strides strideA / strideB / strideC (0 = the operand is shared) in one launch
+template <typename T>
+int gemm_simt_batched(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm, int64_t sAk, int64_t strideA,
+                      const T* B, int64_t sBk, int64_t sBn, int64_t strideB, T beta, T* C, int64_t ldC, int64_t strideC,
+                      int64_t batch)
 {
     Context& c = ctx();
     const int64_t gx = rb_ceil_div(N, GS_BN), gy = rb_ceil_div(M, GS_BM);
@@ -240,17 +259,26 @@ int gemm_simt(int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t sAm,
         const int64_t stripe = 65535LL * GS_BM;
         for (int64_t r0 = 0; r0 < M; r0 += stripe) {
             const int64_t rows = (M - r0) < stripe ? (M - r0) : stripe;
-            int rc = gemm_simt<T>(rows, N, K, alpha, A + r0 * sAm, sAm, sAk, B, sBk, sBn, beta, C + r0 * ldC, ldC);
+            int rc = gemm_simt_batched<T>(rows, N, K, alpha, A + r0 * sAm, sAm, sAk, strideA, B, sBk, sBn, strideB, beta,
+                                          C + r0 * ldC, ldC, strideC, batch);
             if (rc != RB200_OK) return rc;
         }
         return RB200_OK;
     }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    gemm_simt_kernel<T><<<grid, GS_THREADS, 0, c.stream>>>(M, N, K, alpha, A, sAm, sAk, B, sBk, sBn, beta, C, ldC);
-    RB_LAUNCH_CHECK("gemm_simt_kernel");
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int64_t nb = (batch - b0) < 65535 ? (batch - b0) : 65535;
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nb);
+        gemm_simt_kernel<T><<<grid, GS_THREADS, 0, c.stream>>>(M, N, K, alpha, A + b0 * strideA, sAm, sAk, B + b0 * strideB,
+                                                                sBk, sBn, beta, C + b0 * strideC, ldC, strideA, strideB, strideC);
+        RB_LAUNCH_CHECK("gemm_simt_kernel");
+    }
     return RB200_OK;
 }
 
+template int gemm_simt_batched<float>(int64_t, int64_t, int64_t, float, const float*, int64_t, int64_t, int64_t,
+                                      const float*, int64_t, int64_t, int64_t, float, float*, int64_t, int64_t, int64_t);
+template int gemm_simt_batched<double>(int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t, int64_t,
+                                       const double*, int64_t, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t);
 template int gemm_simt<float>(int64_t, int64_t, int64_t, float, const float*, int64_t, int64_t,
                               const float*, int64_t, int64_t, float, float*, int64_t);
 template int gemm_simt<double>(int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t,

@@ -330,16 +330,25 @@ int forward_launch(const Im2colParams& p, const void* images, void* cols)
         if (dims_ok) {
             const int64_t width_x = (tox - 1) * p.stride_w + base_x;
             const int64_t row_elems = width_x * p.channels;
-            // as many out rows per CTA as fit in shared memory (they share source rows), but keep
-            // >= 4 CTAs per SM in flight
+            // Out rows per CTA (they share source rows): among the row counts whose working set fits, take the one
+            // whose grid fills whole waves of resident CTAs best -- C4 with 8 rows is 1792 CTAs = 1.51 waves (the
+            // second wave half empty), with 6 rows 2368 CTAs = exactly 2 waves.  Ties go to the larger count.
             int64_t rows = 1;
             const int64_t col_blocks = rb_ceil_div(p.out_w, tox);
-            while (rows < 8 && rows < p.out_h) {
-                const int64_t r2 = rows + 1;
+            double best_eff = -1.0;
+            for (int64_t r2 = 1; r2 <= 8 && r2 <= p.out_h; r2++) {
                 const int64_t slabs2 = (r2 - 1) * p.stride_h + base_y;
-                if (lut_bytes + slabs2 * row_elems * es > smem_budget) break;
-                if (p.batches * rb_ceil_div(p.out_h, r2) * col_blocks < (int64_t)c.sm_count * 8) break;
-                rows = r2;
+                const int64_t smem2 = lut_bytes + slabs2 * row_elems * es;
+                if (smem2 > smem_budget) break;
+                const int64_t ctas = p.batches * rb_ceil_div(p.out_h, r2) * col_blocks;
+                if (r2 > 1 && ctas < (int64_t)c.sm_count * 8) break;          // keep >= 8 CTAs per SM in the grid
+                int64_t per_sm = (220 * 1024) / (smem2 + 1024);
+                if (per_sm > 8) per_sm = 8;                                     // 2048 threads / 256
+                if (per_sm < 1) per_sm = 1;
+                const double waves = (double)ctas / (double)(per_sm * c.sm_count);
+                double eff = waves / (double)rb_ceil_div(ctas, per_sm * c.sm_count);
+                eff *= 1.0 - 0.02 * (double)(8 - r2) / 8.0;                     // fewer rows re-read more halo rows
+                if (eff >= best_eff) { best_eff = eff; rows = r2; }
             }
             // few CTAs (small images): split the rows into narrower column blocks instead
             if (rows == 1 && tox > 64 && p.batches * p.out_h * col_blocks < (int64_t)c.sm_count * 4) {

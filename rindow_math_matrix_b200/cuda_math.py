@@ -238,6 +238,34 @@ class CudaMath:
             raise RuntimeException("Label number is out of bounds.")
         _capi.check(rc)
 
+    # ---- strided-batched gemm: the call LinearAlgebraCL::matmul makes on its math object
+    #      (src/LinearAlgebraCL.php:2001-2012); row-major, same operand rules as PhpBlas::gemm --------------------
+    def gemmStridedBatched(self, order, transA, transB, m, n, k, alpha, A, offsetA, ldA, strideA,
+                           B, offsetB, ldB, strideB, beta, C, offsetC, ldC, strideC, batchSize, gemm_mode=None) -> None:
+        from .cuda_blas import BLAS, assert_matrix_buffer_spec, assert_shape_parameter, code_to_trans
+        if order != BLAS.RowMajor:
+            raise InvalidArgumentException("gemmStridedBatched is row-major")
+        tA, _ = code_to_trans(transA)
+        tB, _ = code_to_trans(transB)
+        assert_shape_parameter("m", m)
+        assert_shape_parameter("n", n)
+        assert_shape_parameter("k", k)
+        if batchSize < 1:
+            raise InvalidArgumentException("Argument batchSize must be greater than 0.")
+        rowsA, colsA = (m, k) if not tA else (k, m)
+        rowsB, colsB = (k, n) if not tB else (n, k)
+        last = batchSize - 1
+        assert_matrix_buffer_spec("A", A, rowsA, colsA, offsetA + last * strideA, ldA)
+        assert_matrix_buffer_spec("B", B, rowsB, colsB, offsetB + last * strideB, ldB)
+        assert_matrix_buffer_spec("C", C, m, n, offsetC + last * strideC, ldC)
+        _cuda("A", A), _cuda("B", B), _cuda("C", C)
+        if not (A.dtype() == B.dtype() == C.dtype()) or A.dtype() not in (dtypes.float32, dtypes.float64):
+            raise InvalidArgumentException("Unmatch data type for A, B and C")
+        mode = _capi.GEMM_AUTO if gemm_mode is None else gemm_mode
+        _capi.check(self._lib.rb200_gemm_strided_batched(
+            A.dtype(), transA, transB, m, n, k, float(alpha), A.device_ptr(), offsetA, ldA, strideA,
+            B.device_ptr(), offsetB, ldB, strideB, float(beta), C.device_ptr_rw(), offsetC, ldC, strideC, batchSize, mode))
+
     # ---- reductions over the middle axis of A[m,n,k] (PhpMath.php:1552-1643) ----------------------
     def _reduce_check(self, m, n, k, A, offsetA, B, offsetB) -> None:
         if offsetA + m * n * k > len(A):

@@ -166,11 +166,21 @@ class LinearAlgebra:
         tA = BLAS.Trans if transA else BLAS.NoTrans
         tB = BLAS.Trans if transB else BLAS.NoTrans
         offA, offB, offC = A.offset(), B.offset(), C.offset()
+        batched = getattr(self.math, "gemmStridedBatched", None) if type(self.math).__name__ == "CudaMath" else None
         for _ in range(dest // base):
             if batchA > batchB:
                 offB = B.offset()
             else:
                 offA = A.offset()
+            if batched is not None and base > 1:
+                # one driver call per broadcast repeat, as LinearAlgebraCL::matmul does (LinearAlgebraCL.php:1995-2016)
+                batched(BLAS.RowMajor, tA, tB, M, N, K, alpha, A.buffer(), offA, lda, M * K, B.buffer(), offB, ldb, N * K,
+                        beta, C.buffer(), offC, ldc, M * N, base,
+                        gemm_mode=getattr(self.blas, "gemm_mode", None))
+                offA += M * K * base
+                offB += N * K * base
+                offC += M * N * base
+                continue
             for _ in range(base):
                 self.blas.gemm(BLAS.RowMajor, tA, tB, M, N, K, alpha, A.buffer(), offA, lda,
                                B.buffer(), offB, ldb, beta, C.buffer(), offC, ldc)

@@ -187,3 +187,71 @@ def test_blas_widen_errors(cuda_service):
         blas.omatcopy(BLAS.RowMajor, 0, 2, 2, 1.0, X, 0, 2, Y, 0, 2)
     with pytest.raises(InvalidArgumentException, match="Matrix specification too large for bufferB."):
         blas.omatcopy(BLAS.RowMajor, BLAS.Trans, 1, 4, 1.0, X, 0, 4, Y, 1, 1)
+
+
+BATCHED = [
+    # batch, m, n, k, transA, transB, share (which operand is shared: 0 none, 1 A, 2 B), dtype, mode
+    (7, 40, 56, 24, False, False, 0, dtypes.float32, rb.GEMM_AUTO),
+    (5, 33, 17, 65, True, False, 0, dtypes.float32, rb.GEMM_FP32_SIMT),
+    (4, 64, 64, 64, False, True, 2, dtypes.float32, rb.GEMM_TF32X3),
+    (3, 256, 128, 96, False, False, 0, dtypes.float32, rb.GEMM_TF32X3),      # one tensor-core launch per matrix
+    (3, 128, 384, 64, True, True, 1, dtypes.float32, rb.GEMM_TF32),
+    (6, 20, 30, 10, False, False, 0, dtypes.float64, rb.GEMM_AUTO),
+    (70000, 2, 3, 4, False, False, 0, dtypes.float32, rb.GEMM_AUTO),          # more matrices than gridDim.z allows
+]
+
+
+@pytest.mark.parametrize("batch,m,n,k,tA,tB,share,dt,mode", BATCHED, ids=[str(c[:7]) for c in BATCHED])
+def test_gemm_strided_batched_vs_oracle(batch, m, n, k, tA, tB, share, dt, mode, cuda_service):
+    """rb200_gemm_strided_batched == the loop of PhpBlas::gemm calls LinearAlgebra::matmul issues
+    (LinearAlgebra.php:1091-1106), operand strides as there (M*K, N*K, M*N) or 0 for a shared operand."""
+    rng = np.random.default_rng(batch * 7 + m)
+    npdt = NP[dt]
+    sA = 0 if share == 1 else m * k
+    sB = 0 if share == 2 else n * k
+    a = rng.uniform(-1, 1, (1 if share == 1 else batch) * m * k + 5).astype(npdt)
+    b = rng.uniform(-1, 1, (1 if share == 2 else batch) * n * k + 3).astype(npdt)
+    c0 = rng.uniform(-1, 1, batch * m * n + 2).astype(npdt)
+    ldA, ldB = (m if tA else k), (k if tB else n)
+    A, B, C = buf(a, dt), buf(b, dt), buf(c0, dt)
+    math = cuda_service.math()
+    math.gemmStridedBatched(BLAS.RowMajor, BLAS.Trans if tA else BLAS.NoTrans, BLAS.Trans if tB else BLAS.NoTrans, m, n, k,
+                            0.5, A, 5, ldA, sA, B, 3, ldB, sB, 2.0, C, 2, n, m * n, batch, gemm_mode=mode)
+    got = C.to_numpy().astype(np.float64)
+    ref = oracle.as_buffer(c0)
+    ao, bo = oracle.as_buffer(a), oracle.as_buffer(b)
+    check = range(batch) if batch <= 64 else list(range(0, batch, 997)) + [batch - 1]
+    for i in check:
+        oracle.gemm(oracle.RowMajor, oracle.Trans if tA else oracle.NoTrans, oracle.Trans if tB else oracle.NoTrans, m, n, k,
+                    0.5, ao, 5 + i * sA, ldA, bo, 3 + i * sB, ldB, 2.0, ref, 2 + i * m * n, n)
+        sl = slice(2 + i * m * n, 2 + (i + 1) * m * n)
+        tol = 2e-3 if (mode == rb.GEMM_TF32 and m >= 128) else (1e-12 if dt == dtypes.float64 else 5e-5)
+        assert np.max(np.abs(got[sl] - ref[sl])) < tol * max(1.0, np.max(np.abs(ref[sl]))), (i, _capi_path())
+    assert got[0] == c0[0] and got[1] == c0[1]                       # before offsetC: untouched
+
+
+def _capi_path():
+    from rindow_math_matrix_b200 import _capi
+    return _capi.last_gemm_path()
+
+
+def test_matmul_uses_one_batched_launch(cuda_service, oracle_service):
+    from rindow_math_matrix_b200 import _capi
+    rng = np.random.default_rng(11)
+    la, lo = LinearAlgebra(cuda_service), LinearAlgebra(oracle_service)
+    A = rng.standard_normal((6, 8, 48, 32)).astype(np.float32)
+    B = rng.standard_normal((6, 8, 32, 40)).astype(np.float32)
+    a, b = la.array(A), la.array(B)
+    _capi.sync()
+    n0 = _capi.launch_count()
+    got = la.matmul(a, b)
+    launches = _capi.launch_count() - n0
+    assert launches <= 3, launches                                    # zero-fills of C (alloc, zeros) + ONE batched kernel, not 48
+    assert _capi.last_gemm_path() == "simt_f32_batched"
+    ref = np.asarray(lo.matmul(lo.array(A), lo.array(B)).toArray(), np.float64)
+    assert np.max(np.abs(got.to_numpy() - ref)) < 5e-6 * np.max(np.abs(ref))
+    # broadcast of the smaller batch (LinearAlgebra.php:1066-1077): B shared by the outer repeats
+    B2 = rng.standard_normal((8, 32, 40)).astype(np.float32)
+    got2 = la.matmul(a, la.array(B2))
+    ref2 = np.asarray(lo.matmul(lo.array(A), lo.array(B2)).toArray(), np.float64)
+    assert np.max(np.abs(got2.to_numpy() - ref2)) < 5e-6 * np.max(np.abs(ref2))

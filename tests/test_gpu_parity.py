@@ -531,7 +531,7 @@ def test_gemm_tall_skinny_conv_shapes(mnk, cuda_service):
                 assert err < 2e-3, (err, path)
             else:
                 if skinny:      # aligned full-width shapes may take the TMA-fed kernel instead
-                    assert path in ("tcgen05_tf32x3_skinny", "tcgen05_tf32x3", "tcgen05_tf32x3_2cta"), path
+                    assert path in ("tcgen05_tf32x3_skinny", "tcgen05_tf32x3", "tcgen05_tf32x3_2cta", "tcgen05_tf32x3_64"), path
                 assert err < 5e-5, (err, path, mnk)
     err, path = _gemm_case(cuda_service, rb.GEMM_AUTO, m, n, k, True, False, 1.0, 0.0)
     assert "skinny" not in path and "shortk" not in path and err < 5e-5

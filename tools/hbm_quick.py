@@ -69,6 +69,18 @@ def main():
     timed("reduce_sum", lambda i: math.reduceSum(m, n, 1, Rs[i], 0, Bf, 0), m * n * 4)
     timed("reduce_sum_axis0", lambda i: math.reduceSum(1, m, n, Rs[i], 0, Bf, 0), m * n * 4)
     timed("softmax", lambda i: math.softmax(m, n, Rs[i], 0, n), 2 * m * n * 4)
+    del Rs
+    # BASELINE config C4: images [64,224,224,3] -> cols [64,222,222,3,3,3] -> x W [27,64]
+    b, h, w, ch, f = 64, 224, 224, 3, 64
+    oh, ow = h - 2, w - 2
+    Im = [rnd(b * h * w * ch) for _ in range(3)]
+    Co = CudaBuffer(b * oh * ow * 27, f32, zero=False)
+    timed("im2col2d", lambda i: math.im2col2d(False, Im[i], 0, b * h * w * ch, b, h, w, ch, 3, 3, 1, 1, False, False, 1, 1,
+                                              False, Co, 0, b * oh * ow * 27), (b * h * w * ch + b * oh * ow * 27) * 4)
+    Wk, Out = rnd(27 * f), CudaBuffer(b * oh * ow * f, f32, zero=False)
+    M = b * oh * ow
+    timed("conv_gemm", lambda i: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, f, 27, 1.0, Co, 0, 27, Wk, 0, f,
+                                           0.0, Out, 0, f), (M * 27 + 27 * f + M * f) * 4)
 
 
 if __name__ == "__main__":
