@@ -192,6 +192,13 @@ int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alp
 int rb200_omatcopy(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
                    const void* A, int64_t offA, int64_t ldA, void* B, int64_t offB, int64_t ldB);
 
+/* N-dimensional transpose B = permute(A, perm): B's axis d is A's axis perm[d] (shape and perm are HOST arrays of
+ * ndim entries; A's shape is `shape`).  Replaces PhpMath::transpose (PhpMath.php:2959-3025), what
+ * LinearAlgebra::transposeND (LinearAlgebra.php:4471-4519) calls for every rank != 2 and every integer dtype.
+ * A pure copy: any dtype, bit-exact.  ndim <= 8. */
+int rb200_transpose(int dtype, int ndim, const int64_t* shape, const int64_t* perm,
+                    const void* A, int64_t offA, void* B, int64_t offB);
+
 /* ---- Math: replaces PhpMath::add / multiply (PhpMath.php:570-606 / 530-565) ---------- */
 /* trans==0: A[i,j] = alpha*X[j] + A[i,j]  (i<m, j<n, X has n elements)
  * trans!=0: A[i,j] = alpha*X[i] + A[i,j]  (X has m elements); A is m x n with row stride ldA */

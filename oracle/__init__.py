@@ -79,7 +79,8 @@ def lib() -> ctypes.CDLL:
         L.ro_imax.argtypes = [i64, p, i64, i64, i64, p]
         L.ro_imin.argtypes = [i64, p, i64, i64, i64, p]
         L.ro_onehot.argtypes = [i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
-        for name in ("ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
+        for name in ("ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -234,6 +235,15 @@ def astype(n, to_kind, mask, X, offX, incX):
         return x.astype(np.float64)
     v = np.trunc(x).astype(np.int64) if x.dtype.kind == "f" else x.astype(np.int64)
     return (v & mask) if mask else v
+
+
+# PhpMath::transpose, PhpMath.php:2959-3025: B's axis d is A's axis perm[d]
+def transpose(shape, perm, A, offA, B, offB):
+    sh = np.ascontiguousarray(shape, dtype=np.int64)
+    pm = np.ascontiguousarray(perm, dtype=np.int64)
+    if sh.size != pm.size:
+        raise OracleArgumentError("unmatch sourceshape and perm")
+    _check(lib().ro_transpose(int(sh.size), _ptr(sh), _ptr(pm), _ptr(_buf(A)), A.size, offA, _ptr(_buf(B)), B.size, offB))
 
 
 # PhpMath::reduceSum, PhpMath.php:1552-1579

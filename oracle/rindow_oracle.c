@@ -669,4 +669,41 @@ int ro_onehot(int64_t m, int64_t n, double a, const double *X, int64_t countX, i
     return RO_OK;
 }
 
+/* ---- N-D transpose: PhpMath.php:2959-3025 (strides) + transCopy :3043-3067 (the recursive copy) --------------- */
+static void ro_trans_copy(const double *A, int64_t offA, double *B, int64_t offB, int depth, int ndim,
+                          const int64_t *shape, const int64_t *strides, const int64_t *tstrides)
+{
+    const int64_t repeat = shape[depth], stride = strides[depth], tstride = tstrides[depth];
+    if (depth == ndim - 1) {                                     /* math_copy(repeat, A, offA, stride, B, offB, tstride) */
+        for (int64_t i = 0; i < repeat; i++) B[offB + i * tstride] = A[offA + i * stride];
+        return;
+    }
+    for (int64_t pos = 0; pos < repeat; pos++) {
+        ro_trans_copy(A, offA + stride * pos, B, offB + tstride * pos, depth + 1, ndim, shape, strides, tstrides);
+    }
+}
+
+int ro_transpose(int ndim, const int64_t *shape, const int64_t *perm,
+                 const double *A, int64_t countA, int64_t offA, double *B, int64_t countB, int64_t offB)
+{
+    int64_t strides[16], tstrides[16];
+    if (ndim <= 0 || ndim > 16) return RO_E_ARG;                 /* 'Matrix must not be a scalar' */
+    int64_t stride = 1, tstride = 1;
+    for (int d = 0; d < ndim; d++) tstrides[d] = -1;
+    for (int d = ndim - 1; d >= 0; d--) {                        /* :2991-3001 */
+        strides[d] = stride;
+        stride *= shape[d];
+        int64_t targ = perm[d];
+        if (targ >= ndim || targ < 0) return RO_E_ARG;           /* 'dim value in the perm is out of range.' */
+        tstrides[targ] = tstride;
+        tstride *= shape[targ];
+    }
+    if (stride != tstride) return RO_E_ARG;                      /* 'duplicate axis in perm option' */
+    for (int d = 0; d < ndim; d++) if (tstrides[d] < 0) return RO_E_ARG;
+    if (offA + stride > countA) return RO_E_ARG;
+    if (offB + tstride > countB) return RO_E_ARG;
+    ro_trans_copy(A, offA, B, offB, 0, ndim, shape, strides, tstrides);
+    return RO_OK;
+}
+
 int ro_abi_version(void) { return 1; }

@@ -238,6 +238,35 @@ class CudaMath:
             raise RuntimeException("Label number is out of bounds.")
         _capi.check(rc)
 
+    # ---- N-D transpose (PhpMath.php:2959-3025): sourceShape and perm are int32 Buffers, as in the reference ------
+    def transpose(self, sourceShape, perm, A, offsetA, B, offsetB) -> None:
+        if len(sourceShape) != len(perm):
+            raise InvalidArgumentException("unmatch sourceshape and perm")
+        _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("unmatch sourceshape and perm")          # sic (PhpMath.php:2979-2981)
+        ndim = len(sourceShape)
+        if ndim <= 0:
+            raise InvalidArgumentException("Matrix must not be a scalar")
+        shape = [int(sourceShape[i]) for i in range(ndim)]
+        pm = [int(perm[i]) for i in range(ndim)]
+        size = 1
+        for s in shape:
+            size *= s
+        for p in pm:
+            if p >= ndim:
+                raise InvalidArgumentException("dim value in the perm is out of range.")
+        if len(set(pm)) != ndim:
+            raise InvalidArgumentException("duplicate axis in perm option")
+        if offsetA + size > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA")
+        if offsetB + size > len(B):
+            raise InvalidArgumentException("Matrix specification too large for bufferB")
+        c_shape = (ctypes.c_int64 * ndim)(*shape)
+        c_perm = (ctypes.c_int64 * ndim)(*pm)
+        _capi.check(self._lib.rb200_transpose(A.dtype(), ndim, c_shape, c_perm, A.device_ptr(), offsetA,
+                                              B.device_ptr_rw(), offsetB))
+
     # ---- strided-batched gemm: the call LinearAlgebraCL::matmul makes on its math object
     #      (src/LinearAlgebraCL.php:2001-2012); row-major, same operand rules as PhpBlas::gemm --------------------
     def gemmStridedBatched(self, order, transA, transB, m, n, k, alpha, A, offsetA, ldA, strideA,

@@ -208,14 +208,18 @@ class LinearAlgebra:
                            A.buffer(), A.offset(), N, B.buffer(), B.offset(), cols)
         return B
 
-    # ---- 2-D float transpose (LinearAlgebra.php:4438-4465 -> transpose2D :4520-4565) -----------------------
+    # ---- transpose (LinearAlgebra.php:4438-4565): 2-D floats through omatcopy, everything else transposeND --------
     def transpose(self, A: NDArray, perm=None, B: NDArray | None = None) -> NDArray:
         if A.ndim() < 1:
             raise InvalidArgumentException("input array must be grator than or equal 1D.")
-        if not (A.ndim() == 2 and A.dtype() in (dtypes.float32, dtypes.float64)):
-            raise LogicException("transposeND (math->transpose) is outside the B200 path (SURVEY.md section 8f)")
-        if perm is not None and len(perm) and len(perm) != 2:
-            raise InvalidArgumentException("unmatch sourceshape and perm")
+        has_omatcopy = getattr(self.blas, "hasOmatcopy", lambda: False)()
+        if A.ndim() == 2 and A.dtype() in (dtypes.float32, dtypes.float64) and has_omatcopy:
+            if perm is not None and len(perm) and len(perm) != 2:
+                raise InvalidArgumentException("unmatch sourceshape and perm")
+            return self._transpose2D(A, B)
+        return self._transposeND(A, perm, B)
+
+    def _transpose2D(self, A: NDArray, B: NDArray | None) -> NDArray:            # LinearAlgebra.php:4520-4565
         shape = A.shape()[::-1]
         if B is None:
             B = self.alloc(shape, dtype=A.dtype())
@@ -227,6 +231,35 @@ class LinearAlgebra:
         m, n = shape[1], shape[0]
         self.blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A.buffer(), A.offset(), n,
                            B.buffer(), B.offset(), m)
+        return B
+
+    def _transposeND(self, A: NDArray, perm, B: NDArray | None) -> NDArray:      # LinearAlgebra.php:4471-4519
+        if perm is None:
+            perm = list(range(A.ndim() - 1, -1, -1))
+        if isinstance(perm, NDArray):
+            perm = [int(v) for v in np.asarray(perm.toArray()).reshape(-1)]
+        perm = [int(v) for v in perm]
+        shapeA = A.shape()
+        if len(shapeA) != len(perm):
+            raise InvalidArgumentException("unmatch sourceshape and perm")
+        shapeB, seen = [], set()
+        for axis in perm:
+            if axis in seen:
+                raise InvalidArgumentException("duplicate axis in perm option")
+            seen.add(axis)
+            if axis >= len(shapeA):
+                raise InvalidArgumentException("dim value in the perm is out of range.")
+            shapeB.append(shapeA[axis])
+        if B is None:
+            B = self.alloc(shapeB, dtype=A.dtype())
+        else:
+            if B.shape() != shapeB:
+                raise InvalidArgumentException("output shape must be transpose matrix of input.")
+            if B.dtype() != A.dtype():
+                raise InvalidArgumentException("output data type must be same with matrix of input.")
+        sourceShape = self.array(np.asarray(shapeA, np.int32), dtype=dtypes.int32).buffer()
+        permBuf = self.array(np.asarray(perm, np.int32), dtype=dtypes.int32).buffer()
+        self.math.transpose(sourceShape, permBuf, A.buffer(), A.offset(), B.buffer(), B.offset())
         return B
 
     # ---- C := alpha * AB + beta * C   (LinearAlgebra.php:925-995) -----------------------------------

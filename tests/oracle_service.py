@@ -246,6 +246,11 @@ class OracleMath:
     def updateAddOnehot(self, m, n, a, X, offX, incX, Y, offY, ldY):
         _wrap(oracle.onehot, m, n, a, self._f(X), offX, incX, Y.f64(), offY, ldY)
 
+    def transpose(self, sourceShape, perm, A, offA, B, offB):
+        a, b = self._f(A), self._f(B)
+        _wrap(oracle.transpose, sourceShape.data, perm.data, a, offA, b, offB)
+        self._back(B, b)
+
     def zeros(self, n, X, offX, incX):
         X.data[offX:offX + n * incX:incX] = 0
 

@@ -51,6 +51,13 @@ def main():
     timed("gemv", lambda i: blas.gemv(BLAS.RowMajor, BLAS.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Ym, 0, 1), m * n * 4)
     timed("gemv_trans", lambda i: blas.gemv(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, As[i], 0, n, Xm, 0, 1, 0.0, Yn, 0, 1), m * n * 4)
     timed("add", lambda i: math.add(False, m, n, 1.0, X, 0, 1, As[i], 0, n), 2 * m * n * 4)
+    sh = CudaBuffer(4, dtypes.int32).from_numpy(np.asarray([64, 12, 128, 64], np.int32))
+    pm = CudaBuffer(4, dtypes.int32).from_numpy(np.asarray([0, 2, 1, 3], np.int32))
+    nel = 64 * 12 * 128 * 64
+    timed("transpose_heads", lambda i: math.transpose(sh, pm, As[i], 0, Y2, 0), 2 * nel * 4)
+    sh3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([64, 512, 1024], np.int32))
+    pm3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([0, 2, 1], np.int32))
+    timed("transpose_b21", lambda i: math.transpose(sh3, pm3, As[i], 0, Y2, 0), 2 * m * n * 4)
     timed("maximum", lambda i: math.maximum(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
     timed("greater", lambda i: math.greater(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
     timed("duplicate", lambda i: math.duplicate(False, m, n, X, 0, 1, As[i], 0, n), m * n * 4)
