@@ -199,6 +199,19 @@ int rb200_omatcopy(int dtype, int order, int trans, int64_t m, int64_t n, double
 int rb200_transpose(int dtype, int ndim, const int64_t* shape, const int64_t* perm,
                     const void* A, int64_t offA, void* B, int64_t offB);
 
+/* gather / scatter / scatterAdd along the first axis: replaces PhpMath::gather (PhpMath.php:1063-1130) incl. its
+ * reverse+add form scatterAdd2 (:1362-1395).  X holds n indices (index_dtype: any real dtype; index >= numClass is
+ * clamped to numClass-1 like the reference, a negative one to 0), A is [numClass, k], B is [n, k]:
+ *   reverse=0 add=0: B[j,:] = A[X[j],:]      reverse=0 add=1: B[j,:] += A[X[j],:]
+ *   reverse=1 add=0: A[X[j],:] = B[j,:] (duplicates: the last j wins, as in the sequential loop)
+ *   reverse=1 add=1: A[X[j],:] += B[j,:] in ascending j (deterministic).
+ * rb200_reduce_gather: B[i,j] = A[i, X[i,j], j] with A [m, numClass, n], X and B [m, n] (PhpMath::reduceGather
+ * :1135-1208) and the same reverse / add forms.  dtype float32/float64/int32/int64/uint8/bool. */
+int rb200_gather(int dtype, int index_dtype, int reverse, int add_mode, int64_t n, int64_t k, int64_t numClass,
+                 const void* X, int64_t offX, void* A, int64_t offA, void* B, int64_t offB);
+int rb200_reduce_gather(int dtype, int index_dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t numClass,
+                        const void* X, int64_t offX, void* A, int64_t offA, void* B, int64_t offB);
+
 /* ---- Math: replaces PhpMath::add / multiply (PhpMath.php:570-606 / 530-565) ---------- */
 /* trans==0: A[i,j] = alpha*X[j] + A[i,j]  (i<m, j<n, X has n elements)
  * trans!=0: A[i,j] = alpha*X[i] + A[i,j]  (X has m elements); A is m x n with row stride ldA */

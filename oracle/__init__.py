@@ -80,7 +80,9 @@ def lib() -> ctypes.CDLL:
         L.ro_imin.argtypes = [i64, p, i64, i64, i64, p]
         L.ro_onehot.argtypes = [i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
-        for name in ("ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
+        L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
+        for name in ("ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -235,6 +237,17 @@ def astype(n, to_kind, mask, X, offX, incX):
         return x.astype(np.float64)
     v = np.trunc(x).astype(np.int64) if x.dtype.kind == "f" else x.astype(np.int64)
     return (v & mask) if mask else v
+
+
+# PhpMath::gather :1063 (incl. scatterAdd2 :1362) and reduceGather :1135; X is the float64 widening of the indices
+def gather(reverse, add_mode, n, k, numClass, X, offX, A, offA, B, offB):
+    _check(lib().ro_gather(int(bool(reverse)), int(bool(add_mode)), n, k, numClass, _ptr(_buf(X)), X.size, offX,
+                           _ptr(_buf(A)), A.size, offA, _ptr(_buf(B)), B.size, offB))
+
+
+def reduce_gather(reverse, add_mode, m, n, numClass, X, offX, A, offA, B, offB):
+    _check(lib().ro_reduce_gather(int(bool(reverse)), int(bool(add_mode)), m, n, numClass, _ptr(_buf(X)), X.size, offX,
+                                  _ptr(_buf(A)), A.size, offA, _ptr(_buf(B)), B.size, offB))
 
 
 # PhpMath::transpose, PhpMath.php:2959-3025: B's axis d is A's axis perm[d]

@@ -706,4 +706,59 @@ int ro_transpose(int ndim, const int64_t *shape, const int64_t *perm,
     return RO_OK;
 }
 
+/* ---- gather / scatterAdd2 / reduceGather: PhpMath.php:1063-1130, :1362-1395, :1135-1208.  X holds PHP numbers
+ *      (doubles here); the index >= numClass clamp is the reference's (:1107-1111). ------------------------------ */
+int ro_gather(int reverse, int add_mode, int64_t n, int64_t k, int64_t numClass,
+              const double *X, int64_t countX, int64_t offX, double *A, int64_t countA, int64_t offA,
+              double *B, int64_t countB, int64_t offB)
+{
+    if (offX + n > countX) return RO_E_ARG;
+    if (offA + numClass * k > countA) return RO_E_ARG;
+    if (offB + n * k > countB) return RO_E_ARG;
+    if (reverse && add_mode) {                                   /* scatterAdd2: column by column, j ascending */
+        for (int64_t i = 0; i < k; i++) {
+            for (int64_t j = 0; j < n; j++) {
+                int64_t index = (int64_t)X[offX + j];
+                if (index >= numClass) index = numClass - 1;
+                A[offA + index * k + i] = A[offA + index * k + i] + B[offB + j * k + i];
+            }
+        }
+        return RO_OK;
+    }
+    if (numClass <= 0) return RO_E_ARG;
+    for (int64_t j = 0; j < n; j++) {
+        int64_t index = (int64_t)X[offX + j];
+        if (index >= numClass) index = numClass - 1;
+        double *a = A + offA + index * k, *b = B + offB + j * k;
+        for (int64_t t = 0; t < k; t++) {
+            if (reverse) { if (add_mode) a[t] = a[t] + b[t]; else a[t] = b[t]; }          /* math_add / math_copy */
+            else         { if (add_mode) b[t] = b[t] + a[t]; else b[t] = a[t]; }
+        }
+    }
+    return RO_OK;
+}
+
+int ro_reduce_gather(int reverse, int add_mode, int64_t m, int64_t n, int64_t numClass,
+                     const double *X, int64_t countX, int64_t offX, double *A, int64_t countA, int64_t offA,
+                     double *B, int64_t countB, int64_t offB)
+{
+    if (offX + n > countX) return RO_E_ARG;                      /* :1164 (sic: n, not m*n) */
+    if (offX + m * n > countX) return RO_E_ARG;                  /* what the loop actually touches */
+    if (offA + m * numClass > countA) return RO_E_ARG;           /* :1166 */
+    if (offA + m * numClass * n > countA) return RO_E_ARG;
+    if (offB + m * n > countB) return RO_E_ARG;
+    if (numClass <= 0) return RO_E_ARG;
+    int64_t idxX = offX, idxA = offA, idxB = offB;
+    for (int64_t i = 0; i < m; i++, idxX += n, idxA += n * numClass, idxB += n) {
+        for (int64_t j = 0; j < n; j++) {
+            int64_t index = (int64_t)X[idxX + j];
+            if (index >= numClass) index = numClass - 1;
+            int64_t iA = idxA + j + index * n, iB = idxB + j;
+            if (reverse) { if (add_mode) A[iA] = A[iA] + B[iB]; else A[iA] = B[iB]; }
+            else         { if (add_mode) B[iB] = B[iB] + A[iA]; else B[iB] = A[iA]; }
+        }
+    }
+    return RO_OK;
+}
+
 int ro_abi_version(void) { return 1; }

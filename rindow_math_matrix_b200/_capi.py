@@ -65,6 +65,8 @@ SIGNATURES = {
     "rb200_gemv": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
     "rb200_omatcopy": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_transpose": (i32, [i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), vp, i64, vp, i64]),
+    "rb200_gather": (i32, [i32, i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64]),
+    "rb200_reduce_gather": (i32, [i32, i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64]),
     "rb200_add": (i32, [i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_multiply": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),
     "rb200_broadcast": (i32, [i32, i32, i32, i64, i64, vp, i64, i64, vp, i64, i64]),

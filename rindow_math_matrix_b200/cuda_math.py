@@ -238,6 +238,41 @@ class CudaMath:
             raise RuntimeException("Label number is out of bounds.")
         _capi.check(rc)
 
+    # ---- gather / scatter / scatterAdd (PhpMath.php:1063-1130, 1362-1395) and reduceGather (:1135-1208) ----------
+    def gather(self, reverse, addMode, n, k, numClass, X, offsetX, A, offsetA, B, offsetB) -> None:
+        if offsetX + n > len(X):
+            raise InvalidArgumentException("Matrix X specification too large for buffer.")
+        if offsetA + numClass * k > len(A):
+            raise InvalidArgumentException("Matrix A specification too large for buffer.")
+        if offsetB + n * k > len(B):
+            raise InvalidArgumentException("Matrix B specification too large for buffer.")
+        if numClass <= 0:
+            raise InvalidArgumentException("numClass must be grator than zero.")
+        _cuda("X", X), _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        a_ptr = A.device_ptr_rw() if reverse else A.device_ptr()
+        b_ptr = B.device_ptr() if reverse else B.device_ptr_rw()
+        _capi.check(self._lib.rb200_gather(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, n, k, numClass,
+                                           X.device_ptr(), offsetX, a_ptr, offsetA, b_ptr, offsetB))
+
+    def reduceGather(self, reverse, addMode, m, n, numClass, X, offsetX, A, offsetA, B, offsetB) -> None:
+        if offsetX + m * n > len(X):          # the reference tests offsetX+n (:1164); the whole [m,n] index must fit
+            raise InvalidArgumentException("Matrix X specification too large for buffer.")
+        if offsetA + m * numClass * n > len(A):
+            raise InvalidArgumentException("Matrix A specification too large for buffer.")
+        if offsetB + m * n > len(B):
+            raise InvalidArgumentException("Matrix B specification too large for buffer.")
+        if numClass <= 0:
+            raise InvalidArgumentException("numClass must be grator than zero.")
+        _cuda("X", X), _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        a_ptr = A.device_ptr_rw() if reverse else A.device_ptr()
+        b_ptr = B.device_ptr() if reverse else B.device_ptr_rw()
+        _capi.check(self._lib.rb200_reduce_gather(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, m, n,
+                                                  numClass, X.device_ptr(), offsetX, a_ptr, offsetA, b_ptr, offsetB))
+
     # ---- N-D transpose (PhpMath.php:2959-3025): sourceShape and perm are int32 Buffers, as in the reference ------
     def transpose(self, sourceShape, perm, A, offsetA, B, offsetB) -> None:
         if len(sourceShape) != len(perm):

@@ -529,6 +529,97 @@ class LinearAlgebra:
         self.math.astype(X.size(), dtype, X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
         return Y
 
+    # ---- gather / scatterAdd / scatter (LinearAlgebra.php:2441-2690) -------------------------------------------
+    @staticmethod
+    def _printable_shapes(values) -> str:                                        # LinearAlgebra.php:95-115
+        parts = []
+        for v in values:
+            shape = v.shape() if isinstance(v, NDArray) else list(v)
+            parts.append("(" + ",".join(map(str, shape)) + ")")
+        return ",".join(parts)
+
+    def _do_gather(self, scatterAdd: bool, A: NDArray, X: NDArray, axis=None, output: NDArray | None = None,
+                   dtype=None) -> NDArray:
+        if axis is None:
+            postfix, prefix = A.shape(), X.shape()
+            numClass = postfix.pop(0)
+            m, n = 1, int(np.prod(prefix, dtype=np.int64)) if prefix else 1
+            k = int(np.prod(postfix, dtype=np.int64)) if postfix else 1
+            reduction = False
+            outputShape = prefix + postfix
+        else:
+            ndim = A.ndim()
+            if axis < 0:
+                axis = ndim + axis
+            postfix = A.shape()
+            prefix = [postfix.pop(0) for _ in range(axis)]
+            m = int(np.prod(prefix, dtype=np.int64)) if prefix else 1
+            numClass = postfix.pop(0)
+            n = int(np.prod(postfix, dtype=np.int64)) if postfix else 1
+            k = 1
+            reduction = True
+            outputShape = prefix + postfix
+            if X.shape() != outputShape:
+                raise InvalidArgumentException("Unmatch Shape:" + self._printable_shapes([A, X]))
+        if dtype is None:
+            dtype = A.dtype()
+        if output is None:
+            output = self.zeros(self.alloc(outputShape, dtype=dtype))
+        elif output.shape() != outputShape:
+            raise InvalidArgumentException("Unmatch output shape of dimension: " + self._printable_shapes([outputShape, output]))
+        reverse = addMode = bool(scatterAdd)
+        if reduction:
+            self.math.reduceGather(reverse, addMode, m, n, numClass, X.buffer(), X.offset(), A.buffer(), A.offset(),
+                                   output.buffer(), output.offset())
+        else:
+            self.math.gather(reverse, addMode, n, k, numClass, X.buffer(), X.offset(), A.buffer(), A.offset(),
+                             output.buffer(), output.offset())
+        return output
+
+    def gather(self, A: NDArray, X: NDArray, axis=None, output: NDArray | None = None, dtype=None) -> NDArray:
+        return self._do_gather(False, A, X, axis, output, dtype)
+
+    def scatterAdd(self, X: NDArray, A: NDArray, output: NDArray, axis=None, dtype=None) -> NDArray:
+        self._do_gather(True, output, X, axis, A, dtype)
+        return output
+
+    def scatter(self, X: NDArray, A: NDArray, numClass: int, axis=None, output: NDArray | None = None, dtype=None) -> NDArray:
+        if axis is None:
+            postfix, prefix = A.shape(), X.shape()
+            tmp = [postfix.pop(0) for _ in range(X.ndim())]
+            if tmp != prefix:
+                raise InvalidArgumentException("Unmatch Shape:" + self._printable_shapes([X, A]))
+            n = int(np.prod(prefix, dtype=np.int64)) if prefix else 1
+            k = int(np.prod(postfix, dtype=np.int64)) if postfix else 1
+            m, expand = 1, False
+            outputShape = [numClass] + postfix
+        else:
+            ndim = A.ndim()
+            if axis < 0:
+                axis = ndim + axis
+            postfix = A.shape()
+            if postfix != X.shape():
+                raise InvalidArgumentException("Unmatch Shape X and A:" + self._printable_shapes([X, A]))
+            prefix = [postfix.pop(0) for _ in range(axis)]
+            m = int(np.prod(prefix, dtype=np.int64)) if prefix else 1
+            n = int(np.prod(postfix, dtype=np.int64)) if postfix else 1
+            k, expand = 1, True
+            outputShape = prefix + [numClass] + postfix
+        if dtype is None:
+            dtype = A.dtype()
+        if output is None:
+            output = self.zeros(self.alloc(outputShape, dtype=dtype))
+        elif output.shape() != outputShape:
+            raise InvalidArgumentException("Unmatch shape of dimension: (%s),(%s)" % (
+                ",".join(map(str, A.shape())), ",".join(map(str, output.shape()))))
+        if expand:
+            self.math.reduceGather(True, False, m, n, numClass, X.buffer(), X.offset(), output.buffer(), output.offset(),
+                                   A.buffer(), A.offset())
+        else:
+            self.math.gather(True, False, n, k, numClass, X.buffer(), X.offset(), output.buffer(), output.offset(),
+                             A.buffer(), A.offset())
+        return output
+
     # ---- onehot (LinearAlgebra.php:3095-3133) ----------------------------------------------------------------
     def onehot(self, X: NDArray, numClass: int, alpha=None, output: NDArray | None = None) -> NDArray:
         if X.ndim() != 1:

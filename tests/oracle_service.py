@@ -246,6 +246,18 @@ class OracleMath:
     def updateAddOnehot(self, m, n, a, X, offX, incX, Y, offY, ldY):
         _wrap(oracle.onehot, m, n, a, self._f(X), offX, incX, Y.f64(), offY, ldY)
 
+    def gather(self, reverse, addMode, n, k, numClass, X, offX, A, offA, B, offB):
+        a, b = self._f(A), self._f(B)
+        _wrap(oracle.gather, reverse, addMode, n, k, numClass, self._f(X), offX, a, offA, b, offB)
+        self._back(A, a)
+        self._back(B, b)
+
+    def reduceGather(self, reverse, addMode, m, n, numClass, X, offX, A, offA, B, offB):
+        a, b = self._f(A), self._f(B)
+        _wrap(oracle.reduce_gather, reverse, addMode, m, n, numClass, self._f(X), offX, a, offA, b, offB)
+        self._back(A, a)
+        self._back(B, b)
+
     def transpose(self, sourceShape, perm, A, offA, B, offB):
         a, b = self._f(A), self._f(B)
         _wrap(oracle.transpose, sourceShape.data, perm.data, a, offA, b, offB)

@@ -58,6 +58,10 @@ def main():
     sh3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([64, 512, 1024], np.int32))
     pm3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([0, 2, 1], np.int32))
     timed("transpose_b21", lambda i: math.transpose(sh3, pm3, As[i], 0, Y2, 0), 2 * m * n * 4)
+    vocab, dim, ntok = 32768, 1024, 32768                       # table 128 MiB; one step moves 2 x 128 MiB
+    ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
+    timed("gather", lambda i: math.gather(False, False, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 2 * ntok * dim * 4)
+    timed("scatter_add", lambda i: math.gather(True, True, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 3 * ntok * dim * 4)
     timed("maximum", lambda i: math.maximum(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
     timed("greater", lambda i: math.greater(m, n, As[i], 0, n, X, 0, 1), 2 * m * n * 4)
     timed("duplicate", lambda i: math.duplicate(False, m, n, X, 0, 1, As[i], 0, n), m * n * 4)
