@@ -559,6 +559,26 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
     Xt = CudaBuffer(m, dtypes.float32, zero=False).from_numpy(rng.uniform(-1, 1, m).astype(np.float32))
     report("gemv_trans", lambda i: blas1.gemv(_B.RowMajor, _B.Trans, m, n, 1.0, As[i], 0, n, Xt, 0, 1, 0.0, Yt, 0, 1),
            m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096]^T x [8192]"})
+    # section 8(f) ranks 2 and 4 on the same operands: broadcast / unary families, astype, N-D transpose, gather
+    report("maximum", lambda i: math.maximum(m, n, As[i], 0, n, X, 0, 1), ew_bytes, {"shape": "max([8192,4096], [4096])"})
+    report("greater", lambda i: math.greater(m, n, As[i], 0, n, X, 0, 1), ew_bytes, {"shape": "[8192,4096] > [4096]"})
+    report("exp", lambda i: math.exp(m * n, As[i], 0, 1), 2 * m * n * 4, {"shape": "n=33554432 in place"})
+    report("increment", lambda i: math.increment(m * n, 1.0001, As[i], 0, 1, 0.001), 2 * m * n * 4,
+           {"shape": "n=33554432 in place"})
+    I32 = CudaBuffer(m * n, dtypes.int32, zero=False)
+    report("astype_f32_i32", lambda i: math.astype(m * n, dtypes.int32, As[i], 0, 1, I32, 0, 1), 2 * m * n * 4,
+           {"shape": "n=33554432 float32 -> int32"})
+    del I32
+    sh3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([64, 512, 1024], np.int32))
+    pm3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([0, 2, 1], np.int32))
+    report("transpose_nd", lambda i: math.transpose(sh3, pm3, As[i], 0, Y2, 0), 2 * m * n * 4,
+           {"shape": "[64,512,1024] -> [64,1024,512] (perm 0,2,1)"})
+    vocab, dim, ntok = 32768, 1024, 32768
+    ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
+    report("gather", lambda i: math.gather(False, False, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 2 * ntok * dim * 4,
+           {"shape": "table [32768,1024], 32768 row indices (embedding lookup)"})
+    report("scatter_add", lambda i: math.gather(True, True, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 3 * ntok * dim * 4,
+           {"shape": "table [32768,1024] += 32768 rows (embedding gradient; sort + in-order sums, 4 launches)"})
     del As, Y2
     # C3: reductions / softmax on f32 [65536,1024] axis=1
     m, n = 65536, 1024

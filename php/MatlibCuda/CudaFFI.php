@@ -59,6 +59,24 @@ class CudaFFI
                       const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
         int rb200_multiply(int dtype, int trans, int64_t m, int64_t n,
                            const void* X, int64_t offX, int64_t incX, void* A, int64_t offA, int64_t ldA);
+        int rb200_gemm_strided_batched(int dtype, int transA, int transB, int64_t m, int64_t n, int64_t k, double alpha,
+                            const void* A, int64_t offA, int64_t ldA, int64_t strideA,
+                            const void* B, int64_t offB, int64_t ldB, int64_t strideB, double beta,
+                            void* C, int64_t offC, int64_t ldC, int64_t strideC, int64_t batch, int mode);
+        int rb200_ipc_export(void* dptr, void* handle64);
+        int rb200_ipc_open(const void* handle64, void** dptr);
+        int rb200_ipc_close(void* dptr);
+        int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                            float alpha, const float* A, int64_t offA, int64_t ldA,
+                            const float* B, int64_t offB, int64_t ldB,
+                            float beta, float* C, int64_t offC, int64_t ldC, int mode,
+                            int n_peers, void* const* peer_C);
+        int rb200_transpose(int dtype, int ndim, const int64_t* shape, const int64_t* perm,
+                            const void* A, int64_t offA, void* B, int64_t offB);
+        int rb200_gather(int dtype, int index_dtype, int reverse, int add_mode, int64_t n, int64_t k, int64_t numClass,
+                         const void* X, int64_t offX, void* A, int64_t offA, void* B, int64_t offB);
+        int rb200_reduce_gather(int dtype, int index_dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t numClass,
+                         const void* X, int64_t offX, void* A, int64_t offA, void* B, int64_t offB);
         int rb200_broadcast(int dtype, int op, int trans, int64_t m, int64_t n,
                             void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX);
         int rb200_unary(int dtype, int op, int64_t n, double alpha, void* X, int64_t offX, int64_t incX, double beta);

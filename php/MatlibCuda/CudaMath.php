@@ -284,4 +284,68 @@ class CudaMath extends PhpMath
         if ($rc == -6) throw new \RuntimeException('Label number is out of bounds.');   // RB200_E_RANGE
         CudaFFI::check($rc);
     }
+    // ---- gather / scatter / scatterAdd / reduceGather (PhpMath.php:1063-1208, 1362-1395) ------------------------
+    public function gather(bool $reverse,bool $addMode,int $n,int $k,int $numClass,
+        Buffer $X,int $offsetX,Buffer $A,int $offsetA,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($X,$A,$B) || $A->dtype()!=$B->dtype()) {
+            parent::gather($reverse,$addMode,$n,$k,$numClass,$X,$offsetX,$A,$offsetA,$B,$offsetB); return;
+        }
+        if ($offsetX+$n>count($X)) throw new InvalidArgumentException('Matrix X specification too large for buffer.');
+        if ($offsetA+$numClass*$k>count($A)) throw new InvalidArgumentException('Matrix A specification too large for buffer.');
+        if ($offsetB+$n*$k>count($B)) throw new InvalidArgumentException('Matrix B specification too large for buffer.');
+        if ($numClass<=0) throw new InvalidArgumentException('numClass must be grator than zero.');
+        CudaFFI::check(CudaFFI::lib()->rb200_gather($A->abiDtype(),$X->abiDtype(),$reverse?1:0,$addMode?1:0,$n,$k,$numClass,
+            $X->devicePtr(),$offsetX,$reverse?$A->devicePtrRW():$A->devicePtr(),$offsetA,
+            $reverse?$B->devicePtr():$B->devicePtrRW(),$offsetB));
+    }
+
+    public function reduceGather(bool $reverse,bool $addMode,int $m,int $n,int $numClass,
+        Buffer $X,int $offsetX,Buffer $A,int $offsetA,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($X,$A,$B) || $A->dtype()!=$B->dtype()) {
+            parent::reduceGather($reverse,$addMode,$m,$n,$numClass,$X,$offsetX,$A,$offsetA,$B,$offsetB); return;
+        }
+        if ($offsetX+$m*$n>count($X)) throw new InvalidArgumentException('Matrix X specification too large for buffer.');
+        if ($offsetA+$m*$numClass*$n>count($A)) throw new InvalidArgumentException('Matrix A specification too large for buffer.');
+        if ($offsetB+$m*$n>count($B)) throw new InvalidArgumentException('Matrix B specification too large for buffer.');
+        if ($numClass<=0) throw new InvalidArgumentException('numClass must be grator than zero.');
+        CudaFFI::check(CudaFFI::lib()->rb200_reduce_gather($A->abiDtype(),$X->abiDtype(),$reverse?1:0,$addMode?1:0,$m,$n,$numClass,
+            $X->devicePtr(),$offsetX,$reverse?$A->devicePtrRW():$A->devicePtr(),$offsetA,
+            $reverse?$B->devicePtr():$B->devicePtrRW(),$offsetB));
+    }
+
+    // ---- N-D transpose (PhpMath.php:2959-3025): shape and perm are small int32 buffers, read on the host -----------
+    public function transpose(Buffer $sourceShape,Buffer $perm,Buffer $A,int $offsetA,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($A,$B)) { parent::transpose($sourceShape,$perm,$A,$offsetA,$B,$offsetB); return; }
+        $ndim = count($sourceShape);
+        if ($ndim!=count($perm)) throw new InvalidArgumentException('unmatch sourceshape and perm');
+        if ($A->dtype()!=$B->dtype()) throw new InvalidArgumentException('unmatch sourceshape and perm');
+        if ($ndim<=0) throw new InvalidArgumentException('Matrix must not be a scalar');
+        $ffi = CudaFFI::lib();
+        $shape = $ffi->new("int64_t[$ndim]"); $pm = $ffi->new("int64_t[$ndim]");
+        $size = 1; $seen = [];
+        for ($i=0;$i<$ndim;$i++) {
+            $shape[$i] = $sourceShape[$i]; $pm[$i] = $perm[$i]; $size *= $sourceShape[$i];
+            if ($perm[$i]>=$ndim) throw new InvalidArgumentException('dim value in the perm is out of range.');
+            if (isset($seen[$perm[$i]])) throw new InvalidArgumentException('duplicate axis in perm option');
+            $seen[$perm[$i]] = true;
+        }
+        if ($offsetA+$size>count($A)) throw new InvalidArgumentException('Matrix specification too large for bufferA');
+        if ($offsetB+$size>count($B)) throw new InvalidArgumentException('Matrix specification too large for bufferB');
+        CudaFFI::check($ffi->rb200_transpose($A->abiDtype(),$ndim,$shape,$pm,$A->devicePtr(),$offsetA,$B->devicePtrRW(),$offsetB));
+    }
+
+    // ---- strided-batched gemm: the entry LinearAlgebraCL::matmul calls on its math object (LinearAlgebraCL.php:2001);
+    //      a LinearAlgebraCuda::matmul override issues it once per broadcast repeat instead of looping gemm ----------
+    public function gemmStridedBatched(int $order,int $transA,int $transB,int $m,int $n,int $k,float $alpha,
+        Buffer $A,int $offsetA,int $ldA,int $strideA,Buffer $B,int $offsetB,int $ldB,int $strideB,float $beta,
+        Buffer $C,int $offsetC,int $ldC,int $strideC,int $batchSize) : void
+    {
+        if (!$this->onDevice($A,$B,$C)) throw new InvalidArgumentException('gemmStridedBatched needs device buffers');
+        CudaFFI::check(CudaFFI::lib()->rb200_gemm_strided_batched($A->abiDtype(),$transA,$transB,$m,$n,$k,$alpha,
+            $A->devicePtr(),$offsetA,$ldA,$strideA,$B->devicePtr(),$offsetB,$ldB,$strideB,$beta,
+            $C->devicePtrRW(),$offsetC,$ldC,$strideC,$batchSize,0));
+    }
 }

@@ -29,6 +29,12 @@ bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int6
                            const float* B, int64_t ldB, const float* C, int64_t ldC);
 int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
                  const float* A, int64_t ldA, const float* B, int64_t ldB, float beta, float* C, int64_t ldC);
+bool gemm_tcgen05_batched_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA, int64_t strideA,
+                                   const float* B, int64_t ldB, int64_t strideB, const float* C, int64_t ldC,
+                                   int64_t strideC, int64_t batch);
+int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
+                         const float* A, int64_t ldA, int64_t strideA, const float* B, int64_t ldB, int64_t strideB,
+                         float beta, float* C, int64_t ldC, int64_t strideC, int64_t batch);
 }  // namespace rb200
 
 namespace {
@@ -131,13 +137,26 @@ int rb200_gemm_strided_batched(int dtype, int transA, int transB, int64_t m, int
     const float* a = reinterpret_cast<const float*>(A) + offA;
     const float* b = reinterpret_cast<const float*>(B) + offB;
     float* cc = reinterpret_cast<float*>(C) + offC;
-    const bool tensor = mode != RB200_GEMM_FP32_SIMT && m >= 128 && n >= 128 && k >= 32 &&
-                        strideA % 4 == 0 && strideB % 4 == 0 && strideC % 4 == 0 &&
-                        rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC);
-    if (tensor) {
+    // big matrices: one launch each already fills the machine with the CTA-pair kernel
+    const bool big = mode != RB200_GEMM_FP32_SIMT && m >= 1024 && n >= 1024 && k >= 32 &&
+                     (double)m * (double)n * (double)k >= 2048.0 * 2048.0 * 2048.0 &&
+                     strideA % 4 == 0 && strideB % 4 == 0 && strideC % 4 == 0 &&
+                     rb200::gemm_tcgen05_eligible(m, n, k, a, ldA, b, ldB, cc, ldC);
+    if (big) {
         for (int64_t i = 0; i < batch; i++) {
             rc = rb200::gemm_tcgen05(mode, tA, tB, m, n, k, (float)alpha, a + i * strideA, ldA, b + i * strideB, ldB,
                                      (float)beta, cc + i * strideC, ldC);
+            if (rc != RB200_OK) return rc;
+        }
+        return RB200_OK;
+    }
+    // tensor-core sized matrices: ONE persistent launch, the batch as a tile-index digit (chunks of 32768 matrices)
+    if (mode != RB200_GEMM_FP32_SIMT &&
+        rb200::gemm_tcgen05_batched_eligible(m, n, k, a, ldA, strideA, b, ldB, strideB, cc, ldC, strideC, batch < 32768 ? batch : 32768)) {
+        for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+            const int64_t nb = (batch - b0) < 32768 ? (batch - b0) : 32768;
+            rc = rb200::gemm_tcgen05_batched(mode, tA, tB, m, n, k, (float)alpha, a + b0 * strideA, ldA, strideA,
+                                             b + b0 * strideB, ldB, strideB, (float)beta, cc + b0 * strideC, ldC, strideC, nb);
             if (rc != RB200_OK) return rc;
         }
         return RB200_OK;

@@ -160,6 +160,10 @@ struct TcParams {
     // epilogue also stores every finished value to -- NVLink peer stores overlapping the remaining tiles
     int n_peers;
     float* peers[RB200_MAX_PEERS];
+    // strided batch (1-CTA kernels): tile index = (matrix, row block, column block); the third tensor-map coordinate
+    // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
+    int batch, a_bmul, b_bmul;
+    int64_t strideC;
 };
 
 template <int BN, int PLANES, int STAGES>
@@ -168,7 +172,9 @@ struct TcSmem {
     static constexpr int B_PLANE = BN * TC_BK * 4;            // 16 / 32 KB
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int BARRIER_OFF = STAGES * STAGE;
-    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;    // + barriers + alignment slack
+    static constexpr int STG_LD = 36;                         // floats per staged epilogue row (32 + 4: conflict-free float4 rows)
+    static constexpr int STG_OFF = BARRIER_OFF + 256;         // 4 epilogue warps x [32][STG_LD] floats
+    static constexpr int TOTAL = STG_OFF + 4 * 32 * STG_LD * 4 + 1024;   // + alignment slack
 };
 
 // grouped tile order: TC_GROUP_M row-blocks share each column-block before moving on
@@ -227,7 +233,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::BARRIER_OFF + 8 * (2 * STAGES + 4));
 
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int tiles_per = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = tiles_per * p.batch;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -235,8 +242,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int mb, nb;
-                tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
+                const int bt = tile / tiles_per;
+                tile_coords(tile - bt * tiles_per, p.num_m_blocks, p.num_n_blocks, mb, nb);
                 const int m0 = mb * TC_BM, n0 = nb * BN;
+                const int a3 = bt * p.a_bmul * PLANES, b3 = bt * p.b_bmul * PLANES;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), (uint32_t)L::STAGE);
@@ -246,18 +255,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 #pragma unroll
                     for (int pl = 0; pl < PLANES; pl++) {
                         if (!A_MN) {
-                            tma_load_3d(sA + pl * L::A_PLANE, &tmapA, full_bar(stage), k0, m0, pl);
+                            tma_load_3d(sA + pl * L::A_PLANE, &tmapA, full_bar(stage), k0, m0, a3 + pl);
                         } else {
 #pragma unroll
                             for (int j = 0; j < TC_BM / 32; j++)
-                                tma_load_3d(sA + pl * L::A_PLANE + j * 4096, &tmapA, full_bar(stage), m0 + 32 * j, k0, pl);
+                                tma_load_3d(sA + pl * L::A_PLANE + j * 4096, &tmapA, full_bar(stage), m0 + 32 * j, k0, a3 + pl);
                         }
                         if (!B_MN) {
-                            tma_load_3d(sB + pl * L::B_PLANE, &tmapB, full_bar(stage), k0, n0, pl);
+                            tma_load_3d(sB + pl * L::B_PLANE, &tmapB, full_bar(stage), k0, n0, b3 + pl);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / 32; j++)
-                                tma_load_3d(sB + pl * L::B_PLANE + j * 4096, &tmapB, full_bar(stage), n0 + 32 * j, k0, pl);
+                                tma_load_3d(sB + pl * L::B_PLANE + j * 4096, &tmapB, full_bar(stage), n0 + 32 * j, k0, b3 + pl);
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -314,13 +323,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int mb, nb;
-            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb);
-            const int64_t row = (int64_t)mb * TC_BM + q * 32 + lane;
+            const int bt = tile / tiles_per;
+            tile_coords(tile - bt * tiles_per, p.num_m_blocks, p.num_n_blocks, mb, nb);
             const int64_t col0 = (int64_t)nb * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            float* crow = p.C + row * p.ldC;
-            const bool row_ok = row < p.M;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ch++) {
                 uint32_t r[32];
@@ -336,30 +343,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     tc_wait_ld();
                 }
                 const int64_t c0 = col0 + ch * 32;
-                if (row_ok && c0 < p.N) {
-                    if (c0 + 32 <= p.N) {
+                if (c0 < p.N) {                                   // warp-uniform
+                    // lane = row holds 32 consecutive columns: transpose the warp's 32 x 32 block through a padded
+                    // shared-memory tile so that every global access covers whole 128-byte row segments (4 rows x
+                    // 128 bytes per instruction instead of 32 rows x 16 bytes) -- output-heavy short-K products
+                    // (attention scores, conv) are bound by exactly these stores
+                    float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + (warp - 4) * (32 * L::STG_LD);
+                    __syncwarp();
 #pragma unroll
-                        for (int v = 0; v < 8; v++) {
-                            float4 o;
-                            o.x = p.alpha * __uint_as_float(r[4 * v + 0]);
-                            o.y = p.alpha * __uint_as_float(r[4 * v + 1]);
-                            o.z = p.alpha * __uint_as_float(r[4 * v + 2]);
-                            o.w = p.alpha * __uint_as_float(r[4 * v + 3]);
-                            float4* dst = reinterpret_cast<float4*>(crow + c0) + v;
-                            if (p.beta != 0.f) {
-                                const float4 old = *dst;
-                                o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
-                                o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
-                            }
-                            *dst = o;
-                        }
-                    } else {
+                    for (int v = 0; v < 8; v++) {
+                        *reinterpret_cast<float4*>(stg + lane * L::STG_LD + 4 * v) =
+                            make_float4(p.alpha * __uint_as_float(r[4 * v + 0]), p.alpha * __uint_as_float(r[4 * v + 1]),
+                                        p.alpha * __uint_as_float(r[4 * v + 2]), p.alpha * __uint_as_float(r[4 * v + 3]));
+                    }
+                    __syncwarp();
+                    const int64_t row_base = (int64_t)mb * TC_BM + q * 32;
+                    const int cc = (lane & 7) * 4;
+                    float* cmat = p.C + (int64_t)bt * p.strideC;
 #pragma unroll
-                        for (int e = 0; e < 32; e++) {
-                            if (c0 + e < p.N) {
-                                float o = p.alpha * __uint_as_float(r[e]);
-                                if (p.beta != 0.f) o = fmaf(p.beta, crow[c0 + e], o);
-                                crow[c0 + e] = o;
+                    for (int pass = 0; pass < 8; pass++) {
+                        const int rr = pass * 4 + (lane >> 3);
+                        const int64_t grow = row_base + rr;
+                        if (grow < p.M && c0 + cc < p.N) {
+                            float4 o = *reinterpret_cast<const float4*>(stg + rr * L::STG_LD + cc);
+                            float* dstp = cmat + grow * p.ldC + c0 + cc;
+                            if (c0 + cc + 4 <= p.N) {
+                                if (p.beta != 0.f) {
+                                    const float4 old = *reinterpret_cast<const float4*>(dstp);
+                                    o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y);
+                                    o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+                                }
+                                *reinterpret_cast<float4*>(dstp) = o;
+                            } else {
+                                const float oe[4] = {o.x, o.y, o.z, o.w};
+                                for (int e = 0; e < 4; e++) {
+                                    if (c0 + cc + e < p.N) dstp[e] = (p.beta != 0.f) ? fmaf(p.beta, dstp[e], oe[e]) : oe[e];
+                                }
                             }
                         }
                     }
@@ -690,8 +709,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 // planes[0] = tf32(x) (round to nearest, low 13 bits zero), planes[1] = x - planes[0] (exact in fp32).
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
-                  float* __restrict__ dst, int64_t ld_dst, int64_t plane_stride)
+                  float* __restrict__ dst, int64_t ld_dst, int64_t plane_stride, int64_t src_batch_stride)
 {
+    // blockIdx.z = matrix of a strided batch: its hi / lo planes sit at dst + z * 2 * plane_stride
+    src += (int64_t)blockIdx.z * src_batch_stride;
+    dst += (int64_t)blockIdx.z * 2 * plane_stride;
     const int64_t cv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 column
     if (cv * 4 >= cols) return;
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
@@ -759,8 +781,8 @@ int launch_tf32(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p)
         RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const int grid = tiles < c.sm_count ? tiles : c.sm_count;
+    const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks * p.batch;
+    const int grid = tiles < c.sm_count ? (int)tiles : c.sm_count;
     kern<<<grid, TC_THREADS, L::TOTAL, c.stream>>>(mA, mB, p);
     RB_LAUNCH_CHECK("gemm_tf32_kernel");
     return RB200_OK;
@@ -845,12 +867,12 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         float* wB = wA + 2 * plsA;
         {
             dim3 grid((unsigned)rb_ceil_div(cA / 4, 256), (unsigned)(rowsA < 65535 ? rowsA : 65535));
-            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(A, rowsA, colsA, ldA, wA, cA, plsA);
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(A, rowsA, colsA, ldA, wA, cA, plsA, 0);
             RB_LAUNCH_CHECK("split_tf32_kernel");
         }
         {
             dim3 grid((unsigned)rb_ceil_div(cB / 4, 256), (unsigned)(rowsB < 65535 ? rowsB : 65535));
-            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(B, rowsB, colsB, ldB, wB, cB, plsB);
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(B, rowsB, colsB, ldB, wB, cB, plsB, 0);
             RB_LAUNCH_CHECK("split_tf32_kernel");
         }
         srcA = wA; srcB = wB; sldA = cA; sldB = cB;
@@ -898,6 +920,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
         p.n_peers = 0;
+        p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
         static const int use_small = getenv("RB200_GEMM_SMALL_TILES") ? atoi(getenv("RB200_GEMM_SMALL_TILES")) : 1;
@@ -955,6 +978,89 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         else                    rc = launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p);
         if (rc != RB200_OK) return rc;
     }
+    return RB200_OK;
+}
+
+// Strided batch on the single-CTA kernels: the batch is the third tensor-map dimension (times the hi / lo planes in
+// 3xTF32 mode) and an extra digit of the tile index, so ONE persistent launch covers every matrix.  Operands with
+// stride 0 are shared (their third dimension is just the planes).  Strides must keep 16-byte alignment.
+bool gemm_tcgen05_batched_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA, int64_t strideA,
+                                   const float* B, int64_t ldB, int64_t strideB, const float* C, int64_t ldC,
+                                   int64_t strideC, int64_t batch)
+{
+    if (!gemm_tcgen05_eligible(M, N, K, A, ldA, B, ldB, C, ldC)) return false;
+    if (strideA % 4 || strideB % 4 || strideC % 4) return false;
+    if (batch > 32768) return false;
+    if (rb_ceil_div(M, TC_BM) * rb_ceil_div(N, 64) * batch > 0x3fffffffLL) return false;
+    return M >= 64 && N >= 64 && K >= 32;
+}
+
+int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
+                         const float* A, int64_t ldA, int64_t strideA, const float* B, int64_t ldB, int64_t strideB,
+                         float beta, float* C, int64_t ldC, int64_t strideC, int64_t batch)
+{
+    Context& c = ctx();
+    const bool a_mn = transA, b_mn = !transB;
+    const int planes = (mode == RB200_GEMM_TF32X3) ? 2 : 1;
+    const int64_t rowsA = transA ? K : M, colsA = transA ? M : K;
+    const int64_t rowsB = transB ? N : K, colsB = transB ? K : N;
+    const int64_t nA = strideA ? batch : 1, nB = strideB ? batch : 1;       // distinct matrices per operand
+    const float* srcA = A; const float* srcB = B;
+    int64_t sldA = ldA, sldB = ldB, thirdA = strideA, thirdB = strideB;     // third-dimension stride (elements)
+    if (planes == 2) {
+        const int64_t cA = rb_ceil_div(colsA, 4) * 4, cB = rb_ceil_div(colsB, 4) * 4;
+        const int64_t plsA = rowsA * cA, plsB = rowsB * cB;
+        int rc = ensure_workspace((size_t)(2 * plsA * nA + 2 * plsB * nB) * sizeof(float));
+        if (rc != RB200_OK) return rc;
+        float* wA = reinterpret_cast<float*>(c.workspace);
+        float* wB = wA + 2 * plsA * nA;
+        {
+            dim3 grid((unsigned)rb_ceil_div(cA / 4, 256), (unsigned)(rowsA < 1024 ? rowsA : 1024), (unsigned)nA);
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(A, rowsA, colsA, ldA, wA, cA, plsA, strideA);
+            RB_LAUNCH_CHECK("split_tf32_kernel");
+        }
+        {
+            dim3 grid((unsigned)rb_ceil_div(cB / 4, 256), (unsigned)(rowsB < 1024 ? rowsB : 1024), (unsigned)nB);
+            split_tf32_kernel<<<grid, 256, 0, c.stream>>>(B, rowsB, colsB, ldB, wB, cB, plsB, strideB);
+            RB_LAUNCH_CHECK("split_tf32_kernel");
+        }
+        srcA = wA; srcB = wB; sldA = cA; sldB = cB; thirdA = plsA; thirdB = plsB;
+    }
+    const CUtensorMapSwizzle k_sw = CU_TENSOR_MAP_SWIZZLE_128B, mn_sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    // tile width: the wider tile only when it still gives every SM work
+    const int64_t mblocks = rb_ceil_div(M, TC_BM);
+    int BN;
+    if (planes == 1) BN = (N > 128 && mblocks * rb_ceil_div(N, 256) * batch >= c.sm_count) ? 256 : 128;
+    else             BN = (N > 64 && mblocks * rb_ceil_div(N, 128) * batch >= c.sm_count) ? 128 : 64;
+    const int64_t KC = (planes == 2) ? 2048 : K;
+    for (int64_t kc = 0; kc < K; kc += KC) {
+        const int64_t kl = (K - kc) < KC ? (K - kc) : KC;
+        const float* pa = a_mn ? srcA + kc * sldA : srcA + kc;
+        const float* pb = b_mn ? srcB + kc * sldB : srcB + kc;
+        CUtensorMap mA, mB;
+        int rc;
+        // third dimension: planes x matrices; a count of 1 makes make_map ignore the stride
+        const int cntA = (int)(planes * nA), cntB = (int)(planes * nB);
+        if (!a_mn) rc = make_map(&mA, pa, kl, M, sldA, cntA, thirdA, TC_BK, TC_BM, k_sw);
+        else       rc = make_map(&mA, pa, M, kl, sldA, cntA, thirdA, 32, TC_BK, mn_sw);
+        if (rc != RB200_OK) return rc;
+        if (!b_mn) rc = make_map(&mB, pb, kl, N, sldB, cntB, thirdB, TC_BK, BN, k_sw);
+        else       rc = make_map(&mB, pb, N, kl, sldB, cntB, thirdB, 32, TC_BK, mn_sw);
+        if (rc != RB200_OK) return rc;
+        TcParams p;
+        p.M = M; p.N = N; p.K = kl; p.alpha = alpha; p.beta = (kc == 0) ? beta : 1.0f; p.C = C; p.ldC = ldC;
+        p.num_m_blocks = (int)mblocks;
+        p.num_n_blocks = (int)rb_ceil_div(N, BN);
+        p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
+        p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
+        p.group_m = TC_GROUP_M;
+        p.n_peers = 0;
+        p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
+        if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
+        else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);
+        if (rc != RB200_OK) return rc;
+    }
+    c.last_gemm_path = planes == 1 ? "tcgen05_tf32_batched" : "tcgen05_tf32x3_batched";
     return RB200_OK;
 }
 

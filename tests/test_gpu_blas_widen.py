@@ -198,6 +198,14 @@ BATCHED = [
     (3, 128, 384, 64, True, True, 1, dtypes.float32, rb.GEMM_TF32),
     (6, 20, 30, 10, False, False, 0, dtypes.float64, rb.GEMM_AUTO),
     (70000, 2, 3, 4, False, False, 0, dtypes.float32, rb.GEMM_AUTO),          # more matrices than gridDim.z allows
+    # tensor-core batched path (one persistent launch; batch = third tensor-map dimension)
+    (5, 128, 128, 64, False, False, 0, dtypes.float32, rb.GEMM_TF32X3),
+    (16, 64, 64, 32, False, True, 0, dtypes.float32, rb.GEMM_TF32X3),
+    (7, 192, 320, 100, True, False, 0, dtypes.float32, rb.GEMM_TF32X3),       # M / N / K tails
+    (9, 200, 136, 72, True, True, 2, dtypes.float32, rb.GEMM_TF32X3),         # shared B
+    (6, 256, 512, 64, False, False, 1, dtypes.float32, rb.GEMM_TF32),         # shared A, wide tiles
+    (300, 128, 64, 128, False, False, 0, dtypes.float32, rb.GEMM_TF32),
+    (2, 96, 80, 4200, False, True, 0, dtypes.float32, rb.GEMM_TF32X3),        # K chunks of 2048
 ]
 
 
@@ -209,23 +217,27 @@ def test_gemm_strided_batched_vs_oracle(batch, m, n, k, tA, tB, share, dt, mode,
     npdt = NP[dt]
     sA = 0 if share == 1 else m * k
     sB = 0 if share == 2 else n * k
-    a = rng.uniform(-1, 1, (1 if share == 1 else batch) * m * k + 5).astype(npdt)
-    b = rng.uniform(-1, 1, (1 if share == 2 else batch) * n * k + 3).astype(npdt)
-    c0 = rng.uniform(-1, 1, batch * m * n + 2).astype(npdt)
+    tensor = mode in (rb.GEMM_TF32, rb.GEMM_TF32X3) and m >= 64 and n >= 64 and k >= 32 and dt == dtypes.float32
+    oA, oB, oC = (4, 4, 4) if tensor else (5, 3, 2)                     # the tensor-core path needs 16-byte aligned operands
+    a = rng.uniform(-1, 1, (1 if share == 1 else batch) * m * k + oA).astype(npdt)
+    b = rng.uniform(-1, 1, (1 if share == 2 else batch) * n * k + oB).astype(npdt)
+    c0 = rng.uniform(-1, 1, batch * m * n + oC).astype(npdt)
     ldA, ldB = (m if tA else k), (k if tB else n)
     A, B, C = buf(a, dt), buf(b, dt), buf(c0, dt)
     math = cuda_service.math()
     math.gemmStridedBatched(BLAS.RowMajor, BLAS.Trans if tA else BLAS.NoTrans, BLAS.Trans if tB else BLAS.NoTrans, m, n, k,
-                            0.5, A, 5, ldA, sA, B, 3, ldB, sB, 2.0, C, 2, n, m * n, batch, gemm_mode=mode)
+                            0.5, A, oA, ldA, sA, B, oB, ldB, sB, 2.0, C, oC, n, m * n, batch, gemm_mode=mode)
+    if tensor:
+        assert _capi_path() == ("tcgen05_tf32_batched" if mode == rb.GEMM_TF32 else "tcgen05_tf32x3_batched"), _capi_path()
     got = C.to_numpy().astype(np.float64)
     ref = oracle.as_buffer(c0)
     ao, bo = oracle.as_buffer(a), oracle.as_buffer(b)
     check = range(batch) if batch <= 64 else list(range(0, batch, 997)) + [batch - 1]
     for i in check:
         oracle.gemm(oracle.RowMajor, oracle.Trans if tA else oracle.NoTrans, oracle.Trans if tB else oracle.NoTrans, m, n, k,
-                    0.5, ao, 5 + i * sA, ldA, bo, 3 + i * sB, ldB, 2.0, ref, 2 + i * m * n, n)
-        sl = slice(2 + i * m * n, 2 + (i + 1) * m * n)
-        tol = 2e-3 if (mode == rb.GEMM_TF32 and m >= 128) else (1e-12 if dt == dtypes.float64 else 5e-5)
+                    0.5, ao, oA + i * sA, ldA, bo, oB + i * sB, ldB, 2.0, ref, oC + i * m * n, n)
+        sl = slice(oC + i * m * n, oC + (i + 1) * m * n)
+        tol = 2e-3 if (mode == rb.GEMM_TF32 and tensor) else (1e-12 if dt == dtypes.float64 else 5e-5)
         assert np.max(np.abs(got[sl] - ref[sl])) < tol * max(1.0, np.max(np.abs(ref[sl]))), (i, _capi_path())
     assert got[0] == c0[0] and got[1] == c0[1]                       # before offsetC: untouched
 

@@ -43,5 +43,48 @@ def main():
         print("%-7s n=%5d  %.4f ms  %7.1f TFLOP/s  path=%s" % (mode_name, n, best, 2.0 * n ** 3 / best / 1e9, _capi.last_gemm_path()), flush=True)
 
 
+def batched():
+    """attention-shaped strided batches: [B*H, S, D] x [B*H, D, S] and [B*H, S, S] x [B*H, S, D]"""
+    mode_name = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+    mode = {"tf32": rb.GEMM_TF32, "tf32x3": rb.GEMM_TF32X3, "simt": rb.GEMM_FP32_SIMT}[mode_name]
+    math = rb.MatlibCuda(gemm_mode=mode).math()
+    stream = torch.cuda.Stream()
+    _capi.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(0)
+    for (bh, s, d) in ((768, 512, 64), (256, 1024, 64), (1536, 128, 64), (96, 2048, 128)):
+        Q = CudaBuffer(bh * s * d, dtypes.float32).from_numpy(rng.uniform(-1, 1, bh * s * d).astype(np.float32))
+        Kt = CudaBuffer(bh * s * d, dtypes.float32).from_numpy(rng.uniform(-1, 1, bh * s * d).astype(np.float32))
+        S = CudaBuffer(bh * s * s, dtypes.float32)
+        O = CudaBuffer(bh * s * d, dtypes.float32)
+
+        def qk():
+            math.gemmStridedBatched(BLAS.RowMajor, BLAS.NoTrans, BLAS.Trans, s, s, d, 1.0, Q, 0, d, s * d, Kt, 0, d, s * d, 0.0,
+                                    S, 0, s, s * s, bh, gemm_mode=mode)
+
+        def sv():
+            math.gemmStridedBatched(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, s, d, s, 1.0, S, 0, s, s * s, Kt, 0, d, s * d, 0.0,
+                                    O, 0, d, s * d, bh, gemm_mode=mode)
+
+        for name, fn, flops, nbytes in (("QK^T", qk, 2.0 * bh * s * s * d, 4.0 * bh * (2 * s * d + s * s)),
+                                        ("SV", sv, 2.0 * bh * s * s * d, 4.0 * bh * (2 * s * d + s * s))):
+            for _ in range(3):
+                fn()
+            _capi.sync()
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    fn()
+                e1.record(stream)
+                _capi.sync()
+                best = min(best, e0.elapsed_time(e1) / 10)
+            print("%-6s %-5s bh=%5d s=%5d d=%4d  %.4f ms  %7.1f TFLOP/s  %6.0f GB/s  path=%s" % (
+                mode_name, name, bh, s, d, best, flops / best / 1e9, nbytes / best / 1e6, _capi.last_gemm_path()), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "batched":
+        batched()
+    else:
+        main()

@@ -2,7 +2,8 @@
 """Run one hot-path op a few times at its BASELINE size -- the command ncu wraps
 (profiles/README.md lists the exact ncu invocations).  Usage: profile_ops.py OP [REPS]
 OP in: sgemm_tf32 sgemm_tf32x3 sgemm_simt add multiply reduce_sum reduce_sum_axis0 reduce_max
-       reduce_argmax softmax im2col2d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans"""
+       reduce_argmax softmax im2col2d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans
+       maximum exp astype transpose_nd gather scatter_add sum"""
 import os
 import sys
 
@@ -73,6 +74,22 @@ def main():
               "transpose": lambda: blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A, 0, n, Y, 0, m),
               "gemv": lambda: blas.gemv(BLAS.RowMajor, BLAS.NoTrans, m, n, 1.0, A, 0, n, Xn, 0, 1, 0.0, Ym, 0, 1),
               "gemv_trans": lambda: blas.gemv(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, A, 0, n, Xm, 0, 1, 0.0, Yn, 0, 1),
+              }[op]
+    elif op in ("maximum", "exp", "astype", "transpose_nd", "gather", "scatter_add", "sum"):
+        m, n = 8192, 4096
+        A, Y, X = rnd(m * n), rnd(m * n), rnd(n)
+        I32 = CudaBuffer(m * n, dtypes.int32, zero=False)
+        sh3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([64, 512, 1024], np.int32))
+        pm3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([0, 2, 1], np.int32))
+        vocab, dim, ntok = 32768, 1024, 32768
+        ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
+        fn = {"maximum": lambda: math.maximum(m, n, A, 0, n, X, 0, 1),
+              "exp": lambda: math.exp(m * n, A, 0, 1),
+              "astype": lambda: math.astype(m * n, dtypes.int32, A, 0, 1, I32, 0, 1),
+              "transpose_nd": lambda: math.transpose(sh3, pm3, A, 0, Y, 0),
+              "gather": lambda: math.gather(False, False, ntok, dim, vocab, ids, 0, A, 0, Y, 0),
+              "scatter_add": lambda: math.gather(True, True, ntok, dim, vocab, ids, 0, A, 0, Y, 0),
+              "sum": lambda: math.sum(m * n, A, 0, 1),
               }[op]
     else:
         raise SystemExit("unknown op " + op)
