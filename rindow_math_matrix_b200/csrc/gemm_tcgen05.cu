@@ -829,6 +829,30 @@ int launch_2cta(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& 
 
 namespace rb200 {
 
+// General float32 tensor map (rank <= 5) for the skinny / implicit-GEMM kernels: image slabs (unswizzled
+// loads) and output tiles (128-byte swizzled stores).  dims innermost first, strides in bytes for
+// dimensions 1..rank-1, zero fill / clipping outside the tensor.
+int encode_tensor_map_f32(void* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                          const uint32_t* box, bool swizzle128)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RB200_E_CUDA; }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], estr[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) s[i] = strides[i];
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                    const_cast<float*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank=%d dims[0..1]=%llu,%llu box[0..1]=%u,%u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return RB200_E_CUDA;
+    }
+    return RB200_OK;
+}
+
 // Whether the tensor-core path can take this problem (TMA alignment rules).
 bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
                            const float* B, int64_t ldB, const float* C, int64_t ldC)

@@ -18,6 +18,7 @@
 //               tcgen05.ld -> registers -> shared-memory transpose -> coalesced 128-bit stores
 // B (K x N, tiny) is staged once per CTA, transposed to K-major, all k-blocks resident.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -36,6 +37,8 @@ constexpr int SKT_PREFETCH = 3;                      // raw A tiles in flight ah
 constexpr int SKT_RAW_SLOTS = SKT_PREFETCH + 1;
 constexpr int SKT_RAW_STAGE = SKT_BM * SKT_BK * 4;   // 16 KB
 constexpr int SKT_SMEM_LIMIT = 226 * 1024;
+constexpr int SKT_MAX_BOXES = 8;
+constexpr int SKT_ROW_SLOTS = 3;                     // slab slots per producer group of the conv row producer
 
 __device__ __forceinline__ uint32_t sk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sk_mbar_init(uint32_t bar, uint32_t count)
@@ -59,17 +62,23 @@ __device__ __forceinline__ void sk_mbar_wait(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ void sk_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void sk_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void sk_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void sk_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+// warp-converged variants: every lane executes them, one elected lane issues
+__device__ __forceinline__ void sk_mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, e;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void sk_commit_elect(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void sk_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
@@ -97,11 +106,17 @@ __device__ __forceinline__ uint64_t sk_desc(uint32_t smem_addr)          // K-ma
     d |= (uint64_t)2 << 61;
     return d;
 }
+// round to tf32, nearest with ties away from zero == cvt.rna.tf32.f32, which sm_100a expands to this add + mask
+// plus an Inf/NaN test the split does not need: Inf stays Inf, a NaN stays NaN in at least one of hi / lo
 __device__ __forceinline__ float sk_rna(float x)
 {
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-    return __uint_as_float(t);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float sk_lds(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 struct SktParams {
@@ -126,6 +141,16 @@ struct SktParams {
     // always one contiguous run of rows of the [B*oh*ow, N] output); its input slab is staged in smem
     int cv_tw, cv_rows, cv_col_blocks, cv_row_blocks;
     int cv_slab_rows, cv_width_x, cv_row_elems, cv_slab_elems;
+    // row producer (conv == 2, K <= 32): the slab arrives by TMA as cv_nbox boxes of cv_bw floats x
+    // cv_slab_rows rows (zero filled outside the image); box i starts cv_box_start[i] floats into the slab
+    // row, every cell's run of (filt_w-1)*dil_w*chan + chan floats lies inside one box; column k of the
+    // virtual cols row sits koff[k] bytes after the cell's run origin
+    int cv_nbox, cv_bw, cv_box_elems, cv_slot_elems;
+    int cv_xshift;                 // floats the slab origin is moved left so that every TMA x coordinate is a multiple of 4
+    int cv_box_start[SKT_MAX_BOXES];
+    int koff[SKT_BK];
+    uint32_t ring_bytes;           // bytes of the raw / slab ring
+    int tma_store;                 // epilogue stores C tiles with TMA (tmapC: 4-D [.., .., rows, N], 128-byte swizzle)
 };
 
 struct SktTile { int64_t m_start; int nvalid; int b, oy0, ox0; };
@@ -152,9 +177,10 @@ __device__ __forceinline__ SktTile skt_tile(const SktParams& p, int tile)
     return t;
 }
 
-template <int PLANES>
+template <int PLANES, bool ROWS>
 __global__ void __launch_bounds__(SKT_THREADS, 1)
-gemm_tf32_skinny_kernel(SktParams p)
+gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_constant__ CUtensorMap tmap,
+                        const __grid_constant__ CUtensorMap tmapC)
 {
     extern __shared__ uint8_t skt_raw[];
     const uint32_t base = (sk_smem_u32(skt_raw) + 1023u) & ~1023u;
@@ -165,8 +191,8 @@ gemm_tf32_skinny_kernel(SktParams p)
     const uint32_t off_b = SKT_STAGES * a_stage_bytes;
     const uint32_t off_epi = off_b + PLANES * b_plane_bytes;
     const int epi_pitch = p.NP + 4;                                  // floats; keeps rows 16-byte aligned
-    const uint32_t off_raw = off_epi + (uint32_t)p.epi_groups * 4u * 32u * epi_pitch * 4u;   // 16-byte aligned
-    const uint32_t off_bar = off_raw + (uint32_t)p.raw_slots * SKT_RAW_STAGE;
+    const uint32_t off_raw = (off_epi + (uint32_t)p.epi_groups * 4u * 32u * epi_pitch * 4u + 127u) & ~127u;
+    const uint32_t off_bar = off_raw + p.ring_bytes;
     const uint32_t bar = base + ((off_bar + 7u) & ~7u);
     const uint32_t off_rinfo = ((off_bar + 7u) & ~7u) + 128u;            // [128][3] ints, conv only
     auto a_full  = [&](int s) { return bar + 8u * s; };
@@ -174,13 +200,21 @@ gemm_tf32_skinny_kernel(SktParams p)
     auto t_full  = [&](int a) { return bar + 8u * (2 * SKT_STAGES + a); };
     auto t_empty = [&](int a) { return bar + 8u * (2 * SKT_STAGES + 2 + a); };
     const uint32_t tmem_slot = bar + 8u * (2 * SKT_STAGES + 4);
+    // row producer: slab barriers live in the (otherwise unused) row-info area
+    auto slab_full  = [&](int g, int s) { return base + off_rinfo + 8u * (uint32_t)(g * SKT_ROW_SLOTS + s); };
+    auto slab_empty = [&](int g, int s) { return base + off_rinfo + 8u * (uint32_t)(2 * SKT_ROW_SLOTS + g * SKT_ROW_SLOTS + s); };
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ACC_COLS = PLANES * p.NP;
 
     if (warp == SKT_MMA_WARP && lane == 0) {
-        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), SKT_PROD_WARPS); sk_mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), ROWS ? 4 : SKT_PROD_WARPS); sk_mbar_init(a_empty(s), 1); }
+        if (ROWS) {
+            for (int g = 0; g < 2; g++) {
+                for (int s = 0; s < SKT_ROW_SLOTS; s++) { sk_mbar_init(slab_full(g, s), 1); sk_mbar_init(slab_empty(g, s), 4); }
+            }
+        }
         for (int a = 0; a < 2; a++) { sk_mbar_init(t_full(a), 1); sk_mbar_init(t_empty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -199,9 +233,15 @@ gemm_tf32_skinny_kernel(SktParams p)
         float v = 0.f;
         if (k < p.K && n < p.N) v = __ldg(p.B + (int64_t)k * p.ldB + n);
         const float hi = sk_rna(v);
-        const uint32_t o = off_b + (uint32_t)(k >> 5) * (uint32_t)(p.NP * 128) + sk_swz(n, k & 31);
+        // [k-block][plane][n][32 k]: the lo plane of a k-block directly follows its hi plane, so one UMMA
+        // descriptor with N = 2*NP reads B_hi | B_lo as a single operand
+        const uint32_t o = off_b + (uint32_t)(k >> 5) * (uint32_t)(PLANES * p.NP * 128) + sk_swz(n, k & 31);
         *reinterpret_cast<float*>(gen + o) = hi;
-        if (PLANES == 2) *reinterpret_cast<float*>(gen + o + b_plane_bytes) = v - hi;
+        if (PLANES == 2) *reinterpret_cast<float*>(gen + o + (uint32_t)(p.NP * 128)) = v - hi;
+    }
+    float* bias_s = reinterpret_cast<float*>(gen + off_rinfo + 1024u);         // [NP] bias (or zeros); the cp.async conv producer owns the first 1 KB
+    if (p.tma_store) {
+        for (int n = threadIdx.x; n < p.NP; n += SKT_THREADS) bias_s[n] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     sk_fence_before();
@@ -213,7 +253,96 @@ gemm_tf32_skinny_kernel(SktParams p)
         // ===== producers =====
         const int t = threadIdx.x;                                    // 0..SKT_PRODUCERS-1
         int stage = 0; uint32_t phase = 0;
-        if (p.a_contig && p.KB == 1) {
+        if constexpr (ROWS) {
+            // Implicit GEMM, K <= 32, one thread per cols row.  Two groups of four warps; group g builds the
+            // tiles of parity g into A stage g, so two tiles are always under construction.  The input slab
+            // of a tile (zero padded by TMA's out-of-bounds fill) arrives in a per-group ring of
+            // SKT_ROW_SLOTS slots, requested two tiles ahead by one lane of the group.  A thread reads the
+            // K floats of its row with LDS.32 (lane stride = str_w*chan floats: conflict free when odd),
+            // splits them in registers and writes whole 16-byte chunks of the swizzled A row.
+            const int g = warp >> 2;
+            const int r = t & (SKT_BM - 1);
+            int rr = p.cv_rows > 1 ? r / p.cv_tw : 0;
+            int cc = r - rr * p.cv_tw;
+            if (r >= p.cv_rows * p.cv_tw) { rr = 0; cc = 0; }             // never-stored rows: stay inside the slab
+            const int x0 = cc * p.str_w * p.chan + p.cv_xshift;
+            int bi = 0;
+            for (int i = 1; i < p.cv_nbox; i++) { if (p.cv_box_start[i] <= x0) bi = i; }
+            const int roff = bi * p.cv_box_elems + rr * p.str_h * p.cv_bw + (x0 - p.cv_box_start[bi]);
+            const uint32_t ring_g_addr = base + off_raw + (uint32_t)(g * SKT_ROW_SLOTS * p.cv_slot_elems) * 4u;
+            const int step = gridDim.x;
+            const int per_img = p.cv_row_blocks * p.cv_col_blocks;
+            const bool issuer = (warp & 3) == 0 && lane == 0;
+            const uint32_t slot_tx = (uint32_t)(p.cv_nbox * p.cv_bw * p.cv_slab_rows) * 4u;
+            auto issue = [&](int jj) {
+                const int64_t tile64 = (int64_t)blockIdx.x + (int64_t)(2 * jj + g) * step;
+                if (tile64 >= p.num_tiles) return;
+                const int tile = (int)tile64;
+                const int slot = jj % SKT_ROW_SLOTS, n = jj / SKT_ROW_SLOTS;
+                if (n > 0) sk_mbar_wait(slab_empty(g, slot), (uint32_t)((n & 1) ^ 1));
+                const int b = tile / per_img, q = tile - b * per_img;
+                const int rb = q / p.cv_col_blocks, cb = q - rb * p.cv_col_blocks;
+                const int x = (cb * p.cv_tw * p.str_w - p.pad_w) * p.chan - p.cv_xshift;   // multiple of 4 floats
+                const int y = rb * p.cv_rows * p.str_h - p.pad_h;
+                const uint32_t bar_f = slab_full(g, slot);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_f), "r"(slot_tx) : "memory");
+                const uint32_t dst = ring_g_addr + (uint32_t)(slot * p.cv_slot_elems) * 4u;
+#pragma unroll 1
+                for (int i = 0; i < p.cv_nbox; i++) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                        :: "r"(dst + (uint32_t)(i * p.cv_box_elems) * 4u), "l"(reinterpret_cast<uint64_t>(&tmap)),
+                           "r"(x + p.cv_box_start[i]), "r"(y), "r"(b), "r"(bar_f) : "memory");
+                }
+            };
+            if (issuer) { issue(0); issue(1); }
+            const uint32_t swr = (uint32_t)(r & 7);
+            const int kq_last = (p.K - 1) >> 2;
+            for (int j = 0; (int64_t)blockIdx.x + (int64_t)(2 * j + g) * step < p.num_tiles; j++) {
+                if (issuer) issue(j + 2);
+                __syncwarp();
+                const int slot = j % SKT_ROW_SLOTS, n = j / SKT_ROW_SLOTS;
+                sk_mbar_wait(slab_full(g, slot), (uint32_t)(n & 1));
+                const uint32_t sl = ring_g_addr + (uint32_t)(slot * p.cv_slot_elems + roff) * 4u;
+                float v[SKT_BK];
+#pragma unroll
+                for (int q = 0; q < SKT_BK / 4; q++) {
+                    if (4 * q < p.K) {                                   // koff[k >= K] repeats koff[0]: a valid address
+#pragma unroll
+                        for (int i = 0; i < 4; i++) v[4 * q + i] = sk_lds(sl + (uint32_t)p.koff[4 * q + i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) v[4 * q + i] = 0.f;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(slab_empty(g, slot));
+                sk_mbar_wait(a_empty(g), (uint32_t)((j & 1) ^ 1));
+                uint8_t* sa = gen + g * a_stage_bytes + (uint32_t)(r << 7);
+#pragma unroll
+                for (int q = 0; q < SKT_BK / 4; q++) {
+                    if (4 * q < p.K) {
+                        if (q == kq_last) {                              // the chunk K ends in: zero its tail
+                            if (4 * q + 1 >= p.K) v[4 * q + 1] = 0.f;
+                            if (4 * q + 2 >= p.K) v[4 * q + 2] = 0.f;
+                            if (4 * q + 3 >= p.K) v[4 * q + 3] = 0.f;
+                        }
+                        float4 hi, lo;
+                        hi.x = sk_rna(v[4 * q]);     lo.x = v[4 * q] - hi.x;
+                        hi.y = sk_rna(v[4 * q + 1]); lo.y = v[4 * q + 1] - hi.y;
+                        hi.z = sk_rna(v[4 * q + 2]); lo.z = v[4 * q + 2] - hi.z;
+                        hi.w = sk_rna(v[4 * q + 3]); lo.w = v[4 * q + 3] - hi.w;
+                        const uint32_t o = ((uint32_t)q ^ swr) << 4;
+                        *reinterpret_cast<float4*>(sa + o) = hi;
+                        if (PLANES == 2) *reinterpret_cast<float4*>(sa + SKT_A_TILE + o) = lo;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(a_full(g));
+            }
+            (void)stage; (void)phase;
+        } else if (p.a_contig && p.KB == 1) {
             // Each 128-row tile is rows*K contiguous floats.  They are brought into a raw shared-memory
             // ring with 16-byte cp.async copies issued SKT_PREFETCH tiles ahead (each thread later reads
             // back exactly the chunks it copied, so cp.async.wait_group is the only synchronisation), then
@@ -458,8 +587,13 @@ gemm_tf32_skinny_kernel(SktParams p)
         }
     } else if (warp == SKT_MMA_WARP) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
+        // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one
+        // elected lane issues.  3xTF32 takes two instructions per k-step: A_hi x [B_hi | B_lo] fills the big
+        // (hi*hi) and the small (hi*lo) accumulator at once (N = 2*NP, adjacent TMEM columns), then
+        // A_lo x B_hi adds into the small one.
+        {
+            const uint32_t idesc_n  = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
+            const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 2) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -470,23 +604,21 @@ gemm_tf32_skinny_kernel(SktParams p)
                     sk_mbar_wait(a_full(stage), phase);
                     sk_fence_after();
                     const uint32_t sA = base + stage * a_stage_bytes;
-                    const uint32_t sB = base + off_b + (uint32_t)kb * (uint32_t)(p.NP * 128);
+                    const uint32_t sB = base + off_b + (uint32_t)kb * (uint32_t)(PLANES * p.NP * 128);
 #pragma unroll
                     for (int kk = 0; kk < SKT_BK / 8; kk++) {
                         const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
                         const uint64_t a_hi = sk_desc(sA + kk * 32), b_hi = sk_desc(sB + kk * 32);
                         if (PLANES == 1) {
-                            sk_mma(tmem_d, a_hi, b_hi, idesc, first);
+                            sk_mma_elect(tmem_d, a_hi, b_hi, idesc_n, first);
                         } else {
                             const uint64_t a_lo = sk_desc(sA + SKT_A_TILE + kk * 32);
-                            const uint64_t b_lo = sk_desc(sB + b_plane_bytes + kk * 32);
-                            sk_mma(tmem_d + p.NP, a_hi, b_lo, idesc, first);
-                            sk_mma(tmem_d + p.NP, a_lo, b_hi, idesc, 1u);
-                            sk_mma(tmem_d, a_hi, b_hi, idesc, first);
+                            sk_mma_elect(tmem_d, a_hi, b_hi, idesc_2n, first);
+                            sk_mma_elect(tmem_d + p.NP, a_lo, b_hi, idesc_n, 1u);
                         }
                     }
-                    sk_commit(a_empty(stage));
-                    if (kb == p.KB - 1) sk_commit(t_full(acc));
+                    sk_commit_elect(a_empty(stage));
+                    if (kb == p.KB - 1) sk_commit_elect(t_full(acc));
                     if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -495,7 +627,76 @@ gemm_tf32_skinny_kernel(SktParams p)
     } else {
         // ===== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles alternate) =====
         const int g = (warp - SKT_EPI_WARP0) >> 2;
-        if (g < p.epi_groups) {
+        if (g < p.epi_groups && p.tma_store) {
+            // TMA-store epilogue: TMEM -> registers -> alpha (+ bias) -> 128-byte swizzled staging tile of the
+            // group ([NP/32 boxes][128 rows][32 floats]) -> one lane issues cp.async.bulk.tensor stores, which
+            // clip ragged tiles (out-of-range rows / columns are not written) and write whole 128-byte lines.
+            const int q = warp & 3;                                   // TMEM lane quarter of this warp
+            const int r = q * 32 + lane;                              // row of the tile this thread owns
+            const uint32_t stg = base + off_epi + (uint32_t)g * (uint32_t)(p.NP >> 5) * 16384u;
+            const uint32_t row_addr = stg + (uint32_t)r * 128u;
+            const uint32_t sw = (uint32_t)(r & 7);
+            const int nbx = (p.N + 31) >> 5;
+            const bool leader = q == 0 && lane == 0;
+            uint32_t acc_phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                if (p.epi_groups == 2 && acc != g) continue;
+                sk_mbar_wait(t_full(acc), acc_phase);
+                if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
+                sk_fence_after();
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
+                asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
+                for (int ch = 0; ch < p.NP / 16; ch++) {
+                    uint32_t rr[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 16);
+                    sk_ld16(taddr, rr);
+                    if (PLANES == 2) {
+                        uint32_t rs[16];
+                        sk_ld16(taddr + p.NP, rs);
+                        sk_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; e++) rr[e] = __float_as_uint(__uint_as_float(rr[e]) + __uint_as_float(rs[e]));
+                    } else {
+                        sk_wait_ld();
+                    }
+                    const float4* bv = reinterpret_cast<const float4*>(bias_s + ch * 16);
+                    const uint32_t box_addr = row_addr + (uint32_t)(ch >> 1) * 16384u;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const float4 b4 = bv[v];
+                        float4 o;
+                        o.x = fmaf(p.alpha, __uint_as_float(rr[4 * v]), b4.x);
+                        o.y = fmaf(p.alpha, __uint_as_float(rr[4 * v + 1]), b4.y);
+                        o.z = fmaf(p.alpha, __uint_as_float(rr[4 * v + 2]), b4.z);
+                        o.w = fmaf(p.alpha, __uint_as_float(rr[4 * v + 3]), b4.w);
+                        const uint32_t a = box_addr + ((((uint32_t)(ch & 1) * 4u + (uint32_t)v) ^ sw) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                    }
+                }
+                sk_fence_before();
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(t_empty(acc));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
+                if (leader) {
+                    const SktTile ti = skt_tile(p, tile);
+                    int c1, c2, c3;
+                    if (p.conv) { c1 = ti.ox0; c2 = ti.oy0; c3 = ti.b; }
+                    else { c1 = (int)ti.m_start; c2 = 0; c3 = 0; }
+#pragma unroll 1
+                    for (int bx = 0; bx < nbx; bx++) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                            :: "l"(reinterpret_cast<uint64_t>(&tmapC)), "r"(bx * 32), "r"(c1), "r"(c2), "r"(c3),
+                               "r"(stg + (uint32_t)bx * 16384u) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (g < p.epi_groups) {
             const int q = warp & 3;                                   // TMEM lane quarter of this warp
             float* ebuf = reinterpret_cast<float*>(gen + off_epi) + (warp - SKT_EPI_WARP0) * 32 * epi_pitch;
             const int nv = p.NP >> 2;                                 // float4 per row
@@ -609,17 +810,56 @@ gemm_tf32_skinny_kernel(SktParams p)
     }
 }
 
-size_t skt_smem_bytes(int planes, int NP, int KB, int epi_groups, int raw_slots)
+size_t skt_smem_bytes_ring(int planes, int NP, int KB, int epi_groups, size_t ring_bytes)
 {
     size_t a = (size_t)SKT_STAGES * planes * SKT_A_TILE;
     size_t b = (size_t)planes * KB * NP * 128;
     size_t e = (size_t)epi_groups * 4 * 32 * (NP + 4) * 4;
-    return a + b + e + (size_t)raw_slots * SKT_RAW_STAGE + 256 + 128 * 3 * 4 + 1024;
+    return a + b + e + 128 + ring_bytes + 256 + 128 * 3 * 4 + 1024;
+}
+size_t skt_smem_bytes(int planes, int NP, int KB, int epi_groups, int raw_slots)
+{
+    return skt_smem_bytes_ring(planes, NP, KB, epi_groups, (size_t)raw_slots * SKT_RAW_STAGE);
+}
+
+bool skt_tma_store_enabled()
+{
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("RB200_SKT_TMA_STORE"); env = (e && e[0] == '0') ? 0 : 1; }
+    return env != 0;
+}
+
+// one launcher for every producer variant (the tensor map is only read by the conv row producer)
+int skt_launch(int planes, bool rows, const SktParams& p, const CUtensorMap& tmap, const CUtensorMap& tmapC, size_t smem,
+               const char* name)
+{
+    rb200::Context& c = rb200::ctx();
+    static bool configured = false;
+    if (!configured) {
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        configured = true;
+    }
+    const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
+    if (rows) {
+        if (planes == 1) gemm_tf32_skinny_kernel<1, true><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
+        else             gemm_tf32_skinny_kernel<2, true><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
+    } else {
+        if (planes == 1) gemm_tf32_skinny_kernel<1, false><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
+        else             gemm_tf32_skinny_kernel<2, false><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
+    }
+    RB_LAUNCH_CHECK(name);
+    return RB200_OK;
 }
 
 }  // namespace
 
 namespace rb200 {
+
+int encode_tensor_map_f32(void* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                          const uint32_t* box, bool swizzle128);
 
 bool gemm_tcgen05_skinny_eligible(int mode, int64_t M, int64_t N, int64_t K)
 {
@@ -660,16 +900,23 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
         else p.a_contig = 0;
     }
     const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, p.raw_slots);
-    static bool configured[3] = {false, false, false};
-    if (!configured[planes]) {
-        if (planes == 1) RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        else             RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        configured[planes] = true;
+    p.ring_bytes = (uint32_t)p.raw_slots * SKT_RAW_STAGE;
+    p.cv_nbox = p.cv_bw = p.cv_box_elems = p.cv_slot_elems = p.cv_xshift = 0;
+    memset(p.cv_box_start, 0, sizeof(p.cv_box_start));
+    memset(p.koff, 0, sizeof(p.koff));
+    CUtensorMap none, mapC;
+    memset(&none, 0, sizeof(none));
+    memset(&mapC, 0, sizeof(mapC));
+    p.tma_store = 0;
+    if (skt_tma_store_enabled() && beta == 0.f && N >= 32 && (N % 4) == 0 && (ldC % 4) == 0 &&
+        ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && M <= 0x7fffffffLL) {
+        const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
+        const uint64_t strides[3] = {(uint64_t)ldC * 4, (uint64_t)ldC * 4 * (uint64_t)M, (uint64_t)ldC * 4 * (uint64_t)M};
+        const uint32_t box[4] = {32, SKT_BM, 1, 1};
+        p.tma_store = encode_tensor_map_f32(&mapC, C, 4, dims, strides, box, true) == RB200_OK;    // else: plain stores
     }
-    const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
-    if (planes == 1) gemm_tf32_skinny_kernel<1><<<grid, SKT_THREADS, smem, c.stream>>>(p);
-    else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p);
-    RB_LAUNCH_CHECK("gemm_tf32_skinny_kernel");
+    const int rc = skt_launch(planes, false, p, none, mapC, smem, "gemm_tf32_skinny_kernel");
+    if (rc != RB200_OK) return rc;
     c.last_gemm_path = planes == 1 ? "tcgen05_tf32_skinny" : "tcgen05_tf32x3_skinny";
     return RB200_OK;
 }
@@ -711,47 +958,120 @@ int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h,
     p.im_h = (int)im_h; p.im_w = (int)im_w; p.chan = (int)channels; p.filt_w = (int)filter_w;
     p.str_h = (int)stride_h; p.str_w = (int)stride_w; p.dil_h = (int)dilation_h; p.dil_w = (int)dilation_w;
     p.pad_h = (int)pad_h; p.pad_w = (int)pad_w; p.out_h = (int)out_h; p.out_w = (int)out_w;
+    p.cv_nbox = p.cv_bw = p.cv_box_elems = p.cv_slot_elems = p.cv_xshift = 0;
+    memset(p.cv_box_start, 0, sizeof(p.cv_box_start));
+    memset(p.koff, 0, sizeof(p.koff));
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
     // tiling: <= 128 cells per MMA tile, as a block of out columns of one out row (wide images) or as
-    // several whole out rows (narrow feature maps); the slab of inputs must fit one 16 KB ring slot
+    // several whole out rows (narrow feature maps)
     if (out_w >= SKT_BM) { p.cv_tw = SKT_BM; p.cv_rows = 1; }
     else { p.cv_tw = (int)out_w; p.cv_rows = (int)(SKT_BM / out_w); if (p.cv_rows > out_h) p.cv_rows = (int)out_h; }
-    for (;;) {
-        p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
-        p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
-        p.cv_row_elems = p.cv_width_x * p.chan;
-        p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
-        if ((int64_t)p.cv_slab_elems * 4 <= SKT_RAW_STAGE) break;
-        if (p.cv_rows > 1) { p.cv_rows--; continue; }
-        if (p.cv_tw > 16) { p.cv_tw /= 2; continue; }
-        set_error("conv2d_forward: the input slab of one tile exceeds the staging ring (use im2col2d + gemm)");
-        return RB200_E_UNSUPPORTED;
+    const int tw0 = p.cv_tw, rows0 = p.cv_rows;
+
+    // ---- row producer (K <= 32, TMA slabs): the first-layer shapes (3x3x3, 5x5x1, ...) ----
+    bool rows_mode = false;
+    {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("RB200_CONV_ROWS"); env = (e && e[0] == '0') ? 0 : 1; }
+        const int64_t row_floats = im_w * channels;
+        const int run = (int)((filter_w - 1) * dilation_w * channels + channels);
+        auto gcd32 = [](int64_t v) { int g = 1; while (g < 32 && (v % (2 * g)) == 0) g *= 2; return g; };
+        const bool ok = env && p.KB == 1 && (row_floats % 4) == 0 && ((reinterpret_cast<uintptr_t>(images) & 15) == 0) &&
+                        run <= 256 && gcd32(stride_w * channels) <= 2 && im_h <= 0x7fffffffLL && batches <= 0x7fffffffLL;
+        if (ok) {
+            p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
+            p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
+            p.cv_row_elems = p.cv_width_x * p.chan;
+            p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
+            // TMA wants 16-byte aligned box origins: the slab starts cv_xshift floats left of the tile's first
+            // input column (the same shift for every tile: several column blocks only occur with cv_tw = 128)
+            // and boxes start at multiples of 4 floats
+            p.cv_xshift = (int)((((-pad_w * channels) % 4) + 4) % 4);
+            p.cv_row_elems += p.cv_xshift;
+            p.cv_bw = p.cv_row_elems >= 256 ? 256 : (p.cv_row_elems + 3) / 4 * 4;
+            int nbox = 1;
+            bool fits = p.cv_slab_rows <= 256 && run + 3 <= p.cv_bw;
+            p.cv_box_start[0] = 0;
+            for (int cc = 0; cc < p.cv_tw && fits; cc++) {
+                const int x0 = cc * p.str_w * p.chan + p.cv_xshift;
+                if (x0 + run > p.cv_box_start[nbox - 1] + p.cv_bw) {
+                    if (nbox == SKT_MAX_BOXES) { fits = false; break; }
+                    p.cv_box_start[nbox++] = x0 / 4 * 4;
+                }
+            }
+            p.cv_nbox = nbox;
+            p.cv_box_elems = (p.cv_bw * p.cv_slab_rows + 31) / 32 * 32;
+            p.cv_slot_elems = nbox * p.cv_box_elems;
+            const size_t ring = (size_t)2 * SKT_ROW_SLOTS * p.cv_slot_elems * 4;
+            if (fits) {
+                p.epi_groups = skt_smem_bytes_ring(planes, p.NP, p.KB, 2, ring) <= SKT_SMEM_LIMIT ? 2 : 1;
+                fits = skt_smem_bytes_ring(planes, p.NP, p.KB, p.epi_groups, ring) <= SKT_SMEM_LIMIT;
+            }
+            if (fits) {
+                for (int k = 0; k < p.K; k++) {
+                    const int kwc = (int)(filter_w * channels);
+                    const int ky = k / kwc, rem = k - ky * kwc, kx = rem / p.chan, ch = rem - kx * p.chan;
+                    p.koff[k] = (ky * p.dil_h * p.cv_bw + kx * p.dil_w * p.chan + ch) * 4;      // bytes
+                }
+                for (int k = p.K; k < SKT_BK; k++) p.koff[k] = p.koff[0];
+                const uint64_t dims[3] = {(uint64_t)row_floats, (uint64_t)im_h, (uint64_t)batches};
+                const uint64_t strides[2] = {(uint64_t)row_floats * 4, (uint64_t)row_floats * 4 * (uint64_t)im_h};
+                const uint32_t box[3] = {(uint32_t)p.cv_bw, (uint32_t)p.cv_slab_rows, 1};
+                const int rc = encode_tensor_map_f32(&tmap, images, 3, dims, strides, box, false);
+                if (rc != RB200_OK) return rc;
+                p.ring_bytes = (uint32_t)ring;
+                p.raw_slots = 0;
+                p.conv = 2;
+                rows_mode = true;
+            }
+        }
+    }
+    if (!rows_mode) {
+        // the slab of inputs must fit one 16 KB slot of the cp.async ring
+        p.cv_tw = tw0; p.cv_rows = rows0;
+        for (;;) {
+            p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
+            p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
+            p.cv_row_elems = p.cv_width_x * p.chan;
+            p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
+            if ((int64_t)p.cv_slab_elems * 4 <= SKT_RAW_STAGE) break;
+            if (p.cv_rows > 1) { p.cv_rows--; continue; }
+            if (p.cv_tw > 16) { p.cv_tw /= 2; continue; }
+            set_error("conv2d_forward: the input slab of one tile exceeds the staging ring (use im2col2d + gemm)");
+            return RB200_E_UNSUPPORTED;
+        }
+        p.raw_slots = SKT_RAW_SLOTS;
+        p.ring_bytes = (uint32_t)SKT_RAW_SLOTS * SKT_RAW_STAGE;
+        p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT ? 2 : 1;
+        if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) {
+            set_error("conv2d_forward: shared memory budget exceeded for filters=%d, K=%d (use im2col2d + gemm)", p.N, p.K);
+            return RB200_E_UNSUPPORTED;
+        }
     }
     p.cv_col_blocks = (int)rb_ceil_div(out_w, p.cv_tw);
     p.cv_row_blocks = (int)rb_ceil_div(out_h, p.cv_rows);
     const int64_t tiles = batches * p.cv_row_blocks * p.cv_col_blocks;
-    if (tiles > 0x7fffffffLL) {
+    if (tiles > 0x3fffffffLL) {
         set_error("conv2d_forward: problem too large for 32-bit tile indices");
         return RB200_E_UNSUPPORTED;
     }
     p.num_tiles = (int)tiles;
-    p.raw_slots = SKT_RAW_SLOTS;
-    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT ? 2 : 1;
-    if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) {
-        set_error("conv2d_forward: shared memory budget exceeded for filters=%d, K=%d (use im2col2d + gemm)", p.N, p.K);
-        return RB200_E_UNSUPPORTED;
+    const size_t smem = skt_smem_bytes_ring(planes, p.NP, p.KB, p.epi_groups, p.ring_bytes);
+    CUtensorMap mapC;
+    memset(&mapC, 0, sizeof(mapC));
+    p.tma_store = 0;
+    if (skt_tma_store_enabled() && filters >= 32 && (filters % 4) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+        const uint64_t row = (uint64_t)filters * 4;
+        const uint64_t dims[4] = {(uint64_t)filters, (uint64_t)out_w, (uint64_t)out_h, (uint64_t)batches};
+        const uint64_t strides[3] = {row, row * (uint64_t)out_w, row * (uint64_t)out_w * (uint64_t)out_h};
+        const uint32_t box[4] = {32, (uint32_t)p.cv_tw, (uint32_t)p.cv_rows, 1};
+        p.tma_store = encode_tensor_map_f32(&mapC, out, 4, dims, strides, box, true) == RB200_OK;  // else: plain stores
     }
-    const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, p.raw_slots);
-    static bool configured[3] = {false, false, false};
-    if (!configured[planes]) {
-        if (planes == 1) RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        else             RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        configured[planes] = true;
-    }
-    const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
-    if (planes == 1) gemm_tf32_skinny_kernel<1><<<grid, SKT_THREADS, smem, c.stream>>>(p);
-    else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p);
-    RB_LAUNCH_CHECK("gemm_tf32_skinny_kernel(conv)");
-    c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
+    const int rc = skt_launch(planes, rows_mode, p, tmap, mapC, smem, "gemm_tf32_skinny_kernel(conv)");
+    if (rc != RB200_OK) return rc;
+    if (rows_mode) c.last_gemm_path = planes == 1 ? "tcgen05_tf32_rows_conv" : "tcgen05_tf32x3_rows_conv";
+    else           c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
     return RB200_OK;
 }
 

@@ -92,6 +92,11 @@ def main():
     M = b * oh * ow
     timed("conv_gemm", lambda i: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, f, 27, 1.0, Co, 0, 27, Wk, 0, f,
                                            0.0, Out, 0, f), (M * 27 + 27 * f + M * f) * 4)
+    Outs = [Out, CudaBuffer(b * oh * ow * f, f32, zero=False)]
+    timed("conv2d_fused", lambda i: math.conv2d_forward(Im[i], 0, b, h, w, ch, 3, 3, 1, 1, False, 1, 1, Wk, 0, f, None, 0,
+                                                        Outs[i % 2], 0), (b * h * w * ch + 27 * f + M * f) * 4)
+    if not want or "conv2d_fused" in want:
+        print("conv2d_fused path:", _capi.last_gemm_path(), flush=True)
 
 
 if __name__ == "__main__":
