@@ -89,6 +89,16 @@ __device__ __forceinline__ void sk_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+// 16 lanes x 32 columns: register 4c + 2b + a of lane t = row (t / 4) + 8b, column 8c + 2 (t % 4) + a
+__device__ __forceinline__ void sk_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void sk_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled tile: byte offset of element (row r, column kk < 32)
@@ -151,7 +161,15 @@ struct SktParams {
     int koff[SKT_BK];
     uint32_t ring_bytes;           // bytes of the raw / slab ring
     int tma_store;                 // epilogue stores C tiles with TMA (tmapC: 4-D [.., .., rows, N], 128-byte swizzle)
+    int direct_store;              // epilogue stores straight from the 16x256b TMEM fragments (no shared memory)
+    long long* trace;              // diagnostic (RB200_SKT_TRACE=1): [64 tiles][16 events] SM clock stamps of CTA 0
 };
+
+// event e of this CTA's it-th tile (diagnostic only; one lane of the role's first warp calls it)
+__device__ __forceinline__ void skt_trace(const SktParams& p, int it, int e)
+{
+    if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + e] = clock64();
+}
 
 struct SktTile { int64_t m_start; int nvalid; int b, oy0, ox0; };
 
@@ -240,7 +258,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
         if (PLANES == 2) *reinterpret_cast<float*>(gen + o + (uint32_t)(p.NP * 128)) = v - hi;
     }
     float* bias_s = reinterpret_cast<float*>(gen + off_rinfo + 1024u);         // [NP] bias (or zeros); the cp.async conv producer owns the first 1 KB
-    if (p.tma_store) {
+    if (p.tma_store || p.direct_store) {
         for (int n = threadIdx.x; n < p.NP; n += SKT_THREADS) bias_s[n] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -303,6 +321,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 __syncwarp();
                 const int slot = j % SKT_ROW_SLOTS, n = j / SKT_ROW_SLOTS;
                 sk_mbar_wait(slab_full(g, slot), (uint32_t)(n & 1));
+                if (issuer) skt_trace(p, 2 * j + g, 0);
                 const uint32_t sl = ring_g_addr + (uint32_t)(slot * p.cv_slot_elems + roff) * 4u;
                 float v[SKT_BK];
 #pragma unroll
@@ -317,7 +336,9 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 }
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(slab_empty(g, slot));
+                if (issuer) skt_trace(p, 2 * j + g, 1);
                 sk_mbar_wait(a_empty(g), (uint32_t)((j & 1) ^ 1));
+                if (issuer) skt_trace(p, 2 * j + g, 2);
                 uint8_t* sa = gen + g * a_stage_bytes + (uint32_t)(r << 7);
 #pragma unroll
                 for (int q = 0; q < SKT_BK / 4; q++) {
@@ -340,6 +361,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(a_full(g));
+                if (issuer) skt_trace(p, 2 * j + g, 3);
             }
             (void)stage; (void)phase;
         } else if (p.a_contig && p.KB == 1) {
@@ -596,13 +618,16 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
             const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 2) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int mit = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, mit++) {
                 sk_mbar_wait(t_empty(acc), acc_phase ^ 1);
                 sk_fence_after();
+                if (lane == 0) skt_trace(p, mit, 4);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
                 for (int kb = 0; kb < p.KB; kb++) {
                     sk_mbar_wait(a_full(stage), phase);
                     sk_fence_after();
+                    if (lane == 0) skt_trace(p, mit, 5);
                     const uint32_t sA = base + stage * a_stage_bytes;
                     const uint32_t sB = base + off_b + (uint32_t)kb * (uint32_t)(PLANES * p.NP * 128);
 #pragma unroll
@@ -621,13 +646,72 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                     if (kb == p.KB - 1) sk_commit_elect(t_full(acc));
                     if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (lane == 0) skt_trace(p, mit, 6);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles alternate) =====
         const int g = (warp - SKT_EPI_WARP0) >> 2;
-        if (g < p.epi_groups && p.tma_store) {
+        if (g < p.epi_groups && p.direct_store) {
+            // Direct epilogue: tcgen05.ld.16x256b hands four lanes the 32 contiguous bytes of one row, so a
+            // warp-wide 64-bit store writes eight whole 32-byte sectors -- no shared-memory round trip (the
+            // fused conv is shared-memory-bandwidth bound otherwise).
+            const int q = warp & 3;
+            const int t0 = lane & 3, t1 = lane >> 2;
+            uint32_t acc_phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                if (p.epi_groups == 2 && acc != g) continue;
+                const SktTile ti = skt_tile(p, tile);
+                sk_mbar_wait(t_full(acc), acc_phase);
+                if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
+                sk_fence_after();
+                if (q == 0 && lane == 0) skt_trace(p, it, 8);
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const int rbase = q * 32 + h * 16 + t1;               // this lane's rows: rbase, rbase + 8
+                    float* c0 = p.C + (ti.m_start + rbase) * p.ldC + 2 * t0;
+                    const bool ok0 = rbase < ti.nvalid, ok1 = rbase + 8 < ti.nvalid;
+#pragma unroll 1
+                    for (int cb = 0; cb < p.NP / 32; cb++) {
+                        uint32_t rb_[16];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + h * 16) << 16) + (uint32_t)(acc * ACC_COLS + cb * 32);
+                        sk_ld_16x256b_x4(taddr, rb_);
+                        if (PLANES == 2) {
+                            uint32_t rs[16];
+                            sk_ld_16x256b_x4(taddr + p.NP, rs);
+                            sk_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; e++) rb_[e] = __float_as_uint(__uint_as_float(rb_[e]) + __uint_as_float(rs[e]));
+                        } else {
+                            sk_wait_ld();
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int col = cb * 32 + 8 * c + 2 * t0;
+                            if (col < p.N) {                               // N is even on this path
+                                const float2 bv = *reinterpret_cast<const float2*>(bias_s + col);
+#pragma unroll
+                                for (int b = 0; b < 2; b++) {
+                                    float2 o;
+                                    o.x = fmaf(p.alpha, __uint_as_float(rb_[4 * c + 2 * b]), bv.x);
+                                    o.y = fmaf(p.alpha, __uint_as_float(rb_[4 * c + 2 * b + 1]), bv.y);
+                                    if (b == 0 ? ok0 : ok1) {
+                                        __stcs(reinterpret_cast<float2*>(c0 + (int64_t)(8 * b) * p.ldC + cb * 32 + 8 * c), o);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                sk_fence_before();
+                __syncwarp();
+                if (lane == 0) sk_mbar_arrive(t_empty(acc));
+                if (q == 0 && lane == 0) skt_trace(p, it, 10);
+            }
+        } else if (g < p.epi_groups && p.tma_store) {
             // TMA-store epilogue: TMEM -> registers -> alpha (+ bias) -> 128-byte swizzled staging tile of the
             // group ([NP/32 boxes][128 rows][32 floats]) -> one lane issues cp.async.bulk.tensor stores, which
             // clip ragged tiles (out-of-range rows / columns are not written) and write whole 128-byte lines.
@@ -646,8 +730,10 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 sk_mbar_wait(t_full(acc), acc_phase);
                 if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
                 sk_fence_after();
+                if (leader) skt_trace(p, it, 8);
                 if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
                 asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
+                if (leader) skt_trace(p, it, 9);
                 for (int ch = 0; ch < p.NP / 16; ch++) {
                     uint32_t rr[16];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 16);
@@ -678,6 +764,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 sk_fence_before();
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(t_empty(acc));
+                if (leader) skt_trace(p, it, 10);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
                 if (leader) {
@@ -693,6 +780,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                                "r"(stg + (uint32_t)bx * 16384u) : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    skt_trace(p, it, 11);
                 }
             }
             if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -908,6 +996,8 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
     memset(&none, 0, sizeof(none));
     memset(&mapC, 0, sizeof(mapC));
     p.tma_store = 0;
+    p.direct_store = 0;
+    p.trace = nullptr;
     if (skt_tma_store_enabled() && beta == 0.f && N >= 32 && (N % 4) == 0 && (ldC % 4) == 0 &&
         ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && M <= 0x7fffffffLL) {
         const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
@@ -933,11 +1023,22 @@ bool conv2d_tcgen05_eligible(int mode, int64_t M, int64_t N, int64_t K)
     return skt_smem_bytes(planes, NP, KB, 1, 0) <= SKT_SMEM_LIMIT;
 }
 
+int conv2d_tcgen05_rows(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                        int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                        int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
+                        const float* W, int64_t filters, const float* bias, float* out);
+
 int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
                    int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
                    int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
                    const float* W, int64_t filters, const float* bias, float* out)
 {
+    // short reductions (K <= 32) go to the TMEM-operand kernel (conv_tcgen05_rows.cu) when it takes the shape
+    {
+        const int rc = conv2d_tcgen05_rows(mode, images, batches, im_h, im_w, channels, filter_h, filter_w, stride_h, stride_w,
+                                           dilation_h, dilation_w, pad_h, pad_w, out_h, out_w, W, filters, bias, out);
+        if (rc != RB200_E_UNSUPPORTED) return rc;
+    }
     Context& c = ctx();
     const int planes = mode == RB200_GEMM_TF32X3 ? 2 : 1;
     SktParams p;
@@ -1068,8 +1169,41 @@ int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h,
         const uint32_t box[4] = {32, (uint32_t)p.cv_tw, (uint32_t)p.cv_rows, 1};
         p.tma_store = encode_tensor_map_f32(&mapC, out, 4, dims, strides, box, true) == RB200_OK;  // else: plain stores
     }
+    p.direct_store = 0;
+    {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("RB200_SKT_DIRECT_STORE"); env = (e && e[0] == '0') ? 0 : 1; }
+        if (env && rows_mode && (filters % 2) == 0 && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) {
+            p.direct_store = 1;
+            p.tma_store = 0;
+        }
+    }
+    p.trace = nullptr;
+    static int trace_env = -1;
+    if (trace_env < 0) { const char* e = getenv("RB200_SKT_TRACE"); trace_env = (e && e[0] == '1') ? 1 : 0; }
+    if (trace_env) RB_CUDA(cudaMalloc(&p.trace, 64 * 16 * sizeof(long long)));
+    if (p.trace) RB_CUDA(cudaMemsetAsync(p.trace, 0, 64 * 16 * sizeof(long long), c.stream));
     const int rc = skt_launch(planes, rows_mode, p, tmap, mapC, smem, "gemm_tf32_skinny_kernel(conv)");
     if (rc != RB200_OK) return rc;
+    if (p.trace) {
+        // diagnostic dump: per tile of CTA 0, event stamps relative to the first one (SM clocks)
+        static long long host[64 * 16];
+        RB_CUDA(cudaStreamSynchronize(c.stream));
+        RB_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+        RB_CUDA(cudaFree(p.trace));
+        long long t0 = 0;
+        for (int i = 0; i < 64 * 16; i++) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
+        fprintf(stderr, "skt trace (CTA 0): tile | slab lds a_empty a_full | t_empty a_full issued | t_full stg_free tmem_rel store\n");
+        for (int it = 0; it < 64; it++) {
+            fprintf(stderr, "%3d |", it);
+            for (int e = 0; e < 12; e++) {
+                if (e == 4 || e == 8) fprintf(stderr, " |");
+                if (e == 7) continue;
+                fprintf(stderr, " %7lld", host[it * 16 + e] ? host[it * 16 + e] - t0 : -1LL);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     if (rows_mode) c.last_gemm_path = planes == 1 ? "tcgen05_tf32_rows_conv" : "tcgen05_tf32x3_rows_conv";
     else           c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
     return RB200_OK;

@@ -45,6 +45,13 @@ def main():
     As = [rnd(m * n) for _ in range(3)]
     Y2 = rnd(m * n)
     X, Xm, Yn, Ym = rnd(n), rnd(m), CudaBuffer(n, f32), CudaBuffer(m, f32)
+    timed("fill", lambda i: math.zeros(m * n, As[i], 0, 1), m * n * 4)
+    if not want or "torch_zero" in want:
+        tz = [torch.empty(m * n, dtype=torch.float32, device="cuda") for _ in range(3)]
+        with torch.cuda.stream(stream):
+            timed("torch_zero", lambda i: tz[i].zero_(), m * n * 4)
+            timed("torch_copy", lambda i: tz[(i + 1) % 3].copy_(tz[i]), 2 * m * n * 4)
+        del tz
     timed("copy", lambda i: blas.copy(m * n, As[i], 0, 1, Y2, 0, 1), 2 * m * n * 4)
     timed("axpy", lambda i: blas.axpy(m * n, 0.5, As[i], 0, 1, Y2, 0, 1), 3 * m * n * 4)
     timed("transpose", lambda i: blas.omatcopy(BLAS.RowMajor, BLAS.Trans, m, n, 1.0, As[i], 0, n, Y2, 0, m), 2 * m * n * 4)

@@ -11,7 +11,7 @@ for op in $OPS; do
       sgemm_tf32) K="-k regex:gemm_tf32"; C=1;;
       sgemm_tf32x3) K="-k regex:gemm_tf32"; C=1;;
       conv_gemm) K="-k regex:skinny"; C=1;;
-      conv2d_fused) K="-k regex:skinny"; C=1;;
+      conv2d_fused) K="-k regex:conv_rows"; C=1;;
       maximum) K="-k regex:ew_vec"; C=1;;
       exp) K="-k regex:unary_vec"; C=1;;
       astype) K="-k regex:astype"; C=1;;
