@@ -194,7 +194,6 @@ struct CrParams {
     int cv_box_start[CR_MAX_BOXES];
     int koff[CR_BK];
     uint32_t off_stg, off_ring, off_misc;   // shared-memory layout (bytes from the 1024-aligned base)
-    int dbg;                       // experiments (RB200_CR_DBG)
     int trace_t0;                  // first traced tile of CTA 0 (RB200_SKT_TRACE_T0)
     long long* trace;              // diagnostic (RB200_SKT_TRACE=1): [64 tiles][16 events] SM clock stamps of CTA 0
 };
@@ -289,7 +288,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
             float v[CR_BK];
 #pragma unroll
             for (int q = 0; q < CR_BK / 4; q++) {
-                if (4 * q < p.K && !(p.dbg & 16)) {                                       // koff[k >= K] repeats koff[0]: a valid address
+                if (4 * q < p.K) {                                       // koff[k >= K] repeats koff[0]: a valid address
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[4 * q + i] = cr_lds(sl + (uint32_t)p.koff[4 * q + i]);
                     if (q == kq_last) {                                  // the chunk K ends in: zero its tail
@@ -309,7 +308,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
             cr_fence_after();
             if (TRACE && issuer) cr_trace(p, 2 * j + g, 2);
 #pragma unroll
-            for (int h = 0; h < ((p.dbg & 16) ? 0 : 2); h++) {
+            for (int h = 0; h < 2; h++) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
@@ -349,7 +348,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
             const uint32_t tmem_a = tmem_base + a_col0 + (uint32_t)(stage * PLANES * CR_BK);
 #pragma unroll
             for (int kk = 0; kk < CR_BK / 8; kk++) {
-                if (kk < ksteps && !(p.dbg & 32)) {
+                if (kk < ksteps) {
                     // 3xTF32 goes into ONE accumulator: with K <= 32 a tile sees at most 12 accumulation steps, so the
                     // truncating TMEM adds cost ~3e-7 relative -- not worth a second accumulator (half the TMEM loads
                     // and no big + small add in the epilogue)
@@ -391,7 +390,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
                 // 64 columns at a time: both TMEM loads in flight, one wait, then sixteen 128-bit stores whose
                 // swizzled offsets are per-thread constants
 #pragma unroll 1
-                for (int c64 = 0; c64 < ((p.dbg & 8) ? 0 : p.NP); c64 += 64) {
+                for (int c64 = 0; c64 < p.NP; c64 += 64) {
                     const bool two = c64 + 32 < p.NP;
                     uint32_t ra[32], rb[32];
                     cr_ld32(tacc + (uint32_t)c64, ra);
@@ -456,7 +455,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
                 // pull the slab of a tile CR_PREFETCH steps ahead into L2 with plain prefetches: a TMA load that waits
                 // on DRAM holds up the TMA stores queued behind it (measured: 0.122 -> 0.155 ms for config C4)
                 const int64_t pt = (int64_t)tile + (int64_t)(2 * CR_PREFETCH) * step;
-                if (pt < p.num_tiles && !(p.dbg & 128)) {
+                if (pt < p.num_tiles) {
                     const int ptile = (int)pt;
                     const int pb = ptile / per_img, pq = ptile - pb * per_img;
                     const int prb = pq / p.cv_col_blocks, pcb = pq - prb * p.cv_col_blocks;
@@ -481,7 +480,6 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
             const int x = (cb * p.cv_tw * p.str_w - p.pad_w) * p.chan - p.cv_xshift;      // multiple of 4 floats
             const int y = rb * p.cv_rows * p.str_h - p.pad_h;
             const uint32_t bar_f = slab_full(g, slot);
-            if (p.dbg & 64) { cr_arrive_elect(bar_f); continue; }
             cr_expect_tx_elect(bar_f, slot_tx);
             const uint32_t dst = ring_g + (uint32_t)(slot * p.cv_slot_elems) * 4u;
 #pragma unroll 1
@@ -506,7 +504,7 @@ conv_rows_kernel(const __grid_constant__ CrParams p, const __grid_constant__ CUt
             cr_mbar_wait(stg_full(ge, sb), (uint32_t)(use & 1));
             const uint32_t stg = base + p.off_stg + (uint32_t)(ge * p.stg_bufs + sb) * stg_tile;
 #pragma unroll 1
-            for (int bx = 0; bx < ((p.dbg & 4) ? 0 : nbx); bx++) {
+            for (int bx = 0; bx < nbx; bx++) {
                 cr_tma_store4_elect(&tmapO, stg + (uint32_t)bx * 16384u, bx * 32, cbk * p.cv_tw, rbk * p.cv_rows, b);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -650,7 +648,6 @@ int conv2d_tcgen05_rows(int mode, const float* images, int64_t batches, int64_t 
         RB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_LIMIT));
         configured = true;
     }
-    { const char* e = getenv("RB200_CR_DBG"); p.dbg = e ? atoi(e) : 0; }
     static int trace_env = -1;
     if (trace_env < 0) { const char* e = getenv("RB200_SKT_TRACE"); trace_env = (e && e[0] == '1') ? 1 : 0; }
     if (trace_env) {
@@ -676,15 +673,16 @@ int conv2d_tcgen05_rows(int mode, const float* images, int64_t batches, int64_t 
         RB_CUDA(cudaFree(p.trace));
         long long t0 = 0;
         for (int i = 0; i < 64 * 16; i++) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
-        fprintf(stderr, "conv rows trace (CTA 0): tile | slab lds a_empty a_full | t_empty a_full issued | ep_top t_full stg_free ch0_data ch1_data loop_end proxy_fence arrive store_committed\n");
-        static const int order[16] = {0, 1, 2, 3, -1, 4, 5, 6, -1, 13, 8, 9, 12, 7, 14, 15};
+        fprintf(stderr, "conv rows trace (CTA 0): tile | producers: slab_ready lds_done a_empty_ok a_full_arrive | mma: t_empty_ok a_full_ok issued | "
+                        "epilogue: top t_full_ok stg_free staged proxy_fence arrive | store_committed\n");
+        static const int order[14] = {0, 1, 2, 3, -1, 4, 5, 6, -1, 13, 8, 9, 14, 15};
         for (int it = 0; it < 64; it++) {
-            fprintf(stderr, "%3d |", it);
-            for (int i = 0; i < 16; i++) {
+            fprintf(stderr, "%3d |", it + p.trace_t0);
+            for (int i = 0; i < 14; i++) {
                 if (order[i] < 0) { fprintf(stderr, " |"); continue; }
                 fprintf(stderr, " %7lld", host[it * 16 + order[i]] ? host[it * 16 + order[i]] - t0 : -1LL);
             }
-            fprintf(stderr, " %7lld %7lld\n", host[it * 16 + 10] ? host[it * 16 + 10] - t0 : -1LL, host[it * 16 + 11] ? host[it * 16 + 11] - t0 : -1LL);
+            fprintf(stderr, " %7lld | %7lld\n", host[it * 16 + 10] ? host[it * 16 + 10] - t0 : -1LL, host[it * 16 + 11] ? host[it * 16 + 11] - t0 : -1LL);
         }
     }
     return RB200_OK;

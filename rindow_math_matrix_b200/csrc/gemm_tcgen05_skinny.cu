@@ -13,10 +13,15 @@
 // Persistent CTA per SM, 544 threads:
 //   warps 0-7 : producers -- coalesced global loads of the A tile (128 rows x 32 k), software 128-byte
 //               swizzle into the K-major UMMA layout, fence.proxy.async, mbarrier arrive (2 stages)
-//   warp  8   : MMA issuer (one lane): tcgen05.mma M=128, N=NP, K=8; commits free A stages / publish TMEM
+//   warp  8   : MMA issuer -- the whole warp runs the loop, one elected lane issues tcgen05.mma M=128, K=8
+//               (3xTF32: A_hi x [B_hi | B_lo] with N = 2*NP, then A_lo x B_hi); commits free A stages / publish TMEM
 //   warps 9-16: epilogue, two groups of four (group g drains accumulator stage g, tiles alternate) --
-//               tcgen05.ld -> registers -> shared-memory transpose -> coalesced 128-bit stores
-// B (K x N, tiny) is staged once per CTA, transposed to K-major, all k-blocks resident.
+//               tcgen05.ld -> registers -> 128-byte swizzled staging tile -> TMA store (whole 128-byte lines,
+//               ragged tiles clipped by the tensor map); unaligned C / beta != 0 / N < 32 take a shared-memory
+//               transpose with plain 128-bit stores instead
+// B (K x N, tiny) is staged once per CTA, transposed to K-major, all k-blocks resident ([k-block][plane][n]).
+// The fused conv2d entry lives here for K in (32, 128] (cp.async slab ring + per-k gather); K <= 32 goes to
+// conv_tcgen05_rows.cu, which keeps A in tensor memory.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -37,8 +42,6 @@ constexpr int SKT_PREFETCH = 3;                      // raw A tiles in flight ah
 constexpr int SKT_RAW_SLOTS = SKT_PREFETCH + 1;
 constexpr int SKT_RAW_STAGE = SKT_BM * SKT_BK * 4;   // 16 KB
 constexpr int SKT_SMEM_LIMIT = 226 * 1024;
-constexpr int SKT_MAX_BOXES = 8;
-constexpr int SKT_ROW_SLOTS = 3;                     // slab slots per producer group of the conv row producer
 
 __device__ __forceinline__ uint32_t sk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sk_mbar_init(uint32_t bar, uint32_t count)
@@ -89,16 +92,6 @@ __device__ __forceinline__ void sk_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
-// 16 lanes x 32 columns: register 4c + 2b + a of lane t = row (t / 4) + 8b, column 8c + 2 (t % 4) + a
-__device__ __forceinline__ void sk_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void sk_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled tile: byte offset of element (row r, column kk < 32)
@@ -122,13 +115,6 @@ __device__ __forceinline__ float sk_rna(float x)
 {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
-__device__ __forceinline__ float sk_lds(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-
 struct SktParams {
     int64_t M;
     int N, K, NP, KB;              // NP = N rounded up to 32, KB = ceil(K / 32)
@@ -151,25 +137,9 @@ struct SktParams {
     // always one contiguous run of rows of the [B*oh*ow, N] output); its input slab is staged in smem
     int cv_tw, cv_rows, cv_col_blocks, cv_row_blocks;
     int cv_slab_rows, cv_width_x, cv_row_elems, cv_slab_elems;
-    // row producer (conv == 2, K <= 32): the slab arrives by TMA as cv_nbox boxes of cv_bw floats x
-    // cv_slab_rows rows (zero filled outside the image); box i starts cv_box_start[i] floats into the slab
-    // row, every cell's run of (filt_w-1)*dil_w*chan + chan floats lies inside one box; column k of the
-    // virtual cols row sits koff[k] bytes after the cell's run origin
-    int cv_nbox, cv_bw, cv_box_elems, cv_slot_elems;
-    int cv_xshift;                 // floats the slab origin is moved left so that every TMA x coordinate is a multiple of 4
-    int cv_box_start[SKT_MAX_BOXES];
-    int koff[SKT_BK];
     uint32_t ring_bytes;           // bytes of the raw / slab ring
     int tma_store;                 // epilogue stores C tiles with TMA (tmapC: 4-D [.., .., rows, N], 128-byte swizzle)
-    int direct_store;              // epilogue stores straight from the 16x256b TMEM fragments (no shared memory)
-    long long* trace;              // diagnostic (RB200_SKT_TRACE=1): [64 tiles][16 events] SM clock stamps of CTA 0
 };
-
-// event e of this CTA's it-th tile (diagnostic only; one lane of the role's first warp calls it)
-__device__ __forceinline__ void skt_trace(const SktParams& p, int it, int e)
-{
-    if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + e] = clock64();
-}
 
 struct SktTile { int64_t m_start; int nvalid; int b, oy0, ox0; };
 
@@ -195,10 +165,9 @@ __device__ __forceinline__ SktTile skt_tile(const SktParams& p, int tile)
     return t;
 }
 
-template <int PLANES, bool ROWS>
+template <int PLANES>
 __global__ void __launch_bounds__(SKT_THREADS, 1)
-gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_constant__ CUtensorMap tmap,
-                        const __grid_constant__ CUtensorMap tmapC)
+gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_constant__ CUtensorMap tmapC)
 {
     extern __shared__ uint8_t skt_raw[];
     const uint32_t base = (sk_smem_u32(skt_raw) + 1023u) & ~1023u;
@@ -218,21 +187,13 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
     auto t_full  = [&](int a) { return bar + 8u * (2 * SKT_STAGES + a); };
     auto t_empty = [&](int a) { return bar + 8u * (2 * SKT_STAGES + 2 + a); };
     const uint32_t tmem_slot = bar + 8u * (2 * SKT_STAGES + 4);
-    // row producer: slab barriers live in the (otherwise unused) row-info area
-    auto slab_full  = [&](int g, int s) { return base + off_rinfo + 8u * (uint32_t)(g * SKT_ROW_SLOTS + s); };
-    auto slab_empty = [&](int g, int s) { return base + off_rinfo + 8u * (uint32_t)(2 * SKT_ROW_SLOTS + g * SKT_ROW_SLOTS + s); };
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ACC_COLS = PLANES * p.NP;
 
     if (warp == SKT_MMA_WARP && lane == 0) {
-        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), ROWS ? 4 : SKT_PROD_WARPS); sk_mbar_init(a_empty(s), 1); }
-        if (ROWS) {
-            for (int g = 0; g < 2; g++) {
-                for (int s = 0; s < SKT_ROW_SLOTS; s++) { sk_mbar_init(slab_full(g, s), 1); sk_mbar_init(slab_empty(g, s), 4); }
-            }
-        }
+        for (int s = 0; s < SKT_STAGES; s++) { sk_mbar_init(a_full(s), SKT_PROD_WARPS); sk_mbar_init(a_empty(s), 1); }
         for (int a = 0; a < 2; a++) { sk_mbar_init(t_full(a), 1); sk_mbar_init(t_empty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,7 +219,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
         if (PLANES == 2) *reinterpret_cast<float*>(gen + o + (uint32_t)(p.NP * 128)) = v - hi;
     }
     float* bias_s = reinterpret_cast<float*>(gen + off_rinfo + 1024u);         // [NP] bias (or zeros); the cp.async conv producer owns the first 1 KB
-    if (p.tma_store || p.direct_store) {
+    if (p.tma_store) {
         for (int n = threadIdx.x; n < p.NP; n += SKT_THREADS) bias_s[n] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -271,100 +232,7 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
         // ===== producers =====
         const int t = threadIdx.x;                                    // 0..SKT_PRODUCERS-1
         int stage = 0; uint32_t phase = 0;
-        if constexpr (ROWS) {
-            // Implicit GEMM, K <= 32, one thread per cols row.  Two groups of four warps; group g builds the
-            // tiles of parity g into A stage g, so two tiles are always under construction.  The input slab
-            // of a tile (zero padded by TMA's out-of-bounds fill) arrives in a per-group ring of
-            // SKT_ROW_SLOTS slots, requested two tiles ahead by one lane of the group.  A thread reads the
-            // K floats of its row with LDS.32 (lane stride = str_w*chan floats: conflict free when odd),
-            // splits them in registers and writes whole 16-byte chunks of the swizzled A row.
-            const int g = warp >> 2;
-            const int r = t & (SKT_BM - 1);
-            int rr = p.cv_rows > 1 ? r / p.cv_tw : 0;
-            int cc = r - rr * p.cv_tw;
-            if (r >= p.cv_rows * p.cv_tw) { rr = 0; cc = 0; }             // never-stored rows: stay inside the slab
-            const int x0 = cc * p.str_w * p.chan + p.cv_xshift;
-            int bi = 0;
-            for (int i = 1; i < p.cv_nbox; i++) { if (p.cv_box_start[i] <= x0) bi = i; }
-            const int roff = bi * p.cv_box_elems + rr * p.str_h * p.cv_bw + (x0 - p.cv_box_start[bi]);
-            const uint32_t ring_g_addr = base + off_raw + (uint32_t)(g * SKT_ROW_SLOTS * p.cv_slot_elems) * 4u;
-            const int step = gridDim.x;
-            const int per_img = p.cv_row_blocks * p.cv_col_blocks;
-            const bool issuer = (warp & 3) == 0 && lane == 0;
-            const uint32_t slot_tx = (uint32_t)(p.cv_nbox * p.cv_bw * p.cv_slab_rows) * 4u;
-            auto issue = [&](int jj) {
-                const int64_t tile64 = (int64_t)blockIdx.x + (int64_t)(2 * jj + g) * step;
-                if (tile64 >= p.num_tiles) return;
-                const int tile = (int)tile64;
-                const int slot = jj % SKT_ROW_SLOTS, n = jj / SKT_ROW_SLOTS;
-                if (n > 0) sk_mbar_wait(slab_empty(g, slot), (uint32_t)((n & 1) ^ 1));
-                const int b = tile / per_img, q = tile - b * per_img;
-                const int rb = q / p.cv_col_blocks, cb = q - rb * p.cv_col_blocks;
-                const int x = (cb * p.cv_tw * p.str_w - p.pad_w) * p.chan - p.cv_xshift;   // multiple of 4 floats
-                const int y = rb * p.cv_rows * p.str_h - p.pad_h;
-                const uint32_t bar_f = slab_full(g, slot);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_f), "r"(slot_tx) : "memory");
-                const uint32_t dst = ring_g_addr + (uint32_t)(slot * p.cv_slot_elems) * 4u;
-#pragma unroll 1
-                for (int i = 0; i < p.cv_nbox; i++) {
-                    asm volatile(
-                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                        :: "r"(dst + (uint32_t)(i * p.cv_box_elems) * 4u), "l"(reinterpret_cast<uint64_t>(&tmap)),
-                           "r"(x + p.cv_box_start[i]), "r"(y), "r"(b), "r"(bar_f) : "memory");
-                }
-            };
-            if (issuer) { issue(0); issue(1); }
-            const uint32_t swr = (uint32_t)(r & 7);
-            const int kq_last = (p.K - 1) >> 2;
-            for (int j = 0; (int64_t)blockIdx.x + (int64_t)(2 * j + g) * step < p.num_tiles; j++) {
-                if (issuer) issue(j + 2);
-                __syncwarp();
-                const int slot = j % SKT_ROW_SLOTS, n = j / SKT_ROW_SLOTS;
-                sk_mbar_wait(slab_full(g, slot), (uint32_t)(n & 1));
-                if (issuer) skt_trace(p, 2 * j + g, 0);
-                const uint32_t sl = ring_g_addr + (uint32_t)(slot * p.cv_slot_elems + roff) * 4u;
-                float v[SKT_BK];
-#pragma unroll
-                for (int q = 0; q < SKT_BK / 4; q++) {
-                    if (4 * q < p.K) {                                   // koff[k >= K] repeats koff[0]: a valid address
-#pragma unroll
-                        for (int i = 0; i < 4; i++) v[4 * q + i] = sk_lds(sl + (uint32_t)p.koff[4 * q + i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) v[4 * q + i] = 0.f;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) sk_mbar_arrive(slab_empty(g, slot));
-                if (issuer) skt_trace(p, 2 * j + g, 1);
-                sk_mbar_wait(a_empty(g), (uint32_t)((j & 1) ^ 1));
-                if (issuer) skt_trace(p, 2 * j + g, 2);
-                uint8_t* sa = gen + g * a_stage_bytes + (uint32_t)(r << 7);
-#pragma unroll
-                for (int q = 0; q < SKT_BK / 4; q++) {
-                    if (4 * q < p.K) {
-                        if (q == kq_last) {                              // the chunk K ends in: zero its tail
-                            if (4 * q + 1 >= p.K) v[4 * q + 1] = 0.f;
-                            if (4 * q + 2 >= p.K) v[4 * q + 2] = 0.f;
-                            if (4 * q + 3 >= p.K) v[4 * q + 3] = 0.f;
-                        }
-                        float4 hi, lo;
-                        hi.x = sk_rna(v[4 * q]);     lo.x = v[4 * q] - hi.x;
-                        hi.y = sk_rna(v[4 * q + 1]); lo.y = v[4 * q + 1] - hi.y;
-                        hi.z = sk_rna(v[4 * q + 2]); lo.z = v[4 * q + 2] - hi.z;
-                        hi.w = sk_rna(v[4 * q + 3]); lo.w = v[4 * q + 3] - hi.w;
-                        const uint32_t o = ((uint32_t)q ^ swr) << 4;
-                        *reinterpret_cast<float4*>(sa + o) = hi;
-                        if (PLANES == 2) *reinterpret_cast<float4*>(sa + SKT_A_TILE + o) = lo;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) sk_mbar_arrive(a_full(g));
-                if (issuer) skt_trace(p, 2 * j + g, 3);
-            }
-            (void)stage; (void)phase;
-        } else if (p.a_contig && p.KB == 1) {
+        if (p.a_contig && p.KB == 1) {
             // Each 128-row tile is rows*K contiguous floats.  They are brought into a raw shared-memory
             // ring with 16-byte cp.async copies issued SKT_PREFETCH tiles ahead (each thread later reads
             // back exactly the chunks it copied, so cp.async.wait_group is the only synchronisation), then
@@ -618,16 +486,13 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
             const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 2) << 17) | ((uint32_t)(SKT_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            int mit = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, mit++) {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 sk_mbar_wait(t_empty(acc), acc_phase ^ 1);
                 sk_fence_after();
-                if (lane == 0) skt_trace(p, mit, 4);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
                 for (int kb = 0; kb < p.KB; kb++) {
                     sk_mbar_wait(a_full(stage), phase);
                     sk_fence_after();
-                    if (lane == 0) skt_trace(p, mit, 5);
                     const uint32_t sA = base + stage * a_stage_bytes;
                     const uint32_t sB = base + off_b + (uint32_t)kb * (uint32_t)(PLANES * p.NP * 128);
 #pragma unroll
@@ -646,72 +511,13 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                     if (kb == p.KB - 1) sk_commit_elect(t_full(acc));
                     if (++stage == SKT_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (lane == 0) skt_trace(p, mit, 6);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles alternate) =====
         const int g = (warp - SKT_EPI_WARP0) >> 2;
-        if (g < p.epi_groups && p.direct_store) {
-            // Direct epilogue: tcgen05.ld.16x256b hands four lanes the 32 contiguous bytes of one row, so a
-            // warp-wide 64-bit store writes eight whole 32-byte sectors -- no shared-memory round trip (the
-            // fused conv is shared-memory-bandwidth bound otherwise).
-            const int q = warp & 3;
-            const int t0 = lane & 3, t1 = lane >> 2;
-            uint32_t acc_phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
-                const int acc = it & 1;
-                if (p.epi_groups == 2 && acc != g) continue;
-                const SktTile ti = skt_tile(p, tile);
-                sk_mbar_wait(t_full(acc), acc_phase);
-                if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
-                sk_fence_after();
-                if (q == 0 && lane == 0) skt_trace(p, it, 8);
-#pragma unroll 1
-                for (int h = 0; h < 2; h++) {
-                    const int rbase = q * 32 + h * 16 + t1;               // this lane's rows: rbase, rbase + 8
-                    float* c0 = p.C + (ti.m_start + rbase) * p.ldC + 2 * t0;
-                    const bool ok0 = rbase < ti.nvalid, ok1 = rbase + 8 < ti.nvalid;
-#pragma unroll 1
-                    for (int cb = 0; cb < p.NP / 32; cb++) {
-                        uint32_t rb_[16];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + h * 16) << 16) + (uint32_t)(acc * ACC_COLS + cb * 32);
-                        sk_ld_16x256b_x4(taddr, rb_);
-                        if (PLANES == 2) {
-                            uint32_t rs[16];
-                            sk_ld_16x256b_x4(taddr + p.NP, rs);
-                            sk_wait_ld();
-#pragma unroll
-                            for (int e = 0; e < 16; e++) rb_[e] = __float_as_uint(__uint_as_float(rb_[e]) + __uint_as_float(rs[e]));
-                        } else {
-                            sk_wait_ld();
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const int col = cb * 32 + 8 * c + 2 * t0;
-                            if (col < p.N) {                               // N is even on this path
-                                const float2 bv = *reinterpret_cast<const float2*>(bias_s + col);
-#pragma unroll
-                                for (int b = 0; b < 2; b++) {
-                                    float2 o;
-                                    o.x = fmaf(p.alpha, __uint_as_float(rb_[4 * c + 2 * b]), bv.x);
-                                    o.y = fmaf(p.alpha, __uint_as_float(rb_[4 * c + 2 * b + 1]), bv.y);
-                                    if (b == 0 ? ok0 : ok1) {
-                                        __stcs(reinterpret_cast<float2*>(c0 + (int64_t)(8 * b) * p.ldC + cb * 32 + 8 * c), o);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                sk_fence_before();
-                __syncwarp();
-                if (lane == 0) sk_mbar_arrive(t_empty(acc));
-                if (q == 0 && lane == 0) skt_trace(p, it, 10);
-            }
-        } else if (g < p.epi_groups && p.tma_store) {
+        if (g < p.epi_groups && p.tma_store) {
             // TMA-store epilogue: TMEM -> registers -> alpha (+ bias) -> 128-byte swizzled staging tile of the
             // group ([NP/32 boxes][128 rows][32 floats]) -> one lane issues cp.async.bulk.tensor stores, which
             // clip ragged tiles (out-of-range rows / columns are not written) and write whole 128-byte lines.
@@ -730,10 +536,8 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 sk_mbar_wait(t_full(acc), acc_phase);
                 if (p.epi_groups == 2 || acc == 1) acc_phase ^= 1;
                 sk_fence_after();
-                if (leader) skt_trace(p, it, 8);
                 if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
                 asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
-                if (leader) skt_trace(p, it, 9);
                 for (int ch = 0; ch < p.NP / 16; ch++) {
                     uint32_t rr[16];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 16);
@@ -764,7 +568,6 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                 sk_fence_before();
                 __syncwarp();
                 if (lane == 0) sk_mbar_arrive(t_empty(acc));
-                if (leader) skt_trace(p, it, 10);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");
                 if (leader) {
@@ -780,7 +583,6 @@ gemm_tf32_skinny_kernel(const __grid_constant__ SktParams p, const __grid_consta
                                "r"(stg + (uint32_t)bx * 16384u) : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    skt_trace(p, it, 11);
                 }
             }
             if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -917,27 +719,19 @@ bool skt_tma_store_enabled()
     return env != 0;
 }
 
-// one launcher for every producer variant (the tensor map is only read by the conv row producer)
-int skt_launch(int planes, bool rows, const SktParams& p, const CUtensorMap& tmap, const CUtensorMap& tmapC, size_t smem,
-               const char* name)
+// one launcher for the GEMM and the conv producers
+int skt_launch(int planes, const SktParams& p, const CUtensorMap& tmapC, size_t smem, const char* name)
 {
     rb200::Context& c = rb200::ctx();
     static bool configured = false;
     if (!configured) {
-        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
-        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
+        RB_CUDA(cudaFuncSetAttribute(gemm_tf32_skinny_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKT_SMEM_LIMIT));
         configured = true;
     }
     const int grid = p.num_tiles < c.sm_count ? p.num_tiles : c.sm_count;
-    if (rows) {
-        if (planes == 1) gemm_tf32_skinny_kernel<1, true><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
-        else             gemm_tf32_skinny_kernel<2, true><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
-    } else {
-        if (planes == 1) gemm_tf32_skinny_kernel<1, false><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
-        else             gemm_tf32_skinny_kernel<2, false><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmap, tmapC);
-    }
+    if (planes == 1) gemm_tf32_skinny_kernel<1><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmapC);
+    else             gemm_tf32_skinny_kernel<2><<<grid, SKT_THREADS, smem, c.stream>>>(p, tmapC);
     RB_LAUNCH_CHECK(name);
     return RB200_OK;
 }
@@ -989,15 +783,9 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
     }
     const size_t smem = skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, p.raw_slots);
     p.ring_bytes = (uint32_t)p.raw_slots * SKT_RAW_STAGE;
-    p.cv_nbox = p.cv_bw = p.cv_box_elems = p.cv_slot_elems = p.cv_xshift = 0;
-    memset(p.cv_box_start, 0, sizeof(p.cv_box_start));
-    memset(p.koff, 0, sizeof(p.koff));
-    CUtensorMap none, mapC;
-    memset(&none, 0, sizeof(none));
+    CUtensorMap mapC;
     memset(&mapC, 0, sizeof(mapC));
     p.tma_store = 0;
-    p.direct_store = 0;
-    p.trace = nullptr;
     if (skt_tma_store_enabled() && beta == 0.f && N >= 32 && (N % 4) == 0 && (ldC % 4) == 0 &&
         ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && M <= 0x7fffffffLL) {
         const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
@@ -1005,7 +793,7 @@ int gemm_tcgen05_skinny(int mode, int64_t M, int64_t N, int64_t K, float alpha, 
         const uint32_t box[4] = {32, SKT_BM, 1, 1};
         p.tma_store = encode_tensor_map_f32(&mapC, C, 4, dims, strides, box, true) == RB200_OK;    // else: plain stores
     }
-    const int rc = skt_launch(planes, false, p, none, mapC, smem, "gemm_tf32_skinny_kernel");
+    const int rc = skt_launch(planes, p, mapC, smem, "gemm_tf32_skinny_kernel");
     if (rc != RB200_OK) return rc;
     c.last_gemm_path = planes == 1 ? "tcgen05_tf32_skinny" : "tcgen05_tf32x3_skinny";
     return RB200_OK;
@@ -1059,96 +847,28 @@ int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h,
     p.im_h = (int)im_h; p.im_w = (int)im_w; p.chan = (int)channels; p.filt_w = (int)filter_w;
     p.str_h = (int)stride_h; p.str_w = (int)stride_w; p.dil_h = (int)dilation_h; p.dil_w = (int)dilation_w;
     p.pad_h = (int)pad_h; p.pad_w = (int)pad_w; p.out_h = (int)out_h; p.out_w = (int)out_w;
-    p.cv_nbox = p.cv_bw = p.cv_box_elems = p.cv_slot_elems = p.cv_xshift = 0;
-    memset(p.cv_box_start, 0, sizeof(p.cv_box_start));
-    memset(p.koff, 0, sizeof(p.koff));
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
     // tiling: <= 128 cells per MMA tile, as a block of out columns of one out row (wide images) or as
     // several whole out rows (narrow feature maps)
     if (out_w >= SKT_BM) { p.cv_tw = SKT_BM; p.cv_rows = 1; }
     else { p.cv_tw = (int)out_w; p.cv_rows = (int)(SKT_BM / out_w); if (p.cv_rows > out_h) p.cv_rows = (int)out_h; }
-    const int tw0 = p.cv_tw, rows0 = p.cv_rows;
-
-    // ---- row producer (K <= 32, TMA slabs): the first-layer shapes (3x3x3, 5x5x1, ...) ----
-    bool rows_mode = false;
-    {
-        static int env = -1;
-        if (env < 0) { const char* e = getenv("RB200_CONV_ROWS"); env = (e && e[0] == '0') ? 0 : 1; }
-        const int64_t row_floats = im_w * channels;
-        const int run = (int)((filter_w - 1) * dilation_w * channels + channels);
-        auto gcd32 = [](int64_t v) { int g = 1; while (g < 32 && (v % (2 * g)) == 0) g *= 2; return g; };
-        const bool ok = env && p.KB == 1 && (row_floats % 4) == 0 && ((reinterpret_cast<uintptr_t>(images) & 15) == 0) &&
-                        run <= 256 && gcd32(stride_w * channels) <= 2 && im_h <= 0x7fffffffLL && batches <= 0x7fffffffLL;
-        if (ok) {
-            p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
-            p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
-            p.cv_row_elems = p.cv_width_x * p.chan;
-            p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
-            // TMA wants 16-byte aligned box origins: the slab starts cv_xshift floats left of the tile's first
-            // input column (the same shift for every tile: several column blocks only occur with cv_tw = 128)
-            // and boxes start at multiples of 4 floats
-            p.cv_xshift = (int)((((-pad_w * channels) % 4) + 4) % 4);
-            p.cv_row_elems += p.cv_xshift;
-            p.cv_bw = p.cv_row_elems >= 256 ? 256 : (p.cv_row_elems + 3) / 4 * 4;
-            int nbox = 1;
-            bool fits = p.cv_slab_rows <= 256 && run + 3 <= p.cv_bw;
-            p.cv_box_start[0] = 0;
-            for (int cc = 0; cc < p.cv_tw && fits; cc++) {
-                const int x0 = cc * p.str_w * p.chan + p.cv_xshift;
-                if (x0 + run > p.cv_box_start[nbox - 1] + p.cv_bw) {
-                    if (nbox == SKT_MAX_BOXES) { fits = false; break; }
-                    p.cv_box_start[nbox++] = x0 / 4 * 4;
-                }
-            }
-            p.cv_nbox = nbox;
-            p.cv_box_elems = (p.cv_bw * p.cv_slab_rows + 31) / 32 * 32;
-            p.cv_slot_elems = nbox * p.cv_box_elems;
-            const size_t ring = (size_t)2 * SKT_ROW_SLOTS * p.cv_slot_elems * 4;
-            if (fits) {
-                p.epi_groups = skt_smem_bytes_ring(planes, p.NP, p.KB, 2, ring) <= SKT_SMEM_LIMIT ? 2 : 1;
-                fits = skt_smem_bytes_ring(planes, p.NP, p.KB, p.epi_groups, ring) <= SKT_SMEM_LIMIT;
-            }
-            if (fits) {
-                for (int k = 0; k < p.K; k++) {
-                    const int kwc = (int)(filter_w * channels);
-                    const int ky = k / kwc, rem = k - ky * kwc, kx = rem / p.chan, ch = rem - kx * p.chan;
-                    p.koff[k] = (ky * p.dil_h * p.cv_bw + kx * p.dil_w * p.chan + ch) * 4;      // bytes
-                }
-                for (int k = p.K; k < SKT_BK; k++) p.koff[k] = p.koff[0];
-                const uint64_t dims[3] = {(uint64_t)row_floats, (uint64_t)im_h, (uint64_t)batches};
-                const uint64_t strides[2] = {(uint64_t)row_floats * 4, (uint64_t)row_floats * 4 * (uint64_t)im_h};
-                const uint32_t box[3] = {(uint32_t)p.cv_bw, (uint32_t)p.cv_slab_rows, 1};
-                const int rc = encode_tensor_map_f32(&tmap, images, 3, dims, strides, box, false);
-                if (rc != RB200_OK) return rc;
-                p.ring_bytes = (uint32_t)ring;
-                p.raw_slots = 0;
-                p.conv = 2;
-                rows_mode = true;
-            }
-        }
+    // the slab of inputs must fit one 16 KB slot of the cp.async ring
+    for (;;) {
+        p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
+        p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
+        p.cv_row_elems = p.cv_width_x * p.chan;
+        p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
+        if ((int64_t)p.cv_slab_elems * 4 <= SKT_RAW_STAGE) break;
+        if (p.cv_rows > 1) { p.cv_rows--; continue; }
+        if (p.cv_tw > 16) { p.cv_tw /= 2; continue; }
+        set_error("conv2d_forward: the input slab of one tile exceeds the staging ring (use im2col2d + gemm)");
+        return RB200_E_UNSUPPORTED;
     }
-    if (!rows_mode) {
-        // the slab of inputs must fit one 16 KB slot of the cp.async ring
-        p.cv_tw = tw0; p.cv_rows = rows0;
-        for (;;) {
-            p.cv_slab_rows = (p.cv_rows - 1) * p.str_h + (int)(filter_h - 1) * p.dil_h + 1;
-            p.cv_width_x = (p.cv_tw - 1) * p.str_w + (int)(filter_w - 1) * p.dil_w + 1;
-            p.cv_row_elems = p.cv_width_x * p.chan;
-            p.cv_slab_elems = p.cv_slab_rows * p.cv_row_elems;
-            if ((int64_t)p.cv_slab_elems * 4 <= SKT_RAW_STAGE) break;
-            if (p.cv_rows > 1) { p.cv_rows--; continue; }
-            if (p.cv_tw > 16) { p.cv_tw /= 2; continue; }
-            set_error("conv2d_forward: the input slab of one tile exceeds the staging ring (use im2col2d + gemm)");
-            return RB200_E_UNSUPPORTED;
-        }
-        p.raw_slots = SKT_RAW_SLOTS;
-        p.ring_bytes = (uint32_t)SKT_RAW_SLOTS * SKT_RAW_STAGE;
-        p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT ? 2 : 1;
-        if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) {
-            set_error("conv2d_forward: shared memory budget exceeded for filters=%d, K=%d (use im2col2d + gemm)", p.N, p.K);
-            return RB200_E_UNSUPPORTED;
-        }
+    p.raw_slots = SKT_RAW_SLOTS;
+    p.ring_bytes = (uint32_t)SKT_RAW_SLOTS * SKT_RAW_STAGE;
+    p.epi_groups = skt_smem_bytes(planes, p.NP, p.KB, 2, SKT_RAW_SLOTS) <= SKT_SMEM_LIMIT ? 2 : 1;
+    if (skt_smem_bytes(planes, p.NP, p.KB, p.epi_groups, SKT_RAW_SLOTS) > SKT_SMEM_LIMIT) {
+        set_error("conv2d_forward: shared memory budget exceeded for filters=%d, K=%d (use im2col2d + gemm)", p.N, p.K);
+        return RB200_E_UNSUPPORTED;
     }
     p.cv_col_blocks = (int)rb_ceil_div(out_w, p.cv_tw);
     p.cv_row_blocks = (int)rb_ceil_div(out_h, p.cv_rows);
@@ -1169,43 +889,9 @@ int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h,
         const uint32_t box[4] = {32, (uint32_t)p.cv_tw, (uint32_t)p.cv_rows, 1};
         p.tma_store = encode_tensor_map_f32(&mapC, out, 4, dims, strides, box, true) == RB200_OK;  // else: plain stores
     }
-    p.direct_store = 0;
-    {
-        static int env = -1;
-        if (env < 0) { const char* e = getenv("RB200_SKT_DIRECT_STORE"); env = (e && e[0] == '0') ? 0 : 1; }
-        if (env && rows_mode && (filters % 2) == 0 && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) {
-            p.direct_store = 1;
-            p.tma_store = 0;
-        }
-    }
-    p.trace = nullptr;
-    static int trace_env = -1;
-    if (trace_env < 0) { const char* e = getenv("RB200_SKT_TRACE"); trace_env = (e && e[0] == '1') ? 1 : 0; }
-    if (trace_env) RB_CUDA(cudaMalloc(&p.trace, 64 * 16 * sizeof(long long)));
-    if (p.trace) RB_CUDA(cudaMemsetAsync(p.trace, 0, 64 * 16 * sizeof(long long), c.stream));
-    const int rc = skt_launch(planes, rows_mode, p, tmap, mapC, smem, "gemm_tf32_skinny_kernel(conv)");
+    const int rc = skt_launch(planes, p, mapC, smem, "gemm_tf32_skinny_kernel(conv)");
     if (rc != RB200_OK) return rc;
-    if (p.trace) {
-        // diagnostic dump: per tile of CTA 0, event stamps relative to the first one (SM clocks)
-        static long long host[64 * 16];
-        RB_CUDA(cudaStreamSynchronize(c.stream));
-        RB_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
-        RB_CUDA(cudaFree(p.trace));
-        long long t0 = 0;
-        for (int i = 0; i < 64 * 16; i++) if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
-        fprintf(stderr, "skt trace (CTA 0): tile | slab lds a_empty a_full | t_empty a_full issued | t_full stg_free tmem_rel store\n");
-        for (int it = 0; it < 64; it++) {
-            fprintf(stderr, "%3d |", it);
-            for (int e = 0; e < 12; e++) {
-                if (e == 4 || e == 8) fprintf(stderr, " |");
-                if (e == 7) continue;
-                fprintf(stderr, " %7lld", host[it * 16 + e] ? host[it * 16 + e] - t0 : -1LL);
-            }
-            fprintf(stderr, "\n");
-        }
-    }
-    if (rows_mode) c.last_gemm_path = planes == 1 ? "tcgen05_tf32_rows_conv" : "tcgen05_tf32x3_rows_conv";
-    else           c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
+    c.last_gemm_path = planes == 1 ? "tcgen05_tf32_conv" : "tcgen05_tf32x3_conv";
     return RB200_OK;
 }
 

@@ -716,14 +716,15 @@ class LinearAlgebra:
         return images
 
     def conv2d(self, images: NDArray, kernel: NDArray, bias: NDArray | None = None, strides=None, padding=None,
-               dilation_rate=None, fused: bool = False) -> NDArray:
+               dilation_rate=None, fused: bool | None = None) -> NDArray:
         """Conv2D forward for channels-last images [b,h,w,c] and kernel [kh,kw,c,filters] -- the composition
         the reference's users write by hand (im2col :3369 -> reshape -> gemm :925 -> add :1968; the Conv2D
-        layer itself lives in rindow-neuralnetworks).  Default: exactly those three driver calls (on the
-        B200 driver: tiled im2col2d + software-staged tcgen05 GEMM, 0.27 ms for BASELINE config C4).
-        fused=True asks for the driver's single-kernel implicit-GEMM entry (rb200_conv2d_forward: no cols
-        round trip; correct and tested, but in round 1 its producer is still issue-bound -- 0.41 ms -- so
-        it is opt-in) and falls back to the three calls when the driver has none for this shape."""
+        layer itself lives in rindow-neuralnetworks).  On any driver: exactly those three calls (on the B200
+        driver: tiled im2col2d + software-staged tcgen05 GEMM, 0.25 ms for BASELINE config C4).  On the B200
+        driver the single-kernel implicit-GEMM entry (rb200_conv2d_forward: no cols round trip) is taken by
+        default for short reductions, kh*kw*c <= 32, where it runs on the TMEM-operand kernel (0.14 ms for C4,
+        0.92 of HBM); fused=True asks for it at any size it supports, fused=False never.  The three calls
+        remain the fallback whenever the driver declines the shape."""
         if images.ndim() != 4 or kernel.ndim() != 4:
             raise InvalidArgumentException("images and kernel must be 4D dimension")
         batches, in_h, in_w, channels = images.shape()
@@ -742,6 +743,8 @@ class LinearAlgebra:
             raise InvalidArgumentException("Invalid shape or paramaters.")
         if bias is not None and bias.shape() != [filters]:
             raise InvalidArgumentException("Unmatch shape of bias and kernel")
+        if fused is None:
+            fused = filter_h * filter_w * channels <= 32
         fused_fn = getattr(self.math, "conv2d_forward", None) if (fused and type(self.math).__name__ == "CudaMath") else None
         if fused_fn is not None:
             fused = fused_fn

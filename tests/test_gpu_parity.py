@@ -722,6 +722,12 @@ CONV_CASES = [  # (b, h, w, c, kh, kw, filters, strides, padding, dilation, bias
     (2, 12, 12, 5, 2, 4, 100, (1, 2), True, (2, 1), True),         # N = 100 -> padded to 128
     (4, 64, 64, 3, 3, 3, 64, (1, 1), False, (1, 1), True),
     (1, 9, 9, 16, 3, 3, 16, (1, 1), False, (1, 1), False),         # K = 144 > 128: two-call path
+    # K <= 32: the TMEM-operand kernel (conv_tcgen05_rows.cu)
+    (2, 40, 300, 3, 3, 3, 64, (1, 1), True, (1, 1), True),         # three column blocks, same padding (slab shifted left)
+    (2, 33, 140, 1, 5, 5, 32, (1, 1), False, (1, 1), False),       # K = 25, one channel, 32 filters
+    (1, 64, 200, 1, 3, 3, 128, (2, 2), True, (1, 1), True),        # stride 2, 128 filters (two 64-column epilogue passes)
+    (2, 20, 36, 2, 2, 4, 96, (1, 1), False, (1, 2), True),         # two channels, dilated taps, 96 filters, several rows per tile
+    (1, 48, 52, 3, 3, 3, 36, (1, 1), False, (1, 1), False),        # 36 filters: the TMA store clips the filter dimension
 ]
 
 
@@ -742,13 +748,16 @@ def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
                         padding=pad, dilation_rate=dil, fused=True)
         path = rb._capi.last_gemm_path()
         out2 = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st,
-                         padding=pad, dilation_rate=dil)                        # default: im2col -> gemm -> add
+                         padding=pad, dilation_rate=dil, fused=False)           # im2col -> gemm -> add
     finally:
         rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(rb.GEMM_TF32X3))
         cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
     K = kh * kw * c
     if mode != rb.GEMM_FP32_SIMT and K <= 128 and f <= 64:
         assert path.endswith("_conv"), path          # wider filter banks may not fit the shared-memory budget
+    if (mode != rb.GEMM_FP32_SIMT and K <= 32 and 32 <= f <= 128 and f % 4 == 0 and (w * c) % 4 == 0
+            and np.gcd(st[1] * c, 32) <= 2):
+        assert path.endswith("_tmem_conv"), path     # short reductions: A operand in tensor memory
     shape = oracle.im2col2d_out_shape(b, h, w, c, kh, kw, st[0], st[1], pad, dil[0], dil[1], False)
     M = shape[0] * shape[1] * shape[2]
     cols = np.zeros(M * K)
@@ -765,6 +774,28 @@ def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
     got2 = out2.to_numpy().reshape(-1).astype(np.float64)
     assert out2.shape() == out.shape()
     assert np.max(np.abs(got2 - ref)) / np.max(np.abs(ref)) < GEMM_TOL[mode]
+
+
+def test_conv2d_forward_nonfinite_containment(cuda_service):
+    """A NaN / Inf pixel may only reach the outputs whose receptive field holds it (the reference multiplies
+    padding zeros and absent taps by nothing at all): checks the zero tails of the K <= 32 kernel's A rows."""
+    b, h, w, c, f = 1, 20, 24, 3, 64
+    rng = np.random.default_rng(7)
+    img = rng.uniform(0, 1, (b, h, w, c)).astype(np.float32)
+    W = (rng.standard_normal((3, 3, c, f)) * 0.1).astype(np.float32)
+    la = LinearAlgebra(cuda_service)
+    clean = la.conv2d(la.array(img), la.array(W), padding=True, fused=True).to_numpy()
+    assert rb._capi.last_gemm_path().endswith("_tmem_conv")
+    bad = img.copy()
+    bad[0, 5, 7, 1] = np.nan
+    bad[0, 19, 0, 2] = np.inf            # corner pixel: its neighbours' windows reach into the padding
+    out = la.conv2d(la.array(bad), la.array(W), padding=True, fused=True).to_numpy()
+    touched = np.zeros((h, w), bool)
+    for (y, x) in ((5, 7), (19, 0)):
+        touched[max(0, y - 1):y + 2, max(0, x - 1):x + 2] = True
+    assert not np.isfinite(out[0][touched]).any()
+    assert np.isfinite(out[0][~touched]).all()
+    assert np.array_equal(out[0][~touched], clean[0][~touched])
 
 
 # ---------------------------------------------------------------------------------------------------
