@@ -182,6 +182,8 @@ int rb200_scal(int dtype, int64_t n, double alpha, void* X, int64_t offX, int64_
 int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, int64_t incX,
                void* Y, int64_t offY, int64_t incY);
 int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY);
+/* X <-> Y, PhpBlas::swap (:744-760); float32 / float64; the vectors must not overlap. */
+int rb200_swap(int dtype, int64_t n, void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY);
 /* Y[rows] = alpha * op(A)[rows,cols] * X[cols] (+ beta*Y iff beta != 0); A is m x n row-major with ldA;
  * trans: rows = n, cols = m. */
 int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
@@ -276,6 +278,17 @@ int rb200_astype(int64_t n, int from_dtype, const void* X, int64_t offX, int64_t
 int rb200_sum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
 int rb200_imax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
 int rb200_imin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+
+/* ---- BLAS level-1 reductions, PhpBlas.php: asum (:266-286) = sum |x|; nrm2 (:366-392) = sqrt(sum x*x); dot
+ *      (:196-222) = sum x*y; iamax (:288-317) / iamin (:319-348) = index of the first largest / smallest |x|,
+ *      scanning from element 0 with strict comparisons (a NaN at 0 stays, a later NaN never wins).  Every real
+ *      dtype; terms and sums in double, as PHP evaluates them.  The call returns after the value is on the host. */
+int rb200_asum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+int rb200_nrm2(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+int rb200_dot(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
+              const void* Y, int64_t offY, int64_t incY, double* result);
+int rb200_iamax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+int rb200_iamin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
 
 /* Y[i, (int)X[i]] += a for i < m -- PhpMath::updateAddOnehot (:1438-1464), what LinearAlgebra::onehot (:3095)
  * calls.  X holds the labels (any real dtype), Y is float32/float64 with row stride ldY.  A label outside

@@ -62,6 +62,12 @@ SIGNATURES = {
     "rb200_scal": (i32, [i32, i64, f64, vp, i64, i64]),
     "rb200_axpy": (i32, [i32, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_copy": (i32, [i32, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_swap": (i32, [i32, i64, vp, i64, i64, vp, i64, i64]),
+    "rb200_asum": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(f64)]),
+    "rb200_nrm2": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(f64)]),
+    "rb200_dot": (i32, [i32, i64, vp, i64, i64, vp, i64, i64, ctypes.POINTER(f64)]),
+    "rb200_iamax": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(i64)]),
+    "rb200_iamin": (i32, [i32, i64, vp, i64, i64, ctypes.POINTER(i64)]),
     "rb200_gemv": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
     "rb200_omatcopy": (i32, [i32, i32, i32, i64, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_transpose": (i32, [i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), vp, i64, vp, i64]),

@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int B1_THREADS = 256;
-enum { B1_SCAL = 0, B1_AXPY = 1, B1_COPY = 2 };
+enum { B1_SCAL = 0, B1_AXPY = 1, B1_COPY = 2, B1_SWAP = 3 };     // swap (PhpBlas.php:744-760) also writes X
 
 template <typename T> union B1Pack { int4 raw; T v[16 / sizeof(T)]; };
 
@@ -19,7 +19,7 @@ constexpr int B1_UNROLL = 4;     // 16-byte packs in flight per thread and opera
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(B1_THREADS)
-blas1_vec_kernel(int64_t nvec, T alpha, const T* __restrict__ X, T* __restrict__ Y)
+blas1_vec_kernel(int64_t nvec, T alpha, const T* X, T* Y)
 {
     constexpr int V = 16 / (int)sizeof(T);
     const int64_t chunk = (int64_t)B1_THREADS * B1_UNROLL;
@@ -37,13 +37,18 @@ blas1_vec_kernel(int64_t nvec, T alpha, const T* __restrict__ X, T* __restrict__
         for (int u = 0; u < B1_UNROLL; u++) {
             const int64_t i = base + u * B1_THREADS + threadIdx.x;
             if (i < nvec) {
+                if (OP == B1_SWAP) {
+                    __stcs(reinterpret_cast<int4*>(const_cast<T*>(X)) + i, y[u].raw);
+                    __stcs(reinterpret_cast<int4*>(Y) + i, x[u].raw);
+                } else {
 #pragma unroll
-                for (int e = 0; e < V; e++) {
-                    if (OP == B1_SCAL) y[u].v[e] = y[u].v[e] * alpha;
-                    else if (OP == B1_AXPY) y[u].v[e] = fma(alpha, x[u].v[e], y[u].v[e]);
-                    else y[u].v[e] = x[u].v[e];
+                    for (int e = 0; e < V; e++) {
+                        if (OP == B1_SCAL) y[u].v[e] = y[u].v[e] * alpha;
+                        else if (OP == B1_AXPY) y[u].v[e] = fma(alpha, x[u].v[e], y[u].v[e]);
+                        else y[u].v[e] = x[u].v[e];
+                    }
+                    __stcs(reinterpret_cast<int4*>(Y) + i, y[u].raw);
                 }
-                __stcs(reinterpret_cast<int4*>(Y) + i, y[u].raw);
             }
         }
     }
@@ -51,13 +56,14 @@ blas1_vec_kernel(int64_t nvec, T alpha, const T* __restrict__ X, T* __restrict__
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(B1_THREADS)
-blas1_strided_kernel(int64_t n, T alpha, const T* __restrict__ X, int64_t incX, T* __restrict__ Y, int64_t incY)
+blas1_strided_kernel(int64_t n, T alpha, const T* X, int64_t incX, T* Y, int64_t incY)
 {
     const int64_t stride = (int64_t)gridDim.x * B1_THREADS;
     for (int64_t i = (int64_t)blockIdx.x * B1_THREADS + threadIdx.x; i < n; i += stride) {
         T* y = Y + i * incY;
         if (OP == B1_SCAL) *y = *y * alpha;
         else if (OP == B1_AXPY) *y = fma(alpha, X[i * incX], *y);
+        else if (OP == B1_SWAP) { T* x = const_cast<T*>(X) + i * incX; const T t = *y; *y = *x; *x = t; }
         else *y = X[i * incX];
     }
 }
@@ -476,6 +482,11 @@ int rb200_axpy(int dtype, int64_t n, double alpha, const void* X, int64_t offX, 
 int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY)
 {
     return blas1_dispatch<B1_COPY>(dtype, n, 1.0, X, offX, incX, Y, offY, incY);
+}
+
+int rb200_swap(int dtype, int64_t n, void* X, int64_t offX, int64_t incX, void* Y, int64_t offY, int64_t incY)
+{
+    return blas1_dispatch<B1_SWAP>(dtype, n, 1.0, X, offX, incX, Y, offY, incY);
 }
 
 int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,

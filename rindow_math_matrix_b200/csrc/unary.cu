@@ -356,7 +356,7 @@ int astype_from(int from, bool to_bool, int64_t n, const void* X, int64_t offX, 
 
 // ---- sum / imax / imin: one launch, CTA partials + ticket, the last CTA merges them in index order -------------
 constexpr int SR_THREADS = 256;
-enum { SR_SUM = 0, SR_IMAX = 1, SR_IMIN = 2 };
+enum { SR_SUM = 0, SR_IMAX = 1, SR_IMIN = 2, SR_ASUM = 3, SR_NRM2 = 4, SR_DOT = 5, SR_IAMAX = 6, SR_IAMIN = 7 };
 
 template <typename T> __device__ __forceinline__ bool sr_isnan(T) { return false; }
 template <> __device__ __forceinline__ bool sr_isnan<float>(float v) { return v != v; }
@@ -368,18 +368,29 @@ template <> __device__ __forceinline__ uint8_t sr_shfl<uint8_t>(uint8_t v, int d
 template <> __device__ __forceinline__ int16_t sr_shfl<int16_t>(int16_t v, int d) { return (int16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
 template <> __device__ __forceinline__ uint16_t sr_shfl<uint16_t>(uint16_t v, int d) { return (uint16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
 
-// SUM: double accumulator for every dtype (PhpMath::sum starts from 0.0 and adds PHP numbers, :161-164)
-template <typename T> struct SrSum {
+// SUM family: double accumulator for every dtype (PhpMath::sum starts from 0.0 and adds PHP numbers, :161-164).
+// F selects the term: the element (sum), |x| (PhpBlas::asum :266-286), x*x (nrm2 :366-392, sqrt at the end) or
+// x*y (dot :196-222) -- each a double operation on the widened operands, as PHP evaluates it.
+enum { SRF_ID = 0, SRF_ABS = 1, SRF_SQR = 2, SRF_DOT = 3 };
+template <typename T, int F> struct SrSumF {
     struct Acc { double val; };
+    __device__ static __forceinline__ double term(T x, T y)
+    {
+        const double dx = (double)x;
+        if (F == SRF_ABS) return fabs(dx);
+        if (F == SRF_SQR) return dx * dx;
+        if (F == SRF_DOT) return dx * (double)y;
+        return dx;
+    }
     __device__ static __forceinline__ Acc init() { Acc a; a.val = 0.0; return a; }
-    __device__ static __forceinline__ void take(Acc& a, T v, int64_t) { a.val += (double)v; }
+    __device__ static __forceinline__ void take(Acc& a, T x, T y, int64_t) { a.val += term(x, y); }
     // a 16-byte pack is summed as a tree before it joins the running sum: the dependent DADD chain per thread is one
     // add per pack instead of one per element (the kernel is latency-bound otherwise: 40 % of DRAM throughput)
-    template <int V> __device__ static __forceinline__ void take_pack(Acc& a, const T* v, int64_t)
+    template <int V> __device__ static __forceinline__ void take_pack(Acc& a, const T* x, const T* y, int64_t)
     {
         double s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = (double)v[e];
+        for (int e = 0; e < V; e++) s[e] = term(x[e], y[e]);
 #pragma unroll
         for (int w = V / 2; w >= 1; w >>= 1) {
 #pragma unroll
@@ -389,23 +400,35 @@ template <typename T> struct SrSum {
     }
     __device__ static __forceinline__ Acc merge(const Acc& a, const Acc& b) { Acc r; r.val = a.val + b.val; return r; }
     __device__ static __forceinline__ Acc shfl(const Acc& a, int d) { Acc r; r.val = sr_shfl(a.val, d); return r; }
-    __device__ static __forceinline__ int64_t finish(const Acc& a, int64_t, const T*) { return __double_as_longlong(a.val); }
+    __device__ static __forceinline__ int64_t finish(const Acc& a, int64_t, const T*)
+    {
+        return __double_as_longlong(F == SRF_SQR ? sqrt(a.val) : a.val);
+    }
 };
+
+template <typename T> __device__ __forceinline__ T sr_abs(T v) { return v < (T)0 ? (T)(-v) : v; }
+template <> __device__ __forceinline__ uint8_t sr_abs<uint8_t>(uint8_t v) { return v; }
+template <> __device__ __forceinline__ uint16_t sr_abs<uint16_t>(uint16_t v) { return v; }
+template <> __device__ __forceinline__ uint32_t sr_abs<uint32_t>(uint32_t v) { return v; }
+template <> __device__ __forceinline__ float sr_abs<float>(float v) { return fabsf(v); }
+template <> __device__ __forceinline__ double sr_abs<double>(double v) { return fabs(v); }
 
 // IMAX / IMIN: the candidate is the first strict extremum among the non-NaN elements.  A thread visits its elements
 // in increasing index order, so the strict comparison alone keeps the lowest index; merges break ties by index.
-template <typename T, bool MAX> struct SrArg {
+// ABS: the BLAS forms iamax / iamin (PhpBlas.php:288-348) compare |x| and start from element 0, so a NaN there sticks.
+template <typename T, bool MAX, bool ABS> struct SrArg {
     struct Acc { T val; int64_t idx; };      // idx < 0: no candidate yet
     __device__ static __forceinline__ Acc init() { Acc a; a.val = (T)0; a.idx = -1; return a; }
-    __device__ static __forceinline__ void take(Acc& a, T v, int64_t i)
+    __device__ static __forceinline__ void take(Acc& a, T x, T, int64_t i)
     {
-        if (sr_isnan<T>(v)) return;                       // NaN elements never win (imax :185, imin :210)
+        if (sr_isnan<T>(x)) return;                       // NaN elements never win (imax :185, imin :210)
+        const T v = ABS ? sr_abs<T>(x) : x;
         if (a.idx < 0 || (MAX ? (v > a.val) : (v < a.val))) { a.val = v; a.idx = i; }
     }
-    template <int V> __device__ static __forceinline__ void take_pack(Acc& a, const T* v, int64_t i0)
+    template <int V> __device__ static __forceinline__ void take_pack(Acc& a, const T* x, const T*, int64_t i0)
     {
 #pragma unroll
-        for (int e = 0; e < V; e++) take(a, v[e], i0 + e);
+        for (int e = 0; e < V; e++) take(a, x[e], x[e], i0 + e);
     }
     __device__ static __forceinline__ Acc merge(const Acc& a, const Acc& b)
     {
@@ -417,16 +440,16 @@ template <typename T, bool MAX> struct SrArg {
     __device__ static __forceinline__ Acc shfl(const Acc& a, int d) { Acc r; r.val = sr_shfl(a.val, d); r.idx = sr_shfl(a.idx, d); return r; }
     __device__ static __forceinline__ int64_t finish(const Acc& a, int64_t n, const T* X)
     {
-        if (MAX) return (a.idx < 0) ? n - 1 : a.idx;              // all NaN: the scan ends on n-1 (:185)
-        return (a.idx < 0 || sr_isnan<T>(X[0])) ? 0 : a.idx;      // a NaN at 0 is never displaced (:210)
+        if (MAX && !ABS) return (a.idx < 0) ? n - 1 : a.idx;      // all NaN: the scan ends on n-1 (:185)
+        return (a.idx < 0 || sr_isnan<T>(X[0])) ? 0 : a.idx;      // a NaN at 0 is never displaced (:210, blas :296)
     }
 };
 
 // out[0] = the sum (as double bits) or the index
-template <typename T, typename Pol, bool VEC>
+template <typename T, typename Pol, bool VEC, bool TWO>
 __global__ void __launch_bounds__(SR_THREADS)
-scalar_reduce_kernel(int64_t n, const T* __restrict__ X, int64_t incX, int64_t seg, typename Pol::Acc* __restrict__ partials,
-                     int* __restrict__ counter, int64_t* __restrict__ out)
+scalar_reduce_kernel(int64_t n, const T* __restrict__ X, int64_t incX, const T* __restrict__ Y, int64_t incY, int64_t seg,
+                     typename Pol::Acc* __restrict__ partials, int* __restrict__ counter, int64_t* __restrict__ out)
 {
     using Acc = typename Pol::Acc;
     constexpr int V = 16 / (int)sizeof(T);
@@ -435,25 +458,29 @@ scalar_reduce_kernel(int64_t n, const T* __restrict__ X, int64_t incX, int64_t s
     const int64_t begin = (int64_t)blockIdx.x * seg;
     const int64_t end = (begin + seg < n) ? begin + seg : n;
     Acc acc = Pol::init();
-    if (VEC) {                                      // incX == 1, X 16-byte aligned, seg % V == 0
+    if (VEC) {                                      // unit increments, operands 16-byte aligned, seg % V == 0
         const int64_t v0 = begin / V, v1 = end / V;
         const int4* xv = reinterpret_cast<const int4*>(X);
+        const int4* yv = reinterpret_cast<const int4*>(Y);
         for (int64_t base = v0; base < v1; base += SR_THREADS * UN_UNROLL) {
-            UnPack<T> p[UN_UNROLL];
+            UnPack<T> p[UN_UNROLL], q[TWO ? UN_UNROLL : 1];
 #pragma unroll
             for (int u = 0; u < UN_UNROLL; u++) {
                 const int64_t i = base + u * SR_THREADS + threadIdx.x;
-                if (i < v1) p[u].raw = __ldcs(xv + i);
+                if (i < v1) { p[u].raw = __ldcs(xv + i); if (TWO) q[u].raw = __ldcs(yv + i); }
             }
 #pragma unroll
             for (int u = 0; u < UN_UNROLL; u++) {
                 const int64_t i = base + u * SR_THREADS + threadIdx.x;
-                if (i < v1) Pol::template take_pack<V>(acc, p[u].v, i * V);
+                if (i < v1) Pol::template take_pack<V>(acc, p[u].v, TWO ? q[u].v : p[u].v, i * V);
             }
         }
-        for (int64_t i = v1 * V + threadIdx.x; i < end; i += SR_THREADS) Pol::take(acc, X[i], i);   // last CTA's tail
+        for (int64_t i = v1 * V + threadIdx.x; i < end; i += SR_THREADS) Pol::take(acc, X[i], TWO ? Y[i] : X[i], i);   // last CTA's tail
     } else {
-        for (int64_t i = begin + threadIdx.x; i < end; i += SR_THREADS) Pol::take(acc, X[i * incX], i);
+        for (int64_t i = begin + threadIdx.x; i < end; i += SR_THREADS) {
+            const T x = X[i * incX];
+            Pol::take(acc, x, TWO ? Y[i * incY] : x, i);
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc = Pol::merge(acc, Pol::shfl(acc, d));
@@ -496,20 +523,23 @@ scalar_reduce_kernel(int64_t n, const T* __restrict__ X, int64_t incX, int64_t s
     }
 }
 
-template <typename T, typename Pol>
-int scalar_reduce_launch(int64_t n, const void* Xv, int64_t offX, int64_t incX, int64_t* host_out)
+template <typename T, typename Pol, bool TWO>
+int scalar_reduce_launch(int64_t n, const void* Xv, int64_t offX, int64_t incX, const void* Yv, int64_t offY, int64_t incY,
+                         int64_t* host_out)
 {
     using Acc = typename Pol::Acc;
     rb200::Context& c = rb200::ctx();
     const T* X = reinterpret_cast<const T*>(Xv) + offX;
+    const T* Y = TWO ? reinterpret_cast<const T*>(Yv) + offY : X;
     constexpr int V = 16 / (int)sizeof(T);
-    const bool vec = (incX == 1) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && n >= V;
+    const bool vec = (incX == 1) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && n >= V &&
+                     (!TWO || ((incY == 1) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0)));
     // contiguous segments, a multiple of one CTA pass, sized for one wave of 8 CTAs per SM
     const int64_t quantum = (int64_t)SR_THREADS * UN_UNROLL * V;
     int64_t ctas = rb_ceil_div(n, quantum);
     static int per_sm = 0;                                       // resident CTAs per SM of this instantiation
     if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scalar_reduce_kernel<T, Pol, true>, SR_THREADS, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scalar_reduce_kernel<T, Pol, true, TWO>, SR_THREADS, 0) != cudaSuccess ||
             per_sm < 1) per_sm = 4;
     }
     const int64_t cap = (int64_t)c.sm_count * per_sm;            // exactly one wave: no tail
@@ -524,8 +554,8 @@ int scalar_reduce_launch(int64_t n, const void* Xv, int64_t offX, int64_t incX, 
     if (rc != RB200_OK) return rc;
     int64_t* out = reinterpret_cast<int64_t*>(c.workspace);
     Acc* partials = reinterpret_cast<Acc*>(reinterpret_cast<char*>(c.workspace) + 16);
-    if (vec) scalar_reduce_kernel<T, Pol, true><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, 1, seg, partials, counter, out);
-    else     scalar_reduce_kernel<T, Pol, false><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, incX, seg, partials, counter, out);
+    if (vec) scalar_reduce_kernel<T, Pol, true, TWO><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, 1, Y, 1, seg, partials, counter, out);
+    else     scalar_reduce_kernel<T, Pol, false, TWO><<<(unsigned)ctas, SR_THREADS, 0, c.stream>>>(n, X, incX, Y, incY, seg, partials, counter, out);
     RB_LAUNCH_CHECK("scalar_reduce_kernel");
     RB_CUDA(cudaMemcpyAsync(c.pinned_scalar, out, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
     RB_CUDA(cudaStreamSynchronize(c.stream));
@@ -534,31 +564,37 @@ int scalar_reduce_launch(int64_t n, const void* Xv, int64_t offX, int64_t incX, 
 }
 
 template <typename T, int OP>
-int scalar_reduce_op(int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* host_out)
+int scalar_reduce_op(int64_t n, const void* X, int64_t offX, int64_t incX, const void* Y, int64_t offY, int64_t incY, int64_t* host_out)
 {
-    if (OP == SR_SUM) return scalar_reduce_launch<T, SrSum<T>>(n, X, offX, incX, host_out);
-    if (OP == SR_IMAX) return scalar_reduce_launch<T, SrArg<T, true>>(n, X, offX, incX, host_out);
-    return scalar_reduce_launch<T, SrArg<T, false>>(n, X, offX, incX, host_out);
+    if (OP == SR_SUM)   return scalar_reduce_launch<T, SrSumF<T, SRF_ID>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    if (OP == SR_ASUM)  return scalar_reduce_launch<T, SrSumF<T, SRF_ABS>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    if (OP == SR_NRM2)  return scalar_reduce_launch<T, SrSumF<T, SRF_SQR>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    if (OP == SR_DOT)   return scalar_reduce_launch<T, SrSumF<T, SRF_DOT>, true>(n, X, offX, incX, Y, offY, incY, host_out);
+    if (OP == SR_IMAX)  return scalar_reduce_launch<T, SrArg<T, true, false>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    if (OP == SR_IMIN)  return scalar_reduce_launch<T, SrArg<T, false, false>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    if (OP == SR_IAMAX) return scalar_reduce_launch<T, SrArg<T, true, true>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
+    return scalar_reduce_launch<T, SrArg<T, false, true>, false>(n, X, offX, incX, nullptr, 0, 1, host_out);
 }
 
 template <int OP>
-int scalar_reduce_dispatch(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* host_out)
+int scalar_reduce_dispatch(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* host_out,
+                           const void* Y = nullptr, int64_t offY = 0, int64_t incY = 1)
 {
     RB_REQUIRE_INIT();
-    if (!X || !host_out) RB_INVALID("NULL buffer");
+    if (!X || !host_out || (OP == SR_DOT && !Y)) RB_INVALID("NULL buffer");
     if (n < 1) RB_INVALID("Argument n must be greater than 0.");
-    if (incX < 1 || offX < 0) RB_INVALID("bad increment / offset");
+    if (incX < 1 || offX < 0 || incY < 1 || offY < 0) RB_INVALID("bad increment / offset");
     switch (dtype) {
-        case RB200_FLOAT32: return scalar_reduce_op<float, OP>(n, X, offX, incX, host_out);
-        case RB200_FLOAT64: return scalar_reduce_op<double, OP>(n, X, offX, incX, host_out);
-        case RB200_INT32:   return scalar_reduce_op<int32_t, OP>(n, X, offX, incX, host_out);
-        case RB200_INT64:   return scalar_reduce_op<int64_t, OP>(n, X, offX, incX, host_out);
-        case RB200_BOOL: case RB200_UINT8: return scalar_reduce_op<uint8_t, OP>(n, X, offX, incX, host_out);
-        case RB200_INT8:    return scalar_reduce_op<int8_t, OP>(n, X, offX, incX, host_out);
-        case RB200_INT16:   return scalar_reduce_op<int16_t, OP>(n, X, offX, incX, host_out);
-        case RB200_UINT16:  return scalar_reduce_op<uint16_t, OP>(n, X, offX, incX, host_out);
-        case RB200_UINT32:  return scalar_reduce_op<uint32_t, OP>(n, X, offX, incX, host_out);
-        default: RB_UNSUPPORTED("sum / imax / imin: unsupported dtype %d", dtype);
+        case RB200_FLOAT32: return scalar_reduce_op<float, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_FLOAT64: return scalar_reduce_op<double, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_INT32:   return scalar_reduce_op<int32_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_INT64:   return scalar_reduce_op<int64_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_BOOL: case RB200_UINT8: return scalar_reduce_op<uint8_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_INT8:    return scalar_reduce_op<int8_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_INT16:   return scalar_reduce_op<int16_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_UINT16:  return scalar_reduce_op<uint16_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        case RB200_UINT32:  return scalar_reduce_op<uint32_t, OP>(n, X, offX, incX, Y, offY, incY, host_out);
+        default: RB_UNSUPPORTED("scalar reduction: unsupported dtype %d", dtype);
     }
 }
 
@@ -702,6 +738,44 @@ int rb200_imax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, 
 int rb200_imin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result)
 {
     return scalar_reduce_dispatch<SR_IMIN>(dtype, n, X, offX, incX, result);
+}
+
+static int scalar_double(int rc, int64_t bits, double* result)
+{
+    if (rc == RB200_OK) memcpy(result, &bits, sizeof(double));
+    return rc;
+}
+
+int rb200_asum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result)
+{
+    int64_t bits = 0;
+    if (!result) RB_INVALID("result is NULL");
+    return scalar_double(scalar_reduce_dispatch<SR_ASUM>(dtype, n, X, offX, incX, &bits), bits, result);
+}
+
+int rb200_nrm2(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result)
+{
+    int64_t bits = 0;
+    if (!result) RB_INVALID("result is NULL");
+    return scalar_double(scalar_reduce_dispatch<SR_NRM2>(dtype, n, X, offX, incX, &bits), bits, result);
+}
+
+int rb200_dot(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
+              const void* Y, int64_t offY, int64_t incY, double* result)
+{
+    int64_t bits = 0;
+    if (!result) RB_INVALID("result is NULL");
+    return scalar_double(scalar_reduce_dispatch<SR_DOT>(dtype, n, X, offX, incX, &bits, Y, offY, incY), bits, result);
+}
+
+int rb200_iamax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result)
+{
+    return scalar_reduce_dispatch<SR_IAMAX>(dtype, n, X, offX, incX, result);
+}
+
+int rb200_iamin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result)
+{
+    return scalar_reduce_dispatch<SR_IAMIN>(dtype, n, X, offX, incX, result);
 }
 
 int rb200_onehot(int dtype_x, int dtype_y, int64_t m, int64_t n, double a,

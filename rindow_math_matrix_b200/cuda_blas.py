@@ -315,9 +315,53 @@ class CudaBlas:
         _capi.check(self._lib.rb200_omatcopy(self._float_dtype(A, "omatcopy"), BLAS.RowMajor, trans, m, n, alpha,
                                              A.device_ptr(), offsetA, ldA, B.device_ptr_rw(), offsetB, ldB))
 
+    # ---- level-1 reductions (PhpBlas.php:196-222 dot, :266-286 asum, :288-348 iamax / iamin, :366-392 nrm2) --------
+    # every real dtype: PHP's abs / * / + work on ints too; the value is on the host when the call returns
+    def _scalar(self, fn, ctype, n, X, offsetX, incX):
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        self._device_buffers(X=X)
+        out = ctype(0)
+        _capi.check(fn(X.dtype(), n, X.device_ptr(), offsetX, incX, ctypes.byref(out)))
+        return out.value
+
+    def asum(self, n, X, offsetX, incX) -> float:
+        return self._scalar(self._lib.rb200_asum, ctypes.c_double, n, X, offsetX, incX)
+
+    def nrm2(self, n, X, offsetX, incX) -> float:
+        return self._scalar(self._lib.rb200_nrm2, ctypes.c_double, n, X, offsetX, incX)
+
+    def iamax(self, n, X, offsetX, incX) -> int:
+        return self._scalar(self._lib.rb200_iamax, ctypes.c_int64, n, X, offsetX, incX)
+
+    def iamin(self, n, X, offsetX, incX) -> int:
+        return self._scalar(self._lib.rb200_iamin, ctypes.c_int64, n, X, offsetX, incX)
+
+    def dot(self, n, X, offsetX, incX, Y, offsetY, incY) -> float:
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        assert_vector_buffer_spec("Y", Y, n, offsetY, incY)
+        self._device_buffers(X=X, Y=Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        out = ctypes.c_double(0.0)
+        _capi.check(self._lib.rb200_dot(X.dtype(), n, X.device_ptr(), offsetX, incX, Y.device_ptr(), offsetY, incY,
+                                        ctypes.byref(out)))
+        return out.value
+
+    # ---- swap (PhpBlas.php:744-760) ---------------------------------------------------------------------
+    def swap(self, n, X, offsetX, incX, Y, offsetY, incY) -> None:
+        assert_shape_parameter("n", n)
+        assert_vector_buffer_spec("X", X, n, offsetX, incX)
+        assert_vector_buffer_spec("Y", Y, n, offsetY, incY)
+        self._device_buffers(X=X, Y=Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        _capi.check(self._lib.rb200_swap(self._float_dtype(X, "swap"), n, X.device_ptr_rw(), offsetX, incX,
+                                         Y.device_ptr_rw(), offsetY, incY))
+
     def __getattr__(self, name):
-        if name in ("dot", "dotu", "dotc", "asum", "iamax", "iamin", "nrm2", "rotg", "rot",
-                    "rotm", "rotmg", "swap", "symm", "syrk", "syr2k", "trmm", "trsm"):
+        if name in ("dotu", "dotc", "rotg", "rot", "rotm", "rotmg", "symm", "syrk", "syr2k", "trmm", "trsm"):
             def _not_on_device(*a, **k):
                 raise LogicException("CudaBlas::%s is not on the B200 hot path (SURVEY.md section 8f); the PHP "
                                      "shim delegates it to PhpBlas, this package has no CPU fallback" % name)
