@@ -62,6 +62,12 @@ def lib() -> ctypes.CDLL:
         L.ro_scal.argtypes = [i64, dbl, p, i64, i64, i64]
         L.ro_axpy.argtypes = [i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_copy.argtypes = [i64, p, i64, i64, i64, p, i64, i64, i64]
+        L.ro_dot.argtypes = [i64, p, i64, i64, i64, p, i64, i64, i64, p]
+        L.ro_asum.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_nrm2.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_iamax.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_iamin.argtypes = [i64, p, i64, i64, i64, p]
+        L.ro_swap.argtypes = [i64, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_gemv.argtypes = [i32, i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64, dbl, p, i64, i64, i64]
         L.ro_omatcopy.argtypes = [i32, i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_add.argtypes = [i32, i64, i64, dbl, p, i64, i64, i64, p, i64, i64, i64]
@@ -82,7 +88,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -153,6 +159,41 @@ def axpy(n, alpha, X, offX, incX, Y, offY, incY):
 
 def copy(n, X, offX, incX, Y, offY, incY):
     _check(lib().ro_copy(n, _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+# PhpBlas::dot / asum / iamax / iamin / nrm2 / swap, PhpBlas.php:196-222, :266-348, :366-392, :744-760
+def dot(n, X, offX, incX, Y, offY, incY):
+    out = ctypes.c_double(0.0)
+    _check(lib().ro_dot(n, _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY, ctypes.byref(out)))
+    return out.value
+
+
+def asum(n, X, offX, incX):
+    out = ctypes.c_double(0.0)
+    _check(lib().ro_asum(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def nrm2(n, X, offX, incX):
+    out = ctypes.c_double(0.0)
+    _check(lib().ro_nrm2(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def iamax(n, X, offX, incX):
+    out = ctypes.c_int64(0)
+    _check(lib().ro_iamax(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def iamin(n, X, offX, incX):
+    out = ctypes.c_int64(0)
+    _check(lib().ro_iamin(n, _ptr(_buf(X)), X.size, offX, incX, ctypes.byref(out)))
+    return out.value
+
+
+def swap(n, X, offX, incX, Y, offY, incY):
+    _check(lib().ro_swap(n, _ptr(_buf(X)), X.size, offX, incX, _ptr(_buf(Y)), Y.size, offY, incY))
 
 
 def gemv(order, trans, m, n, alpha, A, offA, ldA, X, offX, incX, beta, Y, offY, incY):

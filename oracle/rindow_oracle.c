@@ -479,6 +479,80 @@ int ro_copy(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t in
     return RO_OK;
 }
 
+/* PhpBlas::dot, PhpBlas.php:196-222 (real path :216-220): acc += X*Y from 0.0 in index order */
+int ro_dot(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX,
+           const double *Y, int64_t countY, int64_t offY, int64_t incY, double *result)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    if (offY < 0 || incY < 1 || offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    double acc = 0.0;
+    for (int64_t i = 0, ix = offX, iy = offY; i < n; i++, ix += incX, iy += incY) acc += X[ix] * Y[iy];
+    *result = acc;
+    return RO_OK;
+}
+
+/* PhpBlas::asum, PhpBlas.php:266-286 (real path :279-283): acc += abs(X) */
+int ro_asum(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, double *result)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    double acc = 0.0;
+    for (int64_t i = 0, ix = offX; i < n; i++, ix += incX) acc += fabs(X[ix]);
+    *result = acc;
+    return RO_OK;
+}
+
+/* PhpBlas::iamax / iamin, PhpBlas.php:288-317 / :319-348 (real paths :306-314 / :337-345): acc = abs(X[0]), idx = 0,
+ * then a strict comparison per element -- a NaN at 0 is never displaced, a later NaN never wins */
+int ro_iamax(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, int64_t *result)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    double acc = fabs(X[offX]);
+    int64_t best = 0;
+    for (int64_t i = 1, ix = offX + incX; i < n; i++, ix += incX) {
+        const double a = fabs(X[ix]);
+        if (acc < a) { acc = a; best = i; }
+    }
+    *result = best;
+    return RO_OK;
+}
+
+int ro_iamin(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, int64_t *result)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    double acc = fabs(X[offX]);
+    int64_t best = 0;
+    for (int64_t i = 1, ix = offX + incX; i < n; i++, ix += incX) {
+        const double a = fabs(X[ix]);
+        if (acc > a) { acc = a; best = i; }
+    }
+    *result = best;
+    return RO_OK;
+}
+
+/* PhpBlas::nrm2, PhpBlas.php:366-392 (real path :384-389): sqrt(sum v*v), no scaling */
+int ro_nrm2(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, double *result)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    double sum = 0.0;
+    for (int64_t i = 0, ix = offX; i < n; i++, ix += incX) { const double v = X[ix]; sum += v * v; }
+    *result = sqrt(sum);
+    return RO_OK;
+}
+
+/* PhpBlas::swap, PhpBlas.php:744-760 */
+int ro_swap(int64_t n, double *X, int64_t countX, int64_t offX, int64_t incX,
+            double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (n < 1 || offX < 0 || incX < 1 || offX + (n - 1) * incX >= countX) return RO_E_ARG;
+    if (offY < 0 || incY < 1 || offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    for (int64_t i = 0, ix = offX, iy = offY; i < n; i++, ix += incX, iy += incY) {
+        const double tmp = Y[iy];
+        Y[iy] = X[ix];
+        X[ix] = tmp;
+    }
+    return RO_OK;
+}
+
 /* PhpBlas::gemv, PhpBlas.php:762-844 (real path :826-842): acc += (alpha*A)*X in index order, then
  * Y = acc + beta*Y iff beta != 0.  order/trans are the CBLAS codes. */
 int ro_gemv(int order, int trans, int64_t m, int64_t n, double alpha,

@@ -10,7 +10,7 @@ use Rindow\Math\Matrix\Drivers\MatlibPHP\PhpBlas;
 use Rindow\Math\Matrix\Drivers\MatlibPHP\Utils;
 
 /**
- * blas() object of the B200 service.  gemm, scal, axpy, copy, gemv and omatcopy run on the device for
+ * blas() object of the B200 service.  gemm, scal, axpy, copy, swap, dot, asum, nrm2, iamax, iamin, gemv and omatcopy run on the device for
  * float32/float64 CudaBuffers; every other BLAS method (and every other dtype) is inherited from PhpBlas
  * and therefore runs on the host mirror of the CudaBuffer (ArrayAccess), exactly as SURVEY.md section
  * 8(b) prescribes for the rows marked "next".
@@ -130,7 +130,7 @@ class CudaBlas extends PhpBlas
         $this->assertShapeParameter('n',$n);
         $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
         $alpha = $this->cleanFloatNumber($alpha,'alpha');
-        CudaFFI::check(CudaFFI::lib()->rb200_scal($X->dtype(),$n,$alpha,$X->devicePtrRW(),$offsetX,$incX));
+        CudaFFI::check(CudaFFI::lib()->rb200_scal($X->abiDtype(),$n,$alpha,$X->devicePtrRW(),$offsetX,$incX));
     }
 
     public function axpy(int $n, float|object $alpha,
@@ -143,7 +143,7 @@ class CudaBlas extends PhpBlas
         $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
         $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
         $alpha = $this->cleanFloatNumber($alpha,'alpha');
-        CudaFFI::check(CudaFFI::lib()->rb200_axpy($X->dtype(),$n,$alpha,
+        CudaFFI::check(CudaFFI::lib()->rb200_axpy($X->abiDtype(),$n,$alpha,
             $X->devicePtr(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$incY));
     }
 
@@ -155,8 +155,74 @@ class CudaBlas extends PhpBlas
         $this->assertShapeParameter('n',$n);
         $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
         $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
-        CudaFFI::check(CudaFFI::lib()->rb200_copy($X->dtype(),$n,
+        CudaFFI::check(CudaFFI::lib()->rb200_copy($X->abiDtype(),$n,
             $X->devicePtr(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    public function swap(int $n, Buffer $X, int $offsetX, int $incX, Buffer $Y, int $offsetY, int $incY) : void
+    {
+        if (!$this->onDevice($X,$Y) || $X->dtype()!=$Y->dtype()) {
+            parent::swap($n,$X,$offsetX,$incX,$Y,$offsetY,$incY); return;
+        }
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
+        CudaFFI::check(CudaFFI::lib()->rb200_swap($X->abiDtype(),$n,
+            $X->devicePtrRW(),$offsetX,$incX,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    /** level-1 reductions on the device for every real dtype (PhpBlas.php:196-222, :266-348, :366-392) */
+    protected function realDevice(Buffer ...$buffers) : bool
+    {
+        foreach ($buffers as $b) {
+            if (!($b instanceof CudaBuffer) || $this->cistype($b->dtype())) return false;
+        }
+        return true;
+    }
+
+    protected function scalarResult(string $fn, string $ctype, int $n, Buffer $X, int $offsetX, int $incX) : float|int
+    {
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $out = \FFI::new($ctype);
+        CudaFFI::check(CudaFFI::lib()->$fn($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,\FFI::addr($out)));
+        return $out->cdata;
+    }
+
+    public function asum(int $n, Buffer $X, int $offsetX, int $incX) : float
+    {
+        if (!$this->realDevice($X)) return parent::asum($n,$X,$offsetX,$incX);
+        return $this->scalarResult('rb200_asum','double',$n,$X,$offsetX,$incX);
+    }
+
+    public function nrm2(int $n, Buffer $X, int $offsetX, int $incX) : float
+    {
+        if (!$this->realDevice($X)) return parent::nrm2($n,$X,$offsetX,$incX);
+        return $this->scalarResult('rb200_nrm2','double',$n,$X,$offsetX,$incX);
+    }
+
+    public function iamax(int $n, Buffer $X, int $offsetX, int $incX) : int
+    {
+        if (!$this->realDevice($X)) return parent::iamax($n,$X,$offsetX,$incX);
+        return $this->scalarResult('rb200_iamax','int64_t',$n,$X,$offsetX,$incX);
+    }
+
+    public function iamin(int $n, Buffer $X, int $offsetX, int $incX) : int
+    {
+        if (!$this->realDevice($X)) return parent::iamin($n,$X,$offsetX,$incX);
+        return $this->scalarResult('rb200_iamin','int64_t',$n,$X,$offsetX,$incX);
+    }
+
+    public function dot(int $n, Buffer $X, int $offsetX, int $incX, Buffer $Y, int $offsetY, int $incY) : float|object
+    {
+        if (!$this->realDevice($X,$Y) || $X->dtype()!=$Y->dtype()) return parent::dot($n,$X,$offsetX,$incX,$Y,$offsetY,$incY);
+        $this->assertShapeParameter('n',$n);
+        $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
+        $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
+        $out = \FFI::new('double');
+        CudaFFI::check(CudaFFI::lib()->rb200_dot($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,
+            $Y->devicePtr(),$offsetY,$incY,\FFI::addr($out)));
+        return $out->cdata;
     }
 
     public function gemv(int $order, int $trans, int $m, int $n, float|object $alpha,
@@ -181,7 +247,7 @@ class CudaBlas extends PhpBlas
         $this->assertVectorBufferSpec('Y', $Y, (!$t) ? $m : $n, $offsetY, $incY);
         $alpha = $this->cleanFloatNumber($alpha,'alpha');
         $beta = $this->cleanFloatNumber($beta,'beta');
-        CudaFFI::check(CudaFFI::lib()->rb200_gemv($A->dtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
+        CudaFFI::check(CudaFFI::lib()->rb200_gemv($A->abiDtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
             $A->devicePtr(),$offsetA,$ldA,$X->devicePtr(),$offsetX,$incX,$beta,$Y->devicePtrRW(),$offsetY,$incY));
     }
 
@@ -206,7 +272,7 @@ class CudaBlas extends PhpBlas
             throw new InvalidArgumentException("Unmatch data type for A and B");
         }
         $alpha = $this->cleanFloatNumber($alpha,'alpha');
-        CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->dtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
+        CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->abiDtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
             $A->devicePtr(),$offsetA,$ldA,$B->devicePtrRW(),$offsetB,$ldB));
     }
 }

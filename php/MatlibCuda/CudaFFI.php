@@ -50,6 +50,14 @@ class CudaFFI
                        void* Y, int64_t offY, int64_t incY);
         int rb200_copy(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
                        void* Y, int64_t offY, int64_t incY);
+        int rb200_swap(int dtype, int64_t n, void* X, int64_t offX, int64_t incX,
+                       void* Y, int64_t offY, int64_t incY);
+        int rb200_asum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+        int rb200_nrm2(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result);
+        int rb200_dot(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
+                      const void* Y, int64_t offY, int64_t incY, double* result);
+        int rb200_iamax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
+        int rb200_iamin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result);
         int rb200_gemv(int dtype, int order, int trans, int64_t m, int64_t n, double alpha,
                        const void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX,
                        double beta, void* Y, int64_t offY, int64_t incY);

@@ -740,24 +740,23 @@ int rb200_imin(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, 
     return scalar_reduce_dispatch<SR_IMIN>(dtype, n, X, offX, incX, result);
 }
 
-static int scalar_double(int rc, int64_t bits, double* result)
-{
-    if (rc == RB200_OK) memcpy(result, &bits, sizeof(double));
-    return rc;
-}
 
 int rb200_asum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result)
 {
     int64_t bits = 0;
     if (!result) RB_INVALID("result is NULL");
-    return scalar_double(scalar_reduce_dispatch<SR_ASUM>(dtype, n, X, offX, incX, &bits), bits, result);
+    const int rc = scalar_reduce_dispatch<SR_ASUM>(dtype, n, X, offX, incX, &bits);
+    if (rc == RB200_OK) memcpy(result, &bits, sizeof(double));
+    return rc;
 }
 
 int rb200_nrm2(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, double* result)
 {
     int64_t bits = 0;
     if (!result) RB_INVALID("result is NULL");
-    return scalar_double(scalar_reduce_dispatch<SR_NRM2>(dtype, n, X, offX, incX, &bits), bits, result);
+    const int rc = scalar_reduce_dispatch<SR_NRM2>(dtype, n, X, offX, incX, &bits);
+    if (rc == RB200_OK) memcpy(result, &bits, sizeof(double));
+    return rc;
 }
 
 int rb200_dot(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
@@ -765,7 +764,9 @@ int rb200_dot(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX,
 {
     int64_t bits = 0;
     if (!result) RB_INVALID("result is NULL");
-    return scalar_double(scalar_reduce_dispatch<SR_DOT>(dtype, n, X, offX, incX, &bits, Y, offY, incY), bits, result);
+    const int rc = scalar_reduce_dispatch<SR_DOT>(dtype, n, X, offX, incX, &bits, Y, offY, incY);
+    if (rc == RB200_OK) memcpy(result, &bits, sizeof(double));
+    return rc;
 }
 
 int rb200_iamax(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int64_t* result)

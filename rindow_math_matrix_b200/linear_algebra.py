@@ -93,6 +93,37 @@ class LinearAlgebra:
         self.blas.axpy(X.size(), alpha, X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
         return Y
 
+    # ---- BLAS level-1 reductions and swap (LinearAlgebra.php:374-530, :842-858) ---------------------------
+    def dot(self, X: NDArray, Y: NDArray, conj=None):                            # :374-398 (real dtypes)
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException(self._shape_error(X, Y))
+        return self.blas.dot(X.size(), X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+
+    def asum(self, X: NDArray) -> float:                                         # :403-410
+        return self.blas.asum(X.size(), X.buffer(), X.offset(), 1)
+
+    def iamax(self, X: NDArray) -> int:                                          # :415-422
+        return self.blas.iamax(X.size(), X.buffer(), X.offset(), 1)
+
+    def iamin(self, X: NDArray) -> int:                                          # :427-438 (hasIamin() is true here)
+        return self.blas.iamin(X.size(), X.buffer(), X.offset(), 1)
+
+    def amax(self, X: NDArray) -> float:                                         # :480-492: |X[iamax]|, read from the buffer
+        i = self.blas.iamax(X.size(), X.buffer(), X.offset(), 1)
+        return abs(X.buffer()[X.offset() + i])
+
+    def amin(self, X: NDArray) -> float:                                         # :497-513
+        i = self.blas.iamin(X.size(), X.buffer(), X.offset(), 1)
+        return abs(X.buffer()[X.offset() + i])
+
+    def nrm2(self, X: NDArray) -> float:                                         # :518-527
+        return self.blas.nrm2(X.size(), X.buffer(), X.offset(), 1)
+
+    def swap(self, X: NDArray, Y: NDArray) -> None:                              # :842-858
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException(self._shape_error(X, Y))
+        self.blas.swap(X.size(), X.buffer(), X.offset(), 1, Y.buffer(), Y.offset(), 1)
+
     # ---- y := alpha * Ax + beta * y   (LinearAlgebra.php:861-923) -------------------------------------
     def gemv(self, A: NDArray, X: NDArray, alpha=None, beta=None, Y: NDArray | None = None,
              trans=None, conj=None) -> NDArray:

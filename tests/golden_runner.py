@@ -157,6 +157,8 @@ def run_case(case, service):
                                                   **step.get("kwargs", {}))
             for i, want in case.get("untouched", {}).items():
                 _assert_equal(want, args[int(i)].toArray())
+            for i, want in case.get("args_after", {}).items():       # in-place results (swap)
+                _assert_equal(want, args[int(i)].toArray())
             return out
         raise AssertionError("unknown op " + op)
 

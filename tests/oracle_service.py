@@ -69,6 +69,27 @@ class OracleBlas:
     def hasOmatcopy(self):
         return True
 
+    def hasIamin(self):
+        return True
+
+    def dot(self, n, X, offX, incX, Y, offY, incY):
+        return _wrap(oracle.dot, n, X.f64(), offX, incX, Y.f64(), offY, incY)
+
+    def asum(self, n, X, offX, incX):
+        return _wrap(oracle.asum, n, X.f64(), offX, incX)
+
+    def nrm2(self, n, X, offX, incX):
+        return _wrap(oracle.nrm2, n, X.f64(), offX, incX)
+
+    def iamax(self, n, X, offX, incX):
+        return _wrap(oracle.iamax, n, X.f64(), offX, incX)
+
+    def iamin(self, n, X, offX, incX):
+        return _wrap(oracle.iamin, n, X.f64(), offX, incX)
+
+    def swap(self, n, X, offX, incX, Y, offY, incY):
+        _wrap(oracle.swap, n, X.f64(), offX, incX, Y.f64(), offY, incY)
+
     def gemm(self, order, transA, transB, m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC):
         _wrap(oracle.gemm, order, transA, transB, m, n, k, alpha, A.f64(), offA, ldA, B.f64(), offB, ldB,
               beta, C.f64(), offC, ldC)

@@ -267,3 +267,78 @@ def test_matmul_uses_one_batched_launch(cuda_service, oracle_service):
     got2 = la.matmul(a, la.array(B2))
     ref2 = np.asarray(lo.matmul(lo.array(A), lo.array(B2)).toArray(), np.float64)
     assert np.max(np.abs(got2.to_numpy() - ref2)) < 5e-6 * np.max(np.abs(ref2))
+
+
+# ---------------------------------------------------------------------------------------------------
+# BLAS level-1 reductions and swap (PhpBlas.php:196-222, :266-348, :366-392, :744-760)
+# ---------------------------------------------------------------------------------------------------
+RED = VEC + [((1 << 24) + 5, 1, 1, 0, 0)]
+RED_DT = {dtypes.float32: np.float32, dtypes.float64: np.float64, dtypes.int32: np.int32}
+
+
+@pytest.mark.parametrize("n,incX,incY,offX,offY", RED, ids=[str(v) for v in RED])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32])
+def test_level1_reductions_vs_oracle(n, incX, incY, offX, offY, dt, cuda_service):
+    """asum / nrm2 / dot: terms and sums in double on both sides; the device adds them as a tree, the oracle in
+    index order -- 1e-12 relative to the sum of magnitudes covers the reassociation.  iamax / iamin: exact."""
+    rng = np.random.default_rng(n * 7 + incX)
+    npdt = RED_DT[dt]
+    blas = cuda_service.blas()
+    if dt == dtypes.int32:
+        x = rng.integers(-1000, 1000, offX + (n - 1) * incX + 4).astype(npdt)
+        y = rng.integers(-1000, 1000, offY + (n - 1) * incY + 4).astype(npdt)
+    else:
+        x, y = _vec(rng, n, incX, offX, npdt), _vec(rng, n, incY, offY, npdt)
+    X, Y = buf(x, dt), buf(y, dt)
+    xo, yo = oracle.as_buffer(x), oracle.as_buffer(y)
+    xs, ys = xo[offX:offX + (n - 1) * incX + 1:incX], yo[offY:offY + (n - 1) * incY + 1:incY]
+    mag = float(np.sum(np.abs(xs)))
+    assert abs(blas.asum(n, X, offX, incX) - oracle.asum(n, xo, offX, incX)) <= 1e-12 * mag
+    ref = oracle.nrm2(n, xo, offX, incX)
+    assert abs(blas.nrm2(n, X, offX, incX) - ref) <= 1e-12 * max(ref, 1.0)
+    assert abs(blas.dot(n, X, offX, incX, Y, offY, incY) - oracle.dot(n, xo, offX, incX, yo, offY, incY)) <= \
+        1e-12 * float(np.sum(np.abs(xs * ys)))
+    assert blas.iamax(n, X, offX, incX) == oracle.iamax(n, xo, offX, incX)
+    assert blas.iamin(n, X, offX, incX) == oracle.iamin(n, xo, offX, incX)
+    assert np.array_equal(X.to_numpy(), x) and np.array_equal(Y.to_numpy(), y)       # operands untouched
+
+
+def test_iamax_iamin_ties_and_nonfinite(cuda_service):
+    """First index on ties; a NaN at element 0 stays, a later NaN never wins (PhpBlas.php:296-314, :327-345)."""
+    blas = cuda_service.blas()
+    nan, inf = float("nan"), float("inf")
+    cases = [[3, -3, 3, 1], [1, -5, 5, 5], [0, 0, 0], [nan, 9, -10], [1, nan, -7, nan, 7], [2, -inf, inf, 1],
+             [5, nan, nan], [nan, nan], [-0.0, 0.0, 1]]
+    big = np.ones(100003, np.float32)
+    big[[77, 5000, 99999]] = [-4, 4, 4]
+    cases.append(big.tolist())
+    for c in cases:
+        x = np.asarray(c, np.float32)
+        X = buf(x, dtypes.float32)
+        xo = oracle.as_buffer(x)
+        assert blas.iamax(x.size, X, 0, 1) == oracle.iamax(x.size, xo, 0, 1), c[:8]
+        assert blas.iamin(x.size, X, 0, 1) == oracle.iamin(x.size, xo, 0, 1), c[:8]
+
+
+@pytest.mark.parametrize("n,incX,incY,offX,offY", VEC, ids=[str(v) for v in VEC])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_swap_vs_oracle(n, incX, incY, offX, offY, dt, cuda_service):
+    rng = np.random.default_rng(n + 3 * incY)
+    npdt = NP[dt]
+    x, y = _vec(rng, n, incX, offX, npdt), _vec(rng, n, incY, offY, npdt)
+    X, Y = buf(x, dt), buf(y, dt)
+    cuda_service.blas().swap(n, X, offX, incX, Y, offY, incY)
+    xr, yr = oracle.as_buffer(x), oracle.as_buffer(y)
+    oracle.swap(n, xr, offX, incX, yr, offY, incY)
+    assert np.array_equal(X.to_numpy(), xr.astype(npdt)) and np.array_equal(Y.to_numpy(), yr.astype(npdt))
+
+
+def test_level1_argument_errors(cuda_service):
+    blas = cuda_service.blas()
+    X = buf(np.zeros(4, np.float32), dtypes.float32)
+    with pytest.raises(InvalidArgumentException, match="Argument n must be greater than 0."):
+        blas.asum(0, X, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Vector specification too large for bufferX."):
+        blas.nrm2(5, X, 0, 1)
+    with pytest.raises(InvalidArgumentException, match="Vector specification too large for bufferY."):
+        blas.dot(3, X, 0, 1, X, 2, 1)
