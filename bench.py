@@ -491,6 +491,42 @@ def run_b200(args):
         except Exception:
             pass
 
+    # ---- config C1: MatrixOperator::cross 256x256 float32 (the reference's own CPU-runnable case): latency -----
+    cross_256 = None
+    if rank == 0 and not args.quick:
+        try:
+            from rindow_math_matrix_b200 import MatrixOperator
+            mo = MatrixOperator(svc)
+            blas.setGemmMode(rb.GEMM_AUTO)
+            a256 = np.random.default_rng(1234).uniform(-1, 1, (256, 256)).astype(np.float32)
+            b256 = np.random.default_rng(1235).uniform(-1, 1, (256, 256)).astype(np.float32)
+            A2, B2 = mo.array(a256), mo.array(b256)
+            reps = 50
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    mo.cross(A2, B2)
+                _capi.sync()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    out256 = mo.cross(A2, B2)
+                _capi.sync()
+                host_us = (time.perf_counter() - t0) / reps * 1e6
+            got = out256.to_numpy().astype(np.float64)
+            ref = a256.astype(np.float64) @ b256.astype(np.float64)
+            cross_256 = {"us_per_call": host_us, "calls": reps, "path": _capi.last_gemm_path(),
+                         "max_rel_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
+                         "note": "MatrixOperator.cross on device-resident operands, wall clock per call incl. the "
+                                 "zero-filled C allocation the reference does (MatrixOperator.php:479-503); launch bound"}
+            if world == 1 and not args.no_cpu_baseline:
+                import oracle
+                co = np.zeros(256 * 256)
+                t0 = time.perf_counter()
+                oracle.gemm_rows(0, 256, 256, 256, 1.0, oracle.as_buffer(a256), 256, oracle.as_buffer(b256), 256, 1.0, co, 256)
+                cross_256["oracle_port_us"] = (time.perf_counter() - t0) * 1e6
+        except Exception as e:  # pragma: no cover
+            cross_256 = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        gemm_step()                                    # leave the library in the headline mode
+
     log("rank %d/%d: %.2f ms/step, %.1f TFLOP/s aggregate" % (rank, world, ms_per_step, value))
     if rank == 0:
         line = {
@@ -502,7 +538,7 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(n, world, args.mode),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(), "gemm_modes": gemm_modes, "sgemm_sweep": sweep, "hbm_ops": hbm_ops,
-            "with_gather": with_gather,
+            "with_gather": with_gather, "cross_256": cross_256,
             "peaks": peaks,
         }
         emit(line)
@@ -603,6 +639,16 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
            {"shape": "[65536,1024] axis=0 (split + merge path)"})
     report("softmax", lambda i: math.softmax(m, n, Rs[i], 0, n), 2 * m * n * 4, {"shape": "[65536,1024] in place"})
     del Rs
+    # Conv3D sibling of C4: clips [8,16,112,112,3], 3x3x3 valid -> cols [8,14,110,110,3,3,3,3] (440 MB)
+    b3, d3, h3, w3, c3 = 8, 16, 112, 112, 3
+    vol = np.random.default_rng(4101 + rank).uniform(0, 1, b3 * d3 * h3 * w3 * c3).astype(np.float32)
+    V3 = [CudaBuffer(vol.size, dtypes.float32, zero=False).from_numpy(vol) for _ in range(sets)]
+    n3 = b3 * (d3 - 2) * (h3 - 2) * (w3 - 2) * 81
+    C3 = CudaBuffer(n3, dtypes.float32, zero=False)
+    report("im2col3d", lambda i: math.im2col3d(False, V3[i], 0, vol.size, b3, d3, h3, w3, c3, 3, 3, 3, 1, 1, 1, False, False,
+                                                1, 1, 1, False, C3, 0, n3), (vol.size + n3) * 4,
+           {"shape": "8x16x112x112x3, 3x3x3 valid -> [8,14,110,110,3,3,3,3]"})
+    del V3, C3
     # C4: im2col2d 64x224x224x3, 3x3, stride 1, valid padding
     b, h, w, c = 64, 224, 224, 3
     img = np.random.default_rng(4001 + rank).uniform(0, 1, b * h * w * c).astype(np.float32)

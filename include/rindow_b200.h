@@ -325,6 +325,22 @@ int rb200_im2col2d(int dtype, int reverse,
                    int cols_channels_first,
                    void* cols, int64_t cols_offset, int64_t cols_size);
 
+/* ---- im2col3d / col2im3d: PhpMath::im2col3d (PhpMath.php:2396-2600, copyCell3d :2319-2390), the Conv3D sibling.
+ *      images [b,d,h,w,c] (channels_first: [b,c,d,h,w]); cols [b,od,oh,ow,kd,kh,kw,c] (cols_channels_first:
+ *      [b,od,oh,ow,c,kd,kh,kw]).  Same out / padding rules per axis as im2col2d, including the reference's
+ *      padding_d, which is computed from im_h (:2459).  Forward is a bit-exact copy for every dtype; reverse
+ *      accumulates in the reference's loop order (float32/float64/int32/int64).
+ *      im2col1d (PhpMath.php:1967-2088) needs no entry of its own: it is rb200_im2col2d with im_h = filter_h = 1. */
+int rb200_im2col3d(int dtype, int reverse,
+                   void* images, int64_t images_offset, int64_t images_size,
+                   int64_t batches, int64_t im_d, int64_t im_h, int64_t im_w, int64_t channels,
+                   int64_t filter_d, int64_t filter_h, int64_t filter_w,
+                   int64_t stride_d, int64_t stride_h, int64_t stride_w,
+                   int padding, int channels_first,
+                   int64_t dilation_d, int64_t dilation_h, int64_t dilation_w,
+                   int cols_channels_first,
+                   void* cols, int64_t cols_offset, int64_t cols_size);
+
 /* ---- fused conv2d forward (precedent for a fused entry in the reference:
  *      LinearAlgebraCL::im2col2dclblast, src/LinearAlgebraCL.php:5001).  Computes exactly what
  *      LinearAlgebra::im2col (src/LinearAlgebra.php:3369) + gemm (:925) (+ add, :1968) compute for the

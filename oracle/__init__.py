@@ -78,6 +78,9 @@ def lib() -> ctypes.CDLL:
         L.ro_softmax.argtypes = [i64, i64, p, i64, i64, i64]
         L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
+        L.ro_im2col1d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i32, i32, i64, i32, p, i64, i64, i64]
+        L.ro_im2col3d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
+                                  i32, i32, i64, i64, i64, i32, p, i64, i64, i64]
         L.ro_broadcast.argtypes = [i32, i32, i64, i64, p, i64, i64, i64, p, i64, i64, i64]
         L.ro_unary.argtypes = [i32, i64, dbl, p, i64, i64, i64, dbl]
         L.ro_compare.argtypes = [i32, i64, p, i64, i64, i64, p, i64, i64, i64]
@@ -88,7 +91,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -330,6 +333,24 @@ def im2col2d(reverse, images, images_offset, images_size, batches, im_h, im_w, c
                              images_size, batches, im_h, im_w, channels, filter_h, filter_w,
                              stride_h, stride_w, int(bool(padding)), int(bool(channels_first)),
                              dilation_h, dilation_w, int(bool(cols_channels_first)),
+                             _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
+
+
+# PhpMath::im2col1d :1967-2088, im2col3d :2396-2600
+def im2col1d(reverse, images, images_offset, images_size, batches, im_w, channels, filter_w, stride_w, padding,
+             channels_first, dilation_w, cols_channels_first, cols, cols_offset, cols_size):
+    _check(lib().ro_im2col1d(int(bool(reverse)), _ptr(_buf(images)), images.size, images_offset, images_size,
+                             batches, im_w, channels, filter_w, stride_w, int(bool(padding)), int(bool(channels_first)),
+                             dilation_w, int(bool(cols_channels_first)), _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
+
+
+def im2col3d(reverse, images, images_offset, images_size, batches, im_d, im_h, im_w, channels,
+             filter_d, filter_h, filter_w, stride_d, stride_h, stride_w, padding, channels_first,
+             dilation_d, dilation_h, dilation_w, cols_channels_first, cols, cols_offset, cols_size):
+    _check(lib().ro_im2col3d(int(bool(reverse)), _ptr(_buf(images)), images.size, images_offset, images_size,
+                             batches, im_d, im_h, im_w, channels, filter_d, filter_h, filter_w,
+                             stride_d, stride_h, stride_w, int(bool(padding)), int(bool(channels_first)),
+                             dilation_d, dilation_h, dilation_w, int(bool(cols_channels_first)),
                              _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
 
 

@@ -447,6 +447,161 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::im2col1d, PhpMath.php:1967-2088 (copyCell1d :1912-1958): the loops of im2col2d without the y axis. */
+int ro_im2col1d(int reverse,
+                double *images, int64_t count_images, int64_t images_offset, int64_t images_size,
+                int64_t batches, int64_t im_w, int64_t channels, int64_t filter_w, int64_t stride_w,
+                int padding, int channels_first, int64_t dilation_w, int cols_channels_first,
+                double *cols, int64_t count_cols, int64_t cols_offset, int64_t cols_size)
+{
+    int64_t images_buf_size = batches * im_w * channels;
+    if (images_size != images_buf_size || count_images - images_offset < images_buf_size) return RO_E_ARG;
+    int64_t out_w = (im_w - (filter_w - 1) * dilation_w - 1) / stride_w + 1;
+    if (out_w <= 0) return RO_E_ARG;
+    int64_t out_buf_size, padding_w;
+    if (padding) {
+        out_buf_size = batches * im_w * filter_w * channels;
+        padding_w = ((im_w - 1) * stride_w - im_w + (filter_w - 1) * dilation_w + 1) / 2;
+        out_w = im_w;
+    } else {
+        out_buf_size = batches * out_w * filter_w * channels;
+        padding_w = 0;
+    }
+    if (cols_size != out_buf_size || count_cols - cols_offset != out_buf_size) return RO_E_ARG;
+    int64_t im_w_step, channel_step, batch_step;
+    if (channels_first) { im_w_step = 1; channel_step = im_w; batch_step = im_w * channels; }
+    else { channel_step = 1; im_w_step = channels; batch_step = channels * im_w; }
+    int64_t stride_w_step = im_w_step * stride_w, filter_w_step = im_w_step * dilation_w;
+    int64_t out_filter_step, out_channel_step;
+    if (cols_channels_first) { out_filter_step = 1; out_channel_step = filter_w; }
+    else { out_filter_step = channels; out_channel_step = 1; }
+    int64_t out_cell_step = filter_w * channels;
+    int64_t batch_pos = images_offset - im_w_step * padding_w;
+    int64_t out_pos = cols_offset;
+    int64_t vim_w = out_w * stride_w, vfilter_w = filter_w * dilation_w;
+    for (int64_t batch = 0; batch < batches; batch++) {
+        int64_t stride_w_pos = batch_pos;
+        for (int64_t vim_x = 0; vim_x < vim_w; vim_x += stride_w) {
+            /* copyCell1d */
+            int64_t filter_w_pos = stride_w_pos, out_filter_pos = out_pos;
+            for (int64_t vfx = 0; vfx < vfilter_w; vfx += dilation_w) {
+                int64_t channel_pos = filter_w_pos, out_channel_pos = out_filter_pos;
+                int64_t input_x = vim_x - padding_w + vfx;
+                for (int64_t c = 0; c < channels; c++) {
+                    if (input_x < 0 || input_x >= im_w) {
+                        if (!reverse) cols[out_channel_pos] = 0;
+                    } else if (!reverse) {
+                        cols[out_channel_pos] = images[channel_pos];
+                    } else {
+                        images[channel_pos] += cols[out_channel_pos];
+                    }
+                    out_channel_pos += out_channel_step;
+                    channel_pos += channel_step;
+                }
+                out_filter_pos += out_filter_step;
+                filter_w_pos += filter_w_step;
+            }
+            stride_w_pos += stride_w_step;
+            out_pos += out_cell_step;
+        }
+        batch_pos += batch_step;
+    }
+    return RO_OK;
+}
+
+/* PhpMath::im2col3d, PhpMath.php:2396-2600 (copyCell3d :2319-2390).  padding_d uses im_h as the reference does (:2459),
+ * and only out_h / out_w are tested (:2453). */
+int ro_im2col3d(int reverse,
+                double *images, int64_t count_images, int64_t images_offset, int64_t images_size,
+                int64_t batches, int64_t im_d, int64_t im_h, int64_t im_w, int64_t channels,
+                int64_t filter_d, int64_t filter_h, int64_t filter_w,
+                int64_t stride_d, int64_t stride_h, int64_t stride_w,
+                int padding, int channels_first, int64_t dilation_d, int64_t dilation_h, int64_t dilation_w,
+                int cols_channels_first,
+                double *cols, int64_t count_cols, int64_t cols_offset, int64_t cols_size)
+{
+    int64_t images_buf_size = batches * im_d * im_h * im_w * channels;
+    if (images_size != images_buf_size || count_images - images_offset < images_buf_size) return RO_E_ARG;
+    int64_t out_d = (im_d - (filter_d - 1) * dilation_d - 1) / stride_d + 1;
+    int64_t out_h = (im_h - (filter_h - 1) * dilation_h - 1) / stride_h + 1;
+    int64_t out_w = (im_w - (filter_w - 1) * dilation_w - 1) / stride_w + 1;
+    if (out_h <= 0 || out_w <= 0) return RO_E_ARG;
+    int64_t out_buf_size, padding_d, padding_h, padding_w;
+    if (padding) {
+        out_buf_size = batches * im_d * filter_d * im_h * filter_h * im_w * filter_w * channels;
+        padding_d = ((im_d - 1) * stride_d - im_h + (filter_d - 1) * dilation_d + 1) / 2;
+        padding_h = ((im_h - 1) * stride_h - im_h + (filter_h - 1) * dilation_h + 1) / 2;
+        padding_w = ((im_w - 1) * stride_w - im_w + (filter_w - 1) * dilation_w + 1) / 2;
+        out_d = im_d; out_h = im_h; out_w = im_w;
+    } else {
+        out_buf_size = batches * out_d * filter_d * out_h * filter_h * out_w * filter_w * channels;
+        padding_d = padding_h = padding_w = 0;
+    }
+    if (cols_size != out_buf_size || count_cols - cols_offset != out_buf_size) return RO_E_ARG;
+    int64_t im_w_step, im_h_step, im_d_step, channel_step, batch_step;
+    if (channels_first) {
+        im_w_step = 1; im_h_step = im_w; im_d_step = im_w * im_h; channel_step = im_w * im_h * im_d;
+        batch_step = im_w * im_h * im_d * channels;
+    } else {
+        channel_step = 1; im_w_step = channels; im_h_step = channels * im_w; im_d_step = channels * im_w * im_h;
+        batch_step = channels * im_w * im_h * im_d;
+    }
+    int64_t stride_w_step = im_w_step * stride_w, stride_h_step = im_h_step * stride_h, stride_d_step = im_d_step * stride_d;
+    int64_t filter_w_step = im_w_step * dilation_w, filter_h_step = im_h_step * dilation_h, filter_d_step = im_d_step * dilation_d;
+    int64_t out_filter_step, out_channel_step;
+    if (cols_channels_first) { out_filter_step = 1; out_channel_step = filter_d * filter_h * filter_w; }
+    else { out_filter_step = channels; out_channel_step = 1; }
+    int64_t out_cell_step = filter_d * filter_h * filter_w * channels;
+    int64_t batch_pos = images_offset - im_d_step * padding_d - im_h_step * padding_h - im_w_step * padding_w;
+    int64_t out_pos = cols_offset;
+    int64_t vim_d = out_d * stride_d, vim_h = out_h * stride_h, vim_w = out_w * stride_w;
+    int64_t vfilter_d = filter_d * dilation_d, vfilter_h = filter_h * dilation_h, vfilter_w = filter_w * dilation_w;
+    for (int64_t batch = 0; batch < batches; batch++) {
+        int64_t stride_d_pos = batch_pos;
+        for (int64_t vim_z = 0; vim_z < vim_d; vim_z += stride_d) {
+            int64_t stride_h_pos = stride_d_pos;
+            for (int64_t vim_y = 0; vim_y < vim_h; vim_y += stride_h) {
+                int64_t stride_w_pos = stride_h_pos;
+                for (int64_t vim_x = 0; vim_x < vim_w; vim_x += stride_w) {
+                    /* copyCell3d */
+                    int64_t filter_d_pos = stride_w_pos, out_filter_pos = out_pos;
+                    for (int64_t vfz = 0; vfz < vfilter_d; vfz += dilation_d) {
+                        int64_t filter_h_pos = filter_d_pos;
+                        for (int64_t vfy = 0; vfy < vfilter_h; vfy += dilation_h) {
+                            int64_t filter_w_pos = filter_h_pos;
+                            for (int64_t vfx = 0; vfx < vfilter_w; vfx += dilation_w) {
+                                int64_t channel_pos = filter_w_pos, out_channel_pos = out_filter_pos;
+                                int64_t iz = vim_z - padding_d + vfz, iy = vim_y - padding_h + vfy, ix = vim_x - padding_w + vfx;
+                                for (int64_t c = 0; c < channels; c++) {
+                                    if (iz < 0 || iz >= im_d || iy < 0 || iy >= im_h || ix < 0 || ix >= im_w) {
+                                        if (!reverse) cols[out_channel_pos] = 0;
+                                    } else if (!reverse) {
+                                        cols[out_channel_pos] = images[channel_pos];
+                                    } else {
+                                        images[channel_pos] += cols[out_channel_pos];
+                                    }
+                                    out_channel_pos += out_channel_step;
+                                    channel_pos += channel_step;
+                                }
+                                out_filter_pos += out_filter_step;
+                                filter_w_pos += filter_w_step;
+                            }
+                            filter_h_pos += filter_h_step;
+                        }
+                        filter_d_pos += filter_d_step;
+                    }
+                    stride_w_pos += stride_w_step;
+                    out_pos += out_cell_step;
+                }
+                stride_h_pos += stride_h_step;
+            }
+            stride_d_pos += stride_d_step;
+        }
+        batch_pos += batch_step;
+    }
+    return RO_OK;
+}
+
 /* ---- BLAS level 1 / 2 and omatcopy (SURVEY.md section 8f widening) ------------------------------- */
 
 /* PhpBlas::scal, PhpBlas.php:141-161 (real path :156-159): X[i] = X[i] * alpha */

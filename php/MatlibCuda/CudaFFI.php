@@ -111,6 +111,12 @@ class CudaFFI
                            int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
                            int cols_channels_first,
                            void* cols, int64_t cols_offset, int64_t cols_size);
+        int rb200_im2col3d(int dtype, int reverse, void* images, int64_t images_offset, int64_t images_size,
+                           int64_t batches, int64_t im_d, int64_t im_h, int64_t im_w, int64_t channels,
+                           int64_t filter_d, int64_t filter_h, int64_t filter_w,
+                           int64_t stride_d, int64_t stride_h, int64_t stride_w, int padding, int channels_first,
+                           int64_t dilation_d, int64_t dilation_h, int64_t dilation_w, int cols_channels_first,
+                           void* cols, int64_t cols_offset, int64_t cols_size);
         CDEF;
 
     public static function lib() : FFI

@@ -119,6 +119,68 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** im2col1d (PhpMath.php:1967-2088) is im2col2d with one row of height 1: same layouts, same copy */
+    public function im2col1d(bool $reverse,Buffer $images,int $images_offset,int $images_size,int $batches,
+        int $im_w,int $channels,int $filter_w,int $stride_w,bool $padding,bool $channels_first,int $dilation_w,
+        bool $cols_channels_first,Buffer $cols,int $cols_offset,int $cols_size) : void
+    {
+        if (!($images instanceof CudaBuffer) || !($cols instanceof CudaBuffer)) {
+            parent::im2col1d($reverse,$images,$images_offset,$images_size,$batches,$im_w,$channels,$filter_w,$stride_w,
+                $padding,$channels_first,$dilation_w,$cols_channels_first,$cols,$cols_offset,$cols_size);
+            return;
+        }
+        $images_buf_size = $batches*$im_w*$channels;
+        if ($images_size!=$images_buf_size || count($images)-$images_offset<$images_buf_size) {
+            throw new InvalidArgumentException('images buffer size is invalid');
+        }
+        $out_w = intdiv(($im_w-($filter_w-1)*$dilation_w-1),$stride_w)+1;
+        if ($out_w<=0) {
+            throw new InvalidArgumentException('Invalid shape or parameters.');
+        }
+        $out_buf_size = $batches*($padding ? $im_w : $out_w)*$filter_w*$channels;
+        if ($cols_size!=$out_buf_size || count($cols)-$cols_offset!=$out_buf_size) {
+            throw new InvalidArgumentException('output buffer size is invalid');
+        }
+        $this->im2col2d($reverse,$images,$images_offset,$images_size,$batches,1,$im_w,$channels,1,$filter_w,1,$stride_w,
+            $padding,$channels_first,1,$dilation_w,$cols_channels_first,$cols,$cols_offset,$cols_size);
+    }
+
+    /** im2col3d (PhpMath.php:2396-2600) */
+    public function im2col3d(bool $reverse,Buffer $images,int $images_offset,int $images_size,int $batches,
+        int $im_d,int $im_h,int $im_w,int $channels,int $filter_d,int $filter_h,int $filter_w,
+        int $stride_d,int $stride_h,int $stride_w,bool $padding,bool $channels_first,
+        int $dilation_d,int $dilation_h,int $dilation_w,bool $cols_channels_first,
+        Buffer $cols,int $cols_offset,int $cols_size) : void
+    {
+        if (!($images instanceof CudaBuffer) || !($cols instanceof CudaBuffer)) {
+            parent::im2col3d($reverse,$images,$images_offset,$images_size,$batches,$im_d,$im_h,$im_w,$channels,
+                $filter_d,$filter_h,$filter_w,$stride_d,$stride_h,$stride_w,$padding,$channels_first,
+                $dilation_d,$dilation_h,$dilation_w,$cols_channels_first,$cols,$cols_offset,$cols_size);
+            return;
+        }
+        $images_buf_size = $batches*$im_d*$im_h*$im_w*$channels;
+        if ($images_size!=$images_buf_size || count($images)-$images_offset<$images_buf_size) {
+            throw new InvalidArgumentException('images buffer size is invalid');
+        }
+        $out_d = intdiv(($im_d-($filter_d-1)*$dilation_d-1),$stride_d)+1;
+        $out_h = intdiv(($im_h-($filter_h-1)*$dilation_h-1),$stride_h)+1;
+        $out_w = intdiv(($im_w-($filter_w-1)*$dilation_w-1),$stride_w)+1;
+        if ($out_h<=0 || $out_w<=0) {
+            throw new InvalidArgumentException('Invalid shape or parameters.');
+        }
+        $out_buf_size = $padding ? $batches*$im_d*$filter_d*$im_h*$filter_h*$im_w*$filter_w*$channels
+                                 : $batches*$out_d*$filter_d*$out_h*$filter_h*$out_w*$filter_w*$channels;
+        if ($cols_size!=$out_buf_size || count($cols)-$cols_offset!=$out_buf_size) {
+            throw new InvalidArgumentException('output buffer size is invalid');
+        }
+        $im = $reverse ? $images->devicePtrRW() : $images->devicePtr();
+        $co = $reverse ? $cols->devicePtr() : $cols->devicePtrRW();
+        CudaFFI::check(CudaFFI::lib()->rb200_im2col3d($images->abiDtype(),$reverse?1:0,$im,$images_offset,$images_size,
+            $batches,$im_d,$im_h,$im_w,$channels,$filter_d,$filter_h,$filter_w,$stride_d,$stride_h,$stride_w,
+            $padding?1:0,$channels_first?1:0,$dilation_d,$dilation_h,$dilation_w,$cols_channels_first?1:0,
+            $co,$cols_offset,$cols_size));
+    }
+
     // ---- SURVEY.md section 8(f) widening: the rest of the broadcast family, the unary family, equal / notEqual /
     //      not, astype, sum / imax / imin, updateAddOnehot.  Op codes: RB200_BC_* / RB200_UN_* / RB200_CMP_*
     //      of include/rindow_b200.h.  Validation and messages are PhpMath's own (PhpMath.php:274-528, 687-722,

@@ -396,6 +396,52 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- im2col1d (PhpMath.php:1967-2088): the same copy as im2col2d with one row of height 1 ----------------
+    def im2col1d(self, reverse, images, images_offset, images_size, batches, im_w, channels, filter_w, stride_w,
+                 padding, channels_first, dilation_w, cols_channels_first, cols, cols_offset, cols_size) -> None:
+        images_buf_size = batches * im_w * channels
+        if images_size != images_buf_size or len(images) - images_offset < images_buf_size:
+            raise InvalidArgumentException("images buffer size is invalid")
+        out_w = int((im_w - (filter_w - 1) * dilation_w - 1) / stride_w) + 1
+        if out_w <= 0:
+            raise InvalidArgumentException("Invalid shape or parameters.")
+        out_buf_size = batches * (im_w if padding else out_w) * filter_w * channels
+        if cols_size != out_buf_size or len(cols) - cols_offset != out_buf_size:
+            raise InvalidArgumentException("output buffer size is invalid")
+        self.im2col2d(reverse, images, images_offset, images_size, batches, 1, im_w, channels, 1, filter_w, 1, stride_w,
+                      padding, channels_first, 1, dilation_w, cols_channels_first, cols, cols_offset, cols_size)
+
+    # ---- im2col3d (PhpMath.php:2396-2600) ---------------------------------------------------------------------
+    def im2col3d(self, reverse, images, images_offset, images_size, batches, im_d, im_h, im_w, channels,
+                 filter_d, filter_h, filter_w, stride_d, stride_h, stride_w, padding, channels_first,
+                 dilation_d, dilation_h, dilation_w, cols_channels_first, cols, cols_offset, cols_size) -> None:
+        images_buf_size = batches * im_d * im_h * im_w * channels
+        if images_size != images_buf_size or len(images) - images_offset < images_buf_size:
+            raise InvalidArgumentException("images buffer size is invalid")
+        out_d = int((im_d - (filter_d - 1) * dilation_d - 1) / stride_d) + 1
+        out_h = int((im_h - (filter_h - 1) * dilation_h - 1) / stride_h) + 1
+        out_w = int((im_w - (filter_w - 1) * dilation_w - 1) / stride_w) + 1
+        if out_h <= 0 or out_w <= 0:                                    # the reference does not test out_d (:2453)
+            raise InvalidArgumentException("Invalid shape or parameters.")
+        if padding:
+            out_buf_size = batches * im_d * filter_d * im_h * filter_h * im_w * filter_w * channels
+        else:
+            out_buf_size = batches * out_d * filter_d * out_h * filter_h * out_w * filter_w * channels
+        if cols_size != out_buf_size or len(cols) - cols_offset != out_buf_size:
+            raise InvalidArgumentException("output buffer size is invalid")
+        _cuda("images", images), _cuda("cols", cols)
+        if images.dtype() != cols.dtype():
+            raise InvalidArgumentException("Unmatch data type for images and cols")
+        if reverse:
+            im_ptr, co_ptr = images.device_ptr_rw(), cols.device_ptr()
+        else:
+            im_ptr, co_ptr = images.device_ptr(), cols.device_ptr_rw()
+        _capi.check(self._lib.rb200_im2col3d(images.dtype(), 1 if reverse else 0, im_ptr, images_offset, images_size,
+                                             batches, im_d, im_h, im_w, channels, filter_d, filter_h, filter_w,
+                                             stride_d, stride_h, stride_w, 1 if padding else 0,
+                                             1 if channels_first else 0, dilation_d, dilation_h, dilation_w,
+                                             1 if cols_channels_first else 0, co_ptr, cols_offset, cols_size))
+
     # ---- fused conv2d forward (extension) ----------------------------------------
     def conv2d_forward(self, images, images_offset, batches, im_h, im_w, channels, filter_h, filter_w,
                        stride_h, stride_w, padding, dilation_h, dilation_w, kernel, kernel_offset, filters,

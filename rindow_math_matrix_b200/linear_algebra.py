@@ -732,19 +732,80 @@ class LinearAlgebra:
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
     def im2col(self, images: NDArray, filterSize=None, strides=None, padding=None, channels_first=None,
                dilation_rate=None, cols_channels_first=None, cols: NDArray | None = None) -> NDArray:
-        if images.ndim() != 4:
-            raise InvalidArgumentException("unsuppoted images shape")       # 1d/3d are SURVEY 8(f) "next" rows
-        _cols = self.im2col2d(False, images, filterSize, strides, padding, channels_first, dilation_rate,
-                              cols_channels_first, cols)
+        fn = {3: self.im2col1d, 4: self.im2col2d, 5: self.im2col3d}.get(images.ndim())      # LinearAlgebra.php:3369-3398
+        if fn is None:
+            raise InvalidArgumentException("unsuppoted images shape")
+        _cols = fn(False, images, filterSize, strides, padding, channels_first, dilation_rate, cols_channels_first, cols)
         return _cols if cols is None else cols
 
     def col2im(self, cols: NDArray, images: NDArray, filterSize=None, strides=None, padding=None,
                channels_first=None, dilation_rate=None, cols_channels_first=None) -> NDArray:
-        if images.ndim() != 4:
+        fn = {3: self.im2col1d, 4: self.im2col2d, 5: self.im2col3d}.get(images.ndim())      # :3406-3456
+        if fn is None:
             raise InvalidArgumentException("unsuppoted images shape")
-        self.im2col2d(True, images, filterSize, strides, padding, channels_first, dilation_rate,
-                      cols_channels_first, cols)
+        fn(True, images, filterSize, strides, padding, channels_first, dilation_rate, cols_channels_first, cols)
         return images
+
+    def im2col1d(self, reverse, images: NDArray, filterSize=None, strides=None, padding=None,
+                 channels_first=None, dilation_rate=None, cols_channels_first=None,
+                 cols: NDArray | None = None) -> NDArray:                        # LinearAlgebra.php:3496-3590
+        if images.ndim() != 3:
+            raise InvalidArgumentException("images must be 3D dimension")
+        if channels_first:
+            batches, channels, in_w = images.shape()
+        else:
+            batches, in_w, channels = images.shape()
+        (filter_w,) = filterSize if filterSize else (3,)
+        (stride_w,) = strides if strides else (1,)
+        padding = bool(padding)
+        channels_first = bool(channels_first)
+        (dilation_w,) = dilation_rate if dilation_rate else (1,)
+        cols_channels_first = bool(cols_channels_first)
+        if cols is None:
+            out_w = in_w if padding else _intdiv(in_w - (filter_w - 1) * dilation_w - 1, stride_w) + 1
+            if out_w <= 0:
+                raise InvalidArgumentException("Invalid shape or paramaters.")
+            shape = [batches, out_w, channels, filter_w] if cols_channels_first else [batches, out_w, filter_w, channels]
+            cols = self.zeros(self.alloc(shape, dtype=images.dtype()))
+        self.math.im2col1d(reverse, images.buffer(), images.offset(), images.size(), batches, in_w, channels,
+                           filter_w, stride_w, padding, channels_first, dilation_w, cols_channels_first,
+                           cols.buffer(), cols.offset(), cols.size())
+        return cols
+
+    def im2col3d(self, reverse, images: NDArray, filterSize=None, strides=None, padding=None,
+                 channels_first=None, dilation_rate=None, cols_channels_first=None,
+                 cols: NDArray | None = None) -> NDArray:                        # LinearAlgebra.php:3708-3818
+        if images.ndim() != 5:
+            raise InvalidArgumentException("images must be 5D dimension")
+        if channels_first:
+            batches, channels, in_d, in_h, in_w = images.shape()
+        else:
+            batches, in_d, in_h, in_w, channels = images.shape()
+        filter_d, filter_h, filter_w = filterSize if filterSize else (3, 3, 3)
+        stride_d, stride_h, stride_w = strides if strides else (1, 1, 1)
+        padding = bool(padding)
+        channels_first = bool(channels_first)
+        dilation_d, dilation_h, dilation_w = dilation_rate if dilation_rate else (1, 1, 1)
+        cols_channels_first = bool(cols_channels_first)
+        if cols is None:
+            if padding:
+                out_d, out_h, out_w = in_d, in_h, in_w
+            else:
+                out_d = _intdiv(in_d - (filter_d - 1) * dilation_d - 1, stride_d) + 1
+                out_h = _intdiv(in_h - (filter_h - 1) * dilation_h - 1, stride_h) + 1
+                out_w = _intdiv(in_w - (filter_w - 1) * dilation_w - 1, stride_w) + 1
+            if out_d <= 0 or out_h <= 0 or out_w <= 0:
+                raise InvalidArgumentException("Invalid shape or paramaters.")
+            if cols_channels_first:
+                shape = [batches, out_d, out_h, out_w, channels, filter_d, filter_h, filter_w]
+            else:
+                shape = [batches, out_d, out_h, out_w, filter_d, filter_h, filter_w, channels]
+            cols = self.zeros(self.alloc(shape, dtype=images.dtype()))
+        self.math.im2col3d(reverse, images.buffer(), images.offset(), images.size(), batches, in_d, in_h, in_w,
+                           channels, filter_d, filter_h, filter_w, stride_d, stride_h, stride_w, padding,
+                           channels_first, dilation_d, dilation_h, dilation_w, cols_channels_first,
+                           cols.buffer(), cols.offset(), cols.size())
+        return cols
 
     def conv2d(self, images: NDArray, kernel: NDArray, bias: NDArray | None = None, strides=None, padding=None,
                dilation_rate=None, fused: bool | None = None) -> NDArray:

@@ -253,3 +253,58 @@ def run_im2col_case(params, service):
     assert np.array_equal(np.asarray(newImages.toArray(), dtype=np.float64), back)
     # im2col left the images untouched
     assert np.array_equal(np.asarray(images.toArray(), dtype=np.float64), arange.reshape(shape))
+
+
+def run_im2col_nd_case(params, service):
+    """testIm2col1dNormal / testIm2col3dNormal (LinearAlgebraTest.php:9613-9778, :10653-10882) for one provider row:
+    arange-valued images, cols must hold the source index of every in-bounds tap (0 elsewhere), col2im must add every
+    tap back.  The expectation loops are the reference TEST's (with its own padding formulas), independent of PhpMath."""
+    la = LinearAlgebra(service)
+    p = {k: (v if v is not None else 0) for k, v in params.items()}
+    three = "im_d" in params
+    b_, ch = p["batches"], p["channels"]
+    dims = [p["im_d"], p["im_h"], p["im_w"]] if three else [p["im_w"]]
+    ks = [p["kernel_d"], p["kernel_h"], p["kernel_w"]] if three else [p["kernel_w"]]
+    ss = [p["stride_d"], p["stride_h"], p["stride_w"]] if three else [p["stride_w"]]
+    ds = [p["dilation_d"], p["dilation_h"], p["dilation_w"]] if three else [p["dilation_w"]]
+    padding, cf, ccf = bool(params["padding"]), bool(params["channels_first"]), bool(params["cols_channels_first"])
+    outs = [int((i - (k - 1) * d - 1) / s) + 1 for i, k, s, d in zip(dims, ks, ss, ds)]
+    pads = [0] * len(dims)
+    if padding:
+        pads = [int(((i - 1) * s - i + (k - 1) * d + 1) / 2) for i, k, s, d in zip(dims, ks, ss, ds)]
+        outs = list(dims)
+    n = b_ * ch * int(np.prod(dims))
+    arange = np.arange(n, dtype=np.float32)
+    shape = [b_, ch] + dims if cf else [b_] + dims + [ch]
+    images = la.array(arange.reshape(shape))
+    cols = la.im2col(images, filterSize=ks, strides=ss, padding=params["padding"], channels_first=params["channels_first"],
+                     dilation_rate=ds, cols_channels_first=params["cols_channels_first"])
+    cshape = [b_] + outs + ([ch] + ks if ccf else ks + [ch])
+    assert cols.shape() == cshape
+    # vectorised form of the test's nested loops: source coordinate of every (out cell, tap) pair per axis
+    img = arange.reshape(shape).astype(np.float64)
+    if cf:
+        img = np.moveaxis(img, 1, -1)                          # -> [b, *dims, c]
+    trues = np.zeros([b_] + outs + ks + [ch])
+    back = np.zeros_like(img)
+    nd = len(dims)
+    grids = np.meshgrid(*[np.arange(o) for o in outs], *[np.arange(k) for k in ks], indexing="ij")
+    src = [grids[a] * ss[a] + grids[nd + a] * ds[a] - pads[a] for a in range(nd)]
+    ok = np.ones(src[0].shape, bool)
+    for a in range(nd):
+        ok &= (src[a] >= 0) & (src[a] < dims[a])
+    idx = tuple(np.where(ok, src[a], 0) for a in range(nd))
+    for b in range(b_):
+        vals = img[b][idx]                                     # [*outs, *ks, c]
+        trues[b] = np.where(ok[..., None], vals, 0.0)
+        np.add.at(back[b], tuple(i[ok] for i in idx), vals[ok])
+    if ccf:
+        trues = np.moveaxis(trues, -1, 1 + nd)                 # -> [b, *outs, c, *ks]
+    if cf:
+        back = np.moveaxis(back, -1, 1)
+    assert np.array_equal(np.asarray(cols.toArray(), dtype=np.float64), trues)
+    newImages = la.zerosLike(images)
+    la.col2im(cols, newImages, filterSize=ks, strides=ss, padding=params["padding"], channels_first=params["channels_first"],
+              dilation_rate=ds, cols_channels_first=params["cols_channels_first"])
+    assert np.array_equal(np.asarray(newImages.toArray(), dtype=np.float64), back)
+    assert np.array_equal(np.asarray(images.toArray(), dtype=np.float64), arange.reshape(shape))

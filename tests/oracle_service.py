@@ -143,6 +143,18 @@ class OracleMath:
               filter_h, filter_w, stride_h, stride_w, padding, channels_first, dilation_h, dilation_w,
               cols_channels_first, cols.f64(), cols_offset, cols_size)
 
+    def im2col1d(self, reverse, images, images_offset, images_size, batches, im_w, channels, filter_w, stride_w,
+                 padding, channels_first, dilation_w, cols_channels_first, cols, cols_offset, cols_size):
+        _wrap(oracle.im2col1d, reverse, images.f64(), images_offset, images_size, batches, im_w, channels, filter_w,
+              stride_w, padding, channels_first, dilation_w, cols_channels_first, cols.f64(), cols_offset, cols_size)
+
+    def im2col3d(self, reverse, images, images_offset, images_size, batches, im_d, im_h, im_w, channels,
+                 filter_d, filter_h, filter_w, stride_d, stride_h, stride_w, padding, channels_first,
+                 dilation_d, dilation_h, dilation_w, cols_channels_first, cols, cols_offset, cols_size):
+        _wrap(oracle.im2col3d, reverse, images.f64(), images_offset, images_size, batches, im_d, im_h, im_w, channels,
+              filter_d, filter_h, filter_w, stride_d, stride_h, stride_w, padding, channels_first,
+              dilation_d, dilation_h, dilation_w, cols_channels_first, cols.f64(), cols_offset, cols_size)
+
     # ---- SURVEY.md section 8(f) widening: broadcast / unary / compare families, astype, scalar reductions, onehot
     def _bc(self, op, trans, m, n, A, offA, ldA, X, offX, incX):
         a, x = self._f(A), self._f(X)

@@ -26,6 +26,10 @@ pytestmark = pytest.mark.gpu
 KA = gr.load_known_answers()
 with open(os.path.join(gr.HERE, "golden", "im2col2d_cases.json")) as f:
     IM2COL = json.load(f)["cases"]
+with open(os.path.join(gr.HERE, "golden", "im2col1d_cases.json")) as f:
+    IM2COL1D = json.load(f)["cases"]
+with open(os.path.join(gr.HERE, "golden", "im2col3d_cases.json")) as f:
+    IM2COL3D = json.load(f)["cases"]
 
 
 def isclose_ref(got, ref, rtol=1e-4, atol=1e-7):
@@ -627,6 +631,71 @@ def test_cross_256_config(cuda_service):
 
 
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", IM2COL1D, ids=[c["name"].replace(" ", "_") for c in IM2COL1D])
+def test_im2col1d_provider(case, cuda_service):
+    gr.run_im2col_nd_case(case["params"], cuda_service)
+
+
+@pytest.mark.parametrize("case", IM2COL3D, ids=[c["name"].replace(" ", "_") for c in IM2COL3D])
+def test_im2col3d_provider(case, cuda_service):
+    gr.run_im2col_nd_case(case["params"], cuda_service)
+
+
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32, dtypes.uint8, dtypes.int64])
+@pytest.mark.parametrize("padding,cf,ccf,k,s,d", [(False, False, False, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+                                                 (True, False, False, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+                                                 (True, True, True, (2, 5, 3), (1, 2, 1), (2, 1, 2)),
+                                                 (False, True, False, (2, 2, 4), (2, 1, 3), (1, 2, 1)),
+                                                 (True, False, True, (3, 1, 3), (2, 2, 2), (2, 1, 2))])
+def test_im2col3d_random_bit_exact(dt, padding, cf, ccf, k, s, d, cuda_service):
+    """Volumes with im_d != im_h: with padding the reference derives padding_d from im_h (PhpMath.php:2459); the
+    device and the oracle both follow it.  Forward is a bit-exact copy, col2im exact on small integers."""
+    b, dd, h, w, c = 2, 7, 9, 11, 3
+    rng = np.random.default_rng(4003)
+    npdt = dtypes.NUMPY[dt]
+    img = np.floor(rng.uniform(0, 1, b * dd * h * w * c) * 100).astype(npdt)
+    outs = [dd, h, w] if padding else [(i - (kk - 1) * di - 1) // st + 1 for i, kk, st, di in zip((dd, h, w), k, s, d)]
+    ncols = b * int(np.prod(outs)) * int(np.prod(k)) * c
+    off_i, off_c = 3, 4
+    images = CudaBuffer(off_i + img.size, dt).from_numpy(img, off_i)
+    cols = CudaBuffer(off_c + ncols, dt)
+    math = cuda_service.math()
+    args = (b, dd, h, w, c, k[0], k[1], k[2], s[0], s[1], s[2], padding, cf, d[0], d[1], d[2], ccf)
+    math.im2col3d(False, images, off_i, img.size, *args, cols, off_c, ncols)
+    io = np.concatenate([np.zeros(off_i), img.astype(np.float64)])
+    co = np.zeros(off_c + ncols)
+    oracle.im2col3d(False, io, off_i, img.size, *args, co, off_c, ncols)
+    assert np.array_equal(cols.to_numpy().astype(np.float64), co)
+    if dt in (dtypes.float32, dtypes.float64, dtypes.int32, dtypes.int64):
+        math.im2col3d(True, images, off_i, img.size, *args, cols, off_c, ncols)
+        oracle.im2col3d(True, io, off_i, img.size, *args, co, off_c, ncols)
+        assert np.array_equal(images.to_numpy().astype(np.float64), io)
+
+
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.int32, dtypes.uint8])
+@pytest.mark.parametrize("padding,cf,ccf,k,s,d", [(False, False, False, 3, 1, 1), (True, True, True, 5, 2, 2),
+                                                 (True, False, True, 4, 1, 3), (False, True, False, 2, 3, 1)])
+def test_im2col1d_random_bit_exact(dt, padding, cf, ccf, k, s, d, cuda_service):
+    b, w, c = 3, 257, 5
+    rng = np.random.default_rng(4004)
+    npdt = dtypes.NUMPY[dt]
+    img = np.floor(rng.uniform(0, 1, b * w * c) * 100).astype(npdt)
+    ow = w if padding else (w - (k - 1) * d - 1) // s + 1
+    ncols = b * ow * k * c
+    images = CudaBuffer(img.size, dt).from_numpy(img)
+    cols = CudaBuffer(ncols, dt)
+    math = cuda_service.math()
+    args = (b, w, c, k, s, padding, cf, d, ccf)
+    math.im2col1d(False, images, 0, img.size, *args, cols, 0, ncols)
+    io, co = img.astype(np.float64), np.zeros(ncols)
+    oracle.im2col1d(False, io, 0, img.size, *args, co, 0, ncols)
+    assert np.array_equal(cols.to_numpy().astype(np.float64), co)
+    if dt in (dtypes.float32, dtypes.int32):
+        math.im2col1d(True, images, 0, img.size, *args, cols, 0, ncols)
+        oracle.im2col1d(True, io, 0, img.size, *args, co, 0, ncols)
+        assert np.array_equal(images.to_numpy().astype(np.float64), io)
+
+
 # im2col2d on random data and other dtypes; conv config
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32, dtypes.uint8, dtypes.int64])

@@ -13,6 +13,10 @@ from oracle_service import OracleService
 KA = gr.load_known_answers()
 with open(os.path.join(gr.HERE, "golden", "im2col2d_cases.json")) as f:
     IM2COL = json.load(f)["cases"]
+with open(os.path.join(gr.HERE, "golden", "im2col1d_cases.json")) as f:
+    IM2COL1D = json.load(f)["cases"]
+with open(os.path.join(gr.HERE, "golden", "im2col3d_cases.json")) as f:
+    IM2COL3D = json.load(f)["cases"]
 
 
 @pytest.mark.parametrize("case", KA["cases"], ids=[c["id"] for c in KA["cases"]])
@@ -24,6 +28,18 @@ def test_known_answer(case, oracle_service):
 def test_im2col2d_provider(case, oracle_service):
     assert len(IM2COL) == 28
     gr.run_im2col_case(case["params"], oracle_service)
+
+
+@pytest.mark.parametrize("case", IM2COL1D, ids=[c["name"].replace(" ", "_") for c in IM2COL1D])
+def test_im2col1d_provider(case, oracle_service):
+    assert len(IM2COL1D) == 16
+    gr.run_im2col_nd_case(case["params"], oracle_service)
+
+
+@pytest.mark.parametrize("case", IM2COL3D, ids=[c["name"].replace(" ", "_") for c in IM2COL3D])
+def test_im2col3d_provider(case, oracle_service):
+    assert len(IM2COL3D) == 40
+    gr.run_im2col_nd_case(case["params"], oracle_service)
 
 
 def test_reducemax_nan_rules():

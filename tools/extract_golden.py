@@ -7,7 +7,8 @@ GPU boxes); the output is committed under tests/golden/.
   python tools/extract_golden.py
 
 Currently extracts: providerIm2col2dNormal (the 28 im2col2d parameter sets,
-tests/RindowTest/Math/Matrix/LinearAlgebraTest.php:8455-8880).  The small literal
+tests/RindowTest/Math/Matrix/LinearAlgebraTest.php:8455-8880), providerIm2col1dNormal (:9431-9612) and
+providerIm2col3dNormal (:9860-10627).  The small literal
 known-answer vectors of the other ops are transcribed by hand in
 tests/golden/known_answers.json with a file:line citation per entry.
 """
@@ -49,16 +50,19 @@ def extract_provider(text: str, name: str):
 def main():
     with open(SRC) as f:
         text = f.read()
-    cases = extract_provider(text, "providerIm2col2dNormal")
     os.makedirs(OUT, exist_ok=True)
-    out = {
-        "source": "tests/RindowTest/Math/Matrix/LinearAlgebraTest.php providerIm2col2dNormal",
-        "generated_by": "tools/extract_golden.py",
-        "cases": cases,
-    }
-    with open(os.path.join(OUT, "im2col2d_cases.json"), "w") as f:
-        json.dump(out, f, indent=1)
-    print("im2col2d cases:", len(cases))
+    for provider, fname in (("providerIm2col2dNormal", "im2col2d_cases.json"),
+                            ("providerIm2col1dNormal", "im2col1d_cases.json"),
+                            ("providerIm2col3dNormal", "im2col3d_cases.json")):
+        cases = extract_provider(text, provider)
+        out = {
+            "source": "tests/RindowTest/Math/Matrix/LinearAlgebraTest.php " + provider,
+            "generated_by": "tools/extract_golden.py",
+            "cases": cases,
+        }
+        with open(os.path.join(OUT, fname), "w") as f:
+            json.dump(out, f, indent=1)
+        print(fname, len(cases))
     return 0
 
 

@@ -99,6 +99,15 @@ def main():
     M = b * oh * ow
     timed("conv_gemm", lambda i: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, f, 27, 1.0, Co, 0, 27, Wk, 0, f,
                                            0.0, Out, 0, f), (M * 27 + 27 * f + M * f) * 4)
+    # Conv3D sibling: clips [8,16,112,112,3], 3x3x3 valid -> cols [8,14,110,110,3,3,3,3]
+    if not want or "im2col3d" in want:
+        b3, d3, h3, w3, c3 = 8, 16, 112, 112, 3
+        V3 = [rnd(b3 * d3 * h3 * w3 * c3) for _ in range(3)]
+        n3 = b3 * (d3 - 2) * (h3 - 2) * (w3 - 2) * 81
+        C3 = CudaBuffer(n3, f32, zero=False)
+        timed("im2col3d", lambda i: math.im2col3d(False, V3[i], 0, b3 * d3 * h3 * w3 * c3, b3, d3, h3, w3, c3, 3, 3, 3, 1, 1, 1,
+                                                  False, False, 1, 1, 1, False, C3, 0, n3), (b3 * d3 * h3 * w3 * c3 + n3) * 4)
+        del V3, C3
     Outs = [Out, CudaBuffer(b * oh * ow * f, f32, zero=False)]
     timed("conv2d_fused", lambda i: math.conv2d_forward(Im[i], 0, b, h, w, ch, 3, 3, 1, 1, False, 1, 1, Wk, 0, f, None, 0,
                                                         Outs[i % 2], 0), (b * h * w * ch + 27 * f + M * f) * 4)

@@ -28,6 +28,7 @@ for op in $OPS; do
       reduce_sum_axis0) K="-k regex:reduce_cols"; C=1;;
       softmax) K="-k regex:softmax"; C=1;;
       im2col2d) K="-k regex:im2col2d"; C=1;;
+      im2col3d) K="-k regex:im2col3d"; C=1;;
     esac
     timeout 600 ncu --set full --clock-control none --import-source on $K -s $S -c $C \
       -o gpurun_out/prof/$op -f python tools/profile_ops.py $op 3 > gpurun_out/prof/$op.ncu.log 2>&1

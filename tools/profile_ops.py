@@ -2,7 +2,7 @@
 """Run one hot-path op a few times at its BASELINE size -- the command ncu wraps
 (profiles/README.md lists the exact ncu invocations).  Usage: profile_ops.py OP [REPS]
 OP in: sgemm_tf32 sgemm_tf32x3 sgemm_simt add multiply reduce_sum reduce_sum_axis0 reduce_max
-       reduce_argmax softmax im2col2d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans
+       reduce_argmax softmax im2col2d im2col3d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans
        maximum exp astype transpose_nd gather scatter_add sum"""
 import os
 import sys
@@ -65,6 +65,13 @@ def main():
             blas.setGemmMode(0)
             fn = lambda: blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, M, 64, 27, 1.0, cols, 0, 27, Wt, 0, 64,
                                    0.0, out, 0, 64)
+    elif op == "im2col3d":
+        b3, d3, h3, w3, c3 = 8, 16, 112, 112, 3
+        vol = rnd(b3 * d3 * h3 * w3 * c3)
+        n3 = b3 * (d3 - 2) * (h3 - 2) * (w3 - 2) * 81
+        c3d = CudaBuffer(n3, f32, zero=False)
+        fn = lambda: math.im2col3d(False, vol, 0, b3 * d3 * h3 * w3 * c3, b3, d3, h3, w3, c3, 3, 3, 3, 1, 1, 1, False, False,
+                                   1, 1, 1, False, c3d, 0, n3)
     elif op in ("axpy", "copy", "transpose", "gemv", "gemv_trans"):
         m, n = 8192, 4096
         A, Y = rnd(m * n), rnd(m * n)
