@@ -596,6 +596,10 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
     report("copy", lambda i: blas1.copy(m * n, As[i], 0, 1, Y2, 0, 1), 2 * m * n * 4, {"shape": "n=33554432"})
     report("transpose", lambda i: blas1.omatcopy(_B.RowMajor, _B.Trans, m, n, 1.0, As[i], 0, n, Y2, 0, m),
            2 * m * n * 4, {"shape": "[8192,4096] -> [4096,8192] (omatcopy)"})
+    report("slice", lambda i: math.slice(False, False, m, n, 1, 1, As[i], 0, 1, Y2, 0, 1, 0, m, 512, 3072, 0, 1),
+           2 * m * 3072 * 4, {"shape": "[8192,4096] -> columns 512..3583 (split / concat along axis 1)"})
+    report("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4,
+           {"shape": "[8192,1024] -> [8192,4,1024]"})
     Yv = CudaBuffer(m, dtypes.float32)
     report("gemv", lambda i: blas1.gemv(_B.RowMajor, _B.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Yv, 0, 1),
            m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096] x [4096]"})

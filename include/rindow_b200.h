@@ -325,6 +325,16 @@ int rb200_im2col2d(int dtype, int reverse,
                    int cols_channels_first,
                    void* cols, int64_t cols_offset, int64_t cols_size);
 
+/* ---- slice / stick and repeat: PhpMath::slice (PhpMath.php:2691-2776) moves the sub-block
+ *      [start0,+size0) x [start1,+size1) x [start2,+size2) x size of A[m,n,k,size] to / from the dense Y (reverse:
+ *      Y -> A, add_mode: += instead of =), `size` items with increments incA / incY; PhpMath::repeat (:1400-1422)
+ *      writes B[m,repeats,k] = A[m,k].  Any dtype (copies are bit-exact).  These carry LinearAlgebra::slice / stick /
+ *      stack / concat / split / repeat (LinearAlgebra.php:3944-4365). */
+int rb200_slice(int dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,
+                void* A, int64_t offA, int64_t incA, void* Y, int64_t offY, int64_t incY,
+                int64_t start0, int64_t size0, int64_t start1, int64_t size1, int64_t start2, int64_t size2);
+int rb200_repeat(int dtype, int64_t m, int64_t k, int64_t repeats, const void* A, int64_t offA, void* B, int64_t offB);
+
 /* ---- im2col3d / col2im3d: PhpMath::im2col3d (PhpMath.php:2396-2600, copyCell3d :2319-2390), the Conv3D sibling.
  *      images [b,d,h,w,c] (channels_first: [b,c,d,h,w]); cols [b,od,oh,ow,kd,kh,kw,c] (cols_channels_first:
  *      [b,od,oh,ow,c,kd,kh,kw]).  Same out / padding rules per axis as im2col2d, including the reference's

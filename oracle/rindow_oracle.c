@@ -447,6 +447,47 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::slice, PhpMath.php:2691-2776 (math_copy / math_add :3197-3226) */
+int ro_slice(int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,
+             double *A, int64_t countA, int64_t offA, int64_t incA,
+             double *Y, int64_t countY, int64_t offY, int64_t incY,
+             int64_t start0, int64_t size0, int64_t start1, int64_t size1, int64_t start2, int64_t size2)
+{
+    if (m * n * k * size * incA + offA > countA) return RO_E_ARG;          /* 'unmatch BufferA size and m,n,k' */
+    if (start0 < 0 || start0 >= m || size0 < 0 || size0 + start0 > m) return RO_E_ARG;
+    if (start1 < 0 || start1 >= n || size1 < 0 || size1 + start1 > n) return RO_E_ARG;
+    if (start2 < 0 || start2 >= k || size2 < 0 || size2 + start2 > k) return RO_E_ARG;
+    if (size0 * size1 * size2 * size * incY > countY - offY) return RO_E_ARG;   /* 'BufferY size is too small' */
+    for (int64_t i0 = 0; i0 < size0; i0++) {
+        for (int64_t i1 = 0; i1 < size1; i1++) {
+            for (int64_t i2 = 0; i2 < size2; i2++) {
+                int64_t pa = (i0 + start0) * n * k * size + (i1 + start1) * k * size + (i2 + start2) * size + offA;
+                int64_t py = i0 * size1 * size2 * size + i1 * size2 * size + i2 * size + offY;
+                for (int64_t e = 0; e < size; e++, pa += incA, py += incY) {
+                    if (!reverse) { if (add_mode) Y[py] = Y[py] + A[pa]; else Y[py] = A[pa]; }
+                    else          { if (add_mode) A[pa] = A[pa] + Y[py]; else A[pa] = Y[py]; }
+                }
+            }
+        }
+    }
+    return RO_OK;
+}
+
+/* PhpMath::repeat, PhpMath.php:1400-1422 */
+int ro_repeat(int64_t m, int64_t k, int64_t repeats, const double *A, int64_t countA, int64_t offA,
+              double *B, int64_t countB, int64_t offB)
+{
+    if (offA + m * k > countA) return RO_E_ARG;
+    if (offB + m * repeats * k > countB) return RO_E_ARG;
+    int64_t idA = offA, idB = offB;
+    for (int64_t i = 0; i < m; i++, idA += k) {
+        for (int64_t j = 0; j < repeats; j++, idB += k) {
+            for (int64_t e = 0; e < k; e++) B[idB + e] = A[idA + e];
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::im2col1d, PhpMath.php:1967-2088 (copyCell1d :1912-1958): the loops of im2col2d without the y axis. */
 int ro_im2col1d(int reverse,
                 double *images, int64_t count_images, int64_t images_offset, int64_t images_size,

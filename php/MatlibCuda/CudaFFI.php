@@ -111,6 +111,10 @@ class CudaFFI
                            int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
                            int cols_channels_first,
                            void* cols, int64_t cols_offset, int64_t cols_size);
+        int rb200_slice(int dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,
+                        void* A, int64_t offA, int64_t incA, void* Y, int64_t offY, int64_t incY,
+                        int64_t start0, int64_t size0, int64_t start1, int64_t size1, int64_t start2, int64_t size2);
+        int rb200_repeat(int dtype, int64_t m, int64_t k, int64_t repeats, const void* A, int64_t offA, void* B, int64_t offB);
         int rb200_im2col3d(int dtype, int reverse, void* images, int64_t images_offset, int64_t images_size,
                            int64_t batches, int64_t im_d, int64_t im_h, int64_t im_w, int64_t channels,
                            int64_t filter_d, int64_t filter_h, int64_t filter_w,

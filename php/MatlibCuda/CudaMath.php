@@ -119,6 +119,53 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** slice / stick (PhpMath.php:2691-2776): any dtype, bit-exact copies, += in add mode */
+    public function slice(bool $reverse,bool $addMode,int $m,int $n,int $k,int $size,
+        Buffer $A,int $offsetA,int $incA,Buffer $Y,int $offsetY,int $incY,
+        int $startAxis0,int $sizeAxis0,int $startAxis1,int $sizeAxis1,int $startAxis2,int $sizeAxis2) : void
+    {
+        if (!$this->anyOnDevice($A,$Y) || $A->dtype()!=$Y->dtype()) {
+            parent::slice($reverse,$addMode,$m,$n,$k,$size,$A,$offsetA,$incA,$Y,$offsetY,$incY,
+                $startAxis0,$sizeAxis0,$startAxis1,$sizeAxis1,$startAxis2,$sizeAxis2);
+            return;
+        }
+        if ($m*$n*$k*$size*$incA+$offsetA>count($A)) {
+            throw new InvalidArgumentException('unmatch BufferA size and m,n,k');
+        }
+        if ($startAxis0<0||$startAxis0>=$m||$sizeAxis0<0||$sizeAxis0+$startAxis0>$m) {
+            throw new InvalidArgumentException('Axis0 range is too large for source array.');
+        }
+        if ($startAxis1<0||$startAxis1>=$n||$sizeAxis1<0||$sizeAxis1+$startAxis1>$n) {
+            throw new InvalidArgumentException('Axis1 range is too large for source array.');
+        }
+        if ($startAxis2<0||$startAxis2>=$k||$sizeAxis2<0||$sizeAxis2+$startAxis2>$k) {
+            throw new InvalidArgumentException('Axis2 range is too large for source array.');
+        }
+        if ($sizeAxis0*$sizeAxis1*$sizeAxis2*$size*$incY>count($Y)-$offsetY) {
+            throw new InvalidArgumentException('BufferY size is too small');
+        }
+        $a = $reverse ? $A->devicePtrRW() : $A->devicePtr();
+        $y = $reverse ? $Y->devicePtr() : $Y->devicePtrRW();
+        CudaFFI::check(CudaFFI::lib()->rb200_slice($A->abiDtype(),$reverse?1:0,$addMode?1:0,$m,$n,$k,$size,
+            $a,$offsetA,$incA,$y,$offsetY,$incY,$startAxis0,$sizeAxis0,$startAxis1,$sizeAxis1,$startAxis2,$sizeAxis2));
+    }
+
+    /** repeat (PhpMath.php:1400-1422): B[m,repeats,k] = A[m,k] */
+    public function repeat(int $m,int $k,int $repeats,Buffer $A,int $offsetA,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($A,$B) || $A->dtype()!=$B->dtype()) {
+            parent::repeat($m,$k,$repeats,$A,$offsetA,$B,$offsetB);
+            return;
+        }
+        if ($offsetA+$m*$k>count($A)) {
+            throw new InvalidArgumentException('Matrix A specification too large for buffer.');
+        }
+        if ($offsetB+$m*$repeats*$k>count($B)) {
+            throw new InvalidArgumentException('Matrix B specification too large for buffer.');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_repeat($A->abiDtype(),$m,$k,$repeats,$A->devicePtr(),$offsetA,$B->devicePtrRW(),$offsetB));
+    }
+
     /** im2col1d (PhpMath.php:1967-2088) is im2col2d with one row of height 1: same layouts, same copy */
     public function im2col1d(bool $reverse,Buffer $images,int $images_offset,int $images_size,int $batches,
         int $im_w,int $channels,int $filter_w,int $stride_w,bool $padding,bool $channels_first,int $dilation_w,

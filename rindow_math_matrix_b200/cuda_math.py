@@ -396,6 +396,38 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- slice / repeat (PhpMath.php:2691-2776, :1400-1422) -------------------------------------------------------
+    def slice(self, reverse, addMode, m, n, k, size, A, offsetA, incA, Y, offsetY, incY,
+              startAxis0, sizeAxis0, startAxis1, sizeAxis1, startAxis2, sizeAxis2) -> None:
+        if m * n * k * size * incA + offsetA > len(A):
+            raise InvalidArgumentException("unmatch BufferA size and m,n,k")
+        if startAxis0 < 0 or startAxis0 >= m or sizeAxis0 < 0 or sizeAxis0 + startAxis0 > m:
+            raise InvalidArgumentException("Axis0 range is too large for source array.")
+        if startAxis1 < 0 or startAxis1 >= n or sizeAxis1 < 0 or sizeAxis1 + startAxis1 > n:
+            raise InvalidArgumentException("Axis1 range is too large for source array.")
+        if startAxis2 < 0 or startAxis2 >= k or sizeAxis2 < 0 or sizeAxis2 + startAxis2 > k:
+            raise InvalidArgumentException("Axis2 range is too large for source array.")
+        if sizeAxis0 * sizeAxis1 * sizeAxis2 * size * incY > len(Y) - offsetY:
+            raise InvalidArgumentException("BufferY size is too small")
+        _cuda("A", A), _cuda("Y", Y)
+        if A.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and Y")
+        a_ptr = A.device_ptr_rw() if reverse else A.device_ptr()             # reverse writes A, forward writes Y
+        y_ptr = Y.device_ptr() if reverse else Y.device_ptr_rw()
+        _capi.check(self._lib.rb200_slice(A.dtype(), 1 if reverse else 0, 1 if addMode else 0, m, n, k, size,
+                                          a_ptr, offsetA, incA, y_ptr, offsetY, incY,
+                                          startAxis0, sizeAxis0, startAxis1, sizeAxis1, startAxis2, sizeAxis2))
+
+    def repeat(self, m, k, repeats, A, offsetA, B, offsetB) -> None:
+        if offsetA + m * k > len(A):
+            raise InvalidArgumentException("Matrix A specification too large for buffer.")
+        if offsetB + m * repeats * k > len(B):
+            raise InvalidArgumentException("Matrix B specification too large for buffer.")
+        _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        _capi.check(self._lib.rb200_repeat(A.dtype(), m, k, repeats, A.device_ptr(), offsetA, B.device_ptr_rw(), offsetB))
+
     # ---- im2col1d (PhpMath.php:1967-2088): the same copy as im2col2d with one row of height 1 ----------------
     def im2col1d(self, reverse, images, images_offset, images_size, batches, im_w, channels, filter_w, stride_w,
                  padding, channels_first, dilation_w, cols_channels_first, cols, cols_offset, cols_size) -> None:

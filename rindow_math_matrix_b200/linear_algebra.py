@@ -730,6 +730,140 @@ class LinearAlgebra:
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    # ---- slice / stick / stack / concat / split / repeat (LinearAlgebra.php:3944-4365) -----------------------
+    def slice(self, input: NDArray, begin, size, output: NDArray | None = None) -> NDArray:
+        return self._do_slice(False, input, begin, size, output)
+
+    def stick(self, input: NDArray, output: NDArray, begin, size) -> NDArray:
+        return self._do_slice(True, output, begin, size, input)
+
+    def stack(self, values, axis=None) -> NDArray:
+        axis = axis or 0
+        if axis not in (0, 1, 2):
+            raise InvalidArgumentException("unsuppoted axis")
+        for value in values:
+            if not isinstance(value, NDArray):
+                raise InvalidArgumentException("values must be array of NDArray")
+        shape = values[0].shape()
+        output = self.alloc(shape[:axis] + [len(values)] + shape[axis:], dtype=values[0].dtype())
+        for i, value in enumerate(values):
+            vs = value.shape()
+            self._do_slice(True, output, [0] * axis + [i], [-1] * axis + [1], value.reshape(vs[:axis] + [1] + vs[axis:]))
+        return output
+
+    def concat(self, values, axis=None) -> NDArray:
+        if axis is None:
+            axis = -1
+        if axis < 0:
+            axis = values[0].ndim() + axis
+        m = base = None
+        n = 0
+        reshaped = []
+        prefix, shape = [], []
+        for value in values:
+            shape = value.shape()
+            prefix, shape = shape[:axis], shape[axis:]
+            mm = int(np.prod(prefix)) if prefix else 1
+            nn = shape.pop(0)
+            if base is None:
+                m, base = mm, shape
+            elif m != mm or base != shape:
+                raise InvalidArgumentException("Unmatch shape: " + ",".join("(" + ",".join(map(str, v.shape())) + ")" for v in values))
+            n += nn
+            reshaped.append(value.reshape([mm, nn] + shape))
+        output = self.alloc([m, n] + shape, dtype=values[0].dtype())
+        i = 0
+        for value in reshaped:
+            nn = value.shape()[1]
+            self._do_slice(True, output, [0, i], [-1, nn], value)
+            i += nn
+        return output.reshape(prefix + [n] + shape)
+
+    def split(self, input: NDArray, sizeSplits, axis=None):
+        if axis is None:
+            axis = -1
+        if axis < 0:
+            axis = input.ndim() + axis
+        shape = input.shape()
+        prefix, shape = shape[:axis], shape[axis:]
+        m = int(np.prod(prefix)) if prefix else 1
+        n = shape.pop(0)
+        input = input.reshape([m, n] + shape)
+        i = 0
+        outputs = []
+        for size in sizeSplits:
+            outputs.append(self._do_slice(False, input, [0, i], [-1, size]).reshape(prefix + [size] + shape))
+            i += size
+        return outputs
+
+    def _do_slice(self, reverse, input: NDArray, begin, size, output: NDArray | None = None) -> NDArray:   # :4163-4303
+        message_input = "Output" if reverse else "Input"
+        org_begin = list(begin)
+        begin, size = list(begin), list(size)
+        if not 1 <= len(begin) <= 3:
+            raise InvalidArgumentException("begin must has 1 or 2 or 3 integer.")
+        if not 1 <= len(size) <= 3:
+            raise InvalidArgumentException("Size must has 1 or 2 or 3 integer.")
+        if len(begin) != len(size):
+            raise InvalidArgumentException("Unmatch shape of begin and size")
+        nb = len(begin)
+        if input.ndim() < nb:
+            raise InvalidArgumentException(message_input + " shape rank is low to slice")
+        shape = input.shape()
+        dims, starts, sizes = [1, 1, 1], [0, 0, 0], [1, 1, 1]
+        for ax in range(nb):
+            d = shape.pop(0)
+            st = begin[ax]
+            if st < 0:
+                st = d + st
+            if st < 0 or st >= d:
+                raise InvalidArgumentException("start of axis %d is invalid value.%s" % (
+                    ax, "" if ax == 0 else ":begin=[" + ",".join(map(str, org_begin)) + "]"))
+            sz = size[ax]
+            if sz < 0:
+                sz = d - st + sz + 1
+            if sz < 1 or st + sz > d:
+                raise InvalidArgumentException("size of axis %d is invalid value." % ax)
+            dims[ax], starts[ax], sizes[ax] = d, st, sz
+        item_size = int(np.prod(shape)) if shape else 1
+        output_shape = sizes[:nb] + shape
+        if output is None:
+            output = self.alloc(output_shape, dtype=input.dtype())
+        elif output_shape != output.shape():
+            raise InvalidArgumentException("Unmatch output shape: (%s)<=>(%s)" % (
+                ",".join(map(str, output_shape)), ",".join(map(str, output.shape()))))
+        self.math.slice(reverse, False, dims[0], dims[1], dims[2], item_size, input.buffer(), input.offset(), 1,
+                        output.buffer(), output.offset(), 1, starts[0], sizes[0], starts[1], sizes[1], starts[2], sizes[2])
+        return output
+
+    def repeat(self, A: NDArray, repeats: int, axis=None, keepdims=None) -> NDArray:                        # :4308-4365
+        if repeats < 1:
+            raise InvalidArgumentException("repeats argument must be one or greater.")
+        if axis is not None:
+            if axis < 0:
+                axis = A.ndim() + axis
+            if A.ndim() < axis:
+                raise InvalidArgumentException("dimension rank must be two or greater.")
+        inner = A.shape()
+        outer = []
+        if axis is not None:
+            outer, inner = inner[:axis], inner[axis:]
+        base = 1
+        if axis is None:
+            output_shape = [int(np.prod(outer + [repeats] + inner))]
+        elif keepdims:
+            if not inner:
+                raise InvalidArgumentException("dimension rank must be two or greater on keepdims.")
+            base = inner.pop(0)
+            output_shape = outer + [repeats * base] + inner
+        else:
+            output_shape = outer + [repeats] + inner
+        B = self.alloc(output_shape, dtype=A.dtype())
+        m = int(np.prod(outer)) if outer else 1
+        k = (int(np.prod(inner)) if inner else 1) * base
+        self.math.repeat(m, k, repeats, A.buffer(), A.offset(), B.buffer(), B.offset())
+        return B
+
     def im2col(self, images: NDArray, filterSize=None, strides=None, padding=None, channels_first=None,
                dilation_rate=None, cols_channels_first=None, cols: NDArray | None = None) -> NDArray:
         fn = {3: self.im2col1d, 4: self.im2col2d, 5: self.im2col3d}.get(images.ndim())      # LinearAlgebra.php:3369-3398

@@ -51,6 +51,8 @@ def _la_arg(la, a):
         return la.ones(la.alloc(json.loads(a[5:])))
     if not isinstance(a, dict):
         return _num(a)
+    if "list" in a:                                            # a PHP array of NDArrays (stack / concat values)
+        return [_la_arg(la, x) for x in a["list"]]
     dtype = _DTYPES[a["dtype"]] if "dtype" in a else None
     if "ones" in a:
         x = la.ones(la.alloc(a["ones"], dtype=dtype))
@@ -175,6 +177,10 @@ def run_case(case, service):
         assert out.shape() == case["expect_shape"]
     if "expect_dtype" in case:
         assert out.dtype() == _DTYPES[case["expect_dtype"]]
+    if "expect_list" in case:                                  # split: an array of NDArrays
+        assert len(out) == len(case["expect_list"])
+        for want, got in zip(case["expect_list"], out):
+            _assert_equal(want, got.toArray())
     if "expect" in case:
         _assert_equal(case["expect"], out.toArray() if hasattr(out, "toArray") else out, case.get("tol", 0.0))
     if "expect_fill" in case:

@@ -291,6 +291,17 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def slice(self, reverse, addMode, m, n, k, size, A, offA, incA, Y, offY, incY, st0, sz0, st1, sz1, st2, sz2):
+        a, y = self._f(A), self._f(Y)
+        _wrap(oracle.slice, reverse, addMode, m, n, k, size, a, offA, incA, y, offY, incY, st0, sz0, st1, sz1, st2, sz2)
+        self._back(A, a)
+        self._back(Y, y)
+
+    def repeat(self, m, k, repeats, A, offA, B, offB):
+        a, b = self._f(A), self._f(B)
+        _wrap(oracle.repeat, m, k, repeats, a, offA, b, offB)
+        self._back(B, b)
+
     def transpose(self, sourceShape, perm, A, offA, B, offB):
         a, b = self._f(A), self._f(B)
         _wrap(oracle.transpose, sourceShape.data, perm.data, a, offA, b, offB)

@@ -65,6 +65,10 @@ def main():
     sh3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([64, 512, 1024], np.int32))
     pm3 = CudaBuffer(3, dtypes.int32).from_numpy(np.asarray([0, 2, 1], np.int32))
     timed("transpose_b21", lambda i: math.transpose(sh3, pm3, As[i], 0, Y2, 0), 2 * m * n * 4)
+    if not want or "slice" in want or "repeat" in want:
+        # split [8192, 4096] along axis 1 -> the [8192, 3072] part (96 MB out of 128 MB), and repeat [8192,1024] x 4
+        timed("slice", lambda i: math.slice(False, False, m, n, 1, 1, As[i], 0, 1, Y2, 0, 1, 0, m, 512, 3072, 0, 1), 2 * m * 3072 * 4)
+        timed("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4)
     vocab, dim, ntok = 32768, 1024, 32768                       # table 128 MiB; one step moves 2 x 128 MiB
     ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
     timed("gather", lambda i: math.gather(False, False, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 2 * ntok * dim * 4)
