@@ -460,6 +460,10 @@ def run_b200(args):
     # ---- HBM-bound configs (C2, C3, C4): rotating buffer sets defeat L2 --------------------------------
     hbm_ops = {}
     if not args.quick:
+        # the legs above held the chip at its power cap for seconds (16384^3 GEMMs); give it a moment so the HBM-bound
+        # kernels are not timed at the SM clock that load left behind (each op still gets its own warm-up launches)
+        _capi.sync()
+        time.sleep(2.0)
         hbm_ops = run_hbm_ops(args, svc, timed, peaks, world, rank)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same GEMM with the oracle ---------------
