@@ -335,6 +335,12 @@ int rb200_slice(int dtype, int reverse, int add_mode, int64_t m, int64_t n, int6
                 int64_t start0, int64_t size0, int64_t start1, int64_t size1, int64_t start2, int64_t size2);
 int rb200_repeat(int dtype, int64_t m, int64_t k, int64_t repeats, const void* A, int64_t offA, void* B, int64_t offB);
 
+/* ---- masking: PhpMath::masking (PhpMath.php:3229-3270).  X is a bool buffer [m,k]; wherever X[i,h] is false the
+ *      elements A[i,j,h,l] (A is [m,n,k,len], any real dtype or bool) get fill written (mode 0) or added (mode 1;
+ *      bool A: A || fill).  fill is converted to A's dtype as PHP stores it (truncation for integers). */
+int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode,
+                  const void* X, int64_t offX, void* A, int64_t offA);
+
 /* ---- im2col3d / col2im3d: PhpMath::im2col3d (PhpMath.php:2396-2600, copyCell3d :2319-2390), the Conv3D sibling.
  *      images [b,d,h,w,c] (channels_first: [b,c,d,h,w]); cols [b,od,oh,ow,kd,kh,kw,c] (cols_channels_first:
  *      [b,od,oh,ow,c,kd,kh,kw]).  Same out / padding rules per axis as im2col2d, including the reference's

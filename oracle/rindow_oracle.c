@@ -447,6 +447,31 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::masking, PhpMath.php:3229-3270.  X holds the bool mask as 0 / 1 doubles; kind: 0 float, 1 integer (fill
+ * truncated toward zero as the C buffer stores it), 2 bool (mode 1: A || fill). */
+int ro_masking(int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode, int kind,
+               const double *X, int64_t countX, int64_t offX, double *A, int64_t countA, int64_t offA)
+{
+    if (offX + m * k > countX) return RO_E_ARG;
+    if (offA + m * n * k * len > countA) return RO_E_ARG;
+    if (kind == 1) fill = (double)(int64_t)fill;
+    if (kind == 2) fill = fill != 0.0;
+    for (int64_t i = 0; i < m; i++) {
+        for (int64_t j = 0; j < n; j++) {
+            for (int64_t h = 0; h < k; h++) {
+                if (X[offX + i * k + h] != 0.0) continue;
+                for (int64_t l = 0; l < len; l++) {
+                    int64_t a = offA + ((i * n + j) * k + h) * len + l;
+                    if (mode == 0) A[a] = fill;
+                    else if (kind == 2) A[a] = (A[a] != 0.0 || fill != 0.0);
+                    else A[a] = A[a] + fill;
+                }
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::slice, PhpMath.php:2691-2776 (math_copy / math_add :3197-3226) */
 int ro_slice(int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,
              double *A, int64_t countA, int64_t offA, int64_t incA,

@@ -396,6 +396,18 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- masking (PhpMath.php:3229-3270) ---------------------------------------------------------------------------
+    def masking(self, m, n, k, len_, fill, mode, X, offsetX, A, offsetA) -> None:
+        if X.dtype() != dtypes.bool_:
+            raise InvalidArgumentException("dtype of X must be bool.")
+        if offsetX + m * k > len(X):
+            raise InvalidArgumentException("Matrix specification too large for buffer X.")
+        if offsetA + m * n * k * len_ > len(A):
+            raise InvalidArgumentException("Matrix specification too large for buffer A.")
+        _cuda("X", X), _cuda("A", A)
+        _capi.check(self._lib.rb200_masking(A.dtype(), m, n, k, len_, float(fill), int(mode), X.device_ptr(), offsetX,
+                                            A.device_ptr_rw(), offsetA))
+
     # ---- slice / repeat (PhpMath.php:2691-2776, :1400-1422) -------------------------------------------------------
     def slice(self, reverse, addMode, m, n, k, size, A, offsetA, incA, Y, offsetY, incY,
               startAxis0, sizeAxis0, startAxis1, sizeAxis1, startAxis2, sizeAxis2) -> None:

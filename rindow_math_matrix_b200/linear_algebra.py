@@ -730,6 +730,49 @@ class LinearAlgebra:
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    # ---- masking (LinearAlgebra.php:5325-5432) -------------------------------------------------------------------
+    def masking(self, mask: NDArray, data: NDArray, batchDims=None, axis=None, fill=None, mode=None) -> NDArray:
+        if mask.dtype() != dtypes.bool_:
+            raise InvalidArgumentException("dtype of mask must be bool.: " + dtypes.NAMES.get(mask.dtype(), "?"))
+        batchDims = 0 if batchDims is None else batchDims
+        if batchDims < 0:
+            batchDims += data.ndim()
+        if batchDims > data.ndim():
+            raise InvalidArgumentException("batchDims (%d) must be less than dims of data (%d) or equal." % (batchDims, data.ndim()))
+        axis = batchDims if axis is None else axis
+        if axis < 0:
+            axis += data.ndim()
+        if axis > data.ndim():
+            raise InvalidArgumentException("axis (%d) must be less than to ndims of data (%d)" % (axis, data.ndim()))
+        if batchDims > axis:
+            if axis == 0:
+                batchDims = 0
+            else:
+                raise InvalidArgumentException("batchDims (%d) must be less than or equal to axis (%d)" % (batchDims, axis))
+        if mask.ndim() < batchDims:
+            raise InvalidArgumentException("batchDims (%d) must be less than or equal to ndims of mask (%d)" % (batchDims, mask.ndim()))
+        fill = 0 if fill is None else fill
+        mode = 0 if mode is None else mode
+        shape = data.shape()
+        outer, rest = shape[:batchDims], shape[batchDims:]
+        broadcast, rest = rest[:axis - batchDims], rest[axis - batchDims:]
+        inner, inner_broadcast = rest[:mask.ndim() - batchDims], rest[mask.ndim() - batchDims:]
+        mshape = mask.shape()
+        outer_x, inner_x = mshape[:batchDims], mshape[batchDims:]
+        names = "mask(%s) => data(%s)" % (",".join(map(str, mask.shape())), ",".join(map(str, data.shape())))
+        if outer != outer_x:
+            raise InvalidArgumentException("Unmatch dimension outer shape.: " + names)
+        if inner != inner_x:
+            raise InvalidArgumentException("Unmatch dimension inner shape.: " + names)
+        prod = lambda v: int(np.prod(v)) if v else 1
+        m, n, k, ln = prod(outer), prod(broadcast), prod(inner), prod(inner_broadcast)
+        if n == 1:
+            k, m = m * k, 1
+        if k == 1:
+            k, ln, m, n = m, n * ln, 1, 1
+        self.math.masking(m, n, k, ln, fill, mode, mask.buffer(), mask.offset(), data.buffer(), data.offset())
+        return data
+
     # ---- slice / stick / stack / concat / split / repeat (LinearAlgebra.php:3944-4365) -----------------------
     def slice(self, input: NDArray, begin, size, output: NDArray | None = None) -> NDArray:
         return self._do_slice(False, input, begin, size, output)

@@ -291,6 +291,14 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def masking(self, m, n, k, len_, fill, mode, X, offX, A, offA):
+        if X.dtype() != dtypes.bool_:
+            raise InvalidArgumentException("dtype of X must be bool.")
+        a = self._f(A)
+        kind = 2 if A.dtype() == dtypes.bool_ else (0 if A.dtype() in (dtypes.float32, dtypes.float64) else 1)
+        _wrap(oracle.masking, m, n, k, len_, fill, mode, kind, self._f(X), offX, a, offA)
+        self._back(A, a)
+
     def slice(self, reverse, addMode, m, n, k, size, A, offA, incA, Y, offY, incY, st0, sz0, st1, sz1, st2, sz2):
         a, y = self._f(A), self._f(Y)
         _wrap(oracle.slice, reverse, addMode, m, n, k, size, a, offA, incA, y, offY, incY, st0, sz0, st1, sz1, st2, sz2)

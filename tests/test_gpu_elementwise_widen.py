@@ -385,3 +385,60 @@ def test_baseline_size_properties(cuda_service):
     assert np.all(np.abs(r - np.abs(a)) <= np.spacing(np.abs(a)))
     mean = la.reduceMean(la.array(a), axis=0).to_numpy()
     assert np.allclose(mean, a.astype(np.float64).mean(axis=0), rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# masking (PhpMath.php:3229-3270)
+# ---------------------------------------------------------------------------------------------------
+MASK_SHAPES = [(1, 1, 6, 1), (2, 4, 3, 1), (1, 1, 6, 4), (3, 5, 7, 2), (1, 8, 1024, 1), (16, 12, 128, 128), (64, 1, 512, 64)]
+
+
+@pytest.mark.parametrize("m,n,k,ln", MASK_SHAPES, ids=[str(s) for s in MASK_SHAPES])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32, dtypes.uint8, dtypes.bool_])
+@pytest.mark.parametrize("mode,fill", [(0, 0.0), (0, -1e9), (1, -1000.0), (1, 2.75)])
+def test_masking_vs_oracle(m, n, k, ln, dt, mode, fill, cuda_service):
+    """Bit-exact: a store of the converted fill or one rounded add; untouched elements stay."""
+    if dt in (dtypes.uint8, dtypes.bool_) and fill < 0:
+        pytest.skip("negative fill into an unsigned buffer")
+    rng = np.random.default_rng(m * 100 + k)
+    npdt = dtypes.NUMPY[dt]
+    offX, offA = 2, 3
+    x = (rng.uniform(0, 1, offX + m * k) > 0.4).astype(np.uint8)
+    if dt == dtypes.bool_:
+        a = (rng.uniform(0, 1, offA + m * n * k * ln) > 0.5).astype(np.uint8)
+    else:
+        a = np.floor(rng.uniform(-50, 50, offA + m * n * k * ln)).astype(npdt)
+    X = CudaBuffer(x.size, dtypes.bool_).from_numpy(x)
+    A = CudaBuffer(a.size, dt).from_numpy(a)
+    cuda_service.math().masking(m, n, k, ln, fill, mode, X, offX, A, offA)
+    ao = a.astype(np.float64)
+    kind = 2 if dt == dtypes.bool_ else (0 if dt in (dtypes.float32, dtypes.float64) else 1)
+    oracle.masking(m, n, k, ln, fill, mode, kind, x.astype(np.float64), offX, ao, offA)
+    if dt == dtypes.float32:
+        ao = ao.astype(np.float32).astype(np.float64)
+    if dt == dtypes.uint8:
+        ao = np.mod(ao, 256)
+    got = A.to_numpy().astype(np.float64)
+    if dt == dtypes.float32 and mode == 1:
+        # one float32 add on the device, one double add in the oracle: equal after rounding the operands' sum once
+        ref32 = a.astype(np.float32)
+        sel = np.zeros(ref32.size, bool)
+        msk = np.broadcast_to((x[offX:offX + m * k].reshape(m, 1, k, 1) == 0), (m, n, k, ln)).reshape(-1)
+        sel[offA:offA + msk.size] = msk
+        ref32[sel] = ref32[sel] + np.float32(fill)
+        assert np.array_equal(A.to_numpy(), ref32)
+    else:
+        assert np.array_equal(got, ao)
+    assert np.array_equal(X.to_numpy(), x)
+
+
+def test_masking_errors(cuda_service):
+    math = cuda_service.math()
+    X = CudaBuffer(6, dtypes.bool_)
+    A = CudaBuffer(24, dtypes.float32)
+    with pytest.raises(rb.InvalidArgumentException, match="dtype of X must be bool."):
+        math.masking(1, 1, 6, 1, 0.0, 0, A, 0, A, 0)
+    with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for buffer X."):
+        math.masking(1, 1, 7, 1, 0.0, 0, X, 0, A, 0)
+    with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for buffer A."):
+        math.masking(1, 5, 6, 1, 0.0, 0, X, 0, A, 0)

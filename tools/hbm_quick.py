@@ -69,6 +69,10 @@ def main():
         # split [8192, 4096] along axis 1 -> the [8192, 3072] part (96 MB out of 128 MB), and repeat [8192,1024] x 4
         timed("slice", lambda i: math.slice(False, False, m, n, 1, 1, As[i], 0, 1, Y2, 0, 1, 0, m, 512, 3072, 0, 1), 2 * m * 3072 * 4)
         timed("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4)
+    if not want or "masking" in want:
+        # attention-score mask: scores [64 batch x 16 heads, 128, 256] f32 (128 MB), key mask [64, 256] broadcast
+        Mk = CudaBuffer(64 * 256, dtypes.bool_).from_numpy((rng.uniform(0, 1, 64 * 256) > 0.5).astype(np.uint8))
+        timed("masking", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 0, Mk, 0, As[i], 0), m * n * 4 // 2)
     vocab, dim, ntok = 32768, 1024, 32768                       # table 128 MiB; one step moves 2 x 128 MiB
     ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
     timed("gather", lambda i: math.gather(False, False, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 2 * ntok * dim * 4)
