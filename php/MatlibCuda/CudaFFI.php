@@ -111,6 +111,8 @@ class CudaFFI
                            int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
                            int cols_channels_first,
                            void* cols, int64_t cols_offset, int64_t cols_size);
+        int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode,
+                          const void* X, int64_t offX, void* A, int64_t offA);
         int rb200_slice(int dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,
                         void* A, int64_t offA, int64_t incA, void* Y, int64_t offY, int64_t incY,
                         int64_t start0, int64_t size0, int64_t start1, int64_t size1, int64_t start2, int64_t size2);

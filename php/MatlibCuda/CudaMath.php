@@ -119,6 +119,27 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** masking (PhpMath.php:3229-3270) */
+    public function masking(int $m,int $n,int $k,int $len,float $fill,int $mode,
+        Buffer $X,int $offsetX,Buffer $A,int $offsetA) : void
+    {
+        if (!$this->anyOnDevice($X,$A)) {
+            parent::masking($m,$n,$k,$len,$fill,$mode,$X,$offsetX,$A,$offsetA);
+            return;
+        }
+        if ($X->dtype()!=NDArray::bool) {
+            throw new InvalidArgumentException('dtype of X must be bool.');
+        }
+        if ($offsetX+$m*$k > count($X)) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer X.');
+        }
+        if ($offsetA+$m*$n*$k*$len > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer A.');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_masking($A->abiDtype(),$m,$n,$k,$len,$fill,$mode,
+            $X->devicePtr(),$offsetX,$A->devicePtrRW(),$offsetA));
+    }
+
     /** slice / stick (PhpMath.php:2691-2776): any dtype, bit-exact copies, += in add mode */
     public function slice(bool $reverse,bool $addMode,int $m,int $n,int $k,int $size,
         Buffer $A,int $offsetA,int $incA,Buffer $Y,int $offsetY,int $incY,

@@ -70,9 +70,14 @@ def main():
         timed("slice", lambda i: math.slice(False, False, m, n, 1, 1, As[i], 0, 1, Y2, 0, 1, 0, m, 512, 3072, 0, 1), 2 * m * 3072 * 4)
         timed("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4)
     if not want or "masking" in want:
-        # attention-score mask: scores [64 batch x 16 heads, 128, 256] f32 (128 MB), key mask [64, 256] broadcast
-        Mk = CudaBuffer(64 * 256, dtypes.bool_).from_numpy((rng.uniform(0, 1, 64 * 256) > 0.5).astype(np.uint8))
-        timed("masking", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 0, Mk, 0, As[i], 0), m * n * 4 // 2)
+        # attention-score padding mask: scores [64 batch, 16 heads x 128 queries, 256 keys] f32 (128 MB); per batch the keys
+        # past a random length are masked out (set to -1e9): only those elements are written
+        lens = rng.integers(64, 257, 64)
+        mk = (np.arange(256)[None, :] < lens[:, None]).astype(np.uint8)
+        Mk = CudaBuffer(64 * 256, dtypes.bool_).from_numpy(mk.reshape(-1))
+        masked = int((mk == 0).sum()) * 16 * 128
+        timed("masking", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 0, Mk, 0, As[i], 0), masked * 4)
+        timed("masking_add", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 1, Mk, 0, As[i], 0), 2 * masked * 4)
     vocab, dim, ntok = 32768, 1024, 32768                       # table 128 MiB; one step moves 2 x 128 MiB
     ids = CudaBuffer(ntok, dtypes.int32).from_numpy(rng.integers(0, vocab, ntok).astype(np.int32))
     timed("gather", lambda i: math.gather(False, False, ntok, dim, vocab, ids, 0, As[i], 0, Y2, 0), 2 * ntok * dim * 4)
