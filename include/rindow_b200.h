@@ -341,6 +341,10 @@ int rb200_repeat(int dtype, int64_t m, int64_t k, int64_t repeats, const void* A
 int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode,
                   const void* X, int64_t offX, void* A, int64_t offA);
 
+/* ---- bandpart: PhpMath::bandpart -- zero A[b,i,j] (A is [m,n,k]) outside the band: (lower >= 0 && i-j > lower) ||
+ *      (upper >= 0 && j-i > upper); negative bounds keep the whole triangle.  Any dtype (bool included). */
+int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t offA, int64_t lower, int64_t upper);
+
 /* ---- im2col3d / col2im3d: PhpMath::im2col3d (PhpMath.php:2396-2600, copyCell3d :2319-2390), the Conv3D sibling.
  *      images [b,d,h,w,c] (channels_first: [b,c,d,h,w]); cols [b,od,oh,ow,kd,kh,kw,c] (cols_channels_first:
  *      [b,od,oh,ow,c,kd,kh,kw]).  Same out / padding rules per axis as im2col2d, including the reference's

@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
         L.ro_softmax.argtypes = [i64, i64, p, i64, i64, i64]
         L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
+        L.ro_bandpart.argtypes = [i64, i64, i64, p, i64, i64, i64, i64]
         L.ro_masking.argtypes = [i64, i64, i64, i64, dbl, i32, i32, p, i64, i64, p, i64, i64]
         L.ro_slice.argtypes = [i32, i32, i64, i64, i64, i64, p, i64, i64, i64, p, i64, i64, i64, i64, i64, i64, i64, i64, i64]
         L.ro_repeat.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64]
@@ -94,7 +95,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -337,6 +338,10 @@ def im2col2d(reverse, images, images_offset, images_size, batches, im_h, im_w, c
                              stride_h, stride_w, int(bool(padding)), int(bool(channels_first)),
                              dilation_h, dilation_w, int(bool(cols_channels_first)),
                              _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
+
+
+def bandpart(m, n, k, A, offA, lower, upper):
+    _check(lib().ro_bandpart(m, n, k, _ptr(_buf(A)), A.size, offA, lower, upper))
 
 
 # PhpMath::masking :3229-3270 (kind: 0 float, 1 integer, 2 bool data)

@@ -447,6 +447,20 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::bandpart */
+int ro_bandpart(int64_t m, int64_t n, int64_t k, double *A, int64_t countA, int64_t offA, int64_t lower, int64_t upper)
+{
+    if (offA + m * n * k > countA) return RO_E_ARG;
+    for (int64_t b = 0; b < m; b++) {
+        for (int64_t i = 0; i < n; i++) {
+            for (int64_t j = 0; j < k; j++) {
+                if ((lower >= 0 && (i - j) > lower) || (upper >= 0 && (j - i) > upper)) A[offA + b * n * k + i * k + j] = 0;
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::masking, PhpMath.php:3229-3270.  X holds the bool mask as 0 / 1 doubles; kind: 0 float, 1 integer (fill
  * truncated toward zero as the C buffer stores it), 2 bool (mode 1: A || fill). */
 int ro_masking(int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode, int kind,

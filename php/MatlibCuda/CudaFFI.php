@@ -111,6 +111,7 @@ class CudaFFI
                            int padding, int channels_first, int64_t dilation_h, int64_t dilation_w,
                            int cols_channels_first,
                            void* cols, int64_t cols_offset, int64_t cols_size);
+        int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t offA, int64_t lower, int64_t upper);
         int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode,
                           const void* X, int64_t offX, void* A, int64_t offA);
         int rb200_slice(int dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int64_t size,

@@ -119,6 +119,16 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** bandpart (PhpMath::bandpart): zero outside the band, any dtype */
+    public function bandpart(int $m,int $n,int $k,Buffer $A,int $offset,int $lower,int $upper) : void
+    {
+        if (!$this->anyOnDevice($A)) { parent::bandpart($m,$n,$k,$A,$offset,$lower,$upper); return; }
+        if ($offset+$m*$n*$k > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer.');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_bandpart($A->abiDtype(),$m,$n,$k,$A->devicePtrRW(),$offset,$lower,$upper));
+    }
+
     /** masking (PhpMath.php:3229-3270) */
     public function masking(int $m,int $n,int $k,int $len,float $fill,int $mode,
         Buffer $X,int $offsetX,Buffer $A,int $offsetA) : void

@@ -141,7 +141,51 @@ int masking_launch(int64_t m, int64_t n, int64_t k, int64_t len, double fill, in
     return RB200_OK;
 }
 
+// bandpart (PhpMath.php bandpart): A[b,i,j] = 0 where (lower >= 0 && i-j > lower) || (upper >= 0 && j-i > upper).
+// One thread per element word; zero stores only (A is never read).
+template <typename W>
+__global__ void __launch_bounds__(MK_THREADS)
+bandpart_kernel(int64_t total, int64_t n, int64_t k, int64_t lower, int64_t upper, W* __restrict__ A)
+{
+    const int64_t nk = n * k;
+    for (int64_t t = (int64_t)blockIdx.x * MK_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * MK_THREADS) {
+        const int64_t r = t % nk;
+        const int64_t i = r / k, j = r - i * k;
+        if ((lower >= 0 && (i - j) > lower) || (upper >= 0 && (j - i) > upper)) A[t] = (W)0;
+    }
+}
+
+template <typename W>
+int bandpart_launch(int64_t m, int64_t n, int64_t k, int64_t lower, int64_t upper, void* A)
+{
+    rb200::Context& c = rb200::ctx();
+    const int64_t total = m * n * k;
+    int64_t grid = rb_ceil_div(total, MK_THREADS);
+    const int64_t cap = (int64_t)c.sm_count * 32;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    bandpart_kernel<W><<<(unsigned)grid, MK_THREADS, 0, c.stream>>>(total, n, k, lower, upper, reinterpret_cast<W*>(A));
+    RB_LAUNCH_CHECK("bandpart_kernel");
+    return RB200_OK;
+}
+
 }  // namespace
+
+extern "C" int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t offA, int64_t lower, int64_t upper)
+{
+    RB_REQUIRE_INIT();
+    if (!A) RB_INVALID("NULL buffer");
+    if (m < 1 || n < 1 || k < 1 || offA < 0) RB_INVALID("bandpart: bad shape / offset");
+    const int es = rb_dtype_size(dtype);
+    char* a = reinterpret_cast<char*>(A) + offA * es;
+    switch (es) {                                   // zero is all-bits-zero for every supported dtype
+        case 1: return bandpart_launch<uint8_t>(m, n, k, lower, upper, a);
+        case 2: return bandpart_launch<uint16_t>(m, n, k, lower, upper, a);
+        case 4: return bandpart_launch<uint32_t>(m, n, k, lower, upper, a);
+        case 8: return bandpart_launch<uint64_t>(m, n, k, lower, upper, a);
+        default: RB_UNSUPPORTED("bandpart: unsupported dtype %d", dtype);
+    }
+}
 
 extern "C" int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, double fill, int mode,
                              const void* X, int64_t offX, void* A, int64_t offA)

@@ -396,6 +396,13 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- bandpart (PhpMath::bandpart): zero outside the band, in place ------------------------------------------------
+    def bandpart(self, m, n, k, A, offset, lower, upper) -> None:
+        if offset + m * n * k > len(A):
+            raise InvalidArgumentException("Matrix specification too large for buffer.")
+        _cuda("A", A)
+        _capi.check(self._lib.rb200_bandpart(A.dtype(), m, n, k, A.device_ptr_rw(), offset, int(lower), int(upper)))
+
     # ---- masking (PhpMath.php:3229-3270) ---------------------------------------------------------------------------
     def masking(self, m, n, k, len_, fill, mode, X, offsetX, A, offsetA) -> None:
         if X.dtype() != dtypes.bool_:

@@ -730,6 +730,16 @@ class LinearAlgebra:
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    def bandpart(self, A: NDArray, lower: int, upper: int) -> NDArray:           # LinearAlgebra::bandpart
+        if A.ndim() < 2:
+            raise InvalidArgumentException("input array must be 2D or upper.")
+        shape = A.shape()
+        k = shape.pop()
+        n = shape.pop()
+        m = int(np.prod(shape)) if shape else 1
+        self.math.bandpart(m, n, k, A.buffer(), A.offset(), lower, upper)
+        return A
+
     # ---- masking (LinearAlgebra.php:5325-5432) -------------------------------------------------------------------
     def masking(self, mask: NDArray, data: NDArray, batchDims=None, axis=None, fill=None, mode=None) -> NDArray:
         if mask.dtype() != dtypes.bool_:

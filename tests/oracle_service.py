@@ -291,6 +291,11 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def bandpart(self, m, n, k, A, offA, lower, upper):
+        a = self._f(A)
+        _wrap(oracle.bandpart, m, n, k, a, offA, lower, upper)
+        self._back(A, a)
+
     def masking(self, m, n, k, len_, fill, mode, X, offX, A, offA):
         if X.dtype() != dtypes.bool_:
             raise InvalidArgumentException("dtype of X must be bool.")

@@ -442,3 +442,18 @@ def test_masking_errors(cuda_service):
         math.masking(1, 1, 7, 1, 0.0, 0, X, 0, A, 0)
     with pytest.raises(rb.InvalidArgumentException, match="Matrix specification too large for buffer A."):
         math.masking(1, 5, 6, 1, 0.0, 0, X, 0, A, 0)
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 5, 5), (2, 5, 5), (3, 7, 4), (4, 4, 9), (16, 512, 512), (1, 1, 1)])
+@pytest.mark.parametrize("lower,upper", [(0, -1), (-1, 0), (0, 0), (0, 1), (1, 0), (2, 3), (-1, -1), (100, 100)])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32, dtypes.bool_])
+def test_bandpart_vs_oracle(m, n, k, lower, upper, dt, cuda_service):
+    npdt = dtypes.NUMPY[dt]
+    rng = np.random.default_rng(n * 13 + k)
+    off = 3
+    a = (rng.integers(1, 3, off + m * n * k)).astype(npdt) if dt != dtypes.bool_ else np.ones(off + m * n * k, np.uint8)
+    A = CudaBuffer(a.size, dt).from_numpy(a)
+    cuda_service.math().bandpart(m, n, k, A, off, lower, upper)
+    ao = a.astype(np.float64)
+    oracle.bandpart(m, n, k, ao, off, lower, upper)
+    assert np.array_equal(A.to_numpy().astype(np.float64), ao)
