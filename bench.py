@@ -604,6 +604,15 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
            2 * m * 3072 * 4, {"shape": "[8192,4096] -> columns 512..3583 (split / concat along axis 1)"})
     report("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4,
            {"shape": "[8192,1024] -> [8192,4,1024]"})
+    # attention-score padding mask over [64 batch, 16 heads x 128 queries, 256 keys] (the same 128 MB operands): per batch
+    # the keys past a random length are set to -1e9; only those elements are written
+    lens = np.random.default_rng(77).integers(64, 257, 64)
+    mk = (np.arange(256)[None, :] < lens[:, None]).astype(np.uint8)
+    Mk = CudaBuffer(64 * 256, dtypes.bool_).from_numpy(mk.reshape(-1))
+    masked = int((mk == 0).sum()) * 16 * 128
+    report("masking", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 0, Mk, 0, As[i], 0), masked * 4,
+           {"shape": "scores [64,2048,256], key padding mask [64,256], %.0f %% masked (bytes = masked elements written)"
+                     % (100.0 * masked / (m * n))})
     Yv = CudaBuffer(m, dtypes.float32)
     report("gemv", lambda i: blas1.gemv(_B.RowMajor, _B.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Yv, 0, 1),
            m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096] x [4096]"})
