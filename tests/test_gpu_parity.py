@@ -903,3 +903,70 @@ def test_buffer_host_device_coherence(cuda_service):
     la.add(X, A)
     assert A.toArray() == [[25, 42], [23, 20]]
     assert A[1][1] == 20.0 and A[0].toArray() == [25, 42]
+
+
+_FUZZ_PATHS = []
+
+
+def _conv_fuzz_cases(n=48, seed=20260):
+    """Random K <= 32 conv shapes for the TMEM-operand kernel: channels 1..6, filters up to 5x5, strides / dilations 1..3,
+    both paddings, ragged widths around the 128-cell tile, 32..128 filters."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        c = int(rng.integers(1, 7))
+        kh, kw = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+        if kh * kw * c > 32:
+            continue
+        st = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        dil = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        pad = bool(rng.integers(0, 2))
+        h = int(rng.integers((kh - 1) * dil[0] + 1, 40))
+        w = int(rng.choice([rng.integers((kw - 1) * dil[1] + 1, 64), rng.integers(120, 140), rng.integers(250, 300)]))
+        if w < (kw - 1) * dil[1] + 1:
+            continue
+        f = int(rng.choice([32, 36, 48, 64, 96, 100, 128]))
+        b = int(rng.integers(1, 4))
+        if len(cases) % 3:  # two in three inside the TMEM kernel's envelope (odd column stride, W*C and filters multiples of 4)
+            st = (st[0], int(rng.choice([1, 3])))
+            c = c if c != 4 else 3
+            if kh * kw * c > 32:
+                continue
+            w += (-w) % 4
+            f = int(rng.choice([32, 36, 48, 64, 96, 100, 128]))
+        cases.append((b, h, w, c, kh, kw, f, st, pad, dil, bool(rng.integers(0, 2))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _conv_fuzz_cases(), ids=lambda c: "x".join(str(v) for v in c[:7]))
+def test_conv2d_forward_fuzz_vs_oracle(case, cuda_service):
+    b, h, w, c, kh, kw, f, st, pad, dil, use_bias = case
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.uniform(-1, 1, (b, h, w, c)).astype(np.float32)
+    W = (rng.standard_normal((kh, kw, c, f)) * 0.2).astype(np.float32)
+    bias = rng.standard_normal(f).astype(np.float32) if use_bias else None
+    la = LinearAlgebra(cuda_service)
+    out = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st, padding=pad,
+                    dilation_rate=dil, fused=True)
+    path = rb._capi.last_gemm_path()
+    _FUZZ_PATHS.append(path)
+    K = kh * kw * c
+    shape = oracle.im2col2d_out_shape(b, h, w, c, kh, kw, st[0], st[1], pad, dil[0], dil[1], False)
+    M = shape[0] * shape[1] * shape[2]
+    cols = np.zeros(M * K)
+    oracle.im2col2d(False, oracle.as_buffer(img), 0, img.size, b, h, w, c, kh, kw, st[0], st[1], pad, False,
+                    dil[0], dil[1], False, cols, 0, cols.size)
+    ref = np.zeros(M * f)
+    oracle.gemm_rows_fast(0, M, f, K, 1.0, cols, K, oracle.as_buffer(W), f, 0.0, ref, f)
+    if bias is not None:
+        oracle.add(False, M, f, 1.0, oracle.as_buffer(bias), 0, 1, ref, 0, f)
+    assert out.shape() == [shape[0], shape[1], shape[2], f]
+    got = out.to_numpy().reshape(-1).astype(np.float64)
+    assert np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30) < GEMM_TOL[rb.GEMM_TF32X3], path
+
+
+def test_conv2d_forward_fuzz_covers_the_tmem_kernel():
+    # the kernel's envelope also depends on slab / staging sizes, so the share is asserted over the whole sample
+    if len(_FUZZ_PATHS) < 48:
+        pytest.skip("fuzz cases were deselected")
+    assert sum(p.endswith("_tmem_conv") for p in _FUZZ_PATHS) >= 20, _FUZZ_PATHS
