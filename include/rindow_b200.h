@@ -345,6 +345,25 @@ int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, doubl
  *      (upper >= 0 && j-i > upper); negative bounds keep the whole triangle.  Any dtype (bool included). */
 int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t offA, int64_t lower, int64_t upper);
 
+/* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
+ *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
+ *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order
+ *      (the reference adds serially). */
+int rb200_cumsumb(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA, int exclusive, int reverse,
+                  void* B, int64_t offB);
+
+/* ---- cumsum: PhpMath::cumsum (PhpMath.php:1822-1859), the 1-D form with increments.  As in the reference, reverse
+ *      walks X forwards and writes Y backwards (Y[n-1] = X[0], Y[n-2] = X[0]+X[1] ...). */
+int rb200_cumsum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int exclusive, int reverse,
+                 void* Y, int64_t offY, int64_t incY);
+
+/* ---- searchsorted: PhpMath::searchsorted (PhpMath.php:1780-1820).  Y[i] = number of leading elements of row i of
+ *      A[m,n] (ldA == 0: one shared row) that X[i] is above (right: above or equal), the walk stopping at the first
+ *      element it is not -- identical to the reference for unsorted rows and NaN as well (sorted rows are bisected).
+ *      dtype float32 / float64; index_dtype int32 / uint32 / int64 / uint64. */
+int rb200_searchsorted(int dtype, int index_dtype, int64_t m, int64_t n, const void* A, int64_t offA, int64_t ldA,
+                       const void* X, int64_t offX, int64_t incX, int right, void* Y, int64_t offY, int64_t incY);
+
 /* ---- im2col3d / col2im3d: PhpMath::im2col3d (PhpMath.php:2396-2600, copyCell3d :2319-2390), the Conv3D sibling.
  *      images [b,d,h,w,c] (channels_first: [b,c,d,h,w]); cols [b,od,oh,ow,kd,kh,kw,c] (cols_channels_first:
  *      [b,od,oh,ow,c,kd,kh,kw]).  Same out / padding rules per axis as im2col2d, including the reference's

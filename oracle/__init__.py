@@ -79,6 +79,9 @@ def lib() -> ctypes.CDLL:
         L.ro_im2col2d.argtypes = [i32, p, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
         L.ro_bandpart.argtypes = [i64, i64, i64, p, i64, i64, i64, i64]
+        L.ro_cumsumb.argtypes = [i64, i64, i64, p, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, p, i64, i64]
+        L.ro_cumsum.argtypes = [i64, p, i64, i64, i64, ctypes.c_int, ctypes.c_int, p, i64, i64, i64]
+        L.ro_searchsorted.argtypes = [i64, i64, p, i64, i64, i64, p, i64, i64, i64, ctypes.c_int, p, i64, i64, i64]
         L.ro_masking.argtypes = [i64, i64, i64, i64, dbl, i32, i32, p, i64, i64, p, i64, i64]
         L.ro_slice.argtypes = [i32, i32, i64, i64, i64, i64, p, i64, i64, i64, p, i64, i64, i64, i64, i64, i64, i64, i64, i64]
         L.ro_repeat.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64]
@@ -95,7 +98,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_cumsumb", "ro_cumsum", "ro_searchsorted", "ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -338,6 +341,22 @@ def im2col2d(reverse, images, images_offset, images_size, batches, im_h, im_w, c
                              stride_h, stride_w, int(bool(padding)), int(bool(channels_first)),
                              dilation_h, dilation_w, int(bool(cols_channels_first)),
                              _ptr(_buf(cols)), cols.size, cols_offset, cols_size))
+
+
+# PhpMath::cumsumb :1861-1904, cumsum :1822-1859, searchsorted :1780-1820
+def cumsumb(m, n, k, A, offA, exclusive, reverse, f32, B, offB):
+    _check(lib().ro_cumsumb(m, n, k, _ptr(_buf(A)), A.size, offA, int(bool(exclusive)), int(bool(reverse)), int(bool(f32)),
+                            _ptr(_buf(B)), B.size, offB))
+
+
+def cumsum(n, X, offX, incX, exclusive, reverse, Y, offY, incY):
+    _check(lib().ro_cumsum(n, _ptr(_buf(X)), X.size, offX, incX, int(bool(exclusive)), int(bool(reverse)),
+                           _ptr(_buf(Y)), Y.size, offY, incY))
+
+
+def searchsorted(m, n, A, offA, ldA, X, offX, incX, right, Y, offY, incY):
+    _check(lib().ro_searchsorted(m, n, _ptr(_buf(A)), A.size, offA, ldA, _ptr(_buf(X)), X.size, offX, incX,
+                                 int(bool(right)), _ptr(_buf(Y)), Y.size, offY, incY))
 
 
 def bandpart(m, n, k, A, offA, lower, upper):

@@ -447,6 +447,66 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
+ * buffer rounds at every step (f32 != 0). */
+int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,
+               int f32, double *B, int64_t countB, int64_t offB)
+{
+    if (offA + m * n * k > countA || offB + m * n * k > countB) return RO_E_ARG;
+    for (int64_t i = 0; i < m; i++) {
+        int64_t ida = offA + i * n * k + (reverse ? (n - 1) * k : 0);
+        int64_t idb = offB + i * n * k + (reverse ? (n - 1) * k : 0);
+        const int64_t ld = reverse ? -k : k;
+        for (int64_t h = 0; h < k; h++) B[idb + h] = exclusive ? 0.0 : A[ida + h];
+        for (int64_t j = 0; j < n - 1; j++) {
+            idb += ld;
+            if (!exclusive) ida += ld;
+            for (int64_t h = 0; h < k; h++) {
+                const double v = B[idb - ld + h] + A[ida + h];
+                B[idb + h] = f32 ? (double)(float)v : v;
+            }
+            if (exclusive) ida += ld;
+        }
+    }
+    return RO_OK;
+}
+
+/* PhpMath::cumsum, PhpMath.php:1822-1859: the running value is a PHP float (double); reverse only turns Y around. */
+int ro_cumsum(int64_t n, const double *X, int64_t countX, int64_t offX, int64_t incX, int exclusive, int reverse,
+              double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (n < 1 || offX + (n - 1) * incX >= countX || offY + (n - 1) * incY >= countY) return RO_E_ARG;
+    int64_t idx = offX, idy = offY;
+    if (reverse) { idy = offY + incY * (n - 1); incY = -incY; }
+    double value = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        if (exclusive) { Y[idy] = value; value += X[idx]; }
+        else { value += X[idx]; Y[idy] = value; }
+        idx += incX; idy += incY;
+    }
+    return RO_OK;
+}
+
+/* PhpMath::searchsorted, PhpMath.php:1780-1820 */
+int ro_searchsorted(int64_t m, int64_t n, const double *A, int64_t countA, int64_t offA, int64_t ldA,
+                    const double *X, int64_t countX, int64_t offX, int64_t incX, int right,
+                    double *Y, int64_t countY, int64_t offY, int64_t incY)
+{
+    if (m < 1 || offA + (m - 1) * ldA + n > countA || offX + (m - 1) * incX >= countX || offY + (m - 1) * incY >= countY) {
+        return RO_E_ARG;
+    }
+    for (int64_t i = 0; i < m; i++) {
+        const double v = X[offX + i * incX];
+        const double *a = A + offA + i * ldA;
+        int64_t j = 0;
+        for (; j < n; j++) {
+            if (right ? !(v >= a[j]) : !(v > a[j])) break;
+        }
+        Y[offY + i * incY] = (double)j;
+    }
+    return RO_OK;
+}
+
 /* PhpMath::bandpart */
 int ro_bandpart(int64_t m, int64_t n, int64_t k, double *A, int64_t countA, int64_t offA, int64_t lower, int64_t upper)
 {

@@ -119,6 +119,67 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** cumsumb (PhpMath.php:1861-1904): running sum along the middle axis of [m,n,k] */
+    public function cumsumb(int $m,int $n,int $k,Buffer $A,int $offsetA,bool $exclusive,bool $reverse,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($A,$B)) { parent::cumsumb($m,$n,$k,$A,$offsetA,$exclusive,$reverse,$B,$offsetB); return; }
+        if ($offsetA+$m*$n*$k > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferA.');
+        }
+        if ($offsetB+$m*$n*$k > count($B)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferB.');
+        }
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and B');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_cumsumb($A->abiDtype(),$m,$n,$k,$A->devicePtr(),$offsetA,
+            $exclusive?1:0,$reverse?1:0,$B->devicePtrRW(),$offsetB));
+    }
+
+    /** cumsum (PhpMath.php:1822-1859): 1-D running sum with increments */
+    public function cumsum(int $n,Buffer $X,int $offsetX,int $incX,bool $exclusive,bool $reverse,Buffer $Y,int $offsetY,int $incY) : void
+    {
+        if (!$this->anyOnDevice($X,$Y)) { parent::cumsum($n,$X,$offsetX,$incX,$exclusive,$reverse,$Y,$offsetY,$incY); return; }
+        if ($n<1||$incX<1||$incY<1) {
+            throw new InvalidArgumentException('Argument n / inc must be greater than 0.');
+        }
+        if ($offsetX+($n-1)*$incX >= count($X)) {
+            throw new InvalidArgumentException('Vector specification too large for bufferX.');
+        }
+        if ($offsetY+($n-1)*$incY >= count($Y)) {
+            throw new InvalidArgumentException('Vector specification too large for bufferY.');
+        }
+        if ($X->dtype()!=$Y->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for X and Y');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_cumsum($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,
+            $exclusive?1:0,$reverse?1:0,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
+    /** searchsorted (PhpMath.php:1780-1820) */
+    public function searchsorted(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX,
+        bool $right,Buffer $Y,int $offsetY,int $incY) : void
+    {
+        if (!$this->anyOnDevice($A,$X,$Y)) { parent::searchsorted($m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX,$right,$Y,$offsetY,$incY); return; }
+        if ($m<1||$incX<1||$incY<1) {
+            throw new InvalidArgumentException('Argument m / inc must be greater than 0.');
+        }
+        if ($offsetA+($m-1)*$ldA+$n > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferA.');
+        }
+        if ($offsetX+($m-1)*$incX >= count($X)) {
+            throw new InvalidArgumentException('Vector specification too large for bufferX.');
+        }
+        if ($offsetY+($m-1)*$incY >= count($Y)) {
+            throw new InvalidArgumentException('Vector specification too large for bufferY.');
+        }
+        if ($A->dtype()!=$X->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and X');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_searchsorted($A->abiDtype(),$Y->abiDtype(),$m,$n,$A->devicePtr(),$offsetA,$ldA,
+            $X->devicePtr(),$offsetX,$incX,$right?1:0,$Y->devicePtrRW(),$offsetY,$incY));
+    }
+
     /** bandpart (PhpMath::bandpart): zero outside the band, any dtype */
     public function bandpart(int $m,int $n,int $k,Buffer $A,int $offset,int $lower,int $upper) : void
     {

@@ -396,6 +396,46 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- cumsum / cumsumb / searchsorted (PhpMath.php:1780-1904) ------------------------------------------------------
+    def cumsumb(self, m, n, k, A, offsetA, exclusive, reverse, B, offsetB) -> None:
+        if offsetA + m * n * k > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA.")
+        if offsetB + m * n * k > len(B):
+            raise InvalidArgumentException("Matrix specification too large for bufferB.")
+        _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        _capi.check(self._lib.rb200_cumsumb(A.dtype(), m, n, k, A.device_ptr(), offsetA, 1 if exclusive else 0,
+                                            1 if reverse else 0, B.device_ptr_rw(), offsetB))
+
+    def cumsum(self, n, X, offsetX, incX, exclusive, reverse, Y, offsetY, incY) -> None:
+        if n < 1 or incX < 1 or incY < 1:
+            raise InvalidArgumentException("Argument n / inc must be greater than 0.")
+        if offsetX + (n - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for bufferX.")
+        if offsetY + (n - 1) * incY >= len(Y):
+            raise InvalidArgumentException("Vector specification too large for bufferY.")
+        _cuda("X", X), _cuda("Y", Y)
+        if X.dtype() != Y.dtype():
+            raise InvalidArgumentException("Unmatch data type for X and Y")
+        _capi.check(self._lib.rb200_cumsum(X.dtype(), n, X.device_ptr(), offsetX, incX, 1 if exclusive else 0,
+                                           1 if reverse else 0, Y.device_ptr_rw(), offsetY, incY))
+
+    def searchsorted(self, m, n, A, offsetA, ldA, X, offsetX, incX, right, Y, offsetY, incY) -> None:
+        if m < 1 or incX < 1 or incY < 1:
+            raise InvalidArgumentException("Argument m / inc must be greater than 0.")
+        if offsetA + (m - 1) * ldA + n > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA.")
+        if offsetX + (m - 1) * incX >= len(X):
+            raise InvalidArgumentException("Vector specification too large for bufferX.")
+        if offsetY + (m - 1) * incY >= len(Y):
+            raise InvalidArgumentException("Vector specification too large for bufferY.")
+        _cuda("A", A), _cuda("X", X), _cuda("Y", Y)
+        if A.dtype() != X.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and X")
+        _capi.check(self._lib.rb200_searchsorted(A.dtype(), Y.dtype(), m, n, A.device_ptr(), offsetA, ldA, X.device_ptr(),
+                                                 offsetX, incX, 1 if right else 0, Y.device_ptr_rw(), offsetY, incY))
+
     # ---- bandpart (PhpMath::bandpart): zero outside the band, in place ------------------------------------------------
     def bandpart(self, m, n, k, A, offset, lower, upper) -> None:
         if offset + m * n * k > len(A):

@@ -730,6 +730,56 @@ class LinearAlgebra:
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    def cumsum(self, inputs: NDArray, axis=None, exclusive=None, reverse=None, outputs=None) -> NDArray:
+        """LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812): running sum along one axis through cumsumb."""
+        ndim = inputs.ndim()
+        orig = axis
+        axis = 0 if axis is None else axis
+        if axis < 0:
+            axis += ndim
+        if axis < 0 or axis > ndim - 1:
+            raise InvalidArgumentException(f"Invalid axis: {'null' if orig is None else orig}")
+        shape = inputs.shape()
+        m = int(np.prod(shape[:axis])) if axis else 1
+        n = shape[axis]
+        k = int(np.prod(shape[axis + 1:])) if axis + 1 < ndim else 1
+        if outputs is None:
+            outputs = self.alloc(shape, inputs.dtype())
+        if inputs.shape() != outputs.shape():
+            raise InvalidArgumentException(f"Unmatch shape of dimension: {inputs.shape()},{outputs.shape()}")
+        self.math.cumsumb(m, n, k, inputs.buffer(), inputs.offset(), bool(exclusive), bool(reverse),
+                          outputs.buffer(), outputs.offset())
+        return outputs
+
+    def searchsorted(self, A: NDArray, X: NDArray, right=None, dtype=None, Y=None) -> NDArray:
+        """LinearAlgebra::searchsorted (LinearAlgebra.php:4700-4762): 1-D A is shared by every X, 2-D A pairs row i
+        with X[i]."""
+        if A.ndim() == 1:
+            individual = False
+        elif A.ndim() == 2:
+            individual = True
+        else:
+            raise InvalidArgumentException("A must be 1D or 2D NDArray.")
+        right = bool(right)
+        if dtype is None:
+            dtype = dtypes.int32
+        if Y is None:
+            Y = self.alloc(X.shape(), dtype)
+        if Y.dtype() not in (dtypes.uint32, dtypes.int32, dtypes.uint64, dtypes.int64):
+            raise InvalidArgumentException("dtype of Y must be int32 or int64")
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException(f"Unmatch shape of dimension: {X.shape()},{Y.shape()}")
+        if individual:
+            m, n = A.shape()
+            if m != X.size():
+                raise InvalidArgumentException(f"Unmatch shape of dimension A,X: {A.shape()},{X.shape()}")
+            ldA = n
+        else:
+            m, n, ldA = X.size(), A.size(), 0
+        self.math.searchsorted(m, n, A.buffer(), A.offset(), ldA, X.buffer(), X.offset(), 1, right,
+                               Y.buffer(), Y.offset(), 1)
+        return Y
+
     def bandpart(self, A: NDArray, lower: int, upper: int) -> NDArray:           # LinearAlgebra::bandpart
         if A.ndim() < 2:
             raise InvalidArgumentException("input array must be 2D or upper.")

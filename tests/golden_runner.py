@@ -70,7 +70,8 @@ def _la_arg(la, a):
                                            "uint64": np.uint64}[a["dtype"]])      # PHP ints wrap into the C buffer
         x = la.array(v, dtype=dtype)
     if "view" in a:
-        x = x[a["view"]]
+        v = a["view"]
+        x = x[slice(v[0], v[1])] if isinstance(v, list) else x[v]          # [start, stop): PHP's R(start, stop)
     return x
 
 

@@ -291,6 +291,21 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
+        b = self._f(B)
+        _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)
+        self._back(B, b)
+
+    def cumsum(self, n, X, offX, incX, exclusive, reverse, Y, offY, incY):
+        y = self._f(Y)
+        _wrap(oracle.cumsum, n, self._f(X), offX, incX, exclusive, reverse, y, offY, incY)
+        self._back(Y, y)
+
+    def searchsorted(self, m, n, A, offA, ldA, X, offX, incX, right, Y, offY, incY):
+        y = self._f(Y)
+        _wrap(oracle.searchsorted, m, n, self._f(A), offA, ldA, self._f(X), offX, incX, right, y, offY, incY)
+        self._back(Y, y)
+
     def bandpart(self, m, n, k, A, offA, lower, upper):
         a = self._f(A)
         _wrap(oracle.bandpart, m, n, k, a, offA, lower, upper)

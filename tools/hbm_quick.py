@@ -69,6 +69,13 @@ def main():
         # split [8192, 4096] along axis 1 -> the [8192, 3072] part (96 MB out of 128 MB), and repeat [8192,1024] x 4
         timed("slice", lambda i: math.slice(False, False, m, n, 1, 1, As[i], 0, 1, Y2, 0, 1, 0, m, 512, 3072, 0, 1), 2 * m * 3072 * 4)
         timed("repeat", lambda i: math.repeat(m, 1024, 4, As[i], 0, Y2, 0), (m * 1024 + m * 4096) * 4)
+    if not want or "cumsum" in want:
+        # [8192, 4096] f32 (128 MB): along the rows (k = 1), down the columns (k = 4096) and as one 32M-element vector
+        # (chunked: totals pass + scan pass = 2 reads + 1 write for 1 read + 1 write of algorithmic traffic)
+        timed("cumsum_rows", lambda i: math.cumsumb(m, n, 1, As[i], 0, False, False, Y2, 0), 2 * m * n * 4)
+        timed("cumsum_rows_4032", lambda i: math.cumsumb(m, 4032, 1, As[i], 0, False, False, Y2, 0), 2 * m * 4032 * 4)
+        timed("cumsum_cols", lambda i: math.cumsumb(1, m, n, As[i], 0, False, False, Y2, 0), 2 * m * n * 4)
+        timed("cumsum_flat", lambda i: math.cumsumb(1, m * n, 1, As[i], 0, False, False, Y2, 0), 2 * m * n * 4)
     if not want or "masking" in want:
         # attention-score padding mask: scores [64 batch, 16 heads x 128 queries, 256 keys] f32 (128 MB); per batch the keys
         # past a random length are masked out (set to -1e9): only those elements are written
