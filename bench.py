@@ -613,6 +613,10 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
     report("masking", lambda i: math.masking(64, 16 * 128, 256, 1, -1e9, 0, Mk, 0, As[i], 0), masked * 4,
            {"shape": "scores [64,2048,256], key padding mask [64,256], %.0f %% masked (bytes = masked elements written)"
                      % (100.0 * masked / (m * n))})
+    report("cumsum_rows", lambda i: math.cumsumb(m, n, 1, As[i], 0, False, False, Y2, 0), 2 * m * n * 4,
+           {"shape": "cumsum([8192,4096], axis=1): one pass"})
+    report("cumsum_cols", lambda i: math.cumsumb(1, m, n, As[i], 0, False, False, Y2, 0), 2 * m * n * 4,
+           {"shape": "cumsum([8192,4096], axis=0): totals pass + scan pass, 2 reads + 1 write for 1 + 1 algorithmic"})
     Yv = CudaBuffer(m, dtypes.float32)
     report("gemv", lambda i: blas1.gemv(_B.RowMajor, _B.NoTrans, m, n, 1.0, As[i], 0, n, X, 0, 1, 0.0, Yv, 0, 1),
            m * n * 4 + n * 4 + m * 4, {"shape": "[8192,4096] x [4096]"})

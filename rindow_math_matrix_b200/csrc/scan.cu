@@ -30,6 +30,8 @@ struct ScanRows {
     int revx, revy, exclusive;
 };
 
+template <typename T, int V> struct alignas(sizeof(T) * V) ScVec { T e[V]; };
+
 template <typename T> __device__ __forceinline__ T sc_shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 template <typename T> __device__ __forceinline__ T sc_shfl(T v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 
@@ -44,7 +46,9 @@ scan_rows_kernel(ScanRows p, const T* __restrict__ X, T* __restrict__ Y, T* __re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t units = p.m * p.chunks;
     T* ts = tile_s[warp];
-    for (int64_t u = (int64_t)blockIdx.x * SC_WARPS + warp; u < units; u += (int64_t)gridDim.x * SC_WARPS) {
+    for (int64_t uu = (int64_t)blockIdx.x * SC_WARPS + warp; uu < units; uu += (int64_t)gridDim.x * SC_WARPS) {
+        // pass 2 starts with the chunks pass 1 read last: they are still in L2
+        const int64_t u = (PHASE == 1 && totals != nullptr) ? units - 1 - uu : uu;
         const int64_t i = u / p.chunks, c = u - i * p.chunks;
         const int64_t s0 = c * p.chunk;
         const int64_t s1 = s0 + p.chunk < p.n ? s0 + p.chunk : p.n;
@@ -117,6 +121,99 @@ scan_rows_kernel(ScanRows p, const T* __restrict__ X, T* __restrict__ Y, T* __re
     }
 }
 
+// Forward scans of contiguous, 16-byte aligned rows (the common case) skip shared memory: a lane loads SC_NV 16-byte
+// vectors, vector j of lane l covering elements (j * 32 + l) * V ... + V of the tile -- fully coalesced -- and the
+// tile is scanned as SC_NV sub-tiles of 32 * V elements, one shuffle scan each (independent, so they pipeline).
+constexpr int SC_NV = 4;
+
+template <typename T, int PHASE>
+__global__ void __launch_bounds__(SC_THREADS)
+scan_rows_vec_kernel(ScanRows p, const T* __restrict__ X, T* __restrict__ Y, T* __restrict__ totals)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int TILE = 32 * V * SC_NV;
+    typedef ScVec<T, V> Vec;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t units = p.m * p.chunks;
+    for (int64_t uu = (int64_t)blockIdx.x * SC_WARPS + warp; uu < units; uu += (int64_t)gridDim.x * SC_WARPS) {
+        // pass 2 starts with the chunks pass 1 read last: they are still in L2
+        const int64_t u = (PHASE == 1 && totals != nullptr) ? units - 1 - uu : uu;
+        const int64_t i = u / p.chunks, c = u - i * p.chunks;
+        const int64_t s0 = c * p.chunk;
+        const int64_t s1 = s0 + p.chunk < p.n ? s0 + p.chunk : p.n;
+        const T* x = X + i * p.ldx;
+        T* y = Y + i * p.ldy;
+        Vec zero;
+#pragma unroll
+        for (int w = 0; w < V; w++) zero.e[w] = (T)0;
+        if (PHASE == 0) {
+            T part = (T)0;
+            for (int64_t t0 = s0; t0 < s1; t0 += TILE) {
+                Vec v[SC_NV];
+#pragma unroll
+                for (int j = 0; j < SC_NV; j++) {
+                    const int64_t s = t0 + (int64_t)(j * 32 + lane) * V;
+                    v[j] = s < s1 ? *reinterpret_cast<const Vec*>(x + s) : zero;
+                }
+#pragma unroll
+                for (int j = 0; j < SC_NV; j++) {
+#pragma unroll
+                    for (int w = 0; w < V; w++) part += v[j].e[w];
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0) totals[u] = part;
+            continue;
+        }
+        T carry = totals != nullptr ? totals[u] : (T)0;
+        Vec v[SC_NV];
+#pragma unroll
+        for (int j = 0; j < SC_NV; j++) {
+            const int64_t s = s0 + (int64_t)(j * 32 + lane) * V;
+            v[j] = s < s1 ? *reinterpret_cast<const Vec*>(x + s) : zero;
+        }
+        for (int64_t t0 = s0; t0 < s1; t0 += TILE) {
+            Vec a[SC_NV];
+            T inc[SC_NV];
+#pragma unroll
+            for (int j = 0; j < SC_NV; j++) {
+                a[j] = v[j];
+                T t = (T)0;
+#pragma unroll
+                for (int w = 0; w < V; w++) t += a[j].e[w];
+                inc[j] = t;
+            }
+            if (t0 + TILE < s1) {
+#pragma unroll
+                for (int j = 0; j < SC_NV; j++) {
+                    const int64_t s = t0 + TILE + (int64_t)(j * 32 + lane) * V;
+                    v[j] = s < s1 ? *reinterpret_cast<const Vec*>(x + s) : zero;
+                }
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int j = 0; j < SC_NV; j++) { const T o = sc_shfl_up(inc[j], d); if (lane >= d) inc[j] += o; }
+            }
+#pragma unroll
+            for (int j = 0; j < SC_NV; j++) {
+                const T prev = sc_shfl_up(inc[j], 1);
+                const T sub_total = sc_shfl(inc[j], 31);
+                T run = lane == 0 ? carry : carry + prev;
+                Vec o;
+#pragma unroll
+                for (int w = 0; w < V; w++) {
+                    if (p.exclusive) { o.e[w] = run; run += a[j].e[w]; } else { run += a[j].e[w]; o.e[w] = run; }
+                }
+                const int64_t s = t0 + (int64_t)(j * 32 + lane) * V;
+                if (s < s1) *reinterpret_cast<Vec*>(y + s) = o;
+                carry += sub_total;
+            }
+        }
+    }
+}
+
 // exclusive scan of the chunk totals of each row, in place: one block per row, SC_THREADS * 4 totals per step
 template <typename T>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -164,7 +261,6 @@ struct ScanCols {
     int reverse, exclusive;
 };
 
-template <typename T, int V> struct alignas(sizeof(T) * V) ScVec { T e[V]; };
 
 // one thread per V adjacent (i, h) columns and chunk (V > 1: k % V == 0 and 16-byte aligned buffers); adjacent threads
 // read adjacent columns, SC_UNROLL steps of the scan are in flight.
@@ -177,7 +273,8 @@ scan_cols_kernel(ScanCols p, const T* __restrict__ A, T* __restrict__ B, T* __re
     typedef ScVec<T, V> Vec;
     const int64_t vcols = p.cols / V;
     const int64_t col_blocks = (vcols + SC_THREADS - 1) / SC_THREADS;
-    for (int64_t blk = blockIdx.x; blk < col_blocks * p.chunks; blk += gridDim.x) {
+    for (int64_t bb = blockIdx.x; bb < col_blocks * p.chunks; bb += gridDim.x) {
+        const int64_t blk = (PHASE == 1 && totals != nullptr) ? col_blocks * p.chunks - 1 - bb : bb;
         const int64_t c = blk / col_blocks;
         const int64_t g = ((blk - c * col_blocks) * SC_THREADS + threadIdx.x) * V;
         if (g >= p.cols) continue;
@@ -239,7 +336,11 @@ int scan_rows_launch(ScanRows p, const T* X, T* Y)
         if (chunks > maxc) chunks = maxc;
         if (chunks < 1) chunks = 1;
     }
-    p.chunk = rb_ceil_div(rb_ceil_div(p.n, chunks), SC_TILE) * SC_TILE;
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool vec = p.incx == 1 && p.incy == 1 && !p.revx && !p.revy && (p.n % V) == 0 && (p.ldx % V) == 0 && (p.ldy % V) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0;
+    const int64_t tile = vec ? 32 * V * SC_NV : SC_TILE;
+    p.chunk = rb_ceil_div(rb_ceil_div(p.n, chunks), tile) * tile;
     p.chunks = rb_ceil_div(p.n, p.chunk);
     int64_t grid = rb_ceil_div(p.m * p.chunks, SC_WARPS);
     const int64_t cap = (int64_t)c.sm_count * 8;
@@ -249,12 +350,14 @@ int scan_rows_launch(ScanRows p, const T* X, T* Y)
         int rc = rb200::ensure_workspace((size_t)(p.m * p.chunks) * sizeof(T));
         if (rc != RB200_OK) return rc;
         totals = reinterpret_cast<T*>(c.workspace);
-        scan_rows_kernel<T, 0><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
+        if (vec) scan_rows_vec_kernel<T, 0><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
+        else     scan_rows_kernel<T, 0><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
         RB_LAUNCH_CHECK("scan_rows_kernel<totals>");
         scan_totals_kernel<T><<<(unsigned)p.m, SC_THREADS, 0, c.stream>>>(p.chunks, totals);
         RB_LAUNCH_CHECK("scan_totals_kernel");
     }
-    scan_rows_kernel<T, 1><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
+    if (vec) scan_rows_vec_kernel<T, 1><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
+    else     scan_rows_kernel<T, 1><<<(unsigned)grid, SC_THREADS, 0, c.stream>>>(p, X, Y, totals);
     RB_LAUNCH_CHECK("scan_rows_kernel");
     return RB200_OK;
 }

@@ -29,6 +29,7 @@ def _cumsumb_both(service, m, n, k, a, dt, exclusive, reverse, off=0):
 
 
 SHAPES = [(1, 1, 1), (1, 5, 1), (3, 7, 1), (1, 255, 1), (1, 256, 1), (1, 257, 1), (2, 1000, 1), (1, 100000, 1), (700, 33, 1),
+          (1, 4, 1), (5, 512, 1), (3, 516, 1), (2, 1028, 1), (9000, 64, 1), (1, 300000, 1),
           (1, 3, 2), (4, 9, 5), (1, 300, 3), (2, 64, 33), (1, 4097, 64), (3, 17, 300), (1, 1, 9), (5000, 4, 2), (1, 20000, 2)]
 
 
@@ -39,12 +40,13 @@ def test_cumsumb_exact_data_vs_oracle(m, n, k, exclusive, reverse, cuda_service)
     rng = np.random.default_rng(m * 7 + n * 3 + k)
     for dt in (F32, F64, I32, I64):
         npdt = dtypes.NUMPY[dt]
-        if dt in (F32, F64):
-            a = (np.round(rng.uniform(-4, 4, 2 + m * n * k) * 8) / 8).astype(npdt)
-        else:
-            a = rng.integers(-1000, 1000, 2 + m * n * k).astype(npdt)
-        got, want = _cumsumb_both(cuda_service, m, n, k, a, dt, exclusive, reverse, off=2)
-        assert np.array_equal(got.astype(np.float64), want), (dt, np.flatnonzero(got.astype(np.float64) != want)[:5])
+        for off in (2, 4):                                  # 4: 16-byte aligned rows take the vector kernels
+            if dt in (F32, F64):
+                a = (np.round(rng.uniform(-4, 4, off + m * n * k) * 8) / 8).astype(npdt)
+            else:
+                a = rng.integers(-1000, 1000, off + m * n * k).astype(npdt)
+            got, want = _cumsumb_both(cuda_service, m, n, k, a, dt, exclusive, reverse, off=off)
+            assert np.array_equal(got.astype(np.float64), want), (dt, off, np.flatnonzero(got.astype(np.float64) != want)[:5])
 
 
 @pytest.mark.parametrize("m,n,k", [(1, 100000, 1), (3, 5000, 1), (1, 30000, 4), (64, 777, 40), (2000, 50, 1)])
