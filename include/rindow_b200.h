@@ -345,6 +345,14 @@ int rb200_masking(int dtype, int64_t m, int64_t n, int64_t k, int64_t len, doubl
  *      (upper >= 0 && j-i > upper); negative bounds keep the whole triangle.  Any dtype (bool included). */
 int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t offA, int64_t lower, int64_t upper);
 
+/* ---- gatherb: PhpMath::gatherb (PhpMath.php:1209-1260) behind LinearAlgebra::gatherb / scatterb / scatterbAdd
+ *      (LinearAlgebra.php:2690-2920).  A[batches,m,numClass,k,len], X[batches,n,k] integer, B[batches,m,n,k,len].
+ *      forward: B[b,i,j,h,:] (=|+=) A[b,i,X[b,j,h],h,:]; reverse: A[b,i,X[b,j,h],h,:] (=|+=) B[b,i,j,h,:] in ascending
+ *      j (last j wins a copy; sums are added in j order -- deterministic, the reference's association).  Indices
+ *      outside [0, numClass) skip the element.  Copies: any dtype; add modes: float32 / float64 / int32 / int64. */
+int rb200_gatherb(int dtype, int index_dtype, int reverse, int add_mode, int64_t batches, int64_t m, int64_t n, int64_t k,
+                  int64_t len, int64_t numClass, void* A, int64_t offA, const void* X, int64_t offX, void* B, int64_t offB);
+
 /* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
  *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
  *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order

@@ -447,6 +447,33 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
+/* PhpMath::gatherb, PhpMath.php:1209-1260.  f32: math_add stores every partial sum into a float32 buffer. */
+int ro_gatherb(int reverse, int add_mode, int f32, int64_t batches, int64_t m, int64_t n, int64_t k, int64_t len, int64_t numClass,
+               double *A, int64_t countA, int64_t offA, const double *X, int64_t countX, int64_t offX,
+               double *B, int64_t countB, int64_t offB)
+{
+    if (offX + batches * n * k > countX || offA + batches * m * numClass * k * len > countA ||
+        offB + batches * m * n * k * len > countB) return RO_E_ARG;
+    for (int64_t batch = 0; batch < batches; batch++) {
+        for (int64_t i = 0; i < m; i++) {
+            for (int64_t j = 0; j < n; j++) {
+                for (int64_t h = 0; h < k; h++) {
+                    const int64_t index = (int64_t)X[offX + (batch * n + j) * k + h];
+                    if (index >= numClass || index < 0) continue;
+                    double *a = A + offA + (((batch * m + i) * numClass + index) * k + h) * len;
+                    double *b = B + offB + (((batch * m + i) * n + j) * k + h) * len;
+                    double *from = reverse ? b : a, *to = reverse ? a : b;
+                    for (int64_t t = 0; t < len; t++) {
+                        if (!add_mode) to[t] = from[t];
+                        else { const double v = to[t] + from[t]; to[t] = f32 ? (double)(float)v : v; }
+                    }
+                }
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
  * buffer rounds at every step (f32 != 0). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,

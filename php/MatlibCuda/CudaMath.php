@@ -119,6 +119,54 @@ class CudaMath extends PhpMath
             $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$channels_first?1:0,
             $dilation_h,$dilation_w,$cols_channels_first?1:0,$co,$cols_offset,$cols_size));
     }
+    /** gatherb (PhpMath.php:1209-1260): batched gather / scatter / scatterAdd */
+    public function gatherb(bool $reverse,bool $addMode,int $batches,int $m,int $n,int $k,int $len,int $numClass,
+        Buffer $A,int $offsetA,Buffer $X,int $offsetX,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($A,$X,$B)) {
+            parent::gatherb($reverse,$addMode,$batches,$m,$n,$k,$len,$numClass,$A,$offsetA,$X,$offsetX,$B,$offsetB); return;
+        }
+        if ($offsetX+$batches*$n*$k > count($X)) {
+            throw new InvalidArgumentException('Matrix X specification too large for buffer.');
+        }
+        if ($offsetA+$batches*$m*$numClass*$k*$len > count($A)) {
+            throw new InvalidArgumentException('Matrix A specification too large for buffer.');
+        }
+        if ($offsetB+$batches*$m*$n*$k*$len > count($B)) {
+            throw new InvalidArgumentException('Matrix B specification too large for buffer.');
+        }
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and B');
+        }
+        $a = $reverse ? $A->devicePtrRW() : $A->devicePtr();
+        $b = $reverse ? $B->devicePtr() : $B->devicePtrRW();
+        CudaFFI::check(CudaFFI::lib()->rb200_gatherb($A->abiDtype(),$X->abiDtype(),$reverse?1:0,$addMode?1:0,$batches,$m,$n,$k,
+            $len,$numClass,$a,$offsetA,$X->devicePtr(),$offsetX,$b,$offsetB));
+    }
+
+    /** matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose -- the omatcopy kernel */
+    public function matrixcopy(bool $trans,int $m,int $n,float $alpha,Buffer $A,int $offsetA,int $ldA,Buffer $B,int $offsetB,int $ldB) : void
+    {
+        if (!$this->anyOnDevice($A,$B) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
+            parent::matrixcopy($trans,$m,$n,$alpha,$A,$offsetA,$ldA,$B,$offsetB,$ldB); return;
+        }
+        $rows = $trans ? $n : $m; $cols = $trans ? $m : $n;
+        if ($m<1||$n<1) {
+            throw new InvalidArgumentException('Argument m / n must be greater than 0.');
+        }
+        if ($ldA<$n || $offsetA+($m-1)*$ldA+$n > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferA.');
+        }
+        if ($ldB<$cols || $offsetB+($rows-1)*$ldB+$cols > count($B)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferB.');
+        }
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and B');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->abiDtype(),101,$trans?112:111,$m,$n,$alpha,
+            $A->devicePtr(),$offsetA,$ldA,$B->devicePtrRW(),$offsetB,$ldB));
+    }
+
     /** cumsumb (PhpMath.php:1861-1904): running sum along the middle axis of [m,n,k] */
     public function cumsumb(int $m,int $n,int $k,Buffer $A,int $offsetA,bool $exclusive,bool $reverse,Buffer $B,int $offsetB) : void
     {

@@ -92,6 +92,7 @@ SIGNATURES = {
     "rb200_im2col2d": (i32, [i32, i32, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                              i32, i32, i64, i64, i32, vp, i64, i64]),
     "rb200_bandpart": (i32, [i32, i64, i64, i64, vp, i64, i64, i64]),
+    "rb200_gatherb": (i32, [i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64]),
     "rb200_cumsumb": (i32, [i32, i64, i64, i64, vp, i64, i32, i32, vp, i64]),
     "rb200_cumsum": (i32, [i32, i64, vp, i64, i64, i32, i32, vp, i64, i64]),
     "rb200_searchsorted": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64, i32, vp, i64, i64]),

@@ -256,6 +256,26 @@ class CudaMath:
         _capi.check(self._lib.rb200_gather(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, n, k, numClass,
                                            X.device_ptr(), offsetX, a_ptr, offsetA, b_ptr, offsetB))
 
+    # ---- gatherb (PhpMath.php:1209-1260): batched gather / scatter / scatterAdd ---------------------------------------
+    def gatherb(self, reverse, addMode, batches, m, n, k, len_, numClass, A, offsetA, X, offsetX, B, offsetB) -> None:
+        if min(batches, m, n, k, len_, numClass) < 1:
+            raise InvalidArgumentException("Argument shape must be greater than 0.")
+        if offsetX + batches * n * k > len(X):
+            raise InvalidArgumentException("Matrix X specification too large for buffer.")
+        if offsetA + batches * m * numClass * k * len_ > len(A):
+            raise InvalidArgumentException("Matrix A specification too large for buffer.")
+        if offsetB + batches * m * n * k * len_ > len(B):
+            raise InvalidArgumentException("Matrix B specification too large for buffer.")
+        _cuda("X", X), _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        if X.dtype() not in dtypes.INT_TYPES:
+            raise InvalidArgumentException("dtype of X must be integer.")
+        a_ptr = A.device_ptr_rw() if reverse else A.device_ptr()
+        b_ptr = B.device_ptr() if reverse else B.device_ptr_rw()
+        _capi.check(self._lib.rb200_gatherb(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, batches, m, n, k,
+                                            len_, numClass, a_ptr, offsetA, X.device_ptr(), offsetX, b_ptr, offsetB))
+
     def reduceGather(self, reverse, addMode, m, n, numClass, X, offsetX, A, offsetA, B, offsetB) -> None:
         if offsetX + m * n > len(X):          # the reference tests offsetX+n (:1164); the whole [m,n] index must fit
             raise InvalidArgumentException("Matrix X specification too large for buffer.")
@@ -395,6 +415,24 @@ class CudaMath:
                                              stride_h, stride_w, 1 if padding else 0, 1 if channels_first else 0,
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
+
+    # ---- matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose; the kernel of BLAS omatcopy -----------
+    def matrixcopy(self, trans, m, n, alpha, A, offsetA, ldA, B, offsetB, ldB) -> None:
+        if m < 1 or n < 1:
+            raise InvalidArgumentException("Argument m / n must be greater than 0.")
+        rows, cols = (n, m) if trans else (m, n)
+        if ldA < n or offsetA + (m - 1) * ldA + n > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA.")
+        if ldB < cols or offsetB + (rows - 1) * ldB + cols > len(B):
+            raise InvalidArgumentException("Matrix specification too large for bufferB.")
+        _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        if A.dtype() not in (dtypes.float32, dtypes.float64):
+            raise InvalidArgumentException("Unsupported data type.")
+        # RowMajor = 101, NoTrans = 111, Trans = 112 (the CBLAS codes rb200_omatcopy takes)
+        _capi.check(self._lib.rb200_omatcopy(A.dtype(), 101, 112 if trans else 111, m, n, float(alpha),
+                                             A.device_ptr(), offsetA, ldA, B.device_ptr_rw(), offsetB, ldB))
 
     # ---- cumsum / cumsumb / searchsorted (PhpMath.php:1780-1904) ------------------------------------------------------
     def cumsumb(self, m, n, k, A, offsetA, exclusive, reverse, B, offsetB) -> None:

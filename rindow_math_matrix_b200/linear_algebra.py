@@ -730,6 +730,79 @@ class LinearAlgebra:
         return output
 
     # ---- im2col / col2im (LinearAlgebra.php:3369-3494, 3597-3701) -------------------------------------------
+    # ---- gatherb / scatterb / scatterbAdd (LinearAlgebra.php:2690-2920) ------------------------------------------
+    def _do_gatherb(self, reverse, addMode, A: NDArray, X: NDArray, axis=None, batchDims=None, detailDepth=None,
+                    indexDepth=None, B=None) -> NDArray:
+        """LinearAlgebra::doGatherb: params (batches, m, numClass, k, len), indices (batches, n, k),
+        outputs (batches, m, n, k, len)"""
+        batchDims = 0 if batchDims is None else batchDims
+        if batchDims < 0:
+            batchDims += A.ndim()
+        if batchDims >= A.ndim():
+            raise InvalidArgumentException(f"batchDims ({batchDims}) must be less than to ndims of params ({A.ndim()})")
+        axis = batchDims if axis is None else axis
+        if axis < 0:
+            axis += A.ndim()
+        if axis >= A.ndim():
+            raise InvalidArgumentException(f"axis ({axis}) must be less than to ndims of params ({A.ndim()})")
+        detailDepth = axis + 1 if detailDepth is None else detailDepth
+        indexDepth = X.ndim() if indexDepth is None else indexDepth
+        if batchDims > axis:
+            if axis == 0:
+                batchDims = 0
+            else:
+                raise InvalidArgumentException(f"batchDims ({batchDims}) must be less than or equal to axis ({axis})")
+        shapeA = A.shape()
+        batchShape, outerShape = shapeA[:batchDims], shapeA[batchDims:]
+        outerShape, innerShape = outerShape[:axis - batchDims], outerShape[axis - batchDims:]
+        numClass = innerShape.pop(0)
+        cut = detailDepth - 1 - axis                           # array_splice: a negative offset counts from the end
+        if cut < 0:
+            cut = max(len(innerShape) + cut, 0)
+        innerShape, detailShape = innerShape[:cut], innerShape[cut:]
+        shapeX = X.shape()
+        batchShapeX, indexShape = shapeX[:batchDims], shapeX[batchDims:]
+        cutx = indexDepth - batchDims
+        if cutx < 0:
+            cutx = max(len(indexShape) + cutx, 0)
+        indexShape, innerShapeX = indexShape[:cutx], indexShape[cutx:]
+        if batchShape != batchShapeX:
+            raise InvalidArgumentException(
+                f"Unmatch batch shape of params and indices: {batchShape},{batchShapeX},")
+        if innerShape != innerShapeX:
+            raise InvalidArgumentException(
+                f"Unmatch inner shape of params and indices: param's inner shape is {innerShape},"
+                f"index's inner shape is {innerShapeX},")
+        prod = lambda s: int(np.prod(s, dtype=np.int64)) if s else 1
+        batches, m, n, k, len_ = prod(batchShape), prod(outerShape), prod(indexShape), prod(innerShape), prod(detailShape)
+        outputShape = batchShape + outerShape + indexShape + innerShape + detailShape
+        if B is None:
+            B = self.zeros(self.alloc(outputShape, A.dtype()))
+        elif B.shape() != outputShape:
+            what = "updates" if reverse else "output"
+            raise InvalidArgumentException(f"Unmatch {what} shape: expects {outputShape}, but gives {B.shape()}")
+        self.math.gatherb(reverse, addMode, batches, m, n, k, len_, numClass, A.buffer(), A.offset(), X.buffer(), X.offset(),
+                          B.buffer(), B.offset())
+        return B
+
+    def gatherb(self, params: NDArray, indices: NDArray, axis=None, batchDims=None, detailDepth=None, indexDepth=None,
+                outputs=None) -> NDArray:
+        return self._do_gatherb(False, False, params, indices, axis, batchDims, detailDepth, indexDepth, outputs)
+
+    def scatterb(self, indices: NDArray, updates: NDArray, shape, axis=None, batchDims=None, detailDepth=None,
+                 indexDepth=None, outputs=None) -> NDArray:
+        if outputs is None:
+            outputs = self.zeros(self.alloc(list(shape), updates.dtype()))
+        self._do_gatherb(True, False, outputs, indices, axis, batchDims, detailDepth, indexDepth, updates)
+        return outputs
+
+    def scatterbAdd(self, indices: NDArray, updates: NDArray, shape, axis=None, batchDims=None, detailDepth=None,
+                    indexDepth=None, outputs=None) -> NDArray:
+        if outputs is None:
+            outputs = self.zeros(self.alloc(list(shape), updates.dtype()))
+        self._do_gatherb(True, True, outputs, indices, axis, batchDims, detailDepth, indexDepth, updates)
+        return outputs
+
     def cumsum(self, inputs: NDArray, axis=None, exclusive=None, reverse=None, outputs=None) -> NDArray:
         """LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812): running sum along one axis through cumsumb."""
         ndim = inputs.ndim()

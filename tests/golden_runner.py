@@ -262,6 +262,28 @@ def run_im2col_case(params, service):
     assert np.array_equal(np.asarray(images.toArray(), dtype=np.float64), arange.reshape(shape))
 
 
+def run_gatherb_case(case, service):
+    """tests/golden/gatherb_cases.json (LinearAlgebraTest.php testGatherbNormal / testScatterbNormal /
+    testScatterbAddNormal): params float32 (range over shapeA or a literal), indices int32; operands untouched"""
+    la = LinearAlgebra(service)
+    p = case["params"]
+    if "arange" in p:
+        a = np.arange(int(np.prod(p["arange"])), dtype=np.float32).reshape(p["arange"])
+    else:
+        a = np.array(p["a"], dtype=np.float32)
+    x = np.array(case["indices"], dtype=np.int32)
+    A, X = la.array(a), la.array(x, dtype=_DTYPES["int32"])
+    kw = case["kwargs"]
+    if case["op"] == "gatherb":
+        out = la.gatherb(A, X, **kw)
+    else:
+        out = getattr(la, case["op"])(X, A, case["shape"], **kw)
+    want = np.array(case["expect"], dtype=np.float32)
+    assert out.shape() == list(want.shape), (out.shape(), want.shape)
+    assert np.array_equal(out.to_numpy().reshape(want.shape), want)
+    assert np.array_equal(A.to_numpy().reshape(a.shape), a) and np.array_equal(X.to_numpy().reshape(x.shape), x)
+
+
 def run_im2col_nd_case(params, service):
     """testIm2col1dNormal / testIm2col3dNormal (LinearAlgebraTest.php:9613-9778, :10653-10882) for one provider row:
     arange-valued images, cols must hold the source index of every in-bounds tap (0 elsewhere), col2im must add every

@@ -291,6 +291,13 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def gatherb(self, reverse, addMode, batches, m, n, k, len_, numClass, A, offA, X, offX, B, offB):
+        a, b = self._f(A), self._f(B)
+        _wrap(oracle.gatherb, reverse, addMode, A.dtype() == dtypes.float32, batches, m, n, k, len_, numClass, a, offA,
+              self._f(X), offX, b, offB)
+        self._back(A, a)
+        self._back(B, b)
+
     def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
         b = self._f(B)
         _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)

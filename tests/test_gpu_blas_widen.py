@@ -342,3 +342,26 @@ def test_level1_argument_errors(cuda_service):
         blas.nrm2(5, X, 0, 1)
     with pytest.raises(InvalidArgumentException, match="Vector specification too large for bufferY."):
         blas.dot(3, X, 0, 1, X, 2, 1)
+
+
+@pytest.mark.parametrize("trans", [False, True])
+@pytest.mark.parametrize("m,n,pad", [(1, 1, 0), (5, 7, 0), (33, 65, 3), (300, 257, 1)])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_matrixcopy_vs_oracle(trans, m, n, pad, dt, cuda_service):
+    """PhpMath::matrixcopy (PhpMath.php:2778-2809) rides rb200_omatcopy: one multiply per element, bit-exact"""
+    import oracle
+    npdt = dtypes.NUMPY[dt]
+    rng = np.random.default_rng(m * 31 + n)
+    ldA = n + pad
+    rows, cols = (n, m) if trans else (m, n)
+    ldB = cols + pad
+    offA, offB = 2, 1
+    a = rng.standard_normal(offA + m * ldA).astype(npdt)
+    b = np.full(offB + rows * ldB, 9).astype(npdt)
+    A, B = CudaBuffer(a.size, dt).from_numpy(a), CudaBuffer(b.size, dt).from_numpy(b)
+    cuda_service.math().matrixcopy(trans, m, n, -1.5, A, offA, ldA, B, offB, ldB)
+    bo = b.astype(np.float64)
+    oracle.omatcopy(101, 112 if trans else 111, m, n, -1.5, a.astype(np.float64), offA, ldA, bo, offB, ldB)
+    assert np.array_equal(B.to_numpy().astype(np.float64), bo.astype(npdt).astype(np.float64))
+    with pytest.raises(InvalidArgumentException, match="bufferB"):
+        cuda_service.math().matrixcopy(trans, m, n, 1.0, A, offA, ldA, B, offB + pad + 1, ldB)

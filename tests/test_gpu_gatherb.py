@@ -1,0 +1,89 @@
+"""Parity of gatherb / scatterb / scatterbAdd (rb200_gatherb) through the C ABI: the reference's own 26 test cases
+(tests/golden/gatherb_cases.json) and seeded random shapes against the CPU oracle.  Bit-exact everywhere: copies move
+words, and the adds run in the reference's order (ascending j) with one rounding per step.  pytest -m gpu"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_runner as gr
+import oracle
+from rindow_math_matrix_b200 import CudaBuffer, InvalidArgumentException, LinearAlgebra, dtypes
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(gr.HERE, "golden", "gatherb_cases.json")) as f:
+    GATHERB = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", GATHERB, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERB])
+def test_gatherb_reference_cases(case, cuda_service):
+    gr.run_gatherb_case(case, cuda_service)
+
+
+SHAPES = [(1, 1, 1, 1, 1, 1), (2, 3, 4, 1, 1, 5), (3, 2, 7, 4, 1, 6), (2, 1, 9, 3, 5, 4), (1, 4, 300, 2, 3, 17),
+          (4, 2, 33, 8, 16, 40), (1, 1, 2000, 1, 1, 50), (2, 2, 5, 64, 4, 3)]
+
+
+@pytest.mark.parametrize("batches,m,n,k,len_,numClass", SHAPES)
+@pytest.mark.parametrize("reverse,addMode", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("dt,idt", [(dtypes.float32, dtypes.int32), (dtypes.float64, dtypes.int64), (dtypes.int32, dtypes.int32)])
+def test_gatherb_random_vs_oracle(batches, m, n, k, len_, numClass, reverse, addMode, dt, idt, cuda_service):
+    npdt, npi = dtypes.NUMPY[dt], dtypes.NUMPY[idt]
+    rng = np.random.default_rng(n * 7 + k + numClass)
+    offA, offX, offB = 3, 1, 2
+    if dt == dtypes.int32:
+        a = rng.integers(-50, 50, offA + batches * m * numClass * k * len_).astype(npdt)
+        b = rng.integers(-50, 50, offB + batches * m * n * k * len_).astype(npdt)
+    else:
+        a = rng.standard_normal(offA + batches * m * numClass * k * len_).astype(npdt)     # inexact sums: order matters
+        b = rng.standard_normal(offB + batches * m * n * k * len_).astype(npdt)
+    x = rng.integers(0, numClass, offX + batches * n * k).astype(npi)                      # collisions whenever n > numClass
+    if x.size > 8:
+        x[offX + 3] = numClass + 2                                                          # out of range: skipped
+    A, B = CudaBuffer(a.size, dt).from_numpy(a), CudaBuffer(b.size, dt).from_numpy(b)
+    X = CudaBuffer(x.size, idt).from_numpy(x)
+    cuda_service.math().gatherb(reverse, addMode, batches, m, n, k, len_, numClass, A, offA, X, offX, B, offB)
+    ao, bo = a.astype(np.float64), b.astype(np.float64)
+    oracle.gatherb(reverse, addMode, dt == dtypes.float32, batches, m, n, k, len_, numClass, ao, offA, x.astype(np.float64), offX,
+                   bo, offB)
+    assert np.array_equal(A.to_numpy().astype(np.float64), ao)
+    assert np.array_equal(B.to_numpy().astype(np.float64), bo)
+    assert np.array_equal(X.to_numpy(), x)
+
+
+@pytest.mark.parametrize("dt", [dtypes.bool_, dtypes.uint8, dtypes.int16, dtypes.uint64])
+def test_gatherb_copy_any_dtype(dt, cuda_service):
+    npdt = dtypes.NUMPY[dt]
+    rng = np.random.default_rng(4)
+    batches, m, n, k, len_, numClass = 2, 3, 6, 2, 3, 4
+    a = rng.integers(0, 2 if dt == dtypes.bool_ else 100, batches * m * numClass * k * len_).astype(npdt)
+    x = rng.integers(0, numClass, batches * n * k).astype(np.int32)
+    A, X = CudaBuffer(a.size, dt).from_numpy(a), CudaBuffer(x.size, dtypes.int32).from_numpy(x)
+    B = CudaBuffer(batches * m * n * k * len_, dt)
+    cuda_service.math().gatherb(False, False, batches, m, n, k, len_, numClass, A, 0, X, 0, B, 0)
+    want = np.zeros(batches * m * n * k * len_)
+    oracle.gatherb(False, False, False, batches, m, n, k, len_, numClass, a.astype(np.float64), 0, x.astype(np.float64), 0, want, 0)
+    assert np.array_equal(B.to_numpy().astype(np.float64), want)
+    with pytest.raises(Exception, match="add mode"):
+        cuda_service.math().gatherb(False, True, batches, m, n, k, len_, numClass, A, 0, X, 0, B, 0)
+
+
+def test_gatherb_errors(cuda_service):
+    la = LinearAlgebra(cuda_service)
+    A = la.array(np.arange(24, dtype=np.float32).reshape(4, 3, 2))
+    X = la.array(np.array([2, 2, 1, 0], np.int32), dtype=dtypes.int32)
+    with pytest.raises(InvalidArgumentException, match="batchDims"):
+        la.gatherb(A, X, batchDims=3)
+    with pytest.raises(InvalidArgumentException, match="axis"):
+        la.gatherb(A, X, axis=3)
+    with pytest.raises(InvalidArgumentException, match="Unmatch batch shape"):
+        la.gatherb(A, la.array(np.array([2, 2, 1], np.int32), dtype=dtypes.int32), axis=1, batchDims=1)
+    with pytest.raises(InvalidArgumentException, match="Unmatch output shape"):
+        la.gatherb(A, X, axis=1, batchDims=1, outputs=la.alloc([4, 3], dtypes.float32))
+    m = cuda_service.math()
+    with pytest.raises(InvalidArgumentException, match="Matrix A"):
+        m.gatherb(False, False, 1, 1, 2, 1, 1, 30, A.buffer(), 0, X.buffer(), 0, CudaBuffer(2, dtypes.float32), 0)
+    with pytest.raises(InvalidArgumentException, match="integer"):
+        m.gatherb(False, False, 1, 1, 2, 1, 1, 3, A.buffer(), 0, CudaBuffer(2, dtypes.float32), 0, CudaBuffer(2, dtypes.float32), 0)

@@ -17,6 +17,14 @@ with open(os.path.join(gr.HERE, "golden", "im2col1d_cases.json")) as f:
     IM2COL1D = json.load(f)["cases"]
 with open(os.path.join(gr.HERE, "golden", "im2col3d_cases.json")) as f:
     IM2COL3D = json.load(f)["cases"]
+with open(os.path.join(gr.HERE, "golden", "gatherb_cases.json")) as f:
+    GATHERB = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", GATHERB, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERB])
+def test_gatherb_reference_cases(case, oracle_service):
+    assert len(GATHERB) == 26
+    gr.run_gatherb_case(case, oracle_service)
 
 
 @pytest.mark.parametrize("case", KA["cases"], ids=[c["id"] for c in KA["cases"]])
