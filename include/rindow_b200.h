@@ -353,6 +353,14 @@ int rb200_bandpart(int dtype, int64_t m, int64_t n, int64_t k, void* A, int64_t 
 int rb200_gatherb(int dtype, int index_dtype, int reverse, int add_mode, int64_t batches, int64_t m, int64_t n, int64_t k,
                   int64_t len, int64_t numClass, void* A, int64_t offA, const void* X, int64_t offX, void* B, int64_t offB);
 
+/* ---- gathernd: PhpMath::gathernd (PhpMath.php:1271-1325) behind LinearAlgebra::gatherND / scatterND / scatterNDAdd
+ *      (LinearAlgebra.php:2925-3090).  A[m, paramShape..., k], X[m,n,index_depth] integer, B[m,n,k]; param_shape is a
+ *      HOST array of index_depth entries (<= 8).  forward: B[i,j,:] (=|+=) A[i, X[i,j,:], :]; reverse the other way in
+ *      ascending j (deterministic, the reference's order).  A tuple with an index outside its dimension skips the row.
+ *      X is read from the pointer given: the reference ignores X's offset (PhpMath.php:1292) and so does the caller. */
+int rb200_gathernd(int dtype, int index_dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int index_depth,
+                   const int64_t* param_shape, void* A, int64_t offA, const void* X, void* B, int64_t offB);
+
 /* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
  *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
  *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order

@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
                                   i32, i32, i64, i64, i32, p, i64, i64, i64]
         L.ro_bandpart.argtypes = [i64, i64, i64, p, i64, i64, i64, i64]
         L.ro_gatherb.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, i64, i64, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
+        L.ro_gathernd.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, i64, i64, i64, p, p, i64, i64, p, i64, p, i64, i64]
         L.ro_cumsumb.argtypes = [i64, i64, i64, p, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, p, i64, i64]
         L.ro_cumsum.argtypes = [i64, p, i64, i64, i64, ctypes.c_int, ctypes.c_int, p, i64, i64, i64]
         L.ro_searchsorted.argtypes = [i64, i64, p, i64, i64, i64, p, i64, i64, i64, ctypes.c_int, p, i64, i64, i64]
@@ -99,7 +100,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_gatherb", "ro_cumsumb", "ro_cumsum", "ro_searchsorted", "ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_gathernd", "ro_gatherb", "ro_cumsumb", "ro_cumsum", "ro_searchsorted", "ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -348,6 +349,14 @@ def im2col2d(reverse, images, images_offset, images_size, batches, im_h, im_w, c
 def gatherb(reverse, addMode, f32, batches, m, n, k, len_, numClass, A, offA, X, offX, B, offB):
     _check(lib().ro_gatherb(int(bool(reverse)), int(bool(addMode)), int(bool(f32)), batches, m, n, k, len_, numClass,
                             _ptr(_buf(A)), A.size, offA, _ptr(_buf(X)), X.size, offX, _ptr(_buf(B)), B.size, offB))
+
+
+# PhpMath::gathernd :1271-1325 (paramShape: host sequence; X read from element 0 as the reference does)
+def gathernd(reverse, addMode, f32, m, n, k, depth, paramShape, A, offA, X, B, offB):
+    shape = (ctypes.c_int64 * depth)(*[int(v) for v in paramShape[:depth]])
+    _check(lib().ro_gathernd(int(bool(reverse)), int(bool(addMode)), int(bool(f32)), m, n, k, depth,
+                             ctypes.cast(shape, ctypes.c_void_p), _ptr(_buf(A)), A.size, offA, _ptr(_buf(X)), X.size,
+                             _ptr(_buf(B)), B.size, offB))
 
 
 # PhpMath::cumsumb :1861-1904, cumsum :1822-1859, searchsorted :1780-1820

@@ -474,6 +474,37 @@ int ro_gatherb(int reverse, int add_mode, int f32, int64_t batches, int64_t m, i
     return RO_OK;
 }
 
+/* PhpMath::gathernd, PhpMath.php:1271-1325.  X is read from element 0: the reference does not apply offsetX (:1292). */
+int ro_gathernd(int reverse, int add_mode, int f32, int64_t m, int64_t n, int64_t k, int64_t depth, const int64_t *paramShape,
+                double *A, int64_t countA, int64_t offA, const double *X, int64_t countX,
+                double *B, int64_t countB, int64_t offB)
+{
+    int64_t paramSize = 1;
+    for (int64_t h = 0; h < depth; h++) paramSize *= paramShape[h];
+    if (m * n * depth > countX || offA + m * paramSize * k > countA || offB + m * n * k > countB) return RO_E_ARG;
+    for (int64_t i = 0; i < m; i++) {
+        for (int64_t j = 0; j < n; j++) {
+            int64_t offset = 0;
+            int error = 0;
+            for (int64_t h = 0; h < depth; h++) {
+                offset *= paramShape[h];
+                const int64_t index = (int64_t)X[i * n * depth + j * depth + h];
+                if (index >= paramShape[h] || index < 0) { error = 1; break; }
+                offset += index;
+            }
+            if (error) continue;
+            double *a = A + offA + i * paramSize * k + offset * k;
+            double *b = B + offB + i * n * k + j * k;
+            double *from = reverse ? b : a, *to = reverse ? a : b;
+            for (int64_t t = 0; t < k; t++) {
+                if (!add_mode) to[t] = from[t];
+                else { const double v = to[t] + from[t]; to[t] = f32 ? (double)(float)v : v; }
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
  * buffer rounds at every step (f32 != 0). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,

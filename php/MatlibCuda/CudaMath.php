@@ -144,6 +144,34 @@ class CudaMath extends PhpMath
             $len,$numClass,$a,$offsetA,$X->devicePtr(),$offsetX,$b,$offsetB));
     }
 
+    /** gathernd (PhpMath.php:1271-1325): gatherND / scatterND / scatterNDAdd; paramShape is read on the host */
+    public function gathernd(bool $reverse,bool $addMode,int $m,int $n,int $k,int $indexDepth,Buffer $paramShape,
+        Buffer $A,int $offsetA,Buffer $X,int $offsetX,Buffer $B,int $offsetB) : void
+    {
+        if (!$this->anyOnDevice($A,$X,$B)) {
+            parent::gathernd($reverse,$addMode,$m,$n,$k,$indexDepth,$paramShape,$A,$offsetA,$X,$offsetX,$B,$offsetB); return;
+        }
+        $shape = \FFI::new("int64_t[$indexDepth]");
+        $paramSize = 1;
+        for ($h=0;$h<$indexDepth;$h++) { $shape[$h] = $paramShape[$h]; $paramSize *= $paramShape[$h]; }
+        if ($m*$n*$indexDepth > count($X)) {
+            throw new InvalidArgumentException('Matrix X specification too large for buffer.');
+        }
+        if ($offsetA+$m*$paramSize*$k > count($A)) {
+            throw new InvalidArgumentException('Matrix A specification too large for buffer.');
+        }
+        if ($offsetB+$m*$n*$k > count($B)) {
+            throw new InvalidArgumentException('Matrix B specification too large for buffer.');
+        }
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and B');
+        }
+        $a = $reverse ? $A->devicePtrRW() : $A->devicePtr();
+        $b = $reverse ? $B->devicePtr() : $B->devicePtrRW();
+        CudaFFI::check(CudaFFI::lib()->rb200_gathernd($A->abiDtype(),$X->abiDtype(),$reverse?1:0,$addMode?1:0,$m,$n,$k,
+            $indexDepth,$shape,$a,$offsetA,$X->devicePtr(),$b,$offsetB));
+    }
+
     /** matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose -- the omatcopy kernel */
     public function matrixcopy(bool $trans,int $m,int $n,float $alpha,Buffer $A,int $offsetA,int $ldA,Buffer $B,int $offsetB,int $ldB) : void
     {

@@ -276,6 +276,32 @@ class CudaMath:
         _capi.check(self._lib.rb200_gatherb(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, batches, m, n, k,
                                             len_, numClass, a_ptr, offsetA, X.device_ptr(), offsetX, b_ptr, offsetB))
 
+    # ---- gathernd (PhpMath.php:1271-1325): gatherND / scatterND / scatterNDAdd ---------------------------------------
+    def gathernd(self, reverse, addMode, m, n, k, indexDepth, paramShape, A, offsetA, X, offsetX, B, offsetB) -> None:
+        """paramShape: the indexDepth leading dimensions of the indexed axes (a host sequence or a buffer).  As in the
+        reference, X is read from element 0 whatever offsetX says (PhpMath.php:1292)."""
+        dims = [int(paramShape[h]) for h in range(indexDepth)]
+        if min([m, n, k, indexDepth] + dims) < 1:
+            raise InvalidArgumentException("Argument shape must be greater than 0.")
+        paramSize = int(np.prod(dims, dtype=np.int64))
+        if m * n * indexDepth > len(X):
+            raise InvalidArgumentException("Matrix X specification too large for buffer.")
+        if offsetA + m * paramSize * k > len(A):
+            raise InvalidArgumentException("Matrix A specification too large for buffer.")
+        if offsetB + m * n * k > len(B):
+            raise InvalidArgumentException("Matrix B specification too large for buffer.")
+        _cuda("X", X), _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        if X.dtype() not in dtypes.INT_TYPES:
+            raise InvalidArgumentException("dtype of X must be integer.")
+        shape = (ctypes.c_int64 * indexDepth)(*dims)
+        a_ptr = A.device_ptr_rw() if reverse else A.device_ptr()
+        b_ptr = B.device_ptr() if reverse else B.device_ptr_rw()
+        _capi.check(self._lib.rb200_gathernd(A.dtype(), X.dtype(), 1 if reverse else 0, 1 if addMode else 0, m, n, k,
+                                             indexDepth, ctypes.cast(shape, ctypes.c_void_p), a_ptr, offsetA, X.device_ptr(),
+                                             b_ptr, offsetB))
+
     def reduceGather(self, reverse, addMode, m, n, numClass, X, offsetX, A, offsetA, B, offsetB) -> None:
         if offsetX + m * n > len(X):          # the reference tests offsetX+n (:1164); the whole [m,n] index must fit
             raise InvalidArgumentException("Matrix X specification too large for buffer.")

@@ -803,6 +803,49 @@ class LinearAlgebra:
         self._do_gatherb(True, True, outputs, indices, axis, batchDims, detailDepth, indexDepth, updates)
         return outputs
 
+    # ---- gatherND / scatterND / scatterNDAdd (LinearAlgebra.php:2925-3090) -----------------------------------------
+    def _do_gathernd(self, reverse, addMode, A: NDArray, X: NDArray, batchDims=None, B=None) -> NDArray:
+        """LinearAlgebra::doGatherND: params (m, paramShape..., k), indices (m, n, index_depth), outputs (m, n, k)"""
+        batchDims = 0 if batchDims is None else batchDims
+        batchShape = X.shape()
+        indexDepth = batchShape.pop()
+        batchShape, outerShape = batchShape[:batchDims], batchShape[batchDims:]
+        innerShape = A.shape()
+        paramsBatchShape, innerShape = innerShape[:batchDims], innerShape[batchDims:]
+        if paramsBatchShape != batchShape:
+            raise InvalidArgumentException(f"Unmatch batch shape of params and indices: {paramsBatchShape},{batchShape}")
+        if indexDepth > A.ndim() - batchDims:
+            raise InvalidArgumentException(
+                "ndim of params must greater than index depth or equal: "
+                f"ndim of params gives {A.ndim()} , index depth gives {indexDepth}")
+        paramShape, innerShape = innerShape[:indexDepth], innerShape[indexDepth:]
+        outputShape = batchShape + outerShape + innerShape
+        prod = lambda s: int(np.prod(s, dtype=np.int64)) if s else 1
+        m, n, k = prod(batchShape), prod(outerShape), prod(innerShape)
+        if B is None:
+            B = self.zeros(self.alloc(outputShape, A.dtype()))
+        elif B.shape() != outputShape:
+            what = "updates" if reverse else "output"
+            raise InvalidArgumentException(f"Unmatch {what} shape: expects {outputShape}, but gives {B.shape()}")
+        self.math.gathernd(reverse, addMode, m, n, k, indexDepth, paramShape, A.buffer(), A.offset(), X.buffer(), X.offset(),
+                           B.buffer(), B.offset())
+        return B
+
+    def gatherND(self, params: NDArray, indices: NDArray, batchDims=None, outputs=None) -> NDArray:
+        return self._do_gathernd(False, False, params, indices, batchDims, outputs)
+
+    def scatterND(self, indices: NDArray, updates: NDArray, shape, batchDims=None, outputs=None) -> NDArray:
+        if outputs is None:
+            outputs = self.zeros(self.alloc(list(shape), updates.dtype()))
+        self._do_gathernd(True, False, outputs, indices, batchDims, updates)
+        return outputs
+
+    def scatterNDAdd(self, indices: NDArray, updates: NDArray, shape, batchDims=None, outputs=None) -> NDArray:
+        if outputs is None:
+            outputs = self.zeros(self.alloc(list(shape), updates.dtype()))
+        self._do_gathernd(True, True, outputs, indices, batchDims, updates)
+        return outputs
+
     def cumsum(self, inputs: NDArray, axis=None, exclusive=None, reverse=None, outputs=None) -> NDArray:
         """LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812): running sum along one axis through cumsumb."""
         ndim = inputs.ndim()

@@ -263,8 +263,8 @@ def run_im2col_case(params, service):
 
 
 def run_gatherb_case(case, service):
-    """tests/golden/gatherb_cases.json (LinearAlgebraTest.php testGatherbNormal / testScatterbNormal /
-    testScatterbAddNormal): params float32 (range over shapeA or a literal), indices int32; operands untouched"""
+    """tests/golden/gatherb_cases.json, gathernd_cases.json (LinearAlgebraTest.php testGatherbNormal / testScatterbNormal /
+    testScatterbAddNormal / testGatherNDNormal / testScatterNDNormal / testScatterNDAddNormal): params float32 (range over shapeA or a literal), indices int32; operands untouched"""
     la = LinearAlgebra(service)
     p = case["params"]
     if "arange" in p:
@@ -274,8 +274,8 @@ def run_gatherb_case(case, service):
     x = np.array(case["indices"], dtype=np.int32)
     A, X = la.array(a), la.array(x, dtype=_DTYPES["int32"])
     kw = case["kwargs"]
-    if case["op"] == "gatherb":
-        out = la.gatherb(A, X, **kw)
+    if case["op"] in ("gatherb", "gatherND"):
+        out = getattr(la, case["op"])(A, X, **kw)
     else:
         out = getattr(la, case["op"])(X, A, case["shape"], **kw)
     want = np.array(case["expect"], dtype=np.float32)

@@ -298,6 +298,14 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def gathernd(self, reverse, addMode, m, n, k, indexDepth, paramShape, A, offA, X, offX, B, offB):
+        a, b = self._f(A), self._f(B)
+        dims = [int(paramShape[h]) for h in range(indexDepth)]
+        _wrap(oracle.gathernd, reverse, addMode, A.dtype() == dtypes.float32, m, n, k, indexDepth, dims, a, offA, self._f(X),
+              b, offB)
+        self._back(A, a)
+        self._back(B, b)
+
     def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
         b = self._f(B)
         _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)

@@ -22,6 +22,59 @@ def test_gatherb_reference_cases(case, cuda_service):
     gr.run_gatherb_case(case, cuda_service)
 
 
+with open(os.path.join(gr.HERE, "golden", "gathernd_cases.json")) as f:
+    GATHERND = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", GATHERND, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERND])
+def test_gathernd_reference_cases(case, cuda_service):
+    gr.run_gatherb_case(case, cuda_service)
+
+
+ND_SHAPES = [(1, 1, 1, [1]), (2, 5, 3, [4]), (3, 40, 2, [3, 4]), (1, 500, 1, [6, 5]), (2, 17, 8, [2, 3, 2]), (4, 9, 64, [7])]
+
+
+@pytest.mark.parametrize("m,n,k,dims", ND_SHAPES)
+@pytest.mark.parametrize("reverse,addMode", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("dt,idt", [(dtypes.float32, dtypes.int32), (dtypes.float64, dtypes.int64), (dtypes.int64, dtypes.int32)])
+def test_gathernd_random_vs_oracle(m, n, k, dims, reverse, addMode, dt, idt, cuda_service):
+    npdt, npi = dtypes.NUMPY[dt], dtypes.NUMPY[idt]
+    rng = np.random.default_rng(n * 5 + k + len(dims))
+    depth, psize = len(dims), int(np.prod(dims))
+    offA, offB = 2, 3
+    if dt == dtypes.int64:
+        a = rng.integers(-50, 50, offA + m * psize * k).astype(npdt)
+        b = rng.integers(-50, 50, offB + m * n * k).astype(npdt)
+    else:
+        a = rng.standard_normal(offA + m * psize * k).astype(npdt)
+        b = rng.standard_normal(offB + m * n * k).astype(npdt)
+    x = np.stack([rng.integers(0, d, m * n) for d in dims], axis=1).astype(npi)         # collisions whenever n > psize
+    if m * n > 4:
+        x[2, depth - 1] = dims[-1]                                                        # out of range: row skipped
+    x = x.reshape(-1)
+    A, B = CudaBuffer(a.size, dt).from_numpy(a), CudaBuffer(b.size, dt).from_numpy(b)
+    X = CudaBuffer(x.size, idt).from_numpy(x)
+    cuda_service.math().gathernd(reverse, addMode, m, n, k, depth, dims, A, offA, X, 0, B, offB)
+    ao, bo = a.astype(np.float64), b.astype(np.float64)
+    oracle.gathernd(reverse, addMode, dt == dtypes.float32, m, n, k, depth, dims, ao, offA, x.astype(np.float64), bo, offB)
+    assert np.array_equal(A.to_numpy().astype(np.float64), ao)
+    assert np.array_equal(B.to_numpy().astype(np.float64), bo)
+
+
+def test_gathernd_errors(cuda_service):
+    la = LinearAlgebra(cuda_service)
+    A = la.array(np.arange(40, dtype=np.float32).reshape(4, 5, 2))
+    X = la.array(np.array([[0], [1], [2], [0]], np.int32), dtype=dtypes.int32)
+    with pytest.raises(InvalidArgumentException, match="Unmatch batch shape"):
+        la.gatherND(A, la.array(np.array([[0], [1]], np.int32), dtype=dtypes.int32), batchDims=1)
+    with pytest.raises(InvalidArgumentException, match="index depth"):
+        la.gatherND(A, la.array(np.zeros((2, 4), np.int32), dtype=dtypes.int32))
+    with pytest.raises(InvalidArgumentException, match="Unmatch output shape"):
+        la.gatherND(A, X, batchDims=1, outputs=la.alloc([4, 3], dtypes.float32))
+    with pytest.raises(InvalidArgumentException, match="Unmatch updates shape"):
+        la.scatterND(X, la.alloc([4, 3], dtypes.float32), [4, 5, 2], batchDims=1)
+
+
 SHAPES = [(1, 1, 1, 1, 1, 1), (2, 3, 4, 1, 1, 5), (3, 2, 7, 4, 1, 6), (2, 1, 9, 3, 5, 4), (1, 4, 300, 2, 3, 17),
           (4, 2, 33, 8, 16, 40), (1, 1, 2000, 1, 1, 50), (2, 2, 5, 64, 4, 3)]
 

@@ -21,6 +21,16 @@ with open(os.path.join(gr.HERE, "golden", "gatherb_cases.json")) as f:
     GATHERB = json.load(f)["cases"]
 
 
+with open(os.path.join(gr.HERE, "golden", "gathernd_cases.json")) as f:
+    GATHERND = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", GATHERND, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERND])
+def test_gathernd_reference_cases(case, oracle_service):
+    assert len(GATHERND) == 18
+    gr.run_gatherb_case(case, oracle_service)
+
+
 @pytest.mark.parametrize("case", GATHERB, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERB])
 def test_gatherb_reference_cases(case, oracle_service):
     assert len(GATHERB) == 26

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Extract the gatherb / scatterb / scatterbAdd cases of the reference's own tests
 (tests/RindowTest/Math/Matrix/LinearAlgebraTest.php: testGatherbNormal, testScatterbNormal, testScatterbAddNormal)
-into tests/golden/gatherb_cases.json.  Run in the build container (reads /root/reference); the JSON is committed.
+into tests/golden/gatherb_cases.json, and the gatherND / scatterND / scatterNDAdd cases (testGatherNDNormal,
+testScatterNDNormal, testScatterNDAddNormal) into tests/golden/gathernd_cases.json.  Run in the build container (reads /root/reference); the JSON is committed.
 Each case: op, params ("arange" over shapeA or a literal), indices, kwargs, shape (scatter), expect, ref line."""
 import json
 import re
@@ -77,6 +78,38 @@ def main():
             t_pos = after.index("$trues = $la->array(")
             case["expect"] = php_literal(balanced(after, t_pos + len("$trues = $la->array(")))
             cases.append(case)
+    nd = []
+    for fn in ("testGatherNDNormal", "testScatterNDNormal", "testScatterNDAddNormal"):
+        begin = src.index("public function %s()" % fn)
+        end = src.index("    public function ", begin + 10)
+        body = src[begin:end]
+        base_line = src[:begin].count("\n") + 1
+        prev_end = 0
+        for call in re.finditer(r"\$b = \$la->(gatherND|scatterND|scatterNDAdd)\((.*?)\);", body, re.S):
+            block, after = body[prev_end:call.end()], body[call.end():]
+            prev_end = call.end()
+            op = call.group(1)
+            a_arg = block[block.rindex("$a = $la->array(") + len("$a = $la->array("):].lstrip()
+            if a_arg.startswith("range("):
+                shapeA = php_literal(balanced(block, block.rindex("$shapeA = ") + len("$shapeA = ")))
+                params = {"arange": shapeA}
+            elif a_arg.startswith("["):
+                params = {"a": php_literal(balanced(a_arg, 0))}
+            else:
+                params = {"a": json.loads(a_arg[:a_arg.index(")")])}            # a scalar: $la->array(1)
+            x_arg = block[block.rindex("$x = $la->array(") + len("$x = $la->array("):].lstrip()
+            case = {"op": op, "params": params, "indices": php_literal(balanced(x_arg, 0)),
+                    "kwargs": {"batchDims": int(re.search(r"batchDims:(\d+)", call.group(2)).group(1))},
+                    "ref": "LinearAlgebraTest.php:%d" % (base_line + body[:call.start()].count("\n"))}
+            if op != "gatherND":
+                case["shape"] = php_literal(balanced(block, block.rindex("$shape = ") + len("$shape = ")))
+            # the expectation is the assertEquals(<literal>,$b->toArray()) that follows the shape assertions
+            m = re.search(r"\$this->assertEquals\(\s*((?:(?!\$this->assertEquals).)*?)\s*,\s*\$b->toArray\(\)\);", after, re.S)
+            case["expect"] = php_literal(m.group(1))
+            nd.append(case)
+    json.dump({"source": "LinearAlgebraTest.php testGatherNDNormal / testScatterNDNormal / testScatterNDAddNormal",
+               "cases": nd}, open("tests/golden/gathernd_cases.json", "w"), indent=1)
+    print(len(nd), "cases -> tests/golden/gathernd_cases.json")
     out = sys.argv[1] if len(sys.argv) > 1 else "tests/golden/gatherb_cases.json"
     json.dump({"source": "LinearAlgebraTest.php testGatherbNormal / testScatterbNormal / testScatterbAddNormal",
                "cases": cases}, open(out, "w"), indent=1)
