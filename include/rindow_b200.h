@@ -361,6 +361,13 @@ int rb200_gatherb(int dtype, int index_dtype, int reverse, int add_mode, int64_t
 int rb200_gathernd(int dtype, int index_dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int index_depth,
                    const int64_t* param_shape, void* A, int64_t offA, const void* X, void* B, int64_t offB);
 
+/* ---- imagecopy: PhpMath::imagecopy (PhpMath.php:2877-2957; LinearAlgebra::imagecopy, LinearAlgebra.php:4590-4660).
+ *      B[y,x,c] = A[clamp(y*dy+by), clamp(x*dx+bx), (rgb_flip && c<3) ? 2-c : c] with the reference's shift / flip
+ *      biases; [h,w,c] or channels_first [c,h,w]; any dtype, bit-exact.  A and B must not overlap. */
+int rb200_imagecopy(int dtype, int64_t height, int64_t width, int64_t channels, const void* A, int64_t offA, void* B,
+                    int64_t offB, int channels_first, int64_t height_shift, int64_t width_shift, int vertical_flip,
+                    int horizontal_flip, int rgb_flip);
+
 /* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
  *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
  *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order

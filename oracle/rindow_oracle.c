@@ -505,6 +505,35 @@ int ro_gathernd(int reverse, int add_mode, int f32, int64_t m, int64_t n, int64_
     return RO_OK;
 }
 
+/* PhpMath::imagecopy, PhpMath.php:2877-2957 */
+int ro_imagecopy(int64_t height, int64_t width, int64_t channels, const double *A, int64_t countA, int64_t offA,
+                 double *B, int64_t countB, int64_t offB, int channelsFirst, int64_t heightShift, int64_t widthShift,
+                 int verticalFlip, int horizontalFlip, int rgbFlip)
+{
+    if (width * height * channels + offA > countA || width * height * channels + offB > countB) return RO_E_ARG;
+    int64_t ldC, ldY, ldX;
+    if (channelsFirst) { ldC = width * height; ldY = width; ldX = 1; }
+    else { ldY = width * channels; ldX = channels; ldC = 1; }
+    int64_t directionY = 1, directionX = 1, biasY = 0, biasX = 0;
+    if (verticalFlip) { directionY = -directionY; biasY = height - 1; }
+    if (horizontalFlip) { directionX = -directionX; biasX = width - 1; }
+    biasY -= heightShift * directionY;
+    biasX -= widthShift * directionX;
+    for (int64_t y = 0; y < height; y++) {
+        for (int64_t x = 0; x < width; x++) {
+            for (int64_t c = 0; c < channels; c++) {
+                int64_t sy = y * directionY + biasY, sx = x * directionX + biasX;
+                if (sy < 0) sy = 0; else if (sy >= height) sy = height - 1;
+                if (sx < 0) sx = 0; else if (sx >= width) sx = width - 1;
+                const int64_t srcC = (rgbFlip && c < 3) ? (2 - c) : c;
+                if (srcC >= channels) return RO_E_ARG;             /* the PHP buffer would be read outside the image */
+                B[y * ldY + x * ldX + c * ldC + offB] = A[sy * ldY + sx * ldX + srcC * ldC + offA];
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
  * buffer rounds at every step (f32 != 0). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,

@@ -172,6 +172,27 @@ class CudaMath extends PhpMath
             $indexDepth,$shape,$a,$offsetA,$X->devicePtr(),$b,$offsetB));
     }
 
+    /** imagecopy (PhpMath.php:2877-2957) */
+    public function imagecopy(int $height,int $width,int $channels,Buffer $A,int $offsetA,Buffer $B,int $offsetB,
+        bool $channelsFirst,int $heightShift,int $widthShift,bool $verticalFlip,bool $horizontalFlip,bool $rgbFlip) : void
+    {
+        if (!$this->anyOnDevice($A,$B) || ($rgbFlip && $channels<3)) {
+            parent::imagecopy($height,$width,$channels,$A,$offsetA,$B,$offsetB,$channelsFirst,$heightShift,$widthShift,
+                $verticalFlip,$horizontalFlip,$rgbFlip); return;
+        }
+        if ($width*$height*$channels+$offsetA > count($A)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferA');
+        }
+        if ($width*$height*$channels+$offsetB > count($B)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferB');
+        }
+        if ($A->dtype()!=$B->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A and B');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_imagecopy($A->abiDtype(),$height,$width,$channels,$A->devicePtr(),$offsetA,
+            $B->devicePtrRW(),$offsetB,$channelsFirst?1:0,$heightShift,$widthShift,$verticalFlip?1:0,$horizontalFlip?1:0,$rgbFlip?1:0));
+    }
+
     /** matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose -- the omatcopy kernel */
     public function matrixcopy(bool $trans,int $m,int $n,float $alpha,Buffer $A,int $offsetA,int $ldA,Buffer $B,int $offsetB,int $ldB) : void
     {

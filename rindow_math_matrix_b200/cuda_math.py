@@ -442,6 +442,22 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- imagecopy (PhpMath.php:2877-2957): shift / flip / RGB swap of one image, border clamped ---------------------
+    def imagecopy(self, height, width, channels, A, offsetA, B, offsetB, channelsFirst, heightShift, widthShift,
+                  verticalFlip, horizontalFlip, rgbFlip) -> None:
+        if width * height * channels + offsetA > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA")
+        if width * height * channels + offsetB > len(B):
+            raise InvalidArgumentException("Matrix specification too large for bufferB")
+        _cuda("A", A), _cuda("B", B)
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("Unmatch data type for A and B")
+        if rgbFlip and channels < 3:
+            raise InvalidArgumentException("rgbFlip needs at least 3 channels.")
+        _capi.check(self._lib.rb200_imagecopy(A.dtype(), height, width, channels, A.device_ptr(), offsetA, B.device_ptr_rw(),
+                                              offsetB, 1 if channelsFirst else 0, int(heightShift), int(widthShift),
+                                              1 if verticalFlip else 0, 1 if horizontalFlip else 0, 1 if rgbFlip else 0))
+
     # ---- matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose; the kernel of BLAS omatcopy -----------
     def matrixcopy(self, trans, m, n, alpha, A, offsetA, ldA, B, offsetB, ldB) -> None:
         if m < 1 or n < 1:

@@ -846,6 +846,29 @@ class LinearAlgebra:
         self._do_gathernd(True, True, outputs, indices, batchDims, updates)
         return outputs
 
+    def imagecopy(self, A: NDArray, B=None, channels_first=None, heightShift=None, widthShift=None, verticalFlip=None,
+                  horizontalFlip=None, rgbFlip=None) -> NDArray:
+        """LinearAlgebra::imagecopy (LinearAlgebra.php:4590-4660)"""
+        if A.ndim() != 3:
+            raise InvalidArgumentException("input array must be 3D.")
+        shape = A.shape()
+        if B is None:
+            B = self.zeros(self.alloc(shape, A.dtype()))
+        else:
+            if B.shape() != shape:
+                raise InvalidArgumentException("output shape must be transpose matrix of input.")
+            if B.dtype() != A.dtype():
+                raise InvalidArgumentException("output data type must be same with matrix of input.")
+        if channels_first is None:                             # the reference tests == null: false selects [h,w,c] too
+            channels_first = False
+        if not channels_first:
+            height, width, channels = shape
+        else:
+            channels, height, width = shape
+        self.math.imagecopy(height, width, channels, A.buffer(), A.offset(), B.buffer(), B.offset(), bool(channels_first),
+                            heightShift or 0, widthShift or 0, bool(verticalFlip), bool(horizontalFlip), bool(rgbFlip))
+        return B
+
     def cumsum(self, inputs: NDArray, axis=None, exclusive=None, reverse=None, outputs=None) -> NDArray:
         """LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812): running sum along one axis through cumsumb."""
         ndim = inputs.ndim()

@@ -284,6 +284,18 @@ def run_gatherb_case(case, service):
     assert np.array_equal(A.to_numpy().reshape(a.shape), a) and np.array_equal(X.to_numpy().reshape(x.shape), x)
 
 
+def run_imagecopy_case(case, service):
+    """tests/golden/imagecopy_cases.json (LinearAlgebraTest.php testImagecopy / testImagecopychannelsfirst)"""
+    la = LinearAlgebra(service)
+    a = np.array(case["a"], dtype=np.float32)
+    A = la.array(a)
+    out = la.imagecopy(A, **case["kwargs"])
+    want = np.array(case["expect"], dtype=np.float32)
+    assert out.shape() == list(a.shape)
+    assert np.array_equal(out.to_numpy().reshape(want.shape), want)
+    assert np.array_equal(A.to_numpy().reshape(a.shape), a)
+
+
 def run_im2col_nd_case(params, service):
     """testIm2col1dNormal / testIm2col3dNormal (LinearAlgebraTest.php:9613-9778, :10653-10882) for one provider row:
     arange-valued images, cols must hold the source index of every in-bounds tap (0 elsewhere), col2im must add every

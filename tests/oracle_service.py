@@ -306,6 +306,13 @@ class OracleMath:
         self._back(A, a)
         self._back(B, b)
 
+    def imagecopy(self, height, width, channels, A, offA, B, offB, channelsFirst, heightShift, widthShift, verticalFlip,
+                  horizontalFlip, rgbFlip):
+        b = self._f(B)
+        _wrap(oracle.imagecopy, height, width, channels, self._f(A), offA, b, offB, channelsFirst, heightShift, widthShift,
+              verticalFlip, horizontalFlip, rgbFlip)
+        self._back(B, b)
+
     def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
         b = self._f(B)
         _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)

@@ -140,3 +140,45 @@ def test_gatherb_errors(cuda_service):
         m.gatherb(False, False, 1, 1, 2, 1, 1, 30, A.buffer(), 0, X.buffer(), 0, CudaBuffer(2, dtypes.float32), 0)
     with pytest.raises(InvalidArgumentException, match="integer"):
         m.gatherb(False, False, 1, 1, 2, 1, 1, 3, A.buffer(), 0, CudaBuffer(2, dtypes.float32), 0, CudaBuffer(2, dtypes.float32), 0)
+
+
+# ---- imagecopy -------------------------------------------------------------------------------------------------------
+
+with open(os.path.join(gr.HERE, "golden", "imagecopy_cases.json")) as f:
+    IMAGECOPY = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", IMAGECOPY, ids=["imagecopy_" + c["ref"].split(":")[1] for c in IMAGECOPY])
+def test_imagecopy_reference_cases(case, cuda_service):
+    gr.run_imagecopy_case(case, cuda_service)
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 1), (7, 5, 3), (64, 48, 4), (224, 224, 3)])
+@pytest.mark.parametrize("channels_first", [False, True])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.uint8, dtypes.float64])
+def test_imagecopy_random_vs_oracle(h, w, c, channels_first, dt, cuda_service):
+    npdt = dtypes.NUMPY[dt]
+    rng = np.random.default_rng(h * 3 + w)
+    offA, offB = 2, 1
+    a = rng.integers(0, 255, offA + h * w * c).astype(npdt)
+    for hs, ws, vf, hf, rgb in [(0, 0, False, False, False), (3, -2, True, False, c >= 3), (-h - 1, w + 2, False, True, False),
+                                (1, 1, True, True, c >= 3)]:
+        b = np.full(offB + h * w * c, 7).astype(npdt)
+        A, B = CudaBuffer(a.size, dt).from_numpy(a), CudaBuffer(b.size, dt).from_numpy(b)
+        cuda_service.math().imagecopy(h, w, c, A, offA, B, offB, channels_first, hs, ws, vf, hf, rgb)
+        bo = b.astype(np.float64)
+        oracle.imagecopy(h, w, c, a.astype(np.float64), offA, bo, offB, channels_first, hs, ws, vf, hf, rgb)
+        assert np.array_equal(B.to_numpy().astype(np.float64), bo), (hs, ws, vf, hf, rgb)
+
+
+def test_imagecopy_errors(cuda_service):
+    la = LinearAlgebra(cuda_service)
+    with pytest.raises(InvalidArgumentException, match="3D"):
+        la.imagecopy(la.alloc([4, 4], dtypes.float32))
+    A = la.alloc([4, 4, 3], dtypes.float32)
+    with pytest.raises(InvalidArgumentException, match="output shape"):
+        la.imagecopy(A, la.alloc([4, 4, 4], dtypes.float32))
+    with pytest.raises(InvalidArgumentException, match="output data type"):
+        la.imagecopy(A, la.alloc([4, 4, 3], dtypes.float64))
+    with pytest.raises(InvalidArgumentException, match="bufferB"):
+        cuda_service.math().imagecopy(4, 4, 3, A.buffer(), 0, CudaBuffer(47, dtypes.float32), 0, False, 0, 0, False, False, False)

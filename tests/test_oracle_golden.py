@@ -31,6 +31,16 @@ def test_gathernd_reference_cases(case, oracle_service):
     gr.run_gatherb_case(case, oracle_service)
 
 
+with open(os.path.join(gr.HERE, "golden", "imagecopy_cases.json")) as f:
+    IMAGECOPY = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", IMAGECOPY, ids=["imagecopy_" + c["ref"].split(":")[1] for c in IMAGECOPY])
+def test_imagecopy_reference_cases(case, oracle_service):
+    assert len(IMAGECOPY) == 26
+    gr.run_imagecopy_case(case, oracle_service)
+
+
 @pytest.mark.parametrize("case", GATHERB, ids=[c["op"] + "_" + c["ref"].split(":")[1] for c in GATHERB])
 def test_gatherb_reference_cases(case, oracle_service):
     assert len(GATHERB) == 26

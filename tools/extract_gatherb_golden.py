@@ -110,6 +110,35 @@ def main():
     json.dump({"source": "LinearAlgebraTest.php testGatherNDNormal / testScatterNDNormal / testScatterNDAddNormal",
                "cases": nd}, open("tests/golden/gathernd_cases.json", "w"), indent=1)
     print(len(nd), "cases -> tests/golden/gathernd_cases.json")
+    img = []
+    for fn in ("testImagecopy", "testImagecopychannelsfirst"):
+        begin = src.index("public function %s()" % fn)
+        end = src.index("    public function ", begin + 10)
+        body = src[begin:end]
+        base_line = src[:begin].count("\n") + 1
+        events = [(m.start(), "a", m) for m in re.finditer(r"\$a = \$la->array\(", body)]
+        events += [(m.start(), "call", m) for m in re.finditer(r"\$b = \$la->imagecopy\(\$a,null,(null|true),(.*?)\);", body, re.S)]
+        a = None
+        names = ["heightShift", "widthShift", "verticalFlip", "horizontalFlip", "rgbFlip"]
+        for pos, kind, m in sorted(events, key=lambda e: e[0]):
+            if kind == "a":
+                a = php_literal(balanced(body, m.end()))
+                continue
+            kwargs = {}
+            for slot, arg in enumerate(x.strip() for x in m.group(2).split(",")):
+                value = arg.split("=")[-1].strip()                       # "$heightShift=1" or a bare value
+                if value in ("true", "false"):
+                    kwargs[names[slot]] = value == "true"
+                elif value != "null":
+                    kwargs[names[slot]] = int(value)
+            if m.group(1) == "true":
+                kwargs["channels_first"] = True
+            exp = re.search(r"\$this->assertEquals\(\s*(\[.*?\])\s*,\s*\$b->toArray\(\)\);", body[m.end():], re.S)
+            img.append({"a": a, "kwargs": kwargs, "expect": php_literal(exp.group(1)),
+                        "ref": "LinearAlgebraTest.php:%d" % (base_line + body[:pos].count("\n"))})
+    json.dump({"source": "LinearAlgebraTest.php testImagecopy / testImagecopychannelsfirst", "cases": img},
+              open("tests/golden/imagecopy_cases.json", "w"), indent=1)
+    print(len(img), "cases -> tests/golden/imagecopy_cases.json")
     out = sys.argv[1] if len(sys.argv) > 1 else "tests/golden/gatherb_cases.json"
     json.dump({"source": "LinearAlgebraTest.php testGatherbNormal / testScatterbNormal / testScatterbAddNormal",
                "cases": cases}, open(out, "w"), indent=1)
