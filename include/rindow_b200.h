@@ -368,6 +368,15 @@ int rb200_imagecopy(int dtype, int64_t height, int64_t width, int64_t channels, 
                     int64_t offB, int channels_first, int64_t height_shift, int64_t width_shift, int vertical_flip,
                     int horizontal_flip, int rgb_flip);
 
+/* ---- einsum: PhpMath::einsum (PhpMath.php:3321-3357) and einsum4p1 (:3360-3440, the same sum with four output
+ *      axes and one summed axis).  sizeOfIndices / ldA / ldB are HOST arrays of `depth` entries (<= 16): the first
+ *      ndimC axes index C (row-major, dense), the rest are summed, last axis fastest; an operand's stride is 0 on an
+ *      axis it lacks.  C[ic] = sum A[offA + idx.ldA] * B[offB + idx.ldB], accumulated in double in the reference's
+ *      order with separate multiply and add (bit-identical to PHP's `$sumC += $A[..] * $B[..]`).  float32 / float64.
+ *      einsum4p1 callers pass offC = 0: the reference stores from element 0 of C whatever offsetC says (:3432). */
+int rb200_einsum(int dtype, int depth, int ndimC, const int64_t* sizeOfIndices, const void* A, int64_t offA,
+                 const int64_t* ldA, const void* B, int64_t offB, const int64_t* ldB, void* C, int64_t offC);
+
 /* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
  *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
  *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order

@@ -534,6 +534,41 @@ int ro_imagecopy(int64_t height, int64_t width, int64_t channels, const double *
     return RO_OK;
 }
 
+/* PhpMath::einsum, PhpMath.php:3321-3357 (odometer over all `depth` axes, the first ndimC index C; einsum4p1
+ * :3360-3440 is the depth 5 / ndimC 4 case).  The sum is a PHP float (double). */
+int ro_einsum(int64_t depth, int64_t ndimC, const int64_t *sizeOfIndices, const double *A, int64_t countA, int64_t offA,
+              const int64_t *ldA, const double *B, int64_t countB, int64_t offB, const int64_t *ldB,
+              double *C, int64_t countC, int64_t offC)
+{
+    if (depth < 1 || depth > 16) return RO_E_ARG;
+    int64_t sizeC = 1, maxA = 0, maxB = 0;
+    for (int64_t i = 0; i < depth; i++) {
+        if (i < ndimC) sizeC *= sizeOfIndices[i];
+        maxA += (sizeOfIndices[i] - 1) * ldA[i];
+        maxB += (sizeOfIndices[i] - 1) * ldB[i];
+    }
+    if (offA + maxA >= countA || offB + maxB >= countB || offC + sizeC > countC) return RO_E_ARG;
+    int64_t indices[16] = {0};
+    for (int64_t indexC = 0; indexC < sizeC; indexC++) {
+        double sumC = 0;
+        for (;;) {
+            int64_t indexA = offA, indexB = offB;
+            for (int64_t axis = 0; axis < depth; axis++) { indexA += indices[axis] * ldA[axis]; indexB += indices[axis] * ldB[axis]; }
+            sumC += A[indexA] * B[indexB];
+            int64_t i = depth - 1;                                   /* einsum_next_indices, :3297-3318 */
+            while (i >= 0) {
+                if (indices[i] < sizeOfIndices[i] - 1) break;
+                indices[i] = 0;
+                i--;
+            }
+            if (i >= 0) indices[i]++;
+            if (i < ndimC) break;
+        }
+        C[offC + indexC] = sumC;
+    }
+    return RO_OK;
+}
+
 /* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
  * buffer rounds at every step (f32 != 0). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,

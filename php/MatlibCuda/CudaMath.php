@@ -172,6 +172,62 @@ class CudaMath extends PhpMath
             $indexDepth,$shape,$a,$offsetA,$X->devicePtr(),$b,$offsetB));
     }
 
+    /** einsum (PhpMath.php:3321-3357): the size / stride buffers are read on the host */
+    public function einsum(Buffer $sizeOfIndices,Buffer $A,int $offsetA,Buffer $ldA,Buffer $B,int $offsetB,Buffer $ldB,
+        Buffer $C,int $offsetC,int $ndimC) : void
+    {
+        $depth = count($sizeOfIndices);
+        if (!$this->anyOnDevice($A,$B,$C) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64]) || $depth>16) {
+            parent::einsum($sizeOfIndices,$A,$offsetA,$ldA,$B,$offsetB,$ldB,$C,$offsetC,$ndimC); return;
+        }
+        $s = \FFI::new("int64_t[$depth]"); $la = \FFI::new("int64_t[$depth]"); $lb = \FFI::new("int64_t[$depth]");
+        for ($h=0;$h<$depth;$h++) { $s[$h] = $sizeOfIndices[$h]; $la[$h] = $ldA[$h]; $lb[$h] = $ldB[$h]; }
+        $this->einsumDevice($depth,$ndimC,$s,$la,$lb,$A,$offsetA,$B,$offsetB,$C,$offsetC);
+    }
+
+    /** einsum4p1 (PhpMath.php:3360-3440): four output axes, one summed axis; C is stored from element 0 as in the reference */
+    public function einsum4p1(int $dim0,int $dim1,int $dim2,int $dim3,int $dim4,
+        Buffer $A,int $offsetA,int $ldA0,int $ldA1,int $ldA2,int $ldA3,int $ldA4,
+        Buffer $B,int $offsetB,int $ldB0,int $ldB1,int $ldB2,int $ldB3,int $ldB4,
+        Buffer $C,int $offsetC) : void
+    {
+        if (!$this->anyOnDevice($A,$B,$C) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
+            parent::einsum4p1($dim0,$dim1,$dim2,$dim3,$dim4,$A,$offsetA,$ldA0,$ldA1,$ldA2,$ldA3,$ldA4,
+                $B,$offsetB,$ldB0,$ldB1,$ldB2,$ldB3,$ldB4,$C,$offsetC); return;
+        }
+        if (count($C) <= $offsetC+$dim0*$dim1*$dim2*$dim3-1) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer C.');
+        }
+        $s = \FFI::new("int64_t[5]"); $la = \FFI::new("int64_t[5]"); $lb = \FFI::new("int64_t[5]");
+        foreach ([$dim0,$dim1,$dim2,$dim3,$dim4] as $h=>$v) { $s[$h] = $v; }
+        foreach ([$ldA0,$ldA1,$ldA2,$ldA3,$ldA4] as $h=>$v) { $la[$h] = $v; }
+        foreach ([$ldB0,$ldB1,$ldB2,$ldB3,$ldB4] as $h=>$v) { $lb[$h] = $v; }
+        $this->einsumDevice(5,4,$s,$la,$lb,$A,$offsetA,$B,$offsetB,$C,0);
+    }
+
+    private function einsumDevice(int $depth,int $ndimC,$s,$la,$lb,Buffer $A,int $offsetA,Buffer $B,int $offsetB,Buffer $C,int $offsetC) : void
+    {
+        $maxA = 0; $maxB = 0; $sizeC = 1;
+        for ($h=0;$h<$depth;$h++) {
+            $maxA += ($s[$h]-1)*$la[$h]; $maxB += ($s[$h]-1)*$lb[$h];
+            if ($h<$ndimC) { $sizeC *= $s[$h]; }
+        }
+        if (count($A) <= $offsetA+$maxA) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer A.');
+        }
+        if (count($B) <= $offsetB+$maxB) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer B.');
+        }
+        if (count($C) < $offsetC+$sizeC) {
+            throw new InvalidArgumentException('Matrix specification too large for buffer C.');
+        }
+        if ($A->dtype()!=$B->dtype() || $A->dtype()!=$C->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for A, B and C');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_einsum($A->abiDtype(),$depth,$ndimC,$s,$A->devicePtr(),$offsetA,$la,
+            $B->devicePtr(),$offsetB,$lb,$C->devicePtrRW(),$offsetC));
+    }
+
     /** imagecopy (PhpMath.php:2877-2957) */
     public function imagecopy(int $height,int $width,int $channels,Buffer $A,int $offsetA,Buffer $B,int $offsetB,
         bool $channelsFirst,int $heightShift,int $widthShift,bool $verticalFlip,bool $horizontalFlip,bool $rgbFlip) : void

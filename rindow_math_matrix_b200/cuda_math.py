@@ -442,6 +442,41 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- einsum / einsum4p1 (PhpMath.php:3321-3440) ---------------------------------------------------------------------
+    def _einsum(self, sizes, A, offsetA, ldA, B, offsetB, ldB, C, offsetC, ndimC) -> None:
+        depth = len(sizes)
+        if depth < 1 or depth > 16 or min(sizes) < 1 or min(ldA) < 0 or min(ldB) < 0 or ndimC < 0 or ndimC > depth:
+            raise InvalidArgumentException("Invalid einsum specification.")
+        if offsetA + sum((d - 1) * l for d, l in zip(sizes, ldA)) >= len(A):
+            raise InvalidArgumentException("Matrix specification too large for buffer A.")
+        if offsetB + sum((d - 1) * l for d, l in zip(sizes, ldB)) >= len(B):
+            raise InvalidArgumentException("Matrix specification too large for buffer B.")
+        if offsetC + int(np.prod(sizes[:ndimC], dtype=np.int64)) > len(C):
+            raise InvalidArgumentException("Matrix specification too large for buffer C.")
+        _cuda("A", A), _cuda("B", B), _cuda("C", C)
+        if A.dtype() != B.dtype() or A.dtype() != C.dtype():
+            raise InvalidArgumentException("Unmatch data type for A, B and C")
+        if A.dtype() not in (dtypes.float32, dtypes.float64):
+            raise InvalidArgumentException("Unsupported data type.")
+        arr = lambda v: ctypes.cast((ctypes.c_int64 * depth)(*[int(x) for x in v]), ctypes.c_void_p)
+        s, la_, lb_ = arr(sizes), arr(ldA), arr(ldB)
+        _capi.check(self._lib.rb200_einsum(A.dtype(), depth, ndimC, s, A.device_ptr(), offsetA, la_, B.device_ptr(), offsetB,
+                                           lb_, C.device_ptr_rw(), offsetC))
+
+    def einsum(self, sizeOfIndices, A, offsetA, ldA, B, offsetB, ldB, C, offsetC, ndimC) -> None:
+        """sizeOfIndices / ldA / ldB: host sequences or buffers of len(sizeOfIndices) entries"""
+        depth = len(sizeOfIndices)
+        self._einsum([int(sizeOfIndices[h]) for h in range(depth)], A, offsetA, [int(ldA[h]) for h in range(depth)],
+                     B, offsetB, [int(ldB[h]) for h in range(depth)], C, offsetC, ndimC)
+
+    def einsum4p1(self, dim0, dim1, dim2, dim3, dim4, A, offsetA, ldA0, ldA1, ldA2, ldA3, ldA4,
+                  B, offsetB, ldB0, ldB1, ldB2, ldB3, ldB4, C, offsetC) -> None:
+        if len(C) <= offsetC + dim0 * dim1 * dim2 * dim3 - 1:
+            raise InvalidArgumentException("Matrix specification too large for buffer C.")
+        # the reference stores from element 0 of C whatever offsetC says (PhpMath.php:3432)
+        self._einsum([dim0, dim1, dim2, dim3, dim4], A, offsetA, [ldA0, ldA1, ldA2, ldA3, ldA4],
+                     B, offsetB, [ldB0, ldB1, ldB2, ldB3, ldB4], C, 0, 4)
+
     # ---- imagecopy (PhpMath.php:2877-2957): shift / flip / RGB swap of one image, border clamped ---------------------
     def imagecopy(self, height, width, channels, A, offsetA, B, offsetB, channelsFirst, heightShift, widthShift,
                   verticalFlip, horizontalFlip, rgbFlip) -> None:

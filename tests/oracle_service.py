@@ -313,6 +313,13 @@ class OracleMath:
               verticalFlip, horizontalFlip, rgbFlip)
         self._back(B, b)
 
+    def einsum(self, sizeOfIndices, A, offA, ldA, B, offB, ldB, C, offC, ndimC):
+        depth = len(sizeOfIndices)
+        c = self._f(C)
+        _wrap(oracle.einsum, [int(sizeOfIndices[h]) for h in range(depth)], self._f(A), offA,
+              [int(ldA[h]) for h in range(depth)], self._f(B), offB, [int(ldB[h]) for h in range(depth)], c, offC, ndimC)
+        self._back(C, c)
+
     def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
         b = self._f(B)
         _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)
