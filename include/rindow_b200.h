@@ -377,6 +377,13 @@ int rb200_imagecopy(int dtype, int64_t height, int64_t width, int64_t channels, 
 int rb200_einsum(int dtype, int depth, int ndimC, const int64_t* sizeOfIndices, const void* A, int64_t offA,
                  const int64_t* ldA, const void* B, int64_t offB, const int64_t* ldB, void* C, int64_t offC);
 
+/* ---- topk: PhpMath::topk (PhpMath.php:933-1058; LinearAlgebra::topK, LinearAlgebra.php:2368-2440).  Per row of
+ *      input[m,n]: the k largest values[m,k] and their indices[m,k], produced by the reference's min-heap so ties, NaN
+ *      handling and output order (heap order, or heap-sort order when sorted) are identical.  k > n returns without
+ *      writing, as the reference does.  float32 / float64 / int32 / int64 values; 32- or 64-bit integer indices. */
+int rb200_topk(int dtype, int index_dtype, int64_t m, int64_t n, const void* input, int64_t offInput, int64_t k, int sorted,
+               void* values, int64_t offValues, void* indices, int64_t offIndices);
+
 /* ---- cumsumb: PhpMath::cumsumb (PhpMath.php:1861-1904), what LinearAlgebra::cumsum (LinearAlgebra.php:4764-4812)
  *      calls: B[i,j,h] = sum of A[i,0..j,h] along the middle axis of [m,n,k]; exclusive shifts by one (B[i,0,h] = 0),
  *      reverse runs from j = n-1 down.  float32 / float64 / int32 / int64.  Floating sums are added in tree order

@@ -83,6 +83,7 @@ def lib() -> ctypes.CDLL:
         L.ro_gathernd.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, i64, i64, i64, p, p, i64, i64, p, i64, p, i64, i64]
         L.ro_imagecopy.argtypes = [i64, i64, i64, p, i64, i64, p, i64, i64, ctypes.c_int, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.ro_einsum.argtypes = [i64, i64, p, p, i64, i64, p, p, i64, i64, p, p, i64, i64]
+        L.ro_topk.argtypes = [i64, i64, p, i64, i64, i64, ctypes.c_int, p, i64, i64, p, i64, i64]
         L.ro_cumsumb.argtypes = [i64, i64, i64, p, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, p, i64, i64]
         L.ro_cumsum.argtypes = [i64, p, i64, i64, i64, ctypes.c_int, ctypes.c_int, p, i64, i64, i64]
         L.ro_searchsorted.argtypes = [i64, i64, p, i64, i64, i64, p, i64, i64, i64, ctypes.c_int, p, i64, i64, i64]
@@ -102,7 +103,7 @@ def lib() -> ctypes.CDLL:
         L.ro_transpose.argtypes = [i32, p, p, p, i64, i64, p, i64, i64]
         L.ro_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
         L.ro_reduce_gather.argtypes = [i32, i32, i64, i64, i64, p, i64, i64, p, i64, i64, p, i64, i64]
-        for name in ("ro_einsum", "ro_imagecopy", "ro_gathernd", "ro_gatherb", "ro_cumsumb", "ro_cumsum", "ro_searchsorted", "ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
+        for name in ("ro_topk", "ro_einsum", "ro_imagecopy", "ro_gathernd", "ro_gatherb", "ro_cumsumb", "ro_cumsum", "ro_searchsorted", "ro_bandpart", "ro_masking", "ro_slice", "ro_repeat", "ro_im2col1d", "ro_im2col3d", "ro_dot", "ro_asum", "ro_nrm2", "ro_iamax", "ro_iamin", "ro_swap", "ro_gather", "ro_reduce_gather", "ro_transpose", "ro_broadcast", "ro_unary", "ro_compare", "ro_sum", "ro_imax", "ro_imin", "ro_onehot", "ro_gemm", "ro_gemm_rows", "ro_gemm_rows_interleaved", "ro_gemm3", "ro_add", "ro_multiply",
                      "ro_scal", "ro_axpy", "ro_copy", "ro_gemv", "ro_omatcopy",
                      "ro_reduce_sum", "ro_reduce_max", "ro_reduce_argmax", "ro_softmax",
                      "ro_im2col2d", "ro_abi_version"):
@@ -376,6 +377,12 @@ def einsum(sizeOfIndices, A, offA, ldA, B, offB, ldB, C, offC, ndimC):
     s, la, lb = arr(sizeOfIndices), arr(ldA), arr(ldB)
     _check(lib().ro_einsum(depth, ndimC, s, _ptr(_buf(A)), A.size, offA, la, _ptr(_buf(B)), B.size, offB, lb,
                            _ptr(_buf(C)), C.size, offC))
+
+
+# PhpMath::topk :933-1058
+def topk(m, n, input, offInput, k, sorted, values, offValues, indices, offIndices):
+    _check(lib().ro_topk(m, n, _ptr(_buf(input)), input.size, offInput, k, int(bool(sorted)), _ptr(_buf(values)), values.size,
+                         offValues, _ptr(_buf(indices)), indices.size, offIndices))
 
 
 # PhpMath::cumsumb :1861-1904, cumsum :1822-1859, searchsorted :1780-1820

@@ -569,6 +569,46 @@ int ro_einsum(int64_t depth, int64_t ndimC, const int64_t *sizeOfIndices, const 
     return RO_OK;
 }
 
+/* PhpMath::topk, PhpMath.php:933-1058: min-heap of the first k, the rest offered in order, optional heap sort */
+static void ro_topk_heapify(int64_t size, double *heap, double *idx, int64_t parent)
+{
+    int64_t left = 2 * parent + 1, right = 2 * parent + 2;
+    while (left < size) {
+        int64_t smallest = (right < size && heap[right] < heap[left]) ? right : left;
+        if (heap[parent] <= heap[smallest]) break;
+        double t = heap[parent]; heap[parent] = heap[smallest]; heap[smallest] = t;
+        t = idx[parent]; idx[parent] = idx[smallest]; idx[smallest] = t;
+        parent = smallest;
+        left = 2 * parent + 1;
+        right = 2 * parent + 2;
+    }
+}
+
+int ro_topk(int64_t m, int64_t n, const double *input, int64_t countIn, int64_t offIn, int64_t k, int sorted,
+            double *values, int64_t countV, int64_t offV, double *indices, int64_t countI, int64_t offI)
+{
+    if (m < 1 || n < 1 || k < 1) return RO_E_ARG;
+    if (offIn + m * n > countIn || offV + m * k > countV || offI + m * k > countI) return RO_E_ARG;
+    if (k > n) return RO_OK;
+    for (int64_t r = 0; r < m; r++) {
+        const double *arr = input + offIn + r * n;
+        double *top = values + offV + r * k, *idx = indices + offI + r * k;
+        for (int64_t i = 0; i < k; i++) { top[i] = arr[i]; idx[i] = (double)i; }
+        for (int64_t i = k / 2 - 1; i >= 0; --i) ro_topk_heapify(k, top, idx, i);
+        for (int64_t i = k; i < n; i++) {
+            if (arr[i] > top[0]) { top[0] = arr[i]; idx[0] = (double)i; ro_topk_heapify(k, top, idx, 0); }
+        }
+        if (sorted) {
+            for (int64_t i = k - 1; i > 0; --i) {
+                double t = top[0]; top[0] = top[i]; top[i] = t;
+                t = idx[0]; idx[0] = idx[i]; idx[i] = t;
+                ro_topk_heapify(i, top, idx, 0);
+            }
+        }
+    }
+    return RO_OK;
+}
+
 /* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
  * buffer rounds at every step (f32 != 0). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,

@@ -116,6 +116,7 @@ class CudaFFI
         int rb200_gathernd(int dtype, int index_dtype, int reverse, int add_mode, int64_t m, int64_t n, int64_t k, int index_depth, const int64_t* param_shape, void* A, int64_t offA, const void* X, void* B, int64_t offB);
         int rb200_imagecopy(int dtype, int64_t height, int64_t width, int64_t channels, const void* A, int64_t offA, void* B, int64_t offB, int channels_first, int64_t height_shift, int64_t width_shift, int vertical_flip, int horizontal_flip, int rgb_flip);
         int rb200_einsum(int dtype, int depth, int ndimC, const int64_t* sizeOfIndices, const void* A, int64_t offA, const int64_t* ldA, const void* B, int64_t offB, const int64_t* ldB, void* C, int64_t offC);
+        int rb200_topk(int dtype, int index_dtype, int64_t m, int64_t n, const void* input, int64_t offInput, int64_t k, int sorted, void* values, int64_t offValues, void* indices, int64_t offIndices);
         int rb200_cumsumb(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA, int exclusive, int reverse, void* B, int64_t offB);
         int rb200_cumsum(int dtype, int64_t n, const void* X, int64_t offX, int64_t incX, int exclusive, int reverse, void* Y, int64_t offY, int64_t incY);
         int rb200_searchsorted(int dtype, int index_dtype, int64_t m, int64_t n, const void* A, int64_t offA, int64_t ldA, const void* X, int64_t offX, int64_t incX, int right, void* Y, int64_t offY, int64_t incY);

@@ -228,6 +228,32 @@ class CudaMath extends PhpMath
             $B->devicePtr(),$offsetB,$lb,$C->devicePtrRW(),$offsetC));
     }
 
+    /** topk (PhpMath.php:933-1058): the reference's min-heap per row, one warp per row */
+    public function topk(int $m,int $n,Buffer $input,int $offsetInput,int $k,bool $sorted,
+        Buffer $values,int $offsetValues,Buffer $indices,int $offsetIndices) : void
+    {
+        if (!$this->anyOnDevice($input,$values,$indices) || $k*4*12 > 200*1024) {
+            parent::topk($m,$n,$input,$offsetInput,$k,$sorted,$values,$offsetValues,$indices,$offsetIndices); return;
+        }
+        if ($m<1||$n<1||$k<1) {
+            throw new InvalidArgumentException('Argument m / n / k must be greater than 0.');
+        }
+        if ($offsetInput+$m*$n > count($input)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferinput.');
+        }
+        if ($offsetValues+$m*$k > count($values)) {
+            throw new InvalidArgumentException('Matrix specification too large for buffervalues.');
+        }
+        if ($offsetIndices+$m*$k > count($indices)) {
+            throw new InvalidArgumentException('Matrix specification too large for bufferindices.');
+        }
+        if ($input->dtype()!=$values->dtype()) {
+            throw new InvalidArgumentException('Unmatch data type for input and values');
+        }
+        CudaFFI::check(CudaFFI::lib()->rb200_topk($input->abiDtype(),$indices->abiDtype(),$m,$n,$input->devicePtr(),$offsetInput,
+            $k,$sorted?1:0,$values->devicePtrRW(),$offsetValues,$indices->devicePtrRW(),$offsetIndices));
+    }
+
     /** imagecopy (PhpMath.php:2877-2957) */
     public function imagecopy(int $height,int $width,int $channels,Buffer $A,int $offsetA,Buffer $B,int $offsetB,
         bool $channelsFirst,int $heightShift,int $widthShift,bool $verticalFlip,bool $horizontalFlip,bool $rgbFlip) : void

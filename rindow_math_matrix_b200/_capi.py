@@ -96,6 +96,7 @@ SIGNATURES = {
     "rb200_gathernd": (i32, [i32, i32, i32, i32, i64, i64, i64, i32, vp, vp, i64, vp, vp, i64]),
     "rb200_imagecopy": (i32, [i32, i64, i64, i64, vp, i64, vp, i64, i32, i64, i64, i32, i32, i32]),
     "rb200_einsum": (i32, [i32, i32, i32, vp, vp, i64, vp, vp, i64, vp, vp, i64]),
+    "rb200_topk": (i32, [i32, i32, i64, i64, vp, i64, i64, i32, vp, i64, vp, i64]),
     "rb200_cumsumb": (i32, [i32, i64, i64, i64, vp, i64, i32, i32, vp, i64]),
     "rb200_cumsum": (i32, [i32, i64, vp, i64, i64, i32, i32, vp, i64, i64]),
     "rb200_searchsorted": (i32, [i32, i32, i64, i64, vp, i64, i64, vp, i64, i64, i32, vp, i64, i64]),

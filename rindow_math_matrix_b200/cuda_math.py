@@ -442,6 +442,27 @@ class CudaMath:
                                              dilation_h, dilation_w, 1 if cols_channels_first else 0,
                                              co_ptr, cols_offset, cols_size))
 
+    # ---- topk (PhpMath.php:933-1058): the reference's min-heap per row ------------------------------------------------
+    def topk(self, m, n, input, offsetInput, k, sorted, values, offsetValues, indices, offsetIndices) -> None:
+        if m < 1 or n < 1 or k < 1:
+            raise InvalidArgumentException("Argument m / n / k must be greater than 0.")
+        if offsetInput + m * n > len(input):
+            raise InvalidArgumentException("Matrix specification too large for bufferinput.")
+        if offsetValues + m * k > len(values):
+            raise InvalidArgumentException("Matrix specification too large for buffervalues.")
+        if offsetIndices + m * k > len(indices):
+            raise InvalidArgumentException("Matrix specification too large for bufferindices.")
+        _cuda("input", input), _cuda("values", values), _cuda("indices", indices)
+        if indices.dtype() not in dtypes.INT_TYPES:
+            raise InvalidArgumentException("indices must be integers")
+        if input.dtype() != values.dtype():
+            raise InvalidArgumentException("Unmatch data type for input and values")
+        _capi.check(self._lib.rb200_topk(input.dtype(), indices.dtype(), m, n, input.device_ptr(), offsetInput, k,
+                                         1 if sorted else 0, values.device_ptr_rw(), offsetValues, indices.device_ptr_rw(),
+                                         offsetIndices))
+
+    topK = topk
+
     # ---- einsum / einsum4p1 (PhpMath.php:3321-3440) ---------------------------------------------------------------------
     def _einsum(self, sizes, A, offsetA, ldA, B, offsetB, ldB, C, offsetC, ndimC) -> None:
         depth = len(sizes)

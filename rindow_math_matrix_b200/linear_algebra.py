@@ -846,6 +846,36 @@ class LinearAlgebra:
         self._do_gathernd(True, True, outputs, indices, batchDims, updates)
         return outputs
 
+    def topK(self, input: NDArray, k=None, sorted=None, values=None, indices=None):
+        """LinearAlgebra::topK (LinearAlgebra.php:2368-2440): [values, indices] of the k largest along the last axis"""
+        k = 1 if k is None else k
+        sorted = True if sorted is None else sorted
+        shape = input.shape()
+        n = shape.pop()
+        m = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        shape.append(k)
+        if k > n:
+            raise InvalidArgumentException("k must be less than or equal to the entity.")
+        if values is None:
+            values = self.alloc(shape, input.dtype())
+        else:
+            if values.shape() != shape:
+                raise InvalidArgumentException(f'Unmatch shape of "values" with "input" and "k": {values.shape()}')
+            if values.dtype() != input.dtype():
+                raise InvalidArgumentException('Unmatch dtype of "values" with input')
+        if indices is None:
+            indices = self.alloc(shape, dtypes.int32)
+        else:
+            if indices.ndim() != 2:
+                raise InvalidArgumentException('"indices" must be 2-D dimension')
+            if indices.shape() != shape:
+                raise InvalidArgumentException(f'Unmatch shape of "indices" with "input" and "k": {indices.shape()}')
+            if indices.dtype() != dtypes.int32:
+                raise InvalidArgumentException('Unmatch dtype of "indices" with input')
+        self.math.topk(m, n, input.buffer(), input.offset(), k, sorted, values.buffer(), values.offset(),
+                       indices.buffer(), indices.offset())
+        return [values, indices]
+
     def imagecopy(self, A: NDArray, B=None, channels_first=None, heightShift=None, widthShift=None, verticalFlip=None,
                   horizontalFlip=None, rgbFlip=None) -> NDArray:
         """LinearAlgebra::imagecopy (LinearAlgebra.php:4590-4660)"""

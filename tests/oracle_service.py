@@ -320,6 +320,14 @@ class OracleMath:
               [int(ldA[h]) for h in range(depth)], self._f(B), offB, [int(ldB[h]) for h in range(depth)], c, offC, ndimC)
         self._back(C, c)
 
+    def topk(self, m, n, input, offInput, k, sorted, values, offValues, indices, offIndices):
+        v, ix = self._f(values), self._f(indices)
+        _wrap(oracle.topk, m, n, self._f(input), offInput, k, sorted, v, offValues, ix, offIndices)
+        self._back(values, v)
+        self._back(indices, ix)
+
+    topK = topk
+
     def cumsumb(self, m, n, k, A, offA, exclusive, reverse, B, offB):
         b = self._f(B)
         _wrap(oracle.cumsumb, m, n, k, self._f(A), offA, exclusive, reverse, A.dtype() == dtypes.float32, b, offB)

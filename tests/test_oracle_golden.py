@@ -163,3 +163,17 @@ def test_gemm_rows_variants_bit_identical():
     oracle.gemm_rows(0, m, n, k, 0.7, A, k, B, n, 1.3, c2, n)
     oracle.gemm_rows_fast(0, m, n, k, 0.7, A, k, B, n, 1.3, c3, n)
     assert np.array_equal(c1, c2) and np.array_equal(c1, c3)
+
+
+def test_topk_known_answers(oracle_service):
+    """LinearAlgebraTest.php:8027-8115 (testTopKNormal10) through the oracle service"""
+    from rindow_math_matrix_b200 import LinearAlgebra
+    la = LinearAlgebra(oracle_service)
+    x = la.array(np.arange(10, dtype=np.float32))
+    values, indices = la.topK(x, k=3)
+    assert values.toArray() == [9, 8, 7] and indices.toArray() == [9, 8, 7]
+    values, indices = la.topK(x)
+    assert values.toArray() == [9] and indices.toArray() == [9]
+    x = la.array(np.arange(30, dtype=np.float32).reshape(3, 10))
+    values, indices = la.topK(x, k=3)
+    assert values.toArray() == [[9, 8, 7], [19, 18, 17], [29, 28, 27]] and indices.toArray() == [[9, 8, 7]] * 3
