@@ -13,6 +13,7 @@
 namespace {
 
 constexpr int TK_WARPS = 4;
+constexpr int TK_UNROLL = 8;
 
 template <typename T>
 __device__ __forceinline__ void tk_heapify(int size, T* heap, int* idx, int parent)      // topkMinHeapify, :940-983
@@ -45,21 +46,29 @@ topk_kernel(int64_t m, int n, int k, int sorted, const T* __restrict__ input, T*
             for (int i = k / 2 - 1; i >= 0; --i) tk_heapify<T>(k, heap, idx, i);
         }
         __syncwarp();
-        for (int base = k; base < n; base += 32) {
-            const int i = base + lane;
-            const T v = i < n ? arr[i] : (T)0;
-            const T top = heap[0];
-            unsigned vote = __ballot_sync(0xffffffffu, i < n && v > top);
-            while (vote) {                                                 // rare after the heap has warmed up
-                const int src = __ffs(vote) - 1;
-                vote &= vote - 1;
-                const T cv = __shfl_sync(0xffffffffu, v, src);
-                if (lane == 0 && cv > heap[0]) {
-                    heap[0] = cv;
-                    idx[0] = base + src;
-                    tk_heapify<T>(k, heap, idx, 0);
+        for (int base = k; base < n; base += 32 * TK_UNROLL) {
+            T v[TK_UNROLL];                                                    // TK_UNROLL coalesced loads in flight per lane
+#pragma unroll
+            for (int u = 0; u < TK_UNROLL; u++) {
+                const int i = base + u * 32 + lane;
+                v[u] = i < n ? arr[i] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < TK_UNROLL; u++) {                              // groups offered in index order
+                const int i = base + u * 32 + lane;
+                const T top = heap[0];
+                unsigned vote = __ballot_sync(0xffffffffu, i < n && v[u] > top);
+                while (vote) {                                                 // rare after the heap has warmed up
+                    const int src = __ffs(vote) - 1;
+                    vote &= vote - 1;
+                    const T cv = __shfl_sync(0xffffffffu, v[u], src);
+                    if (lane == 0 && cv > heap[0]) {
+                        heap[0] = cv;
+                        idx[0] = base + u * 32 + src;
+                        tk_heapify<T>(k, heap, idx, 0);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         if (sorted && lane == 0) {                                         // :1015-1022

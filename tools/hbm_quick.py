@@ -76,6 +76,12 @@ def main():
         timed("cumsum_rows_4032", lambda i: math.cumsumb(m, 4032, 1, As[i], 0, False, False, Y2, 0), 2 * m * 4032 * 4)
         timed("cumsum_cols", lambda i: math.cumsumb(1, m, n, As[i], 0, False, False, Y2, 0), 2 * m * n * 4)
         timed("cumsum_flat", lambda i: math.cumsumb(1, m * n, 1, As[i], 0, False, False, Y2, 0), 2 * m * n * 4)
+    if not want or "topk" in want:
+        # top-8 of each row of [1024, 32768] f32 (the 128 MB operand): bytes = the input read once
+        TV, TI = CudaBuffer(1024 * 8, f32), CudaBuffer(1024 * 8, dtypes.int32)
+        timed("topk", lambda i: math.topk(1024, 32768, As[i], 0, 8, True, TV, 0, TI, 0), m * n * 4)
+        TV2, TI2 = CudaBuffer(8192 * 8, f32), CudaBuffer(8192 * 8, dtypes.int32)
+        timed("topk_8192x4096", lambda i: math.topk(8192, 4096, As[i], 0, 8, True, TV2, 0, TI2, 0), m * n * 4)
     if not want or "masking" in want:
         # attention-score padding mask: scores [64 batch, 16 heads x 128 queries, 256 keys] f32 (128 MB); per batch the keys
         # past a random length are masked out (set to -1e9): only those elements are written
