@@ -30,6 +30,8 @@ for op in $OPS; do
       im2col2d) K="-k regex:im2col2d"; C=1;;
       im2col3d) K="-k regex:im2col3d"; C=1;;
       cumsum_rows) K="-k regex:scan_rows_vec"; C=1;;
+      cumsum_cols) K="-k regex:scan_cols"; C=2;;
+      topk) K="-k regex:topk"; C=1;;
     esac
     timeout 600 ncu --set full --clock-control none --import-source on $K -s $S -c $C \
       -o gpurun_out/prof/$op -f python tools/profile_ops.py $op 3 > gpurun_out/prof/$op.ncu.log 2>&1

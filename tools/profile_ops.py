@@ -3,7 +3,7 @@
 (profiles/README.md lists the exact ncu invocations).  Usage: profile_ops.py OP [REPS]
 OP in: sgemm_tf32 sgemm_tf32x3 sgemm_simt add multiply reduce_sum reduce_sum_axis0 reduce_max
        reduce_argmax softmax im2col2d im2col3d conv_gemm conv2d_fused axpy copy transpose gemv gemv_trans
-       maximum exp astype transpose_nd gather scatter_add sum cumsum_rows"""
+       maximum exp astype transpose_nd gather scatter_add sum cumsum_rows cumsum_cols topk"""
 import os
 import sys
 
@@ -72,6 +72,14 @@ def main():
         c3d = CudaBuffer(n3, f32, zero=False)
         fn = lambda: math.im2col3d(False, vol, 0, b3 * d3 * h3 * w3 * c3, b3, d3, h3, w3, c3, 3, 3, 3, 1, 1, 1, False, False,
                                    1, 1, 1, False, c3d, 0, n3)
+    elif op == "cumsum_cols":
+        m, n = 8192, 4096
+        A, Y = rnd(m * n), CudaBuffer(m * n, f32, zero=False)
+        fn = lambda: math.cumsumb(1, m, n, A, 0, False, False, Y, 0)
+    elif op == "topk":
+        A = rnd(8192 * 4096)
+        TV, TI = CudaBuffer(8192 * 8, f32), CudaBuffer(8192 * 8, dtypes.int32)
+        fn = lambda: math.topk(8192, 4096, A, 0, 8, True, TV, 0, TI, 0)
     elif op == "cumsum_rows":
         m, n = 8192, 4096
         A, Y = rnd(m * n), CudaBuffer(m * n, f32, zero=False)
