@@ -118,6 +118,20 @@ int rb200_buffer_fill(int dtype, void* dptr, int64_t off, int64_t n, const void*
 /* pinned host staging memory for the host-indexable mirror of an LV_ADVANCED buffer */
 int rb200_host_alloc(int64_t bytes, void** hptr);
 int rb200_host_free(void* hptr);
+/* Stream-ordered completion markers: the counterpart of the OpenCL event lists the reference's device
+ * variants take as trailing ($events, $waitEvents) arguments (OpenCLMath.php:1851-1859,
+ * LinearAlgebraCL.php:1867-1875) and of DeviceBuffer::read/write's blocking flag (NDArrayCL.php:261-270).
+ * record = "everything queued on the library stream so far"; synchronize blocks the host until then;
+ * query sets *done to 1/0 without blocking; wait makes the library stream wait for an event recorded
+ * earlier (possibly while another stream was adopted with rb200_set_stream).  The host mirror of a
+ * CudaBuffer records one after its asynchronous upload and waits on it before the host writes the
+ * pinned memory again. */
+int rb200_event_create(void** event);
+int rb200_event_destroy(void* event);
+int rb200_event_record(void* event);
+int rb200_event_synchronize(void* event);
+int rb200_event_query(void* event, int* done);
+int rb200_event_wait(void* event);
 
 /* ---- BLAS: replaces PhpBlas::gemm (src/Drivers/MatlibPHP/PhpBlas.php:849-948) ------- */
 /* C[m,n] = alpha * op(A)[m,k] * op(B)[k,n] (+ beta * C iff beta != 0; C is not read when
@@ -311,6 +325,15 @@ int rb200_reduce_max(int dtype, int64_t m, int64_t n, int64_t k,
  * sticks): PhpMath::math_imax (:114-130).  index_dtype: RB200_INT32 or RB200_INT64. */
 int rb200_reduce_argmax(int dtype, int64_t m, int64_t n, int64_t k,
                         const void* A, int64_t offA, int index_dtype, void* B, int64_t offB);
+/* Arg-max of one STRIPE of a reduced axis that is sharded over ranks: writes, per
+ * output, a 16-byte record {double value; int64 index} (index local to the stripe) into `records` (16-byte aligned,
+ * `off_records` counted in records) for the cross-rank merge of math_imax (PhpMath.php:114-130).  The stripe that
+ * starts at global position 0 follows math_imax itself, its never-displaced NaN at position 0 reported as +INF (the
+ * merge cannot tell the two apart); every other stripe continues a running maximum, where `$value > $max` is false
+ * for a NaN wherever it sits, so NaNs are skipped and an all-NaN stripe reports (-INF, INT32_MAX).  Merging the
+ * records in rank order with a strict `>` reproduces the single-buffer result bit for bit. */
+int rb200_reduce_argmax_partial(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA,
+                                int stripe_starts_at_global_0, void* records, int64_t off_records);
 
 /* ---- softmax: replaces PhpMath::softmax (PhpMath.php:1645-1670); in place, row stride ldA */
 int rb200_softmax(int dtype, int64_t m, int64_t n, void* A, int64_t offA, int64_t ldA);

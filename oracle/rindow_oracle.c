@@ -447,7 +447,12 @@ int ro_im2col2d(int reverse,
     return RO_OK;
 }
 
-/* PhpMath::gatherb, PhpMath.php:1209-1260.  f32: math_add stores every partial sum into a float32 buffer. */
+/* PhpMath::gatherb, PhpMath.php:1209-1260.
+ * f32 = 0 is the reference's semantics: a PhpBuffer is an SplFixedArray of PHP doubles, so partial sums are never
+ * rounded.  f32 != 0 is a float32 STORAGE MODEL (every stored partial sum rounded to float32,
+ * what any driver with real float buffers does, the reference's own C/OpenCL drivers included); it is NOT PhpBuffer
+ * behaviour.  The GPU tests assert both: bit-exact against the storage model and within terms*eps32*sum|terms| of
+ * the unrounded result (tests/test_gpu_gatherb.py, test_gpu_scan.py). */
 int ro_gatherb(int reverse, int add_mode, int f32, int64_t batches, int64_t m, int64_t n, int64_t k, int64_t len, int64_t numClass,
                double *A, int64_t countA, int64_t offA, const double *X, int64_t countX, int64_t offX,
                double *B, int64_t countB, int64_t offB)
@@ -609,8 +614,9 @@ int ro_topk(int64_t m, int64_t n, const double *input, int64_t countIn, int64_t 
     return RO_OK;
 }
 
-/* PhpMath::cumsumb, PhpMath.php:1861-1904.  Every stored partial sum is read back by the next step, so a float32
- * buffer rounds at every step (f32 != 0). */
+/* PhpMath::cumsumb, PhpMath.php:1861-1904.  f32 = 0: the reference's semantics (PhpBuffer holds doubles, nothing is
+ * rounded between steps).  f32 != 0: float32 storage model -- every stored partial sum is read back by the next step,
+ * so a real float32 buffer rounds at every step (see ro_gatherb). */
 int ro_cumsumb(int64_t m, int64_t n, int64_t k, const double *A, int64_t countA, int64_t offA, int exclusive, int reverse,
                int f32, double *B, int64_t countB, int64_t offB)
 {

@@ -48,6 +48,12 @@ SIGNATURES = {
     "rb200_buffer_fill": (i32, [i32, vp, i64, i64, vp]),
     "rb200_host_alloc": (i32, [i64, ctypes.POINTER(vp)]),
     "rb200_host_free": (i32, [vp]),
+    "rb200_event_create": (i32, [ctypes.POINTER(vp)]),
+    "rb200_event_destroy": (i32, [vp]),
+    "rb200_event_record": (i32, [vp]),
+    "rb200_event_synchronize": (i32, [vp]),
+    "rb200_event_query": (i32, [vp, ctypes.POINTER(i32)]),
+    "rb200_event_wait": (i32, [vp]),
     "rb200_sgemm": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32]),
     "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
     "rb200_sgemm_streamed": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, vp, i64, i64, vp, vp, i64, i64,
@@ -86,6 +92,7 @@ SIGNATURES = {
     "rb200_reduce_sum": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
     "rb200_reduce_max": (i32, [i32, i64, i64, i64, vp, i64, vp, i64]),
     "rb200_reduce_argmax": (i32, [i32, i64, i64, i64, vp, i64, i32, vp, i64]),
+    "rb200_reduce_argmax_partial": (i32, [i32, i64, i64, i64, vp, i64, i32, vp, i64]),
     "rb200_softmax": (i32, [i32, i64, i64, vp, i64, i64]),
     "rb200_conv2d_forward": (i32, [i32, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, i64, i64,
                                    vp, i64, i64, vp, i64, vp, i64, i32]),

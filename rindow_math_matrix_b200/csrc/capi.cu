@@ -30,7 +30,8 @@ int ensure_workspace(size_t bytes)
     Context& c = ctx();
     if (bytes <= c.workspace_bytes) return RB200_OK;
     if (c.workspace) {
-        RB_CUDA(cudaStreamSynchronize(c.stream));
+        // kernels of a previously adopted stream (rb200_set_stream) may still use the old block
+        RB_CUDA(cudaDeviceSynchronize());
         RB_CUDA(cudaFree(c.workspace));
         c.workspace = nullptr;
         c.workspace_bytes = 0;
@@ -46,7 +47,7 @@ int ensure_counters(int64_t n, int** out)
     Context& c = ctx();
     if ((size_t)n > c.counters_len) {
         if (c.counters) {
-            RB_CUDA(cudaStreamSynchronize(c.stream));
+            RB_CUDA(cudaDeviceSynchronize());
             RB_CUDA(cudaFree(c.counters));
             c.counters = nullptr;
             c.counters_len = 0;
@@ -127,6 +128,8 @@ int rb200_shutdown(void)
     c.counters_len = 0;
     if (c.pinned_scalar) cudaFreeHost(c.pinned_scalar);
     c.pinned_scalar = nullptr;
+    if (c.switch_event) cudaEventDestroy(c.switch_event);
+    c.switch_event = nullptr;
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     c.own_stream = nullptr;
     c.stream = nullptr;
@@ -153,8 +156,15 @@ int rb200_set_stream(void* cuda_stream)
     rb200::Context& c = ctx();
     // cudaStream_t 0 (legacy default stream) is a valid caller stream; NULL restores ours
     // only when the caller passes the sentinel (void*)-1.
-    if (cuda_stream == (void*)(intptr_t)-1) c.stream = c.own_stream;
-    else c.stream = (cudaStream_t)cuda_stream;
+    cudaStream_t next = (cuda_stream == (void*)(intptr_t)-1) ? c.own_stream : (cudaStream_t)cuda_stream;
+    if (next != c.stream) {
+        // the workspace, the arrival counters and the pinned scalar slot are shared by every launch: work queued on
+        // the new stream is ordered after everything queued on the old one
+        if (!c.switch_event) RB_CUDA(cudaEventCreateWithFlags(&c.switch_event, cudaEventDisableTiming));
+        RB_CUDA(cudaEventRecord(c.switch_event, c.stream));
+        RB_CUDA(cudaStreamWaitEvent(next, c.switch_event, 0));
+        c.stream = next;
+    }
     return RB200_OK;
 }
 
@@ -312,6 +322,60 @@ int rb200_host_free(void* hptr)
     RB_REQUIRE_INIT();
     if (!hptr) return RB200_OK;
     RB_CUDA(cudaFreeHost(hptr));
+    return RB200_OK;
+}
+
+/* ---- events ------------------------------------------------------------------------------------- */
+
+int rb200_event_create(void** event)
+{
+    RB_REQUIRE_INIT();
+    if (!event) RB_INVALID("event is NULL");
+    cudaEvent_t e = nullptr;
+    RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *event = (void*)e;
+    return RB200_OK;
+}
+
+int rb200_event_destroy(void* event)
+{
+    RB_REQUIRE_INIT();
+    if (!event) return RB200_OK;
+    RB_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return RB200_OK;
+}
+
+int rb200_event_record(void* event)
+{
+    RB_REQUIRE_INIT();
+    if (!event) RB_INVALID("event is NULL");
+    RB_CUDA(cudaEventRecord((cudaEvent_t)event, ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_event_synchronize(void* event)
+{
+    RB_REQUIRE_INIT();
+    if (!event) RB_INVALID("event is NULL");
+    RB_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return RB200_OK;
+}
+
+int rb200_event_query(void* event, int* done)
+{
+    RB_REQUIRE_INIT();
+    if (!event || !done) RB_INVALID("bad event_query arguments");
+    cudaError_t e = cudaEventQuery((cudaEvent_t)event);
+    if (e == cudaSuccess) { *done = 1; return RB200_OK; }
+    if (e == cudaErrorNotReady) { cudaGetLastError(); *done = 0; return RB200_OK; }
+    return rb200::cuda_fail(e, "cudaEventQuery", __FILE__, __LINE__);
+}
+
+int rb200_event_wait(void* event)
+{
+    RB_REQUIRE_INIT();
+    if (!event) RB_INVALID("event is NULL");
+    RB_CUDA(cudaStreamWaitEvent(ctx().stream, (cudaEvent_t)event, 0));
     return RB200_OK;
 }
 

@@ -18,6 +18,7 @@ struct Context {
     size_t      total_mem = 0;
     cudaStream_t own_stream = nullptr;   // created by rb200_init
     cudaStream_t stream = nullptr;       // the stream kernels are launched on
+    cudaEvent_t  switch_event = nullptr; // orders a newly adopted stream after the previous one (rb200_set_stream)
     int         default_gemm_mode = RB200_GEMM_TF32X3;
     int64_t     launches = 0;
     const char* last_gemm_path = "none";

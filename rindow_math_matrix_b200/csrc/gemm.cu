@@ -312,6 +312,9 @@ int rb200_sgemm_streamed(int order, int transA, int transB, int64_t m, int64_t n
         }
     }
     if (hC) RB_CUDA(cudaStreamSynchronize(st.out));      // the host may read hC as soon as the call returns
+    // the caller may overwrite hA / hB (its pinned mirrors) as soon as the call returns: the uploads must have left
+    // host memory by then.  Only the copies are waited for -- the multiplies of the last stripes stay asynchronous.
+    else if (hA || hB || upload_c) RB_CUDA(cudaStreamSynchronize(st.in));
     return RB200_OK;
 }
 

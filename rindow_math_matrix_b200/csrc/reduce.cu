@@ -77,6 +77,35 @@ template <typename T> struct ArgMaxOp {
     }
 };
 
+// Arg-max of ONE STRIPE of a row-sharded axis (rb200_reduce_argmax_partial): the record (value, index) a rank
+// contributes to the cross-rank merge.  GLOBAL0 = the stripe starts at global position 0: math_imax's rule as above,
+// with the never-displaced NaN at position 0 reported as +INF (nothing is greater than either, and ties keep the lower
+// index, so the merge cannot tell them apart).  Otherwise the stripe continues a running maximum that is never NaN
+// there (PhpMath.php:121-127: `if($value>$max)` is false for a NaN on either side), so NaNs are skipped wherever they
+// sit; an all-NaN stripe reports (-INF, INT_MAX), which never wins.
+template <typename T, bool GLOBAL0> struct ArgMaxPairOp {
+    using Acc = typename ArgMaxOp<T>::Acc;
+    static __device__ __forceinline__ Acc identity() { return ArgMaxOp<T>::identity(); }
+    static __device__ __forceinline__ void accum(Acc& a, T v, int idx)
+    {
+        if (GLOBAL0) { ArgMaxOp<T>::accum(a, v, idx); return; }
+        if (v != v) return;
+        if (v > a.v || (v == a.v && idx < a.idx)) { a.v = v; a.idx = idx; }
+    }
+    static __device__ __forceinline__ Acc combine(const Acc& a, const Acc& b) { return ArgMaxOp<T>::combine(a, b); }
+    static __device__ __forceinline__ Acc shfl(const Acc& a, int mask) { return ArgMaxOp<T>::shfl(a, mask); }
+    static __device__ __forceinline__ void store(void* B, int64_t pos, const Acc& a, int)
+    {
+        // 16-byte records {double value; int64 index}
+        int4 rec;
+        const double v = (double)a.v;
+        const long long i = (long long)a.idx;
+        memcpy(&rec.x, &v, 8);
+        memcpy(&rec.z, &i, 8);
+        reinterpret_cast<int4*>(B)[pos] = rec;
+    }
+};
+
 template <typename Op> __device__ __forceinline__ typename Op::Acc warp_reduce(typename Op::Acc a)
 {
 #pragma unroll
@@ -492,6 +521,27 @@ int rb200_reduce_argmax(int dtype, int64_t m, int64_t n, int64_t k, const void* 
     switch (dtype) {
         case RB200_FLOAT32: return reduce_launch<float, ArgMaxOp<float>>(m, n, k, A, offA, B, offB, idx64);
         case RB200_FLOAT64: return reduce_launch<double, ArgMaxOp<double>>(m, n, k, A, offA, B, offB, idx64);
+        default: RB_UNSUPPORTED("reduceArgMax: unsupported dtype %d", dtype);
+    }
+}
+
+int rb200_reduce_argmax_partial(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA,
+                                int stripe_starts_at_global_0, void* records, int64_t off_records)
+{
+    int rc = reduce_check(m, n, k, A, offA, records, off_records);
+    if (rc != RB200_OK) return rc;
+    if ((reinterpret_cast<uintptr_t>(records) & 15) != 0) RB_INVALID("records must be 16-byte aligned");
+    // B is indexed in records by the kernels: offB counts records
+    if (stripe_starts_at_global_0) {
+        switch (dtype) {
+            case RB200_FLOAT32: return reduce_launch<float, ArgMaxPairOp<float, true>>(m, n, k, A, offA, records, off_records, 0);
+            case RB200_FLOAT64: return reduce_launch<double, ArgMaxPairOp<double, true>>(m, n, k, A, offA, records, off_records, 0);
+            default: RB_UNSUPPORTED("reduceArgMax: unsupported dtype %d", dtype);
+        }
+    }
+    switch (dtype) {
+        case RB200_FLOAT32: return reduce_launch<float, ArgMaxPairOp<float, false>>(m, n, k, A, offA, records, off_records, 0);
+        case RB200_FLOAT64: return reduce_launch<double, ArgMaxPairOp<double, false>>(m, n, k, A, offA, records, off_records, 0);
         default: RB_UNSUPPORTED("reduceArgMax: unsupported dtype %d", dtype);
     }
 }

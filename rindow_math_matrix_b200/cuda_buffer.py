@@ -46,6 +46,8 @@ class CudaBuffer:
         self._host_dirty = False     # host mirror newer than device
         self._dev_dirty = False      # device newer than host mirror
         self._single_reads = 0       # element reads served by one-element d2h since the last device write
+        self._upload_event = None    # recorded behind the asynchronous h2d of the mirror (flush)
+        self._upload_pending = False # that copy may still be reading the pinned mirror
         if zero and self._size:
             z = np.zeros(1, self._np)
             _capi.check(self._lib.rb200_buffer_fill(self._dtype, self._dptr, 0, self._size, z.ctypes.data))
@@ -57,6 +59,11 @@ class CudaBuffer:
             if getattr(self, "_dptr", None):
                 self._lib.rb200_buffer_free(self._dptr)
                 self._dptr = None
+            if getattr(self, "_upload_event", None):
+                if self._upload_pending:
+                    self._lib.rb200_event_synchronize(self._upload_event)
+                self._lib.rb200_event_destroy(self._upload_event)
+                self._upload_event = None
             if getattr(self, "_hptr", None):
                 self._lib.rb200_host_free(self._hptr)
                 self._hptr = None
@@ -158,6 +165,7 @@ class CudaBuffer:
         """The pinned host mirror, current.  Callers that write through it must call
         mark_host_written()."""
         self._ensure_mirror()
+        self._wait_upload()
         if self._dev_dirty:
             if self._host_dirty:
                 raise RuntimeException("CudaBuffer: host and device copies diverged")
@@ -166,7 +174,17 @@ class CudaBuffer:
             self._dev_dirty = False
         return self._host
 
+    def _wait_upload(self) -> None:
+        """flush() queues the h2d of the pinned mirror asynchronously, possibly behind long kernels: the host may
+        not modify the mirror before that copy has read it (X[0]=a; op(X); X[0]=b must show `a` to op)."""
+        if self._upload_pending:
+            _capi.check(self._lib.rb200_event_synchronize(self._upload_event))
+            self._upload_pending = False
+
     def mark_host_written(self) -> None:
+        """The caller wrote through host(); it must have obtained host() AFTER the last kernel touched the buffer
+        (host() waits for a queued upload of the mirror)."""
+        self._wait_upload()
         self._host_dirty = True
 
     # state the streamed (host-operand) GEMM needs: it moves the data itself, pipelined with the multiply
@@ -196,6 +214,12 @@ class CudaBuffer:
         if self._host_dirty:
             if self._bytes:
                 _capi.check(self._lib.rb200_buffer_h2d_async(self._dptr, 0, self._hptr, self._bytes))
+                if self._upload_event is None:
+                    ev = ctypes.c_void_p()
+                    _capi.check(self._lib.rb200_event_create(ctypes.byref(ev)))
+                    self._upload_event = ev.value
+                _capi.check(self._lib.rb200_event_record(self._upload_event))
+                self._upload_pending = True
             self._host_dirty = False
 
     def device_ptr(self) -> int:
@@ -223,6 +247,15 @@ class CudaBuffer:
         if self._host_dirty:
             self.flush()
         _capi.check(self._lib.rb200_buffer_d2h(out.ctypes.data, self._dptr, 0, self._bytes)) if self._bytes else None
+        return out
+
+    def read_range(self, offset: int, n: int) -> np.ndarray:
+        """Elements [offset, offset + n) as a fresh host array (one d2h of exactly those bytes)."""
+        if offset < 0 or n < 0 or offset + n > self._size:
+            raise InvalidArgumentException("range does not fit in buffer")
+        out = np.empty(n, self._np)
+        if n:
+            self.read(out, n * self._np.itemsize, offset * self._np.itemsize)
         return out
 
     @property

@@ -403,6 +403,21 @@ class CudaMath:
         _capi.check(self._lib.rb200_reduce_argmax(A.dtype(), m, n, k, A.device_ptr(), offsetA,
                                                   B.dtype(), B.device_ptr_rw(), offsetB))
 
+    def reduceArgMaxPartial(self, m, n, k, A, offsetA, global0: bool, records, offsetRecords) -> None:
+        """(value, index) records of one stripe of a row-sharded reduced axis, for sharding.merge_argmax
+        (rb200_reduce_argmax_partial).  `records` is an int64 buffer holding two words per output: the bits of the
+        double value, then the stripe-local index."""
+        _cuda("A", A)
+        _cuda("records", records)
+        if m < 1 or n < 1 or k < 1:
+            raise InvalidArgumentException("m, n and k must be greater than 0.")
+        if offsetA < 0 or offsetA + m * n * k > len(A):
+            raise InvalidArgumentException("Matrix specification too large for bufferA.")
+        if records.dtype() != dtypes.int64 or offsetRecords < 0 or 2 * (offsetRecords + m * k) > len(records):
+            raise InvalidArgumentException("records must be an int64 buffer of two words per output")
+        _capi.check(self._lib.rb200_reduce_argmax_partial(A.dtype(), m, n, k, A.device_ptr(), offsetA,
+                                                          1 if global0 else 0, records.device_ptr_rw(), offsetRecords))
+
     # ---- softmax (PhpMath.php:1645-1670) ----------------------------------------------------------------
     def softmax(self, m, n, A, offsetA, ldA) -> None:
         if offsetA + (m - 1) * ldA + (n - 1) >= len(A):

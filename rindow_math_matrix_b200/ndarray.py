@@ -92,7 +92,9 @@ class NDArray:
 
     def to_numpy(self) -> np.ndarray:
         n = self.size()
-        if hasattr(self._buffer, "to_numpy"):
+        if hasattr(self._buffer, "read_range"):                  # device buffer: only the view's bytes travel
+            flat = self._buffer.read_range(self._offset, n)
+        elif hasattr(self._buffer, "to_numpy"):
             flat = self._buffer.to_numpy()[self._offset:self._offset + n]
         else:
             flat = np.array([self._buffer[self._offset + i] for i in range(n)])
@@ -134,6 +136,11 @@ class NDArray:
                 raise OutOfRangeException("Index is out of range")
             self._buffer[self._offset + i] = value
             return
+        if len(self._shape) == 1:
+            # `$a[$i] = $ndarray` on a rank-1 array: the reference only takes scalars there (NDArrayPhp.php:462-474)
+            if i < 0 or i >= self._shape[0]:
+                raise OutOfRangeException("Index is out of range")
+            raise InvalidArgumentException("Must be scalar type")
         sub = self[i]
         src = value.to_numpy() if isinstance(value, NDArray) else np.asarray(value)
         if tuple(src.shape) != tuple(sub._shape):

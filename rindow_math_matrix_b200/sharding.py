@@ -155,27 +155,68 @@ def merge_max(partial: torch.Tensor, group=None) -> torch.Tensor:
     """NaN-sticky maximum over ranks of per-rank partial maxima."""
     stack = _gather_stack(partial, group)                  # [world, k]
     has_nan = torch.isnan(stack).any(dim=0)
-    mx = torch.nan_to_num(stack, nan=float("-inf")).max(dim=0).values
+    # (not nan_to_num: it would also clamp +/-INF to the largest finite value)
+    mx = torch.where(torch.isnan(stack), torch.full_like(stack, float("-inf")), stack).max(dim=0).values
     return torch.where(has_nan, torch.full_like(mx, float("nan")), mx)
 
 
 def merge_argmax(values: torch.Tensor, indices: torch.Tensor, row_offset: int, group=None) -> torch.Tensor:
-    """Global arg-max along the sharded axis from per-rank (max value, local index) pairs.
-    `values` must be the value AT the local argmax (NaN if the local winner is a NaN in local
-    position 0).  Rule (math_imax, PhpMath.php:114-130): first strict maximum wins, ties -> lowest
-    global index; a NaN only wins when it sits at GLOBAL position 0."""
+    """Global arg-max along the sharded axis from per-rank (value, stripe-local index) records as
+    rb200_reduce_argmax_partial / CudaMath.reduceArgMaxPartial writes them: the rank that owns global position 0
+    follows math_imax (PhpMath.php:114-130) with its never-displaced NaN at position 0 reported as +INF; every other
+    rank skips NaNs (`$value > $max` is false for a NaN wherever it sits) and reports (-INF, INT32_MAX) for an all-NaN
+    stripe.  Merged in rank order with a strict `>`: first strict maximum wins, ties -> lowest global index, a NaN
+    only wins at GLOBAL position 0 -- bit-identical to the single-buffer result, NaNs included."""
     gidx = indices.to(torch.int64) + int(row_offset)
     vals = _gather_stack(values, group)                    # [world, k]
     idxs = _gather_stack(gidx, group)
-    world = vals.shape[0]
     best_v, best_i = vals[0].clone(), idxs[0].clone()
-    # rank 0 holds global position 0: if its winner is NaN it is NaN-at-0 and is never displaced
-    locked = torch.isnan(best_v)
-    for r in range(1, world):
-        v, i = vals[r], idxs[r]
-        better = (v > best_v) & ~locked                   # NaN compares false: never wins later
-        # a later rank's NaN-at-local-0 is an ordinary (losing) NaN globally, but the values behind it
-        # on that rank were never compared: callers pass nan_free_values when that matters
-        best_v = torch.where(better, v, best_v)
-        best_i = torch.where(better, i, best_i)
+    for r in range(1, vals.shape[0]):
+        better = vals[r] > best_v                          # strict: ties stay with the lower rank = lower index
+        best_v = torch.where(better, vals[r], best_v)
+        best_i = torch.where(better, idxs[r], best_i)
     return best_i
+
+
+def split_records(records: torch.Tensor, outputs: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values float64 [outputs], indices int64 [outputs]) views of the int64 record buffer
+    reduceArgMaxPartial fills (two words per output: the bits of the double value, the index)."""
+    rec = records[: 2 * outputs].view(outputs, 2)
+    return rec[:, 0].contiguous().view(torch.float64), rec[:, 1].contiguous()
+
+
+class ShardedRows:
+    """A [total_rows, k] matrix row-sharded over the ranks of `group`: this rank holds rows
+    [start, start + rows) in a driver Buffer.  reduce*(axis=0) run the single-GPU kernel on the stripe
+    (math.reduceSum / reduceMax / reduceArgMaxPartial with (m, n, k) = (1, rows, k)) and finish with ONE small
+    exchange of [k]-sized partials: all-reduce for the sum, gathered partials
+    merged in rank order for max / argmax.  Every rank returns the full [k] result as a torch tensor on the
+    partials' device.  `to_tensor(buffer, n, torch_dtype)` views a driver buffer as a tensor (CUDA: zero-copy
+    through __cuda_array_interface__; the gloo tests pass a numpy-backed stand-in)."""
+
+    def __init__(self, math, buffer, total_rows: int, k: int, dtype: int, new_buffer, to_tensor=None, group=None):
+        self.math, self.buffer, self.total_rows, self.k, self.dtype = math, buffer, int(total_rows), int(k), dtype
+        self.group, self.new_buffer = group, new_buffer
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.start, self.rows = row_range(self.total_rows, self.world, self.rank)
+        self.to_tensor = to_tensor or (lambda buf, n, tdt: tensor_of(buf)[:n])
+        if self.rows < 1:
+            raise ValueError("every rank needs at least one row of the sharded axis")
+
+    def reduceSum(self) -> torch.Tensor:
+        part = self.new_buffer(self.k, self.dtype)
+        self.math.reduceSum(1, self.rows, self.k, self.buffer, 0, part, 0)
+        return merge_sum(self.to_tensor(part, self.k, None), self.group)
+
+    def reduceMax(self) -> torch.Tensor:
+        part = self.new_buffer(self.k, self.dtype)
+        self.math.reduceMax(1, self.rows, self.k, self.buffer, 0, part, 0)
+        return merge_max(self.to_tensor(part, self.k, None), self.group)
+
+    def reduceArgMax(self) -> torch.Tensor:
+        from . import dtypes
+        rec = self.new_buffer(2 * self.k, dtypes.int64)
+        self.math.reduceArgMaxPartial(1, self.rows, self.k, self.buffer, 0, self.start == 0, rec, 0)
+        vals, idxs = split_records(self.to_tensor(rec, 2 * self.k, torch.int64), self.k)
+        return merge_argmax(vals, idxs, self.start, self.group)

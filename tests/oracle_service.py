@@ -133,6 +133,34 @@ class OracleMath:
     def reduceArgMax(self, m, n, k, A, offA, B, offB):
         _wrap(oracle.reduce_argmax, m, n, k, A.f64(), offA, B.data, offB)
 
+    def reduceArgMaxPartial(self, m, n, k, A, offA, global0, records, offRecords):
+        """The stripe record of CudaMath.reduceArgMaxPartial, restated from math_imax (PhpMath.php:114-130): the
+        stripe at global position 0 IS math_imax (value read back at the winning index, a NaN there as +INF); any
+        other stripe continues the loop `if($value > $max)` from a running maximum, i.e. from -INF with NaNs never
+        taken.  Pure-Python loop: small cases only."""
+        a = A.f64()[offA:offA + m * n * k].reshape(m, n, k)
+        vals = np.empty((m, k))
+        idxs = np.empty((m, k), np.int64)
+        if global0:
+            tmp = np.zeros(m * k, np.int64)
+            _wrap(oracle.reduce_argmax, m, n, k, A.f64(), offA, tmp, 0)
+            idxs[:] = tmp.reshape(m, k)
+            for i in range(m):
+                for j in range(k):
+                    v = a[i, idxs[i, j], j]
+                    vals[i, j] = np.inf if np.isnan(v) else v
+        else:
+            for i in range(m):
+                for j in range(k):
+                    mx, ix = -np.inf, np.iinfo(np.int32).max
+                    for t in range(n):
+                        if a[i, t, j] > mx:
+                            mx, ix = a[i, t, j], t
+                    vals[i, j], idxs[i, j] = mx, ix
+        rec = records.data[2 * offRecords:2 * (offRecords + m * k)].reshape(m * k, 2)
+        rec[:, 0] = vals.reshape(-1).view(np.int64)
+        rec[:, 1] = idxs.reshape(-1)
+
     def softmax(self, m, n, A, offA, ldA):
         _wrap(oracle.softmax, m, n, A.f64(), offA, ldA)
 

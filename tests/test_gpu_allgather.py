@@ -6,6 +6,7 @@ torchrun (--gpus 2).  pytest -m gpu"""
 import numpy as np
 import pytest
 
+import oracle
 import rindow_math_matrix_b200 as rb
 from rindow_math_matrix_b200 import BLAS, CudaBuffer, _capi, dtypes
 
@@ -44,7 +45,10 @@ def test_sgemm_allgather_local_peers(total, start, rows, n, k, mode, path, n_pee
     blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, rows, n, k, 1.0, A, 0, k, B, 0, n, 0.0, C2, start * n, n)
     want = C2.to_numpy().reshape(total, n)
     assert np.array_equal(got, want)
-    ref = a.astype(np.float64) @ b.astype(np.float64)
+    # the oracle (PhpBlas::gemm's loop, double, k ascending) on the stripe
+    ref = np.zeros(rows * n)
+    oracle.gemm_rows_fast(0, rows, n, k, 1.0, oracle.as_buffer(a), k, oracle.as_buffer(b), n, 0.0, ref, n)
+    ref = ref.reshape(rows, n)
     tol = 2e-3 if mode == rb.GEMM_TF32 else 1e-4
     assert np.max(np.abs(got[start:start + rows] - ref)) < tol * np.max(np.abs(ref))
     assert np.all(got[:start] == 7.0) and np.all(got[start + rows:] == 7.0)      # rows outside the stripe untouched

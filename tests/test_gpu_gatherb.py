@@ -57,7 +57,18 @@ def test_gathernd_random_vs_oracle(m, n, k, dims, reverse, addMode, dt, idt, cud
     cuda_service.math().gathernd(reverse, addMode, m, n, k, depth, dims, A, offA, X, 0, B, offB)
     ao, bo = a.astype(np.float64), b.astype(np.float64)
     oracle.gathernd(reverse, addMode, dt == dtypes.float32, m, n, k, depth, dims, ao, offA, x.astype(np.float64), bo, offB)
-    assert np.array_equal(A.to_numpy().astype(np.float64), ao)
+    assert np.array_equal(A.to_numpy().astype(np.float64), ao)      # float32 STORAGE model of the oracle: bit-exact
+    if dt == dtypes.float32 and addMode:
+        # ... and against the reference's own semantics (a PhpBuffer holds doubles, nothing is rounded between the
+        # steps): within terms * eps32 * sum|terms| per element, the sum of magnitudes taken from
+        # the same unrounded oracle run on |a|, |b|
+        au, bu = a.astype(np.float64), b.astype(np.float64)
+        oracle.gathernd(reverse, addMode, False, m, n, k, depth, dims, au, offA, x.astype(np.float64), bu, offB)
+        am, bm = np.abs(a).astype(np.float64), np.abs(b).astype(np.float64)
+        oracle.gathernd(reverse, addMode, False, m, n, k, depth, dims, am, offA, x.astype(np.float64), bm, offB)
+        eps = float(np.finfo(np.float32).eps)
+        assert np.all(np.abs(A.to_numpy().astype(np.float64) - au) <= (n + 1) * eps * am + 1e-300)
+        assert np.all(np.abs(B.to_numpy().astype(np.float64) - bu) <= (n + 1) * eps * bm + 1e-300)
     assert np.array_equal(B.to_numpy().astype(np.float64), bo)
 
 
@@ -101,9 +112,19 @@ def test_gatherb_random_vs_oracle(batches, m, n, k, len_, numClass, reverse, add
     ao, bo = a.astype(np.float64), b.astype(np.float64)
     oracle.gatherb(reverse, addMode, dt == dtypes.float32, batches, m, n, k, len_, numClass, ao, offA, x.astype(np.float64), offX,
                    bo, offB)
-    assert np.array_equal(A.to_numpy().astype(np.float64), ao)
+    assert np.array_equal(A.to_numpy().astype(np.float64), ao)      # float32 STORAGE model of the oracle: bit-exact
     assert np.array_equal(B.to_numpy().astype(np.float64), bo)
     assert np.array_equal(X.to_numpy(), x)
+    if dt == dtypes.float32 and addMode:
+        # the reference's own semantics (PhpBuffer holds doubles: no rounding between the steps):
+        # within terms * eps32 * sum|terms| per element
+        au, bu = a.astype(np.float64), b.astype(np.float64)
+        oracle.gatherb(reverse, addMode, False, batches, m, n, k, len_, numClass, au, offA, x.astype(np.float64), offX, bu, offB)
+        am, bm = np.abs(a).astype(np.float64), np.abs(b).astype(np.float64)
+        oracle.gatherb(reverse, addMode, False, batches, m, n, k, len_, numClass, am, offA, x.astype(np.float64), offX, bm, offB)
+        eps = float(np.finfo(np.float32).eps)
+        assert np.all(np.abs(A.to_numpy().astype(np.float64) - au) <= (n + 1) * eps * am + 1e-300)
+        assert np.all(np.abs(B.to_numpy().astype(np.float64) - bu) <= (n + 1) * eps * bm + 1e-300)
 
 
 @pytest.mark.parametrize("dt", [dtypes.bool_, dtypes.uint8, dtypes.int16, dtypes.uint64])

@@ -617,6 +617,59 @@ def test_gemm_sweep_sizes_sampled(N, mode, cuda_service):
     assert np.max(np.abs(got.sum(axis=0) - colsum)) < GEMM_TOL[mode] * N * np.max(np.abs(ref))
 
 
+_LARGE = {}
+
+
+def _large_gemm_case(N, nrows):
+    """Operands of the quoted C5 sizes (seeds of SURVEY.md section 8(d)) with the oracle's rows of C for a fixed
+    sample of rows (ro_gemm_rows_interleaved: the reference's per-element k order, double), computed once per
+    size on all host cores and shared by the three arithmetic modes."""
+    if N not in _LARGE:
+        from concurrent.futures import ThreadPoolExecutor
+        _LARGE.clear()                                            # one size resident at a time (16384: ~6 GiB)
+        lg = int(np.log2(N))
+        Ah = np.random.default_rng(5000 + lg).uniform(-1, 1, N * N).astype(np.float32)
+        Bh = np.random.default_rng(5100 + lg).uniform(-1, 1, N * N).astype(np.float32)
+        rows = sorted(np.random.default_rng(9).choice(N, nrows, replace=False).tolist())
+        a_rows = oracle.as_buffer(Ah.reshape(N, N)[rows])        # [nrows, N] compact
+        bo = oracle.as_buffer(Bh)
+        co = np.zeros(nrows * N)
+        threads = min(nrows, os.cpu_count() or 1)
+
+        def work(i):
+            oracle.gemm_rows_fast(i, 1, N, N, 1.0, a_rows, N, bo, N, 0.0, co, N)
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(nrows)))
+        # 1^T C = (1^T A) B in double, B converted in row chunks
+        a_colsum = Ah.reshape(N, N).sum(axis=0, dtype=np.float64)
+        colsum = np.zeros(N)
+        for r0 in range(0, N, 2048):
+            colsum += a_colsum[r0:r0 + 2048] @ bo[r0 * N:(r0 + 2048) * N].reshape(-1, N)
+        del bo
+        _LARGE[N] = (Ah, Bh, rows, co.reshape(nrows, N), colsum)
+    return _LARGE[N]
+
+
+@pytest.mark.parametrize("N,mode", [(8192, rb.GEMM_TF32), (8192, rb.GEMM_TF32X3), (8192, rb.GEMM_FP32_SIMT),
+                                    (16384, rb.GEMM_TF32), (16384, rb.GEMM_TF32X3), (16384, rb.GEMM_FP32_SIMT)])
+def test_gemm_quoted_sizes_sampled(N, mode, cuda_service):
+    """The sizes the bench numbers are quoted on (BASELINE config C5: 8192^3 and 16384^3), every arithmetic mode:
+    64 (8192) / 32 (16384) full rows of C against the oracle within the mode's stated bound, and the column-sum
+    identity over ALL of C (a wrong tile anywhere shows up there)."""
+    Ah, Bh, rows, ref, colsum = _large_gemm_case(N, 64 if N <= 8192 else 32)
+    blas = cuda_service.blas()
+    blas.setGemmMode(mode)
+    A, B, C = buf(Ah), buf(Bh), CudaBuffer(N * N, dtypes.float32)
+    blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, N, N, N, 1.0, A, 0, N, B, 0, N, 0.0, C, 0, N)
+    got = C.to_numpy().reshape(N, N)
+    del A, B, C
+    err = np.max(np.abs(got[rows].astype(np.float64) - ref)) / np.max(np.abs(ref))
+    assert err < GEMM_TOL[mode], (err, rb._capi.last_gemm_path())
+    cs = got.sum(axis=0, dtype=np.float64)
+    assert np.max(np.abs(cs - colsum)) < GEMM_TOL[mode] * N * np.max(np.abs(ref))
+    cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+
+
 def test_cross_256_config(cuda_service):
     """BASELINE config C1: MatrixOperator::cross sgemm 256x256 (alpha=1, beta=1 on a zeroed C)."""
     mo = MatrixOperator(cuda_service)
@@ -781,6 +834,43 @@ def test_conv_config_im2col_gemm(cuda_service):
     for r in rows:
         oracle.gemm_rows_fast(int(r), 1, f, 27, 1.0, ao, 27, bo, f, 0.0, co, f)
     assert isclose_ref(out.to_numpy().reshape(M, f)[rows], co.reshape(M, f)[rows])
+
+
+def test_conv_config_full_batch(cuda_service):
+    """BASELINE config C4 at its FULL size (batch 64, 224x224x3, 64 3x3 filters, valid padding), both routes:
+    im2col2d (cols bit-exact against the index identity) + gemm, and the fused conv2d kernel.  512 sampled output
+    rows against the oracle's gemm loop within the reference isclose bound (and the 3xTF32 bound), plus the
+    column sums of the WHOLE output: 1^T out = (1^T cols) W."""
+    b, h, w, c, f = 64, 224, 224, 3, 64
+    la = LinearAlgebra(cuda_service)
+    cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+    img = np.random.default_rng(4001).uniform(0, 1, (b, h, w, c)).astype(np.float32)
+    W = (np.random.default_rng(4002).standard_normal((27, f)) * 0.1).astype(np.float32)
+    images = la.array(img)
+    cols = la.im2col(images, filterSize=[3, 3])
+    assert cols.shape() == [b, 222, 222, 3, 3, 3]
+    win = np.lib.stride_tricks.sliding_window_view(img, (3, 3), axis=(1, 2)).transpose(0, 1, 2, 4, 5, 3)
+    got_cols = cols.to_numpy()
+    for b0 in range(0, b, 8):                                   # chunked: the view materialises on comparison
+        assert np.array_equal(got_cols[b0:b0 + 8], win[b0:b0 + 8]), b0
+    M = b * 222 * 222
+    out2 = la.gemm(cols.reshape([M, 27]), la.array(W))
+    path2 = rb._capi.last_gemm_path()
+    out1 = la.conv2d(images, la.array(W.reshape(3, 3, c, f)), fused=True)
+    path1 = rb._capi.last_gemm_path()
+    assert path1.endswith("_tmem_conv"), path1
+    rows = np.sort(np.random.default_rng(1).choice(M, 512, replace=False))
+    a_rows = oracle.as_buffer(got_cols.reshape(M, 27)[rows])
+    ref = np.zeros(512 * f)
+    oracle.gemm_rows_fast(0, 512, f, 27, 1.0, a_rows, 27, oracle.as_buffer(W), f, 0.0, ref, f)
+    ref = ref.reshape(512, f)
+    col_total = got_cols.reshape(M, 27).sum(axis=0, dtype=np.float64) @ W.astype(np.float64)
+    for name, out, path in (("im2col+gemm", out2, path2), ("fused", out1, path1)):
+        got = out.to_numpy().reshape(M, f)
+        assert isclose_ref(got[rows], ref), (name, path)
+        assert np.max(np.abs(got[rows] - ref)) / np.max(np.abs(ref)) < GEMM_TOL[rb.GEMM_TF32X3], (name, path)
+        cs = got.sum(axis=0, dtype=np.float64)
+        assert np.max(np.abs(cs - col_total)) < GEMM_TOL[rb.GEMM_TF32X3] * M * np.max(np.abs(ref)), (name, path)
 
 
 CONV_CASES = [  # (b, h, w, c, kh, kw, filters, strides, padding, dilation, bias)

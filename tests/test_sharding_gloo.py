@@ -71,15 +71,41 @@ def _worker(rank, world, port, q):
         assert np.allclose(got_s[ok], gs[ok], rtol=1e-12, atol=1e-12), "merge_sum"
         got_m = sharding.merge_max(torch.from_numpy(pm.copy())).numpy()
         assert np.array_equal(got_m, gm, equal_nan=True), "merge_max (NaN sticky)"
-        vals_at = xs[pi, np.arange(11)].astype(np.float64)
-        got_i = sharding.merge_argmax(torch.from_numpy(vals_at), torch.from_numpy(pi.copy()), start).numpy()
-        # columns whose NaN sits at a local-but-not-global position 0 are outside merge_argmax's contract
-        col_ok = np.ones(11, bool)
-        if world > 1:
-            s1, _ = sharding.row_range(M, world, 1)
-            col_ok &= ~np.isnan(X[s1])
-        assert np.array_equal(got_i[col_ok], gi[col_ok]), ("merge_argmax", got_i, gi)
-        assert got_i[7] == 0                                      # NaN at global 0 sticks
+        # argmax: the stripe records of reduceArgMaxPartial, merged in rank order.  NaNs everywhere that matters:
+        # mid-column on either rank, at global position 0, at LOCAL position 0 of rank 1 (a plain NaN globally: the
+        # hole round 1 documented), a whole stripe of NaN, +/-INF, ties across the rank boundary
+        from oracle_service import OracleBuffer, OracleMath
+        s1, _ = sharding.row_range(M, world, 1)
+        X[s1, 2] = np.nan                      # NaN at local position 0 of rank 1, real maximum behind it
+        X[s1 + 3, 2] = 5.0
+        X[s1:, 6] = np.nan                     # rank 1's whole stripe of column 6 is NaN
+        X[s1, 8] = np.nan                      # NaN at local 0 of rank 1 AND the global maximum sits on rank 0
+        X[2, 8] = 7.0
+        X[4, 9] = np.inf
+        X[s1 + 1, 9] = np.inf                  # +INF tie across the boundary -> lowest global index
+        X[:, 10] = -np.inf                     # all -INF
+        X[1, 1] = X[s1 + 2, 1] = 3.0           # finite tie across the boundary
+        xs = X[start:start + rows]
+        Xo = oracle.as_buffer(X)
+        oracle.reduce_sum(1, M, 11, Xo, 0, gs, 0)
+        oracle.reduce_max(1, M, 11, Xo, 0, gm, 0, sticky=True)
+        oracle.reduce_argmax(1, M, 11, Xo, 0, gi, 0)
+        f64 = 13
+        stripe = OracleBuffer(rows * 11, f64).from_numpy(xs.reshape(-1))
+        om = OracleMath()
+        om.sticky_max = True                   # the accelerated-path rule the CUDA kernels follow
+        sr = sharding.ShardedRows(om, stripe, M, 11, f64, new_buffer=OracleBuffer,
+                                  to_tensor=lambda buf, n, tdt: torch.from_numpy(buf.data[:n]))
+        assert (sr.start, sr.rows) == (start, rows)
+        got_i = sr.reduceArgMax().numpy()
+        assert np.array_equal(got_i, gi), ("ShardedRows.reduceArgMax", got_i, gi)
+        assert got_i[7] == 0 and got_i[2] == s1 + 3 and got_i[8] == 2 and got_i[9] == 4 and got_i[10] == 0
+        got_m = sr.reduceMax().numpy()
+        assert np.array_equal(got_m, gm, equal_nan=True), ("ShardedRows.reduceMax", got_m, gm)
+        assert got_m[9] == np.inf                                  # +INF survives the merge (not clamped)
+        got_s = sr.reduceSum().numpy()
+        ok = np.isfinite(gs)
+        assert np.allclose(got_s[ok], gs[ok], rtol=1e-12, atol=1e-12), "ShardedRows.reduceSum"
         # --- PeerRows (fused gemm + gather): handle exchange and stripe addressing, with fake handles
         pr = sharding.PeerRows(None, M, N, export=lambda: bytes([rank + 1]) * 64, open_handle=lambda h: 1000 + h[0])
         assert pr.world == world and pr.rank == rank
