@@ -6,14 +6,18 @@
   torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU
 
 Metric (BASELINE.json): "sgemm TFLOP/s; add/reduceSum HBM GB/s at 1/2/4/8 B200 vs PHP CPU path".
-The step is one float32 GEMM C = A*B (NoTrans/NoTrans, alpha=1, beta=0) of M=N=K=8192 per GPU
-(config C5; with N GPUs the matrix A/C is row-sharded: rank g owns rows [g*8192,(g+1)*8192) of an
-(8192*N) x 8192 problem, B replicated, no data-path collective -> weak scaling), issued through the
-reference-facing plugin interface (service.blas().gemm(...) with the PhpBlas signature) down the C
-ABI.  `value` times device-resident operands; `e2e` times the same call with HOST buffers (pinned
-host mirror -> h2d -> kernel -> d2h inside the timed region).  The HBM-bound configs (C2/C3/C4:
-add, multiply, reduceSum/Max/ArgMax, softmax, im2col2d) are reported in "hbm_ops" of the same JSON
-line with their own roofline fractions; other GEMM modes in "gemm_modes".
+The step is ONE float32 GEMM C = A*B (NoTrans/NoTrans, alpha=1, beta=0) of M=N=K=16384 (config C5, the largest size
+of the sweep; 3 GiB of operands) issued through the reference-facing plugin interface (service.blas().gemm(...) with
+the PhpBlas signature) down the C ABI.  With N GPUs the SAME problem is row-sharded (strong scaling): rank g owns
+rows [g*16384/N, (g+1)*16384/N) of A and C, B is replicated, and every rank ends the step holding the full C -- the
+stripes are stored into all ranks' copies from the GEMM epilogue over NVLink (NVLS multicast when available) while
+the remaining tiles multiply, followed by one barrier ("with_gather.compute_only" is the same step with C left
+sharded, "with_gather.nccl" the unfused library all-gather for context).  `value` times device-resident operands;
+`e2e` times the same job with HOST buffers (per rank: its A stripe and its 1/N slice of B from pinned memory -> h2d,
+B's slices all-gathered over NVLink, transfer-pipelined multiply, C stripe d2h) inside the timed region.  The
+HBM-bound configs (C2/C3/C4: add, multiply, reduceSum/Max/ArgMax, softmax, im2col2d) are reported in "hbm_ops" of
+the same JSON line with their own roofline fractions and CPU baselines; other GEMM modes (3xTF32 parity mode, FFMA,
+float64) in "gemm_modes"; the C5 size sweep in "sgemm_sweep".
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
@@ -78,14 +82,17 @@ def ncu_traffic(kernel, n):
 
 def workload_config(n, world, mode_name):
     return {
-        "workload": "sgemm M=N=K=%d per GPU (BASELINE config C5), NoTrans/NoTrans, alpha=1, beta=0" % n,
+        "workload": "sgemm M=N=K=%d (BASELINE config C5, the largest size of the sweep), NoTrans/NoTrans, alpha=1, "
+                    "beta=0; ONE problem row-sharded over the GPUs" % n,
         "gemm_mode": mode_name,
         "tolerance": {"tf32": "max|err| < 2e-3*max|C| (1xTF32; outside the reference isclose rtol 1e-4 by design)",
                       "tf32x3": "max|err| < 1e-4*max|C| (reference isclose bound)",
                       "fp32_simt": "max|err| < 1e-4*max|C| (reference isclose bound)"}[mode_name],
-        "global_shape": [n * world, n, n],
-        "parallelism": "row-sharded A/C over %d GPU(s), B replicated, no data-path collective" % world,
-        "l2": "inputs exceed L2: %d MiB working set per GPU vs 126 MB L2" % (3 * n * n * 4 >> 20),
+        "global_shape": [n, n, n],
+        "parallelism": ("A and C row-sharded over %d GPU(s) (%d rows each), B replicated; every rank ends with the full C "
+                        "(stripes pushed from the GEMM epilogue over NVLink, one barrier)" % (world, n // world))
+                       if world > 1 else "1 GPU",
+        "l2": "inputs exceed L2: A stripe %d MiB + B %d MiB per GPU vs 126 MB L2" % (n * n * 4 // world >> 20, n * n * 4 >> 20),
     }
 
 
@@ -98,6 +105,7 @@ class ClockSampler:
 
     def __init__(self, local_rank):
         self.samples, self.reasons, self.ok = [], set(), False
+        self.active = False             # only the timed regions are sampled (set by timed())
         self._stop = threading.Event()
         self.sm_max = None
         try:
@@ -120,6 +128,9 @@ class ClockSampler:
     def _run(self):
         nv = self.nv
         while not self._stop.is_set():
+            if not self.active:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -210,8 +221,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(n, world, "fp32_simt") | {"gemm_mode": "reference (double)"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(n, world, args.mode),
+        "arithmetic": "reference (double accumulation in the reference's loop order)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -234,6 +246,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 driver has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from rindow_math_matrix_b200 import sharding
+    numa = sharding.bind_to_gpu_numa(local_rank)       # before any pinned allocation: mirrors land on the GPU's node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -249,6 +263,7 @@ def run_b200(args):
     blas, math = svc.blas(), svc.math()
     peaks = measured_peaks()
     mode = {"tf32": rb.GEMM_TF32, "tf32x3": rb.GEMM_TF32X3, "fp32_simt": rb.GEMM_FP32_SIMT}[args.mode]
+    sampler = ClockSampler(local_rank)
 
     def barrier():
         if world > 1:
@@ -262,227 +277,213 @@ def run_b200(args):
             return float(t.item())
         return ms
 
-    def timed(fn, steps, warmup):
+    per_rank = {}
+
+    def timed(fn, steps, warmup, tag=None):
         """W untimed calls, then exactly `steps` calls between two events on the launching stream,
-        barrier + synchronize on both sides, max over ranks.  Returns total ms."""
+        barrier + synchronize on both sides, max over ranks.  Returns total ms.  `tag` also records every
+        rank's own time (per_rank[tag], ms per step, rank order)."""
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 fn()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sampler.active = True
             e0.record(stream)
             for i in range(steps):
                 fn()
             e1.record(stream)
             barrier()
-        return max_over_ranks(e0.elapsed_time(e1))
+            sampler.active = False
+        mine = e0.elapsed_time(e1)
+        if tag is not None:
+            if world > 1:
+                t = torch.zeros(world, dtype=torch.float64, device="cuda")
+                t[rank] = mine / steps
+                dist.all_reduce(t)
+                per_rank[tag] = [float(x) for x in t.tolist()]
+            else:
+                per_rank[tag] = [mine / steps]
+        return max_over_ranks(mine)
 
-    # ---- operands (resident in HBM before the timed region) ----------------------------------------
+    # ---- the problem: ONE sgemm n^3, A and C row-sharded, B replicated; operands resident in HBM ---------------
     n = args.n
+    if n % world:
+        raise SystemExit("bench.py: --size must be divisible by the number of GPUs")
+    rows = n // world
     lg = int(np.log2(n))
-    Ah = np.random.default_rng(5000 + lg + 1000 * rank).uniform(-1, 1, n * n).astype(np.float32)
+    # rank r's stripe of A is drawn from its own seed (the global A is the concatenation), B from one seed everywhere
+    Ah = np.random.default_rng(5000 + lg + 1000 * rank).uniform(-1, 1, rows * n).astype(np.float32)
     Bh = np.random.default_rng(5100 + lg).uniform(-1, 1, n * n).astype(np.float32)
-    A = CudaBuffer(n * n, dtypes.float32, zero=False).from_numpy(Ah)
-    B = CudaBuffer(n * n, dtypes.float32, zero=False).from_numpy(Bh)
-    C = CudaBuffer(n * n, dtypes.float32)
+    blas.setGemmMode(mode)
+    job = sharding.RowShardedGemm(blas, n, n, n, gather=False)                 # C stays sharded: no collective
+    job.A.from_numpy(Ah)
+    job.B.from_numpy(Bh)
+    fused = None
+    fused_err = None
+    if world > 1:
+        try:
+            fused = sharding.RowShardedGemm(blas, n, n, n, gather=True, allow_multicast=not args.no_multicast,
+                                            operands=(job.A, job.B))           # same operands, C in symmetric memory
+        except Exception as e:                                                 # no peer access on this box
+            fused_err = "%s: %s" % (type(e).__name__, e)
+            log("fused gather unavailable:", fused_err)
     _capi.sync()
 
-    def gemm_step(m=mode):
-        blas.setGemmMode(m)
-        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A, 0, n, B, 0, n, 0.0, C, 0, n)
+    def compute_step():
+        blas.setGemmMode(mode)
+        job.run()
 
-    sampler = ClockSampler(local_rank)
+    def fused_step():
+        blas.setGemmMode(mode)
+        fused.run()
+
+    headline_step = fused_step if fused is not None else compute_step
     with sampler:
-        # keep the sampler running over a region long enough to see load clocks even for small K
         _capi.launch_count(reset=True)
-        t_pre = time.perf_counter()
-        total_ms = timed(gemm_step, args.steps, args.warmup)
-        launches = _capi.launch_count() - 0
-        warm_launches = launches * args.warmup // (args.steps + args.warmup)
-        gpu_launches = launches - warm_launches
-        while time.perf_counter() - t_pre < 0.25:       # pad with the same kernel so NVML sees load
-            timed(gemm_step, 5, 0)
-    gemm_path = _capi.last_gemm_path()
-    ms_per_step = total_ms / args.steps
-    flops_per_step = 2.0 * n * n * n
-    value = world * flops_per_step / (ms_per_step * 1e-3) / 1e12
-    tf32_peak = peaks["bf16_tflops"] / 2.0
-    achieved = flops_per_step / (ms_per_step * 1e-3) / 1e12
-    if args.mode == "tf32x3":
-        achieved_note = "algorithmic flops 2*N^3 (the kernel issues 3x that on the tensor pipe)"
-    else:
-        achieved_note = "algorithmic flops 2*N^3"
+        total_ms = timed(headline_step, args.steps, args.warmup, tag="headline")
+        launches = _capi.launch_count()
+        gpu_launches = launches - launches * args.warmup // (args.steps + args.warmup)
+        gemm_path = _capi.last_gemm_path()
+        ms_per_step = total_ms / args.steps
+        compute_only = None
+        if fused is not None:
+            c_ms = timed(compute_step, args.steps, args.warmup, tag="compute_only") / args.steps
+            compute_only = {"value": 2.0 * n ** 3 / (c_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": c_ms,
+                            "note": "same stripes, C left sharded: no data-path collective"}
+    clocks = sampler.summary()
+    flops_total = 2.0 * n * n * n
+    flops_rank = flops_total / world
+    value = flops_total / (ms_per_step * 1e-3) / 1e12
+    tf32_meas = tf32_measured_peak()
+    tf32_peak = tf32_meas["burst_tflops"] if tf32_meas else peaks["bf16_tflops"] / 2.0
+    achieved = flops_rank / (ms_per_step * 1e-3) / 1e12
+    achieved_note = ("algorithmic flops 2*N^3 (the kernel issues 3x that on the tensor pipe)" if args.mode == "tf32x3"
+                     else "algorithmic flops 2*N^3")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": ncu_traffic(gemm_path, n),
-                "kernel": gemm_path,
-                "peak_note": "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); %s"
-                             % (peaks["source"], achieved_note)}
+                "frac": achieved / tf32_peak, "traffic": ncu_traffic(gemm_path, n), "kernel": gemm_path,
+                "per": "GPU (this rank's stripe: 2*N^3/%d flop per launch)" % world,
+                "peak_note": ("TF32 dense peak MEASURED on a pool B200 (profiles/peaks_tf32_r02.json: cuBLAS TF32 8192^3 "
+                              "through torch, burst = best of 10); " if tf32_meas else
+                              "TF32 dense = 1/2 of the measured cuBLAS bf16 burst figure (%s); " % peaks["source"])
+                             + achieved_note,
+                "frac_of_half_bf16_burst": achieved / (peaks["bf16_tflops"] / 2.0)}
 
-    # the same kernel back to back for ~2 s: the power-capped figure, against the sustained cuBLAS bf16 peak / 2
+    # the same launch back to back for ~2 s: the power-capped figure, against the sustained cuBLAS peak
     if not args.quick:
         reps = max(args.steps, int(2000.0 / max(ms_per_step, 1e-3)))
-        sus_ms = timed(gemm_step, reps, 0) / reps
-        sus = flops_per_step / (sus_ms * 1e-3) / 1e12
-        roofline["sustained"] = {"achieved": sus, "peak": peaks["bf16_tflops_sustained"] / 2.0,
-                                 "frac": sus / (peaks["bf16_tflops_sustained"] / 2.0), "launches": reps,
+        sus_ms = timed(compute_step, reps, 0) / reps
+        sus = flops_rank / (sus_ms * 1e-3) / 1e12
+        sus_peak = tf32_meas["sustained_tflops"] if tf32_meas else peaks["bf16_tflops_sustained"] / 2.0
+        roofline["sustained"] = {"achieved": sus, "peak": sus_peak, "frac": sus / sus_peak, "launches": reps,
                                  "ms_per_launch": sus_ms,
-                                 "note": "same launch repeated for ~2 s (sw_power_cap engaged); peak = 1/2 of the "
-                                         "sustained cuBLAS bf16 figure"}
+                                 "note": "compute-only launch repeated for ~2 s (sw_power_cap engaged); peak = the "
+                                         "sustained cuBLAS TF32 figure measured the same way"}
 
-    # ---- multi-GPU: the same step followed by the NCCL all-gather of the C stripes (only when the caller
-    #      needs the full C on every rank; reported beside the collective-free number) --------------------
+    # ---- multi-GPU context: gemm + ncclAllGather of the stripes (library collective, not overlapped) ------------
     with_gather = None
     if world > 1:
-        from rindow_math_matrix_b200 import sharding
-        tC = sharding.tensor_of(C, (n, n))
-        with torch.cuda.stream(stream):
-            full = torch.empty((n * world, n), dtype=torch.float32, device="cuda")
-
-        def gather_step():
-            gemm_step()
-            dist.all_gather_into_tensor(full, tC)
-
-        g_steps = max(3, min(args.steps, 10))
-        g_ms = timed(gather_step, g_steps, 3) / g_steps
-        with_gather = {"value": world * flops_per_step / (g_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": g_ms,
-                       "allgather_bytes_per_rank": (world - 1) * n * n * 4,
-                       "note": "gemm + ncclAllGather of the row stripes of C, same stream (not overlapped)"}
-        # the fused form: every rank holds the full C; the GEMM epilogue stores each finished tile of this rank's
-        # stripe into all peers over NVLink (CUDA-IPC peer memory), so the gather overlaps the multiply.  A step
-        # ends with the process-group barrier that orders the ranks (inside the timed region).
-        try:
-            del full
-            Cfull = CudaBuffer(n * world * n, dtypes.float32)
-            pr = sharding.PeerRows(Cfull, n * world, n)
-            off = pr.stripe_offset()
-
-            def fused_step():
-                blas.setGemmMode(mode)
-                blas.gemmAllgather(BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A, 0, n, B, 0, n, 0.0, Cfull, off, n,
-                                   pr.peer_ptrs)
-                pr.arrive()
-
-            f_ms = timed(fused_step, g_steps, 3) / g_steps
-            # every rank checks rows it did NOT compute against its own stripe kernel on the owner's A (same seed)
+        with_gather = {"compute_only": compute_only}
+        if fused is not None:
+            # every rank checks rows it did NOT compute against a float64 product of the owner's A (same seeds)
             peer = (rank + 1) % world
-            Ap = np.random.default_rng(5000 + lg + 1000 * peer).uniform(-1, 1, n * n).astype(np.float32).reshape(n, n)
+            Ap = np.random.default_rng(5000 + lg + 1000 * peer).uniform(-1, 1, rows * n).astype(np.float32).reshape(rows, n)
             _capi.sync()
-            Cfull._dev_dirty = True
-            rows = Cfull.to_numpy().reshape(world * n, n)[peer * n:peer * n + 4]
+            got = fused.C.read_range((peer * rows) * n, 4 * n).reshape(4, n)
             ref = Ap[:4].astype(np.float64) @ Bh.reshape(n, n).astype(np.float64)
-            rel = float(np.max(np.abs(rows - ref)) / np.max(np.abs(ref)))
-            with_gather["fused"] = {"value": world * flops_per_step / (f_ms * 1e-3) / 1e12, "unit": UNIT,
-                                    "ms_per_step": f_ms, "kernel": _capi.last_gemm_path(),
-                                    "peer_rows_rel_err": rel,
-                                    "note": "rb200_sgemm_allgather: C stripe stored to all peers from the GEMM "
-                                            "epilogue (NVLink peer stores) + barrier; full C on every rank"}
-            pr.close()
-            del Cfull
-        except Exception as e:                           # peer access unavailable on this box: report, keep the line
-            with_gather["fused"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+            with_gather["fused"] = {
+                "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "kernel": gemm_path,
+                "multicast": bool(fused.multicast),
+                "peer_rows_rel_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
+                "nvlink_bytes_out_per_rank": rows * n * 4 * (1 if fused.multicast else world - 1),
+                "nvlink_bytes_in_per_rank": rows * n * 4 * (world - 1) + (rows * n * 4 if fused.multicast else 0),
+                "note": "the headline: C stripe stored into every rank's full C from the GEMM epilogue (%s) + "
+                        "symmetric-memory barrier" % ("NVLS multimem.st, one copy leaves the GPU" if fused.multicast
+                                                       else "unicast NVLink peer stores")}
+        else:
+            with_gather["fused"] = {"unavailable": fused_err}
+        try:
+            tC = sharding.tensor_of(job.C, (rows, n))
+            with torch.cuda.stream(stream):
+                full = torch.empty((n, n), dtype=torch.float32, device="cuda")
 
-    # ---- e2e: the same call with HOST buffers (pinned mirror -> h2d, kernel, d2h) --------------------
-    A.host(); B.host(); C.host()                      # create the pinned mirrors outside the timed region
+            def nccl_step():
+                compute_step()
+                dist.all_gather_into_tensor(full, tC)
+
+            g_steps = max(3, min(args.steps, 10))
+            g_ms = timed(nccl_step, g_steps, 3, tag="nccl_gather") / g_steps
+            with_gather["nccl"] = {"value": flops_total / (g_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": g_ms,
+                                   "allgather_bytes_per_rank": (world - 1) * rows * n * 4,
+                                   "note": "gemm + ncclAllGather of the row stripes of C, same stream (not overlapped); "
+                                           "library collective, for context"}
+            del full
+        except Exception as e:  # pragma: no cover
+            with_gather["nccl"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+    # ---- e2e: the same job with HOST operands (sharding.RowShardedGemm.run_from_host) ---------------------------
+    # each rank: its A stripe and its 1/world slice of B from pinned memory -> h2d; B slices all-gathered over NVLink;
+    # transfer-pipelined multiply; C stripe d2h into pinned memory (the step's result), all inside the timed region
+    hA, hB, hC = job.host_buffers()
+    hA[...] = Ah.reshape(rows, n)
+    hB[...] = Bh.reshape(n, n)[job.bstart:job.bstart + job.brows]
+    pcie = measure_pcie(_capi, job) if not args.quick else None
     _capi.sync()
 
     def e2e_step():
-        A.mark_host_written()                          # this step's inputs live in pinned host memory
-        B.mark_host_written()
-        gemm_step()                                    # flushes A,B (h2d) then launches
-        C.host()                                       # d2h read of the result (synchronises)
+        job.run_from_host()
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_ms = timed(e2e_step, e2e_steps, 3) / e2e_steps
-    e2e = {"value": world * flops_per_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
-           "h2d_bytes_per_step": 2 * n * n * 4, "d2h_bytes_per_step": n * n * 4, "ms_per_step": e2e_ms,
-           "steps": e2e_steps}
+    e2e_ms = timed(e2e_step, e2e_steps, 3, tag="e2e") / e2e_steps
+    h2d_b, d2h_b = int(hA.nbytes + hB.nbytes), int(hC.nbytes)
+    e2e = {"value": flops_total / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_b * world, "d2h_bytes_per_step": d2h_b * world,
+           "h2d_bytes_per_step_per_rank": h2d_b, "d2h_bytes_per_step_per_rank": d2h_b,
+           "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "sharding.RowShardedGemm.run_from_host (service.blas().gemm with host-filled buffers on 1 GPU)",
+           "note": "per rank: A stripe + 1/%d of B up, C stripe down; B's slices all-gathered over NVLink" % world}
+    if pcie:
+        bound_ms = max(h2d_b / (pcie["h2d_gbs"] * 1e6), d2h_b / (pcie["d2h_gbs"] * 1e6))
+        e2e["pcie"] = pcie
+        e2e["pcie_frac"] = bound_ms / e2e_ms
+        e2e["pcie_note"] = "max(h2d bytes / measured h2d GB/s, d2h bytes / measured d2h GB/s) / step time (this rank's link)"
+    got = hC[:2].astype(np.float64)
+    ref = Ah.reshape(rows, n)[:2].astype(np.float64) @ Bh.reshape(n, n).astype(np.float64)
+    e2e["rows_rel_err"] = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
 
-    # ---- other GEMM modes + cuBLAS TF32 for context ---------------------------------------------------
+    # ---- other GEMM modes (co-headlines: the parity mode 3xTF32, FFMA, float64) + cuBLAS for context ------------
     gemm_modes = {}
-    if not args.quick:
-        # a result buffer of its own: C now has a pinned mirror (the e2e leg read it from the host), and the
-        # driver brings such results back eagerly -- that d2h copy does not belong in a device-resident timing
-        Cm = CudaBuffer(n * n, dtypes.float32)
+    if not args.quick and world == 1:
+        gemm_modes = run_gemm_modes(args, svc, timed, n, job, achieved, ms_per_step, stream)
 
-        def mode_step(m):
-            blas.setGemmMode(m)
-            blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, A, 0, n, B, 0, n, 0.0, Cm, 0, n)
-
-        for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3), ("fp32_simt", rb.GEMM_FP32_SIMT)):
-            if name == args.mode:
-                gemm_modes[name] = {"tflops_per_gpu": achieved, "ms": ms_per_step}
-                continue
-            k = 3 if name == "fp32_simt" else max(3, min(args.steps, 10))
-            ms = timed(lambda mm=mm: mode_step(mm), k, 2) / k
-            gemm_modes[name] = {"tflops_per_gpu": flops_per_step / (ms * 1e-3) / 1e12, "ms": ms}
-        try:
-            ta = torch.as_tensor(A, device="cuda").view(n, n)
-            tb = torch.as_tensor(B, device="cuda").view(n, n)
-            torch.backends.cuda.matmul.allow_tf32 = True
-            with torch.cuda.stream(stream):
-                tc = torch.empty(n, n, device="cuda")
-            ms = timed(lambda: torch.matmul(ta, tb, out=tc), max(3, min(args.steps, 10)), 2) / max(3, min(args.steps, 10))
-            gemm_modes["cublas_tf32_via_torch"] = {"tflops_per_gpu": flops_per_step / (ms * 1e-3) / 1e12, "ms": ms,
-                                                   "note": "library GEMM for context, not on the product path"}
-        except Exception as e:  # pragma: no cover
-            log("cuBLAS TF32 context measurement failed:", e)
-
-    # ---- config C5: the sgemm sweep M=N=K in {1024 ... 16384} (tf32 and tf32x3), per GPU ------------------
+    # ---- config C5: the sgemm sweep M=N=K in {1024 ... 16384} per GPU ------------------------------------------
     sweep = {}
-    if not args.quick and not args.no_sweep:
-        for sz in (1024, 2048, 4096, 8192, 16384):
-            if sz == n:
-                sweep[str(sz)] = {"tf32_tflops": gemm_modes.get("tf32", {}).get("tflops_per_gpu"),
-                                  "tf32x3_tflops": gemm_modes.get("tf32x3", {}).get("tflops_per_gpu")}
-                continue
-            sa = CudaBuffer(sz * sz, dtypes.float32, zero=False)
-            sb = CudaBuffer(sz * sz, dtypes.float32, zero=False)
-            sc = CudaBuffer(sz * sz, dtypes.float32, zero=False)
-            # uniform(-1,1) operands like the headline run: constant operands toggle fewer bits, draw less
-            # power and clock ~35 % higher on this part -- such a number would not be comparable
-            reps = max(1, (sz * sz) // Ah.size)
-            sa.from_numpy(np.tile(Ah, reps)[:sz * sz] if reps > 1 else Ah[:sz * sz])
-            sb.from_numpy(np.tile(Bh, reps)[:sz * sz] if reps > 1 else Bh[:sz * sz])
-            row = {}
-            for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3)):
-                blas.setGemmMode(mm)
-                k = 20 if sz <= 4096 else 5
-
-                def sweep_step():
-                    blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, sz, sz, sz, 1.0, sa, 0, sz, sb, 0, sz, 0.0,
-                              sc, 0, sz)
-                ms = timed(sweep_step, k, 3) / k
-                row[name + "_tflops"] = 2.0 * sz ** 3 / (ms * 1e-3) / 1e12
-                row[name + "_ms"] = ms
-            sweep[str(sz)] = row
-            del sa, sb, sc
+    if not args.quick and not args.no_sweep and world == 1:
+        sweep = run_sweep(args, svc, timed, n, gemm_modes, Ah, Bh)
 
     # ---- HBM-bound configs (C2, C3, C4): rotating buffer sets defeat L2 --------------------------------
     hbm_ops = {}
     if not args.quick:
-        # the legs above held the chip at its power cap for seconds (16384^3 GEMMs); give it a moment so the HBM-bound
-        # kernels are not timed at the SM clock that load left behind (each op still gets its own warm-up launches)
         _capi.sync()
-        time.sleep(2.0)
+        time.sleep(2.0)              # the GEMM legs held the chip at its power cap: let the clock recover
         hbm_ops = run_hbm_ops(args, svc, timed, peaks, world, rank)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same GEMM with the oracle ---------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = 8
-        t, _, Cref = reference_gemm_sample(n, rows, 1, oracle_inputs(Ah), oracle_inputs(Bh))
-        gemm_step()
-        got = C.to_numpy().reshape(n, n)[:rows].astype(np.float64)
+        crows = 4
+        t, _, Cref = reference_gemm_sample(n, crows, 1, oracle_inputs(Ah), oracle_inputs(Bh))
+        compute_step()
+        got = job.C.read_range(0, crows * n).reshape(crows, n).astype(np.float64)
         err = float(np.max(np.abs(got - Cref)) / np.max(np.abs(Cref)))
         cpu_baseline = {
-            "value": 2.0 * rows * n * n / t / 1e12, "unit": UNIT, "cores": 1, "kind": "port",
+            "value": 2.0 * crows * n * n / t / 1e12, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d of %d rows of C (N=K=%d), reference loop order m,n,k in double, 1 thread (the reference "
                       "reports 1 thread, PhpBlas.php:49-54); C restatement of PhpBlas::gemm -- the PHP interpreter "
-                      "itself is not installable here and would be much slower" % (rows, n, n),
+                      "itself is not installable here and would be much slower" % (crows, n, n),
             "seconds": t, "gpu_vs_oracle_max_rel_err_on_sample": err,
         }
-        # numpy / OpenBLAS on all cores for context (BASELINE.md B1)
-        try:
+        try:                                            # numpy / OpenBLAS on all cores for context (BASELINE.md B1)
             k = 4096
             a = Ah[: k * k].reshape(k, k)
             b = Bh[: k * k].reshape(k, k)
@@ -496,60 +497,202 @@ def run_b200(args):
             pass
 
     # ---- config C1: MatrixOperator::cross 256x256 float32 (the reference's own CPU-runnable case): latency -----
-    cross_256 = None
-    if rank == 0 and not args.quick:
-        try:
-            from rindow_math_matrix_b200 import MatrixOperator
-            mo = MatrixOperator(svc)
-            blas.setGemmMode(rb.GEMM_AUTO)
-            a256 = np.random.default_rng(1234).uniform(-1, 1, (256, 256)).astype(np.float32)
-            b256 = np.random.default_rng(1235).uniform(-1, 1, (256, 256)).astype(np.float32)
-            A2, B2 = mo.array(a256), mo.array(b256)
-            reps = 50
-            with torch.cuda.stream(stream):
-                for _ in range(5):
-                    mo.cross(A2, B2)
-                _capi.sync()
-                t0 = time.perf_counter()
-                for _ in range(reps):
-                    out256 = mo.cross(A2, B2)
-                _capi.sync()
-                host_us = (time.perf_counter() - t0) / reps * 1e6
-            got = out256.to_numpy().astype(np.float64)
-            ref = a256.astype(np.float64) @ b256.astype(np.float64)
-            cross_256 = {"us_per_call": host_us, "calls": reps, "path": _capi.last_gemm_path(),
-                         "max_rel_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
-                         "note": "MatrixOperator.cross on device-resident operands, wall clock per call incl. the "
-                                 "zero-filled C allocation the reference does (MatrixOperator.php:479-503); launch bound"}
-            if world == 1 and not args.no_cpu_baseline:
-                import oracle
-                co = np.zeros(256 * 256)
-                t0 = time.perf_counter()
-                oracle.gemm_rows(0, 256, 256, 256, 1.0, oracle.as_buffer(a256), 256, oracle.as_buffer(b256), 256, 1.0, co, 256)
-                cross_256["oracle_port_us"] = (time.perf_counter() - t0) * 1e6
-        except Exception as e:  # pragma: no cover
-            cross_256 = {"unavailable": "%s: %s" % (type(e).__name__, e)}
-        gemm_step()                                    # leave the library in the headline mode
+    cross_256 = run_cross_256(args, svc, stream, world) if (rank == 0 and not args.quick) else None
 
-    log("rank %d/%d: %.2f ms/step, %.1f TFLOP/s aggregate" % (rank, world, ms_per_step, value))
+    # per-rank times and clocks (the max over ranks is what the headline uses)
+    rank_clocks = [clocks]
+    if world > 1:
+        rank_clocks = [None] * world
+        dist.all_gather_object(rank_clocks, clocks)
+    log("rank %d/%d: %.3f ms/step, %.1f TFLOP/s aggregate" % (rank, world, ms_per_step, value))
     if rank == 0:
+        co_headline = None
+        if gemm_modes.get("tf32x3"):
+            co_headline = {"metric": "sgemm TFLOP/s in the parity mode (3xTF32: inside the reference's isclose bound)",
+                           "value": gemm_modes["tf32x3"]["tflops_per_gpu"], "unit": UNIT,
+                           "ms_per_step": gemm_modes["tf32x3"]["ms"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"tf32": "tf32 (f32 in/out, f32 accumulate)",
-                                           "tf32x3": "3xtf32 (f32 in/out, f32 accumulate)",
-                                           "fp32_simt": "f32"}[args.mode],
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": {"tf32": "tf32 (f32 in/out, f32 accumulate)", "tf32x3": "3xtf32 (f32 in/out, f32 accumulate)",
+                      "fp32_simt": "f32"}[args.mode],
             "data": "synthetic", "config": workload_config(n, world, args.mode),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": sampler.summary(), "gemm_modes": gemm_modes, "sgemm_sweep": sweep, "hbm_ops": hbm_ops,
-            "with_gather": with_gather, "cross_256": cross_256,
-            "peaks": peaks,
+            "clocks": clocks, "co_headline_parity_mode": co_headline,
+            "per_rank": {"ms_per_step": per_rank, "clocks": rank_clocks, "numa_binding": numa},
+            "gemm_modes": gemm_modes, "sgemm_sweep": sweep, "hbm_ops": hbm_ops,
+            "with_gather": with_gather, "cross_256": cross_256, "peaks": peaks, "tf32_peak_measured": tf32_meas,
         }
         emit(line)
+    if fused is not None:
+        fused.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def tf32_measured_peak():
+    """cuBLAS TF32 8192^3 burst / sustained measured on a pool B200 with tools/peak_probe.py (committed copy)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "peaks_tf32_r02.json")) as f:
+            p = json.load(f)
+        return {"burst_tflops": float(p["tf32"]["burst_tflops"]), "sustained_tflops": float(p["tf32"]["sustained_tflops"]),
+                "fp32_tflops": float(p["fp32"]["burst_tflops"]), "fp64_tflops": float(p["fp64"]["burst_tflops"]),
+                "source": "profiles/peaks_tf32_r02.json (tools/peak_probe.py: cuBLAS through torch, CUDA events)"}
+    except Exception:
+        return None
+
+
+def measure_pcie(_capi, job):
+    """This rank's PCIe link: one large pinned h2d, one d2h, timed with the host clock around synchronous copies
+    (256 MiB each, best of 3)."""
+    import ctypes
+    lib = _capi.load()
+    dA, hA = job.A.raw_pointers()
+    nbytes = min(job.A.bytes(), 256 << 20)
+    out = {}
+    for name, fn, args_ in (("h2d_gbs", lib.rb200_buffer_h2d, (dA, 0, hA, nbytes)),
+                            ("d2h_gbs", lib.rb200_buffer_d2h, (hA, dA, 0, nbytes))):
+        best = 1e30
+        for _ in range(3):
+            _capi.sync()
+            t0 = time.perf_counter()
+            _capi.check(fn(*args_))
+            best = min(best, time.perf_counter() - t0)
+        out[name] = nbytes / best / 1e9
+    out["bytes"] = nbytes
+    return out
+
+
+def run_gemm_modes(args, svc, timed, n, job, achieved, ms_per_step, stream):
+    """The other arithmetic modes on the headline operands (1 GPU): 3xTF32 (the parity mode), FFMA float32, DFMA
+    float64 (north_star (a); its own random operands), plus cuBLAS TF32 / FP64 through torch for context."""
+    import torch
+    import rindow_math_matrix_b200 as rb
+    from rindow_math_matrix_b200 import BLAS, CudaBuffer, dtypes
+    blas = svc.blas()
+    out = {}
+    Cm = CudaBuffer(n * n, dtypes.float32)
+
+    def mode_step(m):
+        blas.setGemmMode(m)
+        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, n, n, n, 1.0, job.A, 0, n, job.B, 0, n, 0.0, Cm, 0, n)
+
+    for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3), ("fp32_simt", rb.GEMM_FP32_SIMT)):
+        if name == args.mode:
+            out[name] = {"tflops_per_gpu": achieved, "ms": ms_per_step}
+            continue
+        k = 2 if name == "fp32_simt" else max(3, min(args.steps, 10))
+        ms = timed(lambda mm=mm: mode_step(mm), k, 1 if name == "fp32_simt" else 2) / k
+        out[name] = {"tflops_per_gpu": 2.0 * n ** 3 / (ms * 1e-3) / 1e12, "ms": ms}
+    peak = tf32_measured_peak()
+    if peak:
+        out["fp32_simt"]["frac_of_cublas_fp32"] = out["fp32_simt"]["tflops_per_gpu"] / peak["fp32_tflops"]
+    del Cm
+    # float64 (rb200_dgemm) at 8192^3
+    nd = 8192
+    rng = np.random.default_rng(77)
+    Ad = CudaBuffer(nd * nd, dtypes.float64, zero=False).from_numpy(rng.uniform(-1, 1, nd * nd))
+    Bd = CudaBuffer(nd * nd, dtypes.float64, zero=False).from_numpy(rng.uniform(-1, 1, nd * nd))
+    Cd = CudaBuffer(nd * nd, dtypes.float64)
+
+    def f64_step():
+        blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, nd, nd, nd, 1.0, Ad, 0, nd, Bd, 0, nd, 0.0, Cd, 0, nd)
+    ms = timed(f64_step, 2, 1) / 2
+    from rindow_math_matrix_b200 import _capi
+    out["f64"] = {"tflops_per_gpu": 2.0 * nd ** 3 / (ms * 1e-3) / 1e12, "ms": ms, "n": nd, "path": _capi.last_gemm_path()}
+    if peak:
+        out["f64"]["frac_of_cublas_fp64"] = out["f64"]["tflops_per_gpu"] / peak["fp64_tflops"]
+    del Ad, Bd, Cd
+    try:
+        ta = torch.as_tensor(job.A, device="cuda").view(n, n)
+        tb = torch.as_tensor(job.B, device="cuda").view(n, n)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        with torch.cuda.stream(stream):
+            tc = torch.empty(n, n, device="cuda")
+        k = max(3, min(args.steps, 10))
+        ms = timed(lambda: torch.matmul(ta, tb, out=tc), k, 2) / k
+        out["cublas_tf32_via_torch"] = {"tflops_per_gpu": 2.0 * n ** 3 / (ms * 1e-3) / 1e12, "ms": ms,
+                                        "note": "library GEMM for context, not on the product path"}
+    except Exception as e:  # pragma: no cover
+        log("cuBLAS TF32 context measurement failed:", e)
+    blas.setGemmMode({"tf32": rb.GEMM_TF32, "tf32x3": rb.GEMM_TF32X3, "fp32_simt": rb.GEMM_FP32_SIMT}[args.mode])
+    return out
+
+
+def run_sweep(args, svc, timed, n, gemm_modes, Ah, Bh):
+    import rindow_math_matrix_b200 as rb
+    from rindow_math_matrix_b200 import BLAS, CudaBuffer, dtypes
+    blas = svc.blas()
+    sweep = {}
+    for sz in (1024, 2048, 4096, 8192, 16384):
+        if sz == n:
+            sweep[str(sz)] = {"tf32_tflops": gemm_modes.get("tf32", {}).get("tflops_per_gpu"),
+                              "tf32x3_tflops": gemm_modes.get("tf32x3", {}).get("tflops_per_gpu")}
+            continue
+        sa = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+        sb = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+        sc = CudaBuffer(sz * sz, dtypes.float32, zero=False)
+        # uniform(-1,1) operands like the headline run: constant operands toggle fewer bits, draw less
+        # power and clock ~35 % higher on this part -- such a number would not be comparable
+        sa.from_numpy(Ah[:sz * sz])
+        sb.from_numpy(Bh[:sz * sz])
+        row = {}
+        for name, mm in (("tf32", rb.GEMM_TF32), ("tf32x3", rb.GEMM_TF32X3)):
+            blas.setGemmMode(mm)
+            k = 20 if sz <= 4096 else 5
+
+            def sweep_step():
+                blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, sz, sz, sz, 1.0, sa, 0, sz, sb, 0, sz, 0.0,
+                          sc, 0, sz)
+            ms = timed(sweep_step, k, 3) / k
+            row[name + "_tflops"] = 2.0 * sz ** 3 / (ms * 1e-3) / 1e12
+            row[name + "_ms"] = ms
+        from rindow_math_matrix_b200 import _capi
+        row["path"] = _capi.last_gemm_path()
+        sweep[str(sz)] = row
+        del sa, sb, sc
+    return sweep
+
+
+def run_cross_256(args, svc, stream, world):
+    import torch
+    import rindow_math_matrix_b200 as rb
+    from rindow_math_matrix_b200 import _capi
+    try:
+        from rindow_math_matrix_b200 import MatrixOperator
+        mo = MatrixOperator(svc)
+        svc.blas().setGemmMode(rb.GEMM_AUTO)
+        a256 = np.random.default_rng(1234).uniform(-1, 1, (256, 256)).astype(np.float32)
+        b256 = np.random.default_rng(1235).uniform(-1, 1, (256, 256)).astype(np.float32)
+        A2, B2 = mo.array(a256), mo.array(b256)
+        reps = 50
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                mo.cross(A2, B2)
+            _capi.sync()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out256 = mo.cross(A2, B2)
+            _capi.sync()
+            host_us = (time.perf_counter() - t0) / reps * 1e6
+        got = out256.to_numpy().astype(np.float64)
+        ref = a256.astype(np.float64) @ b256.astype(np.float64)
+        cross_256 = {"us_per_call": host_us, "calls": reps, "path": _capi.last_gemm_path(),
+                     "max_rel_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
+                     "note": "MatrixOperator.cross on device-resident operands, wall clock per call incl. the "
+                             "zero-filled C allocation the reference does (MatrixOperator.php:479-503); launch bound"}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            co = np.zeros(256 * 256)
+            t0 = time.perf_counter()
+            oracle.gemm_rows(0, 256, 256, 256, 1.0, oracle.as_buffer(a256), 256, oracle.as_buffer(b256), 256, 1.0, co, 256)
+            cross_256["oracle_port_us"] = (time.perf_counter() - t0) * 1e6
+        return cross_256
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
 def oracle_inputs(a32):
@@ -710,7 +853,97 @@ def run_hbm_ops(args, svc, timed, peaks, world, rank):
     out["conv2d_fused"]["path"] = _capi.last_gemm_path()
     out["conv2d_fused"]["fused_kernel_used"] = bool(ok["v"])
     sets = sets_saved
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            hbm_cpu_baselines(out)
+        except Exception as e:  # pragma: no cover
+            log("hbm cpu baselines failed:", e)
+        # e2e of one HBM op through HOST buffers: A lives in its pinned mirror, add runs on the device, A is read back
+        try:
+            m, n = 8192, 4096
+            Ae = CudaBuffer(m * n, dtypes.float32, zero=False)
+            Ae.host()[:] = 0.5
+            Xe = CudaBuffer(n, dtypes.float32, zero=False).from_numpy(np.full(n, 0.25, np.float32))
+
+            def e2e_add(_i):
+                Ae.mark_host_written()
+                math.add(False, m, n, 1.0, Xe, 0, 1, Ae, 0, n)
+                Ae.host()
+            st = {"i": 0}
+            ms = timed(lambda: e2e_add(0), 6, 3) / 6
+            out["add"]["e2e"] = {"GB/s": (2 * m * n * 4 + n * 4) / (ms * 1e-3) / 1e9, "ms": ms,
+                                 "h2d_bytes_per_step": m * n * 4, "d2h_bytes_per_step": m * n * 4,
+                                 "note": "math().add with A current only in its pinned host mirror and read back from the "
+                                         "host afterwards (h2d + kernel + d2h inside the timed region): PCIe-bound"}
+        except Exception as e:  # pragma: no cover
+            log("add e2e failed:", e)
     return out
+
+
+def hbm_cpu_baselines(out):
+    """B0 (the oracle: C restatement of the PhpMath loops, double, 1 thread, bounded rows of the same workload) and B1
+    (numpy on the host, vectorised, full size) beside the HBM-bound ops of configs C2/C3/C4.
+    GB/s on the ALGORITHMIC float32 bytes of the sample, like the GPU rows, so the ratios are like for like."""
+    import oracle
+
+    def t_of(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    rng = np.random.default_rng(2001)
+    label = "C restatement of the reference PHP loop (double, 1 thread; the PHP interpreter is unavailable and slower)"
+    # C2 add / multiply: 1024 of 8192 rows
+    m, n = 1024, 4096
+    a = oracle.as_buffer(rng.uniform(-1, 1, m * n).astype(np.float32))
+    x = oracle.as_buffer(rng.uniform(0.9, 1.1, n).astype(np.float32))
+    full32 = rng.uniform(-1, 1, 8192 * 4096).astype(np.float32).reshape(8192, 4096)
+    x32 = x.astype(np.float32)
+    byt = 2 * m * n * 4 + n * 4
+    for name, fn, npfn in (("add", lambda: oracle.add(False, m, n, 1.0, x, 0, 1, a, 0, n), lambda: np.add(full32, x32, out=full32)),
+                           ("multiply", lambda: oracle.multiply(False, m, n, x, 0, 1, a, 0, n), lambda: np.multiply(full32, x32, out=full32))):
+        t = t_of(fn)
+        tn = t_of(npfn)
+        out[name]["cpu_baseline"] = {"value": byt / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                     "sample": "%d of 8192 rows of [8192,4096]; %s" % (m, label),
+                                     "numpy": {"value": (2 * 8192 * 4096 * 4 + n * 4) / tn / 1e9, "unit": "GB/s", "cores": 1,
+                                               "sample": "full size, in place, numpy vectorised (one thread)"}}
+    del full32
+    # C3 reductions / softmax: 4096 of 65536 rows
+    m, n = 4096, 1024
+    r32 = rng.uniform(-1, 1, m * n).astype(np.float32)
+    r = oracle.as_buffer(r32)
+    bsum, bidx = np.zeros(m), np.zeros(m, np.int64)
+    r2 = r32.reshape(m, n)
+    for name, fn, npfn, byt in (
+            ("reduceSum", lambda: oracle.reduce_sum(m, n, 1, r, 0, bsum, 0), lambda: r2.sum(axis=1), m * n * 4 + m * 4),
+            ("reduceMax", lambda: oracle.reduce_max(m, n, 1, r, 0, bsum, 0, sticky=True), lambda: r2.max(axis=1), m * n * 4 + m * 4),
+            ("reduceArgMax", lambda: oracle.reduce_argmax(m, n, 1, r, 0, bidx, 0), lambda: r2.argmax(axis=1), m * n * 4 + m * 4),
+            ("softmax", lambda: oracle.softmax(m, n, r.copy(), 0, n),
+             lambda: (lambda e: e / e.sum(axis=1, keepdims=True))(np.exp(r2 - r2.max(axis=1, keepdims=True))), 2 * m * n * 4)):
+        t = t_of(fn)
+        tn = t_of(npfn)
+        out[name]["cpu_baseline"] = {"value": byt / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                     "sample": "%d of 65536 rows of [65536,1024]; %s" % (m, label),
+                                     "numpy": {"value": byt / tn / 1e9, "unit": "GB/s", "cores": 1,
+                                               "sample": "the same %d rows, numpy vectorised (one thread)" % m}}
+    # C4 im2col2d: 2 of 64 images
+    b, h, w, c = 2, 224, 224, 3
+    img32 = rng.uniform(0, 1, b * h * w * c).astype(np.float32)
+    img = oracle.as_buffer(img32)
+    ncols = b * 222 * 222 * 27
+    cols = np.zeros(ncols)
+    byt = (img.size + ncols) * 4
+    t = t_of(lambda: oracle.im2col2d(False, img, 0, img.size, b, h, w, c, 3, 3, 1, 1, False, False, 1, 1, False, cols, 0, ncols))
+    i4 = img32.reshape(b, h, w, c)
+    tn = t_of(lambda: np.ascontiguousarray(np.lib.stride_tricks.sliding_window_view(i4, (3, 3), axis=(1, 2)).transpose(0, 1, 2, 4, 5, 3)))
+    out["im2col2d"]["cpu_baseline"] = {"value": byt / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                       "sample": "%d of 64 images; %s" % (b, label),
+                                       "numpy": {"value": byt / tn / 1e9, "unit": "GB/s", "cores": 1,
+                                                 "sample": "the same images, stride-trick im2col + copy (one thread)"}}
 
 
 def main():
@@ -719,7 +952,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=8192, help="sgemm size per GPU (M=N=K)")
+    ap.add_argument("--size", dest="n", type=int, default=16384, help="global sgemm size (M=N=K), row-sharded over the GPUs")
+    ap.add_argument("--no-multicast", action="store_true", help="fused gather through unicast peer stores even when NVLS multicast is available")
     ap.add_argument("--mode", default="tf32", choices=["tf32", "tf32x3", "fp32_simt"])
     ap.add_argument("--quick", action="store_true", help="headline workload only (no hbm_ops / other modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

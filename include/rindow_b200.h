@@ -189,6 +189,16 @@ int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t 
                           const float* B, int64_t offB, int64_t ldB,
                           float beta, float* C, int64_t offC, int64_t ldC, int mode,
                           int n_peers, void* const* peer_C);
+/* The same call over an NVLS multicast mapping (NVSwitch): `mc_C` is the multicast alias of the symmetric allocation
+ * that holds C on every rank (cuMulticastCreate / cuMulticastBindMem; torch.distributed._symmetric_memory provides it
+ * as handle.multicast_ptr), indexed like C.  The CTA-pair kernel's epilogue stores each finished 128-byte row segment
+ * ONCE with multimem.st and the switch replicates it into every rank's copy (this rank's included) -- a stripe leaves
+ * the GPU once instead of once per peer.  Other kernel families multiply first and push the stripe with a multimem
+ * copy kernel on the same stream.  Same ordering contract as rb200_sgemm_allgather. */
+int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                             float alpha, const float* A, int64_t offA, int64_t ldA,
+                             const float* B, int64_t offB, int64_t ldB,
+                             float beta, float* C, int64_t offC, int64_t ldC, int mode, void* mc_C);
 
 /* ---- BLAS level 1 / 2: replace PhpBlas::scal (PhpBlas.php:141-161),
  *      axpy (:165-194), copy (:350-364), gemv (:762-844).  float32 / float64. ------------------------------ */

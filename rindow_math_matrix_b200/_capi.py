@@ -65,6 +65,8 @@ SIGNATURES = {
     "rb200_ipc_close": (i32, [vp]),
     "rb200_sgemm_allgather": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32,
                                     i32, ctypes.POINTER(vp)]),
+    "rb200_sgemm_allgather_mc": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32,
+                                       vp]),
     "rb200_scal": (i32, [i32, i64, f64, vp, i64, i64]),
     "rb200_axpy": (i32, [i32, i64, f64, vp, i64, i64, vp, i64, i64]),
     "rb200_copy": (i32, [i32, i64, vp, i64, i64, vp, i64, i64]),

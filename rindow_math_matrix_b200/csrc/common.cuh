@@ -34,6 +34,8 @@ struct Context {
     float*      gemm_peers[RB200_MAX_PEERS] = {};
     int         n_gemm_peers = 0;
     bool        gemm_peers_written = false;
+    // multicast alias of C (+ offC) the next tensor-core GEMM stores its final values to (rb200_sgemm_allgather_mc)
+    float*      gemm_mc = nullptr;
 };
 
 Context& ctx();

@@ -32,6 +32,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
 bool gemm_tcgen05_batched_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA, int64_t strideA,
                                    const float* B, int64_t ldB, int64_t strideB, const float* C, int64_t ldC,
                                    int64_t strideC, int64_t batch);
+int mc_push_rows(const float* src, float* mc, int64_t rows, int64_t cols, int64_t ld);
 int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t N, int64_t K, float alpha,
                          const float* A, int64_t ldA, int64_t strideA, const float* B, int64_t ldB, int64_t strideB,
                          float beta, float* C, int64_t ldC, int64_t strideC, int64_t batch);
@@ -198,6 +199,28 @@ int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t 
         }
     }
     return RB200_OK;
+}
+
+// The NVLS form: `mc_C` is the MULTICAST alias of the symmetric allocation C lives in (same element indexing).  The
+// CTA-pair kernel's epilogue writes every finished 128-byte row segment once with multimem.st; the NVSwitch replicates
+// it into all ranks' copies, so a stripe leaves this GPU once instead of once per peer.
+int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                             float alpha, const float* A, int64_t offA, int64_t ldA,
+                             const float* B, int64_t offB, int64_t ldB,
+                             float beta, float* C, int64_t offC, int64_t ldC, int mode, void* mc_C)
+{
+    RB_REQUIRE_INIT();
+    if (!mc_C) RB_INVALID("mc_C is NULL");
+    if (order != RB200_ROW_MAJOR) RB_UNSUPPORTED("rb200_sgemm_allgather_mc: row-major only (the stripes are rows)");
+    rb200::Context& c = rb200::ctx();
+    c.n_gemm_peers = 0;
+    c.gemm_mc = reinterpret_cast<float*>(mc_C) + offC;
+    c.gemm_peers_written = false;
+    const int rc = rb200_sgemm(order, transA, transB, m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC, mode);
+    float* mc = c.gemm_mc;
+    c.gemm_mc = nullptr;
+    if (rc != RB200_OK || c.gemm_peers_written) return rc;
+    return rb200::mc_push_rows(C + offC, mc, m, n, ldC);
 }
 
 }  // extern "C"

@@ -160,6 +160,9 @@ struct TcParams {
     // epilogue also stores every finished value to -- NVLink peer stores overlapping the remaining tiles
     int n_peers;
     float* peers[RB200_MAX_PEERS];
+    // rb200_sgemm_allgather_mc: the multicast alias of C (NVLS: one multimem.st leaves this GPU once and the NVSwitch
+    // replicates it into every rank's copy, this rank's included); nullptr = unicast peers above
+    float* mc;
     // strided batch (1-CTA kernels): tile index = (matrix, row block, column block); the third tensor-map coordinate
     // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
     int batch, a_bmul, b_bmul;
@@ -455,6 +458,16 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtenso
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar) : "memory");
 }
+// one 16-byte store to a multicast address: the switch writes it to the same offset of every bound allocation
+__device__ __forceinline__ void multimem_st_f4(float* mc_addr, const float4& v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f1(float* mc_addr, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -654,7 +667,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                             }
                         }
                     }
-                    if (p.n_peers > 0) {
+                    if (p.n_peers > 0 || p.mc != nullptr) {
                         // all-gather leg: the warp's 32 x 32 block of final values goes through a padded smem tile so
                         // that every peer store instruction writes whole 128-byte row segments (NVLink-friendly),
                         // instead of 32 scattered 16-byte pieces
@@ -676,7 +689,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                             if (grow < p.M && c0 + cc < p.N) {
                                 const float4 val = *reinterpret_cast<const float4*>(stg + rr * L::STG_LD + cc);
                                 const int64_t at = grow * p.ldC + c0 + cc;
-                                if (c0 + cc + 4 <= p.N) {
+                                if (p.mc != nullptr) {
+                                    if (c0 + cc + 4 <= p.N) multimem_st_f4(p.mc + at, val);
+                                    else {
+                                        const float ve[4] = {val.x, val.y, val.z, val.w};
+                                        for (int e = 0; e < 4; e++)
+                                            if (c0 + cc + e < p.N) multimem_st_f1(p.mc + at + e, ve[e]);
+                                    }
+                                } else if (c0 + cc + 4 <= p.N) {
                                     for (int pj = 0; pj < p.n_peers; pj++)
                                         st_stream_f4(reinterpret_cast<float4*>(p.peers[pj] + at), val);
                                 } else {
@@ -827,7 +847,41 @@ int launch_2cta(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& 
 
 }  // namespace
 
+namespace {
+// fallback of rb200_sgemm_allgather_mc for the kernel families whose epilogue does not store to the multicast alias:
+// the finished stripe is read once and multicast with 16-byte multimem stores (rows of `cols` floats, stride ld)
+__global__ void __launch_bounds__(256)
+mc_push_rows_kernel(const float* __restrict__ src, float* __restrict__ mc, int64_t rows, int64_t cols, int64_t ld, int vec)
+{
+    const int64_t per_row = vec ? cols / 4 : cols;
+    const int64_t total = rows * per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per_row, c = i - r * per_row;
+        if (vec) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(src + r * ld) + c);
+            multimem_st_f4(mc + r * ld + 4 * c, v);
+        } else {
+            multimem_st_f1(mc + r * ld + c, src[r * ld + c]);
+        }
+    }
+}
+}  // namespace
+
 namespace rb200 {
+
+int mc_push_rows(const float* src, float* mc, int64_t rows, int64_t cols, int64_t ld)
+{
+    Context& c = ctx();
+    const int vec = (cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(mc) & 15) == 0) ? 1 : 0;
+    const int64_t total = rows * (vec ? cols / 4 : cols);
+    int64_t grid = rb_ceil_div(total, 256);
+    if (grid > (int64_t)c.sm_count * 8) grid = (int64_t)c.sm_count * 8;
+    if (grid < 1) grid = 1;
+    mc_push_rows_kernel<<<(unsigned)grid, 256, 0, c.stream>>>(src, mc, rows, cols, ld, vec);
+    RB_LAUNCH_CHECK("mc_push_rows_kernel");
+    return RB200_OK;
+}
 
 // General float32 tensor map (rank <= 5) for the skinny / implicit-GEMM kernels: image slabs (unswizzled
 // loads) and output tiles (128-byte swizzled stores).  dims innermost first, strides in bytes for
@@ -943,7 +997,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0;
+        p.n_peers = 0; p.mc = nullptr;
         p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
@@ -958,12 +1012,12 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         const int64_t tiles_small = rb_ceil_div(M, 128) * rb_ceil_div(N, 128);
         const double t_pair = (double)rb_ceil_div(tiles_pair, pairs) * (256.0 * BN / 2.0);
         const double t_small = (double)rb_ceil_div(tiles_small, (int64_t)c.sm_count) * (128.0 * 128.0) * 1.15;
-        const bool small_tiles = planes == 1 && use_small && c.n_gemm_peers == 0 && (!pair_ok || t_small < t_pair);
+        const bool small_tiles = planes == 1 && use_small && c.n_gemm_peers == 0 && !c.gemm_mc && (!pair_ok || t_small < t_pair);
         // 3xTF32: the pair tile is 256 x 128 and the single-CTA tile 128 x 128 (the same work per SM); small
         // problems take 128 x 64 tiles
         const int64_t tiles_x3s = rb_ceil_div(M, 128) * rb_ceil_div(N, 64);
         const double t_x3s = (double)rb_ceil_div(tiles_x3s, (int64_t)c.sm_count) * (128.0 * 64.0) * 1.15;
-        const bool small_x3 = planes == 2 && use_small && c.n_gemm_peers == 0 && t_x3s < t_pair;
+        const bool small_x3 = planes == 2 && use_small && c.n_gemm_peers == 0 && !c.gemm_mc && t_x3s < t_pair;
         if (small_x3) {
             CUtensorMap mBs;
             if (!b_mn) rc = make_map(&mBs, pb, kl, N, sldB, planes, plsB, TC_BK, 64, k_sw);
@@ -991,9 +1045,10 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
             // and an A panel (8 x 256 rows) that stays L2-resident across the waves of its group
             static const int dbg_group = getenv("RB200_GEMM_GROUP") ? atoi(getenv("RB200_GEMM_GROUP")) : 8;
             p.group_m = dbg_group > 0 ? dbg_group : 8;
-            if (c.n_gemm_peers > 0 && kc + KC >= K) {            // the chunk that produces the final values
+            if ((c.n_gemm_peers > 0 || c.gemm_mc) && kc + KC >= K) {     // the chunk that produces the final values
                 p.n_peers = c.n_gemm_peers;
                 for (int pj = 0; pj < c.n_gemm_peers; pj++) p.peers[pj] = c.gemm_peers[pj];
+                p.mc = c.gemm_mc;
                 c.gemm_peers_written = true;
             }
             rc = planes == 1 ? launch_2cta<1>(a_mn, b_mn, mA, mB2, p) : launch_2cta<2>(a_mn, b_mn, mA, mB2, p);
@@ -1078,7 +1133,7 @@ int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t 
         p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
         p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0;
+        p.n_peers = 0; p.mc = nullptr;
         p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
         if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
         else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);

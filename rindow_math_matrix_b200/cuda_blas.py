@@ -199,11 +199,13 @@ class CudaBlas:
 
     # ---- multi-GPU: row-sharded gemm whose C stripe also lands in the peers' full C ----
     def gemmAllgather(self, transA, transB, m, n, k, alpha, A, offsetA, ldA, B, offsetB, ldB,
-                      beta, C, offsetC, ldC, peer_ptrs) -> None:
+                      beta, C, offsetC, ldC, peer_ptrs, multicast_ptr: int | None = None) -> None:
         """PhpBlas::gemm semantics (row-major) for this rank's stripe: C[offsetC ...] is the stripe inside this
         rank's full C; peer_ptrs are the other ranks' full-C allocations mapped here (sharding.PeerRows).  The
         tensor-core kernel stores every finished tile to the peers from its epilogue (rb200_sgemm_allgather);
-        the caller orders the ranks afterwards (PeerRows.arrive)."""
+        the caller orders the ranks afterwards (PeerRows.arrive).  With `multicast_ptr` (the NVLS multicast alias of
+        the symmetric allocation C lives in, sharding.SymmetricRows) the stripe leaves this GPU once: the epilogue
+        stores with multimem.st and the NVSwitch replicates (rb200_sgemm_allgather_mc)."""
         tA, _ = code_to_trans(transA)
         tB, _ = code_to_trans(transB)
         assert_shape_parameter("m", m)
@@ -216,6 +218,12 @@ class CudaBlas:
         assert_matrix_buffer_spec("C", C, m, n, offsetC, ldC)
         if not (A.dtype() == B.dtype() == C.dtype() == dtypes.float32):
             raise LogicException("CudaBlas::gemmAllgather supports float32")
+        if multicast_ptr:
+            _capi.check(self._lib.rb200_sgemm_allgather_mc(
+                BLAS.RowMajor, transA, transB, m, n, k, float(alpha), A.device_ptr(), offsetA, ldA,
+                B.device_ptr(), offsetB, ldB, float(beta), C.device_ptr_rw(), offsetC, ldC, self.gemm_mode,
+                multicast_ptr))
+            return
         peers = (ctypes.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
         _capi.check(self._lib.rb200_sgemm_allgather(
             BLAS.RowMajor, transA, transB, m, n, k, float(alpha), A.device_ptr(), offsetA, ldA,

@@ -53,11 +53,31 @@ class CudaBuffer:
             _capi.check(self._lib.rb200_buffer_fill(self._dtype, self._dptr, 0, self._size, z.ctypes.data))
             self._dev_dirty = True
 
+    @classmethod
+    def adopt(cls, device_ptr: int, size: int, dtype: int, owner=None) -> "CudaBuffer":
+        """A Buffer over device memory somebody else owns (e.g. a torch symmetric-memory allocation that is mapped
+        into every rank and bound to an NVLS multicast object, sharding.SymmetricRows): same interface, never freed
+        here; `owner` is kept alive with the buffer."""
+        if dtype not in dtypes.NUMPY:
+            raise InvalidArgumentException("Invalid data type")
+        _capi.init()
+        self = cls.__new__(cls)
+        self._size, self._dtype = int(size), int(dtype)
+        self._np = np.dtype(dtypes.NUMPY[dtype])
+        self._bytes = self._size * self._np.itemsize
+        self._lib = _capi.load()
+        self._dptr, self._owner, self._adopted = int(device_ptr), owner, True
+        self._hptr = self._host = None
+        self._host_dirty, self._dev_dirty, self._single_reads = False, True, 0
+        self._upload_event, self._upload_pending = None, False
+        return self
+
     # ---- lifetime ------------------------------------------------------------------------
     def __del__(self):
         try:
             if getattr(self, "_dptr", None):
-                self._lib.rb200_buffer_free(self._dptr)
+                if not getattr(self, "_adopted", False):
+                    self._lib.rb200_buffer_free(self._dptr)
                 self._dptr = None
             if getattr(self, "_upload_event", None):
                 if self._upload_pending:

@@ -135,6 +135,182 @@ class PeerRows:
             self._opened = []
 
 
+class SymmetricRows:
+    """The full [total_rows, cols] float32 matrix in SYMMETRIC memory: one allocation per rank, every rank's copy
+    mapped into every process and all of them bound to one NVLS multicast object
+    (torch.distributed._symmetric_memory: cuMemCreate + cuMulticastCreate / cuMulticastBindMem, handles exchanged
+    through the process group -- plumbing only).  `multicast_ptr` is the alias a multimem.st writes through: the
+    NVSwitch replicates the store into all copies, so the producing GEMM's epilogue (rb200_sgemm_allgather_mc) sends
+    a stripe over its NVLink ports ONCE instead of once per peer.  Without multicast support (`multicast_ptr == 0`)
+    the peers' mappings (`peer_ptrs`) serve the unicast form, as PeerRows does over CUDA IPC.
+    arrive() is the symmetric-memory barrier (a signal-pad kernel on the current stream, no host sync)."""
+
+    def __init__(self, total_rows: int, cols: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import dtypes
+        from .cuda_buffer import CudaBuffer
+        self.total_rows, self.cols = int(total_rows), int(cols)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.start, self.rows = row_range(self.total_rows, self.world, self.rank)
+        n = self.total_rows * self.cols
+        self.tensor = symm_mem.empty(n, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        ptrs = list(self.handle.buffer_ptrs)
+        self.peer_ptrs = [int(p) for r, p in enumerate(ptrs) if r != self.rank]
+        self.buffer = CudaBuffer.adopt(self.tensor.data_ptr(), n, dtypes.float32, owner=self.tensor)
+
+    def stripe_offset(self) -> int:
+        return self.start * self.cols
+
+    def arrive(self) -> None:
+        self.handle.barrier(channel=0)
+
+    def close(self) -> None:
+        self.buffer = None
+        self.handle = None
+        self.tensor = None
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process to the CPU cores NVML reports as local to GPU `local_rank` (its NUMA node) BEFORE any pinned
+    host memory is allocated: cudaHostAlloc places pages on the allocating thread's node, and a rank whose mirrors sit
+    on the far socket pays the inter-socket hop on every h2d / d2h.  Returns {"cpus": n, "numa": id or None}; a no-op
+    ({"cpus": 0}) when NVML or the affinity call is unavailable (single-socket boxes lose nothing)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"cpus": 0, "numa": None}
+        os.sched_setaffinity(0, cpus)
+        numa = None
+        try:
+            numa = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        return {"cpus": len(cpus), "numa": numa}
+    except Exception:
+        return {"cpus": 0, "numa": None}
+
+
+class RowShardedGemm:
+    """C = alpha * A . B (+ beta * C) for float32 with A and C ROW-SHARDED over the ranks of `group` and B replicated
+    (SURVEY.md section 8(e) row 1): rank g owns rows [start, start + rows) of the [M, K] matrix A and of the [M, N]
+    result, and runs the single-GPU kernel on its stripe.  Two ways to finish:
+      * gather=False -- C stays sharded (no collective at all);
+      * gather=True  -- every rank ends with the FULL C: the stripes are pushed into all ranks' copies from the GEMM
+        epilogue while the remaining tiles are still being multiplied (NVLS multicast stores when the NVSwitch offers
+        them, unicast peer stores otherwise), then one barrier.
+    run() works on device-resident operands.  run_from_host() is the host-operand form of the same call: every rank
+    uploads ITS stripe of A and ITS 1/world slice of B from pinned memory, the slices of B are all-gathered over
+    NVLink (so B crosses each PCIe link once in total, not once per rank), the stripe is multiplied by the
+    transfer-pipelined rb200_sgemm_streamed and the C stripe comes back to the host while later row blocks multiply."""
+
+    def __init__(self, blas, M: int, N: int, K: int, group=None, gather: bool = True, allow_multicast: bool = True,
+                 operands=None):
+        from . import dtypes
+        from .cuda_buffer import CudaBuffer
+        self.blas, self.M, self.N, self.K, self.group = blas, int(M), int(N), int(K), group
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.start, self.rows = row_range(self.M, self.world, self.rank)
+        self.bstart, self.brows = row_range(self.K, self.world, self.rank)         # this rank's slice of B's rows
+        if self.rows < 1:
+            raise ValueError("every rank needs at least one row of A")
+        f32 = dtypes.float32
+        if operands is not None:                 # share another job's resident A stripe and B
+            self.A, self.B = operands
+        else:
+            self.A = CudaBuffer(self.rows * self.K, f32, zero=False)
+            self.B = CudaBuffer(self.K * self.N, f32, zero=False)
+        self.gather = bool(gather) and self.world > 1
+        self.sym = None
+        self.multicast = False
+        if self.gather:
+            self.sym = SymmetricRows(self.M, self.N, group)
+            self.C, self.offC = self.sym.buffer, self.sym.stripe_offset()
+            self.multicast = bool(allow_multicast and self.sym.multicast_ptr)
+        else:
+            self.C, self.offC = CudaBuffer(self.rows * self.N, f32), 0
+        self._host = None
+
+    # ---- device-resident ------------------------------------------------------------------------------
+    def run(self, alpha: float = 1.0, beta: float = 0.0) -> None:
+        from .cuda_blas import BLAS
+        if not self.gather:
+            self.blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, self.rows, self.N, self.K, alpha, self.A, 0, self.K,
+                           self.B, 0, self.N, beta, self.C, self.offC, self.N)
+            return
+        self.blas.gemmAllgather(BLAS.NoTrans, BLAS.NoTrans, self.rows, self.N, self.K, alpha, self.A, 0, self.K,
+                                self.B, 0, self.N, beta, self.C, self.offC, self.N, self.sym.peer_ptrs,
+                                multicast_ptr=self.sym.multicast_ptr if self.multicast else None)
+        self.sym.arrive()
+
+    # ---- host operands ----------------------------------------------------------------------------------
+    def host_buffers(self):
+        """(A stripe [rows, K], B slice [brows, N], C stripe [rows, N]) as numpy views of pinned host memory the caller
+        fills / reads; created on first use on the calling thread's NUMA node (bind_to_gpu_numa first)."""
+        if self._host is None:
+            from . import dtypes
+            from .cuda_buffer import CudaBuffer
+            f32 = dtypes.float32
+            self._Bslice = CudaBuffer(max(1, self.brows * self.N), f32, zero=False)    # staging mirror of B's slice
+            self._Cstripe = self.C if not self.gather else CudaBuffer(self.rows * self.N, f32)
+            self._host = (self.A.host().reshape(self.rows, self.K), self._Bslice.host().reshape(-1)[: self.brows * self.N]
+                          .reshape(self.brows, self.N), self._Cstripe.host().reshape(self.rows, self.N))
+        return self._host
+
+    def run_from_host(self, alpha: float = 1.0) -> None:
+        """One step with this step's inputs in the pinned host buffers and the C stripe read back into its host buffer
+        (returns when the stripe is on the host)."""
+        from . import _capi
+        from .cuda_blas import BLAS
+        self.host_buffers()
+        lib = _capi.load()
+        # B: own slice up (asynchronously on the library stream), then the NVLink all-gather in place
+        dB, _ = self.B.raw_pointers()
+        _, hS = self._Bslice.raw_pointers()
+        self._Bslice._wait_upload()
+        if self.brows:
+            _capi.check(lib.rb200_buffer_h2d_async(dB, self.bstart * self.N * 4, hS, self.brows * self.N * 4))
+        if self.world > 1:
+            tB = tensor_of(self.B)
+            ranges = all_row_ranges(self.K, self.world)
+            if len({r for _, r in ranges}) == 1:
+                dist.all_gather_into_tensor(tB, tB[self.bstart * self.N:(self.bstart + self.brows) * self.N], group=self.group)
+            else:
+                parts = [tB[s * self.N:(s + r) * self.N] for s, r in ranges]
+                dist.all_gather(parts, parts[self.rank], group=self.group)
+        self.A.mark_host_written()
+        self.blas.setHostResultPrefetch(True)
+        try:
+            self.blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, self.rows, self.N, self.K, alpha, self.A, 0, self.K,
+                           self.B, 0, self.N, 0.0, self._Cstripe, 0, self.N)
+        finally:
+            self.blas.setHostResultPrefetch(None)
+        self._Cstripe.host()                      # current: the streamed call already brought it back
+
+    def close(self) -> None:
+        if self.sym is not None:
+            self.sym.close()
+            self.sym = None
+
+
 def merge_sum(partial: torch.Tensor, group=None) -> torch.Tensor:
     """Sum of per-rank partial sums (all-reduce)."""
     if _world(group) > 1:

@@ -663,10 +663,14 @@ def test_gemm_quoted_sizes_sampled(N, mode, cuda_service):
     blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, N, N, N, 1.0, A, 0, N, B, 0, N, 0.0, C, 0, N)
     got = C.to_numpy().reshape(N, N)
     del A, B, C
+    # float32 accumulation over K = 8192 / 16384 terms: the FFMA path's rounding error grows like sqrt(K)*eps32
+    # (measured 3.9e-6 at K = 8192), so its small-K bound of 2e-6 becomes 1e-5 here -- still 10x inside the
+    # reference's isclose bound (1e-4); the tensor-core modes keep their bounds at every K
+    tol = 1e-5 if mode == rb.GEMM_FP32_SIMT else GEMM_TOL[mode]
     err = np.max(np.abs(got[rows].astype(np.float64) - ref)) / np.max(np.abs(ref))
-    assert err < GEMM_TOL[mode], (err, rb._capi.last_gemm_path())
+    assert err < tol, (err, rb._capi.last_gemm_path())
     cs = got.sum(axis=0, dtype=np.float64)
-    assert np.max(np.abs(cs - colsum)) < GEMM_TOL[mode] * N * np.max(np.abs(ref))
+    assert np.max(np.abs(cs - colsum)) < tol * N * np.max(np.abs(ref))
     cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
 
 
