@@ -13,9 +13,12 @@ from .cuda_math import CudaMath, CudaMathFactory  # noqa: F401
 from .exceptions import (InvalidArgumentException, LogicException, OutOfRangeException,  # noqa: F401
                          RuntimeException)
 from .linear_algebra import LinearAlgebra  # noqa: F401
+from .linear_algebra_cuda import LinearAlgebraCuda  # noqa: F401
+from .ndarray_cuda import (CudaDeviceBuffer, CudaDeviceBufferFactory, CudaEventList, CudaQueue,  # noqa: F401
+                           NDArrayCuda)
 from .matrix_operator import MatrixOperator  # noqa: F401
 from .ndarray import NDArray  # noqa: F401
 from .service import MatlibCuda, Service  # noqa: F401
 
-__all__ = ["MatlibCuda", "Service", "MatrixOperator", "LinearAlgebra", "NDArray", "CudaBuffer", "CudaBlas",
+__all__ = ["MatlibCuda", "Service", "MatrixOperator", "LinearAlgebra", "LinearAlgebraCuda", "NDArray", "NDArrayCuda", "CudaBuffer", "CudaBlas",
            "CudaMath", "BLAS", "dtypes"]

@@ -16,7 +16,7 @@ import numpy as np
 from . import dtypes
 from .cuda_blas import BLAS
 from .exceptions import InvalidArgumentException, LogicException
-from .ndarray import NDArray
+from .ndarray import NDArray, NDArrayInterface
 from .service import Service
 
 
@@ -36,7 +36,7 @@ class LinearAlgebra:
         return self.service.serviceLevel() >= Service.LV_ADVANCED and type(self.blas).__name__.startswith("Cuda")
 
     def array(self, array, dtype: int | None = None) -> NDArray:
-        if isinstance(array, NDArray):
+        if isinstance(array, NDArrayInterface):
             return array
         if dtype is None:
             a = np.asarray(array)
@@ -53,8 +53,17 @@ class LinearAlgebra:
     def toNDArray(self, x: NDArray) -> NDArray:
         return x
 
+    # hooks the device-resident subclass (LinearAlgebraCuda) overrides
+    def _host_array(self, array, dtype: int) -> NDArray:
+        """A small parameter array the DRIVER reads from the host (shape / perm vectors, fill patterns)."""
+        return NDArray(array, dtype=dtype, service=self.service)
+
+    def _element(self, X: NDArray, i: int):
+        """One element of X read on the host (`$XX[$offX+$i]`, LinearAlgebra.php:480-492, 1644-1645)."""
+        return X.buffer()[X.offset() + i]
+
     def fill(self, value, X: NDArray) -> NDArray:                               # LinearAlgebra.php:4662
-        V = NDArray([value], dtype=X.dtype(), service=self.service)
+        V = self._host_array([value], X.dtype())
         self.math.fill(X.size(), V.buffer(), V.offset(), X.buffer(), X.offset(), 1)
         return X
 
@@ -110,11 +119,11 @@ class LinearAlgebra:
 
     def amax(self, X: NDArray) -> float:                                         # :480-492: |X[iamax]|, read from the buffer
         i = self.blas.iamax(X.size(), X.buffer(), X.offset(), 1)
-        return abs(X.buffer()[X.offset() + i])
+        return abs(self._element(X, i))
 
     def amin(self, X: NDArray) -> float:                                         # :497-513
         i = self.blas.iamin(X.size(), X.buffer(), X.offset(), 1)
-        return abs(X.buffer()[X.offset() + i])
+        return abs(self._element(X, i))
 
     def nrm2(self, X: NDArray) -> float:                                         # :518-527
         return self.blas.nrm2(X.size(), X.buffer(), X.offset(), 1)
@@ -267,7 +276,7 @@ class LinearAlgebra:
     def _transposeND(self, A: NDArray, perm, B: NDArray | None) -> NDArray:      # LinearAlgebra.php:4471-4519
         if perm is None:
             perm = list(range(A.ndim() - 1, -1, -1))
-        if isinstance(perm, NDArray):
+        if isinstance(perm, NDArrayInterface):
             perm = [int(v) for v in np.asarray(perm.toArray()).reshape(-1)]
         perm = [int(v) for v in perm]
         shapeA = A.shape()
@@ -288,8 +297,8 @@ class LinearAlgebra:
                 raise InvalidArgumentException("output shape must be transpose matrix of input.")
             if B.dtype() != A.dtype():
                 raise InvalidArgumentException("output data type must be same with matrix of input.")
-        sourceShape = self.array(np.asarray(shapeA, np.int32), dtype=dtypes.int32).buffer()
-        permBuf = self.array(np.asarray(perm, np.int32), dtype=dtypes.int32).buffer()
+        sourceShape = self._host_array(np.asarray(shapeA, np.int32), dtypes.int32).buffer()
+        permBuf = self._host_array(np.asarray(perm, np.int32), dtypes.int32).buffer()
         self.math.transpose(sourceShape, permBuf, A.buffer(), A.offset(), B.buffer(), B.offset())
         return B
 
@@ -377,11 +386,11 @@ class LinearAlgebra:
 
     def max(self, X: NDArray):
         i = self.math.imax(X.size(), X.buffer(), X.offset(), 1)
-        return X.buffer()[X.offset() + i]
+        return self._element(X, i)
 
     def min(self, X: NDArray):
         i = self.math.imin(X.size(), X.buffer(), X.offset(), 1)
-        return X.buffer()[X.offset() + i]
+        return self._element(X, i)
 
     # ---- unary family, in place (LinearAlgebra.php:1664-1715, 2021-2080, 2143-2246, 2296-2304, 4817-4853) ----
     def increment(self, X: NDArray, beta=None, alpha=None) -> NDArray:
@@ -441,7 +450,7 @@ class LinearAlgebra:
     def _calc_broadcast_format(self, A: NDArray, X):
         if isinstance(X, (int, float, np.integer, np.floating)) and not isinstance(X, bool):
             X = self.array(X, dtype=A.dtype())
-        if not isinstance(X, NDArray):
+        if not isinstance(X, NDArrayInterface):
             raise InvalidArgumentException("X must be NDArray or float")
         if X.ndim() == 0:
             X = X.reshape([X.size()])
@@ -565,7 +574,7 @@ class LinearAlgebra:
     def _printable_shapes(values) -> str:                                        # LinearAlgebra.php:95-115
         parts = []
         for v in values:
-            shape = v.shape() if isinstance(v, NDArray) else list(v)
+            shape = v.shape() if isinstance(v, NDArrayInterface) else list(v)
             parts.append("(" + ",".join(map(str, shape)) + ")")
         return ",".join(parts)
 
@@ -1014,7 +1023,7 @@ class LinearAlgebra:
         if axis not in (0, 1, 2):
             raise InvalidArgumentException("unsuppoted axis")
         for value in values:
-            if not isinstance(value, NDArray):
+            if not isinstance(value, NDArrayInterface):
                 raise InvalidArgumentException("values must be array of NDArray")
         shape = values[0].shape()
         output = self.alloc(shape[:axis] + [len(values)] + shape[axis:], dtype=values[0].dtype())

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import dtypes
 from .cuda_blas import BLAS
-from .exceptions import InvalidArgumentException
+from .exceptions import InvalidArgumentException, LogicException
 from .linear_algebra import LinearAlgebra
 from .ndarray import NDArray
 from .service import Service
@@ -34,6 +34,24 @@ class MatrixOperator:
         if self._la is None:
             self._la = LinearAlgebra(self._service, self.defaultFloatType)
         return self._la
+
+    def createLinearAlgebraCuda(self, options=None):                      # cf. createLinearAlgebraCL, :1553-1561
+        from .linear_algebra_cuda import LinearAlgebraCuda
+        queue = self._service.createQueue(options)
+        return LinearAlgebraCuda(queue, self._service, self.defaultFloatType)
+
+    def laAccelerated(self, name: str, options=None):                     # MatrixOperator.php:1566-1579
+        if name == "cuda":
+            if getattr(self, "_cudaLA", None) is None:
+                self._cudaLA = self.createLinearAlgebraCuda(options)
+            return self._cudaLA
+        raise LogicException("Unknown accelerator")
+
+    def isAdvanced(self) -> bool:
+        return self._service.serviceLevel() >= Service.LV_ADVANCED
+
+    def isAccelerated(self) -> bool:
+        return self._service.serviceLevel() >= Service.LV_ACCELERATED
 
     def isIntType(self, dtype: int) -> bool:
         return dtype in dtypes.INT_TYPES

@@ -16,7 +16,12 @@ from . import dtypes
 from .exceptions import InvalidArgumentException, OutOfRangeException
 
 
-class NDArray:
+class NDArrayInterface:
+    """Interop\\Polite\\Math\\Matrix\\NDArray: what LinearAlgebra accepts -- the host-facing NDArray below and the
+    device-resident NDArrayCuda (ndarray_cuda.py) both implement it, as NDArrayPhp and NDArrayCL do in the reference."""
+
+
+class NDArray(NDArrayInterface):
     def __init__(self, array=None, dtype: int | None = None, shape=None, offset: int | None = None,
                  service=None, buffer=None):
         if service is None:

@@ -41,6 +41,7 @@ class MatlibCuda(Service):
         self.mathFactory = mathFactory or CudaMathFactory()
         self._level = None
         self._blas = self._math = self._buffer = None
+        self._device_buffer = None
         if self.serviceLevel() >= Service.LV_ADVANCED:
             _capi.init()
             self._blas = self.blasFactory.Blas()
@@ -66,12 +67,18 @@ class MatlibCuda(Service):
         if ok:
             level = Service.LV_ADVANCED
             self._log("Update current level to Advanced.")
+            # the accelerated tier of AbstractMatlibService.php:193-218 (there: OpenCL + CLBlast factories): device-
+            # resident buffers, queue, NDArrayCuda / LinearAlgebraCuda -- same library, so available together
+            level = Service.LV_ACCELERATED
+            self._log("Update current level to Accelerated.")
         self._level = level
         self._log("The service level was diagnosed as %s." % _LEVEL_STRING[level])
         return level
 
     def _require(self, level):
         level = Service.LV_ADVANCED if level is None else level
+        if level == Service.LV_ACCELERATED:
+            level = Service.LV_ADVANCED            # blas()/math() of the accelerated tier are the same driver objects
         if level == Service.LV_BASIC:
             raise LogicException("LV_BASIC is the reference's pure-PHP driver (PhpBlas/PhpMath); the B200 package "
                                  "ships no CPU implementation")
@@ -102,6 +109,11 @@ class MatlibCuda(Service):
 
     def buffer(self, level=None):
         self._require(level)
+        if level == Service.LV_ACCELERATED:                              # AbstractMatlibService.php:316-318
+            if self._device_buffer is None:
+                from .ndarray_cuda import CudaDeviceBufferFactory
+                self._device_buffer = CudaDeviceBufferFactory()
+            return self._device_buffer
         return self._buffer
 
     def lapack(self, level=None):
@@ -120,4 +132,18 @@ class MatlibCuda(Service):
         raise LogicException("mathCLBlast is not supported.")
 
     def createQueue(self, options=None):
-        raise LogicException("createQueue is not supported: the B200 driver is stream-ordered (rb200_sync)")
+        """The queue NDArrayCuda / LinearAlgebraCuda are constructed with (AbstractMatlibService::createQueue): the
+        library stream."""
+        self._require(None)
+        from .ndarray_cuda import CudaQueue
+        return CudaQueue(options)
+
+    def blasCuda(self, queue):
+        """Device-tier driver objects (the blasCL($queue) / mathCL($queue) slots of Service.php:16-20): the same
+        CudaBlas / CudaMath -- they take device buffers positionally and are ordered on the queue's stream."""
+        self._require(None)
+        return self._blas
+
+    def mathCuda(self, queue):
+        self._require(None)
+        return self._math
