@@ -38,8 +38,10 @@ class CudaBuffer implements LinearBuffer
     protected $host = null;          // typed FFI view of the mirror
     protected bool $hostDirty = false;
     protected bool $devDirty = false;
+    protected $uploadEvent = null;   // recorded behind the asynchronous h2d of the mirror (devicePtr)
+    protected bool $uploadPending = false;
 
-    public function __construct(int $size, int $dtype)
+    public function __construct(int $size, int $dtype, bool $zero=true)
     {
         $t = self::table();
         if (!isset($t[$dtype])) {
@@ -52,14 +54,20 @@ class CudaBuffer implements LinearBuffer
         $p = $ffi->new('void*');
         CudaFFI::check($ffi->rb200_buffer_alloc($size * $this->valueSize, FFI::addr($p)));
         $this->dptr = $p;
-        $zero = $ffi->new($this->ctype);
-        CudaFFI::check($ffi->rb200_buffer_fill($this->abiDtype, $this->dptr, 0, $size, FFI::addr($zero)));
+        if ($zero && $size > 0) {
+            $z = $ffi->new($this->ctype);
+            CudaFFI::check($ffi->rb200_buffer_fill($this->abiDtype, $this->dptr, 0, $size, FFI::addr($z)));
+        }
         $this->devDirty = true;
     }
 
     public function __destruct()
     {
         $ffi = CudaFFI::lib();
+        if ($this->uploadEvent !== null) {
+            if ($this->uploadPending) { $ffi->rb200_event_synchronize($this->uploadEvent); }
+            $ffi->rb200_event_destroy($this->uploadEvent);
+        }
         $ffi->rb200_buffer_free($this->dptr);
         if ($this->hptr !== null) {
             $ffi->rb200_host_free($this->hptr);
@@ -80,9 +88,22 @@ class CudaBuffer implements LinearBuffer
     public function value_size() : int { return $this->valueSize; }
     public function count() : int { return $this->size; }
 
+    /**
+     * devicePtr() queues the h2d of the pinned mirror asynchronously, possibly behind long kernels: the host may
+     * not modify the mirror before that copy has read it ($X[0]=a; op($X); $X[0]=b must show `a` to op).
+     */
+    protected function waitUpload() : void
+    {
+        if ($this->uploadPending) {
+            CudaFFI::check(CudaFFI::lib()->rb200_event_synchronize($this->uploadEvent));
+            $this->uploadPending = false;
+        }
+    }
+
     protected function mirror()
     {
         $ffi = CudaFFI::lib();
+        $this->waitUpload();
         if ($this->host === null) {
             $p = $ffi->new('void*');
             CudaFFI::check($ffi->rb200_host_alloc(max(16, $this->size * $this->valueSize), FFI::addr($p)));
@@ -101,8 +122,16 @@ class CudaBuffer implements LinearBuffer
     public function devicePtr()
     {
         if ($this->hostDirty) {
-            CudaFFI::check(CudaFFI::lib()->rb200_buffer_h2d_async(
+            $ffi = CudaFFI::lib();
+            CudaFFI::check($ffi->rb200_buffer_h2d_async(
                 $this->dptr, 0, $this->hptr, $this->size * $this->valueSize));
+            if ($this->uploadEvent === null) {
+                $ev = $ffi->new('void*');
+                CudaFFI::check($ffi->rb200_event_create(FFI::addr($ev)));
+                $this->uploadEvent = $ev;
+            }
+            CudaFFI::check($ffi->rb200_event_record($this->uploadEvent));
+            $this->uploadPending = true;
             $this->hostDirty = false;
         }
         return $this->dptr;

@@ -132,6 +132,22 @@ class CudaFFI
                            int64_t stride_d, int64_t stride_h, int64_t stride_w, int padding, int channels_first,
                            int64_t dilation_d, int64_t dilation_h, int64_t dilation_w, int cols_channels_first,
                            void* cols, int64_t cols_offset, int64_t cols_size);
+        int rb200_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes);
+        int rb200_set_stream(void* cuda_stream);
+        int rb200_get_stream(void** cuda_stream);
+        int rb200_get_default_gemm_mode(int* mode);
+        int rb200_launch_count(int64_t* count, int reset);
+        const char* rb200_last_gemm_path(void);
+        int rb200_buffer_d2h_async(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes);
+        int rb200_event_create(void** event);
+        int rb200_event_destroy(void* event);
+        int rb200_event_record(void* event);
+        int rb200_event_synchronize(void* event);
+        int rb200_event_query(void* event, int* done);
+        int rb200_event_wait(void* event);
+        int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t offA, int64_t ldA, const float* B, int64_t offB, int64_t ldB, float beta, float* C, int64_t offC, int64_t ldC, int mode, void* mc_C);
+        int rb200_reduce_argmax_partial(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA, int stripe_starts_at_global_0, void* records, int64_t off_records);
+        int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels, int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w, int padding, int64_t dilation_h, int64_t dilation_w, const void* kernel, int64_t kernel_offset, int64_t filters, const void* bias, int64_t bias_offset, void* out, int64_t out_offset, int mode);
         CDEF;
 
     public static function lib() : FFI

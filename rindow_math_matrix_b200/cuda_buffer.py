@@ -259,7 +259,7 @@ class CudaBuffer:
         a = np.ascontiguousarray(a, dtype=self._np).reshape(-1)
         if offset < 0 or offset + a.size > self._size:
             raise InvalidArgumentException("array does not fit in buffer")
-        self.write(a, a.nbytes, offset * self._np.itemsize)
+        CudaBuffer.write(self, a, a.nbytes, offset * self._np.itemsize)
         return self
 
     def to_numpy(self) -> np.ndarray:
@@ -275,7 +275,7 @@ class CudaBuffer:
             raise InvalidArgumentException("range does not fit in buffer")
         out = np.empty(n, self._np)
         if n:
-            self.read(out, n * self._np.itemsize, offset * self._np.itemsize)
+            CudaBuffer.read(self, out, n * self._np.itemsize, offset * self._np.itemsize)
         return out
 
     @property

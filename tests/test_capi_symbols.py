@@ -46,6 +46,25 @@ def test_compute_without_init_fails_loudly():
         _capi.check(rc)
 
 
+def test_php_cdef_declares_every_header_symbol():
+    """The PHP-FFI cdef (php/MatlibCuda/CudaFFI.php) is the reference-side binding of the same header: every entry
+    point include/rindow_b200.h declares must be reachable from PHP (round 1 missed rb200_conv2d_forward and 7 more)."""
+    with open(os.path.join(ROOT, "php", "MatlibCuda", "CudaFFI.php")) as f:
+        php = f.read()
+    cdef = php[php.index("<<<'CDEF'"):php.index("CDEF;")]
+    declared = set(re.findall(r"\b(rb200_\w+)\s*\(", cdef))
+    assert sorted(declared) == header_symbols()
+    for name in ("CudaDeviceBuffer", "CudaDeviceBufferFactory", "CudaQueue", "CudaEventList", "NDArrayCuda",
+                 "LinearAlgebraCuda", "MatrixOperatorCuda"):
+        assert os.path.exists(os.path.join(ROOT, "php", "MatlibCuda", name + ".php")), name
+
+
+@pytest.mark.gpu
+def test_library_is_sm100a_only_on_the_gpu_box():
+    """The same SASS check where the driver's GPU tier runs (it only collects -m gpu tests)."""
+    test_library_is_sm100a_only_with_blackwell_instructions()
+
+
 def test_library_is_sm100a_only_with_blackwell_instructions():
     """cuobjdump shows sm_100a code with tcgen05 (UTCHMMA), TMA (UTMALDG) and TMEM loads (LDTM)."""
     import shutil
