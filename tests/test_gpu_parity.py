@@ -459,6 +459,27 @@ def test_gemm_simt_small(mnk, tA, tB, dt, cuda_service):
         assert err < (2e-6 if dt == dtypes.float32 else 1e-14), (err, path)
 
 
+BIG_SIMT = [(1536, 1664, 300), (1500, 1303, 257), (2048, 1152, 72), (1281, 1290, 33), (3000, 700, 129)]
+
+
+@pytest.mark.parametrize("mnk", BIG_SIMT, ids=[str(s) for s in BIG_SIMT])
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
+def test_gemm_simt_big_tiles(mnk, tA, tB, dt, cuda_service):
+    """The large-tile FFMA / DFMA kernel (128 x 128 x 16 / 128 x 64 x 8, double-buffered): aligned operands take its
+    128-bit loads, odd leading dimensions / offsets its scalar loads; M, N, K tails; beta != 0; all transposes."""
+    m, n, k = mnk
+    for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (-0.5, 2.0, 9, 3), (1.0, 1.0, 4, 4)):
+        err, path = _gemm_case(cuda_service, rb.GEMM_FP32_SIMT, m, n, k, tA, tB, alpha, beta, off, off + 1, off + 2,
+                               ldx, dt=dt)
+        want = ("simt_f32_big",) if dt == dtypes.float32 else ("simt_f64_big",)
+        if dt == dtypes.float32 and k <= 64 and not tA and not tB:
+            want += ("simt_f32_shortk",)                     # short reductions keep their own kernel
+        assert path in want, path
+        assert err < (2e-6 if dt == dtypes.float32 else 1e-14), (err, path)
+
+
 TC_GEMMS = [(256, 256, 256), (128, 128, 32), (128, 256, 64), (384, 640, 160), (512, 384, 1024), (200, 300, 100),
             (1000, 520, 68), (129, 257, 33), (2048, 128, 128), (128, 2048, 1024)]
 
@@ -528,7 +549,7 @@ def test_gemm_tall_skinny_conv_shapes(mnk, cuda_service):
         for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (0.5, 1.5, 3, 1), (1.0, 1.0, 4, 4)):
             err, path = _gemm_case(cuda_service, mode, m, n, k, False, False, alpha, beta, off, off, off, ldx)
             if mode == rb.GEMM_FP32_SIMT:
-                assert path in ("simt_f32_shortk", "simt_f32") and err < 2e-6, (path, err)
+                assert path in ("simt_f32_shortk", "simt_f32", "simt_f32_big") and err < 2e-6, (path, err)
             elif mode == rb.GEMM_TF32:
                 if skinny:
                     assert path in ("tcgen05_tf32_skinny", "tcgen05_tf32", "tcgen05_tf32_2cta", "tcgen05_tf32_128"), path
