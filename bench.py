@@ -155,6 +155,41 @@ class ClockSampler:
             self._stop.set()
             self.t.join()
 
+    def nvlink_bytes(self):
+        """(tx, rx) payload bytes this GPU has moved over all its NVLink ports since boot (NVML field values
+        NVLINK_THROUGHPUT_DATA_TX / RX, KiB, scope = all links); None when the driver does not expose them."""
+        if not self.ok:
+            return None
+        try:
+            nv = self.nv
+            ids = [nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+            try:
+                vals = nv.nvmlDeviceGetFieldValues(self.h, [(i, 0xFFFFFFFF) for i in ids])   # scopeId = all links
+            except Exception:
+                vals = nv.nvmlDeviceGetFieldValues(self.h, ids)
+            out = []
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    raise RuntimeError("field value not available")
+                out.append(int(v.value.ullVal) * 1024)
+            return tuple(out)
+        except Exception:
+            pass
+        # fallback: `nvidia-smi nvlink -gt d` (per-link "Data Tx / Rx: N KiB" lines of this GPU)
+        try:
+            import re
+            import subprocess
+            idx = self.nv.nvmlDeviceGetIndex(self.h)
+            txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(idx)], capture_output=True, text=True,
+                                 timeout=20).stdout
+            tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+            rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+            if tx == 0 and rx == 0:
+                return None
+            return (tx * 1024, rx * 1024)
+        except Exception:
+            return None
+
     def summary(self):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
@@ -341,7 +376,9 @@ def run_b200(args):
     headline_step = fused_step if fused is not None else compute_step
     with sampler:
         _capi.launch_count(reset=True)
+        nv0 = sampler.nvlink_bytes()
         total_ms = timed(headline_step, args.steps, args.warmup, tag="headline")
+        nv1 = sampler.nvlink_bytes()
         launches = _capi.launch_count()
         gpu_launches = launches - launches * args.warmup // (args.steps + args.warmup)
         gemm_path = _capi.last_gemm_path()
@@ -395,6 +432,13 @@ def run_b200(args):
                 "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "kernel": gemm_path,
                 "multicast": bool(fused.multicast),
                 "peer_rows_rel_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
+                "nvlink_counters": (None if not (nv0 and nv1) else {
+                    "tx_bytes_per_step": (nv1[0] - nv0[0]) / (args.steps + args.warmup),
+                    "rx_bytes_per_step": (nv1[1] - nv0[1]) / (args.steps + args.warmup),
+                    "tx_GBps_during_step": (nv1[0] - nv0[0]) / (args.steps + args.warmup) / (ms_per_step * 1e-3) / 1e9,
+                    "rx_GBps_during_step": (nv1[1] - nv0[1]) / (args.steps + args.warmup) / (ms_per_step * 1e-3) / 1e9,
+                    "note": "NVML NVLINK_THROUGHPUT_DATA_TX / RX of this rank's GPU (all links) read before and after "
+                            "the headline region (warm-up steps included in the count)"}),
                 "nvlink_bytes_out_per_rank": rows * n * 4 * (1 if fused.multicast else world - 1),
                 "nvlink_bytes_in_per_rank": rows * n * 4 * (world - 1) + (rows * n * 4 if fused.multicast else 0),
                 "note": "the headline: C stripe stored into every rank's full C from the GEMM epilogue (%s) + "
@@ -427,7 +471,13 @@ def run_b200(args):
     hA, hB, hC = job.host_buffers()
     hA[...] = Ah.reshape(rows, n)
     hB[...] = Bh.reshape(n, n)[job.bstart:job.bstart + job.brows]
-    pcie = measure_pcie(_capi, job) if not args.quick else None
+    pcie = measure_pcie(_capi, job) if (not args.quick or world > 1) else None
+    if pcie and world > 1:
+        # the same copies with ALL ranks going at once: what the host side (one socket's memory and I/O fabric serving
+        # every GPU's link) sustains per rank when the links are used together, as the e2e step uses them
+        barrier()
+        conc = measure_pcie(_capi, job, barrier=barrier)
+        pcie["concurrent_h2d_gbs"], pcie["concurrent_d2h_gbs"] = conc["h2d_gbs"], conc["d2h_gbs"]
     _capi.sync()
 
     def e2e_step():
@@ -446,7 +496,11 @@ def run_b200(args):
         bound_ms = max(h2d_b / (pcie["h2d_gbs"] * 1e6), d2h_b / (pcie["d2h_gbs"] * 1e6))
         e2e["pcie"] = pcie
         e2e["pcie_frac"] = bound_ms / e2e_ms
-        e2e["pcie_note"] = "max(h2d bytes / measured h2d GB/s, d2h bytes / measured d2h GB/s) / step time (this rank's link)"
+        if "concurrent_h2d_gbs" in pcie:
+            cb = max(h2d_b / (pcie["concurrent_h2d_gbs"] * 1e6), d2h_b / (pcie["concurrent_d2h_gbs"] * 1e6))
+            e2e["pcie_frac_concurrent"] = cb / e2e_ms
+        e2e["pcie_note"] = ("max(h2d bytes / measured h2d GB/s, d2h bytes / measured d2h GB/s) / step time (this rank's link); "
+                            "_concurrent: against the rates measured with every rank copying at once")
     got = hC[:2].astype(np.float64)
     ref = Ah.reshape(rows, n)[:2].astype(np.float64) @ Bh.reshape(n, n).astype(np.float64)
     e2e["rows_rel_err"] = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
@@ -545,9 +599,9 @@ def tf32_measured_peak():
         return None
 
 
-def measure_pcie(_capi, job):
+def measure_pcie(_capi, job, barrier=None):
     """This rank's PCIe link: one large pinned h2d, one d2h, timed with the host clock around synchronous copies
-    (256 MiB each, best of 3)."""
+    (up to 256 MiB each, best of 3).  With `barrier` every rank starts each copy together."""
     import ctypes
     lib = _capi.load()
     dA, hA = job.A.raw_pointers()
@@ -558,6 +612,8 @@ def measure_pcie(_capi, job):
         best = 1e30
         for _ in range(3):
             _capi.sync()
+            if barrier is not None:
+                barrier()
             t0 = time.perf_counter()
             _capi.check(fn(*args_))
             best = min(best, time.perf_counter() - t0)

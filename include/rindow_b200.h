@@ -133,6 +133,18 @@ int rb200_event_record(void* event);
 int rb200_event_synchronize(void* event);
 int rb200_event_query(void* event, int* done);
 int rb200_event_wait(void* event);
+/* CUDA-graph capture of a launch-bound sequence of calls (many small gemm / elementwise calls whose kernels run for a
+ * few microseconds: the host-side cost of issuing them dominates).  Between begin and end every compute call on the
+ * library stream is RECORDED instead of executed; rb200_graph_launch replays the recorded kernels with one driver
+ * call.  Pointers, sizes and scalars are baked in.  Calls that allocate or synchronise are not capturable: issue the
+ * sequence once before capturing (workspace and kernel attributes are then in place) and do not call the
+ * scalar-returning entry points (asum, sum, imax ...) or buffer h2d / d2h inside a capture.  The reference has no
+ * counterpart (its OpenCL queue is issued call by call, LinearAlgebraCL.php:145-152); a PHP caller would wrap a
+ * training step's driver calls the same way. */
+int rb200_graph_begin(void);
+int rb200_graph_end(void** graph_exec);
+int rb200_graph_launch(void* graph_exec);
+int rb200_graph_destroy(void* graph_exec);
 
 /* ---- BLAS: replaces PhpBlas::gemm (src/Drivers/MatlibPHP/PhpBlas.php:849-948) ------- */
 /* C[m,n] = alpha * op(A)[m,k] * op(B)[k,n] (+ beta * C iff beta != 0; C is not read when

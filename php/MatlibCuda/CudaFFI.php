@@ -148,6 +148,10 @@ class CudaFFI
         int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t offA, int64_t ldA, const float* B, int64_t offB, int64_t ldB, float beta, float* C, int64_t offC, int64_t ldC, int mode, void* mc_C);
         int rb200_reduce_argmax_partial(int dtype, int64_t m, int64_t n, int64_t k, const void* A, int64_t offA, int stripe_starts_at_global_0, void* records, int64_t off_records);
         int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels, int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w, int padding, int64_t dilation_h, int64_t dilation_w, const void* kernel, int64_t kernel_offset, int64_t filters, const void* bias, int64_t bias_offset, void* out, int64_t out_offset, int mode);
+        int rb200_graph_begin(void);
+        int rb200_graph_end(void** graph_exec);
+        int rb200_graph_launch(void* graph_exec);
+        int rb200_graph_destroy(void* graph_exec);
         CDEF;
 
     public static function lib() : FFI

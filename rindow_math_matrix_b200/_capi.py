@@ -54,6 +54,10 @@ SIGNATURES = {
     "rb200_event_synchronize": (i32, [vp]),
     "rb200_event_query": (i32, [vp, ctypes.POINTER(i32)]),
     "rb200_event_wait": (i32, [vp]),
+    "rb200_graph_begin": (i32, []),
+    "rb200_graph_end": (i32, [ctypes.POINTER(vp)]),
+    "rb200_graph_launch": (i32, [vp]),
+    "rb200_graph_destroy": (i32, [vp]),
     "rb200_sgemm": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32]),
     "rb200_dgemm": (i32, [i32, i32, i32, i64, i64, i64, f64, vp, i64, i64, vp, i64, i64, f64, vp, i64, i64]),
     "rb200_sgemm_streamed": (i32, [i32, i32, i32, i64, i64, i64, f32, vp, vp, i64, i64, vp, vp, i64, i64,
@@ -193,6 +197,41 @@ def set_stream(cuda_stream_ptr: int | None) -> None:
     library-owned stream."""
     ptr = vp(-1 & 0xFFFFFFFFFFFFFFFF) if cuda_stream_ptr is None else vp(cuda_stream_ptr)
     check(load().rb200_set_stream(ptr))
+
+
+class Graph:
+    """`with Graph() as g: <driver calls>` records the calls' kernels (rb200_graph_begin / end); g.launch() replays them
+    with one driver call.  Issue the sequence once before capturing (allocations and synchronising calls cannot be
+    captured)."""
+
+    def __init__(self):
+        self._exec = None
+
+    def __enter__(self):
+        check(load().rb200_graph_begin())
+        return self
+
+    def __exit__(self, et, ev, tb):
+        ex = vp()
+        rc = load().rb200_graph_end(ctypes.byref(ex))
+        if et is None:
+            check(rc)
+            self._exec = ex
+        return False
+
+    def launch(self) -> None:
+        check(load().rb200_graph_launch(self._exec))
+
+    def close(self) -> None:
+        if self._exec is not None:
+            load().rb200_graph_destroy(self._exec)
+            self._exec = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def last_gemm_path() -> str:

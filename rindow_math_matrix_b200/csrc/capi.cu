@@ -325,6 +325,62 @@ int rb200_host_free(void* hptr)
     return RB200_OK;
 }
 
+/* ---- CUDA graphs ------------------------------------------------------------------------------- */
+
+namespace {
+struct GraphExec { cudaGraphExec_t exec; int64_t launches; };
+int64_t g_capture_launch_base = -1;
+}
+
+int rb200_graph_begin(void)
+{
+    RB_REQUIRE_INIT();
+    if (g_capture_launch_base >= 0) RB_INVALID("a capture is already in progress");
+    RB_CUDA(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeRelaxed));
+    g_capture_launch_base = ctx().launches;
+    return RB200_OK;
+}
+
+int rb200_graph_end(void** graph_exec)
+{
+    RB_REQUIRE_INIT();
+    if (!graph_exec) RB_INVALID("graph_exec is NULL");
+    if (g_capture_launch_base < 0) RB_INVALID("no capture in progress");
+    const int64_t recorded = ctx().launches - g_capture_launch_base;
+    ctx().launches = g_capture_launch_base;              // recorded, not executed
+    g_capture_launch_base = -1;
+    cudaGraph_t graph = nullptr;
+    RB_CUDA(cudaStreamEndCapture(ctx().stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return rb200::cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    GraphExec* g = new GraphExec{exec, recorded};
+    *graph_exec = g;
+    return RB200_OK;
+}
+
+int rb200_graph_launch(void* graph_exec)
+{
+    RB_REQUIRE_INIT();
+    if (!graph_exec) RB_INVALID("graph_exec is NULL");
+    GraphExec* g = reinterpret_cast<GraphExec*>(graph_exec);
+    RB_CUDA(cudaGraphLaunch(g->exec, ctx().stream));
+    rb200::count_launch((int)g->launches);
+    return RB200_OK;
+}
+
+int rb200_graph_destroy(void* graph_exec)
+{
+    RB_REQUIRE_INIT();
+    if (!graph_exec) return RB200_OK;
+    GraphExec* g = reinterpret_cast<GraphExec*>(graph_exec);
+    RB_CUDA(cudaStreamSynchronize(ctx().stream));
+    RB_CUDA(cudaGraphExecDestroy(g->exec));
+    delete g;
+    return RB200_OK;
+}
+
 /* ---- events ------------------------------------------------------------------------------------- */
 
 int rb200_event_create(void** event)

@@ -1013,6 +1013,11 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         const double t_pair = (double)rb_ceil_div(tiles_pair, pairs) * (256.0 * BN / 2.0);
         const double t_small = (double)rb_ceil_div(tiles_small, (int64_t)c.sm_count) * (128.0 * 128.0) * 1.15;
         const bool small_tiles = planes == 1 && use_small && c.n_gemm_peers == 0 && !c.gemm_mc && (!pair_ok || t_small < t_pair);
+        // ... and 128 x 64 tiles when even those leave more than a third of the SMs idle (1024^3: 64 tiles of 128 x 128
+        // on 148 SMs -> 128 tiles of 128 x 64; the launch is latency-bound, not tensor-bound, at that size)
+        const int64_t tiles_64 = rb_ceil_div(M, 128) * rb_ceil_div(N, 64);
+        const double t_64 = (double)rb_ceil_div(tiles_64, (int64_t)c.sm_count) * (128.0 * 64.0) * 1.3;
+        const bool tiny_tiles = small_tiles && t_64 < t_small && (!pair_ok || t_64 < t_pair);
         // 3xTF32: the pair tile is 256 x 128 and the single-CTA tile 128 x 128 (the same work per SM); small
         // problems take 128 x 64 tiles
         const int64_t tiles_x3s = rb_ceil_div(M, 128) * rb_ceil_div(N, 64);
@@ -1026,6 +1031,14 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
             p.num_n_blocks = (int)rb_ceil_div(N, 64);
             rc = launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mBs, p);
             c.last_gemm_path = "tcgen05_tf32x3_64";
+        } else if (tiny_tiles) {
+            CUtensorMap mBs;
+            if (!b_mn) rc = make_map(&mBs, pb, kl, N, sldB, planes, plsB, TC_BK, 64, k_sw);
+            else       rc = make_map(&mBs, pb, N, kl, sldB, planes, plsB, 32, TC_BK, mn_sw);
+            if (rc != RB200_OK) return rc;
+            p.num_n_blocks = (int)rb_ceil_div(N, 64);
+            rc = launch_by_major<64, 1, 8>(a_mn, b_mn, mA, mBs, p);
+            c.last_gemm_path = "tcgen05_tf32_64";
         } else if (small_tiles) {
             CUtensorMap mBs;
             if (!b_mn) rc = make_map(&mBs, pb, kl, N, sldB, planes, plsB, TC_BK, 128, k_sw);
