@@ -61,6 +61,12 @@ extern "C" {
 #define RB200_UINT64    8
 #define RB200_FLOAT32   12
 #define RB200_FLOAT64   13
+/* complex storage (PhpBuffer.php:38-41, 60-61: complex_float 8 bytes, complex_double 16 bytes, interleaved real / imag
+ * as dump() packs them :153-158).  Buffers of these dtypes can be allocated, filled, copied, swapped and moved between
+ * host and device; the arithmetic entry points take real dtypes only (the reference's complex gemm branch,
+ * PhpBlas.php:890-926, is outside the hot path). */
+#define RB200_COMPLEX64  16
+#define RB200_COMPLEX128 17
 
 /* CBLAS-valued enums (reference: Interop\Polite\Math\Matrix\BLAS; LinearAlgebra.php:16-17) */
 #define RB200_ROW_MAJOR      101
@@ -96,7 +102,7 @@ int         rb200_get_default_gemm_mode(int* mode);
  * (bench.py's "gpu_launches"). */
 int         rb200_launch_count(int64_t* count, int reset);
 /* Name of the kernel family the last rb200_sgemm/dgemm/conv2d_forward dispatched to: "tcgen05_tf32_2cta",
- * "tcgen05_tf32", "tcgen05_tf32_128", "tcgen05_tf32x3", "tcgen05_tf32x3_64", "tcgen05_tf32x3_2cta", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
+ * "tcgen05_tf32", "tcgen05_tf32_128", "tcgen05_tf32_64", "tcgen05_tf32x3", "tcgen05_tf32x3_64", "tcgen05_tf32x3_2cta", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
  * "simt_f32", "simt_f64" (64 x 64 tiles: small / odd problems), "simt_f32_big", "simt_f64_big" (128 x 128 / 128 x 64
  * double-buffered tiles: every FFMA / DFMA problem that fills the machine). */
 const char* rb200_last_gemm_path(void);

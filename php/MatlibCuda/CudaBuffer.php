@@ -25,6 +25,10 @@ class CudaBuffer implements LinearBuffer
             NDArray::uint16  => [6, 2, 'uint16_t'], NDArray::uint32  => [7, 4, 'uint32_t'],
             NDArray::uint64  => [8, 8, 'uint64_t'], NDArray::float32 => [12, 4, 'float'],
             NDArray::float64 => [13, 8, 'double'],
+            // complex storage (PhpBuffer.php:38-41, 60-61): interleaved real / imag pairs; the FFI view is the
+            // component type, offsetGet / offsetSet translate between pairs and objects with real / imag
+            NDArray::complex64  => [16, 8,  'float'],
+            NDArray::complex128 => [17, 16, 'double'],
         ];
     }
 
@@ -55,8 +59,9 @@ class CudaBuffer implements LinearBuffer
         CudaFFI::check($ffi->rb200_buffer_alloc($size * $this->valueSize, FFI::addr($p)));
         $this->dptr = $p;
         if ($zero && $size > 0) {
-            $z = $ffi->new($this->ctype);
-            CudaFFI::check($ffi->rb200_buffer_fill($this->abiDtype, $this->dptr, 0, $size, FFI::addr($z)));
+            // one zero element on the host (complex: a real / imag pair of the component type)
+            $z = $ffi->new($this->ctype.'[2]');
+            CudaFFI::check($ffi->rb200_buffer_fill($this->abiDtype, $this->dptr, 0, $size, $z));
         }
         $this->devDirty = true;
     }
@@ -108,7 +113,7 @@ class CudaBuffer implements LinearBuffer
             $p = $ffi->new('void*');
             CudaFFI::check($ffi->rb200_host_alloc(max(16, $this->size * $this->valueSize), FFI::addr($p)));
             $this->hptr = $p;
-            $this->host = $ffi->cast($this->ctype.'['.max(1, $this->size).']', $p);
+            $this->host = $ffi->cast($this->ctype.'['.max(1, $this->size * ($this->isComplexDtype() ? 2 : 1)).']', $p);
             $this->devDirty = true;
         }
         if ($this->devDirty) {
@@ -152,7 +157,7 @@ class CudaBuffer implements LinearBuffer
             $p = $ffi->new('void*');
             CudaFFI::check($ffi->rb200_host_alloc(max(16, $this->size * $this->valueSize), FFI::addr($p)));
             $this->hptr = $p;
-            $this->host = $ffi->cast($this->ctype.'['.max(1, $this->size).']', $p);
+            $this->host = $ffi->cast($this->ctype.'['.max(1, $this->size * ($this->isComplexDtype() ? 2 : 1)).']', $p);
             $this->devDirty = true;
         }
     }
@@ -172,6 +177,10 @@ class CudaBuffer implements LinearBuffer
         if (!$this->offsetExists($offset)) {
             throw new RuntimeException("Index invalid or out of range");
         }
+        if ($this->isComplexDtype()) {
+            $m = $this->mirror();
+            return \Rindow\Math\Matrix\C($m[2*$offset], i:$m[2*$offset+1]);     // src/C.php
+        }
         $v = $this->mirror()[$offset];
         return ($this->dtype == NDArray::bool) ? ($v ? true : false) : $v;
     }
@@ -181,8 +190,22 @@ class CudaBuffer implements LinearBuffer
         if (!$this->offsetExists($offset)) {
             throw new RuntimeException("Index invalid or out of range");
         }
-        $this->mirror()[$offset] = $value;
+        if ($this->isComplexDtype()) {
+            if (!is_object($value) || !property_exists($value, 'real') || !property_exists($value, 'imag')) {
+                throw new InvalidArgumentException("Cannot convert to complex number.: ".gettype($value));
+            }
+            $m = $this->mirror();
+            $m[2*$offset] = $value->real;
+            $m[2*$offset+1] = $value->imag;
+        } else {
+            $this->mirror()[$offset] = $value;
+        }
         $this->hostDirty = true;
+    }
+
+    protected function isComplexDtype() : bool
+    {
+        return $this->dtype == NDArray::complex64 || $this->dtype == NDArray::complex128;
     }
 
     public function offsetUnset($offset) : void { throw new \LogicException("Illegal Operation"); }

@@ -89,7 +89,8 @@ static inline int rb_dtype_size(int dtype)
         case RB200_BOOL: case RB200_INT8: case RB200_UINT8: return 1;
         case RB200_INT16: case RB200_UINT16: return 2;
         case RB200_INT32: case RB200_UINT32: case RB200_FLOAT32: return 4;
-        case RB200_INT64: case RB200_UINT64: case RB200_FLOAT64: return 8;
+        case RB200_INT64: case RB200_UINT64: case RB200_FLOAT64: case RB200_COMPLEX64: return 8;
+        case RB200_COMPLEX128: return 16;
         default: return 0;
     }
 }

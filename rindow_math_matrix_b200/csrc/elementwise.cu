@@ -227,6 +227,26 @@ int fill_launch(void* dptr, int64_t off, int64_t n, const void* value)
 }
 
 
+__global__ void __launch_bounds__(256) fill_pairs_kernel(uint64_t* __restrict__ p, int64_t n, uint64_t a, uint64_t b)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        *reinterpret_cast<ulonglong2*>(p + 2 * i) = make_ulonglong2(a, b);
+    }
+}
+
+int fill_pairs_launch(void* dptr, int64_t off, int64_t n, uint64_t a, uint64_t b)
+{
+    rb200::Context& c = rb200::ctx();
+    uint64_t* p = reinterpret_cast<uint64_t*>(dptr) + 2 * off;
+    int64_t blocks = rb_ceil_div(n, 256 * 4);
+    const int64_t max_blocks = (int64_t)c.sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    fill_pairs_kernel<<<(unsigned)blocks, 256, 0, c.stream>>>(p, n, a, b);
+    RB_LAUNCH_CHECK("fill_pairs_kernel");
+    return RB200_OK;
+}
+
 template <typename T>
 int bc_launch(int op, int trans, int64_t m, int64_t n, const void* X, int64_t offX, int64_t incX,
               void* A, int64_t offA, int64_t ldA)
@@ -288,6 +308,15 @@ int rb200_buffer_fill(int dtype, void* dptr, int64_t off, int64_t n, const void*
         case 2: return fill_launch<uint16_t>(dptr, off, n, value);
         case 4: return fill_launch<uint32_t>(dptr, off, n, value);
         case 8: return fill_launch<uint64_t>(dptr, off, n, value);
+        case 16: {
+            // complex128: pairs of 8-byte words; equal halves fill as 2n words, anything else word by word would need
+            // a 16-byte element type -- two strided fills of n words each do it with the kernel at hand
+            uint64_t w[2];
+            memcpy(w, value, 16);
+            if (w[0] == w[1]) return fill_launch<uint64_t>(dptr, 2 * off, 2 * n, &w[0]);
+            int rc = fill_pairs_launch(dptr, off, n, w[0], w[1]);
+            return rc;
+        }
         default: RB_UNSUPPORTED("fill: unsupported dtype %d", dtype);
     }
 }

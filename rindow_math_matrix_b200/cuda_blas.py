@@ -279,7 +279,8 @@ class CudaBlas:
         self._device_buffers(X=X, Y=Y)
         if X.dtype() != Y.dtype():
             raise InvalidArgumentException("Unmatch data type for X and Y")
-        _capi.check(self._lib.rb200_copy(self._float_dtype(X, "copy"), n, X.device_ptr(), offsetX, incX,
+        dt = X.dtype() if X.dtype() in dtypes.COMPLEX_TYPES else self._float_dtype(X, "copy")   # complex: data movement only
+        _capi.check(self._lib.rb200_copy(dt, n, X.device_ptr(), offsetX, incX,
                                          Y.device_ptr_rw(), offsetY, incY))
 
     # ---- gemv (PhpBlas.php:762-844) ---------------------------------------------------------------------
@@ -365,7 +366,8 @@ class CudaBlas:
         self._device_buffers(X=X, Y=Y)
         if X.dtype() != Y.dtype():
             raise InvalidArgumentException("Unmatch data type for X and Y")
-        _capi.check(self._lib.rb200_swap(self._float_dtype(X, "swap"), n, X.device_ptr_rw(), offsetX, incX,
+        dt = X.dtype() if X.dtype() in dtypes.COMPLEX_TYPES else self._float_dtype(X, "swap")
+        _capi.check(self._lib.rb200_swap(dt, n, X.device_ptr_rw(), offsetX, incX,
                                          Y.device_ptr_rw(), offsetY, incY))
 
     def __getattr__(self, name):

@@ -120,9 +120,18 @@ class CudaBuffer:
         v = self.host()[i]
         return bool(v) if self._dtype == dtypes.bool_ else v.item()
 
+    def _element_value(self, value):
+        """Complex buffers take complex values / objects with real and imag, like PhpBuffer::offsetSet
+        (PhpBuffer.php:124-133); everything else is stored as given."""
+        if self._dtype in dtypes.COMPLEX_TYPES:
+            if isinstance(value, (bool, int, float, np.integer, np.floating)) or not (hasattr(value, "real") and hasattr(value, "imag")):
+                raise InvalidArgumentException("Cannot convert to complex number.: " + type(value).__name__)
+            return complex(value.real, value.imag)
+        return value
+
     def __setitem__(self, i, value) -> None:
         i = self._index(i)
-        self.host()[i] = value
+        self.host()[i] = self._element_value(value)
         self._host_dirty = True
 
     def offsetExists(self, i) -> bool:

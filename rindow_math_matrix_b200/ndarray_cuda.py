@@ -123,7 +123,7 @@ class CudaDeviceBuffer(CudaBuffer):
 
     def __setitem__(self, i, value) -> None:
         i = self._index(i)
-        one = np.asarray([value], self._np)
+        one = np.asarray([self._element_value(value)], self._np)
         _capi.check(self._lib.rb200_buffer_h2d(self._dptr, i * self._np.itemsize, one.ctypes.data, self._np.itemsize))
 
     def dump(self) -> bytes:

@@ -38,7 +38,7 @@ def test_sgemm_allgather_local_peers(total, start, rows, n, k, mode, path, n_pee
                        [p.raw_pointers()[0] for p in peers])
     # without peers, problems that leave most CTA pairs idle take the 128 x 128 single-CTA tiles instead
     small = {rb.GEMM_TF32: "tcgen05_tf32_128", rb.GEMM_TF32X3: "tcgen05_tf32x3_64"}.get(mode)
-    assert _capi.last_gemm_path() in ((path, small) if n_peers == 0 else (path,))
+    assert _capi.last_gemm_path() in ((path, small, "tcgen05_tf32_64") if n_peers == 0 else (path,))
     got = C.to_numpy().reshape(total, n)
     # the plain call on the same operands is the reference for "same arithmetic": bit-identical
     C2 = CudaBuffer(total * n, f32).from_numpy(sentinel.reshape(-1))
