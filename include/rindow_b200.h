@@ -103,8 +103,9 @@ int         rb200_get_default_gemm_mode(int* mode);
 int         rb200_launch_count(int64_t* count, int reset);
 /* Name of the kernel family the last rb200_sgemm/dgemm/conv2d_forward dispatched to: "tcgen05_tf32_2cta",
  * "tcgen05_tf32", "tcgen05_tf32_128", "tcgen05_tf32_64", "tcgen05_tf32x3", "tcgen05_tf32x3_64", "tcgen05_tf32x3_2cta", "tcgen05_tf32[x3]_skinny", "tcgen05_tf32[x3]_conv", "simt_f32_shortk",
- * "simt_f32", "simt_f64" (64 x 64 tiles: small / odd problems), "simt_f32_big", "simt_f64_big" (128 x 128 / 128 x 64
- * double-buffered tiles: every FFMA / DFMA problem that fills the machine). */
+ * "simt_f32", "simt_f64" (64 x 64 tiles: small / odd problems), "simt_f32_big" (128 x 128 x 16 double-buffered FFMA
+ * tiles: every float32 FFMA problem that fills the machine), "dmma_f64" (128 x 64 x 16 tiles on the FP64 tensor pipe,
+ * mma.sync m16n8k8: every float64 problem that fills the machine; "simt_f64_big" is its DFMA form, RB200_DGEMM_DMMA=0). */
 const char* rb200_last_gemm_path(void);
 
 /* ---- buffers: replaces PhpBLASFactory::Buffer (PhpBLASFactory.php:35) storage and the

@@ -467,17 +467,39 @@ BIG_SIMT = [(1536, 1664, 300), (1500, 1303, 257), (2048, 1152, 72), (1281, 1290,
 @pytest.mark.parametrize("tB", [False, True])
 @pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64])
 def test_gemm_simt_big_tiles(mnk, tA, tB, dt, cuda_service):
-    """The large-tile FFMA / DFMA kernel (128 x 128 x 16 / 128 x 64 x 8, double-buffered): aligned operands take its
-    128-bit loads, odd leading dimensions / offsets its scalar loads; M, N, K tails; beta != 0; all transposes."""
+    """The large-tile kernels -- FFMA 128 x 128 x 16 for float32, DMMA (mma.sync m16n8k8 f64) 128 x 64 x 16 for float64,
+    both double-buffered: aligned operands take the 128-bit loads, odd leading dimensions / offsets the scalar loads;
+    M, N, K tails; beta != 0; all transposes.  RB200_DGEMM_DMMA=0 keeps the DFMA kernel (covered by the env test)."""
     m, n, k = mnk
     for alpha, beta, off, ldx in ((1.0, 0.0, 0, 0), (-0.5, 2.0, 9, 3), (1.0, 1.0, 4, 4)):
         err, path = _gemm_case(cuda_service, rb.GEMM_FP32_SIMT, m, n, k, tA, tB, alpha, beta, off, off + 1, off + 2,
                                ldx, dt=dt)
-        want = ("simt_f32_big",) if dt == dtypes.float32 else ("simt_f64_big",)
+        want = ("simt_f32_big",) if dt == dtypes.float32 else ("dmma_f64",)        # float64: FP64 tensor pipe (DMMA)
         if dt == dtypes.float32 and k <= 64 and not tA and not tB:
             want += ("simt_f32_shortk",)                     # short reductions keep their own kernel
         assert path in want, path
         assert err < (2e-6 if dt == dtypes.float32 else 1e-14), (err, path)
+
+
+def test_dgemm_dfma_kernel_still_agrees(cuda_service):
+    """The DFMA form of the large-tile kernel (RB200_DGEMM_DMMA=0 in a fresh process: the switch is read once)."""
+    import subprocess
+    import sys
+    code = ("import os, sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import oracle, rindow_math_matrix_b200 as rb\n"
+            "from rindow_math_matrix_b200 import BLAS, CudaBuffer, dtypes, _capi\n"
+            "blas = rb.MatlibCuda().blas(); rng = np.random.default_rng(1); m, n, k = 1500, 1303, 257\n"
+            "a = rng.uniform(-1, 1, (m, k)); b = rng.uniform(-1, 1, (k, n))\n"
+            "A = CudaBuffer(m * k, dtypes.float64).from_numpy(a.reshape(-1)); B = CudaBuffer(k * n, dtypes.float64).from_numpy(b.reshape(-1))\n"
+            "C = CudaBuffer(m * n, dtypes.float64)\n"
+            "blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, m, n, k, 1.0, A, 0, k, B, 0, n, 0.0, C, 0, n)\n"
+            "assert _capi.last_gemm_path() == 'simt_f64_big', _capi.last_gemm_path()\n"
+            "ref = np.zeros(m * n); oracle.gemm_rows_fast(0, m, n, k, 1.0, oracle.as_buffer(a), k, oracle.as_buffer(b), n, 0.0, ref, n)\n"
+            "err = np.max(np.abs(C.to_numpy() - ref)) / np.max(np.abs(ref)); assert err < 1e-14, err\n"
+            % (os.path.dirname(gr.HERE), gr.HERE))
+    env = dict(os.environ, RB200_DGEMM_DMMA="0")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
 
 
 TC_GEMMS = [(256, 256, 256), (128, 128, 32), (128, 256, 64), (384, 640, 160), (512, 384, 1024), (200, 300, 100),
