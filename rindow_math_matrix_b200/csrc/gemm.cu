@@ -371,9 +371,13 @@ int rb200_conv2d_forward(int dtype, const void* images, int64_t images_offset,
     if (mode == RB200_GEMM_AUTO) mode = c.default_gemm_mode;
     const int64_t M = batches * out_h * out_w, K = filter_h * filter_w * channels;
     if (batches * im_h * im_w * channels >= (1LL << 31)) RB_UNSUPPORTED("conv2d_forward: images exceed 2^31 elements");
-    if (!rb200::conv2d_tcgen05_eligible(mode, M, filters, K)) {
-        RB_UNSUPPORTED("conv2d_forward: needs a TF32 mode, filters <= 128 and filter_h*filter_w*channels <= 128 "
-                       "(use im2col2d + gemm)");
+    // long reductions over channels % 32 == 0 take the TMA-fed implicit GEMM (conv_tcgen05_tma.cu), any filter count;
+    // everything else needs filters <= 128 and K <= 128 (TMEM-operand kernel for K <= 32, skinny kernel above)
+    const bool tma_shape = (mode == RB200_GEMM_TF32 || mode == RB200_GEMM_TF32X3) && K > 32 && channels % 32 == 0 &&
+                           filters % 4 == 0 && filters >= 8;
+    if (!tma_shape && !rb200::conv2d_tcgen05_eligible(mode, M, filters, K)) {
+        RB_UNSUPPORTED("conv2d_forward: needs a TF32 mode and either channels %% 32 == 0 with filters %% 4 == 0, or "
+                       "filters <= 128 and filter_h*filter_w*channels <= 128 (use im2col2d + gemm)");
     }
     return rb200::conv2d_tcgen05(mode, reinterpret_cast<const float*>(images) + images_offset, batches, im_h, im_w,
                                  channels, filter_h, filter_w, stride_h, stride_w, dilation_h, dilation_w, pad_h, pad_w,

@@ -907,6 +907,53 @@ int encode_tensor_map_f32(void* map, const float* base, int rank, const uint64_t
     return RB200_OK;
 }
 
+// exported for conv_tcgen05_tma.cu: the operand tensor map of the GEMM kernels (K-major: box {box_inner k, box_outer rows},
+// 128-byte swizzle; MN-major: boxes {32 mn, 32 k}, 32-byte atoms), the hi / lo split pre-pass, and a general encoder
+// with per-dimension element strides (strided boxes)
+int make_gemm_map(void* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int planes,
+                  int64_t plane_stride, int box_inner, int box_outer, int mn_major)
+{
+    return make_map(reinterpret_cast<CUtensorMap*>(map), base, inner, outer, ld, planes, plane_stride, box_inner, box_outer,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int split_tf32_planes(const float* src, int64_t rows, int64_t cols, int64_t ld, float* dst, int64_t ld_dst,
+                      int64_t plane_stride)
+{
+    Context& c = ctx();
+    if (cols % 4 || ld % 4 || ld_dst % 4) {
+        // the pre-pass moves float4 columns: pad-free callers only (conv: channels % 32 == 0; W: ld_dst padded to 4)
+        if (ld % 4 || ld_dst % 4) { set_error("split_tf32_planes: leading dimensions must be multiples of 4"); return RB200_E_INVALID; }
+    }
+    const int64_t c4 = rb_ceil_div(cols, 4);
+    dim3 grid((unsigned)rb_ceil_div(c4, 256), (unsigned)(rows < 65535 ? rows : 65535));
+    split_tf32_kernel<<<grid, 256, 0, c.stream>>>(src, rows, cols, ld, dst, ld_dst, plane_stride, 0);
+    RB_LAUNCH_CHECK("split_tf32_kernel");
+    return RB200_OK;
+}
+
+int encode_tensor_map_f32_strided(void* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                                  const uint32_t* box, const uint32_t* elem_strides, bool swizzle128)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RB200_E_CUDA; }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], estr[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; estr[i] = elem_strides[i]; }
+    for (int i = 0; i + 1 < rank; i++) s[i] = strides[i];
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                    const_cast<float*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank=%d dims=%llu,%llu,%llu box=%u,%u,%u estr=%u,%u,%u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  box[0], box[1], rank > 2 ? box[2] : 0, elem_strides[0], elem_strides[1], rank > 2 ? elem_strides[2] : 0);
+        return RB200_E_CUDA;
+    }
+    return RB200_OK;
+}
+
 // Whether the tensor-core path can take this problem (TMA alignment rules).
 bool gemm_tcgen05_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t ldA,
                            const float* B, int64_t ldB, const float* C, int64_t ldC)

@@ -816,11 +816,26 @@ int conv2d_tcgen05_rows(int mode, const float* images, int64_t batches, int64_t 
                         int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
                         const float* W, int64_t filters, const float* bias, float* out);
 
+int conv2d_tcgen05_tma(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
+                       int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
+                       int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
+                       const float* W, int64_t filters, const float* bias, float* out);
+
 int conv2d_tcgen05(int mode, const float* images, int64_t batches, int64_t im_h, int64_t im_w, int64_t channels,
                    int64_t filter_h, int64_t filter_w, int64_t stride_h, int64_t stride_w,
                    int64_t dilation_h, int64_t dilation_w, int64_t pad_h, int64_t pad_w, int64_t out_h, int64_t out_w,
                    const float* W, int64_t filters, const float* bias, float* out)
 {
+    // long reductions over channels % 32 == 0 (hidden layers): TMA-fed implicit GEMM (conv_tcgen05_tma.cu)
+    if (filter_h * filter_w * channels > 32) {
+        const int rc = conv2d_tcgen05_tma(mode, images, batches, im_h, im_w, channels, filter_h, filter_w, stride_h, stride_w,
+                                          dilation_h, dilation_w, pad_h, pad_w, out_h, out_w, W, filters, bias, out);
+        if (rc != RB200_E_UNSUPPORTED) return rc;
+        if (!conv2d_tcgen05_eligible(mode, batches * out_h * out_w, filters, filter_h * filter_w * channels)) {
+            set_error("conv2d_forward: shape not supported by the fused kernels (use im2col2d + gemm)");
+            return RB200_E_UNSUPPORTED;
+        }
+    }
     // short reductions (K <= 32) go to the TMEM-operand kernel (conv_tcgen05_rows.cu) when it takes the shape
     {
         const int rc = conv2d_tcgen05_rows(mode, images, batches, im_h, im_w, channels, filter_h, filter_w, stride_h, stride_w,

@@ -1230,7 +1230,9 @@ class LinearAlgebra:
         driver: tiled im2col2d + software-staged tcgen05 GEMM, 0.25 ms for BASELINE config C4).  On the B200
         driver the single-kernel implicit-GEMM entry (rb200_conv2d_forward: no cols round trip) is taken by
         default for short reductions, kh*kw*c <= 32, where it runs on the TMEM-operand kernel (0.14 ms for C4,
-        0.92 of HBM); fused=True asks for it at any size it supports, fused=False never.  The three calls
+        0.92 of HBM), and for hidden layers with channels % 32 == 0, where the GEMM's A operand is fetched by TMA
+        straight from the image tensor (conv_tcgen05_tma.cu); fused=True asks for it at any size it supports,
+        fused=False never.  The three calls
         remain the fallback whenever the driver declines the shape."""
         if images.ndim() != 4 or kernel.ndim() != 4:
             raise InvalidArgumentException("images and kernel must be 4D dimension")
@@ -1251,7 +1253,9 @@ class LinearAlgebra:
         if bias is not None and bias.shape() != [filters]:
             raise InvalidArgumentException("Unmatch shape of bias and kernel")
         if fused is None:
-            fused = filter_h * filter_w * channels <= 32
+            # the single-kernel forms that beat im2col + gemm: short reductions (TMEM-operand kernel) and hidden layers
+            # with channels % 32 == 0 (TMA-fed implicit GEMM, no cols buffer at all)
+            fused = filter_h * filter_w * channels <= 32 or (channels % 32 == 0 and filters % 4 == 0 and filters >= 8)
         fused_fn = getattr(self.math, "conv2d_forward", None) if (fused and type(self.math).__name__ == "CudaMath") else None
         if fused_fn is not None:
             fused = fused_fn

@@ -982,6 +982,78 @@ def test_conv2d_forward_vs_oracle(case, mode, cuda_service):
     assert np.max(np.abs(got2 - ref)) / np.max(np.abs(ref)) < GEMM_TOL[mode]
 
 
+TMA_CONV_CASES = [  # (b, h, w, c, kh, kw, filters, strides, padding, dilation, bias)
+    (2, 20, 20, 32, 3, 3, 64, (1, 1), False, (1, 1), False),       # 18 x 18 out: 7 rows per tile, ragged last block
+    (2, 20, 20, 32, 3, 3, 64, (1, 1), True, (1, 1), True),         # same padding = TMA zero fill on all four sides
+    (1, 56, 56, 64, 3, 3, 64, (1, 1), True, (1, 1), True),         # the 64-channel 3x3 layer: 2 rows per tile
+    (2, 30, 150, 32, 3, 3, 128, (1, 1), False, (1, 1), False),     # wide rows: balanced segments of 74 cells
+    (1, 33, 41, 64, 3, 3, 96, (2, 2), True, (1, 1), True),         # stride 2: TMA element strides
+    (1, 31, 29, 32, 3, 3, 40, (2, 1), False, (1, 2), True),        # mixed strides / dilation, 40 filters (column tail)
+    (1, 24, 24, 96, 1, 1, 256, (1, 1), False, (1, 1), False),      # 1x1 conv, 256 filters (BN = 256 in TF32 mode)
+    (1, 16, 16, 64, 5, 5, 32, (1, 1), True, (2, 2), True),         # 5x5 dilated
+    (1, 12, 12, 256, 3, 3, 64, (1, 1), True, (1, 1), True),        # K = 2304: two accumulating launches in 3xTF32
+    (3, 9, 9, 32, 3, 3, 300, (1, 1), False, (1, 1), True),         # 300 filters: several filter blocks
+]
+
+
+@pytest.mark.parametrize("case", TMA_CONV_CASES, ids=[str(c[:7]) for c in TMA_CONV_CASES])
+@pytest.mark.parametrize("mode", [rb.GEMM_TF32X3, rb.GEMM_TF32])
+def test_conv2d_forward_tma_vs_oracle(case, mode, cuda_service):
+    """Hidden-layer shapes (channels % 32 == 0) on the TMA-fed implicit GEMM == oracle im2col2d + oracle gemm (+ bias),
+    in the mode's bound; the default route (fused=None) must pick the fused kernel for them."""
+    b, h, w, c, kh, kw, f, st, pad, dil, use_bias = case
+    rng = np.random.default_rng(h * 100 + w + c)
+    img = rng.uniform(-1, 1, (b, h, w, c)).astype(np.float32)
+    W = (rng.standard_normal((kh, kw, c, f)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(f).astype(np.float32) if use_bias else None
+    la = LinearAlgebra(cuda_service)
+    cuda_service.blas().setGemmMode(mode)
+    rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(mode))
+    try:
+        out = la.conv2d(la.array(img), la.array(W), None if bias is None else la.array(bias), strides=st, padding=pad,
+                        dilation_rate=dil)
+        path = rb._capi.last_gemm_path()
+    finally:
+        rb._capi.check(rb._capi.load().rb200_set_default_gemm_mode(rb.GEMM_TF32X3))
+        cuda_service.blas().setGemmMode(rb.GEMM_AUTO)
+    assert path == ("tcgen05_tf32_tma_conv" if mode == rb.GEMM_TF32 else "tcgen05_tf32x3_tma_conv"), path
+    K = kh * kw * c
+    shape = oracle.im2col2d_out_shape(b, h, w, c, kh, kw, st[0], st[1], pad, dil[0], dil[1], False)
+    M = shape[0] * shape[1] * shape[2]
+    cols = np.zeros(M * K)
+    oracle.im2col2d(False, oracle.as_buffer(img), 0, img.size, b, h, w, c, kh, kw, st[0], st[1], pad, False,
+                    dil[0], dil[1], False, cols, 0, cols.size)
+    ref = np.zeros(M * f)
+    oracle.gemm_rows_fast(0, M, f, K, 1.0, cols, K, oracle.as_buffer(W), f, 0.0, ref, f)
+    if bias is not None:
+        oracle.add(False, M, f, 1.0, oracle.as_buffer(bias), 0, 1, ref, 0, f)
+    assert out.shape() == [shape[0], shape[1], shape[2], f]
+    got = out.to_numpy().reshape(-1).astype(np.float64)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < GEMM_TOL[mode], path
+
+
+def test_conv2d_forward_tma_nonfinite_containment(cuda_service):
+    """NaN / Inf pixels reach only the outputs whose window holds them: padding comes from TMA's zero FILL of the
+    operand tile, and 0 * Inf never happens because out-of-image taps are zeros on the A side only where W is finite."""
+    b, h, w, c, f = 1, 14, 14, 32, 64
+    rng = np.random.default_rng(11)
+    img = rng.uniform(0, 1, (b, h, w, c)).astype(np.float32)
+    W = (rng.standard_normal((3, 3, c, f)) * 0.1).astype(np.float32)
+    la = LinearAlgebra(cuda_service)
+    clean = la.conv2d(la.array(img), la.array(W), padding=True).to_numpy()
+    assert rb._capi.last_gemm_path().endswith("_tma_conv")
+    bad = img.copy()
+    bad[0, 5, 7, 1] = np.nan
+    bad[0, 13, 0, 30] = np.inf
+    out = la.conv2d(la.array(bad), la.array(W), padding=True).to_numpy()
+    touched = np.zeros((h, w), bool)
+    for (y, x) in ((5, 7), (13, 0)):
+        touched[max(0, y - 1):y + 2, max(0, x - 1):x + 2] = True
+    assert not np.isfinite(out[0][touched]).any()
+    assert np.isfinite(out[0][~touched]).all()
+    assert np.array_equal(out[0][~touched], clean[0][~touched])
+
+
 def test_conv2d_forward_nonfinite_containment(cuda_service):
     """A NaN / Inf pixel may only reach the outputs whose receptive field holds it (the reference multiplies
     padding zeros and absent taps by nothing at all): checks the zero tails of the K <= 32 kernel's A rows."""
