@@ -111,7 +111,11 @@ const char* rb200_last_gemm_path(void);
 /* ---- buffers: replaces PhpBLASFactory::Buffer (PhpBLASFactory.php:35) storage and the
  *      DeviceBuffer read/write/copy/fill calls of NDArrayCL (NDArrayCL.php:147-168,
  *      252-272, 390-442) ------------------------------------------------------------- */
+/* Buffers come from the device's stream-ordered memory pool (cudaMallocAsync, freed memory stays cached) and are
+ * released without a synchronisation: LinearAlgebra allocates an output per call (src/LinearAlgebra.php:255-260).
+ * rb200_buffer_alloc_shareable uses plain cudaMalloc: the allocations rb200_ipc_export can export. */
 int rb200_buffer_alloc(int64_t bytes, void** dptr);
+int rb200_buffer_alloc_shareable(int64_t bytes, void** dptr);
 int rb200_buffer_free(void* dptr);
 int rb200_buffer_h2d(void* dptr, int64_t dst_offset_bytes, const void* host, int64_t bytes);
 int rb200_buffer_d2h(void* host, const void* dptr, int64_t src_offset_bytes, int64_t bytes);

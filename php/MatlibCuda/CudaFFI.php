@@ -152,6 +152,7 @@ class CudaFFI
         int rb200_graph_end(void** graph_exec);
         int rb200_graph_launch(void* graph_exec);
         int rb200_graph_destroy(void* graph_exec);
+        int rb200_buffer_alloc_shareable(int64_t bytes, void** dptr);
         CDEF;
 
     public static function lib() : FFI

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rb200_launch_count": (i32, [ctypes.POINTER(i64), i32]),
     "rb200_last_gemm_path": (ctypes.c_char_p, []),
     "rb200_buffer_alloc": (i32, [i64, ctypes.POINTER(vp)]),
+    "rb200_buffer_alloc_shareable": (i32, [i64, ctypes.POINTER(vp)]),
     "rb200_buffer_free": (i32, [vp]),
     "rb200_buffer_h2d": (i32, [vp, i64, vp, i64]),
     "rb200_buffer_d2h": (i32, [vp, vp, i64, i64]),

@@ -2,11 +2,15 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <unordered_set>
+
 #include "common.cuh"
 
 namespace rb200 {
 
 static Context g_ctx;
+// allocations made with plain cudaMalloc (CUDA-IPC exportable); everything else comes from the stream-ordered pool
+static std::unordered_set<void*> g_shareable;
 static thread_local char g_err[1024] = "";
 
 Context& ctx() { return g_ctx; }
@@ -109,6 +113,18 @@ int rb200_init(int device)
     RB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     RB_CUDA(cudaHostAlloc(&c.pinned_scalar, 64, cudaHostAllocDefault));
+    {
+        // buffers come from the device's stream-ordered memory pool and go back to it without a synchronisation:
+        // LinearAlgebra allocates an output per call (src/LinearAlgebra.php:255-260), so cudaMalloc / cudaFree (and the
+        // stream synchronise a safe cudaFree needs) would cost more than the kernels.  Keep freed memory cached.
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
     c.launches = 0;
     c.initialised = true;
     return RB200_OK;
@@ -215,7 +231,21 @@ int rb200_buffer_alloc(int64_t bytes, void** dptr)
     if (bytes < 0) RB_INVALID("negative size");
     *dptr = nullptr;
     if (bytes == 0) bytes = 16;
+    static const int use_pool = getenv("RB200_POOL") ? atoi(getenv("RB200_POOL")) : 1;
+    if (!use_pool) return rb200_buffer_alloc_shareable(bytes, dptr);
+    RB_CUDA(cudaMallocAsync(dptr, (size_t)bytes, ctx().stream));
+    return RB200_OK;
+}
+
+int rb200_buffer_alloc_shareable(int64_t bytes, void** dptr)
+{
+    RB_REQUIRE_INIT();
+    if (!dptr) RB_INVALID("dptr is NULL");
+    if (bytes < 0) RB_INVALID("negative size");
+    *dptr = nullptr;
+    if (bytes == 0) bytes = 16;
     RB_CUDA(cudaMalloc(dptr, (size_t)bytes));
+    rb200::g_shareable.insert(*dptr);
     return RB200_OK;
 }
 
@@ -223,8 +253,15 @@ int rb200_buffer_free(void* dptr)
 {
     RB_REQUIRE_INIT();
     if (!dptr) return RB200_OK;
-    RB_CUDA(cudaStreamSynchronize(ctx().stream));
-    RB_CUDA(cudaFree(dptr));
+    auto it = rb200::g_shareable.find(dptr);
+    if (it != rb200::g_shareable.end()) {
+        rb200::g_shareable.erase(it);
+        RB_CUDA(cudaStreamSynchronize(ctx().stream));
+        RB_CUDA(cudaFree(dptr));
+        return RB200_OK;
+    }
+    // stream-ordered: kernels already queued on the library stream keep the memory until they have run
+    RB_CUDA(cudaFreeAsync(dptr, ctx().stream));
     return RB200_OK;
 }
 

@@ -27,7 +27,7 @@ from .exceptions import InvalidArgumentException, RuntimeException
 
 
 class CudaBuffer:
-    def __init__(self, size: int, dtype: int, *, zero: bool = True):
+    def __init__(self, size: int, dtype: int, *, zero: bool = True, shareable: bool = False):
         if dtype not in dtypes.NUMPY:
             raise InvalidArgumentException("Invalid data type")          # PhpBuffer.php:96-98
         if size < 0:
@@ -39,7 +39,10 @@ class CudaBuffer:
         self._bytes = self._size * self._np.itemsize
         self._lib = _capi.load()
         ptr = ctypes.c_void_p()
-        _capi.check(self._lib.rb200_buffer_alloc(self._bytes, ctypes.byref(ptr)))
+        # shareable: plain cudaMalloc memory that rb200_ipc_export can hand to other processes (sharding.PeerRows);
+        # everything else comes from the stream-ordered pool
+        alloc = self._lib.rb200_buffer_alloc_shareable if shareable else self._lib.rb200_buffer_alloc
+        _capi.check(alloc(self._bytes, ctypes.byref(ptr)))
         self._dptr = ptr.value
         self._hptr = None            # pinned mirror (lazy)
         self._host = None            # numpy view of the mirror

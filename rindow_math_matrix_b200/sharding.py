@@ -78,7 +78,9 @@ class PeerRows:
     """A full [total_rows, cols] float32 matrix replicated on every rank whose row stripes are produced by their
     owners and pushed to all peers over NVLink from inside the producing kernel (rb200_sgemm_allgather) -- the
     fused form of `gemm` + `gather_rows`.  One process per GPU: the full-C allocations are exchanged as CUDA IPC
-    handles through the process group (host plumbing only) and mapped with rb200_ipc_open.
+    handles through the process group (host plumbing only) and mapped with rb200_ipc_open; `full_buffer` must be a
+    `CudaBuffer(..., shareable=True)` (plain cudaMalloc memory: pool memory cannot be exported).  SymmetricRows below
+    is the NVLS / symmetric-memory form the benchmark uses.
 
     exchange() is injectable so the handle plumbing runs under gloo on CPU (tests/test_sharding_gloo.py)."""
 

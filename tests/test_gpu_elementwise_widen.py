@@ -22,7 +22,7 @@ from rindow_math_matrix_b200 import CudaBuffer, InvalidArgumentException, Linear
 
 pytestmark = pytest.mark.gpu
 
-NP = dtypes.NUMPY
+NP = {k: v for k, v in dtypes.NUMPY.items() if k not in dtypes.COMPLEX_TYPES}     # real dtypes: the arithmetic entry points
 F32, F64 = dtypes.float32, dtypes.float64
 
 

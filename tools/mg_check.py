@@ -32,7 +32,7 @@ def main():
         start, rows = sharding.row_range(M, world, rank)
         A = CudaBuffer(rows * K, f32).from_numpy(A_full[start:start + rows].reshape(-1))
         B = CudaBuffer(K * N, f32).from_numpy(B_h.reshape(-1))
-        Cfull = CudaBuffer(M * N, f32)
+        Cfull = CudaBuffer(M * N, f32, shareable=True)
         pr = sharding.PeerRows(Cfull, M, N)
         blas = rb.MatlibCuda(gemm_mode=mode).blas()
         pr.arrive()
