@@ -167,6 +167,11 @@ struct TcParams {
     // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
     int batch, a_bmul, b_bmul;
     int64_t strideC;
+    // CTA-pair kernel: every `sync_kb` k-blocks the producers of all pairs meet at a device-wide progress counter, so
+    // the tiles of a wave walk K within one chunk of each other and the A / B panel slices they share are fetched
+    // from DRAM once (0 = free running).  sync_cnt[0] = arrivals, sync_cnt[1] = finished CTAs (reset by the last one).
+    int sync_kb;
+    unsigned int* sync_cnt;
 };
 
 template <int BN, int PLANES, int STAGES>
@@ -532,11 +537,22 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         // ===== TMA producer (one per CTA: its half of A and of B) =====
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            unsigned int sync_target = 0;                          // arrivals expected at this CTA's next meeting point
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 int mb, nb;
                 tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
                 const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * L::HALF_N;
+                // CTAs that have a tile in this wave (all of them except in the last, partial wave)
+                const int wave_first = tile - pair;
+                const unsigned int wave_ctas = 2u * (unsigned int)min(num_pairs, num_tiles - wave_first);
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    if (p.sync_kb > 0 && kb > 0 && kb % p.sync_kb == 0) {
+                        // bound the drift between the tiles of a wave: nobody starts chunk c + 1 of K before everybody
+                        // has issued the loads of chunk c (a throttle, not a data dependency: relaxed atomics)
+                        sync_target += wave_ctas;
+                        atomicAdd(p.sync_cnt, 1u);
+                        while (*reinterpret_cast<volatile unsigned int*>(p.sync_cnt) < sync_target) { }
+                    }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t leader_full = mapa_rank(full_bar(stage), 0);
                     if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * L::STAGE);     // both CTAs' bytes
@@ -722,6 +738,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+    if (p.sync_kb > 0 && threadIdx.x == 0) {
+        // the last CTA to finish puts the progress counter back to zero for the next launch on this stream
+        if (atomicAdd(p.sync_cnt + 1, 1u) == gridDim.x - 1) {
+            p.sync_cnt[0] = 0u;
+            p.sync_cnt[1] = 0u;
+            __threadfence();
+        }
     }
 }
 
@@ -1044,7 +1068,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
@@ -1110,6 +1134,22 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
                 for (int pj = 0; pj < c.n_gemm_peers; pj++) p.peers[pj] = c.gemm_peers[pj];
                 p.mc = c.gemm_mc;
                 c.gemm_peers_written = true;
+            }
+            {
+                // long reductions: keep the tiles of a wave within one K chunk (64 k-blocks = 2048) of each other (see
+                // TcParams::sync_kb).  Free running, the 74 pair tiles of a wave drift apart over a long K loop until the
+                // A / B panel slices they share have left L2 before the slower tiles ask for them: ncu at 16384^3 showed
+                // 47.7 GB of DRAM reads per launch (L2 hit rate 62 %, SM clock 1.20 GHz under the power cap) against
+                // 17.7 GB with the meeting points (75 %, 1.34 GHz) -- 631-662 -> 704-718 TFLOP/s; 8192^3 +1 %.
+                // RB200_GEMM_SYNC_KB=0 switches it off.
+                static const int sync_kb = getenv("RB200_GEMM_SYNC_KB") ? atoi(getenv("RB200_GEMM_SYNC_KB")) : 64;
+                static unsigned int* sync_cnt = nullptr;
+                if (sync_kb > 0 && !sync_cnt) {
+                    RB_CUDA(cudaMalloc(&sync_cnt, 2 * sizeof(unsigned int)));
+                    RB_CUDA(cudaMemsetAsync(sync_cnt, 0, 2 * sizeof(unsigned int), c.stream));
+                }
+                const int64_t kmin = getenv("RB200_GEMM_SYNC_MINK") ? atoll(getenv("RB200_GEMM_SYNC_MINK")) : 0;
+                if (sync_kb > 0 && kl >= kmin) { p.sync_kb = sync_kb; p.sync_cnt = sync_cnt; }
             }
             rc = planes == 1 ? launch_2cta<1>(a_mn, b_mn, mA, mB2, p) : launch_2cta<2>(a_mn, b_mn, mA, mB2, p);
             c.last_gemm_path = planes == 1 ? "tcgen05_tf32_2cta" : "tcgen05_tf32x3_2cta";
@@ -1193,7 +1233,7 @@ int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t 
         p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
         p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
         if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
         else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);
