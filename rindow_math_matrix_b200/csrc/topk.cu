@@ -32,12 +32,23 @@ __device__ __forceinline__ void tk_heapify(int size, T* heap, int* idx, int pare
 
 template <typename T, typename I>
 __global__ void __launch_bounds__(TK_WARPS * 32)
-topk_kernel(int64_t m, int n, int k, int sorted, const T* __restrict__ input, T* __restrict__ values, I* __restrict__ indices)
+topk_kernel(int64_t m, int n, int k, int sorted, const T* __restrict__ input, T* __restrict__ values, I* __restrict__ indices,
+            unsigned char* gheap)
 {
     extern __shared__ __align__(16) unsigned char tk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T* heap = reinterpret_cast<T*>(tk_smem) + (size_t)warp * k;
-    int* idx = reinterpret_cast<int*>(reinterpret_cast<T*>(tk_smem) + (size_t)TK_WARPS * k) + (size_t)warp * k;
+    // heaps in shared memory; for k beyond the shared-memory budget (the reference accepts any k <= n) the same
+    // algorithm runs on per-warp heaps in the global workspace (L2-resident for the sizes that get here)
+    T* heap;
+    int* idx;
+    if (gheap == nullptr) {
+        heap = reinterpret_cast<T*>(tk_smem) + (size_t)warp * k;
+        idx = reinterpret_cast<int*>(reinterpret_cast<T*>(tk_smem) + (size_t)TK_WARPS * k) + (size_t)warp * k;
+    } else {
+        const size_t gw = (size_t)blockIdx.x * TK_WARPS + warp, nw = (size_t)gridDim.x * TK_WARPS;
+        heap = reinterpret_cast<T*>(gheap) + gw * k;
+        idx = reinterpret_cast<int*>(reinterpret_cast<T*>(gheap) + nw * k) + gw * k;
+    }
     for (int64_t row = (int64_t)blockIdx.x * TK_WARPS + warp; row < m; row += (int64_t)gridDim.x * TK_WARPS) {
         const T* arr = input + row * n;
         for (int i = lane; i < k; i += 32) { heap[i] = arr[i]; idx[i] = i; }
@@ -88,16 +99,26 @@ template <typename T, typename I>
 int topk_launch(int64_t m, int64_t n, int64_t k, int sorted, const void* input, void* values, void* indices)
 {
     rb200::Context& c = rb200::ctx();
-    const size_t smem = (size_t)TK_WARPS * k * (sizeof(T) + sizeof(int));
-    if (smem > 200 * 1024) RB_UNSUPPORTED("topk: k = %lld does not fit the shared-memory heap", (long long)k);
-    if (smem > 48 * 1024) {
-        RB_CUDA(cudaFuncSetAttribute(topk_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    size_t smem = (size_t)TK_WARPS * k * (sizeof(T) + sizeof(int));
     int64_t grid = rb_ceil_div(m, TK_WARPS);
     const int64_t cap = (int64_t)c.sm_count * 16;
     if (grid > cap) grid = cap;
+    unsigned char* gheap = nullptr;
+    if (smem > 200 * 1024) {
+        // heaps in the global workspace: as many warps as 1 GiB of heaps allows
+        const int64_t per_cta = (int64_t)smem;
+        int64_t fit = ((int64_t)1 << 30) / per_cta;
+        if (fit < 1) fit = 1;
+        if (grid > fit) grid = fit;
+        int rc = rb200::ensure_workspace((size_t)(grid * per_cta));
+        if (rc != RB200_OK) return rc;
+        gheap = reinterpret_cast<unsigned char*>(c.workspace);
+        smem = 0;
+    } else if (smem > 48 * 1024) {
+        RB_CUDA(cudaFuncSetAttribute(topk_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     topk_kernel<T, I><<<(unsigned)grid, TK_WARPS * 32, smem, c.stream>>>(m, (int)n, (int)k, sorted, reinterpret_cast<const T*>(input),
-                                                                        reinterpret_cast<T*>(values), reinterpret_cast<I*>(indices));
+                                                                        reinterpret_cast<T*>(values), reinterpret_cast<I*>(indices), gheap);
     RB_LAUNCH_CHECK("topk_kernel");
     return RB200_OK;
 }

@@ -32,7 +32,8 @@ def test_topk_known_answers(cuda_service):
 
 
 @pytest.mark.parametrize("m,n,k", [(1, 1, 1), (1, 10, 10), (3, 10, 3), (7, 33, 5), (64, 5000, 10), (5, 5000, 1), (2, 40000, 100),
-                                   (300, 257, 64), (1, 3000, 1500)])
+                                   (300, 257, 64), (1, 3000, 1500),
+                                   (6, 20000, 9000)])           # k beyond the shared-memory heaps: global-memory heaps
 @pytest.mark.parametrize("sorted_", [True, False])
 @pytest.mark.parametrize("dt", [dtypes.float32, dtypes.float64, dtypes.int32])
 def test_topk_random_vs_oracle(m, n, k, sorted_, dt, cuda_service):
