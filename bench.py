@@ -398,7 +398,9 @@ def run_b200(args):
     achieved_note = ("algorithmic flops 2*N^3 (the kernel issues 3x that on the tensor pipe)" if args.mode == "tf32x3"
                      else "algorithmic flops 2*N^3")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": ncu_traffic(gemm_path, n), "kernel": gemm_path,
+                "frac": achieved / tf32_peak,
+                # the ncu capture is of the single-GPU launch (the whole 16384^3 problem); stripes were not captured
+                "traffic": ncu_traffic(gemm_path, n) if world == 1 else None, "kernel": gemm_path,
                 "per": "GPU (this rank's stripe: 2*N^3/%d flop per launch)" % world,
                 "peak_note": ("TF32 dense peak MEASURED on a pool B200 (profiles/peaks_tf32_r02.json: cuBLAS TF32 8192^3 "
                               "through torch, burst = best of 10); " if tf32_meas else
