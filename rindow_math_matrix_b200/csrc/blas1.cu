@@ -112,13 +112,19 @@ int blas1_dispatch(int dtype, int64_t n, double alpha, const void* X, int64_t of
         // complex buffers: pure data movement only (copy / swap), as 8-byte words
         case RB200_COMPLEX64:
             if (OP == B1_COPY || OP == B1_SWAP) return blas1_launch<double, OP>(n, alpha, X, offX, incX, Y, offY, incY);
-            RB_UNSUPPORTED("blas level 1: complex buffers support copy and swap only");
+            break;
         case RB200_COMPLEX128:
             if ((OP == B1_COPY || OP == B1_SWAP) && incX == 1 && incY == 1)
                 return blas1_launch<double, OP>(2 * n, alpha, X, 2 * offX, 1, Y, 2 * offY, 1);
-            RB_UNSUPPORTED("blas level 1: complex128 buffers support contiguous copy and swap only");
-        default: RB_UNSUPPORTED("blas level 1: unsupported dtype %d", dtype);
+            break;
+        default: break;
     }
+    if (dtype == RB200_COMPLEX64 || dtype == RB200_COMPLEX128) {
+        rb200::set_error("blas level 1: complex buffers support (contiguous) copy and swap only");
+        return RB200_E_UNSUPPORTED;
+    }
+    rb200::set_error("blas level 1: unsupported dtype %d", dtype);
+    return RB200_E_UNSUPPORTED;
 }
 
 // ---- gemv -------------------------------------------------------------------------------------------
