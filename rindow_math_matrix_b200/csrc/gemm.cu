@@ -4,6 +4,8 @@
 // Mirrors the argument handling of PhpBlas::gemm (src/Drivers/MatlibPHP/PhpBlas.php:849-886):
 // ColMajor merely swaps m and n (:862-863); Trans/ConjTrans and NoTrans/ConjNoTrans are the
 // same for real dtypes (:104-123); trans only swaps the two strides of an operand (:883-886).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rb200 {
@@ -213,14 +215,15 @@ int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64
     if (!mc_C) RB_INVALID("mc_C is NULL");
     if (order != RB200_ROW_MAJOR) RB_UNSUPPORTED("rb200_sgemm_allgather_mc: row-major only (the stripes are rows)");
     rb200::Context& c = rb200::ctx();
+    // RB200_MC_EPILOGUE=0 (diagnostic): multiply first, then push the stripe with the contiguous multimem copy kernel
+    static const int mc_epilogue = getenv("RB200_MC_EPILOGUE") ? atoi(getenv("RB200_MC_EPILOGUE")) : 1;
     c.n_gemm_peers = 0;
-    c.gemm_mc = reinterpret_cast<float*>(mc_C) + offC;
+    c.gemm_mc = mc_epilogue ? reinterpret_cast<float*>(mc_C) + offC : nullptr;
     c.gemm_peers_written = false;
     const int rc = rb200_sgemm(order, transA, transB, m, n, k, alpha, A, offA, ldA, B, offB, ldB, beta, C, offC, ldC, mode);
-    float* mc = c.gemm_mc;
     c.gemm_mc = nullptr;
     if (rc != RB200_OK || c.gemm_peers_written) return rc;
-    return rb200::mc_push_rows(C + offC, mc, m, n, ldC);
+    return rb200::mc_push_rows(C + offC, reinterpret_cast<float*>(mc_C) + offC, m, n, ldC);
 }
 
 }  // extern "C"

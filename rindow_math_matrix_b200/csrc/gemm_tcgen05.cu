@@ -163,6 +163,10 @@ struct TcParams {
     // rb200_sgemm_allgather_mc: the multicast alias of C (NVLS: one multimem.st leaves this GPU once and the NVSwitch
     // replicates it into every rank's copy, this rank's included); nullptr = unicast peers above
     float* mc;
+    int mc_weak;                   // diagnostic (RB200_MC_WEAK=1): multimem.st.weak instead of .relaxed.sys
+    // mc_pusher: the epilogue only stores its tile locally; warp 3 of each CTA reads finished tiles back through L2 and
+    // multicasts them as whole contiguous row segments (512 bytes per instruction), up to 4 tiles behind the epilogue
+    int mc_pusher;
     // strided batch (1-CTA kernels): tile index = (matrix, row block, column block); the third tensor-map coordinate
     // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
     int batch, a_bmul, b_bmul;
@@ -469,6 +473,11 @@ __device__ __forceinline__ void multimem_st_f4(float* mc_addr, const float4& v)
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void multimem_st_f4_weak(float* mc_addr, const float4& v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void multimem_st_f1(float* mc_addr, float v)
 {
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(v) : "memory");
@@ -503,6 +512,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar= [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_ptr_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto stored_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 5 + i); };       // epilogue -> pusher, 4 slots
+    auto pushed_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 9 + i); };       // pusher -> epilogue, 4 slots
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5;
@@ -518,6 +529,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        for (int i = 0; i < 4; i++) { mbar_init(stored_bar(i), 4); mbar_init(pushed_bar(i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -627,6 +639,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         // ===== epilogue: this CTA's 128 rows of the pair tile =====
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        int it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             int mb, nb;
             tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
@@ -683,7 +696,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                             }
                         }
                     }
-                    if (p.n_peers > 0 || p.mc != nullptr) {
+                    if ((p.n_peers > 0 || p.mc != nullptr) && !p.mc_pusher) {
                         // all-gather leg: the warp's 32 x 32 block of final values goes through a padded smem tile so
                         // that every peer store instruction writes whole 128-byte row segments (NVLink-friendly),
                         // instead of 32 scattered 16-byte pieces
@@ -706,7 +719,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                                 const float4 val = *reinterpret_cast<const float4*>(stg + rr * L::STG_LD + cc);
                                 const int64_t at = grow * p.ldC + c0 + cc;
                                 if (p.mc != nullptr) {
-                                    if (c0 + cc + 4 <= p.N) multimem_st_f4(p.mc + at, val);
+                                    if (c0 + cc + 4 <= p.N) {
+                                        if (p.mc_weak) multimem_st_f4_weak(p.mc + at, val);
+                                        else multimem_st_f4(p.mc + at, val);
+                                    }
                                     else {
                                         const float ve[4] = {val.x, val.y, val.z, val.w};
                                         for (int e = 0; e < 4; e++)
@@ -729,7 +745,68 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));   // leader's barrier, 8 arrivals
+            if (p.mc_pusher) {
+                // hand the tile to the pusher warp: its rows are in global memory (L2) once the fence has passed; slot
+                // it % 4 may be reused when the pusher has finished the tile of four iterations ago
+                __threadfence();
+                __syncwarp();
+                if (it >= 4) mbar_wait(pushed_bar(it & 3), (uint32_t)(((it >> 2) - 1) & 1));
+                if (lane == 0) mbar_arrive(stored_bar(it & 3));
+            }
+            it++;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == 3 && p.mc_pusher) {
+        // ===== pusher: finished tiles of this CTA (128 rows x BN columns, 1 KB / 512 B contiguous per row) are read back
+        // through L2 and multicast, 512 contiguous bytes per instruction, four rows in flight =====
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
+            int mb, nb;
+            tile_coords(tile, p.num_m_blocks, p.num_n_blocks, mb, nb, p.group_m);
+            mbar_wait(stored_bar(it & 3), (uint32_t)((it >> 2) & 1));
+            const int64_t row0 = (int64_t)mb * 256 + (int64_t)rank * 128;
+            const int64_t col0 = (int64_t)nb * BN;
+            int64_t ncols = p.N - col0;
+            if (ncols > BN) ncols = BN;
+            const bool vec = (ncols % 4 == 0);
+            for (int r = 0; r < 128; r += 4) {
+                float4 v[4][BN / 128];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t row = row0 + r + u;
+#pragma unroll
+                    for (int h = 0; h < BN / 128; h++) {
+                        const int64_t cc = col0 + h * 128 + lane * 4;
+                        if (vec && row < p.M && cc - col0 < ncols) {
+                            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(v[u][h].x), "=f"(v[u][h].y), "=f"(v[u][h].z), "=f"(v[u][h].w)
+                                         : "l"(p.C + row * p.ldC + cc) : "memory");
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t row = row0 + r + u;
+#pragma unroll
+                    for (int h = 0; h < BN / 128; h++) {
+                        const int64_t cc = col0 + h * 128 + lane * 4;
+                        if (row < p.M && cc - col0 < ncols) {
+                            if (vec) {
+                                multimem_st_f4(p.mc + row * p.ldC + cc, v[u][h]);
+                            } else {
+                                for (int e = 0; e < 4; e++)
+                                    if (cc + e - col0 < ncols) {
+                                        float x;
+                                        asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(x) : "l"(p.C + row * p.ldC + cc + e) : "memory");
+                                        multimem_st_f1(p.mc + row * p.ldC + cc + e, x);
+                                    }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pushed_bar(it & 3));
         }
     }
 
@@ -1068,7 +1145,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_weak = 0; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
@@ -1133,6 +1210,10 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
                 p.n_peers = c.n_gemm_peers;
                 for (int pj = 0; pj < c.n_gemm_peers; pj++) p.peers[pj] = c.gemm_peers[pj];
                 p.mc = c.gemm_mc;
+                static const int mc_weak = getenv("RB200_MC_WEAK") ? atoi(getenv("RB200_MC_WEAK")) : 0;
+                p.mc_weak = mc_weak;
+                static const int mc_pusher = getenv("RB200_MC_PUSHER") ? atoi(getenv("RB200_MC_PUSHER")) : 0;
+                p.mc_pusher = (mc_pusher && p.mc != nullptr && p.beta == 0.f) ? 1 : 0;
                 c.gemm_peers_written = true;
             }
             {
@@ -1233,7 +1314,7 @@ int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t 
         p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
         p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_weak = 0; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
         if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
         else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);

@@ -103,6 +103,44 @@ def test_service_without_gpu_is_basic_and_refuses_to_compute():
         rb.CudaBuffer(4, dtypes.float32)
 
 
+def test_device_tier_without_gpu_fails_loudly():
+    """The device-resident tier is importable everywhere and refuses to work without a B200: no queue, no device
+    buffers, no accelerated LA (and the accelerator name the reference knows is not ours)."""
+    from rindow_math_matrix_b200 import _capi
+    assert rb.LinearAlgebraCuda.__mro__[1] is LinearAlgebra and rb.NDArrayCuda.__name__ == "NDArrayCuda"
+    if _capi.device_available():
+        pytest.skip("a GPU is visible")
+    svc = rb.MatlibCuda()
+    assert svc.serviceLevel() < rb.Service.LV_ACCELERATED
+    with pytest.raises(rb.LogicException):
+        svc.createQueue()
+    with pytest.raises(rb.LogicException):
+        svc.buffer(rb.Service.LV_ACCELERATED)
+    mo = MatrixOperator(svc)
+    assert not mo.isAccelerated()
+    with pytest.raises(rb.LogicException):
+        mo.laAccelerated("cuda")
+    with pytest.raises(rb.LogicException, match="Unknown accelerator"):
+        mo.laAccelerated("clblast")
+
+
+def test_sharding_geometry_and_merges_single_process():
+    """row stripes of the sharded gemm and the cross-rank merges on one process (world 1): identities."""
+    import torch
+    from rindow_math_matrix_b200 import sharding
+    assert sharding.row_range(16384, 8, 3) == (6144, 2048)
+    v = torch.tensor([1.0, float("inf"), float("nan"), -float("inf")], dtype=torch.float64)
+    m = sharding.merge_max(v.clone())
+    assert m[0] == 1.0 and m[1] == float("inf") and torch.isnan(m[2]) and m[3] == -float("inf")
+    idx = sharding.merge_argmax(v.clone(), torch.tensor([3, 0, 2, 7]), 10)
+    assert idx.tolist() == [13, 10, 12, 17]
+    rec = torch.tensor([0, 5, 0, 9], dtype=torch.int64)
+    rec[0] = torch.tensor([2.5], dtype=torch.float64).view(torch.int64)[0]
+    rec[2] = torch.tensor([-1.0], dtype=torch.float64).view(torch.int64)[0]
+    vals, ids = sharding.split_records(rec, 2)
+    assert vals.tolist() == [2.5, -1.0] and ids.tolist() == [5, 9]
+
+
 def test_conv2d_composition_over_any_driver(oracle_service):
     """LinearAlgebra.conv2d without a fused driver entry = im2col -> gemm -> add (the reference calls)."""
     la = LinearAlgebra(oracle_service)
