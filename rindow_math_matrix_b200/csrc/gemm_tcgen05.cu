@@ -163,7 +163,6 @@ struct TcParams {
     // rb200_sgemm_allgather_mc: the multicast alias of C (NVLS: one multimem.st leaves this GPU once and the NVSwitch
     // replicates it into every rank's copy, this rank's included); nullptr = unicast peers above
     float* mc;
-    int mc_weak;                   // diagnostic (RB200_MC_WEAK=1): multimem.st.weak instead of .relaxed.sys
     // mc_pusher: the epilogue only stores its tile locally; warp 3 of each CTA reads finished tiles back through L2 and
     // multicasts them as whole contiguous row segments (512 bytes per instruction), up to 4 tiles behind the epilogue
     int mc_pusher;
@@ -473,11 +472,6 @@ __device__ __forceinline__ void multimem_st_f4(float* mc_addr, const float4& v)
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void multimem_st_f4_weak(float* mc_addr, const float4& v)
-{
-    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                 :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void multimem_st_f1(float* mc_addr, float v)
 {
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(v) : "memory");
@@ -719,10 +713,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                                 const float4 val = *reinterpret_cast<const float4*>(stg + rr * L::STG_LD + cc);
                                 const int64_t at = grow * p.ldC + c0 + cc;
                                 if (p.mc != nullptr) {
-                                    if (c0 + cc + 4 <= p.N) {
-                                        if (p.mc_weak) multimem_st_f4_weak(p.mc + at, val);
-                                        else multimem_st_f4(p.mc + at, val);
-                                    }
+                                    if (c0 + cc + 4 <= p.N) multimem_st_f4(p.mc + at, val);
                                     else {
                                         const float ve[4] = {val.x, val.y, val.z, val.w};
                                         for (int e = 0; e < 4; e++)
@@ -769,10 +760,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             int64_t ncols = p.N - col0;
             if (ncols > BN) ncols = BN;
             const bool vec = (ncols % 4 == 0);
-            for (int r = 0; r < 128; r += 4) {
-                float4 v[4][BN / 128];
+            constexpr int PR = 8;                                 // rows in flight per iteration (8 KB per SM)
+            for (int r = 0; r < 128; r += PR) {
+                float4 v[PR][BN / 128];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < PR; u++) {
                     const int64_t row = row0 + r + u;
 #pragma unroll
                     for (int h = 0; h < BN / 128; h++) {
@@ -785,7 +777,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < PR; u++) {
                     const int64_t row = row0 + r + u;
 #pragma unroll
                     for (int h = 0; h < BN / 128; h++) {
@@ -1145,7 +1137,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.mc_weak = 0; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
@@ -1210,9 +1202,10 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
                 p.n_peers = c.n_gemm_peers;
                 for (int pj = 0; pj < c.n_gemm_peers; pj++) p.peers[pj] = c.gemm_peers[pj];
                 p.mc = c.gemm_mc;
-                static const int mc_weak = getenv("RB200_MC_WEAK") ? atoi(getenv("RB200_MC_WEAK")) : 0;
-                p.mc_weak = mc_weak;
-                static const int mc_pusher = getenv("RB200_MC_PUSHER") ? atoi(getenv("RB200_MC_PUSHER")) : 0;
+                // default: the pusher warp (N = 8, 16384^3: 2.03 ms with epilogue stores of 128-byte row segments, 1.92 ms
+                // with the pusher's 512-byte contiguous stores; the contiguous multimem copy kernel alone moves a rank's
+                // stripe into all eight copies at 772 GB/s of ingress per GPU -- profiles/nvls_gather_variants_r02.txt)
+                static const int mc_pusher = getenv("RB200_MC_PUSHER") ? atoi(getenv("RB200_MC_PUSHER")) : 1;
                 p.mc_pusher = (mc_pusher && p.mc != nullptr && p.beta == 0.f) ? 1 : 0;
                 c.gemm_peers_written = true;
             }
@@ -1314,7 +1307,7 @@ int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t 
         p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
         p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.mc_weak = 0; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
         if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
         else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);
