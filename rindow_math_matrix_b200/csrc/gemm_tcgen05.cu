@@ -163,8 +163,8 @@ struct TcParams {
     // rb200_sgemm_allgather_mc: the multicast alias of C (NVLS: one multimem.st leaves this GPU once and the NVSwitch
     // replicates it into every rank's copy, this rank's included); nullptr = unicast peers above
     float* mc;
-    // mc_pusher: the epilogue only stores its tile locally; warp 3 of each CTA reads finished tiles back through L2 and
-    // multicasts them as whole contiguous row segments (512 bytes per instruction), up to 4 tiles behind the epilogue
+    // mc_pusher: the epilogue only stores its tile locally; warps 2 and 3 of each CTA read finished tiles back through L2
+    // and multicast them as whole contiguous row segments (512 bytes per instruction), up to 4 tiles behind the epilogue
     int mc_pusher;
     // strided batch (1-CTA kernels): tile index = (matrix, row block, column block); the third tensor-map coordinate
     // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
@@ -523,7 +523,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
-        for (int i = 0; i < 4; i++) { mbar_init(stored_bar(i), 4); mbar_init(pushed_bar(i), 1); }
+        for (int i = 0; i < 4; i++) { mbar_init(stored_bar(i), 4); mbar_init(pushed_bar(i), 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -747,9 +747,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             it++;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp == 3 && p.mc_pusher) {
-        // ===== pusher: finished tiles of this CTA (128 rows x BN columns, 1 KB / 512 B contiguous per row) are read back
-        // through L2 and multicast, 512 contiguous bytes per instruction, four rows in flight =====
+    } else if (p.mc_pusher) {
+        // ===== pushers (warps 2 and 3, 64 rows of the tile each; warp 2 is idle between TMEM alloc and dealloc): finished
+        // tiles of this CTA (128 rows x BN columns, 1 KB / 512 B contiguous per row) are read back through L2 and
+        // multicast, 512 contiguous bytes per instruction, eight rows in flight per warp =====
+        const int half = warp - 2;
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             int mb, nb;
@@ -761,7 +763,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             if (ncols > BN) ncols = BN;
             const bool vec = (ncols % 4 == 0);
             constexpr int PR = 8;                                 // rows in flight per iteration (8 KB per SM)
-            for (int r = 0; r < 128; r += PR) {
+            for (int r = half * 64; r < half * 64 + 64; r += PR) {
                 float4 v[PR][BN / 128];
 #pragma unroll
                 for (int u = 0; u < PR; u++) {
