@@ -165,7 +165,8 @@ struct TcParams {
     float* mc;
     // mc_pusher: the epilogue only stores its tile locally; warps 2 and 3 of each CTA read finished tiles back through L2
     // and multicast them as whole contiguous row segments (512 bytes per instruction), up to 4 tiles behind the epilogue
-    int mc_pusher;
+    int mc_pusher;                 // 0 = epilogue stores, 1 = warp 3 pushes, 2 = warps 2 and 3 push half a tile each
+    int mc_push_rows;              // rows in flight per pusher warp (4 or 8)
     // strided batch (1-CTA kernels): tile index = (matrix, row block, column block); the third tensor-map coordinate
     // of an operand is matrix * bmul * PLANES + plane (bmul = 0 shares the operand across the batch)
     int batch, a_bmul, b_bmul;
@@ -523,7 +524,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
-        for (int i = 0; i < 4; i++) { mbar_init(stored_bar(i), 4); mbar_init(pushed_bar(i), 2); }
+        for (int i = 0; i < 4; i++) { mbar_init(stored_bar(i), 4); mbar_init(pushed_bar(i), p.mc_pusher == 2 ? 2 : 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -747,11 +748,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             it++;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (p.mc_pusher) {
-        // ===== pushers (warps 2 and 3, 64 rows of the tile each; warp 2 is idle between TMEM alloc and dealloc): finished
-        // tiles of this CTA (128 rows x BN columns, 1 KB / 512 B contiguous per row) are read back through L2 and
-        // multicast, 512 contiguous bytes per instruction, eight rows in flight per warp =====
-        const int half = warp - 2;
+    } else if (p.mc_pusher == 2 || (p.mc_pusher == 1 && warp == 3)) {
+        // ===== pusher(s): warp 3 (and, with mc_pusher == 2, warp 2, which is idle between TMEM alloc and dealloc; then
+        // 64 rows of the tile each): finished tiles of this CTA (128 rows x BN columns, 1 KB / 512 B contiguous per row)
+        // are read back through L2 and multicast, 512 contiguous bytes per instruction, mc_push_rows rows in flight =====
+        const int r_begin = p.mc_pusher == 2 ? (warp - 2) * 64 : 0;
+        const int r_end = p.mc_pusher == 2 ? r_begin + 64 : 128;
+        const int pr = p.mc_push_rows;
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             int mb, nb;
@@ -762,8 +765,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
             int64_t ncols = p.N - col0;
             if (ncols > BN) ncols = BN;
             const bool vec = (ncols % 4 == 0);
-            constexpr int PR = 8;                                 // rows in flight per iteration (8 KB per SM)
-            for (int r = half * 64; r < half * 64 + 64; r += PR) {
+            constexpr int PR = 8;                                 // upper bound of rows in flight per iteration
+            for (int r = r_begin; r < r_end; r += pr) {
                 float4 v[PR][BN / 128];
 #pragma unroll
                 for (int u = 0; u < PR; u++) {
@@ -771,7 +774,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 #pragma unroll
                     for (int h = 0; h < BN / 128; h++) {
                         const int64_t cc = col0 + h * 128 + lane * 4;
-                        if (vec && row < p.M && cc - col0 < ncols) {
+                        if (u < pr && vec && row < p.M && cc - col0 < ncols) {
                             asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
                                          : "=f"(v[u][h].x), "=f"(v[u][h].y), "=f"(v[u][h].z), "=f"(v[u][h].w)
                                          : "l"(p.C + row * p.ldC + cc) : "memory");
@@ -784,7 +787,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 #pragma unroll
                     for (int h = 0; h < BN / 128; h++) {
                         const int64_t cc = col0 + h * 128 + lane * 4;
-                        if (row < p.M && cc - col0 < ncols) {
+                        if (u < pr && row < p.M && cc - col0 < ncols) {
                             if (vec) {
                                 multimem_st_f4(p.mc + row * p.ldC + cc, v[u][h]);
                             } else {
@@ -1139,7 +1142,7 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
         p.mn_sbo = dbg_sbo >= 0 ? (uint32_t)dbg_sbo : 512u;
         p.mn_layout = dbg_layout >= 0 ? (uint32_t)dbg_layout : 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.mc_push_rows = 4; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = 1; p.a_bmul = 0; p.b_bmul = 0; p.strideC = 0;
         static const int use_2cta = getenv("RB200_GEMM_2CTA") ? atoi(getenv("RB200_GEMM_2CTA")) : 1;
         static const int use_2cta_x3 = getenv("RB200_GEMM_2CTA_X3") ? atoi(getenv("RB200_GEMM_2CTA_X3")) : 1;
@@ -1207,8 +1210,12 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
                 // default: the pusher warp (N = 8, 16384^3: 2.03 ms with epilogue stores of 128-byte row segments, 1.92 ms
                 // with the pusher's 512-byte contiguous stores; the contiguous multimem copy kernel alone moves a rank's
                 // stripe into all eight copies at 772 GB/s of ingress per GPU -- profiles/nvls_gather_variants_r02.txt)
+                // One pusher warp with four rows in flight is the measured optimum: two warps x eight rows read 2.06 ms
+                // (the extra L2 read-back and store traffic competes with the operand loads).
                 static const int mc_pusher = getenv("RB200_MC_PUSHER") ? atoi(getenv("RB200_MC_PUSHER")) : 1;
-                p.mc_pusher = (mc_pusher && p.mc != nullptr && p.beta == 0.f) ? 1 : 0;
+                static const int mc_push_rows = getenv("RB200_MC_PUSH_ROWS") ? atoi(getenv("RB200_MC_PUSH_ROWS")) : 4;
+                p.mc_pusher = (mc_pusher > 0 && p.mc != nullptr && p.beta == 0.f) ? (mc_pusher >= 2 ? 2 : 1) : 0;
+                p.mc_push_rows = mc_push_rows >= 8 ? 8 : 4;
                 c.gemm_peers_written = true;
             }
             {
@@ -1309,7 +1316,7 @@ int gemm_tcgen05_batched(int mode, bool transA, bool transB, int64_t M, int64_t 
         p.num_k_blocks = (int)rb_ceil_div(kl, TC_BK);
         p.mn_lbo = 4096u; p.mn_sbo = 512u; p.mn_layout = 1u;
         p.group_m = TC_GROUP_M;
-        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.sync_kb = 0; p.sync_cnt = nullptr;
+        p.n_peers = 0; p.mc = nullptr; p.mc_pusher = 0; p.mc_push_rows = 4; p.sync_kb = 0; p.sync_cnt = nullptr;
         p.batch = (int)batch; p.a_bmul = strideA ? 1 : 0; p.b_bmul = strideB ? 1 : 0; p.strideC = strideC;
         if (planes == 1) rc = BN == 256 ? launch_by_major<256, 1, 4>(a_mn, b_mn, mA, mB, p) : launch_by_major<128, 1, 6>(a_mn, b_mn, mA, mB, p);
         else             rc = BN == 128 ? launch_by_major<128, 2, 3>(a_mn, b_mn, mA, mB, p) : launch_by_major<64, 2, 4>(a_mn, b_mn, mA, mB, p);
