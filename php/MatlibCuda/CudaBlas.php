@@ -275,4 +275,50 @@ class CudaBlas extends PhpBlas
         CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->abiDtype(),BLAS::RowMajor,$trans,$m,$n,$alpha,
             $A->devicePtr(),$offsetA,$ldA,$B->devicePtrRW(),$offsetB,$ldB));
     }
+
+    /**
+     * Row-sharded gemm whose C stripe also lands in every other process's full C (one process per GPU).
+     * $C[$offsetC...] is this rank's stripe inside its own full C; $peers are the other ranks' full-C allocations mapped
+     * here (rb200_ipc_open of handles from rb200_ipc_export), or -- with $multicast, the NVLS multicast alias of a
+     * symmetric allocation -- the single address a multimem store replicates through the NVSwitch.  Order the ranks
+     * afterwards (a barrier of the process group).  Executable mirror: CudaBlas.gemmAllgather / sharding.RowShardedGemm.
+     * @param array<int,mixed> $peers  void* device pointers
+     */
+    public function gemmAllgather(int $transA,int $transB,int $m,int $n,int $k,float $alpha,
+        Buffer $A,int $offsetA,int $ldA,Buffer $B,int $offsetB,int $ldB,float $beta,
+        Buffer $C,int $offsetC,int $ldC,array $peers,mixed $multicast=null) : void
+    {
+        $ffi = CudaFFI::lib();
+        if ($multicast!==null) {
+            CudaFFI::check($ffi->rb200_sgemm_allgather_mc(BLAS::RowMajor,$transA,$transB,$m,$n,$k,$alpha,
+                $ffi->cast('float*',$A->devicePtr()),$offsetA,$ldA,$ffi->cast('float*',$B->devicePtr()),$offsetB,$ldB,
+                $beta,$ffi->cast('float*',$C->devicePtrRW()),$offsetC,$ldC,$this->gemmMode,$multicast));
+            return;
+        }
+        $np = count($peers);
+        $arr = $ffi->new('void*['.max(1,$np).']');
+        foreach (array_values($peers) as $i => $ptr) { $arr[$i] = $ptr; }
+        CudaFFI::check($ffi->rb200_sgemm_allgather(BLAS::RowMajor,$transA,$transB,$m,$n,$k,$alpha,
+            $ffi->cast('float*',$A->devicePtr()),$offsetA,$ldA,$ffi->cast('float*',$B->devicePtr()),$offsetB,$ldB,
+            $beta,$ffi->cast('float*',$C->devicePtrRW()),$offsetC,$ldC,$this->gemmMode,$np,$arr));
+    }
+
+    /**
+     * Record the driver calls issued by $calls into a CUDA graph and return a handle; graphLaunch() replays them with
+     * one driver call (launch-bound sequences of small operations).  Issue the sequence once before capturing; no
+     * allocating, scalar-returning or host-transfer calls inside.
+     */
+    public function graphCapture(callable $calls) : mixed
+    {
+        $ffi = CudaFFI::lib();
+        CudaFFI::check($ffi->rb200_graph_begin());
+        try { $calls(); } finally {
+            $exec = $ffi->new('void*');
+            $rc = $ffi->rb200_graph_end(\FFI::addr($exec));
+        }
+        CudaFFI::check($rc);
+        return $exec;
+    }
+    public function graphLaunch(mixed $exec) : void { CudaFFI::check(CudaFFI::lib()->rb200_graph_launch($exec)); }
+    public function graphDestroy(mixed $exec) : void { CudaFFI::check(CudaFFI::lib()->rb200_graph_destroy($exec)); }
 }

@@ -728,4 +728,51 @@ class CudaMath extends PhpMath
             $A->devicePtr(),$offsetA,$ldA,$strideA,$B->devicePtr(),$offsetB,$ldB,$strideB,$beta,
             $C->devicePtrRW(),$offsetC,$ldC,$strideC,$batchSize,0));
     }
+
+    /**
+     * Fused conv2d forward: out[b,oy,ox,f] = im2col2d(images) x kernel (+ bias) without a cols buffer
+     * (rb200_conv2d_forward; the composition LinearAlgebra users write by hand is im2col :3369 -> gemm :925 -> add :1968,
+     * and LinearAlgebraCL::im2col2dclblast :5001-5144 is the reference's own fused precedent).  Channels-last images
+     * [b,h,w,c], kernel [kh,kw,c,filters].  Returns false -- nothing launched -- when the shape needs the two-call path
+     * (status RB200_E_UNSUPPORTED): short reductions kh*kw*c <= 32 and hidden layers with channels % 32 == 0 are taken.
+     */
+    public function conv2dForward(Buffer $images,int $imagesOffset,int $batches,int $im_h,int $im_w,int $channels,
+        int $filter_h,int $filter_w,int $stride_h,int $stride_w,bool $padding,int $dilation_h,int $dilation_w,
+        Buffer $kernel,int $kernelOffset,int $filters,?Buffer $bias,int $biasOffset,Buffer $out,int $outOffset,
+        int $gemmMode=0) : bool
+    {
+        if (!$this->onDevice($images) || !($kernel instanceof CudaBuffer) || !($out instanceof CudaBuffer)) { return false; }
+        if (count($images)-$imagesOffset < $batches*$im_h*$im_w*$channels)
+            throw new InvalidArgumentException('images buffer size is invalid');
+        if (count($kernel)-$kernelOffset < $filter_h*$filter_w*$channels*$filters)
+            throw new InvalidArgumentException('kernel buffer size is invalid');
+        if ($bias!==null && count($bias)-$biasOffset < $filters)
+            throw new InvalidArgumentException('bias buffer size is invalid');
+        $rc = CudaFFI::lib()->rb200_conv2d_forward($images->abiDtype(),$images->devicePtr(),$imagesOffset,
+            $batches,$im_h,$im_w,$channels,$filter_h,$filter_w,$stride_h,$stride_w,$padding?1:0,$dilation_h,$dilation_w,
+            $kernel->devicePtr(),$kernelOffset,$filters,($bias instanceof CudaBuffer)?$bias->devicePtr():null,$biasOffset,
+            $out->devicePtrRW(),$outOffset,$gemmMode);
+        if ($rc == -3) { return false; }                  // RB200_E_UNSUPPORTED
+        CudaFFI::check($rc);
+        return true;
+    }
+
+    /**
+     * (value, index) records of ONE STRIPE of a reduced axis that is sharded over processes, for the cross-rank merge
+     * of math_imax (PhpMath.php:114-130): $records is an int64 CudaBuffer holding two words per output -- the bits of
+     * the double value, then the stripe-local index.  $global0: the stripe starts at global position 0.
+     */
+    public function reduceArgMaxPartial(int $m,int $n,int $k,Buffer $A,int $offsetA,bool $global0,
+        Buffer $records,int $offsetRecords) : void
+    {
+        if (!$this->onDevice($A) || !($records instanceof CudaBuffer))
+            throw new InvalidArgumentException('reduceArgMaxPartial needs device buffers');
+        if ($m<1||$n<1||$k<1) throw new InvalidArgumentException('m, n and k must be greater than 0.');
+        if ($offsetA<0 || $offsetA+$m*$n*$k>count($A))
+            throw new InvalidArgumentException('Matrix specification too large for bufferA.');
+        if ($offsetRecords<0 || 2*($offsetRecords+$m*$k)>count($records))
+            throw new InvalidArgumentException('records must be an int64 buffer of two words per output');
+        CudaFFI::check(CudaFFI::lib()->rb200_reduce_argmax_partial($A->abiDtype(),$m,$n,$k,$A->devicePtr(),$offsetA,
+            $global0?1:0,$records->devicePtrRW(),$offsetRecords));
+    }
 }
