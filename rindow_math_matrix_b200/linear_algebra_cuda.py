@@ -74,8 +74,9 @@ class LinearAlgebraCuda(LinearAlgebra):
     def finish(self) -> None:
         self.queue.finish()
 
-    def newEventList(self) -> CudaEventList:
-        return CudaEventList()
+    def newEventList(self):
+        make = getattr(self.queue, "newEventList", None)         # a non-CUDA queue brings its own event lists
+        return make() if make else CudaEventList()
 
     # ---- arrays (LinearAlgebraCL.php:321-368, 441-460, 793-814) --------------------------------------------------
     def array(self, array, dtype: int | None = None, flags: int | None = None) -> NDArrayCuda:

@@ -206,7 +206,7 @@ class NDArrayCuda(NDArrayInterface):
         if service is None:
             raise InvalidArgumentException("No service specified.")                       # NDArrayCL.php:77-79
         self._service = service
-        self._factory = service.buffer(service.LV_ACCELERATED)
+        self._factory = service.buffer(getattr(service, "LV_ACCELERATED", 3))
         self._queue = queue
         self._context = queue.getContext()
         dtype = dtypes.float32 if dtype is None else dtype
@@ -219,7 +219,8 @@ class NDArrayCuda(NDArrayInterface):
         self._flags = flags
         self._events = None
         size = self.size()
-        if isinstance(buffer, CudaDeviceBuffer):
+        if isinstance(buffer, CudaDeviceBuffer) or (hasattr(buffer, "bytes") and hasattr(buffer, "read")
+                                                   and getattr(buffer, "is_device_buffer", False)):
             if buffer.bytes() < (size + offset) * dtypes.VALUE_SIZE[dtype]:
                 raise InvalidArgumentException("Invalid dimension size")
             self._dtype, self._buffer, self._offset = dtype, buffer, offset
@@ -293,6 +294,8 @@ class NDArrayCuda(NDArrayInterface):
         return self.toNDArray().toArray()
 
     def to_numpy(self) -> np.ndarray:
+        if not hasattr(self._buffer, "read_range"):               # a non-CUDA device buffer: go through toNDArray
+            return self.toNDArray().to_numpy()
         flat = self._buffer.read_range(self._offset, self.size())
         out = flat.reshape(self._shape)
         return out.astype(bool) if self._dtype == dtypes.bool_ else out

@@ -415,8 +415,88 @@ class OracleBufferFactory:
         return OracleBuffer(size, dtype)
 
 
+class OracleDeviceBuffer(OracleBuffer):
+    """DeviceBuffer stand-in (src/NDArrayCL.php:147-168, 261-270, 416-441): bytes() + queue-ordered read / write / copy
+    with BYTE sizes and offsets, backed by the same numpy storage as OracleBuffer -- so NDArrayCuda / LinearAlgebraCuda
+    (the host logic of the device tier) run on CPU in the not-gpu suite."""
+    is_device_buffer = True
+
+    def __init__(self, context, bytes_, flags=0, hostBuffer=None, hostOffset=0, dtype=None):
+        if dtype is None:
+            dtype = hostBuffer.dtype()
+        vs = dtypes.VALUE_SIZE[dtype]
+        super().__init__(bytes_ // vs, dtype)
+        self._vs = vs
+        self._flags = flags
+        if hostBuffer is not None:
+            self.write(None, hostBuffer, bytes_, 0, hostOffset * vs)
+
+    def bytes(self):
+        return self.data.size * self._vs
+
+    def _partner_vs(self, other):
+        return dtypes.VALUE_SIZE[other.dtype()]
+
+    def read(self, queue, hostBuf, size=0, offset=0, hostoffset=0, blocking_read=None, events=None, waitEvents=None):
+        n = (size or self.bytes() - offset) // self._vs
+        o, h = offset // self._vs, hostoffset // self._partner_vs(hostBuf)
+        hostBuf.data[h:h + n] = self.data[o:o + n]
+        if events is not None:
+            events.record()
+
+    def write(self, queue, hostBuf, size=0, offset=0, hostoffset=0, blocking_write=None, events=None, waitEvents=None):
+        pvs = self._partner_vs(hostBuf)
+        n = (size // self._vs) if size else min(hostBuf.data.size - hostoffset // pvs, self.data.size - offset // self._vs)
+        o, h = offset // self._vs, hostoffset // pvs
+        self.data[o:o + n] = hostBuf.data[h:h + n]
+        if events is not None:
+            events.record()
+
+    def copy(self, queue, src, size=0, src_offset=0, dst_offset=0, events=None, waitEvents=None):
+        n = (size or src.bytes() - src_offset) // self._vs
+        so, do = src_offset // self._vs, dst_offset // self._vs
+        self.data[do:do + n] = src.data[so:so + n]
+        if events is not None:
+            events.record()
+
+
+class OracleDeviceBufferFactory:
+    def isAvailable(self):
+        return True
+
+    def Buffer(self, context, bytes_, flags=0, hostBuffer=None, hostOffset=0, dtype=None):
+        return OracleDeviceBuffer(context, bytes_, flags, hostBuffer, hostOffset, dtype)
+
+
+class OracleEventList:
+    def __init__(self):
+        self.n = 0
+
+    def record(self):
+        self.n += 1
+
+    def wait(self):
+        pass
+
+    def __len__(self):
+        return self.n
+
+
+class OracleQueue:
+    finished = 0
+
+    def getContext(self):
+        return self
+
+    def finish(self):
+        self.finished += 1
+
+    def newEventList(self):
+        return OracleEventList()
+
+
 class OracleService:
-    LV_BASIC, LV_ADVANCED = 1, 2
+    LV_BASIC, LV_ADVANCED, LV_ACCELERATED = 1, 2, 3
 
     def __init__(self, sticky_max=False):
         self._blas, self._math, self._buffer = OracleBlas(), OracleMath(), OracleBufferFactory()
@@ -435,4 +515,9 @@ class OracleService:
         return self._math
 
     def buffer(self, level=None):
+        if level == self.LV_ACCELERATED:
+            return OracleDeviceBufferFactory()
         return self._buffer
+
+    def createQueue(self, options=None):
+        return OracleQueue()
