@@ -215,10 +215,11 @@ int rb200_sgemm_allgather(int order, int transA, int transB, int64_t m, int64_t 
                           int n_peers, void* const* peer_C);
 /* The same call over an NVLS multicast mapping (NVSwitch): `mc_C` is the multicast alias of the symmetric allocation
  * that holds C on every rank (cuMulticastCreate / cuMulticastBindMem; torch.distributed._symmetric_memory provides it
- * as handle.multicast_ptr), indexed like C.  The CTA-pair kernel's epilogue stores each finished 128-byte row segment
- * ONCE with multimem.st and the switch replicates it into every rank's copy (this rank's included) -- a stripe leaves
- * the GPU once instead of once per peer.  Other kernel families multiply first and push the stripe with a multimem
- * copy kernel on the same stream.  Same ordering contract as rb200_sgemm_allgather. */
+ * as handle.multicast_ptr), indexed like C.  In the CTA-pair kernel a pusher warp per CTA reads every finished tile back
+ * through L2 and stores it ONCE with multimem.st (512 contiguous bytes per instruction, decoupled from the TMEM drain by
+ * a 4-tile mbarrier ring); the switch replicates it into every rank's copy (this rank's included) -- a stripe leaves the
+ * GPU once instead of once per peer.  beta != 0 stores from the epilogue instead; other kernel families multiply first
+ * and push the stripe with a multimem copy kernel on the same stream.  Same ordering contract as rb200_sgemm_allgather. */
 int rb200_sgemm_allgather_mc(int order, int transA, int transB, int64_t m, int64_t n, int64_t k,
                              float alpha, const float* A, int64_t offA, int64_t ldA,
                              const float* B, int64_t offB, int64_t ldB,

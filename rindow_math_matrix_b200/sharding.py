@@ -231,7 +231,12 @@ class RowShardedGemm:
         self.world = _world(group)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.start, self.rows = row_range(self.M, self.world, self.rank)
-        self.bstart, self.brows = row_range(self.K, self.world, self.rank)         # this rank's slice of B's rows
+        # this rank's slice of B's rows for the host-operand form; when K does not divide evenly every rank uploads all
+        # of B itself (the in-place all-gather needs equal slices)
+        if self.K % self.world == 0:
+            self.bstart, self.brows = row_range(self.K, self.world, self.rank)
+        else:
+            self.bstart, self.brows = 0, self.K
         if self.rows < 1:
             raise ValueError("every rank needs at least one row of A")
         f32 = dtypes.float32
@@ -290,21 +295,17 @@ class RowShardedGemm:
         self._Bslice._wait_upload()
         if self.brows:
             _capi.check(lib.rb200_buffer_h2d_async(dB, self.bstart * self.N * 4, hS, self.brows * self.N * 4))
-        if self.world > 1:
+        if self.world > 1 and self.brows < self.K:
             tB = tensor_of(self.B)
-            ranges = all_row_ranges(self.K, self.world)
-            if len({r for _, r in ranges}) == 1:
-                dist.all_gather_into_tensor(tB, tB[self.bstart * self.N:(self.bstart + self.brows) * self.N], group=self.group)
-            else:
-                parts = [tB[s * self.N:(s + r) * self.N] for s, r in ranges]
-                dist.all_gather(parts, parts[self.rank], group=self.group)
+            dist.all_gather_into_tensor(tB, tB[self.bstart * self.N:(self.bstart + self.brows) * self.N], group=self.group)
         self.A.mark_host_written()
+        previous = self.blas.host_result_prefetch
         self.blas.setHostResultPrefetch(True)
         try:
             self.blas.gemm(BLAS.RowMajor, BLAS.NoTrans, BLAS.NoTrans, self.rows, self.N, self.K, alpha, self.A, 0, self.K,
                            self.B, 0, self.N, 0.0, self._Cstripe, 0, self.N)
         finally:
-            self.blas.setHostResultPrefetch(None)
+            self.blas.setHostResultPrefetch(previous)
         self._Cstripe.host()                      # current: the streamed call already brought it back
 
     def close(self) -> None:
