@@ -6,6 +6,8 @@
 // axpy :165-194  Y[i] = alpha*X[i] + Y[i];  copy :350-364  Y[i] = X[i];
 // gemv :762-844  Y[i] = sum_j (alpha*opA[i,j])*X[j] (+ beta*Y[i] iff beta != 0).  All HBM-bound:
 // 128-bit accesses when the increments are 1 and the operands 16-byte aligned, strided scalar otherwise.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -133,9 +135,9 @@ int blas1_dispatch(int dtype, int64_t n, double alpha, const void* X, int64_t of
 // CTAs per SM (<= 32 registers) so that the 8192 rows of the bench shape are all resident in ONE wave: with 4
 // CTAs per SM the same launch is 1.73 waves and pays the tail.  VEC: 16-byte loads of A and X (ldA, the
 // offsets and the base pointers 16-byte aligned, incX == 1), four packs in flight per lane.
-constexpr int GEMV_PACKS = 2;     // 16-byte packs of A in flight per lane: <= 32 registers, 64 warps resident per SM
+constexpr int GEMV_PACKS = 2;     // 16-byte packs of A in flight per lane (3 also fits 32 registers; measured the same: 24.8 vs 25.0 us)
 
-template <typename T, bool VEC, int SPLIT>
+template <typename T, bool VEC, int SPLIT, int PACKS>
 __global__ void __launch_bounds__(B1_THREADS, SPLIT == 1 ? 8 : 6)
 gemv_n_kernel(int64_t m, int64_t n, int64_t part_cols, T alpha, const T* __restrict__ A, int64_t ldA,
               const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY)
@@ -159,15 +161,15 @@ gemv_n_kernel(int64_t m, int64_t n, int64_t part_cols, T alpha, const T* __restr
                 const int64_t v0 = c_begin / V, v1 = c_end / V;
                 const int4* rv = reinterpret_cast<const int4*>(row);
                 const int4* xv = reinterpret_cast<const int4*>(X);
-                for (int64_t jb = v0; jb < v1; jb += 32 * GEMV_PACKS) {
-                    B1Pack<T> a[GEMV_PACKS];
+                for (int64_t jb = v0; jb < v1; jb += 32 * PACKS) {
+                    B1Pack<T> a[PACKS];
 #pragma unroll
-                    for (int q = 0; q < GEMV_PACKS; q++) {
+                    for (int q = 0; q < PACKS; q++) {
                         const int64_t jv = jb + q * 32 + lane;
                         if (jv < v1) a[q].raw = __ldcs(rv + jv);
                     }
 #pragma unroll
-                    for (int q = 0; q < GEMV_PACKS; q++) {
+                    for (int q = 0; q < PACKS; q++) {
                         const int64_t jv = jb + q * 32 + lane;
                         if (jv < v1) {
                             B1Pack<T> x;
@@ -211,7 +213,7 @@ gemv_n_kernel(int64_t m, int64_t n, int64_t part_cols, T alpha, const T* __restr
 // adds the segments in a fixed order -- one launch, deterministic.
 constexpr int GEMV_T_PACKS = 4;
 
-template <typename T, int CPT>
+template <typename T, int CPT, int TPACKS>
 __global__ void __launch_bounds__(B1_THREADS)
 gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restrict__ A, int64_t ldA,
               const T* __restrict__ X, int64_t incX, T beta, T* __restrict__ Y, int64_t incY, T* __restrict__ partial,
@@ -233,15 +235,15 @@ gemv_t_kernel(int64_t m, int64_t n, int64_t seg_rows, T alpha, const T* __restri
         }
     } else if (j < n) {                    // n % CPT == 0 on this path: a pack never straddles the edge
         const T* a = A + j;
-        for (int64_t ib = i0 + ty; ib < i1; ib += 8 * GEMV_T_PACKS) {
-            B1Pack<T> v[GEMV_T_PACKS];
+        for (int64_t ib = i0 + ty; ib < i1; ib += 8 * TPACKS) {
+            B1Pack<T> v[TPACKS];
 #pragma unroll
-            for (int u = 0; u < GEMV_T_PACKS; u++) {
+            for (int u = 0; u < TPACKS; u++) {
                 const int64_t i = ib + u * 8;
                 if (i < i1) v[u].raw = __ldcs(reinterpret_cast<const int4*>(a + i * ldA));
             }
 #pragma unroll
-            for (int u = 0; u < GEMV_T_PACKS; u++) {
+            for (int u = 0; u < TPACKS; u++) {
                 const int64_t i = ib + u * 8;
                 if (i < i1) {
                     const T x = __ldg(X + i * incX);
@@ -321,7 +323,7 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
         static int resident = 0;
         if (!resident) {
             int per_sm = 0;
-            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_n_kernel<T, true, 1>, B1_THREADS, 0));
+            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_n_kernel<T, true, 1, GEMV_PACKS>, B1_THREADS, 0));
             resident = (per_sm > 0 ? per_sm : 1) * c.sm_count;
         }
         // one warp per row; rows are split over 2/4/8 warps only when there are too few of them to occupy the SMs
@@ -330,8 +332,11 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
         const int64_t units = rb_ceil_div(m * split, B1_THREADS / 32);
         int64_t grid = units < resident ? units : resident;
         int64_t part_cols = rb_ceil_div(rb_ceil_div(n, split), 128) * 128;
-#define RB_GEMV_N(VEC_, SP_) gemv_n_kernel<T, VEC_, SP_><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>( \
-            m, n, part_cols, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY)
+        static const int n_packs = getenv("RB200_GEMV_PACKS") ? atoi(getenv("RB200_GEMV_PACKS")) : GEMV_PACKS;
+#define RB_GEMV_N(VEC_, SP_) do { if (n_packs == 2) gemv_n_kernel<T, VEC_, SP_, 2><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>( \
+            m, n, part_cols, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY); \
+        else gemv_n_kernel<T, VEC_, SP_, 3><<<(unsigned)grid, B1_THREADS, 0, c.stream>>>( \
+            m, n, part_cols, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY); } while (0)
         if (vec) { if (split == 1) RB_GEMV_N(true, 1); else if (split == 2) RB_GEMV_N(true, 2);
                    else if (split == 4) RB_GEMV_N(true, 4); else RB_GEMV_N(true, 8); }
         else     { if (split == 1) RB_GEMV_N(false, 1); else if (split == 2) RB_GEMV_N(false, 2);
@@ -346,7 +351,7 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
         static int t_resident = 0;
         if (!t_resident) {
             int per_sm = 0;
-            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_t_kernel<T, V>, B1_THREADS, 0));
+            RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_t_kernel<T, V, GEMV_T_PACKS>, B1_THREADS, 0));
             t_resident = (per_sm > 0 ? per_sm : 1) * c.sm_count;
         }
         int64_t segs = t_resident / gx;
@@ -365,8 +370,10 @@ int gemv_launch(bool trans, int64_t m, int64_t n, double alpha, const void* Av, 
             if (rc != RB200_OK) return rc;
         }
         const dim3 grid((unsigned)gx, (unsigned)segs);
-        if (vec) gemv_t_kernel<T, V><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
-        else gemv_t_kernel<T, 1><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
+        static const int t_packs = getenv("RB200_GEMV_T_PACKS") ? atoi(getenv("RB200_GEMV_T_PACKS")) : GEMV_T_PACKS;
+        if (vec && t_packs >= 8) gemv_t_kernel<T, V, 8><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
+        else if (vec) gemv_t_kernel<T, V, 4><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
+        else gemv_t_kernel<T, 1, 4><<<grid, B1_THREADS, 0, c.stream>>>(m, n, seg_rows, (T)alpha, A, ldA, X, incX, (T)beta, Y, incY, partial, counters);
         RB_LAUNCH_CHECK("gemv_t_kernel");
     }
     return RB200_OK;
