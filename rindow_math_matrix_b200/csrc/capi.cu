@@ -142,6 +142,8 @@ int rb200_shutdown(void)
     if (c.counters) cudaFree(c.counters);
     c.counters = nullptr;
     c.counters_len = 0;
+    if (c.gemm_sync) cudaFree(c.gemm_sync);
+    c.gemm_sync = nullptr;
     if (c.pinned_scalar) cudaFreeHost(c.pinned_scalar);
     c.pinned_scalar = nullptr;
     if (c.switch_event) cudaEventDestroy(c.switch_event);

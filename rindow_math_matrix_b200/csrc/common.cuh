@@ -36,6 +36,8 @@ struct Context {
     bool        gemm_peers_written = false;
     // multicast alias of C (+ offC) the next tensor-core GEMM stores its final values to (rb200_sgemm_allgather_mc)
     float*      gemm_mc = nullptr;
+    // arrival / exit counters of the CTA-pair GEMM's meeting points (gemm_tcgen05.cu, TcParams::sync_cnt)
+    unsigned int* gemm_sync = nullptr;
 };
 
 Context& ctx();

@@ -174,6 +174,11 @@ struct TcParams {
     // CTA-pair kernel: every `sync_kb` k-blocks the producers of all pairs meet at a device-wide progress counter, so
     // the tiles of a wave walk K within one chunk of each other and the A / B panel slices they share are fetched
     // from DRAM once (0 = free running).  sync_cnt[0] = arrivals, sync_cnt[1] = finished CTAs (reset by the last one).
+    // The spin needs every CTA of the wave resident at once: the grid is at most one CTA per SM, and the library
+    // issues all of its kernels on ONE stream (rb200_set_stream orders a new stream behind the old one), so no other
+    // kernel of this context can hold SMs while a wave waits (a kernel of another stream that does not itself wait
+    // on this one only delays the wave).  Two processes on one GPU time-slice whole contexts; under MPS, where two
+    // such GEMMs could interleave their CTAs, run with RB200_GEMM_SYNC_KB=0.
     int sync_kb;
     unsigned int* sync_cnt;
 };
@@ -1226,13 +1231,12 @@ int gemm_tcgen05(int mode, bool transA, bool transB, int64_t M, int64_t N, int64
                 // 17.7 GB with the meeting points (75 %, 1.34 GHz) -- 631-662 -> 704-718 TFLOP/s; 8192^3 +1 %.
                 // RB200_GEMM_SYNC_KB=0 switches it off.
                 static const int sync_kb = getenv("RB200_GEMM_SYNC_KB") ? atoi(getenv("RB200_GEMM_SYNC_KB")) : 64;
-                static unsigned int* sync_cnt = nullptr;
-                if (sync_kb > 0 && !sync_cnt) {
-                    RB_CUDA(cudaMalloc(&sync_cnt, 2 * sizeof(unsigned int)));
-                    RB_CUDA(cudaMemsetAsync(sync_cnt, 0, 2 * sizeof(unsigned int), c.stream));
+                if (sync_kb > 0 && !c.gemm_sync) {               // per context: freed by rb200_shutdown with the device
+                    RB_CUDA(cudaMalloc(&c.gemm_sync, 2 * sizeof(unsigned int)));
+                    RB_CUDA(cudaMemsetAsync(c.gemm_sync, 0, 2 * sizeof(unsigned int), c.stream));
                 }
                 const int64_t kmin = getenv("RB200_GEMM_SYNC_MINK") ? atoll(getenv("RB200_GEMM_SYNC_MINK")) : 0;
-                if (sync_kb > 0 && kl >= kmin) { p.sync_kb = sync_kb; p.sync_cnt = sync_cnt; }
+                if (sync_kb > 0 && kl >= kmin) { p.sync_kb = sync_kb; p.sync_cnt = c.gemm_sync; }
             }
             rc = planes == 1 ? launch_2cta<1>(a_mn, b_mn, mA, mB2, p) : launch_2cta<2>(a_mn, b_mn, mA, mB2, p);
             c.last_gemm_path = planes == 1 ? "tcgen05_tf32_2cta" : "tcgen05_tf32x3_2cta";
