@@ -218,6 +218,8 @@ class Graph:
         if et is None:
             check(rc)
             self._exec = ex
+        elif rc == 0 and ex:
+            load().rb200_graph_destroy(ex)      # the body raised: end the capture, keep nothing
         return False
 
     def launch(self) -> None:

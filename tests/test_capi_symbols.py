@@ -77,3 +77,63 @@ def test_library_is_sm100a_only_with_blackwell_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+
+
+def _header_prototypes(text):
+    """symbol -> [coarse parameter types] ('int', 'i64', 'float', 'double', 'ptr') from C prototype text."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"\b(rb200_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        kinds = []
+        if params not in ("", "void"):
+            for p in params.split(","):
+                p = " ".join(p.split())
+                if "*" in p or "[" in p:
+                    kinds.append("ptr")
+                elif re.search(r"\bint64_t\b", p):
+                    kinds.append("i64")
+                elif re.search(r"\bdouble\b", p):
+                    kinds.append("double")
+                elif re.search(r"\bfloat\b", p):
+                    kinds.append("float")
+                elif re.search(r"\bint\b", p):
+                    kinds.append("int")
+                else:
+                    raise AssertionError("unrecognised parameter '%s' of %s" % (p, m.group(1)))
+        protos[m.group(1)] = kinds
+    return protos
+
+
+def test_ctypes_argtypes_match_the_header_prototypes():
+    """Arity and coarse type of every bound argument: an int passed where the ABI takes int64_t (or a float for a
+    double) corrupts the call silently."""
+    with open(os.path.join(ROOT, "include", "rindow_b200.h")) as f:
+        protos = _header_prototypes(f.read())
+    assert sorted(protos) == header_symbols()
+
+    def kind(t):
+        if t is ctypes.c_int:
+            return "int"
+        if t is ctypes.c_int64:
+            return "i64"
+        if t is ctypes.c_float:
+            return "float"
+        if t is ctypes.c_double:
+            return "double"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        raise AssertionError("unexpected ctypes type %r" % (t,))
+
+    for name, (_, args) in _capi.SIGNATURES.items():
+        assert [kind(t) for t in args] == protos[name], name
+
+
+def test_php_cdef_prototypes_match_the_header():
+    with open(os.path.join(ROOT, "include", "rindow_b200.h")) as f:
+        protos = _header_prototypes(f.read())
+    with open(os.path.join(ROOT, "php", "MatlibCuda", "CudaFFI.php")) as f:
+        php = f.read()
+    cdef = php[php.index("<<<'CDEF'") + len("<<<'CDEF'"):php.index("CDEF;")]
+    assert _header_prototypes(cdef) == protos
