@@ -25,18 +25,3 @@ class CudaQueue
     public function finish() : void { CudaFFI::check(CudaFFI::lib()->rb200_sync()); }
     public function flush() : void {}
 }
-
-class CudaContext
-{
-    /** @return array<string,int> */
-    public function getInfo(mixed $what=null) : array
-    {
-        $ffi = CudaFFI::lib();
-        $dev = $ffi->new('int'); $sm = $ffi->new('int'); $maj = $ffi->new('int'); $mnr = $ffi->new('int');
-        $mem = $ffi->new('int64_t');
-        CudaFFI::check($ffi->rb200_device_info(\FFI::addr($dev), \FFI::addr($sm), \FFI::addr($maj), \FFI::addr($mnr),
-            \FFI::addr($mem)));
-        return ['device'=>$dev->cdata, 'sm_count'=>$sm->cdata, 'cc_major'=>$maj->cdata, 'cc_minor'=>$mnr->cdata,
-                'total_mem'=>$mem->cdata];
-    }
-}

@@ -2,6 +2,7 @@
 namespace Rindow\Math\Matrix;
 
 use InvalidArgumentException;
+use LogicException;
 use Interop\Polite\Math\Matrix\NDArray;
 use Interop\Polite\Math\Matrix\LinearBuffer;
 use Interop\Polite\Math\Matrix\DeviceBuffer;
@@ -14,7 +15,12 @@ use Rindow\Math\Matrix\Drivers\MatlibCuda\CudaEventList;
  * NDArrayCuda.  Constructed from a queue and the service (:75-93); accelerated() is true (:234-237); array() uploads
  * host arrays and passes device arrays through (:321-352); toNDArray() downloads (:354-360); alloc() creates device
  * arrays (:441-460); allocHost()/zerosHost() stay on the host (:793-814); blocking()/finish() (:145-152, :250-253);
- * scalar-valued calls return rank-0 device arrays unless scalarNumeric(true) (:220-227, :2526-2529).
+ * Scalar-valued calls (sum, asum, nrm2, amax, amin, max, min, imax, imin, iamax, iamin, dot) are inherited as they are
+ * and return PHP numbers: LinearAlgebra declares them `: float` / `: int`, and PHP's covariant return types do not let a
+ * subclass hand back the rank-0 device array LinearAlgebraCL returns when scalarNumeric is off (:220-227, :2526-2529).
+ * scalarNumeric() therefore reports true and refuses false; `$la->scalar($la->sum($x))`, the form the reference's
+ * accelerated tests use (tests/RindowTest/Math/Matrix/LinearAlgebraTest.php), works unchanged.  The scalar comes back
+ * through a blocking d2h copy of one element, so these calls are synchronising in either blocking() mode.
  *
  * Every operation is INHERITED from LinearAlgebra (src/LinearAlgebra.php): its methods only do shape algebra and one
  * positional call on $this->blas / $this->math with `$X->buffer(), $X->offset()`, and CudaBlas / CudaMath take
@@ -28,10 +34,6 @@ class LinearAlgebraCuda extends LinearAlgebra
     protected object $queue;
     protected object $context;
     protected bool $blocking = false;
-    protected bool $scalarNumeric = false;
-
-    /** scalar-valued methods wrapped by __call-free overrides below */
-    protected const INDEX_CALLS = ['imax','imin','iamax','iamin'];
 
     public function __construct(object $queue, Service $service, ?int $defaultFloatType=null)
     {
@@ -58,8 +60,10 @@ class LinearAlgebraCuda extends LinearAlgebra
 
     public function scalarNumeric(?bool $switch=null) : bool
     {
-        if($switch!==null) { $this->scalarNumeric = $switch; }
-        return $this->scalarNumeric;
+        if($switch===false) {
+            throw new LogicException('LinearAlgebraCuda returns scalars as numbers (return types of LinearAlgebra).');
+        }
+        return true;
     }
 
     public function array(mixed $array, ?int $dtype=null, ?int $flags=null) : NDArray
@@ -109,33 +113,5 @@ class LinearAlgebraCuda extends LinearAlgebra
     {
         $this->math->zeros($X->size(), $X->buffer(), $X->offset(), 1);
         return $X;
-    }
-
-    /** rank-0 device array holding a scalar result (LinearAlgebraCL returns $R unless scalarNumeric) */
-    protected function scalarResult(string $name, mixed $value, ?NDArray $like) : mixed
-    {
-        if($this->blocking) { $this->finish(); }
-        if($this->scalarNumeric || !is_numeric($value)) {
-            return $value;
-        }
-        $dtype = in_array($name, self::INDEX_CALLS) ? NDArray::int32
-               : (($like!==null && $this->isFloat($like)) ? $like->dtype() : $this->defaultFloatType);
-        return $this->array(new NDArrayPhp($value, dtype:$dtype, service:$this->service));
-    }
-
-    public function sum(NDArray $X) : mixed   { return $this->scalarResult('sum',   parent::sum($X),   $X); }
-    public function asum(NDArray $X) : mixed  { return $this->scalarResult('asum',  parent::asum($X),  $X); }
-    public function nrm2(NDArray $X) : mixed  { return $this->scalarResult('nrm2',  parent::nrm2($X),  $X); }
-    public function amax(NDArray $X) : mixed  { return $this->scalarResult('amax',  parent::amax($X),  $X); }
-    public function amin(NDArray $X) : mixed  { return $this->scalarResult('amin',  parent::amin($X),  $X); }
-    public function max(NDArray $X) : mixed   { return $this->scalarResult('max',   parent::max($X),   $X); }
-    public function min(NDArray $X) : mixed   { return $this->scalarResult('min',   parent::min($X),   $X); }
-    public function imax(NDArray $X) : mixed  { return $this->scalarResult('imax',  parent::imax($X),  $X); }
-    public function imin(NDArray $X) : mixed  { return $this->scalarResult('imin',  parent::imin($X),  $X); }
-    public function iamax(NDArray $X) : mixed { return $this->scalarResult('iamax', parent::iamax($X), $X); }
-    public function iamin(NDArray $X) : mixed { return $this->scalarResult('iamin', parent::iamin($X), $X); }
-    public function dot(NDArray $X, NDArray $Y, ?bool $conj=null) : mixed
-    {
-        return $this->scalarResult('dot', parent::dot($X, $Y, $conj), $X);
     }
 }

@@ -3,6 +3,10 @@ namespace RindowTest\Math\Matrix\LinearAlgebraCudaTest;
 
 use Rindow\Math\Matrix\Drivers\Service;
 use Rindow\Math\Matrix\Drivers\MatlibCuda\MatlibCuda;
+// the reference's test classes are not autoloaded (cf. LinearAlgebraPHPModeTest.php:12-14)
+if(!class_exists('RindowTest\Math\Matrix\LinearAlgebraTest\LinearAlgebraTest')) {
+    require_once __DIR__.'/LinearAlgebraTest.php';
+}
 use RindowTest\Math\Matrix\LinearAlgebraTest\LinearAlgebraTest as ORGTest;
 
 /**

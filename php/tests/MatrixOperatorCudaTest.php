@@ -4,6 +4,10 @@ namespace RindowTest\Math\Matrix\MatrixOperatorCudaTest;
 use Rindow\Math\Matrix\MatrixOperator;
 use Rindow\Math\Matrix\Drivers\Service;
 use Rindow\Math\Matrix\Drivers\MatlibCuda\MatlibCuda;
+// the reference's test classes are not autoloaded (cf. LinearAlgebraPHPModeTest.php:12-14)
+if(!class_exists('RindowTest\Math\Matrix\MatrixOperatorTest\MatrixOperatorTest')) {
+    require_once __DIR__.'/MatrixOperatorTest.php';
+}
 use RindowTest\Math\Matrix\MatrixOperatorTest\MatrixOperatorTest as ORGTest;
 
 /** MatrixOperatorTest over the B200 driver (cf. MatrixOperatorPhpModeTest.php:14-25). */

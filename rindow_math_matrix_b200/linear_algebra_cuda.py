@@ -5,7 +5,9 @@ the service (:75-93), `accelerated()` is true (:234-237), `array()` uploads a ho
 device array and passes device arrays through (:321-352), `toNDArray()` downloads (:354-360), `alloc()` creates
 device arrays (:441-460), `allocHost()` / `zerosHost()` stay on the host (:793-814), `blocking()` / `finish()` control
 whether a call returns before its kernels have run (:145-152, 250-253), scalar-valued calls return rank-0 device
-arrays unless `scalarNumeric(true)` (:220-227, 2526-2529), `scalar()` reads one back (:362-368).
+arrays unless `scalarNumeric(true)` (:220-227, 2526-2529), `scalar()` reads one back (:362-368).  (The PHP class,
+php/MatlibCuda/LinearAlgebraCuda.php, extends LinearAlgebra whose `sum(): float` etc. cannot be widened by a subclass,
+so it always behaves as scalarNumeric(true); `la.scalar(la.sum(x))` is the form that works on both.)
 
 Every operation itself is inherited from the driver-agnostic LinearAlgebra mirror: the shape algebra is the same,
 and the driver objects (CudaBlas / CudaMath) take device buffers positionally exactly as the host-facing ones do --

@@ -4,50 +4,17 @@ There is no PHP interpreter in this image, so the shim ca
 catch what a parser and the FFI loader would catch first: unbalanced delimiters, an FFI call whose symbol the header
 does not declare, and an FFI call whose argument count differs from the C prototype in include/rindow_b200.h.
 """
+import json
 import pathlib
 import re
 
 import pytest
 
+from php_signatures import class_signatures, strip_php
+
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 PHP_FILES = sorted((ROOT / "php").rglob("*.php"))
 HEADER = (ROOT / "include" / "rindow_b200.h").read_text()
-
-
-def strip_php(src: str) -> str:
-    """PHP source with comments removed and string literals emptied (delimiters kept)."""
-    out = []
-    i, n = 0, len(src)
-    while i < n:
-        c = src[i]
-        two = src[i:i + 2]
-        if two == "//" or c == "#" and src[i:i + 2] != "#[":
-            j = src.find("\n", i)
-            i = n if j < 0 else j
-        elif two == "/*":
-            j = src.find("*/", i + 2)
-            i = n if j < 0 else j + 2
-        elif src[i:i + 3] == "<<<":
-            m = re.match(r"<<<\s*(['\"]?)(\w+)\1\n", src[i:])
-            if not m:
-                out.append(c)
-                i += 1
-                continue
-            end = re.search(r"\n\s*" + m.group(2) + r"\b", src[i + m.end() - 1:])
-            assert end, "unterminated heredoc"
-            out.append("''")
-            i = i + m.end() - 1 + end.end()
-        elif c in "'\"":
-            j = i + 1
-            while j < n and src[j] != c:
-                j += 2 if src[j] == "\\" else 1
-            assert j < n, "unterminated string literal"
-            out.append(c + c)
-            i = j + 1
-        else:
-            out.append(c)
-            i += 1
-    return "".join(out)
 
 
 def c_prototypes() -> dict:
@@ -154,3 +121,177 @@ def test_php_classes_match_their_files():
         assert m, f"{path.name}: no class"
         assert m.group(1) == path.stem, f"{path.name}: declares {m.group(1)}"
         assert re.search(r"^\s*namespace\s+[\w\\]+\s*;", code, flags=re.M), f"{path.name}: no namespace"
+
+
+def _shim_classes():
+    """(file, class, parent) of every shim class that extends something."""
+    out = []
+    for path in PHP_FILES:
+        code = strip_php(path.read_text())
+        for m in re.finditer(r"\bclass\s+(\w+)\s+extends\s+([\w\\\\]+)", code):
+            out.append((path, m.group(1), m.group(2).split("\\")[-1]))
+    return out
+
+
+def _type_accepts(child: str, parent: str) -> bool:
+    """Parameter types are contravariant: the override must accept everything the parent does."""
+    if child == "" or child == "mixed" or child == parent:
+        return True
+    if parent == "":
+        return False
+    return set(parent.split("|")) <= set(child.split("|"))
+
+
+def test_overrides_are_compatible_with_the_reference_parents():
+    """PHP verifies an overriding method against its parent when the class is loaded (arity, optional parameters,
+    static-ness, visibility, parameter and return types); the reference callers also pass every argument by position
+    (src/LinearAlgebra.php:2006 etc.).  The parents' signatures are the fixture tests/golden/reference_signatures.json
+    (tools/extract_reference_signatures.py)."""
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    own = {}
+    for path in PHP_FILES:
+        code = path.read_text()
+        for m in re.finditer(r"\bclass\s+(\w+)", strip_php(code)):
+            own[m.group(1)] = class_signatures(code, m.group(1))
+    rank = {"private": 0, "protected": 1, "public": 2}
+    checked = 0
+    for path, cls, parent in _shim_classes():
+        parents = ref[parent]["methods"] if parent in ref else own.get(parent)
+        if parents is None:
+            continue
+        # walk further up when the parent is itself a shim class or a reference class with a known parent
+        chain = [parents]
+        if parent == "NDArrayCL" or parent == "LinearAlgebraCL":
+            pass
+        for name, sig in own[cls].items():
+            if name == "__construct":
+                continue
+            for table in chain:
+                if name not in table:
+                    continue
+                psig = table[name]
+                if psig["visibility"] == "private":
+                    continue
+                where = "%s::%s overrides %s::%s" % (cls, name, parent, name)
+                assert sig["static"] == psig["static"], where + ": static differs"
+                assert rank[sig["visibility"]] >= rank[psig["visibility"]], where + ": narrower visibility"
+                assert len(sig["params"]) >= len(psig["params"]), where + ": fewer parameters"
+                for i, pp in enumerate(psig["params"]):
+                    cp = sig["params"][i]
+                    assert cp["by_ref"] == pp["by_ref"], "%s: parameter %d by-reference differs" % (where, i + 1)
+                    assert cp["variadic"] == pp["variadic"], "%s: parameter %d variadic differs" % (where, i + 1)
+                    assert _type_accepts(cp["type"], pp["type"]), \
+                        "%s: parameter %d (%s) takes %s, parent takes %s" % (where, i + 1, cp["name"], cp["type"], pp["type"])
+                    if pp["default"]:
+                        assert cp["default"], "%s: parameter %d (%s) must stay optional" % (where, i + 1, cp["name"])
+                for cp in sig["params"][len(psig["params"]):]:
+                    assert cp["default"] or cp["variadic"], "%s: extra parameter $%s must be optional" % (where, cp["name"])
+                if psig["returns"]:
+                    assert sig["returns"], where + ": return type dropped"
+                    child_r, parent_r = set(sig["returns"].split("|")), set(psig["returns"].split("|"))
+                    ok = child_r <= parent_r or "mixed" in parent_r or (child_r - {"static", "self", cls}) <= parent_r | {parent}
+                    assert ok, "%s: returns %s, parent returns %s" % (where, sig["returns"], psig["returns"])
+                checked += 1
+    assert checked >= 80, checked
+
+
+def test_hot_path_methods_keep_the_reference_parameter_order():
+    """The reference calls its drivers positionally; the overriding hot-path methods keep the parent's parameter
+    names in the parent's order (names are not checked by PHP, but a swapped pair of ints would pass every type check)."""
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    math = class_signatures((ROOT / "php" / "MatlibCuda" / "CudaMath.php").read_text(), "CudaMath")
+    blas = class_signatures((ROOT / "php" / "MatlibCuda" / "CudaBlas.php").read_text(), "CudaBlas")
+    for own, parent, names in ((math, "PhpMath", ("add", "multiply", "reduceSum", "reduceMax", "reduceArgMax", "softmax",
+                                                  "im2col2d")),
+                               (blas, "PhpBlas", ("gemm", "gemv", "axpy", "copy", "scal"))):
+        for name in names:
+            assert name in own, name
+            want = [p["name"].lower() for p in ref[parent]["methods"][name]["params"]]
+            got = [p["name"].lower() for p in own[name]["params"]][:len(want)]
+            assert got == want, "%s: %s vs reference %s" % (name, got, want)
+
+
+# interfaces of interop-phpobjects/polite-math the reference itself imports (grep `use Interop\\Polite` over src/)
+POLITE = {"NDArray", "Buffer", "LinearBuffer", "DeviceBuffer", "BLAS", "OpenCL"}
+PHP_BUILTIN = {"FFI", "ArrayAccess", "Countable", "IteratorAggregate", "Traversable", "ArrayIterator", "ArrayObject",
+               "InvalidArgumentException", "RuntimeException", "LogicException", "OutOfRangeException", "TypeError",
+               "DomainException", "Throwable", "Exception", "stdClass", "Serializable"}
+
+
+def _declared_shim_classes():
+    out = {}
+    for path in PHP_FILES:
+        code = strip_php(path.read_text())
+        ns = re.search(r"^\s*namespace\s+([\w\\]+)\s*;", code, flags=re.M).group(1)
+        for m in re.finditer(r"^\s*(?:final\s+|abstract\s+)?(?:class|interface|trait)\s+(\w+)", code, flags=re.M):
+            out[ns + "\\" + m.group(1)] = path
+    return out
+
+
+def test_every_use_line_resolves():
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    known = set(ref["__classes__"]) | set(_declared_shim_classes())
+    for path in PHP_FILES:
+        code = strip_php(path.read_text())
+        for m in re.finditer(r"^use\s+(function\s+)?([\w\\]+)(?:\s+as\s+\w+)?\s*;", code, flags=re.M):
+            name = m.group(2).lstrip("\\")
+            if m.group(1):
+                assert name in ("Rindow\\Math\\Matrix\\R", "Rindow\\Math\\Matrix\\C"), f"{path.name}: use function {name}"
+            elif name.startswith("Interop\\Polite\\Math\\Matrix\\"):
+                assert name.split("\\")[-1] in POLITE, f"{path.name}: {name} is not a polite-math interface the reference uses"
+            elif name.startswith("PHPUnit\\") or name.startswith("RindowTest\\"):
+                assert "tests" in path.parts, f"{path.name}: test-only import {name}"
+            elif "\\" not in name:
+                assert name in PHP_BUILTIN, f"{path.name}: unknown global class {name}"
+            else:
+                assert name in known, f"{path.name}: use {name} resolves to nothing in the reference or the shim"
+
+
+def test_this_and_parent_calls_resolve_to_a_method():
+    """`$this->name(` / `parent::name(` / `self::name(` / `static::name(` must name a method of the class, of a shim
+    parent, or of the reference parent (fixture) -- what PHP reports as 'Call to undefined method' at run time."""
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    own, parent_of = {}, {}
+    for path in PHP_FILES:
+        src = path.read_text()
+        code = strip_php(src)
+        for m in re.finditer(r"\bclass\s+(\w+)(?:\s+extends\s+([\w\\]+))?", code):
+            own[m.group(1)] = (class_signatures(src, m.group(1)), path)
+            parent_of[m.group(1)] = m.group(2).split("\\")[-1] if m.group(2) else None
+
+    def methods_of(cls):
+        names, open_ended = set(), False
+        while cls:
+            if cls in own:
+                names |= set(own[cls][0])
+                cls = parent_of[cls]
+            elif cls in ref:
+                names |= set(ref[cls]["methods"])
+                # the reference parents whose own parents / traits are outside the fixture
+                open_ended = cls in ("NDArrayCL", "AbstractMatlibService", "PhpBlas", "PhpMath", "LinearAlgebra", "MatrixOperator")
+                cls = None
+            else:
+                open_ended = True           # PHPUnit TestCase, reference test suites
+                cls = None
+        return names, open_ended
+
+    # traits the reference parents pull in (src/Drivers/MatlibPHP/Utils.php, src/ComplexUtils.php)
+    trait_methods = {"assertShapeParameter", "assertVectorBufferSpec", "assertMatrixBufferSpec", "cbuild", "crebuild",
+                     "cisobject", "cistype", "cadd", "csub", "cmul", "cdiv", "csqrt", "cabs", "ciszero", "cisone",
+                     "cconj", "cobjecttype", "transToCode"}
+    checked = 0
+    for cls, (sigs, path) in own.items():
+        names, open_ended = methods_of(cls)
+        body = strip_php(path.read_text())
+        for m in re.finditer(r"(\$this->|parent::|self::|static::)(\w+)\s*\(", body):
+            name = m.group(2)
+            if name in names or name in trait_methods:
+                checked += 1
+                continue
+            if m.group(1) == "$this->" and re.search(r"\$" + name + r"\b", body):
+                continue                     # a callable property
+            line = body.count("\n", 0, m.start()) + 1
+            if open_ended and "tests" in path.parts:
+                continue                     # PHPUnit assertions and helpers of the reference suites
+            assert not True, f"{path.name}:{line}: {m.group(1)}{name}() is not a method of {cls} or its parents"
+    assert checked > 100, checked

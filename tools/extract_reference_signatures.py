@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Writes tests/golden/reference_signatures.json: the public / protected method signatures of the reference classes
+the PHP shim extends (PHP checks an override against its parent when the class is loaded, so a mismatch is a fatal
+error the moment the shim is used).  Run in the build container, where /root/reference exists; the fixture travels.
+
+    python tools/extract_reference_signatures.py
+"""
+import json
+import pathlib
+import re
+import sys
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1] / "tests"))
+from php_signatures import class_signatures, strip_php  # noqa: E402
+
+REF = pathlib.Path("/root/reference/src")
+SOURCES = {
+    "PhpMath": "Drivers/MatlibPHP/PhpMath.php",
+    "PhpBlas": "Drivers/MatlibPHP/PhpBlas.php",
+    "LinearAlgebra": "LinearAlgebra.php",
+    "LinearAlgebraCL": "LinearAlgebraCL.php",
+    "MatrixOperator": "MatrixOperator.php",
+    "NDArrayCL": "NDArrayCL.php",
+    "NDArrayPhp": "NDArrayPhp.php",
+    "AbstractMatlibService": "Drivers/AbstractMatlibService.php",
+}
+
+
+def main():
+    out = {}
+    for cls, rel in SOURCES.items():
+        sigs = class_signatures((REF / rel).read_text(), cls)
+        out[cls] = {"file": "src/" + rel, "methods": sigs}
+    # every class / interface / trait the reference declares under src/ (fully qualified), for the shim's `use` lines
+    classes = []
+    for f in sorted(REF.rglob("*.php")):
+        code = strip_php(f.read_text())
+        ns = re.search(r"^\s*namespace\s+([\w\\]+)\s*;", code, flags=re.M)
+        for m in re.finditer(r"^\s*(?:final\s+|abstract\s+)?(?:class|interface|trait)\s+(\w+)", code, flags=re.M):
+            classes.append((ns.group(1) + "\\" if ns else "") + m.group(1))
+    out["__classes__"] = sorted(set(classes))
+    dst = pathlib.Path(__file__).resolve().parents[1] / "tests" / "golden" / "reference_signatures.json"
+    dst.write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
+    print("wrote", dst, {k: len(v["methods"]) for k, v in out.items() if k != "__classes__"}, len(out["__classes__"]), "classes")
+
+
+if __name__ == "__main__":
+    main()
