@@ -184,7 +184,7 @@ class CudaBlas extends PhpBlas
     {
         $this->assertShapeParameter('n',$n);
         $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
-        $out = \FFI::new($ctype);
+        $out = CudaFFI::lib()->new($ctype);
         CudaFFI::check(CudaFFI::lib()->$fn($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,\FFI::addr($out)));
         return $out->cdata;
     }
@@ -219,7 +219,7 @@ class CudaBlas extends PhpBlas
         $this->assertShapeParameter('n',$n);
         $this->assertVectorBufferSpec('X', $X, $n, $offsetX, $incX);
         $this->assertVectorBufferSpec('Y', $Y, $n, $offsetY, $incY);
-        $out = \FFI::new('double');
+        $out = CudaFFI::lib()->new('double');
         CudaFFI::check(CudaFFI::lib()->rb200_dot($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,
             $Y->devicePtr(),$offsetY,$incY,\FFI::addr($out)));
         return $out->cdata;

@@ -3,6 +3,7 @@ namespace Rindow\Math\Matrix\Drivers\MatlibCuda;
 
 use Interop\Polite\Math\Matrix\LinearBuffer;
 use Interop\Polite\Math\Matrix\NDArray;
+use Rindow\Math\Matrix\Complex;
 use FFI;
 use InvalidArgumentException;
 use RuntimeException;
@@ -179,7 +180,7 @@ class CudaBuffer implements LinearBuffer
         }
         if ($this->isComplexDtype()) {
             $m = $this->mirror();
-            return \Rindow\Math\Matrix\C($m[2*$offset], i:$m[2*$offset+1]);     // src/C.php
+            return new Complex((float)$m[2*$offset], (float)$m[2*$offset+1]);      // what C() builds (src/C.php:6-13)
         }
         $v = $this->mirror()[$offset];
         return ($this->dtype == NDArray::bool) ? ($v ? true : false) : $v;

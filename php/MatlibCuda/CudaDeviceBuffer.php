@@ -3,6 +3,8 @@ namespace Rindow\Math\Matrix\Drivers\MatlibCuda;
 
 use Interop\Polite\Math\Matrix\DeviceBuffer;
 use Interop\Polite\Math\Matrix\LinearBuffer;
+use Interop\Polite\Math\Matrix\NDArray;
+use Rindow\Math\Matrix\Complex;
 use FFI;
 use InvalidArgumentException;
 use LogicException;
@@ -48,18 +50,40 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
     {
         if(!$this->offsetExists($offset)) { throw new RuntimeException('Index invalid or out of range'); }
         $ffi = CudaFFI::lib();
+        if($this->isComplexDtype()) {                // interleaved real / imag pair of the component type
+            $pair = $ffi->new($this->ctype.'[2]');
+            CudaFFI::check($ffi->rb200_buffer_d2h($pair, $this->dptr, $offset*$this->valueSize, $this->valueSize));
+            return new Complex((float)$pair[0], (float)$pair[1]);
+        }
         $one = $ffi->new($this->ctype);
         CudaFFI::check($ffi->rb200_buffer_d2h(FFI::addr($one), $this->dptr, $offset*$this->valueSize, $this->valueSize));
-        return $one->cdata;
+        return ($this->dtype == NDArray::bool) ? ($one->cdata ? true : false) : $one->cdata;
+    }
+
+    /** one element of this dtype on the host, ready to be passed as `const void*` */
+    protected function hostElement(mixed $value) : object
+    {
+        $ffi = CudaFFI::lib();
+        if($this->isComplexDtype()) {
+            if(!is_object($value) || !property_exists($value, 'real') || !property_exists($value, 'imag')) {
+                throw new InvalidArgumentException('Cannot convert to complex number.: '.gettype($value));
+            }
+            $pair = $ffi->new($this->ctype.'[2]');
+            $pair[0] = $value->real;
+            $pair[1] = $value->imag;
+            return $pair;
+        }
+        $one = $ffi->new($this->ctype.'[1]');
+        $one[0] = $value;
+        return $one;
     }
 
     public function offsetSet($offset, $value) : void
     {
         if(!$this->offsetExists($offset)) { throw new RuntimeException('Index invalid or out of range'); }
-        $ffi = CudaFFI::lib();
-        $one = $ffi->new($this->ctype);
-        $one->cdata = $value;
-        CudaFFI::check($ffi->rb200_buffer_h2d($this->dptr, $offset*$this->valueSize, FFI::addr($one), $this->valueSize));
+        CudaFFI::check(CudaFFI::lib()->rb200_buffer_h2d($this->dptr, $offset*$this->valueSize,
+            $this->hostElement($value), $this->valueSize));
+        $this->devDirty = true;
     }
 
     /** device -> host buffer (src/NDArrayCL.php:261-270).  A CudaBuffer partner receives the bytes on the device side. */
@@ -76,7 +100,7 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
             // an FFI-backed host buffer of another driver (rindow-math-buffer-ffi): raw address of element 0
             CudaFFI::check($ffi->rb200_buffer_d2h($hostBuffer->addr(0), $this->dptr, $offset, $size));
         } else {
-            $tmp = FFI::new('char['.$size.']');
+            $tmp = $ffi->new('char['.$size.']');
             CudaFFI::check($ffi->rb200_buffer_d2h($tmp, $this->dptr, $offset, $size));
             $hostBuffer->load(FFI::string($tmp, $size));       // PhpBuffer::load, hostoffset 0 only
         }
@@ -94,7 +118,7 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
         } else {
             $bytes = $hostBuffer->dump();
             $size = $size ?: min(strlen($bytes) - $hostoffset, $this->bytes() - $offset);
-            $tmp = FFI::new('char['.max(1,$size).']');
+            $tmp = $ffi->new('char['.max(1,$size).']');
             FFI::memcpy($tmp, substr($bytes, $hostoffset, $size), $size);
             CudaFFI::check($ffi->rb200_buffer_h2d($this->dptr, $offset, $tmp, $size));
         }
@@ -103,9 +127,12 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
     }
 
     /** DeviceBuffer::copy(queue, src, size, srcOffset, dstOffset, events, waitEvents) (src/NDArrayCL.php:416-441) */
-    public function copy(?object $queue, CudaBuffer $src, int $size=0, int $src_offset=0, int $dst_offset=0,
+    public function copy(?object $queue, object $src, int $size=0, int $src_offset=0, int $dst_offset=0,
         ?object $events=null, ?object $waitEvents=null) : void
     {
+        if(!($src instanceof CudaBuffer)) {
+            throw new InvalidArgumentException('copy source must be a buffer of this driver: '.get_class($src));
+        }
         if($waitEvents!==null) { $waitEvents->wait(); }
         $size = $size ?: (count($src)*$src->value_size() - $src_offset);
         CudaFFI::check(CudaFFI::lib()->rb200_buffer_d2d($this->dptr, $dst_offset, $src->devicePtr(), $src_offset, $size));
@@ -118,12 +145,9 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
         int $pattern_offset=0, ?object $events=null, ?object $waitEvents=null) : void
     {
         if($waitEvents!==null) { $waitEvents->wait(); }
-        $ffi = CudaFFI::lib();
-        $one = $ffi->new($this->ctype);
-        $one->cdata = $pattern[$pattern_offset];
         $size = $size ?: ($this->bytes() - $offset);
-        CudaFFI::check($ffi->rb200_buffer_fill($this->abiDtype, $this->dptr, intdiv($offset,$this->valueSize),
-            intdiv($size,$this->valueSize), FFI::addr($one)));
+        CudaFFI::check(CudaFFI::lib()->rb200_buffer_fill($this->abiDtype, $this->dptr, intdiv($offset,$this->valueSize),
+            intdiv($size,$this->valueSize), $this->hostElement($pattern[$pattern_offset])));
         $this->devDirty = true;
         if($events!==null) { $events->record(); }
     }
@@ -131,17 +155,19 @@ class CudaDeviceBuffer extends CudaBuffer implements DeviceBuffer
     public function dump() : string
     {
         $n = $this->bytes();
-        $tmp = FFI::new('char['.max(1,$n).']');
-        CudaFFI::check(CudaFFI::lib()->rb200_buffer_d2h($tmp, $this->dptr, 0, $n));
+        $ffi = CudaFFI::lib();
+        $tmp = $ffi->new('char['.max(1,$n).']');
+        CudaFFI::check($ffi->rb200_buffer_d2h($tmp, $this->dptr, 0, $n));
         return FFI::string($tmp, $n);
     }
 
     public function load(string $string) : void
     {
         if(strlen($string) > $this->bytes()) { throw new RuntimeException('Unpack error'); }
-        $tmp = FFI::new('char['.max(1,strlen($string)).']');
+        $ffi = CudaFFI::lib();
+        $tmp = $ffi->new('char['.max(1,strlen($string)).']');
         FFI::memcpy($tmp, $string, strlen($string));
-        CudaFFI::check(CudaFFI::lib()->rb200_buffer_h2d($this->dptr, 0, $tmp, strlen($string)));
+        CudaFFI::check($ffi->rb200_buffer_h2d($this->dptr, 0, $tmp, strlen($string)));
         $this->devDirty = true;
     }
 }

@@ -159,8 +159,13 @@ class CudaFFI
     {
         if (self::$ffi === null) {
             $path = getenv('RINDOW_B200_LIB') ?: 'librindow_b200.so';
-            self::$ffi = FFI::cdef(self::CDEF, $path);
-            self::check(self::$ffi->rb200_init((int)(getenv('RINDOW_B200_DEVICE') ?: 0)));
+            $ffi = FFI::cdef(self::CDEF, $path);
+            $status = $ffi->rb200_init((int)(getenv('RINDOW_B200_DEVICE') ?: 0));
+            if ($status != 0) {             // no B200 / wrong architecture: stay unavailable on every later call too
+                throw new RuntimeException(
+                    'librindow_b200 status '.$status.': '.FFI::string($ffi->rb200_last_error()));
+            }
+            self::$ffi = $ffi;
         }
         return self::$ffi;
     }

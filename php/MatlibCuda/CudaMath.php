@@ -151,7 +151,7 @@ class CudaMath extends PhpMath
         if (!$this->anyOnDevice($A,$X,$B)) {
             parent::gathernd($reverse,$addMode,$m,$n,$k,$indexDepth,$paramShape,$A,$offsetA,$X,$offsetX,$B,$offsetB); return;
         }
-        $shape = \FFI::new("int64_t[$indexDepth]");
+        $shape = CudaFFI::lib()->new("int64_t[$indexDepth]");
         $paramSize = 1;
         for ($h=0;$h<$indexDepth;$h++) { $shape[$h] = $paramShape[$h]; $paramSize *= $paramShape[$h]; }
         if ($m*$n*$indexDepth > count($X)) {
@@ -180,7 +180,7 @@ class CudaMath extends PhpMath
         if (!$this->anyOnDevice($A,$B,$C) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64]) || $depth>16) {
             parent::einsum($sizeOfIndices,$A,$offsetA,$ldA,$B,$offsetB,$ldB,$C,$offsetC,$ndimC); return;
         }
-        $s = \FFI::new("int64_t[$depth]"); $la = \FFI::new("int64_t[$depth]"); $lb = \FFI::new("int64_t[$depth]");
+        $s = CudaFFI::lib()->new("int64_t[$depth]"); $la = CudaFFI::lib()->new("int64_t[$depth]"); $lb = CudaFFI::lib()->new("int64_t[$depth]");
         for ($h=0;$h<$depth;$h++) { $s[$h] = $sizeOfIndices[$h]; $la[$h] = $ldA[$h]; $lb[$h] = $ldB[$h]; }
         $this->einsumDevice($depth,$ndimC,$s,$la,$lb,$A,$offsetA,$B,$offsetB,$C,$offsetC);
     }
@@ -198,7 +198,7 @@ class CudaMath extends PhpMath
         if (count($C) <= $offsetC+$dim0*$dim1*$dim2*$dim3-1) {
             throw new InvalidArgumentException('Matrix specification too large for buffer C.');
         }
-        $s = \FFI::new("int64_t[5]"); $la = \FFI::new("int64_t[5]"); $lb = \FFI::new("int64_t[5]");
+        $s = CudaFFI::lib()->new("int64_t[5]"); $la = CudaFFI::lib()->new("int64_t[5]"); $lb = CudaFFI::lib()->new("int64_t[5]");
         foreach ([$dim0,$dim1,$dim2,$dim3,$dim4] as $h=>$v) { $s[$h] = $v; }
         foreach ([$ldA0,$ldA1,$ldA2,$ldA3,$ldA4] as $h=>$v) { $la[$h] = $v; }
         foreach ([$ldB0,$ldB1,$ldB2,$ldB3,$ldB4] as $h=>$v) { $lb[$h] = $v; }

@@ -275,6 +275,18 @@ def test_this_and_parent_calls_resolve_to_a_method():
                 cls = None
         return names, open_ended
 
+    def signature_of(cls, name):
+        while cls:
+            if cls in own:
+                if name in own[cls][0]:
+                    return own[cls][0][name]
+                cls = parent_of[cls]
+            elif cls in ref:
+                return ref[cls]["methods"].get(name)
+            else:
+                return None
+        return None
+
     # traits the reference parents pull in (src/Drivers/MatlibPHP/Utils.php, src/ComplexUtils.php)
     trait_methods = {"assertShapeParameter", "assertVectorBufferSpec", "assertMatrixBufferSpec", "cbuild", "crebuild",
                      "cisobject", "cistype", "cadd", "csub", "cmul", "cdiv", "csqrt", "cabs", "ciszero", "cisone",
@@ -287,6 +299,14 @@ def test_this_and_parent_calls_resolve_to_a_method():
             name = m.group(2)
             if name in names or name in trait_methods:
                 checked += 1
+                sig = signature_of(cls, name)
+                if sig is not None:
+                    got = call_arity(body, m.end() - 1)
+                    required = sum(1 for q in sig["params"] if not q["default"] and not q["variadic"])
+                    most = 10 ** 6 if any(q["variadic"] for q in sig["params"]) else len(sig["params"])
+                    line = body.count("\n", 0, m.start()) + 1
+                    assert required <= got <= most, \
+                        f"{path.name}:{line}: {m.group(1)}{name}() called with {got} arguments, takes {required}..{most}"
                 continue
             if m.group(1) == "$this->" and re.search(r"\$" + name + r"\b", body):
                 continue                     # a callable property
