@@ -438,8 +438,13 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
     // k > 1
     const bool vec = base_aligned && (k % V == 0);
     const int64_t kv = vec ? k / V : k;
+    // threads along k: 32 (512-byte row pieces per warp, 8 rows in flight per CTA).  RB200_REDUCE_COLS_TX = 64 / 128 /
+    // 256 widens the contiguous run a CTA reads per row; measured worse at axis 0 of [65536,1024] (0.82 -> 0.67 / 0.41 /
+    // 0.16 of HBM peak: fewer column blocks leave the final merge of the row segments to fewer CTAs).
+    static const int tx_max = [] { const char* e = getenv("RB200_REDUCE_COLS_TX"); const int v = e ? atoi(e) : 32;
+                                   return (v == 64 || v == 128 || v == 256) ? v : 32; }();
     int tx = 1;
-    while (tx < 32 && tx < kv) tx <<= 1;
+    while (tx < tx_max && tx < kv) tx <<= 1;
     const int ty = RD_THREADS / tx;
     const int64_t col_blocks = rb_ceil_div(kv, tx);
     int64_t S = 1;
