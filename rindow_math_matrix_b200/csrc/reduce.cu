@@ -438,13 +438,18 @@ int reduce_launch(int64_t m, int64_t n, int64_t k, const void* Av, int64_t offA,
     // k > 1
     const bool vec = base_aligned && (k % V == 0);
     const int64_t kv = vec ? k / V : k;
-    // threads along k: 32 (512-byte row pieces per warp, 8 rows in flight per CTA).  RB200_REDUCE_COLS_TX = 64 / 128 /
-    // 256 widens the contiguous run a CTA reads per row; measured worse at axis 0 of [65536,1024] (0.82 -> 0.67 / 0.41 /
-    // 0.16 of HBM peak: fewer column blocks leave the final merge of the row segments to fewer CTAs).
-    static const int tx_max = [] { const char* e = getenv("RB200_REDUCE_COLS_TX"); const int v = e ? atoi(e) : 32;
-                                   return (v == 64 || v == 128 || v == 256) ? v : 32; }();
-    int tx = 1;
-    while (tx < tx_max && tx < kv) tx <<= 1;
+    // threads along k.  Unsplit (enough (row, column block) units to fill the SMs): 32, i.e. 512-byte row pieces per
+    // warp.  When the reduced axis has to be split into row segments, the last CTA of each column block merges the
+    // segments' partials, and that tail is on the critical path (ncu at axis 0 of [65536,1024]: SMs active 80 k of
+    // 101 k elapsed cycles, the merging SMs 94 k): 8 threads along k give four times as many, four times smaller
+    // merges -- 0.82 -> 0.87 of HBM peak there; 16: 0.83; 64 / 128 / 256: 0.67 / 0.41 / 0.16
+    // (profiles/hbm_straggler_experiments_r02.txt).  RB200_REDUCE_COLS_TX forces a width.
+    static const int tx_env = [] { const char* e = getenv("RB200_REDUCE_COLS_TX"); const int v = e ? atoi(e) : 0;
+                                   return (v == 8 || v == 16 || v == 32 || v == 64 || v == 128 || v == 256) ? v : 0; }();
+    auto threads_along_k = [&](int cap) { int t = 1; while (t < cap && t < kv) t <<= 1; return t; };
+    int tx = threads_along_k(32);
+    if (tx_env) tx = threads_along_k(tx_env);
+    else if (m * rb_ceil_div(kv, (int64_t)tx) < target_ctas) tx = threads_along_k(8);
     const int ty = RD_THREADS / tx;
     const int64_t col_blocks = rb_ceil_div(kv, tx);
     int64_t S = 1;
