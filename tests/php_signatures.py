@@ -97,7 +97,13 @@ def class_signatures(src: str, cls: str) -> dict:
     """method -> {visibility, static, params: [{type, name, default, variadic, by_ref}], returns}"""
     body = class_body(strip_php(src), cls)
     sigs = {}
+    depth_at, d = [], 0                  # brace depth before each character: methods of the class sit at depth 0
+    for ch in body:
+        depth_at.append(d)
+        d += (ch == "{") - (ch == "}")
     for m in re.finditer(r"((?:\b(?:public|protected|private|static|final|abstract)\s+)*)function\s+&?\s*(\w+)\s*\(", body):
+        if depth_at[m.start()] != 0:
+            continue                     # a closure or a method of an anonymous class inside a method body
         mods = m.group(1).split()
         vis = next((v for v in mods if v in ("public", "protected", "private")), "public")
         close = _matching_paren(body, m.end() - 1)

@@ -315,3 +315,69 @@ def test_this_and_parent_calls_resolve_to_a_method():
                 continue                     # PHPUnit assertions and helpers of the reference suites
             assert not True, f"{path.name}:{line}: {m.group(1)}{name}() is not a method of {cls} or its parents"
     assert checked > 100, checked
+
+
+def _call_args(code: str, open_paren: int):
+    """Top-level argument strings of the call whose '(' is at open_paren."""
+    depth, cur, args = 0, [], []
+    for i in range(open_paren, len(code)):
+        c = code[i]
+        if c in "([{":
+            depth += 1
+            if depth == 1:
+                continue
+        elif c in ")]}":
+            depth -= 1
+            if depth == 0:
+                tail = "".join(cur).strip()
+                if tail:
+                    args.append(tail)
+                return args
+        if c == "," and depth == 1:
+            args.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(c)
+    raise AssertionError("unterminated call")
+
+
+def test_named_arguments_of_constructor_calls_exist():
+    """`new NDArrayPhp($v, dtype:$d, service:$s)`: a misspelt named argument is an Error at run time."""
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    ctor = {cls: v["methods"].get("__construct") for cls, v in ref.items() if cls != "__classes__"}
+    parent_of = {}
+    for path in PHP_FILES:
+        src = path.read_text()
+        code = strip_php(src)
+        for m in re.finditer(r"\bclass\s+(\w+)(?:\s+extends\s+([\w\\]+))?", code):
+            sigs = class_signatures(src, m.group(1))
+            parent_of[m.group(1)] = m.group(2).split("\\")[-1] if m.group(2) else None
+            ctor[m.group(1)] = sigs.get("__construct")
+    for cls in list(parent_of):                  # inherited constructors (NDArrayCuda -> NDArrayCL)
+        c = cls
+        while ctor.get(cls) is None and parent_of.get(c):
+            c = parent_of[c]
+            if ctor.get(c) is not None:
+                ctor[cls] = ctor[c]
+    checked = 0
+    for path in PHP_FILES:
+        code = strip_php(path.read_text())
+        for m in re.finditer(r"\bnew\s+\\?([\w\\]+)\s*\(", code):
+            cls = m.group(1).split("\\")[-1]
+            sig = ctor.get(cls)
+            if sig is None:
+                continue
+            names = [p["name"] for p in sig["params"]]
+            line = code.count("\n", 0, m.start()) + 1
+            args = _call_args(code, m.end() - 1)
+            positional = 0
+            for a in args:
+                nm = re.match(r"^(\w+)\s*:(?!:)", a)
+                if nm:
+                    assert nm.group(1) in names, f"{path.name}:{line}: new {cls}(... {nm.group(1)}: ...) -- parameters are {names}"
+                    assert names.index(nm.group(1)) >= positional, f"{path.name}:{line}: {nm.group(1)} given twice"
+                    checked += 1
+                else:
+                    positional += 1
+            assert positional <= len(names) or any(p["variadic"] for p in sig["params"]), f"{path.name}:{line}: too many arguments to new {cls}"
+    assert checked >= 10, checked
