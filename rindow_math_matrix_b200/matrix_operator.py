@@ -26,6 +26,7 @@ class MatrixOperator:
         self._service = service
         self._la = None
         self.defaultFloatType = dtypes.float32
+        self.defaultIntType = dtypes.int32                                # MatrixOperator.php:53
 
     def service(self):
         return self._service
@@ -58,8 +59,18 @@ class MatrixOperator:
 
     def getBlas(self, dtype: int):                                       # MatrixOperator.php:225-231
         if self.isIntType(dtype):
-            return self._service.blas(Service.LV_BASIC)
+            return self._basic_or_device("blas")
         return self._service.blas()
+
+    def _basic_or_device(self, kind: str):
+        """Integer arrays go to the LV_BASIC (pure-PHP) driver in the reference because OpenBLAS-class drivers have no
+        integer kernels.  This package ships no host driver (service.py): where the service has no LV_BASIC slot the
+        device driver is used -- its level-1 / scalar entry points take every real dtype."""
+        getter = getattr(self._service, kind)
+        try:
+            return getter(Service.LV_BASIC)
+        except LogicException:
+            return getter()
 
     def array(self, array, dtype: int | None = None) -> NDArray:
         if dtype is None:
@@ -150,3 +161,133 @@ class MatrixOperator:
                           A.buffer(), A.offset(), K, B.buffer(), B.offset() + N * K * l, N, beta,
                           C.buffer(), C.offset() + N * l, L * N)
         return C
+
+    # ---- reductions along an axis (MatrixOperator.php:824-1023) ----------------------------------------------------
+    # The reference walks the remaining axes on the host and asks the driver for ONE scalar per output element
+    # (walkAxis :824-857: `$YY[$posY] = $math->sum($N,$XX,$offX+$bufPos,$incX)`), i.e. prod(shape)/shape[axis] driver
+    # calls.  Viewed as A[m, n, k] with n = shape[axis] that is exactly the layout of the driver's reduce entry points
+    # (PhpMath.php:1552-1643), so for float arrays sum / mean / max / argMax / min / argMin run as one to three kernels:
+    #   sum     reduceSum                         mean    reduceSum + scal(1/n)
+    #   argMax  reduceArgMax (first strict maximum, the math_imax rule, PhpMath.php:114-130)
+    #   max     reduceArgMax, then reduceGather of X at those positions (`$XX[... + $pos*$incX]`, :911-916) -- not
+    #           reduceMax, whose NaN rule is the sticky one of the accelerated drivers
+    #   argMin / min   the same on -X (math_imin is math_imax mirrored: first strict minimum)
+    # Everything else (integer and bool arrays, the |x| family asum / amax / amin / argAmax / argAmin, axis=None) keeps
+    # the reference's walk, one driver call per output element.
+
+    def setDefaultIntType(self, dtype: int) -> None:                      # :252-255
+        self.defaultIntType = dtype
+
+    def setDefaultFloatType(self, dtype: int) -> None:                    # :257-260
+        self.defaultFloatType = dtype
+
+    def getMath(self, dtype: int):                                        # :232-238
+        if self.isIntType(dtype):
+            return self._basic_or_device("math")
+        return self._service.math()
+
+    @staticmethod
+    def _axis_layout(X: NDArray, axis: int):
+        shape = X.shape()
+        if axis < 0 or axis >= len(shape):                                # :838-840
+            raise InvalidArgumentException("Invalid axis: axis=%d,shape=[%s]" % (axis, ",".join(map(str, shape))))
+        m = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
+        k = int(np.prod(shape[axis + 1:], dtype=np.int64)) if axis + 1 < len(shape) else 1
+        return m, shape[axis], k, shape[:axis] + shape[axis + 1:]
+
+    def walkAxis(self, func, X: NDArray, axis=None, dtype=None):          # :824-857
+        XX, offX = X.buffer(), X.offset()
+        if axis is None:
+            return func(X.size(), XX, offX, 0, 1)
+        m, n, k, outShape = self._axis_layout(X, axis)
+        Y = NDArray(None, dtype=X.dtype() if dtype is None else dtype, shape=outShape, service=self._service)
+        YY = Y.buffer()
+        pos = 0
+        for outer in range(m):                                            # createMatrixBufferIterator order (:727-822)
+            for inner in range(k):
+                YY[pos] = func(n, XX, offX, outer * n * k + inner, k)
+                pos += 1
+        return Y
+
+    def _on_device_axis(self, X: NDArray, axis) -> bool:
+        return axis is not None and X.dtype() in dtypes.FLOAT_TYPES
+
+    def _arg_extreme(self, X: NDArray, axis: int, smallest: bool, dtype=None) -> NDArray:
+        la = self.la()
+        self._axis_layout(X, axis)                                        # the reference's axis check and message
+        src = la.scal(-1.0, la.copy(X)) if smallest else X
+        return la.reduceArgMax(src, axis=axis, dtype=dtype)
+
+    def sum(self, X: NDArray, axis=None):                                 # :873-892
+        if self._on_device_axis(X, axis):
+            self._axis_layout(X, axis)
+            return self.la().reduceSum(X, axis=axis)
+        if X.dtype() == dtypes.bool_:
+            def func(N, XX, offX, bufPos, incX):                          # the reference's own loop bounds (:877-883)
+                return sum(1 for i in range(0, N, incX) if XX[offX + bufPos + i])
+        else:
+            math = self.getMath(X.dtype())
+
+            def func(N, XX, offX, bufPos, incX):
+                return math.sum(N, XX, offX + bufPos, incX)
+        return self.walkAxis(func, X, axis)
+
+    def mean(self, X: NDArray, axis=None):                                # :1014-1022
+        if self._on_device_axis(X, axis):
+            _, n, _, _ = self._axis_layout(X, axis)
+            la = self.la()
+            return la.scal(1.0 / n, la.reduceSum(X, axis=axis))
+        math = self.getMath(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: math.sum(N, XX, offX + bufPos, incX) / N, X, axis)
+
+    def asum(self, X: NDArray, axis=None):                                # :894-901
+        blas = self.getBlas(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: blas.asum(N, XX, offX + bufPos, incX), X, axis)
+
+    def max(self, X: NDArray, axis=None):                                 # :903-912
+        if self._on_device_axis(X, axis):
+            return self.la().gather(X, self._arg_extreme(X, axis, False), axis=axis)
+        math = self.getMath(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX:
+                             XX[offX + bufPos + math.imax(N, XX, offX + bufPos, incX) * incX], X, axis)
+
+    def argMax(self, X: NDArray, axis=None):                              # :914-923
+        if self._on_device_axis(X, axis):
+            return self._arg_extreme(X, axis, False, self.defaultIntType)
+        math = self.getMath(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: math.imax(N, XX, offX + bufPos, incX), X, axis,
+                             self.defaultIntType)
+
+    def min(self, X: NDArray, axis=None):                                 # :950-959
+        if self._on_device_axis(X, axis):
+            return self.la().gather(X, self._arg_extreme(X, axis, True), axis=axis)
+        math = self.getMath(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX:
+                             XX[offX + bufPos + math.imin(N, XX, offX + bufPos, incX) * incX], X, axis)
+
+    def argMin(self, X: NDArray, axis=None):                              # :961-970
+        if self._on_device_axis(X, axis):
+            return self._arg_extreme(X, axis, True, self.defaultIntType)
+        math = self.getMath(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: math.imin(N, XX, offX + bufPos, incX), X, axis,
+                             self.defaultIntType)
+
+    def amax(self, X: NDArray, axis=None):                                # :925-934
+        blas = self.getBlas(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX:
+                             XX[offX + bufPos + blas.iamax(N, XX, offX + bufPos, incX) * incX], X, axis)
+
+    def argAmax(self, X: NDArray, axis=None):                             # :936-945
+        blas = self.getBlas(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: blas.iamax(N, XX, offX + bufPos, incX), X, axis,
+                             self.defaultIntType)
+
+    def amin(self, X: NDArray, axis=None):                                # :972-990 (hasIamin() is true on this driver)
+        blas = self.getBlas(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX:
+                             XX[offX + bufPos + blas.iamin(N, XX, offX + bufPos, incX) * incX], X, axis)
+
+    def argAmin(self, X: NDArray, axis=None):                             # :992-1012
+        blas = self.getBlas(X.dtype())
+        return self.walkAxis(lambda N, XX, offX, bufPos, incX: blas.iamin(N, XX, offX + bufPos, incX), X, axis,
+                             self.defaultIntType)

@@ -159,3 +159,33 @@ def test_conv2d_composition_over_any_driver(oracle_service):
     assert np.array_equal(out.to_numpy(), ref)
     with pytest.raises(rb.InvalidArgumentException, match="Unmatch channels"):
         la.conv2d(la.array(img), la.array(W[:, :, :2, :]))
+
+
+def test_driver_mirrors_keep_the_reference_parameter_lists():
+    """CudaMath / CudaBlas take the reference drivers' arguments by position (src/LinearAlgebra.php passes them that
+    way): every public method that exists in both has the same parameter names in the same order.  The reference
+    side is the fixture tests/golden/reference_signatures.json (tools/extract_reference_signatures.py)."""
+    import inspect
+    import json
+    import os
+
+    from rindow_math_matrix_b200.cuda_blas import CudaBlas
+    from rindow_math_matrix_b200.cuda_math import CudaMath
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_signatures.json")) as f:
+        ref = json.load(f)
+    compared = 0
+    for cls, parent in ((CudaMath, "PhpMath"), (CudaBlas, "PhpBlas")):
+        for name, sig in ref[parent]["methods"].items():
+            fn = getattr(cls, name, None)
+            if sig["visibility"] != "public" or name.startswith("__") or fn is None or not callable(fn):
+                continue
+            want = [p["name"].lower() for p in sig["params"]]
+            got = [p.name.rstrip("_").lower() for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+            assert got[:len(want)] == want, "%s.%s: %s vs reference %s" % (cls.__name__, name, got, want)
+            for extra in list(inspect.signature(fn).parameters.values())[1 + len(want):]:
+                assert extra.default is not inspect.Parameter.empty or extra.kind in (
+                    inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD), (name, extra.name)
+            compared += 1
+    assert compared >= 70, compared
