@@ -91,8 +91,56 @@ class MatrixOperator:
     def arange(self, count: int, start=None, step=None, dtype: int | None = None) -> NDArray:
         start = 0 if start is None else start
         step = 1 if step is None else step
-        dtype = dtypes.int32 if dtype is None else dtype
+        if dtype is None:                                                 # MatrixOperator.php:405-410
+            dtype = self.defaultIntType if isinstance(start, (int, np.integer)) else self.defaultFloatType
         return NDArray(np.arange(count) * step + start, dtype=dtype, service=self._service)
+
+    def isFloatType(self, dtype: int) -> bool:                            # :395-398
+        return dtype in dtypes.FLOAT_TYPES
+
+    def full(self, shape, value, dtype: int | None = None) -> NDArray:    # :342-366: alloc + la->fill
+        if dtype is None:
+            dtype = self.defaultFloatType
+        if not isinstance(value, (bool, int, float, np.integer, np.floating, np.bool_)):
+            raise InvalidArgumentException("value must be scalar")
+        x = NDArray(None, dtype=dtype, shape=shape, service=self._service)
+        return self.la().fill(value, x)
+
+    def zerosLike(self, array: NDArray) -> NDArray:                       # :368-371
+        return self.zeros(array.shape(), array.dtype())
+
+    def fullLike(self, array: NDArray, value: int) -> NDArray:            # :373-376
+        return self.full(array.shape(), value, array.dtype())
+
+    def astype(self, array: NDArray, dtype: int) -> NDArray:              # :378-381
+        return self.la().astype(array, dtype)
+
+    def copy(self, array: NDArray) -> NDArray:                            # :422-427
+        new = NDArray(None, dtype=array.dtype(), shape=array.shape(), service=self._service)
+        return self.la().copy(array, new)
+
+    def transpose(self, X: NDArray, perm=None) -> NDArray:                # :587-593
+        return self.la().transpose(X, perm=perm)
+
+    def dot(self, A: NDArray, B: NDArray):                                # :622-636
+        if A.shape() != B.shape():
+            raise InvalidArgumentException("unmatch shape of dimension")
+        if A.dtype() != B.dtype():
+            raise InvalidArgumentException("unmatch value type")
+        return self.getBlas(A.dtype()).dot(A.size(), A.buffer(), A.offset(), 1, B.buffer(), B.offset(), 1)
+
+    def add(self, X: NDArray, Y: NDArray) -> NDArray:                     # :638-647: copy(Y), then axpy
+        if X.shape() != Y.shape():
+            raise InvalidArgumentException("Unmatch shape of dimension to add: (%s),(%s)" % (
+                ",".join(map(str, X.shape())), ",".join(map(str, Y.shape()))))
+        return self.la().axpy(X, self.copy(Y))
+
+    def scale(self, a, X: NDArray) -> NDArray:                            # :649-661: copy(X), then blas->scal
+        if isinstance(a, bool) or not isinstance(a, (int, float, np.integer, np.floating)):
+            raise InvalidArgumentException("the scalar must be a numeric")
+        C = self.copy(X)
+        self.getBlas(X.dtype()).scal(X.size(), a, C.buffer(), C.offset(), 1)
+        return C
 
     def cross(self, A: NDArray, B: NDArray) -> NDArray:                   # MatrixOperator.php:429-440
         if A.ndim() >= 2 and B.ndim() >= 2:

@@ -186,3 +186,60 @@ def test_integer_arrays_use_the_device_scalar_calls_gpu(cuda_service):
     assert mo.argMax(I, axis=1).toArray() == [2, 0] and mo.min(I, axis=0).toArray() == [1, -5, -6]
     B = mo.array([[True, False, True], [True, True, False]], dtype=dtypes.bool_)
     assert mo.sum(B) == 4
+
+
+# ---- the thin facade methods next to them: one or two driver calls each (src/MatrixOperator.php:342-427, 587-661) ----
+
+def check_facade(svc):
+    mo = MatrixOperator(service=svc)
+    a, b = [1, 2, 3, 4, 5, 6], [3, 4, 5, 6, 7, 8]
+    A1, B1 = mo.array(a, dtype=F32), mo.array(b, dtype=F32)
+    A2, B2 = mo.array([a[:3], a[3:]], dtype=F32), mo.array([b[:3], b[3:]], dtype=F32)
+    AV = mo.array([[0] * 6, a], dtype=F32)[1]
+    BV = mo.array([[0] * 6, b], dtype=F32)[1]
+    assert AV.offset() == 6 and BV.offset() == 6
+    # MatrixOperatorTest.php:454-476, 478-500, 502-521
+    assert mo.dot(A1, B1) == 133 and mo.dot(A2, B2) == 133 and mo.dot(AV, BV) == 133
+    assert mo.add(A1, B1).toArray() == [4, 6, 8, 10, 12, 14]
+    assert mo.add(A2, B2).toArray() == [[4, 6, 8], [10, 12, 14]] and mo.add(AV, BV).toArray() == [4, 6, 8, 10, 12, 14]
+    assert mo.scale(7, A1).toArray() == [7, 14, 21, 28, 35, 42] and mo.scale(7, AV).toArray() == [7, 14, 21, 28, 35, 42]
+    assert mo.scale(7, A2).toArray() == [[7, 14, 21], [28, 35, 42]] and A2.toArray() == [[1, 2, 3], [4, 5, 6]]
+    # :113-135 copy: a new buffer, views copied from their offset
+    c = mo.copy(A2)
+    assert c.toArray() == [[1, 2, 3], [4, 5, 6]] and c.buffer() is not A2.buffer() and c.dtype() == F32
+    c = mo.copy(A2[1])
+    assert c.toArray() == [4, 5, 6] and c.offset() == 0 and len(c.buffer()) == 3
+    # :403-452 transpose
+    assert mo.transpose(A1).toArray() == a and mo.transpose(A2).toArray() == [[1, 4], [2, 5], [3, 6]]
+    t3 = mo.transpose(mo.array(np.arange(1, 25).reshape(4, 3, 2)))
+    assert t3.toArray() == [[[1, 7, 13, 19], [3, 9, 15, 21], [5, 11, 17, 23]], [[2, 8, 14, 20], [4, 10, 16, 22], [6, 12, 18, 24]]]
+    assert mo.transpose(mo.array([[[0] * 3] * 2, [a[:3], a[3:]]], dtype=F32)[1]).toArray() == [[1, 4], [2, 5], [3, 6]]
+    # :55-72 full, :368-376 zerosLike / fullLike, :98-111 arange dtypes, :1536-1550 astype
+    f = mo.full([2, 3], 1.0, dtypes.float64)
+    assert f.dtype() == dtypes.float64 and f.toArray() == [[1.0] * 3] * 2
+    f = mo.full([2, 3], 1, dtypes.int64)
+    assert f.dtype() == dtypes.int64 and f.toArray() == [[1] * 3] * 2
+    f = mo.full([2, 3], True, dtypes.bool_)
+    assert f.dtype() == dtypes.bool_ and f.toArray() == [[True] * 3] * 2
+    assert mo.zerosLike(A2).toArray() == [[0] * 3] * 2 and mo.fullLike(A2, 5).toArray() == [[5] * 3] * 2
+    assert mo.arange(5).dtype() == dtypes.int32 and mo.arange(5, 1.0).dtype() == F32
+    assert mo.arange(5, 1, 2).toArray() == [1, 3, 5, 7, 9] and mo.arange(5, 1.0, 0.5).toArray() == [1.0, 1.5, 2.0, 2.5, 3.0]
+    Y = mo.astype(mo.array([[100, 101, 102], [103, 104, 105]], dtype=dtypes.int32), dtypes.float64)
+    assert Y.dtype() == dtypes.float64 and Y.toArray() == [[100, 101, 102], [103, 104, 105]]
+    with pytest.raises(rb.InvalidArgumentException, match=r"Unmatch shape of dimension to add: \(6\),\(2,3\)"):
+        mo.add(A1, B2)
+    with pytest.raises(rb.InvalidArgumentException, match="unmatch shape of dimension"):
+        mo.dot(A1, B2)
+    with pytest.raises(rb.InvalidArgumentException, match="the scalar must be a numeric"):
+        mo.scale("7", A1)
+    with pytest.raises(rb.InvalidArgumentException, match="value must be scalar"):
+        mo.full([2], [1, 2])
+
+
+def test_facade_host_logic(oracle_service):
+    check_facade(oracle_service)
+
+
+@pytest.mark.gpu
+def test_facade_gpu(cuda_service):
+    check_facade(cuda_service)
