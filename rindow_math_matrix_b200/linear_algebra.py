@@ -35,6 +35,77 @@ class LinearAlgebra:
     def accelerated(self) -> bool:
         return self.service.serviceLevel() >= Service.LV_ADVANCED and type(self.blas).__name__.startswith("Cuda")
 
+    # ---- accessors (LinearAlgebra.php:61-93, 153-162, 183-189) -------------------------------------------------
+    def getBlas(self):
+        return self.blas
+
+    def getMath(self):
+        return self.math
+
+    def getConfig(self) -> str:
+        return self.blas.getConfig()
+
+    def fp64(self) -> bool:
+        return True
+
+    def finish(self) -> None:
+        """Host drivers have nothing to wait for (:91-93); the CUDA service is stream-ordered and host reads
+        synchronise themselves, so the LV_ADVANCED tier keeps the reference's no-op (LinearAlgebraCuda overrides)."""
+
+    def isInt(self, value: NDArray) -> bool:
+        return value.dtype() in dtypes.INT_TYPES
+
+    def isFloat(self, value: NDArray) -> bool:
+        return value.dtype() in dtypes.FLOAT_TYPES
+
+    def isComplexDtype(self, dtype: int) -> bool:                               # :4955-4958
+        return dtype in dtypes.COMPLEX_TYPES
+
+    def scalar(self, array):
+        return array.toArray() if isinstance(array, NDArrayInterface) else array
+
+    def abs(self, value) -> float:                                              # :4970-4980 (real scalars)
+        if isinstance(value, bool) or not isinstance(value, (int, float, np.integer, np.floating)):
+            raise InvalidArgumentException("invalid data type: " + type(value).__name__)
+        return abs(value)
+
+    def expandDims(self, x: NDArray, axis: int) -> NDArray:                     # :191-215
+        shape = x.shape()
+        ndim = len(shape)
+        orgAxis = axis
+        if axis < 0:
+            axis = ndim + axis + 1
+        if axis < 0 or axis > ndim:
+            raise InvalidArgumentException("axis is out of range: %d" % orgAxis)
+        return x.reshape(shape[:axis] + [1] + shape[axis:])
+
+    def squeeze(self, x: NDArray, axis: int | None = None) -> NDArray:          # :217-250
+        shape = x.shape()
+        if axis is None:
+            return x.reshape([n for n in shape if n != 1])
+        ndim = len(shape)
+        orgAxis = axis
+        if axis < 0:
+            axis = ndim + axis
+        if axis < 0 or axis >= ndim:
+            raise InvalidArgumentException("axis is out of range: %d" % orgAxis)
+        if shape[axis] != 1:
+            raise InvalidArgumentException("Can not squeeze dim[%d]" % axis)
+        return x.reshape(shape[:axis] + shape[axis + 1:])
+
+    def isclose(self, a: NDArray, b: NDArray, rtol=None, atol=None, debug=None) -> bool:   # :5439-5464
+        """The reference's comparator (its tests' tolerance convention):
+        max|b - a| < atol + rtol * max|b|, rtol 1e-4, atol 1e-7 -- copy / axpy / scal / iamax on the driver."""
+        rtol = 1e-04 if rtol is None else rtol
+        atol = 1e-07 if atol is None else atol
+        if a.shape() != b.shape():
+            return False
+        diff = self.abs(self.scalar(self.amax(self.axpy(a, self.copy(b), -1))))
+        close = atol + self.abs(self.scalar(self.amax(self.scal(rtol, self.copy(b)))))
+        if debug:
+            print("diff=%14.8e, close=%14.8e" % (diff, close))
+        return bool(diff < close)
+
     def array(self, array, dtype: int | None = None) -> NDArray:
         if isinstance(array, NDArrayInterface):
             return array
@@ -50,8 +121,8 @@ class LinearAlgebra:
         return NDArray(None, dtype=self.defaultFloatType if dtype is None else dtype, shape=shape,
                        service=self.service)
 
-    def toNDArray(self, x: NDArray) -> NDArray:
-        return x
+    def toNDArray(self, ndarray: NDArray) -> NDArray:                           # LinearAlgebra.php:175-181
+        return ndarray
 
     # hooks the device-resident subclass (LinearAlgebraCuda) overrides
     def _host_array(self, array, dtype: int) -> NDArray:
@@ -74,8 +145,8 @@ class LinearAlgebra:
     def ones(self, X: NDArray) -> NDArray:
         return self.fill(1.0, X)
 
-    def zerosLike(self, X: NDArray) -> NDArray:
-        return self.zeros(self.alloc(X.shape(), X.dtype()))
+    def zerosLike(self, array: NDArray) -> NDArray:                             # LinearAlgebra.php:298-301
+        return self.zeros(self.alloc(array.shape(), array.dtype()))
 
     # ---- BLAS level 1 mirrors (LinearAlgebra.php:312-371) ----------------------------------------------
     @staticmethod
@@ -163,7 +234,7 @@ class LinearAlgebra:
 
     # ---- batched C := alpha * AB + beta * C with batch broadcast (LinearAlgebra.php:1000-1110) ----------
     def matmul(self, A: NDArray, B: NDArray, transA=None, transB=None, C: NDArray | None = None,
-               alpha=None, beta=None) -> NDArray:
+               alpha=None, beta=None, conjA=None, conjB=None) -> NDArray:
         transA, transB = bool(transA), bool(transB)
         shapes = "[%s]<=>[%s]" % (",".join(map(str, A.shape())), ",".join(map(str, B.shape())))
         if A.ndim() < 2 or B.ndim() < 2:
@@ -203,8 +274,8 @@ class LinearAlgebra:
                                                      ",".join(map(str, C.shape()))))
         else:
             C = self.zeros(self.alloc(orgShapeC, dtype=A.dtype()))
-        tA = BLAS.Trans if transA else BLAS.NoTrans
-        tB = BLAS.Trans if transB else BLAS.NoTrans
+        tA = self._trans_code(transA, conjA)
+        tB = self._trans_code(transB, conjB)
         offA, offB, offC = A.offset(), B.offset(), C.offset()
         batched = getattr(self.math, "gemmStridedBatched", None) if type(self.math).__name__ == "CudaMath" else None
         for _ in range(dest // base):
@@ -303,8 +374,15 @@ class LinearAlgebra:
         return B
 
     # ---- C := alpha * AB + beta * C   (LinearAlgebra.php:925-995) -----------------------------------
+    @staticmethod
+    def _trans_code(trans, conj) -> int:                                        # complementTrans / transToCode, :125-143
+        trans, conj = bool(trans), bool(conj)                                   # real dtypes: conj defaults to false
+        if trans:
+            return BLAS.ConjTrans if conj else BLAS.Trans
+        return BLAS.ConjNoTrans if conj else BLAS.NoTrans
+
     def gemm(self, A: NDArray, B: NDArray, alpha=None, beta=None, C: NDArray | None = None,
-             transA=None, transB=None) -> NDArray:
+             transA=None, transB=None, conjA=None, conjB=None) -> NDArray:
         transA, transB = bool(transA), bool(transB)
         if A.ndim() != 2 or B.ndim() != 2:
             raise InvalidArgumentException("Dimensions must be 2D-NDArray")
@@ -333,8 +411,7 @@ class LinearAlgebra:
         lda = M if transA else K
         ldb = K if transB else N
         ldc = N
-        self.blas.gemm(BLAS.RowMajor, BLAS.Trans if transA else BLAS.NoTrans,
-                       BLAS.Trans if transB else BLAS.NoTrans, M, N, K, alpha,
+        self.blas.gemm(BLAS.RowMajor, self._trans_code(transA, conjA), self._trans_code(transB, conjB), M, N, K, alpha,
                        A.buffer(), A.offset(), lda, B.buffer(), B.offset(), ldb, beta,
                        C.buffer(), C.offset(), ldc)
         return C

@@ -189,3 +189,77 @@ def test_driver_mirrors_keep_the_reference_parameter_lists():
                     inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD), (name, extra.name)
             compared += 1
     assert compared >= 70, compared
+
+
+def test_linear_algebra_shape_helpers_and_isclose(oracle_service):
+    """expandDims / squeeze (LinearAlgebraTest.php:195-259), the accessors (:61-93, 153-189) and the reference's own
+    comparator isclose (src/LinearAlgebra.php:5439-5464), over the oracle service."""
+    import rindow_math_matrix_b200 as rb
+    from rindow_math_matrix_b200 import LinearAlgebra, NDArray, dtypes
+
+    la = LinearAlgebra(oracle_service)
+    x = la.alloc([2, 3])
+    assert [la.expandDims(x, axis=a).shape() for a in (0, 1, 2, -1, -2, -3)] == \
+        [[1, 2, 3], [2, 1, 3], [2, 3, 1], [2, 3, 1], [2, 1, 3], [1, 2, 3]]
+    s = la.alloc([])
+    assert s.shape() == [] and s.size() == 1 and len(s.buffer()) == 1
+    assert la.expandDims(s, axis=0).shape() == [1] and la.expandDims(s, axis=-1).shape() == [1]
+    with pytest.raises(rb.InvalidArgumentException, match="axis is out of range: -4"):
+        la.expandDims(x, axis=-4)
+    y = la.alloc([1, 2, 1, 3, 1])
+    assert la.squeeze(y).shape() == [2, 3]
+    assert [la.squeeze(y, axis=a).shape() for a in (0, 2, 4, -1, -3, -5)] == \
+        [[2, 1, 3, 1], [1, 2, 3, 1], [1, 2, 1, 3], [1, 2, 1, 3], [1, 2, 3, 1], [2, 1, 3, 1]]
+    with pytest.raises(rb.InvalidArgumentException, match="axis is out of range: -6"):
+        la.squeeze(y, axis=-6)
+    with pytest.raises(rb.InvalidArgumentException, match=r"Can not squeeze dim\[3\]"):
+        la.squeeze(y, axis=3)
+
+    assert la.fp64() and la.getBlas() is la.blas and la.getMath() is la.math
+    i = NDArray([1, 2], dtype=dtypes.int32, service=oracle_service)
+    assert la.isInt(i) and not la.isFloat(i) and la.isFloat(x) and not la.isInt(x)
+    assert la.scalar(3.5) == 3.5 and la.scalar(NDArray([1, 2], service=oracle_service)) == [1, 2]
+    assert la.abs(-2.5) == 2.5 and not la.isComplexDtype(dtypes.float32) and la.isComplexDtype(dtypes.complex64)
+
+    a = NDArray([[1.0, 2.0], [3.0, 1000.0]], service=oracle_service)
+    assert la.isclose(a, la.copy(a))
+    b = la.copy(a)
+    b.buffer()[3] = 1000.05                               # 0.05 < 1e-7 + 1e-4 * 1000.05
+    assert la.isclose(a, b)
+    b.buffer()[0] = 1.2                                   # 0.2 > 0.1
+    assert not la.isclose(a, b)
+    assert la.isclose(a, b, rtol=1e-3)
+    assert not la.isclose(a, NDArray([1.0, 2.0, 3.0, 1000.0], service=oracle_service))       # shapes differ
+    assert a.toArray() == [[1.0, 2.0], [3.0, 1000.0]]     # the operands are left alone
+
+    # conjA / conjB on real dtypes select the Conj* codes, which mean the same as the plain ones (PhpBlas.php:883-886)
+    A = NDArray([[1, 2, 3], [4, 5, 6]], service=oracle_service)
+    B = NDArray([[1, 0], [0, 1], [1, 1]], service=oracle_service)
+    want = la.gemm(A, B).toArray()
+    assert la.gemm(A, B, conjA=True, conjB=True).toArray() == want
+    assert la.gemm(B, A, transA=True, transB=True, conjA=True).toArray() == la.gemm(B, A, transA=True, transB=True).toArray()
+
+
+def test_linear_algebra_mirror_keeps_the_reference_parameter_lists():
+    """Every public LinearAlgebra / MatrixOperator / NDArray method the mirror has takes the reference's parameters,
+    by name and order (named arguments are how the reference's tests call them: `axis:`, `dtype:`, `keepdims:` ...)."""
+    import inspect
+    import json
+    import os
+
+    from rindow_math_matrix_b200 import LinearAlgebra, MatrixOperator, NDArray
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_signatures.json")) as f:
+        ref = json.load(f)
+    compared = 0
+    for cls, parent in ((LinearAlgebra, "LinearAlgebra"), (MatrixOperator, "MatrixOperator"), (NDArray, "NDArrayPhp")):
+        for name, sig in ref[parent]["methods"].items():
+            fn = getattr(cls, name, None)
+            if sig["visibility"] != "public" or name.startswith("__") or fn is None or not callable(fn):
+                continue
+            want = [p["name"].lower() for p in sig["params"]]
+            got = [p.name.rstrip("_").lower() for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+            assert got[:len(want)] == want, "%s.%s: %s vs reference %s" % (cls.__name__, name, got, want)
+            compared += 1
+    assert compared >= 130, compared
