@@ -92,8 +92,8 @@ class LinearAlgebraCuda(LinearAlgebra):
         flags = (CL_MEM_READ_WRITE if flags is None else flags) | CL_MEM_COPY_HOST_PTR
         return NDArrayCuda(self.queue, array.buffer(), array.dtype(), array.shape(), array.offset(), flags, self.service)
 
-    def toNDArray(self, x):
-        return x.toNDArray() if isinstance(x, NDArrayCuda) else x
+    def toNDArray(self, ndarray):                                               # LinearAlgebraCL.php:354-360
+        return ndarray.toNDArray() if isinstance(ndarray, NDArrayCuda) else ndarray
 
     def scalar(self, array):
         if isinstance(array, (NDArray, NDArrayCuda)):
