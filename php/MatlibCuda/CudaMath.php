@@ -123,7 +123,7 @@ class CudaMath extends PhpMath
     public function gatherb(bool $reverse,bool $addMode,int $batches,int $m,int $n,int $k,int $len,int $numClass,
         Buffer $A,int $offsetA,Buffer $X,int $offsetX,Buffer $B,int $offsetB) : void
     {
-        if (!$this->anyOnDevice($A,$X,$B)) {
+        if (!$this->anyOnDevice($A,$X,$B) || $A->dtype()!=$B->dtype()) {
             parent::gatherb($reverse,$addMode,$batches,$m,$n,$k,$len,$numClass,$A,$offsetA,$X,$offsetX,$B,$offsetB); return;
         }
         if ($offsetX+$batches*$n*$k > count($X)) {
@@ -135,9 +135,6 @@ class CudaMath extends PhpMath
         if ($offsetB+$batches*$m*$n*$k*$len > count($B)) {
             throw new InvalidArgumentException('Matrix B specification too large for buffer.');
         }
-        if ($A->dtype()!=$B->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and B');
-        }
         $a = $reverse ? $A->devicePtrRW() : $A->devicePtr();
         $b = $reverse ? $B->devicePtr() : $B->devicePtrRW();
         CudaFFI::check(CudaFFI::lib()->rb200_gatherb($A->abiDtype(),$X->abiDtype(),$reverse?1:0,$addMode?1:0,$batches,$m,$n,$k,
@@ -148,7 +145,7 @@ class CudaMath extends PhpMath
     public function gathernd(bool $reverse,bool $addMode,int $m,int $n,int $k,int $indexDepth,Buffer $paramShape,
         Buffer $A,int $offsetA,Buffer $X,int $offsetX,Buffer $B,int $offsetB) : void
     {
-        if (!$this->anyOnDevice($A,$X,$B)) {
+        if (!$this->anyOnDevice($A,$X,$B) || $A->dtype()!=$B->dtype()) {
             parent::gathernd($reverse,$addMode,$m,$n,$k,$indexDepth,$paramShape,$A,$offsetA,$X,$offsetX,$B,$offsetB); return;
         }
         $shape = CudaFFI::lib()->new("int64_t[$indexDepth]");
@@ -162,9 +159,6 @@ class CudaMath extends PhpMath
         }
         if ($offsetB+$m*$n*$k > count($B)) {
             throw new InvalidArgumentException('Matrix B specification too large for buffer.');
-        }
-        if ($A->dtype()!=$B->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and B');
         }
         $a = $reverse ? $A->devicePtrRW() : $A->devicePtr();
         $b = $reverse ? $B->devicePtr() : $B->devicePtrRW();
@@ -191,7 +185,7 @@ class CudaMath extends PhpMath
         Buffer $B,int $offsetB,int $ldB0,int $ldB1,int $ldB2,int $ldB3,int $ldB4,
         Buffer $C,int $offsetC) : void
     {
-        if (!$this->anyOnDevice($A,$B,$C) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
+        if (!$this->anyOnDevice($A,$B,$C) || $A->dtype()!=$B->dtype() || $A->dtype()!=$C->dtype() || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
             parent::einsum4p1($dim0,$dim1,$dim2,$dim3,$dim4,$A,$offsetA,$ldA0,$ldA1,$ldA2,$ldA3,$ldA4,
                 $B,$offsetB,$ldB0,$ldB1,$ldB2,$ldB3,$ldB4,$C,$offsetC); return;
         }
@@ -221,9 +215,6 @@ class CudaMath extends PhpMath
         if (count($C) < $offsetC+$sizeC) {
             throw new InvalidArgumentException('Matrix specification too large for buffer C.');
         }
-        if ($A->dtype()!=$B->dtype() || $A->dtype()!=$C->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A, B and C');
-        }
         CudaFFI::check(CudaFFI::lib()->rb200_einsum($A->abiDtype(),$depth,$ndimC,$s,$A->devicePtr(),$offsetA,$la,
             $B->devicePtr(),$offsetB,$lb,$C->devicePtrRW(),$offsetC));
     }
@@ -232,23 +223,21 @@ class CudaMath extends PhpMath
     public function topk(int $m,int $n,Buffer $input,int $offsetInput,int $k,bool $sorted,
         Buffer $values,int $offsetValues,Buffer $indices,int $offsetIndices) : void
     {
-        if (!$this->anyOnDevice($input,$values,$indices) || $k*4*12 > 200*1024) {
+        if (!$this->anyOnDevice($input,$values,$indices) || $input->dtype()!=$values->dtype() || $k*4*12 > 200*1024) {
             parent::topk($m,$n,$input,$offsetInput,$k,$sorted,$values,$offsetValues,$indices,$offsetIndices); return;
         }
-        if ($m<1||$n<1||$k<1) {
-            throw new InvalidArgumentException('Argument m / n / k must be greater than 0.');
+        // the reference's own checks, in its order (PhpMath.php:1035-1047)
+        $this->assertShapeParameter("m", $m);
+        $this->assertShapeParameter("n", $n);
+        $this->assertShapeParameter("k", $k);
+        $this->assertMatrixBufferSpec("input", $input, $m,$n, $offsetInput, $n);
+        $this->assertMatrixBufferSpec("values", $values, $m,$k, $offsetValues, $k);
+        $this->assertMatrixBufferSpec("indices", $indices, $m,$k, $offsetIndices, $k);
+        if (!$this->isIntegerDtype($indices->dtype())) {
+            throw new InvalidArgumentException("indices must be integers");
         }
-        if ($offsetInput+$m*$n > count($input)) {
-            throw new InvalidArgumentException('Matrix specification too large for bufferinput.');
-        }
-        if ($offsetValues+$m*$k > count($values)) {
-            throw new InvalidArgumentException('Matrix specification too large for buffervalues.');
-        }
-        if ($offsetIndices+$m*$k > count($indices)) {
-            throw new InvalidArgumentException('Matrix specification too large for bufferindices.');
-        }
-        if ($input->dtype()!=$values->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for input and values');
+        if ($k>$n) {
+            return;
         }
         CudaFFI::check(CudaFFI::lib()->rb200_topk($input->abiDtype(),$indices->abiDtype(),$m,$n,$input->devicePtr(),$offsetInput,
             $k,$sorted?1:0,$values->devicePtrRW(),$offsetValues,$indices->devicePtrRW(),$offsetIndices));
@@ -258,7 +247,7 @@ class CudaMath extends PhpMath
     public function imagecopy(int $height,int $width,int $channels,Buffer $A,int $offsetA,Buffer $B,int $offsetB,
         bool $channelsFirst,int $heightShift,int $widthShift,bool $verticalFlip,bool $horizontalFlip,bool $rgbFlip) : void
     {
-        if (!$this->anyOnDevice($A,$B) || ($rgbFlip && $channels<3)) {
+        if (!$this->anyOnDevice($A,$B) || $A->dtype()!=$B->dtype() || ($rgbFlip && $channels<3)) {
             parent::imagecopy($height,$width,$channels,$A,$offsetA,$B,$offsetB,$channelsFirst,$heightShift,$widthShift,
                 $verticalFlip,$horizontalFlip,$rgbFlip); return;
         }
@@ -268,9 +257,6 @@ class CudaMath extends PhpMath
         if ($width*$height*$channels+$offsetB > count($B)) {
             throw new InvalidArgumentException('Matrix specification too large for bufferB');
         }
-        if ($A->dtype()!=$B->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and B');
-        }
         CudaFFI::check(CudaFFI::lib()->rb200_imagecopy($A->abiDtype(),$height,$width,$channels,$A->devicePtr(),$offsetA,
             $B->devicePtrRW(),$offsetB,$channelsFirst?1:0,$heightShift,$widthShift,$verticalFlip?1:0,$horizontalFlip?1:0,$rgbFlip?1:0));
     }
@@ -278,7 +264,7 @@ class CudaMath extends PhpMath
     /** matrixcopy (PhpMath.php:2778-2809): B = alpha * A or its transpose -- the omatcopy kernel */
     public function matrixcopy(bool $trans,int $m,int $n,float $alpha,Buffer $A,int $offsetA,int $ldA,Buffer $B,int $offsetB,int $ldB) : void
     {
-        if (!$this->anyOnDevice($A,$B) || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
+        if (!$this->anyOnDevice($A,$B) || $A->dtype()!=$B->dtype() || !in_array($A->dtype(),[NDArray::float32,NDArray::float64])) {
             parent::matrixcopy($trans,$m,$n,$alpha,$A,$offsetA,$ldA,$B,$offsetB,$ldB); return;
         }
         $rows = $trans ? $n : $m; $cols = $trans ? $m : $n;
@@ -291,9 +277,6 @@ class CudaMath extends PhpMath
         if ($ldB<$cols || $offsetB+($rows-1)*$ldB+$cols > count($B)) {
             throw new InvalidArgumentException('Matrix specification too large for bufferB.');
         }
-        if ($A->dtype()!=$B->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and B');
-        }
         CudaFFI::check(CudaFFI::lib()->rb200_omatcopy($A->abiDtype(),101,$trans?112:111,$m,$n,$alpha,
             $A->devicePtr(),$offsetA,$ldA,$B->devicePtrRW(),$offsetB,$ldB));
     }
@@ -301,15 +284,12 @@ class CudaMath extends PhpMath
     /** cumsumb (PhpMath.php:1861-1904): running sum along the middle axis of [m,n,k] */
     public function cumsumb(int $m,int $n,int $k,Buffer $A,int $offsetA,bool $exclusive,bool $reverse,Buffer $B,int $offsetB) : void
     {
-        if (!$this->anyOnDevice($A,$B)) { parent::cumsumb($m,$n,$k,$A,$offsetA,$exclusive,$reverse,$B,$offsetB); return; }
+        if (!$this->anyOnDevice($A,$B) || $A->dtype()!=$B->dtype()) { parent::cumsumb($m,$n,$k,$A,$offsetA,$exclusive,$reverse,$B,$offsetB); return; }
         if ($offsetA+$m*$n*$k > count($A)) {
             throw new InvalidArgumentException('Matrix specification too large for bufferA.');
         }
         if ($offsetB+$m*$n*$k > count($B)) {
             throw new InvalidArgumentException('Matrix specification too large for bufferB.');
-        }
-        if ($A->dtype()!=$B->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and B');
         }
         CudaFFI::check(CudaFFI::lib()->rb200_cumsumb($A->abiDtype(),$m,$n,$k,$A->devicePtr(),$offsetA,
             $exclusive?1:0,$reverse?1:0,$B->devicePtrRW(),$offsetB));
@@ -318,7 +298,7 @@ class CudaMath extends PhpMath
     /** cumsum (PhpMath.php:1822-1859): 1-D running sum with increments */
     public function cumsum(int $n,Buffer $X,int $offsetX,int $incX,bool $exclusive,bool $reverse,Buffer $Y,int $offsetY,int $incY) : void
     {
-        if (!$this->anyOnDevice($X,$Y)) { parent::cumsum($n,$X,$offsetX,$incX,$exclusive,$reverse,$Y,$offsetY,$incY); return; }
+        if (!$this->anyOnDevice($X,$Y) || $X->dtype()!=$Y->dtype()) { parent::cumsum($n,$X,$offsetX,$incX,$exclusive,$reverse,$Y,$offsetY,$incY); return; }
         if ($n<1||$incX<1||$incY<1) {
             throw new InvalidArgumentException('Argument n / inc must be greater than 0.');
         }
@@ -328,9 +308,6 @@ class CudaMath extends PhpMath
         if ($offsetY+($n-1)*$incY >= count($Y)) {
             throw new InvalidArgumentException('Vector specification too large for bufferY.');
         }
-        if ($X->dtype()!=$Y->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for X and Y');
-        }
         CudaFFI::check(CudaFFI::lib()->rb200_cumsum($X->abiDtype(),$n,$X->devicePtr(),$offsetX,$incX,
             $exclusive?1:0,$reverse?1:0,$Y->devicePtrRW(),$offsetY,$incY));
     }
@@ -339,7 +316,7 @@ class CudaMath extends PhpMath
     public function searchsorted(int $m,int $n,Buffer $A,int $offsetA,int $ldA,Buffer $X,int $offsetX,int $incX,
         bool $right,Buffer $Y,int $offsetY,int $incY) : void
     {
-        if (!$this->anyOnDevice($A,$X,$Y)) { parent::searchsorted($m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX,$right,$Y,$offsetY,$incY); return; }
+        if (!$this->anyOnDevice($A,$X,$Y) || $A->dtype()!=$X->dtype()) { parent::searchsorted($m,$n,$A,$offsetA,$ldA,$X,$offsetX,$incX,$right,$Y,$offsetY,$incY); return; }
         if ($m<1||$incX<1||$incY<1) {
             throw new InvalidArgumentException('Argument m / inc must be greater than 0.');
         }
@@ -351,9 +328,6 @@ class CudaMath extends PhpMath
         }
         if ($offsetY+($m-1)*$incY >= count($Y)) {
             throw new InvalidArgumentException('Vector specification too large for bufferY.');
-        }
-        if ($A->dtype()!=$X->dtype()) {
-            throw new InvalidArgumentException('Unmatch data type for A and X');
         }
         CudaFFI::check(CudaFFI::lib()->rb200_searchsorted($A->abiDtype(),$Y->abiDtype(),$m,$n,$A->devicePtr(),$offsetA,$ldA,
             $X->devicePtr(),$offsetX,$incX,$right?1:0,$Y->devicePtrRW(),$offsetY,$incY));

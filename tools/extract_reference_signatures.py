@@ -39,9 +39,14 @@ def main():
         for m in re.finditer(r"^\s*(?:final\s+|abstract\s+)?(?:class|interface|trait)\s+(\w+)", code, flags=re.M):
             classes.append((ns.group(1) + "\\" if ns else "") + m.group(1))
     out["__classes__"] = sorted(set(classes))
+    # methods the reference parents get from their traits (protected helpers the shim calls through $this->)
+    out["__traits__"] = {
+        "Utils": sorted(class_signatures((REF / "Drivers/MatlibPHP/Utils.php").read_text(), "Utils")),
+        "ComplexUtils": sorted(class_signatures((REF / "ComplexUtils.php").read_text(), "ComplexUtils")),
+    }
     dst = pathlib.Path(__file__).resolve().parents[1] / "tests" / "golden" / "reference_signatures.json"
     dst.write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
-    print("wrote", dst, {k: len(v["methods"]) for k, v in out.items() if k != "__classes__"}, len(out["__classes__"]), "classes")
+    print("wrote", dst, {k: len(v["methods"]) for k, v in out.items() if not k.startswith("__")}, len(out["__classes__"]), "classes")
 
 
 if __name__ == "__main__":
