@@ -379,3 +379,40 @@ def test_named_arguments_of_constructor_calls_exist():
                     positional += 1
             assert positional <= len(names) or any(p["variadic"] for p in sig["params"]), f"{path.name}:{line}: too many arguments to new {cls}"
     assert checked >= 10, checked
+
+
+# wording that belongs to this driver only (no counterpart in the reference): device-side constraints and diagnostics
+DRIVER_ONLY_MESSAGES = {
+    "Index invalid or out of range", "Illegal Operation",                                   # PhpBuffer raises through PHP itself
+    "dtype is required", "bytes is not a multiple of the value size",
+    "CudaDeviceBuffer has no host mirror: use read()", "CudaDeviceBuffer has no host mirror",
+    "copy source must be a buffer of this driver: ", "librindow_b200 status ",
+    "librindow_b200.so / B200 not available",
+    "LinearAlgebraCuda returns scalars as numbers (return types of LinearAlgebra).",
+    # entry points the reference does not have (gemmStridedBatched, conv2dForward, reduceArgMaxPartial)
+    "gemmStridedBatched needs device buffers", "kernel buffer size is invalid", "bias buffer size is invalid",
+    "reduceArgMaxPartial needs device buffers", "m, n and k must be greater than 0.",
+    "records must be an int64 buffer of two words per output",
+    # bounds the reference leaves to PHP's own offset errors; a kernel must not be launched out of range
+    "Argument m / n must be greater than 0.", "Argument n / inc must be greater than 0.",
+    "Argument m / inc must be greater than 0.", "Matrix specification too large for bufferA.",
+    "Matrix specification too large for bufferB.", "Matrix specification too large for buffer.",
+    "Vector specification too large for bufferX.", "Vector specification too large for bufferY.",
+}
+
+
+def test_exception_wording_is_the_references_or_declared_driver_only():
+    """Callers (and the reference's tests) match on exception messages: a message thrown by the shim is either one the
+    reference throws (fixture: every literal of PhpMath / PhpBlas / Utils / PhpBuffer / NDArrayCL / LinearAlgebra(CL) /
+    MatrixOperator) or listed above as driver-only."""
+    ref = json.loads((ROOT / "tests" / "golden" / "reference_signatures.json").read_text())
+    known = set(ref["__messages__"])
+    seen_ref = 0
+    for path in sorted((ROOT / "php" / "MatlibCuda").glob("*.php")):
+        for m in re.finditer(r"throw\s+new\s+\\?\w+\(\s*(['\"])((?:\\.|(?!\1).)*)\1", path.read_text()):
+            msg = m.group(2)
+            if msg in known:
+                seen_ref += 1
+                continue
+            assert msg in DRIVER_ONLY_MESSAGES, f"{path.name}: '{msg}' is neither the reference's wording nor declared driver-only"
+    assert seen_ref >= 60, seen_ref

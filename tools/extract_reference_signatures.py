@@ -44,6 +44,14 @@ def main():
         "Utils": sorted(class_signatures((REF / "Drivers/MatlibPHP/Utils.php").read_text(), "Utils")),
         "ComplexUtils": sorted(class_signatures((REF / "ComplexUtils.php").read_text(), "ComplexUtils")),
     }
+    # every exception message literal of the driver / array / LA classes (the shim repeats the reference's wording)
+    msgs = set()
+    for rel in ("Drivers/MatlibPHP/PhpMath.php", "Drivers/MatlibPHP/PhpBlas.php", "Drivers/MatlibPHP/Utils.php",
+                "Drivers/MatlibPHP/PhpBuffer.php", "NDArrayCL.php", "NDArrayPhp.php", "LinearAlgebra.php",
+                "LinearAlgebraCL.php", "MatrixOperator.php", "Drivers/AbstractMatlibService.php"):
+        for m in re.finditer(r"throw\s+new\s+\\?\w+\(\s*(['\"])((?:\\.|(?!\1).)*)\1", (REF / rel).read_text()):
+            msgs.add(m.group(2))
+    out["__messages__"] = sorted(msgs)
     dst = pathlib.Path(__file__).resolve().parents[1] / "tests" / "golden" / "reference_signatures.json"
     dst.write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
     print("wrote", dst, {k: len(v["methods"]) for k, v in out.items() if not k.startswith("__")}, len(out["__classes__"]), "classes")
