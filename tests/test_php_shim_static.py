@@ -416,3 +416,64 @@ def test_exception_wording_is_the_references_or_declared_driver_only():
                 continue
             assert msg in DRIVER_ONLY_MESSAGES, f"{path.name}: '{msg}' is neither the reference's wording nor declared driver-only"
     assert seen_ref >= 60, seen_ref
+
+
+# ---- the PHP calls pass the same arguments, in the same order, as the ctypes mirror (which the GPU suite runs) --------
+
+def _norm_php_arg(a: str) -> str:
+    a = a.replace(" ", "")
+    a = re.sub(r"\\?FFI::addr\((.*)\)$", r"&\1", a)
+    a = re.sub(r"(?:\$ffi|CudaFFI::lib\(\))->cast\('',(.*)\)$", r"\1", a)
+    a = re.sub(r"^\(?(.*?)\)?\?1:0$", r"\1", a)
+    a = a.replace("$this->", "self.").replace("$", "")
+    a = a.replace("->abiDtype()", ".dtype").replace("->devicePtrRW()", ".ptr").replace("->devicePtr()", ".ptr").replace("::", ".")
+    return a.lower().replace("_", "")
+
+
+def _norm_py_arg(a: str) -> str:
+    a = " ".join(a.split())
+    for pat, rep in ((r"^1 if (.*) else 0$", r"\1"), (r"^(?:float|int|bool)\((.*)\)$", r"\1"),
+                     (r"^ctypes\.byref\((.*)\)$", r"&\1"), (r"^_cuda\(\"\w+\", (\w+)\)\.dtype\(\)$", r"\1.dtype"),
+                     (r"^self\._float_dtype\((\w+), .*\)$", r"\1.dtype")):
+        a = re.sub(pat, rep, a)
+    a = a.replace(" ", "").replace(".dtype()", ".dtype").replace(".device_ptr_rw()", ".ptr").replace(".device_ptr()", ".ptr")
+    return a.lower().replace("_", "")
+
+
+# local variable names that differ between the two hosts for the same thing
+_LOCAL_ALIASES = {"a": "aptr", "b": "bptr", "c": "cptr", "y": "yptr", "im": "imptr", "co": "coptr", "x.dtype": "dt"}
+
+
+def test_php_ffi_calls_pass_what_the_ctypes_mirror_passes():
+    """The ctypes host (`rindow_math_matrix_b200/cuda_blas.py`, `cuda_math.py`) is what the GPU suite executes; the PHP
+    host cannot run here.  For the compute entry points the two must hand the SAME expressions to the SAME positions --
+    the one mistake neither the prototype check nor PHP's type system would see is two swapped integers."""
+    php, py = {}, {}
+    for path in sorted((ROOT / "php" / "MatlibCuda").glob("*.php")):
+        if path.name in ("CudaFFI.php", "CudaBuffer.php", "CudaDeviceBuffer.php", "CudaContext.php", "CudaEventList.php",
+                         "CudaQueue.php"):
+            continue                                   # buffer / event plumbing is structured differently per host
+        code = strip_php(path.read_text())
+        for m in re.finditer(r"->\s*(rb200_\w+)\s*\(", code):
+            php.setdefault(m.group(1), []).append([_norm_php_arg(x) for x in _call_args(code, m.end() - 1)])
+    for path in sorted((ROOT / "rindow_math_matrix_b200").glob("cuda_*.py")):
+        src = path.read_text()
+        for m in re.finditer(r"\.(rb200_\w+)\s*\(", src):
+            py.setdefault(m.group(1), []).append([_norm_py_arg(x) for x in _call_args(src, m.end() - 1)])
+    must_match = ("rb200_sgemm", "rb200_dgemm", "rb200_add", "rb200_multiply", "rb200_reduce_sum", "rb200_reduce_max",
+                  "rb200_reduce_argmax", "rb200_softmax", "rb200_im2col2d", "rb200_im2col3d", "rb200_gemv", "rb200_axpy",
+                  "rb200_copy", "rb200_scal", "rb200_swap", "rb200_dot",      # asum / nrm2 / iamax / iamin: `->$fn(` in PHP
+                  "rb200_sum", "rb200_imax", "rb200_imin", "rb200_topk", "rb200_cumsum", "rb200_cumsumb",
+                  "rb200_searchsorted", "rb200_bandpart", "rb200_masking", "rb200_repeat", "rb200_imagecopy",
+                  "rb200_onehot", "rb200_reduce_argmax_partial", "rb200_slice", "rb200_gatherb", "rb200_einsum")
+    matched = 0
+    for sym in must_match:
+        assert sym in php and sym in py, sym
+        for a in php[sym]:
+            ok = False
+            for b in py[sym]:
+                if len(a) == len(b) and all(x == y or _LOCAL_ALIASES.get(x) == y for x, y in zip(a, b)):
+                    ok = True
+            assert ok, "%s: PHP passes %s, the ctypes mirror passes %s" % (sym, a, py[sym])
+            matched += 1
+    assert matched >= len(must_match)
