@@ -477,3 +477,21 @@ def test_php_ffi_calls_pass_what_the_ctypes_mirror_passes():
             assert ok, "%s: PHP passes %s, the ctypes mirror passes %s" % (sym, a, py[sym])
             matched += 1
     assert matched >= len(must_match)
+
+
+def test_php_dtype_table_matches_the_header_enum_and_the_mirror():
+    """CudaBuffer::table() is the ONE place polite-math dtype constants meet ABI dtype codes: code and element size per
+    dtype must equal include/rindow_b200.h and rindow_math_matrix_b200/dtypes.py."""
+    from rindow_math_matrix_b200 import dtypes
+    enum = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define\s+RB200_([A-Z0-9]+)\s+(\d+)\b", HEADER)}
+    src = (ROOT / "php" / "MatlibCuda" / "CudaBuffer.php").read_text()
+    rows = re.findall(r"NDArray::(\w+)\s*=>\s*\[(\d+),\s*(\d+),\s*'(\w+)'\]", src)
+    assert len(rows) == 13
+    ctype_bytes = {"uint8_t": 1, "int8_t": 1, "int16_t": 2, "uint16_t": 2, "int32_t": 4, "uint32_t": 4, "int64_t": 8,
+                   "uint64_t": 8, "float": 4, "double": 8}
+    for name, code, size, ctype in rows:
+        code, size = int(code), int(size)
+        assert enum[name] == code, name
+        py = getattr(dtypes, "bool_" if name == "bool" else name)
+        assert py == code and dtypes.VALUE_SIZE[py] == size, name
+        assert ctype_bytes[ctype] * (2 if name.startswith("complex") else 1) == size, name
